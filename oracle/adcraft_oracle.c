@@ -1,0 +1,619 @@
+/* TEST INFRASTRUCTURE -- CPU oracle for the BiddingSimulation.step hot path.
+ * See adcraft_oracle.h for scope and parity status (PINNED against the reference
+ * Python through tests/golden/ and tests/test_oracle_vs_reference.py).
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off; contraction must stay off so
+ * that the float32/float64 sampler arithmetic below is bit-identical to the CUDA
+ * implementation, which is compiled with --fmad=false and uses explicit fma).
+ *
+ * Layout of this file
+ *   1. Philox4x32-10 + the deterministic samplers ("tape function")
+ *   2. restatement of the src/lib.rs helpers on the path
+ *   3. the env step: volume split, lane loop, shared budget, early break
+ *   4. drift, batched free-running driver (OpenMP) used as the CPU baseline
+ */
+#include "adcraft_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------- */
+/* 1. Philox4x32-10 (Salmon et al., SC'11; Random123 KATs in tests)           */
+/* ------------------------------------------------------------------------- */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* counter layout: c0 = index, c1 = step, c2 = stream<<28 | agent<<20 | kw, c3 = env */
+enum { ST_AUCTION = 0, ST_UNIT = 1, ST_REVENUE = 2, ST_PHANTOM = 3 };
+
+static void draw4(uint64_t seed, uint32_t env, uint32_t step, uint32_t agent, uint32_t kw,
+                  uint32_t stream, uint32_t idx, uint32_t out[4])
+{
+    uint32_t ctr[4] = { idx, step, (stream << 28) | (agent << 20) | kw, env };
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    orc_philox4x32_10(ctr, key, out);
+}
+
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+/* ln(m) for m in [sqrt(1/2), sqrt(2)] via f = m-1; Cephes logf coefficients, every
+ * multiply-add is an explicit fmaf so CPU and GPU round identically. */
+static inline float ln_mant(float f)
+{
+    float z = f * f;
+    float y = 7.0376836292E-2f;
+    y = fmaf(y, f, -1.1514610310E-1f);
+    y = fmaf(y, f, 1.1676998740E-1f);
+    y = fmaf(y, f, -1.2420140846E-1f);
+    y = fmaf(y, f, 1.4249322787E-1f);
+    y = fmaf(y, f, -1.6668057665E-1f);
+    y = fmaf(y, f, 2.0000714765E-1f);
+    y = fmaf(y, f, -2.4999993993E-1f);
+    y = fmaf(y, f, 3.3333331174E-1f);
+    y = (y * f) * z;
+    y = fmaf(-0.5f, z, y);
+    return f + y;
+}
+
+/* split a positive normal float into exponent k and mantissa m in [sqrt(1/2), sqrt(2)) */
+static inline float split_mant(float a, int32_t *k)
+{
+    uint32_t b = f2u(a);
+    int32_t e = (int32_t)(b >> 23) - 127;
+    float m = u2f((b & 0x007FFFFFu) | 0x3F800000u);
+    if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
+    *k = e;
+    return m;
+}
+
+#define ORC_LN2F 0.693147182f
+
+float orc_lnf(float a)
+{
+    int32_t k;
+    float m = split_mant(a, &k);
+    float r = ln_mant(m - 1.0f);
+    return fmaf((float)k, ORC_LN2F, r);
+}
+
+/* -ln((w31 + 0.5) / 2^31) for a 31-bit uniform integer: an Exp(1) variate. */
+float orc_neglog_u31(uint32_t w31)
+{
+    float a = (float)(2u * w31 + 1u); /* uint32 -> float, round-to-nearest-even */
+    int32_t k;
+    float m = split_mant(a, &k);
+    float r = ln_mant(m - 1.0f);
+    return fmaf((float)(32 - k), ORC_LN2F, -r);
+}
+
+/* Standard normal from one 32-bit word: sign bit + 31-bit tail probability, inverse
+ * CDF by M. Giles' single-precision erfinv polynomial evaluated on the tail variable. */
+float orc_znorm(uint32_t w)
+{
+    uint32_t w31 = w & 0x7FFFFFFFu;
+    float t = (float)(2u * w31 + 1u) * 2.3283064365386963e-10f; /* (w31+.5)/2^31 in (0,1] */
+    float a = t * (2.0f - t);                                   /* (1-x)(1+x), x = 1-t     */
+    float wl = -orc_lnf(a);
+    float p;
+    if (wl < 5.0f) {
+        float v = wl - 2.5f;
+        p = 2.81022636e-08f;
+        p = fmaf(p, v, 3.43273939e-07f);
+        p = fmaf(p, v, -3.5233877e-06f);
+        p = fmaf(p, v, -4.39150654e-06f);
+        p = fmaf(p, v, 0.00021858087f);
+        p = fmaf(p, v, -0.00125372503f);
+        p = fmaf(p, v, -0.00417768164f);
+        p = fmaf(p, v, 0.246640727f);
+        p = fmaf(p, v, 1.50140941f);
+    } else {
+        float v = sqrtf(wl) - 3.0f;
+        p = -0.000200214257f;
+        p = fmaf(p, v, 0.000100950558f);
+        p = fmaf(p, v, 0.00134934322f);
+        p = fmaf(p, v, -0.00367342844f);
+        p = fmaf(p, v, 0.00573950773f);
+        p = fmaf(p, v, -0.0076224613f);
+        p = fmaf(p, v, 0.00943887047f);
+        p = fmaf(p, v, 1.00167406f);
+        p = fmaf(p, v, 2.83297682f);
+    }
+    float z = (p * (1.0f - t)) * 1.41421354f;
+    return (w >> 31) ? -z : z;
+}
+
+/* exp(x) in float64 with explicit fma (used once per unit by the explicit keyword's
+ * thresholded sigmoid; libm exp is not bit-reproducible across CPU/GPU). */
+double orc_exp(double x)
+{
+    if (x != x) return x;
+    if (x > 709.0) return INFINITY;
+    if (x < -700.0) return 0.0;
+    double kf = rint(x * 1.4426950408889634);
+    double r = fma(-kf, 6.93147180369123816490e-01, x);
+    r = fma(-kf, 1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0; /* 1/13! */
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    int64_t k = (int64_t)kf;
+    uint64_t bits = (uint64_t)(k + 1023) << 52; /* 2^k, k in [-1010, 1023] */
+    double s; memcpy(&s, &bits, 8);
+    return p * s;
+}
+
+/* Competitor bid of the single-competitor ImplicitKeyword, in cents:
+ * around(max(|Laplace(loc,scale)|, 0), 2)  (synthetic_kw_helpers.py:104-113). */
+int32_t orc_laplace_cents(uint32_t w0, float loc, float scale)
+{
+    float e = orc_neglog_u31(w0 & 0x7FFFFFFFu);
+    float s = (w0 >> 31) ? -scale : scale;
+    float x = fmaf(s, e, loc);
+    return (int32_t)lrintf(fabsf(x) * 100.0f);
+}
+
+/* around(max(N(mean,std), 0.01), 2) in cents (synthetic_kw_helpers.py:66-70). */
+int32_t orc_revenue_cents(uint32_t w, float mean, float std)
+{
+    float v = fmaf(std, orc_znorm(w), mean);
+    int32_t c = (int32_t)lrintf(v * 100.0f);
+    return c < 1 ? 1 : c;
+}
+
+/* round_half_away(max(N(mean,std), 0))  (src/lib.rs:314-325). */
+int64_t orc_volume(uint32_t w, double mean, double std)
+{
+    double v = mean + std * (double)orc_znorm(w);
+    if (!(v > 0.0)) v = 0.0;
+    return (int64_t)round(v);
+}
+
+/* ------------------------------------------------------------------------- */
+/* 2. src/lib.rs helpers on the path                                           */
+/* ------------------------------------------------------------------------- */
+static inline double clampd(double x, double lo, double hi)
+{   /* num::clamp: if x < lo {lo} else if x > hi {hi} else x */
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
+/* src/lib.rs:92-105 + :290-300, exp replaced by orc_exp (<= 2 ulp from libm). */
+double orc_threshold_sigmoid(double bid, double thresh_in, double intercept, double slope)
+{
+    double halver = 2.0 + 1e-10;
+    double thresh = clampd(halver * thresh_in, 0.0, 1.0) / halver;
+    double r = 1.0 / (1.0 + orc_exp(-slope * (bid - intercept)));
+    return clampd((1.0 + 2.0 * thresh) * r - thresh, 0.0, 1.0);
+}
+
+/* P(u <= p) for u = w * 2^-32: w <= floor(p * 2^32), saturated to 2^32-1. */
+uint32_t orc_prob_threshold(double p)
+{
+    if (!(p > 0.0)) return 0u; /* u <= 0 only for w == 0 */
+    double t = floor(p * 4294967296.0);
+    if (t >= 4294967295.0) return 0xFFFFFFFFu;
+    return (uint32_t)t;
+}
+
+/* src/lib.rs:53-67 cost_create (constant 4.4) for one impression. */
+double orc_explicit_cost(uint32_t w3, double bid)
+{
+    double xs = sqrt(bid);
+    double sd = 1e-10 + xs / 6.0;
+    double c = (xs / 4.0 + 4.4 / 2.0) + sd * (double)orc_znorm(w3);
+    return clampd(c, 0.0, 4.4);
+}
+
+/* ndarray::sum on a contiguous slice = numeric_util::unrolled_fold (src/lib.rs:107-111) */
+double orc_sum_array(const double *x, int64_t n)
+{
+    double p[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    int64_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        for (int j = 0; j < 8; ++j) p[j] += x[i + j];
+    double s = 0.0;
+    s += p[0] + p[4];
+    s += p[1] + p[5];
+    s += p[2] + p[6];
+    s += p[3] + p[7];
+    for (; i < n; ++i) s += x[i];
+    return s;
+}
+
+int32_t orc_bid_to_cents(double bid)
+{   /* round(np.maximum(bid, 0.01), 2): rint(x*100)/100  (gymnasium_kw_env.py:215) */
+    double b = bid > 0.01 ? bid : 0.01;
+    if (!(b == b)) b = 0.01;
+    double c = rint(b * 100.0);
+    if (c > 2.0e9) c = 2.0e9;
+    return (int32_t)c;
+}
+
+/* ------------------------------------------------------------------------- */
+/* 3. one env step                                                             */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    int mode; /* 0 tape, 1 philox */
+    const orc_tape *tape;
+    uint64_t seed; uint32_t env, step, agent;
+    orc_record *rec;
+} draw_src;
+
+typedef struct { /* per-keyword running cursors for one env step */
+    int64_t auction; /* auctions evaluated so far (day-level ordinal) */
+    int64_t n_click, n_conv, n_rev, n_cost;
+} kw_cursor;
+
+#define MAX_LANE_STACK 4096
+
+static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, double *remaining,
+                    int alias, int64_t n, draw_src *src, kw_cursor *cur, orc_result *out,
+                    uint32_t thr_click, uint32_t thr_conv, uint32_t thr_impr,
+                    double *cost_seq, double *rev_seq)
+{
+    /* One call of simulate_epoch_of_bidding (bidding_simulation.py:44-120). */
+    const double bid = (double)bid_cents / 100.0;
+    const int explicit_kw = kw->kind == ORC_EXPLICIT;
+    double stack_cost[256]; uint8_t stack_clicked[256]; uint32_t stack_aw[256];
+    int64_t cap = n > 0 ? n : 1;
+    double *slot_cost = stack_cost; uint8_t *clicked = stack_clicked; uint32_t *slot_w2 = stack_aw;
+    if (cap > 256) {
+        slot_cost = (double *)malloc(sizeof(double) * cap);
+        clicked = (uint8_t *)malloc(cap);
+        slot_w2 = (uint32_t *)malloc(sizeof(uint32_t) * cap);
+    }
+    int64_t slots = 0, I = 0;
+    orc_record *rec = src->rec;
+    const orc_tape *tp = src->tape;
+    uint32_t w[4];
+
+    /* --- keyword.auction (classes:520-538 explicit / :623-646 + helpers:116-180) --- */
+    if (!explicit_kw) {
+        for (int64_t a = 0; a < n; ++a) {
+            int64_t j = cur->auction + a;
+            int32_t c;
+            uint32_t w1 = 0, w2 = 0;
+            if (src->mode == 0) {
+                c = tp->comp_cents[tp->comp_off[k] + j];
+            } else {
+                draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_AUCTION, (uint32_t)j, w);
+                c = orc_laplace_cents(w[0], (float)kw->p1[k], (float)kw->p2[k]);
+                w1 = w[1]; w2 = w[2];
+                if (rec && j < rec->cap_per_kw) { rec->comp_cents[(int64_t)k * rec->cap_per_kw + j] = c; rec->n_comp[k] = (int32_t)(j + 1); }
+            }
+            /* nth_price_auction(n=2, num_winners=1) with one competitor: win iff bid > c
+             * (strict; searchsorted-left index must exceed n), cost = c. */
+            if (bid_cents > c) {
+                slot_cost[slots] = (double)c / 100.0;
+                clicked[slots] = 0;
+                /* philox mode: click/conv words travel with the auction */
+                slot_w2[slots] = w2;
+                if (src->mode == 1) clicked[slots] = (uint8_t)(w1 <= thr_click) | 0x80; /* bit7: decided */
+                if (src->mode == 1 && rec) {
+                    int64_t pos = (int64_t)k * rec->cap_per_kw + cur->n_click + slots;
+                    if (cur->n_click + slots < rec->cap_per_kw) rec->u_click[pos] = (double)w1 * 2.3283064365386963e-10;
+                }
+                ++slots; ++I;
+            }
+        }
+    } else {
+        if (src->mode == 0) {
+            I = tp->impr[k * ORC_SUBSTEPS + t];
+            if (I > cap) { /* tape inconsistent with volume */
+                if (cap > 256) { free(slot_cost); free(clicked); free(slot_w2); }
+                return -2;
+            }
+            for (int64_t i = 0; i < I; ++i) {
+                slot_cost[i] = tp->cost[tp->cost_off[k] + cur->n_cost + i];
+                clicked[i] = 0; slot_w2[i] = 0;
+            }
+            slots = I;
+        } else {
+            for (int64_t a = 0; a < n; ++a) {
+                int64_t j = cur->auction + a;
+                draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_AUCTION, (uint32_t)j, w);
+                if (w[0] <= thr_impr) { /* Bernoulli(p): their sum is Binomial(n,p) */
+                    slot_cost[slots] = orc_explicit_cost(w[3], bid);
+                    clicked[slots] = (uint8_t)(w[1] <= thr_click) | 0x80;
+                    slot_w2[slots] = w[2];
+                    if (rec) {
+                        if (cur->n_cost + slots < rec->cap_per_kw) rec->cost[(int64_t)k * rec->cap_per_kw + cur->n_cost + slots] = slot_cost[slots];
+                        if (cur->n_click + slots < rec->cap_per_kw) rec->u_click[(int64_t)k * rec->cap_per_kw + cur->n_click + slots] = (double)w[1] * 2.3283064365386963e-10;
+                    }
+                    ++slots; ++I;
+                }
+            }
+            if (rec) rec->impr[k * ORC_SUBSTEPS + t] = (int32_t)I;
+        }
+        cur->n_cost += I;
+        if (I < 1) { /* phantom zero-cost slot (classes:514-515) */
+            slot_cost[0] = 0.0; clicked[0] = 0; slot_w2[0] = 0; slots = 1;
+            if (src->mode == 1) {
+                draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_PHANTOM, (uint32_t)t, w);
+                clicked[0] = (uint8_t)(w[1] <= thr_click) | 0x80;
+                slot_w2[0] = w[2];
+                if (rec && cur->n_click < rec->cap_per_kw) rec->u_click[(int64_t)k * rec->cap_per_kw + cur->n_click] = (double)w[1] * 2.3283064365386963e-10;
+            }
+        }
+    }
+    cur->auction += n;
+
+    /* --- sample_buyside_click: one flip per slot, all drawn (bsim:94-96, helpers:73-77) --- */
+    if (src->mode == 0) {
+        const double ctr = kw->ctr[k];
+        for (int64_t i = 0; i < slots; ++i)
+            clicked[i] = tp->u_click[tp->click_off[k] + cur->n_click + i] <= ctr;
+    } else {
+        for (int64_t i = 0; i < slots; ++i) clicked[i] &= 1;
+        if (rec) rec->n_click[k] = (int32_t)((cur->n_click + slots) < rec->cap_per_kw ? (cur->n_click + slots) : rec->cap_per_kw);
+    }
+    cur->n_click += slots;
+
+    /* --- serial budget walk (bsim:97-104) --- */
+    double b = *remaining;
+    double lane_cost_sum = 0.0; /* rust.sum_list(costs): sequential */
+    int64_t B = 0, S = 0;
+    double lane_rev[256]; double *rev = lane_rev;
+    uint32_t acc_w2[256]; uint32_t *aw2 = acc_w2;
+    if (slots > 256) { aw2 = (uint32_t *)malloc(sizeof(uint32_t) * slots); rev = (double *)malloc(sizeof(double) * slots); }
+    for (int64_t i = 0; i < slots; ++i) {
+        if (clicked[i]) {
+            if (b >= slot_cost[i]) {
+                aw2[B] = slot_w2[i];
+                ++B;
+                lane_cost_sum += slot_cost[i];
+                *cost_seq += slot_cost[i]; /* whole-day sequential sum (env:235) */
+                if (!explicit_kw) out->cost_cents[k] += (int64_t)llrint(slot_cost[i] * 100.0);
+                b -= slot_cost[i];
+            } else {
+                break;
+            }
+        }
+    }
+
+    /* --- conversions (bsim:106-109) and revenues (bsim:111, helpers:66-70) --- */
+    for (int64_t i = 0; i < B; ++i) {
+        int conv;
+        if (src->mode == 0) {
+            conv = tp->u_conv[tp->conv_off[k] + cur->n_conv + i] <= kw->cvr[k];
+        } else {
+            conv = aw2[i] <= thr_conv;
+            if (rec && cur->n_conv + i < rec->cap_per_kw) rec->u_conv[(int64_t)k * rec->cap_per_kw + cur->n_conv + i] = (double)aw2[i] * 2.3283064365386963e-10;
+        }
+        S += conv;
+    }
+    cur->n_conv += B;
+    if (src->mode == 1 && rec) rec->n_conv[k] = (int32_t)(cur->n_conv < rec->cap_per_kw ? cur->n_conv : rec->cap_per_kw);
+    for (int64_t i = 0; i < S; ++i) {
+        int32_t rc;
+        int64_t r = cur->n_rev + i;
+        if (src->mode == 0) {
+            rc = tp->rev_cents[tp->rev_off[k] + r];
+        } else {
+            if ((r & 3) == 0 || i == 0)
+                draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_REVENUE, (uint32_t)(r >> 2), w);
+            rc = orc_revenue_cents(w[r & 3], (float)kw->rev_mean[k], (float)kw->rev_std[k]);
+            if (rec && r < rec->cap_per_kw) { rec->rev_cents[(int64_t)k * rec->cap_per_kw + r] = rc; rec->n_rev[k] = (int32_t)(r + 1); }
+        }
+        rev[i] = (double)rc / 100.0;
+        *rev_seq += rev[i]; /* env:240 sequential whole-day sum */
+        out->revenue_cents[k] += rc;
+    }
+    cur->n_rev += S;
+
+    /* profit = rust.sum_array(revenues) - rust.sum_list(costs)  (bsim:117) */
+    double lane_profit = orc_sum_array(rev, S) - lane_cost_sum;
+
+    /* combine_outcomes addable fields (bsim:127,138-139) */
+    out->impressions[k] += (int32_t)I;
+    out->clicks[k] += (int32_t)B;
+    out->conversions[k] += (int32_t)S;
+    out->profit[k] += lane_profit;
+    if (out->lane_I) {
+        out->lane_I[t * kw->K + k] = (int32_t)I;
+        out->lane_B[t * kw->K + k] = (int32_t)B;
+        out->lane_S[t * kw->K + k] = (int32_t)S;
+    }
+    /* Array-valued budgets (what the action space's Box(shape=(1,)) yields) are decremented
+     * IN PLACE by `budget -= cost` (bsim:102) because `budget` aliases the caller's
+     * `remaining_budget` ndarray; the caller then subtracts the lane's costs again (bsim:225).
+     * Scalar budgets (the notebooks' `"budget": 100000`) are immutable, so only bsim:225 acts. */
+    if (alias) *remaining = b;
+    *remaining -= lane_cost_sum; /* bsim:225 */
+
+    if (cap > 256) { free(slot_cost); free(clicked); free(slot_w2); }
+    if (slots > 256) { free(aw2); free(rev); }
+    return 0;
+}
+
+static int step_common(const orc_keywords *kw, const int32_t *bid_cents, double budget,
+                       int alias, draw_src *src, orc_result *out)
+{
+    const int K = kw->K;
+    int64_t *vol = (int64_t *)malloc(sizeof(int64_t) * K);
+    kw_cursor *cur = (kw_cursor *)calloc(K, sizeof(kw_cursor));
+    uint32_t *thr = (uint32_t *)malloc(sizeof(uint32_t) * 3 * K);
+    double *cost_seq = (double *)calloc(K, sizeof(double));
+    double *rev_seq = (double *)calloc(K, sizeof(double));
+    uint32_t w[4];
+    int rc = 0;
+
+    /* uniform_get_auctions_per_timestep (bsim:151-167): one volume draw per keyword */
+    for (int k = 0; k < K; ++k) {
+        if (src->mode == 0) {
+            vol[k] = src->tape->volume[k];
+        } else {
+            draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_UNIT, 0u, w);
+            vol[k] = orc_volume(w[0], kw->vol_mean[k], kw->vol_std[k]);
+            if (src->rec) {
+                src->rec->volume[k] = (int32_t)vol[k];
+                src->rec->n_comp[k] = src->rec->n_click[k] = src->rec->n_conv[k] = 0;
+                src->rec->n_rev[k] = src->rec->n_cost[k] = 0;
+            }
+        }
+        thr[3 * k + 0] = orc_prob_threshold(kw->ctr[k]);
+        thr[3 * k + 1] = orc_prob_threshold(kw->cvr[k]);
+        thr[3 * k + 2] = 0;
+        if (kw->kind == ORC_EXPLICIT) {
+            double bid = (double)bid_cents[k] / 100.0;
+            double p = orc_threshold_sigmoid(bid, kw->impression_thresh, kw->p1[k], kw->p2[k]);
+            thr[3 * k + 2] = orc_prob_threshold(p);
+        }
+        out->impressions[k] = out->clicks[k] = out->conversions[k] = 0;
+        out->cost[k] = out->revenue[k] = out->profit[k] = 0.0;
+        out->cost_cents[k] = out->revenue_cents[k] = 0;
+    }
+    if (out->lane_I) {
+        memset(out->lane_I, 0, sizeof(int32_t) * ORC_SUBSTEPS * K);
+        memset(out->lane_B, 0, sizeof(int32_t) * ORC_SUBSTEPS * K);
+        memset(out->lane_S, 0, sizeof(int32_t) * ORC_SUBSTEPS * K);
+    }
+
+    double remaining = budget; /* bsim:214 */
+    int lanes = 0, stop = 0;
+    for (int t = 0; t < ORC_SUBSTEPS && !stop; ++t) {
+        for (int k = 0; k < K; ++k) {
+            int64_t q = vol[k] / ORC_SUBSTEPS;
+            int64_t n = (t == 0) ? vol[k] - (ORC_SUBSTEPS - 1) * q : q;
+            rc = lane_run(kw, k, t, bid_cents[k], &remaining, alias, n, src, &cur[k], out,
+                          thr[3 * k], thr[3 * k + 1], thr[3 * k + 2], &cost_seq[k], &rev_seq[k]);
+            if (rc) { stop = 1; break; }
+            ++lanes;
+            if (remaining <= 0) { stop = 1; break; } /* bsim:230-233 */
+        }
+    }
+    for (int k = 0; k < K; ++k) {
+        out->cost[k] = cost_seq[k];
+        out->revenue[k] = rev_seq[k];
+        if (src->mode == 1 && src->rec) src->rec->n_cost[k] = (int32_t)cur[k].n_cost;
+    }
+    /* profits = rust.sum_list([kw["profit"] ...])  (env:222) */
+    double reward = 0.0;
+    for (int k = 0; k < K; ++k) reward += out->profit[k];
+    out->reward = reward;
+    out->remaining_budget = remaining;
+    out->lanes_run = lanes;
+    free(vol); free(cur); free(thr); free(cost_seq); free(rev_seq);
+    return rc;
+}
+
+int orc_step_replay(const orc_keywords *kw, const int32_t *bid_cents, double budget,
+                    int budget_alias, const orc_tape *tape, orc_result *out)
+{
+    draw_src s; memset(&s, 0, sizeof s);
+    s.mode = 0; s.tape = tape;
+    return step_common(kw, bid_cents, budget, budget_alias, &s, out);
+}
+
+int orc_step_philox(const orc_keywords *kw, const int32_t *bid_cents, double budget,
+                    int budget_alias, uint64_t seed, uint32_t env_id, uint32_t step,
+                    uint32_t agent, orc_result *out, orc_record *rec)
+{
+    draw_src s; memset(&s, 0, sizeof s);
+    s.mode = 1; s.seed = seed; s.env = env_id; s.step = step; s.agent = agent; s.rec = rec;
+    return step_common(kw, bid_cents, budget, budget_alias, &s, out);
+}
+
+/* ------------------------------------------------------------------------- */
+/* 4. drift + batched driver                                                   */
+/* ------------------------------------------------------------------------- */
+void orc_drift_apply(int32_t K, const uint8_t *mask, int32_t num_updates, const double *coeff,
+                     const double *init_std, double *vol_mean, double *ctr, double *cvr)
+{   /* gymnasium_kw_env.py:132-158; zip() stops at the shortest iterable = num_updates */
+    int32_t lim = num_updates < K ? num_updates : K;
+    for (int32_t k = 0; k < lim; ++k) {
+        if (!mask[k]) continue;
+        double v = vol_mean[k] + coeff[0 * K + k] * init_std[k];
+        vol_mean[k] = v > 0.0 ? v : 0.0;                 /* nonnegify */
+        ctr[k] = clampd(ctr[k] * (1.0 + coeff[1 * K + k]), 0.0, 1.0); /* probify */
+        cvr[k] = clampd(cvr[k] * (1.0 + coeff[2 * K + k]), 0.0, 1.0);
+    }
+}
+
+void orc_drift_philox(int32_t K, uint64_t seed, uint32_t env_id, uint32_t step,
+                      const double mag[3], double *coeff)
+{
+    uint32_t w[4];
+    for (int32_t k = 0; k < K; ++k) {
+        draw4(seed, env_id, step, 0u, (uint32_t)k, ST_UNIT, 0u, w);
+        for (int c = 0; c < 3; ++c) {
+            double u = ((double)w[1 + c] + 0.5) * 2.3283064365386963e-10;
+            coeff[c * K + k] = mag[c] * (2.0 * u - 1.0);
+        }
+    }
+}
+
+int orc_batch_step(orc_batch *b, const double *bids, int32_t *impressions, int32_t *clicks,
+                   int32_t *conversions, double *cost, double *revenue, double *reward,
+                   uint8_t *terminated, uint8_t *truncated, int n_threads)
+{
+    const int K = b->K;
+    int err = 0;
+    int32_t num_updates = 0;
+    if (b->drift_mask) for (int k = 0; k < K; ++k) num_updates += b->drift_mask[k] ? 1 : 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+    for (int e = 0; e < b->E; ++e) {
+        int64_t po = (int64_t)e * b->param_env_stride;
+        orc_keywords kw;
+        kw.kind = b->kind; kw.K = K;
+        kw.vol_mean = b->vol_mean + po; kw.vol_std = b->vol_std + po;
+        kw.p1 = b->p1 + po; kw.p2 = b->p2 + po; kw.ctr = b->ctr + po; kw.cvr = b->cvr + po;
+        kw.rev_mean = b->rev_mean + po; kw.rev_std = b->rev_std + po;
+        kw.impression_thresh = b->impression_thresh;
+        int32_t *bc = (int32_t *)malloc(sizeof(int32_t) * K);
+        double *profit = (double *)malloc(sizeof(double) * K);
+        int64_t *cc = (int64_t *)malloc(sizeof(int64_t) * 2 * K);
+        for (int k = 0; k < K; ++k) bc[k] = orc_bid_to_cents(bids[(int64_t)e * K + k]);
+        orc_result r; memset(&r, 0, sizeof r);
+        r.impressions = impressions + (int64_t)e * K; r.clicks = clicks + (int64_t)e * K;
+        r.conversions = conversions + (int64_t)e * K;
+        r.cost = cost + (int64_t)e * K; r.revenue = revenue + (int64_t)e * K;
+        r.profit = profit; r.cost_cents = cc; r.revenue_cents = cc + K;
+        int rc = orc_step_philox(&kw, bc, b->budget[e], b->budget_alias, b->seed, b->env_base + (uint32_t)e, b->step, 0u, &r, 0);
+        if (rc) err = rc;
+        reward[e] = r.reward;
+        /* env tail (gymnasium_kw_env.py:222-230) */
+        b->cum_profit[e] += r.reward;
+        truncated[e] = b->cum_profit[e] < -b->loss_threshold;
+        b->day[e] += 1;
+        terminated[e] = b->day[e] >= b->max_days;
+        if (b->drift_mask && b->param_env_stride) {
+            double *coeff = (double *)malloc(sizeof(double) * 3 * K);
+            orc_drift_philox(K, b->seed, b->env_base + (uint32_t)e, b->step, b->drift_mag, coeff);
+            orc_drift_apply(K, b->drift_mask, num_updates, coeff, b->vol_std + po,
+                            b->vol_mean + po, b->ctr + po, b->cvr + po);
+            free(coeff);
+        }
+        if (terminated[e] || truncated[e]) { b->cum_profit[e] = 0.0; b->day[e] = 0; } /* auto-reset */
+        free(bc); free(profit); free(cc);
+    }
+    b->step += 1;
+    return err;
+}
