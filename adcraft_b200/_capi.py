@@ -1,0 +1,127 @@
+"""ctypes binding of include/adcraft_b200.h (the C ABI of the CUDA library).
+
+The product path has NO fallback: if the shared library is missing, or there is no CUDA
+device, loading / stepping raises.  Layout is verified against the compiled struct sizes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+SUBSTEPS = 24
+IMPLICIT, EXPLICIT = 0, 1
+F32, F64 = 0, 1
+
+
+class AdcError(RuntimeError):
+    pass
+
+
+class Keywords(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("K", C.c_int32), ("env_stride", C.c_int64),
+        ("vol_mean", C.c_void_p), ("vol_std", C.c_void_p), ("p1", C.c_void_p), ("p2", C.c_void_p),
+        ("ctr", C.c_void_p), ("cvr", C.c_void_p), ("rev_mean", C.c_void_p), ("rev_std", C.c_void_p),
+        ("impression_thresh", C.c_double),
+    ]
+
+
+class EnvState(C.Structure):
+    _fields_ = [
+        ("budget", C.c_void_p), ("cum_profit", C.c_void_p), ("day", C.c_void_p),
+        ("max_days", C.c_int32), ("loss_threshold", C.c_double),
+    ]
+
+
+class Drift(C.Structure):
+    _fields_ = [("mask", C.c_void_p), ("num_updates", C.c_int32), ("mag", C.c_double * 3)]
+
+
+class StepOut(C.Structure):
+    _fields_ = [
+        ("impressions", C.c_void_p), ("clicks", C.c_void_p), ("conversions", C.c_void_p),
+        ("cost", C.c_void_p), ("revenue", C.c_void_p), ("float_dtype", C.c_int32),
+        ("cost_cents", C.c_void_p), ("revenue_cents", C.c_void_p), ("reward", C.c_void_p),
+        ("obs_cum_profit", C.c_void_p), ("obs_days", C.c_void_p), ("terminated", C.c_void_p),
+        ("truncated", C.c_void_p), ("remaining_budget", C.c_void_p),
+    ]
+
+
+class Scratch(C.Structure):
+    _fields_ = [
+        ("serial_list", C.c_void_p), ("serial_count", C.c_void_p), ("env_profit", C.c_void_p),
+        ("env_cost", C.c_void_p), ("env_done", C.c_void_p), ("unit_cost_f64", C.c_void_p),
+    ]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [
+        ("E", C.c_int32), ("env_base", C.c_uint32), ("step", C.c_uint32), ("seed", C.c_uint64),
+        ("n_lanes", C.c_int32), ("budget_alias", C.c_int32), ("autoreset", C.c_int32),
+        ("force_serial", C.c_int32),
+        ("kw", Keywords), ("env", EnvState), ("drift", Drift),
+        ("bids", C.c_void_p), ("bids_dtype", C.c_int32), ("budget_in", C.c_void_p),
+        ("out", StepOut), ("scratch", Scratch),
+    ]
+
+
+class Tape(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "volume", "comp_off", "comp_cents", "click_off", "u_click", "conv_off", "u_conv",
+        "rev_off", "rev_cents", "impr", "cost_off", "cost", "drift")]
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return os.environ.get("ADCRAFT_B200_LIB", _build.LIB_PATH)
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise if it is missing or its ABI does not match."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise AdcError(
+            f"adcraft_b200: CUDA library not found at {path}. Build it with "
+            "`python -m adcraft_b200.build` (needs nvcc); there is no CPU fallback.")
+    lib = C.CDLL(path)
+    lib.adc_last_error.restype = C.c_char_p
+    lib.adc_abi_version.restype = C.c_int
+    lib.adc_device_count.restype = C.c_int
+    lib.adc_sizeof_step_args.restype = C.c_int
+    lib.adc_sizeof_tape.restype = C.c_int
+    lib.adc_step_philox.restype = C.c_int
+    lib.adc_step_philox.argtypes = [C.POINTER(StepArgs), C.c_void_p]
+    lib.adc_step_replay.restype = C.c_int
+    lib.adc_step_replay.argtypes = [C.POINTER(StepArgs), C.POINTER(Tape), C.c_void_p]
+    lib.adc_reset_envs.restype = C.c_int
+    lib.adc_reset_envs.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.adc_launch_count.restype = C.c_int64
+    lib.adc_launch_count.argtypes = [C.c_int]
+    if lib.adc_abi_version() != 1:
+        raise AdcError(f"adcraft_b200: ABI version {lib.adc_abi_version()} != 1")
+    if lib.adc_sizeof_step_args() != C.sizeof(StepArgs) or lib.adc_sizeof_tape() != C.sizeof(Tape):
+        raise AdcError(
+            "adcraft_b200: struct layout mismatch between _capi.py and the compiled library "
+            f"({lib.adc_sizeof_step_args()} vs {C.sizeof(StepArgs)}, "
+            f"{lib.adc_sizeof_tape()} vs {C.sizeof(Tape)}); rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().adc_last_error()
+        raise AdcError(f"{msg.decode() if msg else 'adcraft_b200 error'} (status {rc})")
+
+
+EXPORTED_SYMBOLS = (
+    "adc_last_error", "adc_abi_version", "adc_device_count", "adc_sizeof_step_args",
+    "adc_sizeof_tape", "adc_step_philox", "adc_step_replay", "adc_reset_envs", "adc_launch_count",
+)

@@ -1,0 +1,61 @@
+"""Build the CUDA library in-tree (adcraft_b200/_build/libadcraft_b200.so) for sm_100a.
+
+nvcc cross-compiles without a GPU.  The .so is git-ignored but travels with the tree to the
+GPU box.  Flags: --fmad=false keeps float arithmetic un-contracted so the samplers are
+bit-reproducible against an IEEE CPU evaluation (see csrc/adc_rng.cuh).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+BUILD_DIR = os.path.join(_HERE, "_build")
+LIB_PATH = os.path.join(BUILD_DIR, "libadcraft_b200.so")
+SOURCES = ["adc_step.cu", "adc_capi.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
+    "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build adcraft_b200")
+
+
+def _deps() -> list:
+    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    out.append(os.path.join(_HERE, "..", "include", "adcraft_b200.h"))
+    return out
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in _deps())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd), file=sys.stderr)
+    # host compiler: the image's CC/CXX wrappers are fine for nvcc, but keep it explicit
+    env = dict(os.environ)
+    subprocess.run(cmd, check=True, env=env)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,138 @@
+// extern "C" entry points declared in include/adcraft_b200.h.
+// Argument validation + error reporting live here; kernels and launch logic in adc_step.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "adc_step.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int64_t g_launches = 0;
+
+int fail(adc_status st, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return (int)st;
+}
+
+int check_device()
+{
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        return fail(ADC_ERR_NO_DEVICE, "adcraft_b200: no CUDA device (%s); there is no CPU fallback",
+                    e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+    }
+    return ADC_OK;
+}
+
+#define ADC_REQUIRE(cond, what) \
+    if (!(cond)) return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: %s", what)
+
+int validate(const adc_step_args *a, const adc_tape *tape)
+{
+    ADC_REQUIRE(a != nullptr, "args is NULL");
+    ADC_REQUIRE(a->E > 0, "E must be > 0");
+    ADC_REQUIRE(a->kw.K > 0 && a->kw.K < (1 << 20), "K must be in [1, 2^20)");
+    ADC_REQUIRE(a->kw.kind == ADC_IMPLICIT || a->kw.kind == ADC_EXPLICIT, "kw.kind");
+    ADC_REQUIRE(a->kw.env_stride == 0 || a->kw.env_stride == a->kw.K, "kw.env_stride must be 0 or K");
+    ADC_REQUIRE(a->kw.vol_mean && a->kw.vol_std && a->kw.p1 && a->kw.p2 && a->kw.ctr && a->kw.cvr &&
+                    a->kw.rev_mean && a->kw.rev_std, "kw parameter pointer is NULL");
+    ADC_REQUIRE(a->env.budget && a->env.cum_profit && a->env.day, "env state pointer is NULL");
+    ADC_REQUIRE(a->bids != nullptr, "bids is NULL");
+    ADC_REQUIRE(a->bids_dtype == ADC_F32 || a->bids_dtype == ADC_F64, "bids_dtype");
+    ADC_REQUIRE(a->out.float_dtype == ADC_F32 || a->out.float_dtype == ADC_F64, "out.float_dtype");
+    ADC_REQUIRE(a->out.impressions && a->out.clicks && a->out.conversions && a->out.cost &&
+                    a->out.revenue && a->out.cost_cents && a->out.revenue_cents && a->out.reward &&
+                    a->out.obs_cum_profit && a->out.obs_days && a->out.terminated && a->out.truncated,
+                "output pointer is NULL");
+    ADC_REQUIRE(a->scratch.serial_list && a->scratch.serial_count && a->scratch.env_profit &&
+                    a->scratch.env_cost && a->scratch.env_done, "scratch pointer is NULL");
+    ADC_REQUIRE(a->kw.kind != ADC_EXPLICIT || a->scratch.unit_cost_f64 != nullptr,
+                "scratch.unit_cost_f64 is required for explicit keywords");
+    ADC_REQUIRE(a->drift.mask == nullptr || a->kw.env_stride == a->kw.K,
+                "drift needs per-env keyword parameters (kw.env_stride == K)");
+    ADC_REQUIRE(a->drift.mask == nullptr || (a->drift.num_updates >= 0 && a->drift.num_updates <= a->kw.K),
+                "drift.num_updates");
+    if (a->n_lanes != 0) {
+        const int L = a->n_lanes;
+        ADC_REQUIRE(L >= 1 && L <= 32 && (L & (L - 1)) == 0, "n_lanes must be 0 or a power of two <= 32");
+    }
+    if (tape) {
+        ADC_REQUIRE(tape->volume && tape->click_off && tape->u_click && tape->conv_off && tape->u_conv &&
+                        tape->rev_off && tape->rev_cents, "tape stream pointer is NULL");
+        if (a->kw.kind == ADC_IMPLICIT)
+            ADC_REQUIRE(tape->comp_off && tape->comp_cents, "tape.comp_* required for implicit keywords");
+        else
+            ADC_REQUIRE(tape->impr && tape->cost_off && tape->cost, "tape.impr/cost_* required for explicit keywords");
+        ADC_REQUIRE(a->drift.mask == nullptr || tape->drift != nullptr, "tape.drift required when drift is on");
+    }
+    return ADC_OK;
+}
+
+int run(const adc_step_args *args, const adc_tape *tape, void *stream)
+{
+    int rc = validate(args, tape);
+    if (rc) return rc;
+    rc = check_device();
+    if (rc) return rc;
+    const cudaError_t e = adc::launch_step(*args, tape, static_cast<cudaStream_t>(stream), &g_launches);
+    if (e != cudaSuccess) return fail(ADC_ERR_CUDA, "adcraft_b200: launch failed: %s", cudaGetErrorString(e));
+    return ADC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *adc_last_error(void) { return g_err; }
+
+int adc_abi_version(void) { return ADC_ABI_VERSION; }
+
+int adc_sizeof_step_args(void) { return (int)sizeof(adc_step_args); }
+
+int adc_sizeof_tape(void) { return (int)sizeof(adc_tape); }
+
+int adc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int adc_step_philox(const adc_step_args *args, void *stream) { return run(args, nullptr, stream); }
+
+int adc_step_replay(const adc_step_args *args, const adc_tape *tape, void *stream)
+{
+    if (tape == nullptr) return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: tape is NULL");
+    return run(args, tape, stream);
+}
+
+int adc_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day, void *stream)
+{
+    if (E <= 0 || !cum_profit || !day) return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: reset_envs");
+    const int rc = check_device();
+    if (rc) return rc;
+    const cudaError_t e =
+        adc::launch_reset_envs(E, mask, cum_profit, day, static_cast<cudaStream_t>(stream), &g_launches);
+    if (e != cudaSuccess) return fail(ADC_ERR_CUDA, "adcraft_b200: launch failed: %s", cudaGetErrorString(e));
+    return ADC_OK;
+}
+
+int64_t adc_launch_count(int reset)
+{
+    const int64_t n = g_launches;
+    if (reset) g_launches = 0;
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+// Counter-based draws of the B200 AdCraft step: Philox4x32-10 + deterministic samplers.
+//
+// The "tape function" (DESIGN.md): every random quantity of (env, keyword, step) is a pure
+// function of a Philox counter, so results do not depend on grid shape or GPU count.
+//   key = (seed_lo, seed_hi);  ctr = (index, step, stream<<28 | agent<<20 | keyword, env)
+// All floating-point arithmetic uses explicit round-to-nearest intrinsics (no implicit FMA
+// contraction, no fast-math), so a CPU that evaluates the same expressions with IEEE fmaf gets
+// bit-identical values -- that is what lets the tests compare integer outcomes exactly.
+//
+// Reference behaviour sampled here:
+//   competitor bid   around(max(|Laplace(loc,scale)|,0),2)   adcraft/synthetic_kw_helpers.py:104-113
+//   revenue          around(max(N(mu,sd),0.01),2)            adcraft/synthetic_kw_helpers.py:66-70
+//   volume           round(max(N(mu,sd),0)) half away        src/lib.rs:314-325
+//   click / conv     U <= p                                   adcraft/synthetic_kw_helpers.py:73-77
+//   impressions      Binomial(n, thresholded sigmoid)         src/lib.rs:69-76,92-105
+//   explicit cost    clamp(sqrt(b)/4 + 2.2 + N(0,1e-10+sqrt(b)/6), 0, 4.4)   src/lib.rs:53-67
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace adc {
+
+enum : uint32_t { ST_AUCTION = 0u, ST_UNIT = 1u, ST_REVENUE = 2u, ST_PHANTOM = 3u };
+
+struct PhiloxKey {
+    uint32_t k0, k1;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ uint32_t stream_word(uint32_t stream, uint32_t agent, uint32_t kw)
+{
+    return (stream << 28) | (agent << 20) | kw;
+}
+
+// ln(1+f) for 1+f in [sqrt(1/2), sqrt(2)] (Cephes logf minimax coefficients).
+__device__ __forceinline__ float ln_mant(float f)
+{
+    const float z = __fmul_rn(f, f);
+    float y = 7.0376836292E-2f;
+    y = __fmaf_rn(y, f, -1.1514610310E-1f);
+    y = __fmaf_rn(y, f, 1.1676998740E-1f);
+    y = __fmaf_rn(y, f, -1.2420140846E-1f);
+    y = __fmaf_rn(y, f, 1.4249322787E-1f);
+    y = __fmaf_rn(y, f, -1.6668057665E-1f);
+    y = __fmaf_rn(y, f, 2.0000714765E-1f);
+    y = __fmaf_rn(y, f, -2.4999993993E-1f);
+    y = __fmaf_rn(y, f, 3.3333331174E-1f);
+    y = __fmul_rn(__fmul_rn(y, f), z);
+    y = __fmaf_rn(-0.5f, z, y);
+    return __fadd_rn(f, y);
+}
+
+__device__ __forceinline__ float split_mant(float a, int &k)
+{
+    const uint32_t b = __float_as_uint(a);
+    int e = (int)(b >> 23) - 127;
+    float m = __uint_as_float((b & 0x007FFFFFu) | 0x3F800000u);
+    if (m > 1.41421354f) {
+        m = __fmul_rn(m, 0.5f);
+        e += 1;
+    }
+    k = e;
+    return m;
+}
+
+constexpr float kLn2f = 0.693147182f;
+
+__device__ __forceinline__ float lnf_det(float a)
+{
+    int k;
+    const float m = split_mant(a, k);
+    const float r = ln_mant(__fsub_rn(m, 1.0f));
+    return __fmaf_rn((float)k, kLn2f, r);
+}
+
+// -ln((w31 + 0.5) / 2^31): Exp(1) variate from a 31-bit uniform integer.
+__device__ __forceinline__ float neglog_u31(uint32_t w31)
+{
+    const float a = __uint2float_rn(2u * w31 + 1u);
+    int k;
+    const float m = split_mant(a, k);
+    const float r = ln_mant(__fsub_rn(m, 1.0f));
+    return __fmaf_rn((float)(32 - k), kLn2f, -r);
+}
+
+// Standard normal from one word: sign bit + 31-bit tail probability through Giles' erfinv.
+__device__ __forceinline__ float znorm(uint32_t w)
+{
+    const uint32_t w31 = w & 0x7FFFFFFFu;
+    const float t = __fmul_rn(__uint2float_rn(2u * w31 + 1u), 2.3283064365386963e-10f);
+    const float a = __fmul_rn(t, __fsub_rn(2.0f, t));
+    const float wl = -lnf_det(a);
+    float p;
+    if (wl < 5.0f) {
+        const float v = __fsub_rn(wl, 2.5f);
+        p = 2.81022636e-08f;
+        p = __fmaf_rn(p, v, 3.43273939e-07f);
+        p = __fmaf_rn(p, v, -3.5233877e-06f);
+        p = __fmaf_rn(p, v, -4.39150654e-06f);
+        p = __fmaf_rn(p, v, 0.00021858087f);
+        p = __fmaf_rn(p, v, -0.00125372503f);
+        p = __fmaf_rn(p, v, -0.00417768164f);
+        p = __fmaf_rn(p, v, 0.246640727f);
+        p = __fmaf_rn(p, v, 1.50140941f);
+    } else {
+        const float v = __fsub_rn(__fsqrt_rn(wl), 3.0f);
+        p = -0.000200214257f;
+        p = __fmaf_rn(p, v, 0.000100950558f);
+        p = __fmaf_rn(p, v, 0.00134934322f);
+        p = __fmaf_rn(p, v, -0.00367342844f);
+        p = __fmaf_rn(p, v, 0.00573950773f);
+        p = __fmaf_rn(p, v, -0.0076224613f);
+        p = __fmaf_rn(p, v, 0.00943887047f);
+        p = __fmaf_rn(p, v, 1.00167406f);
+        p = __fmaf_rn(p, v, 2.83297682f);
+    }
+    const float z = __fmul_rn(__fmul_rn(p, __fsub_rn(1.0f, t)), 1.41421354f);
+    return (w >> 31) ? -z : z;
+}
+
+// exp(x) in float64, explicit fma only (explicit keywords' thresholded sigmoid, once per unit).
+__device__ __forceinline__ double exp_det(double x)
+{
+    if (x != x) return x;
+    if (x > 709.0) return __longlong_as_double(0x7FF0000000000000LL);
+    if (x < -700.0) return 0.0;
+    const double kf = rint(__dmul_rn(x, 1.4426950408889634));
+    double r = __fma_rn(-kf, 6.93147180369123816490e-01, x);
+    r = __fma_rn(-kf, 1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = __fma_rn(p, r, 1.0 / 479001600.0);
+    p = __fma_rn(p, r, 1.0 / 39916800.0);
+    p = __fma_rn(p, r, 1.0 / 3628800.0);
+    p = __fma_rn(p, r, 1.0 / 362880.0);
+    p = __fma_rn(p, r, 1.0 / 40320.0);
+    p = __fma_rn(p, r, 1.0 / 5040.0);
+    p = __fma_rn(p, r, 1.0 / 720.0);
+    p = __fma_rn(p, r, 1.0 / 120.0);
+    p = __fma_rn(p, r, 1.0 / 24.0);
+    p = __fma_rn(p, r, 1.0 / 6.0);
+    p = __fma_rn(p, r, 0.5);
+    p = __fma_rn(p, r, 1.0);
+    p = __fma_rn(p, r, 1.0);
+    const long long k = (long long)kf;
+    const double s = __longlong_as_double((k + 1023LL) << 52);
+    return __dmul_rn(p, s);
+}
+
+__device__ __forceinline__ int laplace_cents(uint32_t w0, float loc, float scale)
+{
+    const float e = neglog_u31(w0 & 0x7FFFFFFFu);
+    const float s = (w0 >> 31) ? -scale : scale;
+    const float x = __fmaf_rn(s, e, loc);
+    return __float2int_rn(__fmul_rn(fabsf(x), 100.0f));
+}
+
+__device__ __forceinline__ int revenue_cents(uint32_t w, float mean, float sd)
+{
+    const float v = __fmaf_rn(sd, znorm(w), mean);
+    const int c = __float2int_rn(__fmul_rn(v, 100.0f));
+    return c < 1 ? 1 : c;
+}
+
+__device__ __forceinline__ long long volume_draw(uint32_t w, double mean, double sd)
+{
+    double v = __dadd_rn(mean, __dmul_rn(sd, (double)znorm(w)));
+    if (!(v > 0.0)) v = 0.0;
+    return (long long)round(v);
+}
+
+__device__ __forceinline__ double clampd(double x, double lo, double hi)
+{
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
+__device__ __forceinline__ double threshold_sigmoid(double bid, double thresh_in, double intercept,
+                                                    double slope)
+{
+    const double halver = 2.0 + 1e-10;
+    const double thresh = __ddiv_rn(clampd(__dmul_rn(halver, thresh_in), 0.0, 1.0), halver);
+    const double ex = exp_det(__dmul_rn(-slope, __dsub_rn(bid, intercept)));
+    const double r = __ddiv_rn(1.0, __dadd_rn(1.0, ex));
+    const double a = __dadd_rn(1.0, __dmul_rn(2.0, thresh));
+    return clampd(__dsub_rn(__dmul_rn(a, r), thresh), 0.0, 1.0);
+}
+
+// P(w * 2^-32 <= p)  <=>  w <= floor(p * 2^32), saturated.
+__device__ __forceinline__ uint32_t prob_threshold(double p)
+{
+    if (!(p > 0.0)) return 0u;
+    const double t = floor(__dmul_rn(p, 4294967296.0));
+    if (t >= 4294967295.0) return 0xFFFFFFFFu;
+    return (uint32_t)t;
+}
+
+__device__ __forceinline__ double explicit_cost(uint32_t w3, double bid)
+{
+    const double xs = __dsqrt_rn(bid);
+    const double sd = __dadd_rn(1e-10, __ddiv_rn(xs, 6.0));
+    const double mean = __dadd_rn(__ddiv_rn(xs, 4.0), 4.4 / 2.0);
+    const double c = __dadd_rn(mean, __dmul_rn(sd, (double)znorm(w3)));
+    return clampd(c, 0.0, 4.4);
+}
+
+// round(np.maximum(bid, 0.01), 2) in integer cents (adcraft/gymnasium_kw_env.py:215).
+__device__ __forceinline__ int bid_to_cents(double bid)
+{
+    double b = bid > 0.01 ? bid : 0.01;
+    if (!(b == b)) b = 0.01;
+    double c = rint(__dmul_rn(b, 100.0));
+    if (c > 2.0e9) c = 2.0e9;
+    return (int)c;
+}
+
+}  // namespace adc

@@ -1,0 +1,774 @@
+// Kernels of the B200-native BiddingSimulation.step (sm_100a).
+//
+// Path (reference file:line):
+//   BiddingSimulation.step                      adcraft/gymnasium_kw_env.py:160-269
+//   simulate_epoch_of_bidding_on_campaign       adcraft/bidding_simulation.py:170-234
+//   simulate_epoch_of_bidding (one "lane")      adcraft/bidding_simulation.py:44-120
+//   ImplicitKeyword.auction / nth_price_auction adcraft/synthetic_kw_classes.py:623-646,
+//                                               adcraft/synthetic_kw_helpers.py:116-180
+//   ExplicitKeyword.auction                     adcraft/synthetic_kw_classes.py:493-538
+//   update_keywords                             adcraft/gymnasium_kw_env.py:114-158
+//
+// Three kernels:
+//   adc_lanes_philox_implicit_kernel<L>  hot kernel: L threads share one (env,keyword) unit and
+//       split its day of auctions; every auction is one Philox4x32-10 call (competitor bid,
+//       click and conversion words travel together), outcomes are integer cents, the unit is
+//       reduced with warp shuffles and the env with L2 atomics; the thread group that
+//       completes an env's last unit runs the env tail (reward, flags, auto-reset, drift).
+//   adc_units_kernel<Src, kExplicit>     one thread per unit, lanes walked in order without the
+//       budget (explicit keywords in free-running mode, and replay of either kind).
+//   adc_serial_kernel<Src>               exact serial walk in (sub-step, keyword, click) order
+//       with the shared budget, early break and the ndarray-aliasing double charge; one thread
+//       per env, only for envs whose day's spend could reach the budget.
+// A unit's outcome does not depend on the sub-step split unless the budget binds (implicit) --
+// that is what lets the hot kernel treat the day as one flat loop ("fast path").
+#include "adc_rng.cuh"
+#include "adc_step.h"
+
+#include <cstdio>
+
+namespace adc {
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double load_f(const void *p, int dtype, int64_t i)
+{
+    return dtype == ADC_F64 ? reinterpret_cast<const double *>(p)[i]
+                            : (double)reinterpret_cast<const float *>(p)[i];
+}
+
+__device__ __forceinline__ void store_f(void *p, int dtype, int64_t i, double v)
+{
+    if (dtype == ADC_F64)
+        reinterpret_cast<double *>(p)[i] = v;
+    else
+        reinterpret_cast<float *>(p)[i] = (float)v;
+}
+
+__device__ __forceinline__ double cents_to_dollars(long long c)
+{
+    return __ddiv_rn((double)c, 100.0);  // == np.around(x, 2) of the same cents value
+}
+
+// budget of env e for this step: action budget rounded to cents (env:199) or the persisted one
+__device__ __forceinline__ double step_budget(const adc_step_args &a, int e)
+{
+    if (a.budget_in != nullptr) {
+        const double b = load_f(a.budget_in, a.bids_dtype, e);
+        return __ddiv_rn(rint(__dmul_rn(b, 100.0)), 100.0);
+    }
+    return a.env.budget[e];
+}
+
+// Can the day's total spend possibly make a `budget >= cost` check fail or drive the remaining
+// budget to <= 0?  `spend` is the exact (cents) or f64 total; the margin covers the rounding of
+// the reference's sequential float subtractions (<= n_clicks * ulp(budget)).
+__device__ __forceinline__ bool budget_is_safe(double budget, double spend, int alias)
+{
+    const double s = alias ? 2.0 * spend : spend;
+    return s + 0.005 + 1e-7 * fabs(budget) + 1e-9 * s < budget;
+}
+
+struct Drift3 {
+    double c[3];
+};
+
+__device__ __forceinline__ Drift3 drift_from_words(const adc_step_args &a, uint4 w)
+{
+    Drift3 d;
+    const uint32_t ws[3] = {w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double u = __dmul_rn(__dadd_rn((double)ws[i], 0.5), 2.3283064365386963e-10);
+        d.c[i] = __dmul_rn(a.drift.mag[i], __dsub_rn(__dmul_rn(2.0, u), 1.0));
+    }
+    return d;
+}
+
+// update_keywords for one keyword (env:145-158): nonnegify / probify
+__device__ __forceinline__ void drift_apply(const adc_step_args &a, int e, int k, const Drift3 &d)
+{
+    const int64_t i = (int64_t)e * a.kw.env_stride + k;
+    const double vm = __dadd_rn(a.kw.vol_mean[i], __dmul_rn(d.c[0], a.kw.vol_std[i]));
+    a.kw.vol_mean[i] = vm > 0.0 ? vm : 0.0;
+    a.kw.ctr[i] = clampd(__dmul_rn(a.kw.ctr[i], __dadd_rn(1.0, d.c[1])), 0.0, 1.0);
+    a.kw.cvr[i] = clampd(__dmul_rn(a.kw.cvr[i], __dadd_rn(1.0, d.c[2])), 0.0, 1.0);
+}
+
+__device__ __forceinline__ bool drift_wanted(const adc_step_args &a, int k)
+{
+    return a.drift.mask != nullptr && k < a.drift.num_updates && a.drift.mask[k] != 0;
+}
+
+// env tail (env:222-230) + auto-reset.  reward in dollars.
+__device__ __forceinline__ void env_tail(const adc_step_args &a, int e, double reward,
+                                         double budget, double remaining)
+{
+    const double cum = __dadd_rn(a.env.cum_profit[e], reward);
+    const bool trunc = cum < -a.env.loss_threshold;
+    const int day = a.env.day[e] + 1;
+    const bool term = day >= a.env.max_days;
+    a.out.reward[e] = reward;
+    a.out.obs_cum_profit[e] = cum;
+    a.out.obs_days[e] = day;
+    a.out.terminated[e] = term ? 1 : 0;
+    a.out.truncated[e] = trunc ? 1 : 0;
+    if (a.out.remaining_budget) a.out.remaining_budget[e] = remaining;
+    const bool done = a.autoreset && (term || trunc);
+    a.env.cum_profit[e] = done ? 0.0 : cum;
+    a.env.day[e] = done ? 0 : day;
+    // an ndarray budget is mutated in place by the lanes, so the leftover persists (bsim:102)
+    a.env.budget[e] = a.budget_alias ? remaining : budget;
+}
+
+// ------------------------------------------------------------------------------------------
+// draw sources
+// ------------------------------------------------------------------------------------------
+struct PhiloxSrc {
+    static constexpr bool kTape = false;
+    uint32_t k0, k1, step, env;
+    __device__ __forceinline__ uint4 draw(uint32_t stream, uint32_t kw, uint32_t idx) const
+    {
+        return philox4x32_10(idx, step, stream_word(stream, 0u, kw), env, k0, k1);
+    }
+};
+
+struct TapeSrc {
+    static constexpr bool kTape = true;
+    const adc_tape *t;
+};
+
+// running cursors of one unit inside one env step
+struct UnitCur {
+    long long auction;  // auctions evaluated so far (day-level ordinal)
+    int n_click;        // click slots drawn so far
+    int n_conv;         // accepted clicks so far
+    int n_rev;          // conversions so far
+    int n_cost;         // explicit: impressions so far
+};
+
+struct UnitPar {
+    int bid_cents;
+    double bid;  // dollars (explicit)
+    float loc, scale, rev_mean, rev_sd;
+    double ctr, cvr;
+    uint32_t thr_click, thr_conv, thr_impr;
+};
+
+struct LaneOut {
+    int I, B, S;
+    long long cost_cents, rev_cents;
+    double lane_cost_sum;  // dollars, sequential rust.sum_list of this lane's costs (bsim:225)
+};
+
+// One call of simulate_epoch_of_bidding (bsim:44-120) for unit u, sub-step t, n auctions.
+// kBudget=false: budget is +inf (no check can fail).  `b` is the lane-local budget copy;
+// `day_cost` is the keyword's running sequential f64 cost sum over the day's concatenated
+// clicks (env:235) -- only the explicit keywords' un-rounded costs need it.
+template <typename Src, bool kExplicit, bool kBudget>
+__device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp, int64_t u, int kw,
+                                             int t, long long n, const UnitPar &p, UnitCur &cur,
+                                             double &b, double &day_cost)
+{
+    LaneOut o;
+    o.I = o.B = o.S = 0;
+    o.cost_cents = o.rev_cents = 0;
+    o.lane_cost_sum = 0.0;
+    bool stopped = false;  // the `break` of bsim:103-104: later slots are drawn but not scanned
+    int slots = 0;
+    uint4 rw = make_uint4(0, 0, 0, 0);
+    bool rw_valid = false;
+
+    auto on_slot = [&](double cost, long long cost_c, bool clicked, uint32_t w2) {
+        // clicked slot: budget walk (bsim:97-104), conversion flip (bsim:106-109), revenue (bsim:111)
+        if (!clicked || stopped) return;
+        if (kBudget && !(b >= cost)) {
+            stopped = true;
+            return;
+        }
+        bool conv;
+        if constexpr (Src::kTape)
+            conv = tp->u_conv[tp->conv_off[u] + cur.n_conv + o.B] <= p.cvr;
+        else
+            conv = w2 <= p.thr_conv;
+        o.B += 1;
+        o.cost_cents += cost_c;
+        if constexpr (kExplicit) day_cost = __dadd_rn(day_cost, cost);
+        o.lane_cost_sum = __dadd_rn(o.lane_cost_sum, cost);
+        if (kBudget) b = __dsub_rn(b, cost);
+        if (conv) {
+            const int r = cur.n_rev + o.S;
+            int rc;
+            if constexpr (Src::kTape) {
+                rc = tp->rev_cents[tp->rev_off[u] + r];
+            } else {
+                if (!rw_valid || (r & 3) == 0) {
+                    rw = src.draw(ST_REVENUE, (uint32_t)kw, (uint32_t)(r >> 2));
+                    rw_valid = true;
+                }
+                const uint32_t w = (r & 3) == 0 ? rw.x : (r & 3) == 1 ? rw.y : (r & 3) == 2 ? rw.z : rw.w;
+                rc = revenue_cents(w, p.rev_mean, p.rev_sd);
+            }
+            o.S += 1;
+            o.rev_cents += rc;
+        }
+    };
+
+    if constexpr (!kExplicit) {
+        // second-price auction against one competitor (classes:644-646, helpers:116-180):
+        // win iff bid > competitor (strict), cost = competitor's bid.
+        for (long long a = 0; a < n; ++a) {
+            const long long j = cur.auction + a;
+            int c;
+            uint32_t w1 = 0, w2 = 0;
+            if constexpr (Src::kTape) {
+                c = tp->comp_cents[tp->comp_off[u] + j];
+            } else {
+                const uint4 w = src.draw(ST_AUCTION, (uint32_t)kw, (uint32_t)j);
+                c = laplace_cents(w.x, p.loc, p.scale);
+                w1 = w.y;
+                w2 = w.z;
+            }
+            if (p.bid_cents > c) {
+                bool clicked;
+                if constexpr (Src::kTape)
+                    clicked = tp->u_click[tp->click_off[u] + cur.n_click + slots] <= p.ctr;
+                else
+                    clicked = w1 <= p.thr_click;
+                on_slot(cents_to_dollars(c), c, clicked, w2);
+                ++slots;
+                ++o.I;
+            }
+        }
+    } else {
+        if constexpr (Src::kTape) {
+            const int I = tp->impr[u * ADC_SUBSTEPS + t];
+            for (int i = 0; i < I; ++i) {
+                const double cost = tp->cost[tp->cost_off[u] + cur.n_cost + i];
+                const bool clicked = tp->u_click[tp->click_off[u] + cur.n_click + i] <= p.ctr;
+                on_slot(cost, 0, clicked, 0u);
+            }
+            o.I = I;
+            slots = I;
+            if (I < 1) {  // phantom zero-cost slot (classes:514-515)
+                const bool clicked = tp->u_click[tp->click_off[u] + cur.n_click] <= p.ctr;
+                on_slot(0.0, 0, clicked, 0u);
+                slots = 1;
+            }
+        } else {
+            for (long long a = 0; a < n; ++a) {
+                const long long j = cur.auction + a;
+                const uint4 w = src.draw(ST_AUCTION, (uint32_t)kw, (uint32_t)j);
+                if (w.x <= p.thr_impr) {  // Bernoulli(p); the lane's sum is Binomial(n,p)
+                    on_slot(explicit_cost(w.w, p.bid), 0, w.y <= p.thr_click, w.z);
+                    ++slots;
+                    ++o.I;
+                }
+            }
+            if (o.I < 1) {
+                const uint4 w = src.draw(ST_PHANTOM, (uint32_t)kw, (uint32_t)t);
+                on_slot(0.0, 0, w.y <= p.thr_click, w.z);
+                slots = 1;
+            }
+        }
+        cur.n_cost += o.I;
+    }
+    cur.auction += n;
+    cur.n_click += slots;
+    cur.n_conv += o.B;
+    cur.n_rev += o.S;
+    return o;
+}
+
+__device__ __forceinline__ UnitPar load_unit_par(const adc_step_args &a, int e, int k)
+{
+    UnitPar p;
+    const int64_t pi = (int64_t)e * a.kw.env_stride + k;
+    const int64_t u = (int64_t)e * a.kw.K + k;
+    p.bid_cents = bid_to_cents(load_f(a.bids, a.bids_dtype, u));
+    p.bid = cents_to_dollars(p.bid_cents);
+    p.ctr = a.kw.ctr[pi];
+    p.cvr = a.kw.cvr[pi];
+    p.thr_click = prob_threshold(p.ctr);
+    p.thr_conv = prob_threshold(p.cvr);
+    p.rev_mean = (float)a.kw.rev_mean[pi];
+    p.rev_sd = (float)a.kw.rev_std[pi];
+    p.loc = (float)a.kw.p1[pi];
+    p.scale = (float)a.kw.p2[pi];
+    p.thr_impr = 0u;
+    if (a.kw.kind == ADC_EXPLICIT)
+        p.thr_impr = prob_threshold(threshold_sigmoid(p.bid, a.kw.impression_thresh, a.kw.p1[pi], a.kw.p2[pi]));
+    return p;
+}
+
+template <typename Src>
+__device__ __forceinline__ long long unit_volume(const adc_step_args &a, const Src &src,
+                                                 const adc_tape *tp, int e, int k, uint4 *unit_words)
+{
+    if constexpr (Src::kTape) {
+        *unit_words = make_uint4(0, 0, 0, 0);
+        return tp->volume[(int64_t)e * a.kw.K + k];
+    } else {
+        const int64_t pi = (int64_t)e * a.kw.env_stride + k;
+        const uint4 w = src.draw(ST_UNIT, (uint32_t)k, 0u);
+        *unit_words = w;
+        long long v = volume_draw(w.x, a.kw.vol_mean[pi], a.kw.vol_std[pi]);
+        return v > 2147483647LL ? 2147483647LL : v;
+    }
+}
+
+template <typename Src>
+__device__ __forceinline__ Drift3 unit_drift(const adc_step_args &a, const adc_tape *tp, int e, int k,
+                                             uint4 unit_words)
+{
+    if constexpr (Src::kTape) {
+        Drift3 d;
+        const int K = a.kw.K;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) d.c[i] = tp->drift ? tp->drift[((int64_t)e * 3 + i) * K + k] : 0.0;
+        return d;
+    } else {
+        return drift_from_words(a, unit_words);
+    }
+}
+
+// Unit finished: publish it, and if it was the env's last unit, run the env tail or queue the
+// env for the exact serial walk.  Returns (to the calling thread only) 1 if this env is safe and
+// the caller should apply the drift, 0 otherwise.  Called by ONE thread per unit.
+__device__ __forceinline__ int unit_done(const adc_step_args &a, int e, long long profit_cents,
+                                         long long cost_cents)
+{
+    if (profit_cents != 0) atomicAdd(reinterpret_cast<unsigned long long *>(a.scratch.env_profit + e),
+                                     (unsigned long long)profit_cents);
+    if (cost_cents != 0) atomicAdd(reinterpret_cast<unsigned long long *>(a.scratch.env_cost + e),
+                                   (unsigned long long)cost_cents);
+    __threadfence();
+    const int old = atomicAdd(a.scratch.env_done + e, 1);
+    if (old != a.kw.K - 1) return 0;
+    __threadfence();
+    a.scratch.env_done[e] = 0;
+    const long long profit =
+        (long long)atomicExch(reinterpret_cast<unsigned long long *>(a.scratch.env_profit + e), 0ull);
+    const long long cost =
+        (long long)atomicExch(reinterpret_cast<unsigned long long *>(a.scratch.env_cost + e), 0ull);
+    const double budget = step_budget(a, e);
+    double reward, spend;
+    if (a.kw.kind == ADC_EXPLICIT) {
+        // un-rounded explicit costs: sum the per-unit f64 results in keyword order (env:222)
+        reward = 0.0;
+        spend = 0.0;
+        const int K = a.kw.K;
+        for (int k = 0; k < K; ++k) {
+            const int64_t u = (int64_t)e * K + k;
+            const double c = __ldcg(a.scratch.unit_cost_f64 + u);
+            const double r = cents_to_dollars(__ldcg(a.out.revenue_cents + u));
+            reward = __dadd_rn(reward, __dsub_rn(r, c));
+            spend = __dadd_rn(spend, c);
+        }
+    } else {
+        reward = cents_to_dollars(profit);
+        spend = cents_to_dollars(cost);
+    }
+    if (a.force_serial || !budget_is_safe(budget, spend, a.budget_alias)) {
+        const int slot = atomicAdd(a.scratch.serial_count, 1);
+        a.scratch.serial_list[slot] = e;
+        return 0;
+    }
+    const double used = a.budget_alias ? __dmul_rn(2.0, spend) : spend;
+    env_tail(a, e, reward, budget, __dsub_rn(budget, used));
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// hot kernel: implicit keywords, Philox draws, L threads per unit
+// ------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(256)
+adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
+{
+    const int K = a.kw.K;
+    const int64_t total = (int64_t)a.E * K;
+    const int lane = threadIdx.x & (L - 1);
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+    const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / L;
+    const int64_t iters = (total + n_groups - 1) / n_groups;
+    const unsigned wl = threadIdx.x & 31u;
+    const unsigned gmask = L == 32 ? 0xFFFFFFFFu : (((1u << L) - 1u) << (wl & ~(unsigned)(L - 1)));
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t u = it * n_groups + group;
+        const bool valid = u < total;  // uniform inside a group
+        int e = 0, k = 0;
+        long long V = 0;
+        UnitPar p;
+        uint4 uw = make_uint4(0, 0, 0, 0);
+        uint32_t genv = 0;
+        if (valid) {
+            e = (int)(u / K);
+            k = (int)(u - (int64_t)e * K);
+            genv = a.env_base + (uint32_t)e;
+            p = load_unit_par(a, e, k);
+            PhiloxSrc src{k0, k1, a.step, genv};
+            V = unit_volume(a, src, nullptr, e, k, &uw);
+        }
+        // ---- the day's auctions, strided over the group's lanes ----
+        int I = 0, B = 0, S = 0;
+        long long cost = 0;
+        const uint32_t c2 = stream_word(ST_AUCTION, 0u, (uint32_t)k);
+        for (long long j = lane; j < V; j += L) {
+            const uint4 w = philox4x32_10((uint32_t)j, a.step, c2, genv, k0, k1);
+            const int c = laplace_cents(w.x, p.loc, p.scale);
+            const bool win = p.bid_cents > c;
+            const bool clk = win && (w.y <= p.thr_click);
+            const bool cnv = clk && (w.z <= p.thr_conv);
+            I += win;
+            B += clk;
+            S += cnv;
+            cost += clk ? c : 0;
+        }
+        // ---- group reduction (counts packed 21 bits each) ----
+        unsigned long long packed = (unsigned long long)I | ((unsigned long long)B << 21) |
+                                    ((unsigned long long)S << 42);
+#pragma unroll
+        for (int off = L / 2; off > 0; off >>= 1) {
+            packed += __shfl_xor_sync(gmask, packed, off);
+            cost += __shfl_xor_sync(gmask, cost, off);
+        }
+        I = (int)(packed & 0x1FFFFFull);
+        B = (int)((packed >> 21) & 0x1FFFFFull);
+        S = (int)(packed >> 42);
+        // ---- revenues: one draw per conversion, indexed by conversion rank ----
+        long long rev = 0;
+        const uint32_t c2r = stream_word(ST_REVENUE, 0u, (uint32_t)k);
+        for (int blk = lane; 4 * blk < S; blk += L) {
+            const uint4 w = philox4x32_10((uint32_t)blk, a.step, c2r, genv, k0, k1);
+            const int r0 = 4 * blk;
+            rev += revenue_cents(w.x, p.rev_mean, p.rev_sd);
+            if (r0 + 1 < S) rev += revenue_cents(w.y, p.rev_mean, p.rev_sd);
+            if (r0 + 2 < S) rev += revenue_cents(w.z, p.rev_mean, p.rev_sd);
+            if (r0 + 3 < S) rev += revenue_cents(w.w, p.rev_mean, p.rev_sd);
+        }
+#pragma unroll
+        for (int off = L / 2; off > 0; off >>= 1) rev += __shfl_xor_sync(gmask, rev, off);
+
+        int safe = 0;
+        if (valid && lane == 0) {
+            a.out.impressions[u] = I;
+            a.out.clicks[u] = B;
+            a.out.conversions[u] = S;
+            a.out.cost_cents[u] = cost;
+            a.out.revenue_cents[u] = rev;
+            store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
+            store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
+            safe = unit_done(a, e, rev - cost, cost);
+        }
+        // ---- drift of a finished, budget-safe env (env:246); queued envs drift in the serial kernel
+        if (a.drift.mask != nullptr) {
+            safe = __shfl_sync(gmask, safe, 0, L);
+            if (safe) {
+                PhiloxSrc src{k0, k1, a.step, genv};
+                for (int kk = lane; kk < K; kk += L) {
+                    if (!drift_wanted(a, kk)) continue;
+                    const uint4 w = src.draw(ST_UNIT, (uint32_t)kk, 0u);
+                    drift_apply(a, e, kk, drift_from_words(a, w));
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic kernel: one thread per unit, lanes in order, no budget
+// ------------------------------------------------------------------------------------------
+template <typename Src, bool kExplicit>
+__global__ void __launch_bounds__(128)
+adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant__ adc_tape tape)
+{
+    const int K = a.kw.K;
+    const int64_t total = (int64_t)a.E * K;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += stride) {
+        const int e = (int)(u / K);
+        const int k = (int)(u - (int64_t)e * K);
+        Src src;
+        if constexpr (Src::kTape) {
+            src.t = &tape;
+        } else {
+            src.k0 = (uint32_t)a.seed;
+            src.k1 = (uint32_t)(a.seed >> 32);
+            src.step = a.step;
+            src.env = a.env_base + (uint32_t)e;
+        }
+        const UnitPar p = load_unit_par(a, e, k);
+        uint4 uw;
+        const long long V = unit_volume(a, src, &tape, e, k, &uw);
+        const long long q = V / ADC_SUBSTEPS;
+        UnitCur cur = {0, 0, 0, 0, 0};
+        int I = 0, B = 0, S = 0;
+        long long cost_c = 0, rev_c = 0;
+        double cost_f = 0.0, binf = 0.0;
+        for (int t = 0; t < ADC_SUBSTEPS; ++t) {
+            const long long n = t == 0 ? V - (ADC_SUBSTEPS - 1) * q : q;  // bsim:151-167
+            const LaneOut o =
+                lane_walk<Src, kExplicit, false>(src, &tape, u, k, t, n, p, cur, binf, cost_f);
+            I += o.I;
+            B += o.B;
+            S += o.S;
+            cost_c += o.cost_cents;
+            rev_c += o.rev_cents;
+        }
+        a.out.impressions[u] = I;
+        a.out.clicks[u] = B;
+        a.out.conversions[u] = S;
+        a.out.revenue_cents[u] = rev_c;
+        store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev_c));
+        int safe;
+        if constexpr (kExplicit) {
+            a.out.cost_cents[u] = 0;
+            a.scratch.unit_cost_f64[u] = cost_f;
+            store_f(a.out.cost, a.out.float_dtype, u, cost_f);
+            safe = unit_done(a, e, 0, 0);
+        } else {
+            a.out.cost_cents[u] = cost_c;
+            store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost_c));
+            safe = unit_done(a, e, rev_c - cost_c, cost_c);
+        }
+        if (safe && a.drift.mask != nullptr) {
+            for (int kk = 0; kk < K; ++kk) {
+                if (!drift_wanted(a, kk)) continue;
+                uint4 w = make_uint4(0, 0, 0, 0);
+                if constexpr (!Src::kTape) w = src.draw(ST_UNIT, (uint32_t)kk, 0u);
+                drift_apply(a, e, kk, unit_drift<Src>(a, &tape, e, kk, w));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact serial kernel: one thread per queued env, (sub-step, keyword, click) order, shared budget
+// ------------------------------------------------------------------------------------------
+template <typename Src>
+__global__ void __launch_bounds__(64)
+adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant__ adc_tape tape)
+{
+    const int K = a.kw.K;
+    const int count = *a.scratch.serial_count;
+    const bool explicit_kw = a.kw.kind == ADC_EXPLICIT;
+    const int stride = gridDim.x * blockDim.x;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += stride) {
+        const int e = a.scratch.serial_list[idx];
+        Src src;
+        if constexpr (Src::kTape) {
+            src.t = &tape;
+        } else {
+            src.k0 = (uint32_t)a.seed;
+            src.k1 = (uint32_t)(a.seed >> 32);
+            src.step = a.step;
+            src.env = a.env_base + (uint32_t)e;
+        }
+        for (int k = 0; k < K; ++k) {
+            const int64_t u = (int64_t)e * K + k;
+            a.out.impressions[u] = 0;
+            a.out.clicks[u] = 0;
+            a.out.conversions[u] = 0;
+            a.out.cost_cents[u] = 0;
+            a.out.revenue_cents[u] = 0;
+            if (explicit_kw) a.scratch.unit_cost_f64[u] = 0.0;
+        }
+        const double budget = step_budget(a, e);
+        double remaining = budget;  // bsim:214
+        bool stop = false;
+        for (int t = 0; t < ADC_SUBSTEPS && !stop; ++t) {
+            for (int k = 0; k < K; ++k) {
+                const int64_t u = (int64_t)e * K + k;
+                const UnitPar p = load_unit_par(a, e, k);
+                uint4 uw;
+                const long long V = unit_volume(a, src, &tape, e, k, &uw);
+                const long long q = V / ADC_SUBSTEPS;
+                const long long n0 = V - (ADC_SUBSTEPS - 1) * q;
+                const long long n = t == 0 ? n0 : q;
+                UnitCur cur;
+                cur.auction = t == 0 ? 0 : n0 + (long long)(t - 1) * q;
+                cur.n_conv = a.out.clicks[u];
+                cur.n_rev = a.out.conversions[u];
+                cur.n_cost = a.out.impressions[u];
+                cur.n_click = a.out.impressions[u];
+                if (explicit_kw) {
+                    if constexpr (Src::kTape) {  // one slot per impression, or one phantom slot
+                        int s = 0;
+                        for (int tt = 0; tt < t; ++tt) {
+                            const int i = tape.impr[u * ADC_SUBSTEPS + tt];
+                            s += i < 1 ? 1 : i;
+                        }
+                        cur.n_click = s;
+                    }
+                }
+                double b = remaining;
+                LaneOut o;
+                if (explicit_kw) {
+                    double day_cost = a.scratch.unit_cost_f64[u];
+                    o = lane_walk<Src, true, true>(src, &tape, u, k, t, n, p, cur, b, day_cost);
+                    a.scratch.unit_cost_f64[u] = day_cost;
+                } else {
+                    double unused = 0.0;
+                    o = lane_walk<Src, false, true>(src, &tape, u, k, t, n, p, cur, b, unused);
+                }
+                a.out.impressions[u] += o.I;
+                a.out.clicks[u] += o.B;
+                a.out.conversions[u] += o.S;
+                a.out.cost_cents[u] += o.cost_cents;
+                a.out.revenue_cents[u] += o.rev_cents;
+                if (a.budget_alias) remaining = b;                    // bsim:102 on an aliased ndarray
+                remaining = __dsub_rn(remaining, o.lane_cost_sum);   // bsim:225
+                if (remaining <= 0) {                                // bsim:230-233
+                    stop = true;
+                    break;
+                }
+            }
+        }
+        double reward = 0.0;
+        long long profit_c = 0;
+        for (int k = 0; k < K; ++k) {
+            const int64_t u = (int64_t)e * K + k;
+            const double rv = cents_to_dollars(a.out.revenue_cents[u]);
+            store_f(a.out.revenue, a.out.float_dtype, u, rv);
+            if (explicit_kw) {
+                const double c = a.scratch.unit_cost_f64[u];
+                store_f(a.out.cost, a.out.float_dtype, u, c);
+                reward = __dadd_rn(reward, __dsub_rn(rv, c));
+            } else {
+                store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(a.out.cost_cents[u]));
+                profit_c += a.out.revenue_cents[u] - a.out.cost_cents[u];
+            }
+        }
+        if (!explicit_kw) reward = cents_to_dollars(profit_c);
+        env_tail(a, e, reward, budget, remaining);
+        if (a.drift.mask != nullptr) {
+            for (int kk = 0; kk < K; ++kk) {
+                if (!drift_wanted(a, kk)) continue;
+                uint4 w = make_uint4(0, 0, 0, 0);
+                if constexpr (!Src::kTape) w = src.draw(ST_UNIT, (uint32_t)kk, 0u);
+                drift_apply(a, e, kk, unit_drift<Src>(a, &tape, e, kk, w));
+            }
+        }
+    }
+}
+
+__global__ void adc_serial_count_reset_kernel(int32_t *count) { *count = 0; }
+
+__global__ void adc_reset_envs_kernel(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < E && (mask == nullptr || mask[e])) {
+        cum_profit[e] = 0.0;
+        day[e] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+
+static int num_sms()
+{
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int L>
+static cudaError_t launch_lanes(const adc_step_args &a, cudaStream_t s, int64_t *launches)
+{
+    const int block = 256;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adc_lanes_philox_implicit_kernel<L>, block, 0);
+    if (per_sm < 1) per_sm = 1;
+    const int64_t total = (int64_t)a.E * a.kw.K;
+    const int64_t want = (total * L + block - 1) / block;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    adc_lanes_philox_implicit_kernel<L><<<(unsigned)grid, block, 0, s>>>(a);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+template <typename K>
+static int64_t grid_for(K kernel, int block, int64_t work_items)
+{
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    const int64_t want = (work_items + block - 1) / block;
+    if (want < grid) grid = want;
+    return grid < 1 ? 1 : grid;
+}
+
+cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream_t s, int64_t *launches)
+{
+    const bool explicit_kw = a.kw.kind == ADC_EXPLICIT;
+    const int64_t total = (int64_t)a.E * a.kw.K;
+    cudaError_t err = cudaSuccess;
+    adc_tape t0 = {};
+    const adc_tape &tp = tape ? *tape : t0;
+    if (tape == nullptr && !explicit_kw) {
+        int L = a.n_lanes > 0 ? a.n_lanes : 8;
+        switch (L) {
+            case 1: err = launch_lanes<1>(a, s, launches); break;
+            case 2: err = launch_lanes<2>(a, s, launches); break;
+            case 4: err = launch_lanes<4>(a, s, launches); break;
+            case 8: err = launch_lanes<8>(a, s, launches); break;
+            case 16: err = launch_lanes<16>(a, s, launches); break;
+            case 32: err = launch_lanes<32>(a, s, launches); break;
+            default: return cudaErrorInvalidValue;
+        }
+    } else if (tape == nullptr) {
+        auto kern = adc_units_kernel<PhiloxSrc, true>;
+        kern<<<(unsigned)grid_for(kern, 128, total), 128, 0, s>>>(a, tp);
+        ++*launches;
+        err = cudaGetLastError();
+    } else if (explicit_kw) {
+        auto kern = adc_units_kernel<TapeSrc, true>;
+        kern<<<(unsigned)grid_for(kern, 128, total), 128, 0, s>>>(a, tp);
+        ++*launches;
+        err = cudaGetLastError();
+    } else {
+        auto kern = adc_units_kernel<TapeSrc, false>;
+        kern<<<(unsigned)grid_for(kern, 128, total), 128, 0, s>>>(a, tp);
+        ++*launches;
+        err = cudaGetLastError();
+    }
+    if (err != cudaSuccess) return err;
+    // exact serial walk of the queued envs (reads the count on the device; exits at once if 0)
+    if (tape == nullptr) {
+        auto kern = adc_serial_kernel<PhiloxSrc>;
+        kern<<<(unsigned)grid_for(kern, 64, a.E), 64, 0, s>>>(a, tp);
+    } else {
+        auto kern = adc_serial_kernel<TapeSrc>;
+        kern<<<(unsigned)grid_for(kern, 64, a.E), 64, 0, s>>>(a, tp);
+    }
+    ++*launches;
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    adc_serial_count_reset_kernel<<<1, 1, 0, s>>>(a.scratch.serial_count);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day,
+                              cudaStream_t s, int64_t *launches)
+{
+    adc_reset_envs_kernel<<<(E + 255) / 256, 256, 0, s>>>(E, mask, cum_profit, day);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace adc

@@ -1,0 +1,230 @@
+"""Keyword parameter tables and the reset-time keyword factories.
+
+Host-side (numpy) mirror of the reference's keyword sampling, consuming the env's numpy
+Generator in exactly the reference's order so that ``reset(seed=s)`` yields the same keywords:
+
+* :func:`sample_random_keywords`  <- ``adcraft/gymnasium_kw_utils.py:113-156`` (ExplicitKeyword)
+* :func:`sample_implicit_keywords_from_quantiles` <- ``gymnasium_kw_utils.py:260-349`` +
+  ``pull_quantiles_data/quantiles_to_keywords.py:13-28`` + the in-memory equivalent of
+  ``experiment_utils/experiment_quantiles.py:7-84`` (the CSV round trip is skipped; the same
+  singleton quantile rows are built directly, or a user ``load_quant_func`` is called).
+
+The table is SoA float64: ``((vol_mean, vol_std), loc|intercept, scale|slope, bctr, sctr,
+mean_rev, std_rev)`` of ``gymnasium_kw_utils.py:20-28``; for implicit keywords ``p2`` holds the
+Laplace *scale* (the reference's params tuple stores ``1/scale``, utils:195).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+
+IMPLICIT, EXPLICIT = 0, 1
+PARAM_NAMES = ("vol_mean", "vol_std", "p1", "p2", "ctr", "cvr", "rev_mean", "rev_std")
+
+# experiment_quantiles.py:16-25
+GENERIC_SPARSITY_QUANTILES = {
+    "vol": [64, 128, 256],
+    "ave_cpc": [0.3, 0.55, 1],
+    "std_cpc": [0.01, 0.15, 0.3],
+    "bctr": [0.1, 0.5, 0.9],
+    "sctr": [0.1, 0.5, 0.9],
+    "rpsc": [0.3, 1.0, 1.5],
+    "std_rpsc": [0.01, 0.15, 0.3],
+}
+
+
+@dataclass
+class KeywordTable:
+    kind: int
+    vol_mean: np.ndarray
+    vol_std: np.ndarray
+    p1: np.ndarray
+    p2: np.ndarray
+    ctr: np.ndarray
+    cvr: np.ndarray
+    rev_mean: np.ndarray
+    rev_std: np.ndarray
+    impression_thresh: float = 0.05  # gymnasium_kw_utils.py:81
+
+    def __post_init__(self):
+        for n in PARAM_NAMES:
+            setattr(self, n, np.ascontiguousarray(getattr(self, n), dtype=np.float64))
+        shapes = {getattr(self, n).shape for n in PARAM_NAMES}
+        assert len(shapes) == 1, f"inconsistent keyword parameter shapes: {shapes}"
+
+    @property
+    def K(self) -> int:
+        return self.vol_mean.shape[-1]
+
+    @property
+    def per_env(self) -> bool:
+        return self.vol_mean.ndim == 2
+
+    @property
+    def env_stride(self) -> int:
+        return self.K if self.per_env else 0
+
+    def env(self, e: int) -> "KeywordTable":
+        """The keyword set of env e as a shared ([K]) table."""
+        if not self.per_env:
+            return self
+        return KeywordTable(self.kind, *[getattr(self, n)[e] for n in PARAM_NAMES],
+                            impression_thresh=self.impression_thresh)
+
+    def describe(self, e: int = 0) -> str:
+        """``repr_all_params`` (gymnasium_kw_utils.py:352-380) for env e."""
+        t = self.env(e)
+        names = ["volume", "imp_intercept", "imp_slope", "bctr", "sctr", "mean revenue", "std revenue"]
+        rows = []
+        for k in range(t.K):
+            p2 = t.p2[k] if t.kind == EXPLICIT else 1.0 / t.p2[k]
+            vm, vs = t.vol_mean[k], t.vol_std[k]
+            if t.kind == IMPLICIT and vm == int(vm) and vs == int(vs):
+                vol = (int(vm), int(vs))
+            else:
+                vol = (float(vm), float(vs))
+            vals = [vol, float(t.p1[k]), float(p2), float(t.ctr[k]), float(t.cvr[k]),
+                    float(t.rev_mean[k]), float(t.rev_std[k])]
+            rows.append(f"kw{k} params:\n " + ",   ".join(f"{n}: {v}" for n, v in zip(names, vals)))
+        return "\n".join(rows)
+
+
+def _stack(tables) -> KeywordTable:
+    t0 = tables[0]
+    if len(tables) == 1:
+        return t0
+    return KeywordTable(t0.kind, *[np.stack([getattr(t, n) for t in tables]) for n in PARAM_NAMES],
+                        impression_thresh=t0.impression_thresh)
+
+
+def _consume_constructor_draws(rng: np.random.Generator, K: int) -> None:
+    """Keyword.__init__ probes its reward sampler with rds(2), rds(5), rds(5)
+    (synthetic_kw_classes.py:337-339), i.e. 12 normals per keyword from the shared Generator.
+    They do not influence the parameters; consumed only to leave `rng` where the reference does."""
+    for _ in range(K):
+        rng.normal(0.0, 1.0, 2)
+        rng.normal(0.0, 1.0, 5)
+        rng.normal(0.0, 1.0, 5)
+
+
+def _sample_random_one(K: int, rng: np.random.Generator) -> KeywordTable:
+    # gymnasium_kw_utils.py:129-140, same draw order
+    v_mean = (2 ** rng.beta(2, 5, size=K) * 15 - 1).astype(int)
+    v_std = rng.random(size=K) * 0.5 * (v_mean + 1)
+    sctr = rng.beta(5, 2, size=K)
+    intercept = rng.random(size=K) * 1.5
+    mean_rev = rng.beta(2, 5, size=K) * 1.5
+    std_rev = rng.beta(2, 5, size=K) * mean_rev
+    bctr = rng.beta(2, 5, size=K)
+    slope = rng.beta(5, 5, size=K) * 25
+    _consume_constructor_draws(rng, K)
+    # Keyword._buyside_ctr_init / _sellside_paid_ctr_init probify the rates (classes:405-407)
+    return KeywordTable(EXPLICIT, v_mean, v_std, intercept, slope, np.clip(bctr, 0.0, 1.0),
+                        np.clip(sctr, 0.0, 1.0), mean_rev, std_rev)
+
+
+def sample_random_keywords(num_keywords: int, rng: np.random.Generator,
+                           num_envs: Optional[int] = None) -> KeywordTable:
+    """ExplicitKeyword parameters (default env); ``num_envs`` draws one set per env in turn."""
+    n = 1 if num_envs is None else int(num_envs)
+    out = _stack([_sample_random_one(num_keywords, rng) for _ in range(n)])
+    if num_envs is not None and not out.per_env:
+        out = KeywordTable(out.kind, *[getattr(out, n_)[None] for n_ in PARAM_NAMES],
+                           impression_thresh=out.impression_thresh)
+    return out
+
+
+def sample_from_quantiles(n, num_buckets, mins, meds, maxs, rng) -> np.ndarray:
+    """quantiles_to_keywords.py:13-28: uniform bucket, then piecewise-linear interpolation."""
+    buckets = rng.integers(low=0, high=num_buckets, size=(n,))
+    samples = rng.random(size=(n,))
+    mins, meds, maxs = (np.asarray(a, dtype=np.float64) for a in (mins, meds, maxs))
+    lo, mid, hi = mins[buckets], meds[buckets], maxs[buckets]
+    # np.interp(q, [0, .5, 1], [lo, mid, hi]) evaluated per element
+    out = np.where(samples <= 0.5, lo + (mid - lo) * (samples / 0.5),
+                   mid + (hi - mid) * ((samples - 0.5) / 0.5))
+    exact = np.array([np.interp(q, [0.0, 0.5, 1.0], [a, b, c])
+                      for q, a, b, c in zip(samples, lo, mid, hi)]) if n <= 4096 else out
+    return exact
+
+
+def quantile_rows_from_config(keyword_config: Dict) -> Dict[str, np.ndarray]:
+    """Quantile table as a dict of columns ``count_/min_/median_/max_<param>``.
+
+    Accepts (a) a user ``load_quant_func`` (+ optional ``make_quant_func``) exactly like the
+    reference (utils:281-289), (b) an explicit ``quantile_table`` mapping, or (c) the experiment
+    configs' ``mean_volume`` / ``conversion_rate`` pair (experiment_quantiles.py:37-47)."""
+    load = keyword_config.get("load_quant_func")
+    if load is not None:
+        if not keyword_config.get("quantiles_folder", False):
+            make = keyword_config.get("make_quant_func")
+            if make is not None:
+                make(keyword_config)
+        data = load(keyword_config)
+        assert data is not None, "Invalid quantile parameters specified in keyword_config for data"
+        return {c: np.asarray(data[c], dtype=np.float64) for c in data.columns if c.split("_")[0] in
+                ("count", "min", "median", "max")}
+    if "quantile_table" in keyword_config:
+        return {k: np.atleast_1d(np.asarray(v, dtype=np.float64))
+                for k, v in keyword_config["quantile_table"].items()}
+    d = {k: list(v) for k, v in GENERIC_SPARSITY_QUANTILES.items()}
+    if "mean_volume" in keyword_config:
+        v = keyword_config["mean_volume"]
+        d["vol"] = [v, v, v]
+    if "conversion_rate" in keyword_config:
+        c = keyword_config["conversion_rate"]
+        d["sctr"] = [c, c, c]
+    if "clickthrough_rate" in keyword_config:
+        c = keyword_config["clickthrough_rate"]
+        d["bctr"] = [c, c, c]
+    cols = {}
+    for name, (lo, mid, hi) in d.items():  # singleton_mmm_dict (experiment_quantiles.py:7-14)
+        cols[f"count_{name}"] = np.array([3.0])
+        cols[f"min_{name}"] = np.array([float(lo)])
+        cols[f"median_{name}"] = np.array([float(mid)])
+        cols[f"max_{name}"] = np.array([float(hi)])
+    return cols
+
+
+def _sample_implicit_one(K: int, rng: np.random.Generator, data: Dict[str, np.ndarray],
+                         no_volume_prob: float) -> KeywordTable:
+    nrows = len(data["min_vol"])
+    v = sample_from_quantiles(K, nrows, data["min_vol"], data["median_vol"], data["max_vol"], rng)
+    vol_mean = np.zeros(K)
+    vol_std = np.zeros(K)
+    for i in range(K):  # utils:296-309: the condition's draw comes first, then the std's draw
+        has_vol = rng.random() > no_volume_prob and not np.isnan(v[i])
+        if has_vol:
+            vol_mean[i] = int(v[i])
+            vol_std[i] = int(1 + rng.random() * 0.5 * v[i])
+        else:
+            vol_mean[i] = 0
+            vol_std[i] = rng.random() * 0.5
+    cols = []
+    for param in ["ave_cpc", "std_cpc", "bctr", "sctr", "rpsc", "std_rpsc"]:
+        keep = data[f"count_{param}"] > 0
+        vals = sample_from_quantiles(K, int(keep.sum()), data[f"min_{param}"][keep],
+                                     data[f"median_{param}"][keep], data[f"max_{param}"][keep], rng)
+        if param.startswith("std_"):  # un-normalise: multiplier on the preceding average
+            vals = np.maximum(0.01, vals * cols[-1])
+        cols.append(vals)
+    loc, scale, bctr, sctr, rev, rev_std = cols
+    _consume_constructor_draws(rng, K)
+    return KeywordTable(IMPLICIT, vol_mean, vol_std, loc, scale, np.clip(bctr, 0.0, 1.0),
+                        np.clip(sctr, 0.0, 1.0), rev, rev_std)
+
+
+def sample_implicit_keywords_from_quantiles(num_keywords: int, rng: np.random.Generator,
+                                            keyword_config: Dict,
+                                            num_envs: Optional[int] = None) -> KeywordTable:
+    """ImplicitKeyword parameters with one competitor (utils:260-349, :159-195)."""
+    data = quantile_rows_from_config(keyword_config)
+    p0 = keyword_config.get("no_vol_prob", 0.0)
+    n = 1 if num_envs is None else int(num_envs)
+    out = _stack([_sample_implicit_one(num_keywords, rng, data, p0) for _ in range(n)])
+    if num_envs is not None and not out.per_env:
+        out = KeywordTable(out.kind, *[getattr(out, n_)[None] for n_ in PARAM_NAMES],
+                           impression_thresh=out.impression_thresh)
+    return out

@@ -1,0 +1,331 @@
+"""VectorBiddingSimulation: E copies of the reference ``BiddingSimulation`` advanced per launch.
+
+Host-side mirror of ``adcraft/gymnasium_kw_env.py:22-363`` with a leading env axis.  The
+constructor keeps the reference's keyword arguments (``keyword_config, num_keywords, budget,
+render_mode, loss_threshold, max_days, updater_params, updater_mask``, env:54-65); ``reset`` /
+``step`` keep their signatures and return tuples (env:160-269, :271-346); observations are the
+same 7-key dict (``gymnasium_kw_utils.py:45-64``) with shapes ``[E, K]`` / ``[E, 1]``.
+
+All arithmetic of ``step`` runs in the CUDA library behind ``include/adcraft_b200.h``; torch
+only owns device memory and streams.  There is no CPU path: constructing the env without a
+CUDA device or without the built library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _capi
+from . import keywords as kwmod
+from .spaces import get_action_space, get_observation_space
+from .tape import DeviceTape
+
+ArrayLike = Union[np.ndarray, torch.Tensor, Sequence[float], float]
+
+DEFAULT_UPDATER_PARAMS = [["vol", 0.03], ["ctr", 0.03], ["cvr", 0.03]]
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class VectorBiddingSimulation:
+    """E independent bidding environments on one GPU (or one rank's shard of them)."""
+
+    metadata = {"render_modes": ["ansi"]}
+
+    def __init__(
+        self,
+        num_envs: int,
+        keyword_config: Optional[Dict] = None,
+        num_keywords: int = 10,
+        budget: float = 1000.0,
+        render_mode: Optional[str] = None,
+        loss_threshold: float = 10000.0,
+        max_days: int = 60,
+        updater_params: List[List] = DEFAULT_UPDATER_PARAMS,
+        updater_mask: Optional[List[bool]] = None,
+        *,
+        device: Union[str, torch.device] = "cuda",
+        seed: int = 0,
+        keywords: Optional[kwmod.KeywordTable] = None,
+        shared_keywords: bool = True,
+        obs_dtype: torch.dtype = torch.float32,
+        env_base: int = 0,
+        n_lanes: int = 0,
+        budget_alias: bool = False,
+        autoreset: bool = True,
+        **kwargs,
+    ) -> None:
+        assert render_mode is None or render_mode in self.metadata["render_modes"], (
+            f"Specified render_mode of ({render_mode}) is not in the allowed options of (ansi)")
+        self._lib = _capi.load()  # raises if the CUDA library is missing
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available() or self._lib.adc_device_count() < 1:
+            raise _capi.AdcError("adcraft_b200 needs a CUDA device; there is no CPU fallback")
+        self.num_envs = int(num_envs)
+        self.keyword_config = keyword_config
+        self.num_keywords = int(num_keywords)
+        self.budget = float(budget)
+        self.render_mode = render_mode
+        self.loss_threshold = float(loss_threshold)
+        self.max_days = int(max_days)
+        self.updater_params = updater_params
+        self.updater_mask = None
+        self.num_updates = 0
+        self.seed = int(seed)
+        self.env_base = int(env_base)
+        self.n_lanes = int(n_lanes)
+        self.budget_alias = bool(budget_alias)
+        self.autoreset = bool(autoreset)
+        self.shared_keywords = bool(shared_keywords)
+        self.obs_dtype = obs_dtype
+        assert obs_dtype in (torch.float32, torch.float64)
+        self.action_space = get_action_space(self.num_keywords)
+        self.observation_space = get_observation_space(self.num_keywords, self.budget)
+        self.single_action_space = self.action_space
+        self.single_observation_space = self.observation_space
+        self.np_random: Optional[np.random.Generator] = None
+        self._keywords_given = keywords
+        self.keywords: Optional[kwmod.KeywordTable] = None
+        self._have_keywords = False
+        self._step_count = 0
+        self._alloc()
+        if updater_mask is not None:
+            self.set_updater_mask(updater_mask)
+
+    # ------------------------------------------------------------------ allocation
+    def _alloc(self) -> None:
+        E, K, dev = self.num_envs, self.num_keywords, self.device
+        i32, i64, f64 = torch.int32, torch.int64, torch.float64
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
+        self._out = dict(
+            impressions=z(E, K, dtype=i32), buyside_clicks=z(E, K, dtype=i32),
+            sellside_conversions=z(E, K, dtype=i32),
+            cost=z(E, K, dtype=self.obs_dtype), revenue=z(E, K, dtype=self.obs_dtype),
+            cost_cents=z(E, K, dtype=i64), revenue_cents=z(E, K, dtype=i64),
+            reward=z(E, dtype=f64), cumulative_profit=z(E, dtype=f64), days_passed=z(E, dtype=i32),
+            terminated=z(E, dtype=torch.uint8), truncated=z(E, dtype=torch.uint8),
+            remaining_budget=z(E, dtype=f64))
+        self._state = dict(
+            budget=torch.full((E,), self.budget, dtype=f64, device=dev),
+            cum_profit=z(E, dtype=f64), day=z(E, dtype=i32))
+        self._scratch = dict(
+            serial_list=z(E, dtype=i32), serial_count=z(1, dtype=i32), env_profit=z(E, dtype=i64),
+            env_cost=z(E, dtype=i64), env_done=z(E, dtype=i32), unit_cost_f64=z(E, K, dtype=f64))
+        self._bids_dev = {torch.float32: z(E, K, dtype=torch.float32), torch.float64: z(E, K, dtype=f64)}
+        self._budget_dev = {torch.float32: z(E, dtype=torch.float32), torch.float64: z(E, dtype=f64)}
+        self._mask_dev: Optional[torch.Tensor] = None
+        self._host: Dict[str, torch.Tensor] = {}
+        self._args = _capi.StepArgs()
+
+    # ------------------------------------------------------------------ keywords / reset
+    def set_updater_mask(self, new_updater_mask: List[bool]) -> None:
+        """Replace updater mask (env:105-112)."""
+        assert len(new_updater_mask) == self.num_keywords, (
+            f"Updater mask length ({len(new_updater_mask)})\n"
+            + f"must match number of keywords ({self.num_keywords}) to be applied.")
+        self.updater_mask = [bool(m) for m in new_updater_mask]
+        self.num_updates = int(np.sum(self.updater_mask))
+        self._mask_dev = torch.tensor(self.updater_mask, dtype=torch.uint8, device=self.device)
+        if self.keywords is not None and self.keywords.env_stride == 0:
+            self._install_keywords(self.keywords)  # drift needs per-env parameter copies
+
+    def _install_keywords(self, table: kwmod.KeywordTable) -> None:
+        E, K = self.num_envs, self.num_keywords
+        assert table.K == K, f"keyword table has K={table.K}, env has {K}"
+        per_env = table.per_env or self.updater_mask is not None
+        cols = {}
+        for name in kwmod.PARAM_NAMES:
+            a = np.asarray(getattr(table, name), dtype=np.float64)
+            if per_env and a.ndim == 1:
+                a = np.broadcast_to(a, (E, K))
+            if a.ndim == 2:
+                assert a.shape == (E, K), f"{name}: expected {(E, K)}, got {a.shape}"
+            cols[name] = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        self._kw_dev = cols
+        self._kw_stride = K if per_env else 0
+        self.keywords = table
+        self.kind = table.kind
+        self._have_keywords = True
+
+    def keyword_params(self) -> Dict[str, np.ndarray]:
+        """Current (possibly drifted) keyword parameters, host copies."""
+        return {n: t.cpu().numpy() for n, t in self._kw_dev.items()}
+
+    def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
+        """Reset every env (env:271-346).  Keywords are re-sampled when a seed is given or none
+        exist yet; without a seed the (drifted) keywords persist, as in the reference."""
+        if seed is not None or self.np_random is None:
+            self.np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        if seed is not None or not self._have_keywords:
+            if self._keywords_given is not None:
+                table = self._keywords_given
+            elif self.keyword_config is not None:
+                table = kwmod.sample_implicit_keywords_from_quantiles(
+                    self.num_keywords, self.np_random, self.keyword_config,
+                    num_envs=None if self.shared_keywords else self.num_envs)
+            else:
+                table = kwmod.sample_random_keywords(
+                    self.num_keywords, self.np_random,
+                    num_envs=None if self.shared_keywords else self.num_envs)
+            self._install_keywords(table)
+            if seed is not None:
+                self.seed = int(seed)
+        if options:
+            self.max_days = options.get("max_days", self.max_days)
+            rm = options.get("render_mode", self.render_mode)
+            if rm is None or rm in self.metadata["render_modes"]:
+                self.render_mode = rm
+            self.loss_threshold = options.get("loss_threshold", self.loss_threshold)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _capi.check(self._lib.adc_reset_envs(
+            self.num_envs, None, self._state["cum_profit"].data_ptr(), self._state["day"].data_ptr(),
+            C.c_void_p(stream)))
+        for k in ("impressions", "buyside_clicks", "sellside_conversions", "cost", "revenue",
+                  "cumulative_profit", "days_passed", "reward"):
+            self._out[k].zero_()
+        return self._obs(), {"keyword_params": self.keywords.describe()}
+
+    # ------------------------------------------------------------------ step
+    def _obs(self) -> Dict[str, torch.Tensor]:
+        o = self._out
+        return dict(
+            impressions=o["impressions"], buyside_clicks=o["buyside_clicks"], cost=o["cost"],
+            sellside_conversions=o["sellside_conversions"], revenue=o["revenue"],
+            cumulative_profit=o["cumulative_profit"].view(-1, 1),
+            days_passed=o["days_passed"].view(-1, 1))
+
+    def _stage(self, x: ArrayLike, store: Dict[torch.dtype, torch.Tensor], shape) -> torch.Tensor:
+        """Bring an action array onto the device (f32/f64 kept) without a per-step allocation."""
+        if isinstance(x, torch.Tensor) and x.device == self.device and x.is_contiguous() \
+                and x.dtype in store and tuple(x.shape) == tuple(shape):
+            return x
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(np.asarray(x))
+        if x.dtype not in store:
+            x = x.to(torch.float64 if x.dtype == torch.float64 else torch.float32)
+        dst = store[x.dtype]
+        dst.copy_(x.reshape(shape) if x.numel() == dst.numel() else x.expand(shape), non_blocking=True)
+        return dst
+
+    def _fill_args(self, bids: torch.Tensor, budget: Optional[torch.Tensor], force_serial: bool):
+        a, o, s, st = self._args, self._out, self._scratch, self._state
+        E, K = self.num_envs, self.num_keywords
+        a.E, a.env_base, a.step, a.seed = E, self.env_base, self._step_count, self.seed
+        a.n_lanes, a.budget_alias = self.n_lanes, int(self.budget_alias)
+        a.autoreset, a.force_serial = int(self.autoreset), int(force_serial)
+        kw = a.kw
+        kw.kind, kw.K, kw.env_stride = self.kind, K, self._kw_stride
+        for n in kwmod.PARAM_NAMES:
+            setattr(kw, n, self._kw_dev[n].data_ptr())
+        kw.impression_thresh = self.keywords.impression_thresh
+        a.env.budget, a.env.cum_profit, a.env.day = (st["budget"].data_ptr(), st["cum_profit"].data_ptr(),
+                                                     st["day"].data_ptr())
+        a.env.max_days, a.env.loss_threshold = self.max_days, self.loss_threshold
+        if self.updater_mask is not None:
+            a.drift.mask, a.drift.num_updates = self._mask_dev.data_ptr(), self.num_updates
+            a.drift.mag = (C.c_double * 3)(*[float(p[1]) for p in self.updater_params])
+        else:
+            a.drift.mask, a.drift.num_updates = None, 0
+        a.bids = bids.data_ptr()
+        a.bids_dtype = _capi.F64 if bids.dtype == torch.float64 else _capi.F32
+        a.budget_in = _ptr(budget)
+        out = a.out
+        out.impressions, out.clicks = o["impressions"].data_ptr(), o["buyside_clicks"].data_ptr()
+        out.conversions = o["sellside_conversions"].data_ptr()
+        out.cost, out.revenue = o["cost"].data_ptr(), o["revenue"].data_ptr()
+        out.float_dtype = _capi.F64 if self.obs_dtype == torch.float64 else _capi.F32
+        out.cost_cents, out.revenue_cents = o["cost_cents"].data_ptr(), o["revenue_cents"].data_ptr()
+        out.reward, out.obs_cum_profit = o["reward"].data_ptr(), o["cumulative_profit"].data_ptr()
+        out.obs_days = o["days_passed"].data_ptr()
+        out.terminated, out.truncated = o["terminated"].data_ptr(), o["truncated"].data_ptr()
+        out.remaining_budget = o["remaining_budget"].data_ptr()
+        sc = a.scratch
+        for n in ("serial_list", "serial_count", "env_profit", "env_cost", "env_done", "unit_cost_f64"):
+            setattr(sc, n, s[n].data_ptr())
+        return a
+
+    def _prepare(self, action: Dict[str, ArrayLike]):
+        assert self._have_keywords, "reset required, need to generate keywords to bid on"
+        E, K = self.num_envs, self.num_keywords
+        bids = self._stage(action["keyword_bids"], self._bids_dev, (E, K))
+        budget = action.get("budget") if isinstance(action, dict) else None
+        if budget is not None:
+            budget = self._stage(budget, self._budget_dev, (E,))
+            if budget.dtype != bids.dtype:  # one dtype tag covers both in the ABI
+                budget = self._stage(budget.to(bids.dtype), self._budget_dev, (E,))
+        return bids, budget
+
+    def step(self, action: Dict[str, ArrayLike], *, force_serial: bool = False):
+        """One env step for all E envs (env:160-269).  Returns device tensors."""
+        bids, budget = self._prepare(action)
+        a = self._fill_args(bids, budget, force_serial)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _capi.check(self._lib.adc_step_philox(C.byref(a), C.c_void_p(stream)))
+        self._step_count += 1
+        return self._result()
+
+    def step_replay(self, action: Dict[str, ArrayLike], tape: DeviceTape, *, force_serial: bool = False):
+        """Parity mode: the same step fed by pre-drawn volumes / bids / uniforms / revenues."""
+        bids, budget = self._prepare(action)
+        a = self._fill_args(bids, budget, force_serial)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        t = tape.c_struct()
+        _capi.check(self._lib.adc_step_replay(C.byref(a), C.byref(t), C.c_void_p(stream)))
+        self._step_count += 1
+        return self._result()
+
+    def _result(self):
+        o = self._out
+        return (self._obs(), o["reward"], o["terminated"].view(torch.bool),
+                o["truncated"].view(torch.bool), {"step": self._step_count})
+
+    # ------------------------------------------------------------------ host round trip (e2e)
+    def step_host(self, bids_host: torch.Tensor, budget_host: Optional[torch.Tensor] = None):
+        """``step`` with HOST buffers: pinned host bids in, pinned host observations out.
+
+        This is the call a CPU-side RL loop makes; the H2D and D2H copies are part of it.
+        Returns a dict of pinned host tensors (valid until the next call)."""
+        action = {"keyword_bids": bids_host}
+        if budget_host is not None:
+            action["budget"] = budget_host
+        obs, reward, term, trunc, _ = self.step(action)
+        if not self._host:
+            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            for k, v in obs.items():
+                self._host[k] = pin(v)
+            self._host["reward"] = pin(reward)
+            self._host["terminated"] = pin(self._out["terminated"])
+            self._host["truncated"] = pin(self._out["truncated"])
+        for k, v in obs.items():
+            self._host[k].copy_(v, non_blocking=True)
+        self._host["reward"].copy_(reward, non_blocking=True)
+        self._host["terminated"].copy_(self._out["terminated"], non_blocking=True)
+        self._host["truncated"].copy_(self._out["truncated"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._host
+
+    def host_bytes_per_step(self):
+        """(h2d, d2h) bytes moved by step_host for this shape."""
+        E, K = self.num_envs, self.num_keywords
+        fb = 8 if self.obs_dtype == torch.float64 else 4
+        return E * K * 4, E * K * (3 * 4 + 2 * fb) + E * (8 + 4 + 8 + 1 + 1)
+
+    # ------------------------------------------------------------------ misc reference API
+    def render(self) -> Optional[str]:
+        if self.render_mode == "ansi":
+            r = self._out["reward"]
+            return (f"Time step: {int(self._out['days_passed'].max())}/{self.max_days},   "
+                    f"Mean profit per env in step: {float(r.mean()):.2f}\n")
+        return None
+
+    def close(self) -> None:
+        pass
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.adc_launch_count(0))

@@ -1,0 +1,181 @@
+/* adcraft_b200 -- C ABI of the B200-native BiddingSimulation.step hot path.
+ *
+ * This header is the drop-in boundary.  The reference (Mikata-Project/adcraft) crosses one
+ * FFI on this path: the PyO3 module `adcraft.rust` (src/lib.rs:14-278), called per keyword and
+ * per lane from the Python loops in adcraft/bidding_simulation.py:170-234.  On the GPU the whole
+ * loop nest moves behind the boundary, so the entry points below replace, at batch
+ * granularity (E envs x K keywords per call):
+ *
+ *   adc_step_philox   <- BiddingSimulation.step            adcraft/gymnasium_kw_env.py:160-269
+ *                        simulate_epoch_of_bidding_on_campaign  adcraft/bidding_simulation.py:170-234
+ *                        simulate_epoch_of_bidding              adcraft/bidding_simulation.py:44-120
+ *                        ImplicitKeyword.auction / nth_price_auction
+ *                                                     adcraft/synthetic_kw_classes.py:623-646,
+ *                                                     adcraft/synthetic_kw_helpers.py:116-180
+ *                        ExplicitKeyword.auction           adcraft/synthetic_kw_classes.py:493-538
+ *                        rust.nonneg_int_normal_sampler    src/lib.rs:245-248,314-325
+ *                        rust.binomial_impressions         src/lib.rs:69-76
+ *                        rust.threshold_sigmoid            src/lib.rs:92-105
+ *                        rust.cost_create                  src/lib.rs:53-67
+ *                        rust.sum_list/sum_array/sum_array_bool  src/lib.rs:107-127
+ *                        update_keywords (drift)           adcraft/gymnasium_kw_env.py:114-158
+ *   adc_step_replay   <- the same path, fed pre-drawn volumes / competitor bids / uniforms /
+ *                        revenues (parity mode; the reference's RNG is unseedable, src/lib.rs:316-320)
+ *   adc_reset_envs    <- BiddingSimulation.reset (state part) adcraft/gymnasium_kw_env.py:326-329
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ or torch types.
+ *   - every array pointer is a CALLER-OWNED DEVICE pointer unless its name ends in _host;
+ *     the library allocates nothing and keeps no state between calls.
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*); they return after
+ *     enqueueing.  Return value: 0 on success, a negative adc_status otherwise, with a
+ *     thread-local message available from adc_last_error().  Nothing throws across the ABI.
+ *   - money is carried in integer cents inside the kernels (competitor bids, costs and revenues
+ *     are cent-rounded in the reference: synthetic_kw_helpers.py:68-70,108-113); float outputs
+ *     are cents/100 converted once.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     ADC_ERR_NO_DEVICE.
+ */
+#ifndef ADCRAFT_B200_H
+#define ADCRAFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADC_ABI_VERSION 1
+#define ADC_SUBSTEPS 24 /* adcraft/bidding_simulation.py:213 */
+
+typedef enum adc_status {
+    ADC_OK = 0,
+    ADC_ERR_INVALID = -1,   /* bad argument (null pointer, size, enum)       */
+    ADC_ERR_NO_DEVICE = -2, /* no CUDA device / driver                        */
+    ADC_ERR_CUDA = -3,      /* a CUDA call or launch failed                   */
+    ADC_ERR_UNSUPPORTED = -4
+} adc_status;
+
+enum { ADC_IMPLICIT = 0, ADC_EXPLICIT = 1 };  /* keyword kind (synthetic_kw_classes.py:457,578) */
+enum { ADC_F32 = 0, ADC_F64 = 1 };            /* dtype tags for bids / float outputs             */
+
+/* Keyword parameters, SoA float64 (gymnasium_kw_utils.py:20-28).  env_stride = 0: one keyword set
+ * [K] shared by every env; env_stride = K: per-env sets [E,K] (required when drift is on).
+ * vol_mean, ctr, cvr are updated in place by the drift. */
+typedef struct adc_keywords {
+    int32_t kind;
+    int32_t K;
+    int64_t env_stride;
+    double *vol_mean;
+    const double *vol_std;   /* also the drift scale "init_volumes" (gymnasium_kw_env.py:136-137) */
+    const double *p1;        /* implicit: Laplace loc   | explicit: impression_bid_intercept */
+    const double *p2;        /* implicit: Laplace scale | explicit: impression_slope         */
+    double *ctr;
+    double *cvr;
+    const double *rev_mean;
+    const double *rev_std;
+    double impression_thresh; /* explicit only (0.05, gymnasium_kw_utils.py:81) */
+} adc_keywords;
+
+/* Per-env state [E] (gymnasium_kw_env.py:80,327-328). */
+typedef struct adc_env_state {
+    double *budget;      /* persisted budget ("this timestep and onward", env:197-199) */
+    double *cum_profit;
+    int32_t *day;
+    int32_t max_days;
+    double loss_threshold;
+} adc_env_state;
+
+/* Drift (update_keywords, env:114-158).  mask == NULL: stationary. */
+typedef struct adc_drift {
+    const uint8_t *mask;  /* [K] */
+    int32_t num_updates;  /* sum(mask): zip() truncation, only keywords < num_updates considered */
+    double mag[3];        /* updater_params: vol, ctr, cvr half-widths */
+} adc_drift;
+
+/* Outputs of one step.  [E,K] unless noted; optional pointers may be NULL. */
+typedef struct adc_step_out {
+    int32_t *impressions;
+    int32_t *clicks;        /* buyside_clicks        */
+    int32_t *conversions;   /* sellside_conversions  */
+    void *cost;             /* float_dtype           */
+    void *revenue;          /* float_dtype           */
+    int32_t float_dtype;    /* ADC_F32 / ADC_F64     */
+    int64_t *cost_cents;    /* REQUIRED exact cents accumulator (explicit keywords: unused, 0) */
+    int64_t *revenue_cents; /* REQUIRED exact cents accumulator                                */
+    double *reward;         /* [E] */
+    double *obs_cum_profit; /* [E] value reported in the observation (before auto-reset) */
+    int32_t *obs_days;      /* [E] */
+    uint8_t *terminated;    /* [E] */
+    uint8_t *truncated;     /* [E] */
+    double *remaining_budget; /* [E] optional: budget left after the day */
+} adc_step_out;
+
+/* Scratch the step needs (caller-owned so that nothing is allocated per call). */
+typedef struct adc_scratch {
+    int32_t *serial_list;   /* [E] envs that need the exact serial budget walk              */
+    int32_t *serial_count;  /* [1] must be 0 on entry; left at 0 on exit                    */
+    int64_t *env_profit;    /* [E] per-env profit cents accumulator, 0 on entry and on exit */
+    int64_t *env_cost;      /* [E] per-env cost cents accumulator,   0 on entry and on exit */
+    int32_t *env_done;      /* [E] finished-unit counter,            0 on entry and on exit */
+    double *unit_cost_f64;  /* [E,K] explicit keywords only: un-rounded cost sums (else NULL) */
+} adc_scratch;
+
+typedef struct adc_step_args {
+    int32_t E;              /* envs owned by this call / rank                      */
+    uint32_t env_base;      /* global id of env 0 (Philox counter; rank sharding)  */
+    uint32_t step;          /* global step counter (Philox counter)                */
+    uint64_t seed;          /* Philox key                                          */
+    int32_t n_lanes;        /* threads cooperating on one (env,keyword): 0 = auto, else 1..32 pow2 */
+    int32_t budget_alias;   /* 1: ndarray-budget double charge (bsim:102 + :225), 0: scalar budget */
+    int32_t autoreset;      /* 1: zero cum_profit/day of finished envs after reporting them */
+    int32_t force_serial;   /* 1: run every env through the exact serial kernel (testing)   */
+    adc_keywords kw;
+    adc_env_state env;
+    adc_drift drift;
+    const void *bids;       /* [E,K] dollars, canonicalised to cents inside (env:215) */
+    int32_t bids_dtype;     /* ADC_F32 / ADC_F64 */
+    const void *budget_in;  /* optional [E] dollars, same dtype as bids: rounded to cents and stored */
+    adc_step_out out;
+    adc_scratch scratch;
+} adc_step_args;
+
+/* Replay tape for E envs, consumption order, CSR over the E*K units (u = e*K + k):
+ * stream[off[u] .. off[u+1]).  Streams may be longer than what gets consumed. */
+typedef struct adc_tape {
+    const int32_t *volume;                              /* [E,K]                          */
+    const int64_t *comp_off;  const int32_t *comp_cents;   /* implicit: one per auction      */
+    const int64_t *click_off; const double *u_click;       /* one per click slot             */
+    const int64_t *conv_off;  const double *u_conv;        /* one per accepted click         */
+    const int64_t *rev_off;   const int32_t *rev_cents;    /* one per conversion             */
+    const int32_t *impr;                                /* explicit: [E,K,24] impressions */
+    const int64_t *cost_off;  const double *cost;          /* explicit: one per impression   */
+    const double *drift;                                /* optional [E,3,K] coefficients  */
+} adc_tape;
+
+const char *adc_last_error(void);
+int adc_abi_version(void);
+int adc_device_count(void);
+/* sizeof(adc_step_args) / sizeof(adc_tape) as compiled: lets an FFI binding check its layout. */
+int adc_sizeof_step_args(void);
+int adc_sizeof_tape(void);
+
+/* One free-running env step for E envs (counter-based Philox draws keyed by
+ * (seed, env_base+e, keyword, step)).  Launches: fused lane kernel, then the exact serial kernel
+ * for envs whose budget may bind (skips itself when the list is empty). */
+int adc_step_philox(const adc_step_args *args, void *stream);
+
+/* The same step driven by a pre-drawn tape (parity mode). seed/step in args are ignored. */
+int adc_step_replay(const adc_step_args *args, const adc_tape *tape, void *stream);
+
+/* Reset per-env episode state of the envs with mask[e] != 0 (mask NULL: all). */
+int adc_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day, void *stream);
+
+/* Number of kernel launches issued by this library on the calling thread since the last call
+ * with reset != 0 (bench.py's gpu_launches). */
+int64_t adc_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADCRAFT_B200_H */

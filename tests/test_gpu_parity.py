@@ -1,0 +1,154 @@
+"""GPU parity: the CUDA path (through the C ABI) against the C oracle on the same inputs.
+
+Integer outcomes (impressions, clicks, conversions, flags, exact cents) must be bit-exact;
+float outputs within 1e-6 relative in f64 (1e-4 in f32) as BASELINE.json's north_star states
+(in practice the f64 results are exact: money is integer cents on both sides).
+"""
+import numpy as np
+import pytest
+
+from conftest import make_explicit_table, make_implicit_table, oracle_keywordset
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+RTOL64, RTOL32 = 1e-6, 1e-4
+
+
+def _env(table, E, **kw):
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    env = VectorBiddingSimulation(E, num_keywords=table.K, keywords=table, device="cuda", **kw)
+    env.reset()
+    return env
+
+
+def _oracle_batch(orc, table, E, *, seed, budget, mask=None, alias=False, max_days=60,
+                  loss_threshold=10000.0, step0=0, env_base=0):
+    from adcraft_b200 import keywords as kwm
+    params = {n: getattr(table, n) for n in kwm.PARAM_NAMES}
+    return orc.BatchOracle(table.kind, E, table.K, params, seed=seed, budget=budget, max_days=max_days,
+                           loss_threshold=loss_threshold, drift_mask=mask, env_base=env_base,
+                           step0=step0, budget_alias=alias, impression_thresh=table.impression_thresh)
+
+
+def _compare(obs, reward, term, trunc, ref, env, rtol):
+    for a, b in (("impressions", "impressions"), ("buyside_clicks", "clicks"),
+                 ("sellside_conversions", "conversions")):
+        got = obs[a].cpu().numpy()
+        assert np.array_equal(got, ref[b]), f"{a} differs at {np.argwhere(got != ref[b])[:5]}"
+    assert np.array_equal(term.cpu().numpy().astype(np.uint8), ref["terminated"])
+    assert np.array_equal(trunc.cpu().numpy().astype(np.uint8), ref["truncated"])
+    for a in ("cost", "revenue"):
+        np.testing.assert_allclose(obs[a].cpu().numpy().astype(np.float64), ref[a], rtol=rtol, atol=1e-9)
+    scale = np.abs(ref["cost"]).sum(1) + np.abs(ref["revenue"]).sum(1) + 1.0
+    assert np.all(np.abs(reward.cpu().numpy() - ref["reward"]) <= rtol * scale)
+
+
+@pytest.mark.parametrize("n_lanes", [1, 4, 8, 32])
+@pytest.mark.parametrize("vol,K,E,budget", [(128, 100, 64, 1e5), (16, 37, 50, 1e5), (300, 5, 33, 1e5),
+                                            (64, 20, 40, 25.0), (0, 3, 4, 10.0)])
+def test_philox_implicit_matches_oracle(orc, n_lanes, vol, K, E, budget):
+    rng = np.random.default_rng(vol * 1000 + K)
+    table = make_implicit_table(rng, K, max(vol, 1))
+    if vol == 0:
+        table.vol_mean[:] = 0.0
+        table.vol_std[:] = 0.3
+    env = _env(table, E, seed=4242, budget=budget, n_lanes=n_lanes, obs_dtype=torch.float64, max_days=3)
+    ob = _oracle_batch(orc, table, E, seed=4242, budget=budget, max_days=3)
+    for s in range(5):
+        bids = np.round(rng.uniform(0.05, 1.6, (E, K)), 2)
+        obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda()})
+        ref = ob.step(bids, n_threads=4)
+        _compare(obs, reward, term, trunc, ref, env, RTOL64)
+        assert np.array_equal(env._out["cost_cents"].cpu().numpy(), np.rint(ref["cost"] * 100).astype(np.int64))
+
+
+@pytest.mark.parametrize("alias", [False, True])
+def test_budget_binding_serial_path(orc, alias):
+    rng = np.random.default_rng(7)
+    K, E = 12, 48
+    table = make_implicit_table(rng, K, 96)
+    budgets = rng.choice([0.5, 3.0, 12.0, 40.0, 1e5], size=E)
+    env = _env(table, E, seed=99, budget=1000.0, budget_alias=alias, obs_dtype=torch.float64)
+    ob = _oracle_batch(orc, table, E, seed=99, budget=1000.0, alias=alias)
+    for s in range(4):
+        bids = np.round(rng.uniform(0.2, 1.5, (E, K)), 2)
+        ob.budget[:] = budgets
+        obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda(),
+                                                "budget": torch.from_numpy(budgets).cuda()})
+        ref = ob.step(bids, n_threads=4)
+        _compare(obs, reward, term, trunc, ref, env, RTOL64)
+
+
+def test_force_serial_equals_fast_path(orc):
+    rng = np.random.default_rng(11)
+    K, E = 30, 40
+    table = make_implicit_table(rng, K, 128)
+    bids = torch.from_numpy(np.round(rng.uniform(0.2, 1.5, (E, K)), 2)).cuda()
+    a = _env(table, E, seed=5, budget=1e6, obs_dtype=torch.float64)
+    b = _env(table, E, seed=5, budget=1e6, obs_dtype=torch.float64)
+    for s in range(3):
+        oa = a.step({"keyword_bids": bids})
+        ob_ = b.step({"keyword_bids": bids}, force_serial=True)
+        for k in oa[0]:
+            assert torch.equal(oa[0][k], ob_[0][k]), k
+        assert torch.equal(oa[1], ob_[1])
+
+
+def test_philox_explicit_matches_oracle(orc):
+    rng = np.random.default_rng(3)
+    for (K, E, budget) in [(1, 16, 1000.0), (10, 32, 1000.0), (10, 32, 15.0)]:
+        table = make_explicit_table(rng, K)
+        env = _env(table, E, seed=77, budget=budget, obs_dtype=torch.float64)
+        ob = _oracle_batch(orc, table, E, seed=77, budget=budget)
+        for s in range(4):
+            bids = np.round(rng.uniform(0.01, 3.0, (E, K)), 2)
+            obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda()})
+            ref = ob.step(bids, n_threads=4)
+            _compare(obs, reward, term, trunc, ref, env, RTOL64)
+
+
+def test_drift_matches_oracle(orc):
+    rng = np.random.default_rng(21)
+    K, E = 16, 24
+    table = make_implicit_table(rng, K, 64, E=E)
+    mask = rng.random(K) < 0.7
+    env = _env(table, E, seed=31, budget=1e5, updater_mask=list(mask), obs_dtype=torch.float64)
+    ob = _oracle_batch(orc, table, E, seed=31, budget=1e5, mask=mask)
+    for s in range(6):
+        bids = np.round(rng.uniform(0.2, 1.5, (E, K)), 2)
+        obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda()})
+        ref = ob.step(bids, n_threads=4)
+        _compare(obs, reward, term, trunc, ref, env, RTOL64)
+        cur = env.keyword_params()
+        for n in ("vol_mean", "ctr", "cvr"):
+            assert np.array_equal(cur[n], ob.p[n]), n
+
+
+def test_f32_outputs_and_f32_bids(orc):
+    rng = np.random.default_rng(5)
+    K, E = 25, 32
+    table = make_implicit_table(rng, K, 128)
+    env = _env(table, E, seed=1, budget=1e5, obs_dtype=torch.float32)
+    ob = _oracle_batch(orc, table, E, seed=1, budget=1e5)
+    bids = np.round(rng.uniform(0.2, 1.5, (E, K)), 2)
+    obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids.astype(np.float32)).cuda()})
+    ref = ob.step(bids, n_threads=4)
+    _compare(obs, reward, term, trunc, ref, env, RTOL32)
+    assert obs["cost"].dtype == torch.float32
+
+
+def test_sharding_invariance(orc):
+    """Global env ids key the draws: two shards of 20 envs equal one env batch of 40."""
+    rng = np.random.default_rng(9)
+    K, E = 10, 40
+    table = make_implicit_table(rng, K, 64)
+    bids = np.round(rng.uniform(0.2, 1.5, (E, K)), 2)
+    full = _env(table, E, seed=8, budget=1e5)
+    lo = _env(table, E // 2, seed=8, budget=1e5, env_base=0)
+    hi = _env(table, E // 2, seed=8, budget=1e5, env_base=E // 2)
+    of = full.step({"keyword_bids": torch.from_numpy(bids).cuda()})[0]
+    ol = lo.step({"keyword_bids": torch.from_numpy(bids[: E // 2]).cuda()})[0]
+    oh = hi.step({"keyword_bids": torch.from_numpy(bids[E // 2:]).cuda()})[0]
+    for k in of:
+        assert torch.equal(of[k], torch.cat([ol[k], oh[k]])), k
