@@ -45,6 +45,43 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// Philox with the first round split off: c1 (step), c2 (stream|kw) and c3 (env) are fixed for a
+// whole (env, keyword, step) unit, so half of round 1 is computed once per unit (philox_pre) and
+// the per-draw work is 1 + 2*9 multiplies (philox_from_pre).  Same function as philox4x32_10.
+struct PhiloxPre {
+    uint32_t n0, n1, x3;  // n0 = hi(M1*c2)^c1^k0, n1 = lo(M1*c2), x3 = c3^k1
+};
+
+__device__ __forceinline__ PhiloxPre philox_pre(uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                uint32_t k1)
+{
+    PhiloxPre p;
+    p.n0 = __umulhi(0xCD9E8D57u, c2) ^ c1 ^ k0;
+    p.n1 = 0xCD9E8D57u * c2;
+    p.x3 = c3 ^ k1;
+    return p;
+}
+
+__device__ __forceinline__ uint4 philox_from_pre(uint32_t idx, uint32_t n0, uint32_t n1, uint32_t x3,
+                                                 uint32_t k0, uint32_t k1)
+{
+    uint32_t c0 = n0, c1 = n1;
+    uint32_t c2 = __umulhi(0xD2511F53u, idx) ^ x3;
+    uint32_t c3 = 0xD2511F53u * idx;
+#pragma unroll
+    for (int r = 1; r < 10; ++r) {
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0;
+        c2 = h0 ^ c3 ^ k1;
+        c1 = l1;
+        c3 = l0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 __device__ __forceinline__ uint32_t stream_word(uint32_t stream, uint32_t agent, uint32_t kw)
 {
     return (stream << 28) | (agent << 20) | kw;

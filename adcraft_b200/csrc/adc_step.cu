@@ -371,7 +371,7 @@ __device__ __forceinline__ int unit_done(const adc_step_args &a, int e, long lon
         spend = cents_to_dollars(cost);
     }
     if (a.force_serial || !budget_is_safe(budget, spend, a.budget_alias)) {
-        const int slot = atomicAdd(a.scratch.serial_count, 1);
+        const int slot = atomicAdd(a.scratch.serial_count + (a.step & 1u), 1);
         a.scratch.serial_list[slot] = e;
         return 0;
     }
@@ -396,6 +396,9 @@ adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     const unsigned wl = threadIdx.x & 31u;
     const unsigned gmask = L == 32 ? 0xFFFFFFFFu : (((1u << L) - 1u) << (wl & ~(unsigned)(L - 1)));
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    // the serial-queue counter is double-buffered on the step parity: this step appends to
+    // [step&1]; the other one (read by the previous step's serial kernel) is cleared here.
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
 
     for (int64_t it = 0; it < iters; ++it) {
         const int64_t u = it * n_groups + group;
@@ -479,6 +482,236 @@ adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// hot kernel, warp-flattened: a warp takes a batch of 32 units, and the auctions of all 32 are
+// laid end to end in one index space that the 32 lanes stride through together.  Lanes stay busy
+// whatever the per-unit volumes are (the per-unit volume is N(128, up to 64) in the dense
+// config, which costs the L-threads-per-unit kernel ~30 % of its lanes).  Per-unit sums are
+// formed with ballots / REDUX over the lanes that fall in the same unit.
+// ------------------------------------------------------------------------------------------
+struct __align__(16) FlatUnit {
+    int bid_cents;
+    float loc, scale;
+    uint32_t thr_click;
+    uint32_t thr_conv;
+    uint32_t n0, n1, x3;  // PhiloxPre of the unit's auction stream
+};
+
+struct __align__(16) FlatRev {
+    float mean, sd;
+    int S;
+    uint32_t n0;
+    uint32_t n1, x3, pad0, pad1;
+};
+
+constexpr int kFlatWarps = 8;
+constexpr int kMaxFlatVolume = 1 << 25;  // per-unit cap keeps the batch total inside int32
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, v, off);
+        if (lane >= off) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kFlatWarps * 32)
+adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
+{
+    __shared__ FlatUnit s_unit[kFlatWarps][32];
+    __shared__ FlatRev s_rev[kFlatWarps][32];
+    __shared__ int s_start[kFlatWarps][33];
+    __shared__ unsigned s_cnt[kFlatWarps][32][3];
+    __shared__ unsigned long long s_cost[kFlatWarps][32];
+    __shared__ unsigned long long s_revsum[kFlatWarps][32];
+
+    const int K = a.kw.K;
+    const int64_t total = (int64_t)a.E * K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gwarp = (int64_t)blockIdx.x * kFlatWarps + warp;
+    const int64_t n_warps = (int64_t)gridDim.x * kFlatWarps;
+    const int64_t n_batches = (total + 31) / 32;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const unsigned FULL = 0xFFFFFFFFu;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
+
+    FlatUnit *units = s_unit[warp];
+    FlatRev *revs = s_rev[warp];
+    int *start = s_start[warp];
+
+    for (int64_t batch = gwarp; batch < n_batches; batch += n_warps) {
+        // ---------------- per-unit setup, lane <-> unit ----------------
+        const int64_t u = batch * 32 + lane;
+        const bool valid = u < total;
+        int e = 0, k = 0, V = 0;
+        uint32_t genv = 0;
+        UnitPar p;
+        p.bid_cents = 0; p.loc = 0.f; p.scale = 0.f; p.thr_click = 0; p.thr_conv = 0;
+        p.rev_mean = 0.f; p.rev_sd = 0.f;
+        if (valid) {
+            e = (int)(u / K);
+            k = (int)(u - (int64_t)e * K);
+            genv = a.env_base + (uint32_t)e;
+            p = load_unit_par(a, e, k);
+            const int64_t pi = (int64_t)e * a.kw.env_stride + k;
+            const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)k), genv, k0, k1);
+            const long long v = volume_draw(w.x, a.kw.vol_mean[pi], a.kw.vol_std[pi]);
+            V = (int)(v > kMaxFlatVolume ? kMaxFlatVolume : v);
+        }
+        {
+            const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), genv, k0, k1);
+            FlatUnit fu;
+            fu.bid_cents = p.bid_cents; fu.loc = p.loc; fu.scale = p.scale;
+            fu.thr_click = p.thr_click; fu.thr_conv = p.thr_conv;
+            fu.n0 = pa.n0; fu.n1 = pa.n1; fu.x3 = pa.x3;
+            units[lane] = fu;
+        }
+        const int incl = warp_incl_scan(V, lane);
+        start[lane + 1] = incl;
+        if (lane == 0) start[0] = 0;
+        s_cnt[warp][lane][0] = 0; s_cnt[warp][lane][1] = 0; s_cnt[warp][lane][2] = 0;
+        s_cost[warp][lane] = 0ull;
+        s_revsum[warp][lane] = 0ull;
+        __syncwarp();
+        const int T = __shfl_sync(FULL, incl, 31);
+
+        // ---------------- the batch's auctions, flattened ----------------
+        // Lanes accumulate privately for the unit of lane 0's auction (b0) and for the next one;
+        // the sums are warp-reduced once per unit when b0 advances.  An iteration that spans more
+        // than two units (volumes below 16) sends the far lanes through shared-memory atomics.
+        int b0 = 0;
+        int s_cur = 0, s_nxt = start[1], s_nxt2 = start[2];
+        unsigned cI = 0, cB = 0, cS = 0, nI = 0, nB = 0, nS = 0;
+        unsigned long long cC = 0, nC = 0;
+        auto flush = [&](int bb, unsigned fI, unsigned fB, unsigned fS, unsigned long long fC) {
+            const unsigned tI = __reduce_add_sync(FULL, fI);
+            const unsigned tB = __reduce_add_sync(FULL, fB);
+            const unsigned tS = __reduce_add_sync(FULL, fS);
+            const unsigned lo = __reduce_add_sync(FULL, (unsigned)(fC & 0xFFFFFFull));
+            const unsigned hi = __reduce_add_sync(FULL, (unsigned)(fC >> 24));
+            if (lane == 0) {
+                atomicAdd(&s_cnt[warp][bb][0], tI);
+                atomicAdd(&s_cnt[warp][bb][1], tB);
+                atomicAdd(&s_cnt[warp][bb][2], tS);
+                atomicAdd(&s_cost[warp][bb], (unsigned long long)lo + ((unsigned long long)hi << 24));
+            }
+        };
+        for (int base = 0; base < T; base += 32) {
+            while (s_nxt <= base) {  // warp-uniform: lane 0's auction moved to the next unit
+                flush(b0, cI, cB, cS, cC);
+                cI = nI; cB = nB; cS = nS; cC = nC;
+                nI = nB = nS = 0; nC = 0;
+                ++b0;
+                s_cur = s_nxt;
+                s_nxt = s_nxt2;
+                s_nxt2 = b0 + 2 <= 32 ? start[b0 + 2] : 0x7FFFFFFF;
+            }
+            const int i = base + lane;
+            const bool act = i < T;
+            const bool in_next = i >= s_nxt;
+            int b = b0 + (in_next ? 1 : 0);
+            int s_b = in_next ? s_nxt : s_cur;
+            if (act && i >= s_nxt2) {  // rare: more than two units inside one 32-auction stripe
+                while (i >= start[b + 1]) ++b;
+                s_b = start[b];
+            }
+            const FlatUnit fu = units[b];
+            const uint4 w = philox_from_pre((uint32_t)(i - s_b), fu.n0, fu.n1, fu.x3, k0, k1);
+            const int c = laplace_cents(w.x, fu.loc, fu.scale);
+            const bool win = act && fu.bid_cents > c;
+            const bool clk = win && (w.y <= fu.thr_click);
+            const bool cnv = clk && (w.z <= fu.thr_conv);
+            const unsigned cc = clk ? (unsigned)c : 0u;
+            if (b == b0) {
+                cI += win; cB += clk; cS += cnv; cC += cc;
+            } else if (b == b0 + 1) {
+                nI += win; nB += clk; nS += cnv; nC += cc;
+            } else if (win) {
+                atomicAdd(&s_cnt[warp][b][0], 1u);
+                if (clk) {
+                    atomicAdd(&s_cnt[warp][b][1], 1u);
+                    atomicAdd(&s_cost[warp][b], (unsigned long long)cc);
+                }
+                if (cnv) atomicAdd(&s_cnt[warp][b][2], 1u);
+            }
+        }
+        flush(b0, cI, cB, cS, cC);
+        if (b0 + 1 < 32) flush(b0 + 1, nI, nB, nS, nC);
+        __syncwarp();
+
+        // ---------------- revenues: one draw per conversion, 4 per Philox call ----------------
+        const int I = (int)s_cnt[warp][lane][0];
+        const int B = (int)s_cnt[warp][lane][1];
+        const int S = (int)s_cnt[warp][lane][2];
+        const long long cost = (long long)s_cost[warp][lane];
+        {
+            const PhiloxPre pr = philox_pre(a.step, stream_word(ST_REVENUE, 0u, (uint32_t)k), genv, k0, k1);
+            FlatRev fr;
+            fr.mean = p.rev_mean; fr.sd = p.rev_sd; fr.S = S;
+            fr.n0 = pr.n0; fr.n1 = pr.n1; fr.x3 = pr.x3; fr.pad0 = 0; fr.pad1 = 0;
+            revs[lane] = fr;
+        }
+        const int nblk = (S + 3) >> 2;
+        const int incl_b = warp_incl_scan(nblk, lane);
+        __syncwarp();  // everyone has read the auction-phase tables
+        start[lane + 1] = incl_b;
+        __syncwarp();
+        const int TB = __shfl_sync(FULL, incl_b, 31);
+        b0 = 0;
+        for (int base = 0; base < TB; base += 32) {
+            while (start[b0 + 1] <= base) ++b0;
+            const int i = base + lane;
+            if (i < TB) {
+                int b = b0;
+                while (i >= start[b + 1]) ++b;
+                const FlatRev fr = revs[b];
+                const int blk = i - start[b];
+                const uint4 w = philox_from_pre((uint32_t)blk, fr.n0, fr.n1, fr.x3, k0, k1);
+                const int r0 = 4 * blk;
+                long long sum = revenue_cents(w.x, fr.mean, fr.sd);
+                if (r0 + 1 < fr.S) sum += revenue_cents(w.y, fr.mean, fr.sd);
+                if (r0 + 2 < fr.S) sum += revenue_cents(w.z, fr.mean, fr.sd);
+                if (r0 + 3 < fr.S) sum += revenue_cents(w.w, fr.mean, fr.sd);
+                atomicAdd(&s_revsum[warp][b], (unsigned long long)sum);
+            }
+        }
+        __syncwarp();
+        const long long rev = (long long)s_revsum[warp][lane];
+
+        // ---------------- outputs (coalesced: 32 consecutive units), env completion ----------------
+        int safe = 0;
+        if (valid) {
+            a.out.impressions[u] = I;
+            a.out.clicks[u] = B;
+            a.out.conversions[u] = S;
+            a.out.cost_cents[u] = cost;
+            a.out.revenue_cents[u] = rev;
+            store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
+            store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
+            safe = unit_done(a, e, rev - cost, cost);
+        }
+        if (a.drift.mask != nullptr) {
+            // drift of finished budget-safe envs (env:246), the warp shares each env's keywords
+            unsigned todo = __ballot_sync(FULL, safe != 0);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int ee = __shfl_sync(FULL, e, src);
+                const uint32_t ge = a.env_base + (uint32_t)ee;
+                for (int kk = lane; kk < K; kk += 32) {
+                    if (!drift_wanted(a, kk)) continue;
+                    const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)kk), ge, k0, k1);
+                    drift_apply(a, ee, kk, drift_from_words(a, w));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // generic kernel: one thread per unit, lanes in order, no budget
 // ------------------------------------------------------------------------------------------
@@ -489,6 +722,7 @@ adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant_
     const int K = a.kw.K;
     const int64_t total = (int64_t)a.E * K;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += stride) {
         const int e = (int)(u / K);
         const int k = (int)(u - (int64_t)e * K);
@@ -554,7 +788,7 @@ __global__ void __launch_bounds__(64)
 adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant__ adc_tape tape)
 {
     const int K = a.kw.K;
-    const int count = *a.scratch.serial_count;
+    const int count = a.scratch.serial_count[a.step & 1u];
     const bool explicit_kw = a.kw.kind == ADC_EXPLICIT;
     const int stride = gridDim.x * blockDim.x;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += stride) {
@@ -656,8 +890,6 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
     }
 }
 
-__global__ void adc_serial_count_reset_kernel(int32_t *count) { *count = 0; }
-
 __global__ void adc_reset_envs_kernel(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -719,8 +951,20 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     cudaError_t err = cudaSuccess;
     adc_tape t0 = {};
     const adc_tape &tp = tape ? *tape : t0;
-    if (tape == nullptr && !explicit_kw) {
-        int L = a.n_lanes > 0 ? a.n_lanes : 8;
+    if (tape == nullptr && !explicit_kw && a.n_lanes == 0) {
+        const int block = kFlatWarps * 32;
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adc_flat_philox_implicit_kernel, block, 0);
+        if (per_sm < 1) per_sm = 1;
+        int64_t grid = (int64_t)num_sms() * per_sm;
+        const int64_t want = ((total + 31) / 32 + kFlatWarps - 1) / kFlatWarps;
+        if (want < grid) grid = want;
+        if (grid < 1) grid = 1;
+        adc_flat_philox_implicit_kernel<<<(unsigned)grid, block, 0, s>>>(a);
+        ++*launches;
+        err = cudaGetLastError();
+    } else if (tape == nullptr && !explicit_kw) {
+        int L = a.n_lanes;
         switch (L) {
             case 1: err = launch_lanes<1>(a, s, launches); break;
             case 2: err = launch_lanes<2>(a, s, launches); break;
@@ -755,10 +999,6 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         auto kern = adc_serial_kernel<TapeSrc>;
         kern<<<(unsigned)grid_for(kern, 64, a.E), 64, 0, s>>>(a, tp);
     }
-    ++*launches;
-    err = cudaGetLastError();
-    if (err != cudaSuccess) return err;
-    adc_serial_count_reset_kernel<<<1, 1, 0, s>>>(a.scratch.serial_count);
     ++*launches;
     return cudaGetLastError();
 }

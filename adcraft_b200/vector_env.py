@@ -114,7 +114,7 @@ class VectorBiddingSimulation:
             budget=torch.full((E,), self.budget, dtype=f64, device=dev),
             cum_profit=z(E, dtype=f64), day=z(E, dtype=i32))
         self._scratch = dict(
-            serial_list=z(E, dtype=i32), serial_count=z(1, dtype=i32), env_profit=z(E, dtype=i64),
+            serial_list=z(E, dtype=i32), serial_count=z(2, dtype=i32), env_profit=z(E, dtype=i64),
             env_cost=z(E, dtype=i64), env_done=z(E, dtype=i32), unit_cost_f64=z(E, K, dtype=f64))
         self._bids_dev = {torch.float32: z(E, K, dtype=torch.float32), torch.float64: z(E, K, dtype=f64)}
         self._budget_dev = {torch.float32: z(E, dtype=torch.float32), torch.float64: z(E, dtype=f64)}

@@ -114,7 +114,7 @@ typedef struct adc_step_out {
 /* Scratch the step needs (caller-owned so that nothing is allocated per call). */
 typedef struct adc_scratch {
     int32_t *serial_list;   /* [E] envs that need the exact serial budget walk              */
-    int32_t *serial_count;  /* [1] must be 0 on entry; left at 0 on exit                    */
+    int32_t *serial_count;  /* [2] double-buffered on step parity; both 0 before the first step */
     int64_t *env_profit;    /* [E] per-env profit cents accumulator, 0 on entry and on exit */
     int64_t *env_cost;      /* [E] per-env cost cents accumulator,   0 on entry and on exit */
     int32_t *env_done;      /* [E] finished-unit counter,            0 on entry and on exit */
@@ -124,7 +124,8 @@ typedef struct adc_scratch {
 typedef struct adc_step_args {
     int32_t E;              /* envs owned by this call / rank                      */
     uint32_t env_base;      /* global id of env 0 (Philox counter; rank sharding)  */
-    uint32_t step;          /* global step counter (Philox counter)                */
+    uint32_t step;          /* global step counter (Philox counter); must advance by 1 per call
+                               on a given scratch (its parity double-buffers serial_count)    */
     uint64_t seed;          /* Philox key                                          */
     int32_t n_lanes;        /* threads cooperating on one (env,keyword): 0 = auto, else 1..32 pow2 */
     int32_t budget_alias;   /* 1: ndarray-budget double charge (bsim:102 + :225), 0: scalar budget */
