@@ -32,8 +32,10 @@ int check_device()
     return ADC_OK;
 }
 
-#define ADC_REQUIRE(cond, what) \
-    if (!(cond)) return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: %s", what)
+#define ADC_REQUIRE(cond, what)                                                                   \
+    do {                                                                                          \
+        if (!(cond)) return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: %s", what);    \
+    } while (0)
 
 int validate(const adc_step_args *a, const adc_tape *tape)
 {

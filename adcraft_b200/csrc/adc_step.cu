@@ -160,7 +160,24 @@ struct LaneOut {
     int I, B, S;
     long long cost_cents, rev_cents;
     double lane_cost_sum;  // dollars, sequential rust.sum_list of this lane's costs (bsim:225)
+    bool overrun;          // tape mode: a stream ended before the walk did (see tape_at)
 };
+
+// Bounds-checked tape read.  A tape recorded from a run whose budget bound holds only what that
+// run consumed (lanes after the early break drew nothing), so the budget-free walk can run off
+// the end of a unit's stream: it then reads a harmless default, reports `overrun`, and the env
+// is sent to the exact serial kernel, which consumes precisely what the reference consumed.
+template <typename T>
+__device__ __forceinline__ T tape_at(const T *vals, const int64_t *off, int64_t u, int64_t i, T dflt,
+                                     bool &overrun)
+{
+    const int64_t idx = off[u] + i;
+    if (idx >= off[u + 1]) {
+        overrun = true;
+        return dflt;
+    }
+    return vals[idx];
+}
 
 // One call of simulate_epoch_of_bidding (bsim:44-120) for unit u, sub-step t, n auctions.
 // kBudget=false: budget is +inf (no check can fail).  `b` is the lane-local budget copy;
@@ -175,6 +192,7 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
     o.I = o.B = o.S = 0;
     o.cost_cents = o.rev_cents = 0;
     o.lane_cost_sum = 0.0;
+    o.overrun = false;
     bool stopped = false;  // the `break` of bsim:103-104: later slots are drawn but not scanned
     int slots = 0;
     uint4 rw = make_uint4(0, 0, 0, 0);
@@ -189,7 +207,7 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
         }
         bool conv;
         if constexpr (Src::kTape)
-            conv = tp->u_conv[tp->conv_off[u] + cur.n_conv + o.B] <= p.cvr;
+            conv = tape_at(tp->u_conv, tp->conv_off, u, cur.n_conv + o.B, 2.0, o.overrun) <= p.cvr;
         else
             conv = w2 <= p.thr_conv;
         o.B += 1;
@@ -201,7 +219,7 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
             const int r = cur.n_rev + o.S;
             int rc;
             if constexpr (Src::kTape) {
-                rc = tp->rev_cents[tp->rev_off[u] + r];
+                rc = tape_at(tp->rev_cents, tp->rev_off, u, r, 0, o.overrun);
             } else {
                 if (!rw_valid || (r & 3) == 0) {
                     rw = src.draw(ST_REVENUE, (uint32_t)kw, (uint32_t)(r >> 2));
@@ -223,7 +241,7 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
             int c;
             uint32_t w1 = 0, w2 = 0;
             if constexpr (Src::kTape) {
-                c = tp->comp_cents[tp->comp_off[u] + j];
+                c = tape_at(tp->comp_cents, tp->comp_off, u, j, 0x7FFFFFFF, o.overrun);
             } else {
                 const uint4 w = src.draw(ST_AUCTION, (uint32_t)kw, (uint32_t)j);
                 c = laplace_cents(w.x, p.loc, p.scale);
@@ -233,7 +251,7 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
             if (p.bid_cents > c) {
                 bool clicked;
                 if constexpr (Src::kTape)
-                    clicked = tp->u_click[tp->click_off[u] + cur.n_click + slots] <= p.ctr;
+                    clicked = tape_at(tp->u_click, tp->click_off, u, cur.n_click + slots, 2.0, o.overrun) <= p.ctr;
                 else
                     clicked = w1 <= p.thr_click;
                 on_slot(cents_to_dollars(c), c, clicked, w2);
@@ -245,14 +263,14 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
         if constexpr (Src::kTape) {
             const int I = tp->impr[u * ADC_SUBSTEPS + t];
             for (int i = 0; i < I; ++i) {
-                const double cost = tp->cost[tp->cost_off[u] + cur.n_cost + i];
-                const bool clicked = tp->u_click[tp->click_off[u] + cur.n_click + i] <= p.ctr;
+                const double cost = tape_at(tp->cost, tp->cost_off, u, cur.n_cost + i, 0.0, o.overrun);
+                const bool clicked = tape_at(tp->u_click, tp->click_off, u, cur.n_click + i, 2.0, o.overrun) <= p.ctr;
                 on_slot(cost, 0, clicked, 0u);
             }
             o.I = I;
             slots = I;
             if (I < 1) {  // phantom zero-cost slot (classes:514-515)
-                const bool clicked = tp->u_click[tp->click_off[u] + cur.n_click] <= p.ctr;
+                const bool clicked = tape_at(tp->u_click, tp->click_off, u, cur.n_click, 2.0, o.overrun) <= p.ctr;
                 on_slot(0.0, 0, clicked, 0u);
                 slots = 1;
             }
@@ -743,6 +761,7 @@ adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant_
         int I = 0, B = 0, S = 0;
         long long cost_c = 0, rev_c = 0;
         double cost_f = 0.0, binf = 0.0;
+        bool overrun = false;
         for (int t = 0; t < ADC_SUBSTEPS; ++t) {
             const long long n = t == 0 ? V - (ADC_SUBSTEPS - 1) * q : q;  // bsim:151-167
             const LaneOut o =
@@ -752,7 +771,11 @@ adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant_
             S += o.S;
             cost_c += o.cost_cents;
             rev_c += o.rev_cents;
+            overrun |= o.overrun;
         }
+        // a truncated tape means the recorded run stopped early: make the env look unaffordable
+        // so that unit_done queues it for the exact serial walk
+        const long long kForceSerialCents = 1LL << 60;
         a.out.impressions[u] = I;
         a.out.clicks[u] = B;
         a.out.conversions[u] = S;
@@ -761,13 +784,13 @@ adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant_
         int safe;
         if constexpr (kExplicit) {
             a.out.cost_cents[u] = 0;
-            a.scratch.unit_cost_f64[u] = cost_f;
+            a.scratch.unit_cost_f64[u] = overrun ? __longlong_as_double(0x7FF0000000000000LL) : cost_f;
             store_f(a.out.cost, a.out.float_dtype, u, cost_f);
             safe = unit_done(a, e, 0, 0);
         } else {
             a.out.cost_cents[u] = cost_c;
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost_c));
-            safe = unit_done(a, e, rev_c - cost_c, cost_c);
+            safe = unit_done(a, e, rev_c - cost_c, overrun ? kForceSerialCents : cost_c);
         }
         if (safe && a.drift.mask != nullptr) {
             for (int kk = 0; kk < K; ++kk) {

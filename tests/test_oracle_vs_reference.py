@@ -1,0 +1,108 @@
+"""Pins the C oracle to the UNMODIFIED reference Python, live (build container only; skipped on
+the GPU box, where /root/reference does not exist -- the committed goldens cover it there)."""
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import ref_harness as rh
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")]
+
+
+def _check(a, b, name):
+    for f in ("impressions", "clicks", "conversions", "lane_I", "lane_B", "lane_S"):
+        assert np.array_equal(np.asarray(a[f], np.int64), np.asarray(b[f], np.int64)), (name, f)
+    for f in ("cost", "revenue", "profit"):
+        assert np.array_equal(np.asarray(a[f]), np.asarray(b[f])), (name, f)
+    assert a["reward"] == b["reward"] and a["lanes_run"] == b["lanes_run"], name
+
+
+@pytest.mark.parametrize("vol,cvr,K,budget,seed", [
+    (16, 0.5, 2, 1000.0, 0), (128, 0.8, 7, np.array([100000.0]), 1), (64, 0.1, 5, np.array([30.0]), 2),
+    (128, 0.8, 6, 55.5, 3), (16, 0.1, 9, np.array([2.0]), 4), (64, 0.8, 4, 0.0, 5)])
+def test_recorded_implicit_steps(orc, vol, cvr, K, budget, seed):
+    from oracle import ref_driver as rd
+    ref = rh.load_reference()
+    tmp = tempfile.mkdtemp()
+    env = ref["env"].bidding_sim_creator(dict(
+        keyword_config=rh.experiment_keyword_config(vol, cvr, tmp), num_keywords=K, max_days=10,
+        updater_mask=[True] * K))
+    env.reset(seed=seed)
+    rng = np.random.default_rng(seed)
+    for s in range(3):
+        bids = np.round(rng.uniform(0.2, 1.5, size=K), 2)
+        r = rd.record_step(env, {"keyword_bids": bids, "budget": budget})
+        o = orc.step_replay(r["kw_before"], r["bid_cents"], r["budget"], r["tape"], budget_alias=r["budget_alias"])
+        _check(r, o, (vol, K, s))
+
+
+@pytest.mark.parametrize("K,budget,seed", [(1, 1000.0, 0), (10, np.array([1000.0]), 1), (10, np.array([20.0]), 2),
+                                           (4, 3.0, 3)])
+def test_recorded_explicit_steps(orc, K, budget, seed):
+    from oracle import ref_driver as rd
+    ref = rh.load_reference()
+    env = ref["env"].BiddingSimulation(num_keywords=K)
+    env.reset(seed=seed)
+    rng = np.random.default_rng(seed)
+    for s in range(3):
+        bids = np.round(rng.uniform(0.01, 3.0, size=K), 2)
+        r = rd.record_step(env, {"keyword_bids": bids, "budget": budget})
+        o = orc.step_replay(r["kw_before"], r["bid_cents"], r["budget"], r["tape"], budget_alias=r["budget_alias"])
+        _check(r, o, ("explicit", K, s))
+
+
+@pytest.mark.parametrize("kind_name", ["implicit", "explicit"])
+@pytest.mark.parametrize("K,vol,budget,alias", [(3, 16, 1000.0, False), (8, 128, 1e5, False), (6, 64, 20.0, False),
+                                                (6, 64, 20.0, True), (5, 128, 3.5, True)])
+def test_philox_tapes_through_the_reference(orc, kind_name, K, vol, budget, alias):
+    """Free-running oracle -> recorded tape -> unmodified reference: same integers, same floats,
+    same drifted parameters, same cumulative profit."""
+    from conftest import make_explicit_table, make_implicit_table, oracle_keywordset
+    from oracle import ref_driver as rd
+    rng = np.random.default_rng(K * 100 + vol)
+    table = make_implicit_table(rng, K, vol) if kind_name == "implicit" else make_explicit_table(rng, K)
+    kw = oracle_keywordset(orc, table)
+    mask = np.ones(K, bool)
+    env = rd.build_replay_env(kw, budget=budget, drift_mask=mask)
+    kwc, cum = kw.copy(), 0.0
+    for step in range(3):
+        bids = np.round(rng.uniform(0.2, 1.5 if kind_name == "implicit" else 3.0, K), 2)
+        bc = np.rint(bids * 100).astype(np.int32)
+        o = orc.step_philox(kwc, bc, budget, seed=1234, env_id=5, step=step, record_cap=4096, budget_alias=alias)
+        tape = o["tape"]
+        tape.drift = orc.drift_philox(K, 1234, 5, step)
+        r = rd.replay_step(env, bids, np.array([budget]) if alias else None, tape)
+        _check(r, o, (kind_name, K, step))
+        orc.drift_apply(kwc, mask, tape.drift, kw.vol_std)
+        for n in ("vol_mean", "ctr", "cvr"):
+            assert np.array_equal(getattr(r["kw_after"], n), getattr(kwc, n)), n
+        cum += o["reward"]
+        assert r["cumulative_profit"] == cum
+
+
+def test_keyword_factories_match_reference_rng_order(orc):
+    from adcraft_b200 import keywords as kwm
+    from oracle import ref_driver as rd
+    ref = rh.load_reference()
+    tmp = tempfile.mkdtemp()
+    for vol, cvr, K, seed in [(16, 0.5, 2, 0), (100, 0.3, 30, 10), (128, 0.8, 100, 5)]:
+        env = ref["env"].bidding_sim_creator(dict(keyword_config=rh.experiment_keyword_config(vol, cvr, tmp),
+                                                  num_keywords=K))
+        env.reset(seed=seed)
+        a = rd.keywordset_from_env(env)
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        t = kwm.sample_implicit_keywords_from_quantiles(K, g, {"mean_volume": vol, "conversion_rate": cvr})
+        for n in kwm.PARAM_NAMES:
+            np.testing.assert_allclose(getattr(a, n), getattr(t, n), rtol=1e-15 if n == "p2" else 0)
+        assert env.np_random.random() == g.random()  # generator left in the same state
+    for K, seed in [(10, 1), (1, 0)]:
+        env = ref["env"].BiddingSimulation(num_keywords=K)
+        env.reset(seed=seed)
+        a = rd.keywordset_from_env(env)
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        t = kwm.sample_random_keywords(K, g)
+        for n in kwm.PARAM_NAMES:
+            assert np.array_equal(getattr(a, n), getattr(t, n)), n
+        assert env.np_random.random() == g.random()
