@@ -62,18 +62,27 @@ __device__ __forceinline__ PhiloxPre philox_pre(uint32_t c1, uint32_t c2, uint32
     return p;
 }
 
+// 32x32 -> 64 multiply as ONE IMAD.WIDE.U32 (the plain C++ forms sometimes compile to IMAD.HI + IMAD)
+__device__ __forceinline__ void mulwide(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo)
+{
+    unsigned long long p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+}
+
 __device__ __forceinline__ uint4 philox_from_pre(uint32_t idx, uint32_t n0, uint32_t n1, uint32_t x3,
                                                  uint32_t k0, uint32_t k1)
 {
-    uint32_t c0 = n0, c1 = n1;
-    uint32_t c2 = __umulhi(0xD2511F53u, idx) ^ x3;
-    uint32_t c3 = 0xD2511F53u * idx;
+    uint32_t c0 = n0, c1 = n1, c2, c3;
+    mulwide(0xD2511F53u, idx, c2, c3);
+    c2 ^= x3;
 #pragma unroll
     for (int r = 1; r < 10; ++r) {
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t h0, l0, h1, l1;
+        mulwide(0xD2511F53u, c0, h0, l0);
+        mulwide(0xCD9E8D57u, c2, h1, l1);
         c0 = h1 ^ c1 ^ k0;
         c2 = h0 ^ c3 ^ k1;
         c1 = l1;

@@ -544,7 +544,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     __shared__ int s_start[kFlatWarps][33];
     __shared__ unsigned s_cnt[kFlatWarps][32][3];
     __shared__ unsigned long long s_cost[kFlatWarps][32];
-    __shared__ unsigned long long s_revsum[kFlatWarps][32];
+    __shared__ unsigned s_revsum[kFlatWarps][32][2];  // 24-bit split: native 32-bit smem atomics
 
     const int K = a.kw.K;
     const int64_t total = (int64_t)a.E * K;
@@ -592,7 +592,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         if (lane == 0) start[0] = 0;
         s_cnt[warp][lane][0] = 0; s_cnt[warp][lane][1] = 0; s_cnt[warp][lane][2] = 0;
         s_cost[warp][lane] = 0ull;
-        s_revsum[warp][lane] = 0ull;
+        s_revsum[warp][lane][0] = 0u; s_revsum[warp][lane][1] = 0u;
         __syncwarp();
         const int T = __shfl_sync(FULL, incl, 31);
 
@@ -617,7 +617,41 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
                 atomicAdd(&s_cost[warp][bb], (unsigned long long)lo + ((unsigned long long)hi << 24));
             }
         };
-        for (int base = 0; base < T; base += 32) {
+        // phase 1 of an auction: which unit it belongs to (rarely a search), its ordinal there
+        auto locate = [&](int i, int &b, uint32_t &j) {
+            const bool in_next = i >= s_nxt;
+            b = b0 + (in_next ? 1 : 0);
+            int s_b = in_next ? s_nxt : s_cur;
+            if (i < T && i >= s_nxt2) {  // rare: more than two units inside one stripe
+                while (i >= start[b + 1]) ++b;
+                s_b = start[b];
+            }
+            j = (uint32_t)(i - s_b);
+        };
+        // phase 2: straight-line Philox + sampler + outcome (two of these interleave per trip)
+        auto outcome = [&](int i, int b, uint32_t j, bool &win, bool &clk, bool &cnv, unsigned &cc) {
+            const FlatUnit fu = units[b];
+            const uint4 w = philox_from_pre(j, fu.n0, fu.n1, fu.x3, k0, k1);
+            const int c = laplace_cents(w.x, fu.loc, fu.scale);
+            win = (i < T) && fu.bid_cents > c;
+            clk = win && (w.y <= fu.thr_click);
+            cnv = clk && (w.z <= fu.thr_conv);
+            cc = clk ? (unsigned)c : 0u;
+        };
+        auto tally = [&](int b, bool win, bool clk, bool cnv, unsigned cc) {
+            const bool in0 = b == b0, in1 = b == b0 + 1;
+            cI += (win && in0); cB += (clk && in0); cS += (cnv && in0); cC += in0 ? cc : 0u;
+            nI += (win && in1); nB += (clk && in1); nS += (cnv && in1); nC += in1 ? cc : 0u;
+            if (win && !in0 && !in1) {
+                atomicAdd(&s_cnt[warp][b][0], 1u);
+                if (clk) {
+                    atomicAdd(&s_cnt[warp][b][1], 1u);
+                    atomicAdd(&s_cost[warp][b], (unsigned long long)cc);
+                }
+                if (cnv) atomicAdd(&s_cnt[warp][b][2], 1u);
+            }
+        };
+        for (int base = 0; base < T; base += 64) {  // two independent auctions per lane per trip
             while (s_nxt <= base) {  // warp-uniform: lane 0's auction moved to the next unit
                 flush(b0, cI, cB, cS, cC);
                 cI = nI; cB = nB; cS = nS; cC = nC;
@@ -627,34 +661,16 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
                 s_nxt = s_nxt2;
                 s_nxt2 = b0 + 2 <= 32 ? start[b0 + 2] : 0x7FFFFFFF;
             }
-            const int i = base + lane;
-            const bool act = i < T;
-            const bool in_next = i >= s_nxt;
-            int b = b0 + (in_next ? 1 : 0);
-            int s_b = in_next ? s_nxt : s_cur;
-            if (act && i >= s_nxt2) {  // rare: more than two units inside one 32-auction stripe
-                while (i >= start[b + 1]) ++b;
-                s_b = start[b];
-            }
-            const FlatUnit fu = units[b];
-            const uint4 w = philox_from_pre((uint32_t)(i - s_b), fu.n0, fu.n1, fu.x3, k0, k1);
-            const int c = laplace_cents(w.x, fu.loc, fu.scale);
-            const bool win = act && fu.bid_cents > c;
-            const bool clk = win && (w.y <= fu.thr_click);
-            const bool cnv = clk && (w.z <= fu.thr_conv);
-            const unsigned cc = clk ? (unsigned)c : 0u;
-            if (b == b0) {
-                cI += win; cB += clk; cS += cnv; cC += cc;
-            } else if (b == b0 + 1) {
-                nI += win; nB += clk; nS += cnv; nC += cc;
-            } else if (win) {
-                atomicAdd(&s_cnt[warp][b][0], 1u);
-                if (clk) {
-                    atomicAdd(&s_cnt[warp][b][1], 1u);
-                    atomicAdd(&s_cost[warp][b], (unsigned long long)cc);
-                }
-                if (cnv) atomicAdd(&s_cnt[warp][b][2], 1u);
-            }
+            int bA, bB;
+            bool winA, clkA, cnvA, winB, clkB, cnvB;
+            unsigned ccA, ccB;
+            uint32_t jA, jB;
+            locate(base + lane, bA, jA);
+            locate(base + 32 + lane, bB, jB);
+            outcome(base + lane, bA, jA, winA, clkA, cnvA, ccA);
+            outcome(base + 32 + lane, bB, jB, winB, clkB, cnvB, ccB);
+            tally(bA, winA, clkA, cnvA, ccA);
+            tally(bB, winB, clkB, cnvB, ccB);
         }
         flush(b0, cI, cB, cS, cC);
         if (b0 + 1 < 32) flush(b0 + 1, nI, nB, nS, nC);
@@ -693,11 +709,12 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
                 if (r0 + 1 < fr.S) sum += revenue_cents(w.y, fr.mean, fr.sd);
                 if (r0 + 2 < fr.S) sum += revenue_cents(w.z, fr.mean, fr.sd);
                 if (r0 + 3 < fr.S) sum += revenue_cents(w.w, fr.mean, fr.sd);
-                atomicAdd(&s_revsum[warp][b], (unsigned long long)sum);
+                atomicAdd(&s_revsum[warp][b][0], (unsigned)(sum & 0xFFFFFF));
+                atomicAdd(&s_revsum[warp][b][1], (unsigned)(sum >> 24));
             }
         }
         __syncwarp();
-        const long long rev = (long long)s_revsum[warp][lane];
+        const long long rev = (long long)s_revsum[warp][lane][0] + ((long long)s_revsum[warp][lane][1] << 24);
 
         // ---------------- outputs (coalesced: 32 consecutive units), env completion ----------------
         int safe = 0;

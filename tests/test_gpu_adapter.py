@@ -1,0 +1,87 @@
+"""The E = 1 adapter, flat wrapper and device metrics on the GPU (reference API shape)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def test_single_env_adapter_api_and_dtypes():
+    """Mirrors adcraft/tests/test_env.py: reset/step run, obs are in the observation space after the
+    reference's own dtype cast (test_env.py:60-69), reward is a float, flags are bools."""
+    from adcraft_b200.gymnasium_kw_env import BiddingSimulation, bidding_sim_creator
+    env = BiddingSimulation()
+    reset_obs, info = env.reset(seed=1)
+    assert env.observation_space.contains(reset_obs) and "keyword_params" in info
+    action = env.action_space.sample()
+    obs, reward, terminated, truncated, info = env.step(action)
+    assert isinstance(reward, float) and isinstance(terminated, bool) and isinstance(truncated, bool)
+    assert set(info) == {"bids", "bidding_outcomes", "keyword_params"}
+    assert obs["impressions"].dtype == np.int64 and obs["cost"].dtype == np.float64
+    assert obs["cumulative_profit"].shape == (1,) and obs["days_passed"].tolist() == [1]
+    cast = {k: obs[k].astype(v.dtype) for k, v in reset_obs.items()}
+    assert env.observation_space.contains(cast)
+    assert abs(obs["cumulative_profit"][0] - reward) < 1e-9
+    env2 = bidding_sim_creator(dict(keyword_config={"mean_volume": 16, "conversion_rate": 0.5}, num_keywords=2,
+                                    max_days=3))
+    _, info2 = env2.reset(seed=0)
+    assert "imp_intercept: 0.6459721981904619" in info2["keyword_params"]  # notebook golden
+    done = False
+    for _ in range(3):
+        o, r, done, tr, _ = env2.step({"keyword_bids": np.array([0.75, 0.75]), "budget": 100000})
+    assert done and o["days_passed"][0] == 3
+
+
+def test_adapter_budget_aliasing_follows_action_type():
+    from adcraft_b200.gymnasium_kw_env import BiddingSimulation
+    cfg = dict(keyword_config={"mean_volume": 128, "conversion_rate": 0.8}, num_keywords=20, seed=3)
+    a, b = BiddingSimulation(**cfg), BiddingSimulation(**cfg)
+    a.reset(seed=7); b.reset(seed=7)
+    bids = np.full(20, 0.9)
+    oa = a.step({"keyword_bids": bids, "budget": 40.0})[0]
+    ob = b.step({"keyword_bids": bids, "budget": np.array([40.0])})[0]
+    # the ndarray budget is charged twice per click: about half the spend before the day ends
+    assert oa["cost"].sum() <= 40.0 + 1e-9 and ob["cost"].sum() <= 20.0 + 1.5
+    assert ob["cost"].sum() < oa["cost"].sum()
+    assert isinstance(b.budget, np.ndarray) and float(b.budget[0]) <= 0.0 + 1.5
+
+
+def test_flat_wrapper_round_trip():
+    from adcraft_b200.gymnasium_kw_env import BiddingSimulation
+    from adcraft_b200.wrappers import FlatArrayWrapper, observation_slices
+    env = FlatArrayWrapper(BiddingSimulation(num_keywords=5))
+    flat, _ = env.reset(seed=2)
+    assert flat.shape == (27,)
+    act = np.concatenate([[1000.0], np.full(5, 1.2)]).astype(np.float32)
+    flat, reward, term, trunc, info = env.step(act)
+    sl = observation_slices(5)
+    assert flat.shape == (27,) and flat[sl["days_passed"]][0] == 1
+    assert abs(flat[sl["revenue"]].sum() - flat[sl["cost"]].sum() - reward) < 1e-9
+
+
+def test_device_metrics_against_host_definitions():
+    from adcraft_b200 import keywords as kwm, metrics as m
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    rng = np.random.default_rng(5)
+    K, E = 12, 16
+    table = kwm.sample_implicit_keywords_from_quantiles(K, rng, {"mean_volume": 64, "conversion_rate": 0.8})
+    env = VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=1e5, device="cuda", seed=1,
+                                  obs_dtype=torch.float64)
+    env.reset()
+    grid = torch.arange(0.01, 3.00, 0.01, dtype=torch.float64, device="cuda")
+    dev = lambda n: torch.tensor(getattr(table, n), device="cuda")
+    rate, cpc = m.implicit_bid_profile(dev("p1"), dev("p2"), grid)
+    ideal, _, _ = m.max_expected_bid_profits(dev("vol_mean"), dev("ctr"), dev("cvr"), dev("rev_mean"), cpc, rate)
+    acc = m.MetricAccumulator(E, K, "cuda")
+    profits, bids = [], torch.full((E, K), 0.75, dtype=torch.float64, device="cuda")
+    for t in range(10):
+        obs, reward, term, trunc, _ = env.step({"keyword_bids": bids})
+        acc.update(obs, reward, ideal=ideal[None], done=term)
+        profits.append((obs["revenue"] - obs["cost"]).cpu().numpy())
+    pe = acc.per_env()
+    P, I = np.stack(profits), np.tile(ideal.cpu().numpy(), (10, 1))
+    for e in range(E):
+        assert abs(float(pe["akncp"][e]) - m.compute_AKNCP(P[:, e], I)) < 1e-9
+        assert abs(float(pe["ncp"][e]) - m.compute_NCP(P[:, e], I)) < 1e-9
+    s = m.summarize(m.reduce_metrics(acc.summary_vector()))
+    assert s["n_envs"] == E
