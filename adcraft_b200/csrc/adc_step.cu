@@ -502,11 +502,13 @@ adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
 
 
 // ------------------------------------------------------------------------------------------
-// hot kernel, warp-flattened: a warp takes a batch of 32 units, and the auctions of all 32 are
-// laid end to end in one index space that the 32 lanes stride through together.  Lanes stay busy
-// whatever the per-unit volumes are (the per-unit volume is N(128, up to 64) in the dense
-// config, which costs the L-threads-per-unit kernel ~30 % of its lanes).  Per-unit sums are
-// formed with ballots / REDUX over the lanes that fall in the same unit.
+// hot kernel, warp-batched: a warp takes a batch of 32 units.  Setup is lane <-> unit (parameters,
+// volume draw, thresholds, Philox pre-round -> 32 B per unit in shared memory), so it runs at
+// full lane efficiency; then the warp walks the 32 units one after the other with all 32 lanes
+// on one unit's auctions (warp-uniform parameters in registers, private lane accumulators, one
+// REDUX set per unit).  Volume imbalance between units costs nothing (the L-threads-per-unit
+// kernel loses ~30 % of its lanes to it); only the last 32-auction trip of a unit has idle lanes.
+// Revenues are flattened across the batch (4 draws per Philox call).
 // ------------------------------------------------------------------------------------------
 struct __align__(16) FlatUnit {
     int bid_cents;
@@ -524,7 +526,10 @@ struct __align__(16) FlatRev {
 };
 
 constexpr int kFlatWarps = 8;
-constexpr int kMaxFlatVolume = 1 << 25;  // per-unit cap keeps the batch total inside int32
+// Caps of the fast kernel's 16/32-bit lane accumulators; a unit beyond them sends its env to the
+// exact serial kernel instead (volumes and bids this large do not occur in the reference's configs).
+constexpr int kMaxFlatVolume = 1 << 20;
+constexpr int kMaxFlatBidCents = 65535;
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 {
@@ -542,8 +547,6 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     __shared__ FlatUnit s_unit[kFlatWarps][32];
     __shared__ FlatRev s_rev[kFlatWarps][32];
     __shared__ int s_start[kFlatWarps][33];
-    __shared__ unsigned s_cnt[kFlatWarps][32][3];
-    __shared__ unsigned long long s_cost[kFlatWarps][32];
     __shared__ unsigned s_revsum[kFlatWarps][32][2];  // 24-bit split: native 32-bit smem atomics
 
     const int K = a.kw.K;
@@ -565,6 +568,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         const int64_t u = batch * 32 + lane;
         const bool valid = u < total;
         int e = 0, k = 0, V = 0;
+        bool over_cap = false;
         uint32_t genv = 0;
         UnitPar p;
         p.bid_cents = 0; p.loc = 0.f; p.scale = 0.f; p.thr_click = 0; p.thr_conv = 0;
@@ -577,7 +581,8 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             const int64_t pi = (int64_t)e * a.kw.env_stride + k;
             const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)k), genv, k0, k1);
             const long long v = volume_draw(w.x, a.kw.vol_mean[pi], a.kw.vol_std[pi]);
-            V = (int)(v > kMaxFlatVolume ? kMaxFlatVolume : v);
+            over_cap = v > kMaxFlatVolume || p.bid_cents > kMaxFlatBidCents;
+            V = over_cap ? 0 : (int)v;
         }
         {
             const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), genv, k0, k1);
@@ -587,100 +592,49 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             fu.n0 = pa.n0; fu.n1 = pa.n1; fu.x3 = pa.x3;
             units[lane] = fu;
         }
-        const int incl = warp_incl_scan(V, lane);
-        start[lane + 1] = incl;
         if (lane == 0) start[0] = 0;
-        s_cnt[warp][lane][0] = 0; s_cnt[warp][lane][1] = 0; s_cnt[warp][lane][2] = 0;
-        s_cost[warp][lane] = 0ull;
         s_revsum[warp][lane][0] = 0u; s_revsum[warp][lane][1] = 0u;
         __syncwarp();
-        const int T = __shfl_sync(FULL, incl, 31);
 
-        // ---------------- the batch's auctions, flattened ----------------
-        // Lanes accumulate privately for the unit of lane 0's auction (b0) and for the next one;
-        // the sums are warp-reduced once per unit when b0 advances.  An iteration that spans more
-        // than two units (volumes below 16) sends the far lanes through shared-memory atomics.
-        int b0 = 0;
-        int s_cur = 0, s_nxt = start[1], s_nxt2 = start[2];
-        unsigned cI = 0, cB = 0, cS = 0, nI = 0, nB = 0, nS = 0;
-        unsigned long long cC = 0, nC = 0;
-        auto flush = [&](int bb, unsigned fI, unsigned fB, unsigned fS, unsigned long long fC) {
-            const unsigned tI = __reduce_add_sync(FULL, fI);
-            const unsigned tB = __reduce_add_sync(FULL, fB);
-            const unsigned tS = __reduce_add_sync(FULL, fS);
-            const unsigned lo = __reduce_add_sync(FULL, (unsigned)(fC & 0xFFFFFFull));
-            const unsigned hi = __reduce_add_sync(FULL, (unsigned)(fC >> 24));
-            if (lane == 0) {
-                atomicAdd(&s_cnt[warp][bb][0], tI);
-                atomicAdd(&s_cnt[warp][bb][1], tB);
-                atomicAdd(&s_cnt[warp][bb][2], tS);
-                atomicAdd(&s_cost[warp][bb], (unsigned long long)lo + ((unsigned long long)hi << 24));
-            }
-        };
-        // phase 1 of an auction: which unit it belongs to (rarely a search), its ordinal there
-        auto locate = [&](int i, int &b, uint32_t &j) {
-            const bool in_next = i >= s_nxt;
-            b = b0 + (in_next ? 1 : 0);
-            int s_b = in_next ? s_nxt : s_cur;
-            if (i < T && i >= s_nxt2) {  // rare: more than two units inside one stripe
-                while (i >= start[b + 1]) ++b;
-                s_b = start[b];
-            }
-            j = (uint32_t)(i - s_b);
-        };
-        // phase 2: straight-line Philox + sampler + outcome (two of these interleave per trip)
-        auto outcome = [&](int i, int b, uint32_t j, bool &win, bool &clk, bool &cnv, unsigned &cc) {
+        // ---------------- the batch's auctions: one unit after the other, 32 lanes per unit ------
+        // The unit is warp-uniform inside a trip: its parameters sit in registers, the lane
+        // accumulators are private, and one REDUX set per unit lands the sums in the owner lane's
+        // registers.  Only the last trip of a unit has idle lanes (volume rounded up to 32).
+        int I = 0, B = 0, S = 0;
+        long long cost = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int Vb = __shfl_sync(FULL, V, b);
+            if (Vb == 0) continue;  // warp-uniform
             const FlatUnit fu = units[b];
-            const uint4 w = philox_from_pre(j, fu.n0, fu.n1, fu.x3, k0, k1);
-            const int c = laplace_cents(w.x, fu.loc, fu.scale);
-            win = (i < T) && fu.bid_cents > c;
-            clk = win && (w.y <= fu.thr_click);
-            cnv = clk && (w.z <= fu.thr_conv);
-            cc = clk ? (unsigned)c : 0u;
-        };
-        auto tally = [&](int b, bool win, bool clk, bool cnv, unsigned cc) {
-            const bool in0 = b == b0, in1 = b == b0 + 1;
-            cI += (win && in0); cB += (clk && in0); cS += (cnv && in0); cC += in0 ? cc : 0u;
-            nI += (win && in1); nB += (clk && in1); nS += (cnv && in1); nC += in1 ? cc : 0u;
-            if (win && !in0 && !in1) {
-                atomicAdd(&s_cnt[warp][b][0], 1u);
-                if (clk) {
-                    atomicAdd(&s_cnt[warp][b][1], 1u);
-                    atomicAdd(&s_cost[warp][b], (unsigned long long)cc);
-                }
-                if (cnv) atomicAdd(&s_cnt[warp][b][2], 1u);
+            unsigned cntIB = 0, cntS = 0, cst = 0;  // I | B << 16 ; S ; cost cents (< 2^32, see caps)
+            auto one = [&](int j) {
+                const uint4 w = philox_from_pre((uint32_t)j, fu.n0, fu.n1, fu.x3, k0, k1);
+                const int c = laplace_cents(w.x, fu.loc, fu.scale);
+                const bool win = (j < Vb) && fu.bid_cents > c;
+                const bool clk = win && (w.y <= fu.thr_click);
+                const bool cnv = clk && (w.z <= fu.thr_conv);
+                cntIB += (win ? 1u : 0u) + (clk ? 0x10000u : 0u);
+                cntS += cnv ? 1u : 0u;
+                cst += clk ? (unsigned)c : 0u;
+            };
+            for (int base = 0; base < Vb; base += 64) {
+                one(base + lane);
+                if (base + 32 < Vb) one(base + 32 + lane);  // warp-uniform: second independent chain
             }
-        };
-        for (int base = 0; base < T; base += 64) {  // two independent auctions per lane per trip
-            while (s_nxt <= base) {  // warp-uniform: lane 0's auction moved to the next unit
-                flush(b0, cI, cB, cS, cC);
-                cI = nI; cB = nB; cS = nS; cC = nC;
-                nI = nB = nS = 0; nC = 0;
-                ++b0;
-                s_cur = s_nxt;
-                s_nxt = s_nxt2;
-                s_nxt2 = b0 + 2 <= 32 ? start[b0 + 2] : 0x7FFFFFFF;
+            const unsigned tI = __reduce_add_sync(FULL, cntIB & 0xFFFFu);
+            const unsigned tB = __reduce_add_sync(FULL, cntIB >> 16);
+            const unsigned tS = __reduce_add_sync(FULL, cntS);
+            const unsigned lo = __reduce_add_sync(FULL, cst & 0xFFFFu);
+            const unsigned hi = __reduce_add_sync(FULL, cst >> 16);
+            if (lane == b) {
+                I = (int)tI;
+                B = (int)tB;
+                S = (int)tS;
+                cost = (long long)lo + ((long long)hi << 16);
             }
-            int bA, bB;
-            bool winA, clkA, cnvA, winB, clkB, cnvB;
-            unsigned ccA, ccB;
-            uint32_t jA, jB;
-            locate(base + lane, bA, jA);
-            locate(base + 32 + lane, bB, jB);
-            outcome(base + lane, bA, jA, winA, clkA, cnvA, ccA);
-            outcome(base + 32 + lane, bB, jB, winB, clkB, cnvB, ccB);
-            tally(bA, winA, clkA, cnvA, ccA);
-            tally(bB, winB, clkB, cnvB, ccB);
         }
-        flush(b0, cI, cB, cS, cC);
-        if (b0 + 1 < 32) flush(b0 + 1, nI, nB, nS, nC);
-        __syncwarp();
 
         // ---------------- revenues: one draw per conversion, 4 per Philox call ----------------
-        const int I = (int)s_cnt[warp][lane][0];
-        const int B = (int)s_cnt[warp][lane][1];
-        const int S = (int)s_cnt[warp][lane][2];
-        const long long cost = (long long)s_cost[warp][lane];
         {
             const PhiloxPre pr = philox_pre(a.step, stream_word(ST_REVENUE, 0u, (uint32_t)k), genv, k0, k1);
             FlatRev fr;
@@ -694,7 +648,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         start[lane + 1] = incl_b;
         __syncwarp();
         const int TB = __shfl_sync(FULL, incl_b, 31);
-        b0 = 0;
+        int b0 = 0;
         for (int base = 0; base < TB; base += 32) {
             while (start[b0 + 1] <= base) ++b0;
             const int i = base + lane;
@@ -726,7 +680,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             a.out.revenue_cents[u] = rev;
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
-            safe = unit_done(a, e, rev - cost, cost);
+            safe = unit_done(a, e, rev - cost, over_cap ? (1LL << 60) : cost);
         }
         if (a.drift.mask != nullptr) {
             // drift of finished budget-safe envs (env:246), the warp shares each env's keywords

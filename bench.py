@@ -300,6 +300,7 @@ def run_gpu(args):
 
 
 def main():
+    global E_ENVS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=240)
@@ -307,9 +308,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-lanes", type=int, default=0, dest="n_lanes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--envs", type=int, default=E_ENVS, help="experiment only: envs per GPU (default = C2's 4096)")
+    ap.add_argument("--envs", type=int, default=4096, help="experiment only: envs per GPU (default = C2's 4096)")
     args = ap.parse_args()
-    global E_ENVS
     E_ENVS = args.envs
     if args.impl == "reference":
         return run_reference(args)

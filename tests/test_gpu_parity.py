@@ -152,3 +152,19 @@ def test_sharding_invariance(orc):
     oh = hi.step({"keyword_bids": torch.from_numpy(bids[E // 2:]).cuda()})[0]
     for k in of:
         assert torch.equal(of[k], torch.cat([ol[k], oh[k]])), k
+
+
+def test_bids_beyond_fast_kernel_caps_take_the_exact_route(orc):
+    """Bids above 65535 cents overflow the fast kernel's 32-bit lane accumulators by design: such
+    envs are routed to the exact serial kernel and still match the oracle."""
+    rng = np.random.default_rng(13)
+    K, E = 9, 20
+    table = make_implicit_table(rng, K, 80)
+    env = _env(table, E, seed=3, budget=1e9, obs_dtype=torch.float64)
+    ob = _oracle_batch(orc, table, E, seed=3, budget=1e9)
+    bids = np.round(rng.uniform(0.2, 1.5, (E, K)), 2)
+    bids[::3, 2] = 700.0
+    bids[1::4, 5] = 1.0e6
+    obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda()})
+    ref = ob.step(bids, n_threads=4)
+    _compare(obs, reward, term, trunc, ref, env, RTOL64)
