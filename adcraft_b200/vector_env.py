@@ -102,13 +102,23 @@ class VectorBiddingSimulation:
         E, K, dev = self.num_envs, self.num_keywords, self.device
         i32, i64, f64 = torch.int32, torch.int64, torch.float64
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
-        self._out = dict(
-            impressions=z(E, K, dtype=i32), buyside_clicks=z(E, K, dtype=i32),
-            sellside_conversions=z(E, K, dtype=i32),
-            cost=z(E, K, dtype=self.obs_dtype), revenue=z(E, K, dtype=self.obs_dtype),
+        # Everything step_host returns lives in ONE contiguous device block (and one pinned host
+        # mirror), so the device->host read of a step is a single copy.
+        fdt = self.obs_dtype
+        layout = [("impressions", i32, (E, K)), ("buyside_clicks", i32, (E, K)),
+                  ("sellside_conversions", i32, (E, K)), ("cost", fdt, (E, K)), ("revenue", fdt, (E, K)),
+                  ("reward", f64, (E,)), ("cumulative_profit", f64, (E,)), ("days_passed", i32, (E,)),
+                  ("terminated", torch.uint8, (E,)), ("truncated", torch.uint8, (E,))]
+        self._block_layout, off = [], 0
+        for name, dt, shape in layout:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            self._block_layout.append((name, dt, shape, off, nbytes))
+            off += (nbytes + 15) // 16 * 16
+        self._block_bytes = off
+        self._block = torch.zeros(off, dtype=torch.uint8, device=dev)
+        self._out = self._views(self._block)
+        self._out.update(
             cost_cents=z(E, K, dtype=i64), revenue_cents=z(E, K, dtype=i64),
-            reward=z(E, dtype=f64), cumulative_profit=z(E, dtype=f64), days_passed=z(E, dtype=i32),
-            terminated=z(E, dtype=torch.uint8), truncated=z(E, dtype=torch.uint8),
             remaining_budget=z(E, dtype=f64))
         self._state = dict(
             budget=torch.full((E,), self.budget, dtype=f64, device=dev),
@@ -121,6 +131,12 @@ class VectorBiddingSimulation:
         self._mask_dev: Optional[torch.Tensor] = None
         self._host: Dict[str, torch.Tensor] = {}
         self._args = _capi.StepArgs()
+        self._args_sig = None
+        self._obs_cache = None
+        self._result_cache = None
+
+    def _views(self, block: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {name: block[o:o + n].view(dt).view(shape) for name, dt, shape, o, n in self._block_layout}
 
     # ------------------------------------------------------------------ keywords / reset
     def set_updater_mask(self, new_updater_mask: List[bool]) -> None:
@@ -192,12 +208,15 @@ class VectorBiddingSimulation:
 
     # ------------------------------------------------------------------ step
     def _obs(self) -> Dict[str, torch.Tensor]:
+        if self._obs_cache is not None:
+            return self._obs_cache
         o = self._out
-        return dict(
+        self._obs_cache = dict(
             impressions=o["impressions"], buyside_clicks=o["buyside_clicks"], cost=o["cost"],
             sellside_conversions=o["sellside_conversions"], revenue=o["revenue"],
             cumulative_profit=o["cumulative_profit"].view(-1, 1),
             days_passed=o["days_passed"].view(-1, 1))
+        return self._obs_cache
 
     def _stage(self, x: ArrayLike, store: Dict[torch.dtype, torch.Tensor], shape) -> torch.Tensor:
         """Bring an action array onto the device (f32/f64 kept) without a per-step allocation."""
@@ -213,11 +232,28 @@ class VectorBiddingSimulation:
         return dst
 
     def _fill_args(self, bids: torch.Tensor, budget: Optional[torch.Tensor], force_serial: bool):
+        """Per-step fields only; the pointer block is rebuilt when something structural changed."""
+        a = self._args
+        sig = (self.kind, self._kw_stride, id(self._kw_dev), self.max_days, self.loss_threshold,
+               self.updater_mask is not None, self.num_updates, self.autoreset, self.n_lanes,
+               self.seed, self.env_base)
+        if sig != self._args_sig:
+            self._fill_static_args()
+            self._args_sig = sig
+        a.step = self._step_count
+        a.budget_alias = int(self.budget_alias)
+        a.force_serial = int(force_serial)
+        a.bids = bids.data_ptr()
+        a.bids_dtype = _capi.F64 if bids.dtype == torch.float64 else _capi.F32
+        a.budget_in = _ptr(budget)
+        return a
+
+    def _fill_static_args(self) -> None:
         a, o, s, st = self._args, self._out, self._scratch, self._state
         E, K = self.num_envs, self.num_keywords
-        a.E, a.env_base, a.step, a.seed = E, self.env_base, self._step_count, self.seed
-        a.n_lanes, a.budget_alias = self.n_lanes, int(self.budget_alias)
-        a.autoreset, a.force_serial = int(self.autoreset), int(force_serial)
+        a.E, a.env_base, a.seed = E, self.env_base, self.seed
+        a.n_lanes = self.n_lanes
+        a.autoreset = int(self.autoreset)
         kw = a.kw
         kw.kind, kw.K, kw.env_stride = self.kind, K, self._kw_stride
         for n in kwmod.PARAM_NAMES:
@@ -231,9 +267,6 @@ class VectorBiddingSimulation:
             a.drift.mag = (C.c_double * 3)(*[float(p[1]) for p in self.updater_params])
         else:
             a.drift.mask, a.drift.num_updates = None, 0
-        a.bids = bids.data_ptr()
-        a.bids_dtype = _capi.F64 if bids.dtype == torch.float64 else _capi.F32
-        a.budget_in = _ptr(budget)
         out = a.out
         out.impressions, out.clicks = o["impressions"].data_ptr(), o["buyside_clicks"].data_ptr()
         out.conversions = o["sellside_conversions"].data_ptr()
@@ -247,7 +280,6 @@ class VectorBiddingSimulation:
         sc = a.scratch
         for n in ("serial_list", "serial_count", "env_profit", "env_cost", "env_done", "unit_cost_f64"):
             setattr(sc, n, s[n].data_ptr())
-        return a
 
     def _prepare(self, action: Dict[str, ArrayLike]):
         assert self._have_keywords, "reset required, need to generate keywords to bid on"
@@ -280,9 +312,11 @@ class VectorBiddingSimulation:
         return self._result()
 
     def _result(self):
-        o = self._out
-        return (self._obs(), o["reward"], o["terminated"].view(torch.bool),
-                o["truncated"].view(torch.bool), {"step": self._step_count})
+        if self._result_cache is None:
+            o = self._out
+            self._result_cache = (self._obs(), o["reward"], o["terminated"].view(torch.bool),
+                                  o["truncated"].view(torch.bool))
+        return (*self._result_cache, {"step": self._step_count})
 
     # ------------------------------------------------------------------ host round trip (e2e)
     def step_host(self, bids_host: torch.Tensor, budget_host: Optional[torch.Tensor] = None):
@@ -293,19 +327,13 @@ class VectorBiddingSimulation:
         action = {"keyword_bids": bids_host}
         if budget_host is not None:
             action["budget"] = budget_host
-        obs, reward, term, trunc, _ = self.step(action)
+        self.step(action)
         if not self._host:
-            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            for k, v in obs.items():
-                self._host[k] = pin(v)
-            self._host["reward"] = pin(reward)
-            self._host["terminated"] = pin(self._out["terminated"])
-            self._host["truncated"] = pin(self._out["truncated"])
-        for k, v in obs.items():
-            self._host[k].copy_(v, non_blocking=True)
-        self._host["reward"].copy_(reward, non_blocking=True)
-        self._host["terminated"].copy_(self._out["terminated"], non_blocking=True)
-        self._host["truncated"].copy_(self._out["truncated"], non_blocking=True)
+            self._host_block = torch.empty(self._block_bytes, dtype=torch.uint8, pin_memory=True)
+            self._host = self._views(self._host_block)
+            self._host["cumulative_profit"] = self._host["cumulative_profit"].view(-1, 1)
+            self._host["days_passed"] = self._host["days_passed"].view(-1, 1)
+        self._host_block.copy_(self._block, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._host
 
@@ -313,7 +341,7 @@ class VectorBiddingSimulation:
         """(h2d, d2h) bytes moved by step_host for this shape."""
         E, K = self.num_envs, self.num_keywords
         fb = 8 if self.obs_dtype == torch.float64 else 4
-        return E * K * 4, E * K * (3 * 4 + 2 * fb) + E * (8 + 4 + 8 + 1 + 1)
+        return E * K * 4, self._block_bytes
 
     # ------------------------------------------------------------------ misc reference API
     def render(self) -> Optional[str]:

@@ -39,6 +39,10 @@ B_UNIT = 24  # read bid 4 B + write 3 x int32 + 2 x f32 per (env
 # Python reference (unmodified, numpy shim for the Rust helpers) measured in the build
 # container on 1 core, dense config: BASELINE.md section 2.
 PY_REFERENCE_UNITS_PER_S_1CORE = 290.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one hot-kernel launch on this workload, from the
+# committed `ncu --set full` capture (profiles/r01_flat_kernel_ncu_metrics.csv): the outputs stay in
+# the 126 MB L2 between steps, so DRAM traffic is below the 9.8 MB of algorithmic bytes.
+NCU_DRAM_BYTES_PER_LAUNCH = 1848064 + 7936
 
 
 def workload_table():
@@ -262,7 +266,8 @@ def run_gpu(args):
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "kernel": "adc_lanes_philox_implicit_kernel", "peak_source": peak_src,
+        "traffic": NCU_DRAM_BYTES_PER_LAUNCH if E_ENVS == 4096 else None,
+        "kernel": "adc_flat_philox_implicit_kernel", "peak_source": peak_src,
         "algorithmic_bytes_per_unit": B_UNIT,
         "note": "free-running mode draws ~128 auctions per unit from Philox: the kernel is issue-bound, "
                 "not HBM-bound (see profiles/ and DESIGN.md); the step = this kernel + an empty serial-queue kernel",
