@@ -134,6 +134,7 @@ class VectorBiddingSimulation:
         self._args_sig = None
         self._obs_cache = None
         self._result_cache = None
+        self._host_view_cache = None
 
     def _views(self, block: torch.Tensor) -> Dict[str, torch.Tensor]:
         return {name: block[o:o + n].view(dt).view(shape) for name, dt, shape, o, n in self._block_layout}
@@ -319,23 +320,62 @@ class VectorBiddingSimulation:
         return (*self._result_cache, {"step": self._step_count})
 
     # ------------------------------------------------------------------ host round trip (e2e)
-    def step_host(self, bids_host: torch.Tensor, budget_host: Optional[torch.Tensor] = None):
+    def step_host(self, bids_host: torch.Tensor, budget_host: Optional[torch.Tensor] = None,
+                  zero_copy: bool = True):
         """``step`` with HOST buffers: pinned host bids in, pinned host observations out.
 
-        This is the call a CPU-side RL loop makes; the H2D and D2H copies are part of it.
+        This is the call a CPU-side RL loop makes; moving the bids to the GPU and the observations
+        back is part of it.  With ``zero_copy`` (default) the transfers are fused into the kernels:
+        the hot kernel reads the bids straight from the pinned host buffer and writes every
+        observation straight into a pinned host block (UVA-mapped), so PCIe traffic overlaps the
+        auction loop batch by batch and no separate copy is enqueued.  ``zero_copy=False`` stages
+        through device memory (one H2D copy, the step, one D2H copy of the contiguous block).
         Returns a dict of pinned host tensors (valid until the next call)."""
-        action = {"keyword_bids": bids_host}
-        if budget_host is not None:
-            action["budget"] = budget_host
-        self.step(action)
         if not self._host:
-            self._host_block = torch.empty(self._block_bytes, dtype=torch.uint8, pin_memory=True)
+            self._host_block = torch.zeros(self._block_bytes, dtype=torch.uint8).pin_memory()
             self._host = self._views(self._host_block)
-            self._host["cumulative_profit"] = self._host["cumulative_profit"].view(-1, 1)
-            self._host["days_passed"] = self._host["days_passed"].view(-1, 1)
-        self._host_block.copy_(self._block, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return self._host
+        if not zero_copy or not (isinstance(bids_host, torch.Tensor) and bids_host.is_pinned()
+                                 and bids_host.dtype in (torch.float32, torch.float64)
+                                 and bids_host.is_contiguous()
+                                 and tuple(bids_host.shape) == (self.num_envs, self.num_keywords)):
+            action = {"keyword_bids": bids_host}
+            if budget_host is not None:
+                action["budget"] = budget_host
+            self.step(action)
+            self._host_block.copy_(self._block, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return self._host_views()
+        assert self._have_keywords, "reset required, need to generate keywords to bid on"
+        budget = None
+        if budget_host is not None:
+            budget = self._stage(budget_host.to(bids_host.dtype), self._budget_dev, (self.num_envs,))
+        a = self._fill_args(bids_host, budget, False)
+        out, h = a.out, self._host
+        saved = (out.impressions, out.clicks, out.conversions, out.cost, out.revenue, out.reward,
+                 out.obs_cum_profit, out.obs_days, out.terminated, out.truncated)
+        out.impressions, out.clicks = h["impressions"].data_ptr(), h["buyside_clicks"].data_ptr()
+        out.conversions = h["sellside_conversions"].data_ptr()
+        out.cost, out.revenue = h["cost"].data_ptr(), h["revenue"].data_ptr()
+        out.reward, out.obs_cum_profit = h["reward"].data_ptr(), h["cumulative_profit"].data_ptr()
+        out.obs_days = h["days_passed"].data_ptr()
+        out.terminated, out.truncated = h["terminated"].data_ptr(), h["truncated"].data_ptr()
+        stream = torch.cuda.current_stream(self.device)
+        try:
+            _capi.check(self._lib.adc_step_philox(C.byref(a), C.c_void_p(stream.cuda_stream)))
+        finally:
+            (out.impressions, out.clicks, out.conversions, out.cost, out.revenue, out.reward,
+             out.obs_cum_profit, out.obs_days, out.terminated, out.truncated) = saved
+        self._step_count += 1
+        stream.synchronize()
+        return self._host_views()
+
+    def _host_views(self) -> Dict[str, torch.Tensor]:
+        if self._host_view_cache is None:
+            h = dict(self._host)
+            h["cumulative_profit"] = h["cumulative_profit"].view(-1, 1)
+            h["days_passed"] = h["days_passed"].view(-1, 1)
+            self._host_view_cache = h
+        return self._host_view_cache
 
     def host_bytes_per_step(self):
         """(h2d, d2h) bytes moved by step_host for this shape."""

@@ -85,3 +85,23 @@ def test_device_metrics_against_host_definitions():
         assert abs(float(pe["ncp"][e]) - m.compute_NCP(P[:, e], I)) < 1e-9
     s = m.summarize(m.reduce_metrics(acc.summary_vector()))
     assert s["n_envs"] == E
+
+
+def test_step_host_zero_copy_equals_staged_copy():
+    """The fused (UVA zero-copy) host round trip returns exactly what the staged one returns."""
+    from adcraft_b200 import keywords as kwm
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    rng = np.random.default_rng(8)
+    K, E = 33, 70
+    table = kwm.sample_implicit_keywords_from_quantiles(K, rng, {"mean_volume": 64, "conversion_rate": 0.8})
+    mk = lambda: VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=60.0, device="cuda", seed=4,
+                                         max_days=2)
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    for step in range(3):
+        bids = torch.from_numpy(np.round(rng.uniform(0.2, 1.5, (E, K)), 2).astype(np.float32)).pin_memory()
+        ha = {k: v.clone() for k, v in a.step_host(bids, zero_copy=True).items()}
+        hb = b.step_host(bids, zero_copy=False)
+        for k in hb:
+            assert torch.equal(ha[k], hb[k]), (k, step)
+        assert ha["impressions"].sum() > 0
