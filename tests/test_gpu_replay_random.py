@@ -31,9 +31,10 @@ def _random_tape(orc, rng, kind, K, vols, explicit_p=0.5):
                                cost=cost if kind == orc.EXPLICIT else None)
 
 
+@pytest.mark.parametrize("n_lanes", [0, 1])
 @pytest.mark.parametrize("kind_name", ["implicit", "explicit"])
 @pytest.mark.parametrize("alias", [False, True])
-def test_replay_matches_oracle(orc, kind_name, alias):
+def test_replay_matches_oracle(orc, kind_name, alias, n_lanes):
     from adcraft_b200.tape import DeviceTape
     from adcraft_b200.vector_env import VectorBiddingSimulation
     rng = np.random.default_rng(17 + alias)
@@ -41,12 +42,13 @@ def test_replay_matches_oracle(orc, kind_name, alias):
     K, E = 11, 37
     table = make_implicit_table(rng, K, 60) if kind == orc.IMPLICIT else make_explicit_table(rng, K)
     env = VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=1000.0, device="cuda",
-                                  budget_alias=alias, obs_dtype=torch.float64, autoreset=False)
+                                  budget_alias=alias, obs_dtype=torch.float64, autoreset=False, n_lanes=n_lanes)
     env.reset()
     budgets = rng.choice([0.0, 0.4, 2.5, 9.0, 30.0, 1e6], size=E)
     cum = np.zeros(E)
     for step in range(3):
         vols = rng.integers(0, 90, (E, K))
+        vols[rng.random((E, K)) < 0.1] += 300  # more than one 128-auction trip
         vols[rng.random((E, K)) < 0.15] = 0  # empty units
         tapes = [_random_tape(orc, rng, kind, K, vols[e]) for e in range(E)]
         bids = np.round(rng.uniform(0.01, 1.6, (E, K)), 2)
