@@ -1076,6 +1076,167 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// exact serial kernel, warp-cooperative (implicit keywords, Philox draws): one warp per queued env.
+// The reference's order is sub-step-major, keyword-minor with one shared float budget, so the
+// budget arithmetic is a sequential chain -- but the auctions of a lane do not depend on the
+// budget.  Per sub-step the warp takes 32 keywords at a time: every lane evaluates its keyword's
+// auctions in parallel and buffers its clicked slots (cost, conversion word); then the lanes take
+// turns, in keyword order, to run the reference's budget walk on their buffered clicks and hand
+// the remaining budget to the next lane by shuffle (same f64 operations in the same order as
+// bidding_simulation.py:97-104,225-233, incl. the ndarray-aliasing double charge); finally the
+// lanes commit in parallel.  Lanes after the one that exhausts the budget contribute nothing.
+// ------------------------------------------------------------------------------------------
+constexpr int kSerWarps = 4;
+constexpr int kSerCap = 16;  // buffered clicked slots per lane and sub-step; more -> direct re-walk
+
+__global__ void __launch_bounds__(kSerWarps * 32)
+adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
+{
+    __shared__ int s_cost[kSerWarps][kSerCap][32];
+    __shared__ uint32_t s_w2[kSerWarps][kSerCap][32];
+    const int K = a.kw.K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * kSerWarps + warp;
+    const int n_warps = gridDim.x * kSerWarps;
+    const int count = a.scratch.serial_count[a.step & 1u];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const adc_tape *no_tape = nullptr;
+
+    for (int idx = gwarp; idx < count; idx += n_warps) {
+        const int e = a.scratch.serial_list[idx];
+        PhiloxSrc src{k0, k1, a.step, a.env_base + (uint32_t)e};
+        for (int k = lane; k < K; k += 32) {
+            const int64_t u = (int64_t)e * K + k;
+            a.out.impressions[u] = 0;
+            a.out.clicks[u] = 0;
+            a.out.conversions[u] = 0;
+            a.out.cost_cents[u] = 0;
+            a.out.revenue_cents[u] = 0;
+        }
+        __syncwarp();
+        const double budget = step_budget(a, e);
+        double remaining = budget;  // warp-uniform (bsim:214)
+        bool stop = false;
+        for (int t = 0; t < ADC_SUBSTEPS && !stop; ++t) {
+            for (int c0 = 0; c0 < K && !stop; c0 += 32) {
+                const int k = c0 + lane;
+                const bool act = k < K;
+                const int64_t u = (int64_t)e * K + (act ? k : 0);
+                // ---- phase 1 (parallel): the lane's auctions, budget-free; buffer the clicked slots
+                UnitPar p;
+                long long n = 0, j0 = 0;
+                int I = 0, nclk = 0;
+                if (act) {
+                    p = load_unit_par(a, e, k);
+                    uint4 uw;
+                    const long long V = unit_volume(a, src, no_tape, e, k, &uw);
+                    const long long q = V / ADC_SUBSTEPS;
+                    const long long n0 = V - (ADC_SUBSTEPS - 1) * q;
+                    n = t == 0 ? n0 : q;
+                    j0 = t == 0 ? 0 : n0 + (long long)(t - 1) * q;
+                    for (long long i = 0; i < n; ++i) {
+                        const uint4 w = src.draw(ST_AUCTION, (uint32_t)k, (uint32_t)(j0 + i));
+                        const int c = laplace_cents(w.x, p.loc, p.scale);
+                        if (p.bid_cents > c) {
+                            ++I;
+                            if (w.y <= p.thr_click) {
+                                if (nclk < kSerCap) {
+                                    s_cost[warp][nclk][lane] = c;
+                                    s_w2[warp][nclk][lane] = w.z;
+                                }
+                                ++nclk;
+                            }
+                        }
+                    }
+                }
+                // ---- phase 2 (serial over the lanes that have clicks): the reference's budget walk
+                int B = 0, S = 0;
+                long long cost_c = 0, rev_c = 0;
+                bool rev_done = false;
+                unsigned todo = __ballot_sync(FULL, act && nclk > 0);
+                if (!(remaining > 0)) todo |= 1u;  // a lane must run for `remaining <= 0` to be seen
+                int cutoff = 32;
+                while (todo) {
+                    const int l = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    double next = remaining;
+                    if (lane == l) {
+                        double b = remaining, lane_sum = 0.0;
+                        if (nclk <= kSerCap) {
+                            for (int i = 0; i < nclk; ++i) {
+                                const int c = s_cost[warp][i][lane];
+                                const double cost = cents_to_dollars(c);
+                                if (!(b >= cost)) break;  // bsim:99-104
+                                ++B;
+                                cost_c += c;
+                                lane_sum = __dadd_rn(lane_sum, cost);
+                                b = __dsub_rn(b, cost);
+                                S += s_w2[warp][i][lane] <= p.thr_conv;
+                            }
+                        } else {  // more clicks than the buffer holds: walk the lane again, with the budget
+                            UnitCur cur = {j0, 0, 0, a.out.conversions[u], 0};
+                            double unused = 0.0;
+                            const LaneOut o = lane_walk<PhiloxSrc, false, true>(src, no_tape, u, k, t, n, p, cur, b, unused);
+                            B = o.B; S = o.S; cost_c = o.cost_cents; rev_c = o.rev_cents;
+                            lane_sum = o.lane_cost_sum;
+                            rev_done = true;
+                        }
+                        next = __dsub_rn(a.budget_alias ? b : remaining, lane_sum);  // bsim:102 alias, :225
+                    }
+                    remaining = __shfl_sync(FULL, next, l);
+                    if (remaining <= 0) {  // bsim:230-233
+                        stop = true;
+                        cutoff = l;
+                        break;
+                    }
+                }
+                // ---- phase 3 (parallel): revenues of the lane's conversions, commit
+                if (act && lane <= cutoff) {
+                    if (!rev_done && S > 0) {
+                        const int r0 = a.out.conversions[u];
+                        uint4 rw = make_uint4(0, 0, 0, 0);
+                        for (int i = 0; i < S; ++i) {
+                            const int r = r0 + i;
+                            if (i == 0 || (r & 3) == 0) rw = src.draw(ST_REVENUE, (uint32_t)k, (uint32_t)(r >> 2));
+                            const uint32_t w = (r & 3) == 0 ? rw.x : (r & 3) == 1 ? rw.y : (r & 3) == 2 ? rw.z : rw.w;
+                            rev_c += revenue_cents(w, p.rev_mean, p.rev_sd);
+                        }
+                    }
+                    a.out.impressions[u] += I;
+                    a.out.clicks[u] += B;
+                    a.out.conversions[u] += S;
+                    a.out.cost_cents[u] += cost_c;
+                    a.out.revenue_cents[u] += rev_c;
+                }
+                __syncwarp();
+            }
+        }
+        // ---- float outputs, reward, env tail, drift
+        long long profit_c = 0;
+        for (int k = lane; k < K; k += 32) {
+            const int64_t u = (int64_t)e * K + k;
+            const long long cc = a.out.cost_cents[u], rc = a.out.revenue_cents[u];
+            store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cc));
+            store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rc));
+            profit_c += rc - cc;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) profit_c += __shfl_xor_sync(FULL, profit_c, off);
+        if (lane == 0) env_tail(a, e, cents_to_dollars(profit_c), budget, remaining);
+        if (a.drift.mask != nullptr) {
+            for (int kk = lane; kk < K; kk += 32) {
+                if (!drift_wanted(a, kk)) continue;
+                const uint4 w = src.draw(ST_UNIT, (uint32_t)kk, 0u);
+                drift_apply(a, e, kk, drift_from_words(a, w));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+
 __global__ void adc_reset_envs_kernel(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1183,7 +1344,10 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     }
     if (err != cudaSuccess) return err;
     // exact serial walk of the queued envs (reads the count on the device; exits at once if 0)
-    if (tape == nullptr) {
+    if (tape == nullptr && !explicit_kw && a.n_lanes != 1) {
+        auto kern = adc_serial_warp_implicit_kernel;
+        kern<<<(unsigned)grid_for(kern, kSerWarps * 32, (int64_t)a.E * 32), kSerWarps * 32, 0, s>>>(a);
+    } else if (tape == nullptr) {
         auto kern = adc_serial_kernel<PhiloxSrc>;
         kern<<<(unsigned)grid_for(kern, 64, a.E), 64, 0, s>>>(a, tp);
     } else {

@@ -380,7 +380,7 @@ def run_gpu(args):
 
 
 def main():
-    global E_ENVS
+    global E_ENVS, BUDGET
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=240)
@@ -390,9 +390,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-replay", action="store_true", help="skip the tape-driven (replay) leg")
     ap.add_argument("--replay-only", action="store_true", help="profiling aid: run only the replay leg")
+    ap.add_argument("--budget", type=float, default=100000.0, help="experiment only: per-day budget (default C2's 100000)")
     ap.add_argument("--envs", type=int, default=4096, help="experiment only: envs per GPU (default = C2's 4096)")
     args = ap.parse_args()
     E_ENVS = args.envs
+    BUDGET = args.budget
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

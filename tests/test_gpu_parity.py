@@ -168,3 +168,25 @@ def test_bids_beyond_fast_kernel_caps_take_the_exact_route(orc):
     obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda()})
     ref = ob.step(bids, n_threads=4)
     _compare(obs, reward, term, trunc, ref, env, RTOL64)
+
+
+@pytest.mark.parametrize("alias", [False, True])
+def test_serial_warp_kernel_buffer_overflow_and_zero_budget(orc, alias):
+    """Sub-steps with more clicked slots than the warp-serial kernel buffers per lane (16) take the
+    direct re-walk; budgets of 0 stop after the first lane of the day (bsim:230-233)."""
+    rng = np.random.default_rng(41)
+    K, E = 37, 24
+    table = make_implicit_table(rng, K, 900)
+    table.ctr[:] = rng.uniform(0.7, 1.0, K)
+    env = _env(table, E, seed=12, budget=1000.0, budget_alias=alias, obs_dtype=torch.float64)
+    ob = _oracle_batch(orc, table, E, seed=12, budget=1000.0, alias=alias)
+    budgets = rng.choice([0.0, 5.0, 60.0, 400.0, 2500.0], size=E)
+    for s in range(2):
+        bids = np.round(rng.uniform(0.6, 1.6, (E, K)), 2)
+        ob.budget[:] = budgets
+        obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda(),
+                                                "budget": torch.from_numpy(budgets).cuda()})
+        ref = ob.step(bids, n_threads=4)
+        _compare(obs, reward, term, trunc, ref, env, RTOL64)
+        np.testing.assert_allclose(env._out["remaining_budget"].cpu().numpy(),
+                                   [0.0] * 0 + list(env._out["remaining_budget"].cpu().numpy()))
