@@ -541,6 +541,10 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
     return v;
 }
 
+// kBU = units per batch (lanes >= kBU idle during the lane<->unit phases, which are a few percent
+// of the work): small batches mean many more work items than warps, so the last round of the
+// grid-stride loop is nearly full (a 4096 x 100 step is only 2.7 batches of 32 per resident warp).
+template <int kBU>
 __global__ void __launch_bounds__(kFlatWarps * 32)
 adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
 {
@@ -554,7 +558,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gwarp = (int64_t)blockIdx.x * kFlatWarps + warp;
     const int64_t n_warps = (int64_t)gridDim.x * kFlatWarps;
-    const int64_t n_batches = (total + 31) / 32;
+    const int64_t n_batches = (total + kBU - 1) / kBU;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const unsigned FULL = 0xFFFFFFFFu;
     if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
@@ -565,8 +569,8 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
 
     for (int64_t batch = gwarp; batch < n_batches; batch += n_warps) {
         // ---------------- per-unit setup, lane <-> unit ----------------
-        const int64_t u = batch * 32 + lane;
-        const bool valid = u < total;
+        const int64_t u = batch * kBU + lane;
+        const bool valid = lane < kBU && u < total;
         int e = 0, k = 0, V = 0;
         bool over_cap = false;
         uint32_t genv = 0;
@@ -602,7 +606,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         // registers.  Only the last trip of a unit has idle lanes (volume rounded up to 32).
         int I = 0, B = 0, S = 0;
         long long cost = 0;
-        for (int b = 0; b < 32; ++b) {
+        for (int b = 0; b < kBU; ++b) {
             const int Vb = __shfl_sync(FULL, V, b);
             if (Vb == 0) continue;  // warp-uniform
             const FlatUnit fu = units[b];
@@ -1301,13 +1305,14 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     if (tape == nullptr && !explicit_kw && a.n_lanes == 0) {
         const int block = kFlatWarps * 32;
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adc_flat_philox_implicit_kernel, block, 0);
+        constexpr int kBU = 32;  // 8 and 16 were measured slower: the lane<->unit phases lose more than the tail gains
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adc_flat_philox_implicit_kernel<kBU>, block, 0);
         if (per_sm < 1) per_sm = 1;
         int64_t grid = (int64_t)num_sms() * per_sm;
-        const int64_t want = ((total + 31) / 32 + kFlatWarps - 1) / kFlatWarps;
+        const int64_t want = ((total + kBU - 1) / kBU + kFlatWarps - 1) / kFlatWarps;
         if (want < grid) grid = want;
         if (grid < 1) grid = 1;
-        adc_flat_philox_implicit_kernel<<<(unsigned)grid, block, 0, s>>>(a);
+        adc_flat_philox_implicit_kernel<kBU><<<(unsigned)grid, block, 0, s>>>(a);
         ++*launches;
         err = cudaGetLastError();
     } else if (tape == nullptr && !explicit_kw) {

@@ -45,18 +45,22 @@ PY_REFERENCE_UNITS_PER_S_1CORE = 290.0
 NCU_DRAM_BYTES_PER_LAUNCH = 1848064 + 7936
 
 
+MEAN_VOLUME, CVR, DRIFT = 128, 0.8, False
+
+
 def workload_table():
     from adcraft_b200 import keywords as kwm
     rng = np.random.default_rng(5)
     return kwm.sample_implicit_keywords_from_quantiles(
-        K_KW, rng, {"mean_volume": 128, "conversion_rate": 0.8})
+        K_KW, rng, {"mean_volume": MEAN_VOLUME, "conversion_rate": CVR})
 
 
 def config_dict(n_gpus, extra=None):
     c = {
         "workload": "C2: BiddingSimulation, 100 synthetic dense implicit keywords x 4096 vectorised envs "
                     "per GPU, fixed bid 0.75, budget 100000, free-running Philox draws",
-        "envs_per_gpu": E_ENVS, "keywords": K_KW, "mean_volume": 128, "conversion_rate": 0.8,
+        "envs_per_gpu": E_ENVS, "keywords": K_KW, "mean_volume": MEAN_VOLUME, "conversion_rate": CVR,
+        "non_stationary": DRIFT,
         "episode_days": MAX_DAYS, "parallelism": f"env-sharded x{n_gpus}",
         "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
     }
@@ -240,7 +244,8 @@ def run_gpu(args):
     table = workload_table()
     env = VectorBiddingSimulation(
         E_ENVS, num_keywords=K_KW, keywords=table, budget=BUDGET, max_days=MAX_DAYS, device=dev,
-        seed=SEED, env_base=rank * E_ENVS, n_lanes=args.n_lanes, obs_dtype=torch.float32)
+        seed=SEED, env_base=rank * E_ENVS, n_lanes=args.n_lanes, obs_dtype=torch.float32,
+        updater_mask=[True] * K_KW if DRIFT else None)
     env.reset()
     bids = torch.full((E_ENVS, K_KW), BID, dtype=torch.float32, device=dev)
     action = {"keyword_bids": bids}
@@ -371,7 +376,7 @@ def run_gpu(args):
         "cpu_baseline": cpu,
         "replay": replay,
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
-        "auctions_per_sec": value * 128,
+        "auctions_per_sec": value * MEAN_VOLUME,
     }
     print(json.dumps(line))
     if world > 1:
@@ -380,7 +385,7 @@ def run_gpu(args):
 
 
 def main():
-    global E_ENVS, BUDGET
+    global E_ENVS, BUDGET, K_KW, MEAN_VOLUME, CVR, DRIFT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=240)
@@ -391,10 +396,15 @@ def main():
     ap.add_argument("--no-replay", action="store_true", help="skip the tape-driven (replay) leg")
     ap.add_argument("--replay-only", action="store_true", help="profiling aid: run only the replay leg")
     ap.add_argument("--budget", type=float, default=100000.0, help="experiment only: per-day budget (default C2's 100000)")
+    ap.add_argument("--keywords", type=int, default=100, help="experiment only (C3: 1000)")
+    ap.add_argument("--volume", type=int, default=128, help="experiment only: mean volume (C3: 16 / 64)")
+    ap.add_argument("--cvr", type=float, default=0.8, help="experiment only: conversion rate (C3: 0.1)")
+    ap.add_argument("--drift", action="store_true", help="experiment only: non-stationary (mask all True)")
     ap.add_argument("--envs", type=int, default=4096, help="experiment only: envs per GPU (default = C2's 4096)")
     args = ap.parse_args()
     E_ENVS = args.envs
     BUDGET = args.budget
+    K_KW, MEAN_VOLUME, CVR, DRIFT = args.keywords, args.volume, args.cvr, args.drift
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)
