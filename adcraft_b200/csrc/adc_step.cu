@@ -552,6 +552,9 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     __shared__ FlatRev s_rev[kFlatWarps][32];
     __shared__ int s_start[kFlatWarps][33];
     __shared__ unsigned s_revsum[kFlatWarps][32][2];  // 24-bit split: native 32-bit smem atomics
+    __shared__ float2 s_tab[128];                     // Exp(1) sampler table, staged from global
+    if (threadIdx.x < 128) s_tab[threadIdx.x] = kNeglogTab[threadIdx.x];
+    __syncthreads();
 
     const int K = a.kw.K;
     const int64_t total = (int64_t)a.E * K;
@@ -613,7 +616,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             unsigned cntIB = 0, cntS = 0, cst = 0;  // I | B << 16 ; S ; cost cents (< 2^32, see caps)
             auto one = [&](int j) {
                 const uint4 w = philox_from_pre((uint32_t)j, fu.n0, fu.n1, fu.x3, k0, k1);
-                const int c = laplace_cents(w.x, fu.loc, fu.scale);
+                const int c = laplace_cents(w.x, fu.loc, fu.scale, s_tab);
                 const bool win = (j < Vb) && fu.bid_cents > c;
                 const bool clk = win && (w.y <= fu.thr_click);
                 const bool cnv = clk && (w.z <= fu.thr_conv);

@@ -92,14 +92,23 @@ float orc_lnf(float a)
     return fmaf((float)k, ORC_LN2F, r);
 }
 
-/* -ln((w31 + 0.5) / 2^31) for a 31-bit uniform integer: an Exp(1) variate. */
+/* -ln((w31 + 0.5) / 2^31) for a 31-bit uniform integer: an Exp(1) variate.
+ * a = 2*w31+1 is normalised (a << clz) to x = an/2^32 in [0.5,1); -ln(x) is read off a 128-entry
+ * chord table on the 7 bits below the leading one (error <= 7.6e-6, tools/gen_neglog_table.py):
+ *   e = clz * ln2 + T[idx] - S[idx] * lo,   lo = low 24 bits. */
+static const float ORC_NEGLOG_TAB[128][2] = {
+#include "neglog_table.inc"
+};
+
 float orc_neglog_u31(uint32_t w31)
 {
-    float a = (float)(2u * w31 + 1u); /* uint32 -> float, round-to-nearest-even */
-    int32_t k;
-    float m = split_mant(a, &k);
-    float r = ln_mant(m - 1.0f);
-    return fmaf((float)(32 - k), ORC_LN2F, -r);
+    const uint32_t a = 2u * w31 + 1u;
+    const int lz = __builtin_clz(a);
+    const uint32_t an = a << lz;
+    const uint32_t idx = (an >> 24) & 0x7Fu;
+    const uint32_t lo = an & 0x00FFFFFFu;
+    const float inner = fmaf(-(float)lo, ORC_NEGLOG_TAB[idx][1], ORC_NEGLOG_TAB[idx][0]);
+    return fmaf((float)lz, ORC_LN2F, inner);
 }
 
 /* Standard normal from one 32-bit word: sign bit + 31-bit tail probability, inverse

@@ -25,8 +25,9 @@ def build(force: bool = False) -> None:
     so = os.path.join(_BUILD, "liboracle.so")
     src = os.path.join(_HERE, "adcraft_oracle.c")
     hdr = os.path.join(_HERE, "adcraft_oracle.h")
+    tab = os.path.join(_HERE, "neglog_table.inc")
     if (not force and os.path.exists(so)
-            and os.path.getmtime(so) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            and os.path.getmtime(so) >= max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(tab))):
         return
     subprocess.run(["make", "-C", _HERE, "-s"], check=True)
 
