@@ -269,6 +269,22 @@ __device__ __forceinline__ uint32_t prob_threshold(double p)
     return (uint32_t)t;
 }
 
+// Implicit keywords take click and conversion from ONE word cc (two auctions share a Philox call):
+// click <=> cc <= T1 = prob_threshold(ctr); given a click cc is uniform on [0, T1], so
+// u_conv = (cc + 0.5) / (T1 + 1) is a fresh uniform and conversion <=> u_conv <= cvr (the
+// reference's comparison, synthetic_kw_helpers.py:77) <=> cc < T2, T2 = #{v <= T1 : u_conv(v) <= cvr}.
+__device__ __forceinline__ unsigned long long conv_threshold(uint32_t t1, double cvr)
+{
+    const double n = __dadd_rn((double)t1, 1.0);
+    double est = ceil(__dsub_rn(__dmul_rn(cvr, n), 0.5));
+    if (!(est > 0.0)) est = 0.0;
+    if (est > n) est = n;
+    long long v = (long long)est;
+    while (v > 0 && __ddiv_rn(__dadd_rn((double)(v - 1), 0.5), n) > cvr) --v;
+    while ((double)v < n && __ddiv_rn(__dadd_rn((double)v, 0.5), n) <= cvr) ++v;
+    return (unsigned long long)v;
+}
+
 __device__ __forceinline__ double explicit_cost(uint32_t w3, double bid)
 {
     const double xs = __dsqrt_rn(bid);

@@ -154,6 +154,8 @@ struct UnitPar {
     float loc, scale, rev_mean, rev_sd;
     double ctr, cvr;
     uint32_t thr_click, thr_conv, thr_impr;
+    uint32_t thr_cc;  // implicit: conversion <=> conv_all || cc < thr_cc  (cc = the click word)
+    bool conv_all;
 };
 
 struct LaneOut {
@@ -208,8 +210,10 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
         bool conv;
         if constexpr (Src::kTape)
             conv = tape_at(tp->u_conv, tp->conv_off, u, cur.n_conv + o.B, 2.0, o.overrun) <= p.cvr;
-        else
+        else if constexpr (kExplicit)
             conv = w2 <= p.thr_conv;
+        else
+            conv = p.conv_all || w2 < p.thr_cc;  // w2 is the click word cc
         o.B += 1;
         o.cost_cents += cost_c;
         if constexpr (kExplicit) day_cost = __dadd_rn(day_cost, cost);
@@ -243,10 +247,11 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
             if constexpr (Src::kTape) {
                 c = tape_at(tp->comp_cents, tp->comp_off, u, j, 0x7FFFFFFF, o.overrun);
             } else {
-                const uint4 w = src.draw(ST_AUCTION, (uint32_t)kw, (uint32_t)j);
-                c = laplace_cents(w.x, p.loc, p.scale);
-                w1 = w.y;
-                w2 = w.z;
+                // two auctions per Philox call: even j -> words x,y; odd j -> words z,w
+                const uint4 w = src.draw(ST_AUCTION, (uint32_t)kw, (uint32_t)(j >> 1));
+                c = laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale);
+                w1 = (j & 1) ? w.w : w.y;
+                w2 = w1;
             }
             if (p.bid_cents > c) {
                 bool clicked;
@@ -315,8 +320,15 @@ __device__ __forceinline__ UnitPar load_unit_par(const adc_step_args &a, int e, 
     p.loc = (float)a.kw.p1[pi];
     p.scale = (float)a.kw.p2[pi];
     p.thr_impr = 0u;
-    if (a.kw.kind == ADC_EXPLICIT)
+    p.thr_cc = 0u;
+    p.conv_all = false;
+    if (a.kw.kind == ADC_EXPLICIT) {
         p.thr_impr = prob_threshold(threshold_sigmoid(p.bid, a.kw.impression_thresh, a.kw.p1[pi], a.kw.p2[pi]));
+    } else {
+        const unsigned long long t2 = conv_threshold(p.thr_click, p.cvr);
+        p.conv_all = t2 > 0xFFFFFFFFull;
+        p.thr_cc = p.conv_all ? 0xFFFFFFFFu : (uint32_t)t2;
+    }
     return p;
 }
 
@@ -439,11 +451,12 @@ adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         long long cost = 0;
         const uint32_t c2 = stream_word(ST_AUCTION, 0u, (uint32_t)k);
         for (long long j = lane; j < V; j += L) {
-            const uint4 w = philox4x32_10((uint32_t)j, a.step, c2, genv, k0, k1);
-            const int c = laplace_cents(w.x, p.loc, p.scale);
+            const uint4 w = philox4x32_10((uint32_t)(j >> 1), a.step, c2, genv, k0, k1);
+            const uint32_t cc = (j & 1) ? w.w : w.y;
+            const int c = laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale);
             const bool win = p.bid_cents > c;
-            const bool clk = win && (w.y <= p.thr_click);
-            const bool cnv = clk && (w.z <= p.thr_conv);
+            const bool clk = win && (cc <= p.thr_click);
+            const bool cnv = clk && (p.conv_all || cc < p.thr_cc);
             I += win;
             B += clk;
             S += cnv;
@@ -595,7 +608,8 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), genv, k0, k1);
             FlatUnit fu;
             fu.bid_cents = p.bid_cents; fu.loc = p.loc; fu.scale = p.scale;
-            fu.thr_click = p.thr_click; fu.thr_conv = p.thr_conv;
+            fu.thr_click = p.thr_click; fu.thr_conv = p.thr_cc;
+            if (p.conv_all) fu.bid_cents |= (int)0x80000000u;  // flag rides in the sign bit (bids <= 65535)
             fu.n0 = pa.n0; fu.n1 = pa.n1; fu.x3 = pa.x3;
             units[lane] = fu;
         }
@@ -612,21 +626,37 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         for (int b = 0; b < kBU; ++b) {
             const int Vb = __shfl_sync(FULL, V, b);
             if (Vb == 0) continue;  // warp-uniform
-            const FlatUnit fu = units[b];
+            FlatUnit fu = units[b];
+            const bool conv_all = fu.bid_cents < 0;
+            fu.bid_cents &= 0x7FFFFFFF;
             unsigned cntIB = 0, cntS = 0, cst = 0;  // I | B << 16 ; S ; cost cents (< 2^32, see caps)
-            auto one = [&](int j) {
-                const uint4 w = philox_from_pre((uint32_t)j, fu.n0, fu.n1, fu.x3, k0, k1);
-                const int c = laplace_cents(w.x, fu.loc, fu.scale, s_tab);
-                const bool win = (j < Vb) && fu.bid_cents > c;
-                const bool clk = win && (w.y <= fu.thr_click);
-                const bool cnv = clk && (w.z <= fu.thr_conv);
+            // one auction: competitor bid from `wc`, click + conversion from the single word `cc`
+            auto tally = [&](bool act, uint32_t wc, uint32_t cc) {
+                const int c = laplace_cents(wc, fu.loc, fu.scale, s_tab);
+                const bool win = act && fu.bid_cents > c;
+                const bool clk = win && (cc <= fu.thr_click);
+                const bool cnv = clk && (conv_all || cc < fu.thr_conv);
                 cntIB += (win ? 1u : 0u) + (clk ? 0x10000u : 0u);
                 cntS += cnv ? 1u : 0u;
                 cst += clk ? (unsigned)c : 0u;
             };
-            for (int base = 0; base < Vb; base += 64) {
-                one(base + lane);
-                if (base + 32 < Vb) one(base + 32 + lane);  // warp-uniform: second independent chain
+            // full trips: each lane takes one Philox call = two consecutive auctions (64 per trip)
+            int base = 0;
+            for (; base + 64 <= Vb; base += 64) {
+                const uint4 w = philox_from_pre((uint32_t)((base >> 1) + lane), fu.n0, fu.n1, fu.x3, k0, k1);
+                tally(true, w.x, w.y);
+                tally(true, w.z, w.w);
+            }
+            const int rem = Vb - base;  // 0..63 auctions left
+            if (rem > 32) {             // still worth pairing: lanes past the end idle
+                const int j = base + 2 * lane;
+                const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
+                tally(j < Vb, w.x, w.y);
+                tally(j + 1 < Vb, w.z, w.w);
+            } else if (rem > 0) {       // at most 32 left: one auction per lane, half a call each
+                const int j = base + lane;
+                const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
+                tally(j < Vb, (j & 1) ? w.z : w.x, (j & 1) ? w.w : w.y);
             }
             const unsigned tI = __reduce_add_sync(FULL, cntIB & 0xFFFFu);
             const unsigned tB = __reduce_add_sync(FULL, cntIB >> 16);
@@ -687,7 +717,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             a.out.revenue_cents[u] = rev;
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
-            safe = unit_done(a, e, rev - cost, over_cap ? (1LL << 60) : cost);
+            safe = unit_done(a, e, rev - cost, over_cap ? (1LL << 40) : cost);
         }
         if (a.drift.mask != nullptr) {
             // drift of finished budget-safe envs (env:246), the warp shares each env's keywords
@@ -882,7 +912,7 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
             a.out.revenue_cents[u] = rev;
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
-            safe = unit_done(a, e, rev - cost, my_overrun ? (1LL << 60) : cost);
+            safe = unit_done(a, e, rev - cost, my_overrun ? (1LL << 40) : cost);
         }
         if (a.drift.mask != nullptr) {
             unsigned todo = __ballot_sync(FULL, safe != 0);
@@ -944,8 +974,9 @@ adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant_
             overrun |= o.overrun;
         }
         // a truncated tape means the recorded run stopped early: make the env look unaffordable
-        // so that unit_done queues it for the exact serial walk
-        const long long kForceSerialCents = 1LL << 60;
+        // so that unit_done queues it for the exact serial walk (2^40 cents per unit: K < 2^20
+        // of them still fit the int64 env accumulator)
+        const long long kForceSerialCents = 1LL << 40;
         a.out.impressions[u] = I;
         a.out.clicks[u] = B;
         a.out.conversions[u] = S;
@@ -1144,14 +1175,16 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                     n = t == 0 ? n0 : q;
                     j0 = t == 0 ? 0 : n0 + (long long)(t - 1) * q;
                     for (long long i = 0; i < n; ++i) {
-                        const uint4 w = src.draw(ST_AUCTION, (uint32_t)k, (uint32_t)(j0 + i));
-                        const int c = laplace_cents(w.x, p.loc, p.scale);
+                        const long long j = j0 + i;
+                        const uint4 w = src.draw(ST_AUCTION, (uint32_t)k, (uint32_t)(j >> 1));
+                        const uint32_t cc = (j & 1) ? w.w : w.y;
+                        const int c = laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale);
                         if (p.bid_cents > c) {
                             ++I;
-                            if (w.y <= p.thr_click) {
+                            if (cc <= p.thr_click) {
                                 if (nclk < kSerCap) {
                                     s_cost[warp][nclk][lane] = c;
-                                    s_w2[warp][nclk][lane] = w.z;
+                                    s_w2[warp][nclk][lane] = cc;
                                 }
                                 ++nclk;
                             }
@@ -1180,7 +1213,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                                 cost_c += c;
                                 lane_sum = __dadd_rn(lane_sum, cost);
                                 b = __dsub_rn(b, cost);
-                                S += s_w2[warp][i][lane] <= p.thr_conv;
+                                S += p.conv_all || s_w2[warp][i][lane] < p.thr_cc;
                             }
                         } else {  // more clicks than the buffer holds: walk the lane again, with the budget
                             UnitCur cur = {j0, 0, 0, a.out.conversions[u], 0};

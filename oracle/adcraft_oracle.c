@@ -229,6 +229,28 @@ uint32_t orc_prob_threshold(double p)
     return (uint32_t)t;
 }
 
+/* Implicit keywords draw click and conversion from ONE 32-bit word cc (two auctions share a
+ * Philox call): click <=> cc <= T1 = orc_prob_threshold(ctr).  Given a click, cc is uniform on
+ * [0, T1], so u_conv = (cc + 0.5) / (T1 + 1) is a uniform on (0,1) independent of everything the
+ * reference has used so far; conversion <=> u_conv <= cvr (the reference's own comparison,
+ * synthetic_kw_helpers.py:77) <=> cc < T2 with T2 = #{v in [0,T1] : fl((v+0.5)/(T1+1)) <= cvr}. */
+double orc_conv_uniform(uint32_t cc, uint32_t t1)
+{
+    return ((double)cc + 0.5) / ((double)t1 + 1.0);
+}
+
+uint64_t orc_conv_threshold(uint32_t t1, double cvr)
+{
+    const double n = (double)t1 + 1.0;
+    double est = ceil(cvr * n - 0.5);
+    if (!(est > 0.0)) est = 0.0;
+    if (est > n) est = n;
+    int64_t v = (int64_t)est;
+    while (v > 0 && ((double)(v - 1) + 0.5) / n > cvr) --v;
+    while ((double)v < n && ((double)v + 0.5) / n <= cvr) ++v;
+    return (uint64_t)v;
+}
+
 /* src/lib.rs:53-67 cost_create (constant 4.4) for one impression. */
 double orc_explicit_cost(uint32_t w3, double bid)
 {
@@ -282,7 +304,7 @@ typedef struct { /* per-keyword running cursors for one env step */
 
 static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, double *remaining,
                     int alias, int64_t n, draw_src *src, kw_cursor *cur, orc_result *out,
-                    uint32_t thr_click, uint32_t thr_conv, uint32_t thr_impr,
+                    uint32_t thr_click, uint32_t thr_conv, uint64_t thr_cc, uint32_t thr_impr,
                     double *cost_seq, double *rev_seq)
 {
     /* One call of simulate_epoch_of_bidding (bidding_simulation.py:44-120). */
@@ -310,9 +332,10 @@ static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, dou
             if (src->mode == 0) {
                 c = tp->comp_cents[tp->comp_off[k] + j];
             } else {
-                draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_AUCTION, (uint32_t)j, w);
-                c = orc_laplace_cents(w[0], (float)kw->p1[k], (float)kw->p2[k]);
-                w1 = w[1]; w2 = w[2];
+                /* two auctions per Philox call: even j -> words 0,1; odd j -> words 2,3 */
+                draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_AUCTION, (uint32_t)(j >> 1), w);
+                c = orc_laplace_cents(w[(j & 1) ? 2 : 0], (float)kw->p1[k], (float)kw->p2[k]);
+                w1 = w[(j & 1) ? 3 : 1]; w2 = w1; /* click and conversion share the word cc */
                 if (rec && j < rec->cap_per_kw) { rec->comp_cents[(int64_t)k * rec->cap_per_kw + j] = c; rec->n_comp[k] = (int32_t)(j + 1); }
             }
             /* nth_price_auction(n=2, num_winners=1) with one competitor: win iff bid > c
@@ -411,8 +434,13 @@ static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, dou
         if (src->mode == 0) {
             conv = tp->u_conv[tp->conv_off[k] + cur->n_conv + i] <= kw->cvr[k];
         } else {
-            conv = aw2[i] <= thr_conv;
-            if (rec && cur->n_conv + i < rec->cap_per_kw) rec->u_conv[(int64_t)k * rec->cap_per_kw + cur->n_conv + i] = (double)aw2[i] * 2.3283064365386963e-10;
+            if (explicit_kw) {
+                conv = aw2[i] <= thr_conv;
+                if (rec && cur->n_conv + i < rec->cap_per_kw) rec->u_conv[(int64_t)k * rec->cap_per_kw + cur->n_conv + i] = (double)aw2[i] * 2.3283064365386963e-10;
+            } else {
+                conv = (uint64_t)aw2[i] < thr_cc;
+                if (rec && cur->n_conv + i < rec->cap_per_kw) rec->u_conv[(int64_t)k * rec->cap_per_kw + cur->n_conv + i] = orc_conv_uniform(aw2[i], thr_click);
+            }
         }
         S += conv;
     }
@@ -467,6 +495,7 @@ static int step_common(const orc_keywords *kw, const int32_t *bid_cents, double 
     int64_t *vol = (int64_t *)malloc(sizeof(int64_t) * K);
     kw_cursor *cur = (kw_cursor *)calloc(K, sizeof(kw_cursor));
     uint32_t *thr = (uint32_t *)malloc(sizeof(uint32_t) * 3 * K);
+    uint64_t *thr_cc = (uint64_t *)malloc(sizeof(uint64_t) * K);
     double *cost_seq = (double *)calloc(K, sizeof(double));
     double *rev_seq = (double *)calloc(K, sizeof(double));
     uint32_t w[4];
@@ -488,6 +517,7 @@ static int step_common(const orc_keywords *kw, const int32_t *bid_cents, double 
         thr[3 * k + 0] = orc_prob_threshold(kw->ctr[k]);
         thr[3 * k + 1] = orc_prob_threshold(kw->cvr[k]);
         thr[3 * k + 2] = 0;
+        thr_cc[k] = orc_conv_threshold(thr[3 * k + 0], kw->cvr[k]);
         if (kw->kind == ORC_EXPLICIT) {
             double bid = (double)bid_cents[k] / 100.0;
             double p = orc_threshold_sigmoid(bid, kw->impression_thresh, kw->p1[k], kw->p2[k]);
@@ -510,7 +540,7 @@ static int step_common(const orc_keywords *kw, const int32_t *bid_cents, double 
             int64_t q = vol[k] / ORC_SUBSTEPS;
             int64_t n = (t == 0) ? vol[k] - (ORC_SUBSTEPS - 1) * q : q;
             rc = lane_run(kw, k, t, bid_cents[k], &remaining, alias, n, src, &cur[k], out,
-                          thr[3 * k], thr[3 * k + 1], thr[3 * k + 2], &cost_seq[k], &rev_seq[k]);
+                          thr[3 * k], thr[3 * k + 1], thr_cc[k], thr[3 * k + 2], &cost_seq[k], &rev_seq[k]);
             if (rc) { stop = 1; break; }
             ++lanes;
             if (remaining <= 0) { stop = 1; break; } /* bsim:230-233 */
@@ -527,7 +557,7 @@ static int step_common(const orc_keywords *kw, const int32_t *bid_cents, double 
     out->reward = reward;
     out->remaining_budget = remaining;
     out->lanes_run = lanes;
-    free(vol); free(cur); free(thr); free(cost_seq); free(rev_seq);
+    free(vol); free(cur); free(thr); free(thr_cc); free(cost_seq); free(rev_seq);
     return rc;
 }
 

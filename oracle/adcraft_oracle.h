@@ -80,6 +80,8 @@ int32_t orc_revenue_cents(uint32_t w, float mean, float std);
 int64_t orc_volume(uint32_t w, double mean, double std);
 double orc_threshold_sigmoid(double bid, double thresh, double intercept, double slope);
 uint32_t orc_prob_threshold(double p);
+uint64_t orc_conv_threshold(uint32_t t1, double cvr);
+double orc_conv_uniform(uint32_t cc, uint32_t t1);
 double orc_explicit_cost(uint32_t w3, double bid);
 double orc_sum_array(const double *x, int64_t n); /* ndarray::sum order, src/lib.rs:107-111 */
 
