@@ -574,7 +574,15 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gwarp = (int64_t)blockIdx.x * kFlatWarps + warp;
     const int64_t n_warps = (int64_t)gridDim.x * kFlatWarps;
-    const int64_t n_batches = (total + kBU - 1) / kBU;
+    // Work items: R full rounds of kBU-unit batches (every warp gets exactly R of them), then the
+    // remaining units in small batches of kTail units, dealt round-robin.  The small batches cost a
+    // little more per unit (the lane<->unit phases run at kTail/32 lane efficiency) but they even
+    // out the end of the kernel: a 4096 x 100 step is only 2.7 big batches per resident warp.
+    constexpr int kTail = 8;
+    const int64_t big_rounds = total / ((int64_t)kBU * n_warps);
+    const int64_t n_big = big_rounds * n_warps;
+    const int64_t tail_units = total - n_big * kBU;
+    const int64_t n_batches = n_big + (tail_units + kTail - 1) / kTail;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const unsigned FULL = 0xFFFFFFFFu;
     if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
@@ -585,8 +593,10 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
 
     for (int64_t batch = gwarp; batch < n_batches; batch += n_warps) {
         // ---------------- per-unit setup, lane <-> unit ----------------
-        const int64_t u = batch * kBU + lane;
-        const bool valid = lane < kBU && u < total;
+        const bool big = batch < n_big;
+        const int cnt = big ? kBU : kTail;
+        const int64_t u = (big ? batch * kBU : n_big * kBU + (batch - n_big) * kTail) + lane;
+        const bool valid = lane < cnt && u < total;
         int e = 0, k = 0, V = 0;
         bool over_cap = false;
         uint32_t genv = 0;
@@ -623,7 +633,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         // registers.  Only the last trip of a unit has idle lanes (volume rounded up to 32).
         int I = 0, B = 0, S = 0;
         long long cost = 0;
-        for (int b = 0; b < kBU; ++b) {
+        for (int b = 0; b < cnt; ++b) {
             const int Vb = __shfl_sync(FULL, V, b);
             if (Vb == 0) continue;  // warp-uniform
             FlatUnit fu = units[b];
