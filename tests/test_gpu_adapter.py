@@ -105,3 +105,14 @@ def test_step_host_zero_copy_equals_staged_copy():
         for k in hb:
             assert torch.equal(ha[k], hb[k]), (k, step)
         assert ha["impressions"].sum() > 0
+
+
+def test_rollout_example_runs():
+    """examples/rollout_collect.py: MLP policy on flat observations, metric accumulation, reduce."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "rollout_collect.py"), "--envs", "256",
+                          "--keywords", "20", "--steps", "5"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["n_envs"] == 256 and d["episodes"] == 256 and d["units_per_s"] > 0
