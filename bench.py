@@ -272,7 +272,11 @@ def run_gpu(args):
 
     # ---- device-timed steps, inputs resident in HBM --------------------------------------
     for _ in range(max(args.warmup, 3)):
-        env.step(action)
+        obs, reward, term, trunc, _ = env.step(action)
+    if world > 1:  # NCCL connects lazily: establish the all-reduce path before the timed region
+        for _ in range(2):
+            episode_reduce(obs, reward, term)
+        metric_acc.zero_()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     lib = _capi.load()
