@@ -56,6 +56,11 @@ class Scratch(C.Structure):
     ]
 
 
+class Detail(C.Structure):
+    _fields_ = [("cap", C.c_int32), ("costs", C.c_void_p), ("rev_per_cost", C.c_void_p),
+                ("n_recorded", C.c_void_p), ("volume_seen", C.c_void_p)]
+
+
 class StepArgs(C.Structure):
     _fields_ = [
         ("E", C.c_int32), ("env_base", C.c_uint32), ("step", C.c_uint32), ("seed", C.c_uint64),
@@ -63,7 +68,7 @@ class StepArgs(C.Structure):
         ("force_serial", C.c_int32),
         ("kw", Keywords), ("env", EnvState), ("drift", Drift),
         ("bids", C.c_void_p), ("bids_dtype", C.c_int32), ("budget_in", C.c_void_p),
-        ("out", StepOut), ("scratch", Scratch),
+        ("out", StepOut), ("scratch", Scratch), ("detail", Detail),
     ]
 
 

@@ -188,7 +188,8 @@ __device__ __forceinline__ T tape_at(const T *vals, const int64_t *off, int64_t 
 template <typename Src, bool kExplicit, bool kBudget>
 __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp, int64_t u, int kw,
                                              int t, long long n, const UnitPar &p, UnitCur &cur,
-                                             double &b, double &day_cost)
+                                             double &b, double &day_cost,
+                                             const adc_detail *det = nullptr)
 {
     LaneOut o;
     o.I = o.B = o.S = 0;
@@ -219,6 +220,12 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
         if constexpr (kExplicit) day_cost = __dadd_rn(day_cost, cost);
         o.lane_cost_sum = __dadd_rn(o.lane_cost_sum, cost);
         if (kBudget) b = __dsub_rn(b, cost);
+        const int click_ord = cur.n_conv + o.B - 1;  // ordinal of this accepted click in the day
+        const bool rec = det != nullptr && det->costs != nullptr && click_ord < det->cap;
+        if (rec) {
+            det->costs[u * det->cap + click_ord] = cost;
+            det->rev_per_cost[u * det->cap + click_ord] = 0.0;
+        }
         if (conv) {
             const int r = cur.n_rev + o.S;
             int rc;
@@ -234,6 +241,7 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
             }
             o.S += 1;
             o.rev_cents += rc;
+            if (rec) det->rev_per_cost[u * det->cap + click_ord] = cents_to_dollars(rc);
         }
     };
 
@@ -1044,7 +1052,12 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
             a.out.cost_cents[u] = 0;
             a.out.revenue_cents[u] = 0;
             if (explicit_kw) a.scratch.unit_cost_f64[u] = 0.0;
+            if (a.detail.costs != nullptr) {
+                a.detail.n_recorded[u] = 0;
+                a.detail.volume_seen[u] = 0.0;
+            }
         }
+        const adc_detail *det = a.detail.costs != nullptr ? &a.detail : nullptr;
         const double budget = step_budget(a, e);
         double remaining = budget;  // bsim:214
         bool stop = false;
@@ -1077,11 +1090,16 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
                 LaneOut o;
                 if (explicit_kw) {
                     double day_cost = a.scratch.unit_cost_f64[u];
-                    o = lane_walk<Src, true, true>(src, &tape, u, k, t, n, p, cur, b, day_cost);
+                    o = lane_walk<Src, true, true>(src, &tape, u, k, t, n, p, cur, b, day_cost, det);
                     a.scratch.unit_cost_f64[u] = day_cost;
                 } else {
                     double unused = 0.0;
-                    o = lane_walk<Src, false, true>(src, &tape, u, k, t, n, p, cur, b, unused);
+                    o = lane_walk<Src, false, true>(src, &tape, u, k, t, n, p, cur, b, unused, det);
+                }
+                if (det != nullptr) {
+                    const int nb = a.out.clicks[u] + o.B;
+                    det->n_recorded[u] = nb < det->cap ? nb : det->cap;
+                    if (o.I >= 1) det->volume_seen[u] += (double)n;  // bsim:130-137
                 }
                 a.out.impressions[u] += o.I;
                 a.out.clicks[u] += o.B;

@@ -7,8 +7,9 @@ of shape ``(1,)``), same info keys, ``render`` / ``close`` / ``set_updater_mask`
 ``bidding_sim_creator``.  All arithmetic happens on the GPU through VectorBiddingSimulation.
 
 Differences, by construction: draws come from Philox counters (the reference's Rust RNG cannot be
-seeded, so its numbers are not reproducible either); ``info["bidding_outcomes"]`` lists per-keyword
-totals instead of every click's cost (the per-click lists are not materialised on the device).
+seeded, so its numbers are not reproducible either).  ``info["bidding_outcomes"]`` carries every
+click's cost, the per-click revenues and the impression share like the reference's string: the
+single-env adapter always takes the exact serial kernel, which records them.
 """
 from __future__ import annotations
 
@@ -39,7 +40,8 @@ class BiddingSimulation(_Base):
             1, keyword_config=keyword_config, num_keywords=num_keywords, budget=budget,
             render_mode=render_mode, loss_threshold=loss_threshold, max_days=max_days,
             updater_params=updater_params, updater_mask=updater_mask,
-            obs_dtype=torch.float64, autoreset=False, **kwargs)
+            obs_dtype=torch.float64, autoreset=False, n_lanes=1, detail_cap=kwargs.pop("detail_cap", 4096),
+            **kwargs)
         self.keyword_config = keyword_config
         self.num_keywords = num_keywords
         self.budget = budget
@@ -106,7 +108,8 @@ class BiddingSimulation(_Base):
         bids_in = np.asarray(action["keyword_bids"], dtype=np.float64).reshape(1, -1)
         act = {"keyword_bids": bids_in,
                "budget": np.asarray(budget_in, dtype=np.float64).reshape(-1)[:1]}
-        obs, reward, term, trunc, _ = self._vec.step(act)
+        # the exact serial walk also records the per-click lists of info["bidding_outcomes"]
+        obs, reward, term, trunc, _ = self._vec.step(act, force_serial=True)
         torch.cuda.current_stream(self._vec.device).synchronize()
         o = {k: v[0].cpu().numpy() for k, v in obs.items()}
         observations = dict(
@@ -122,14 +125,8 @@ class BiddingSimulation(_Base):
         self.budget = (np.array([left]) if self._vec.budget_alias
                        else np.round(np.asarray(budget_in, dtype=float), 2))
         bids = [float(np.round(np.maximum(b, 0.01), 2)) for b in bids_in[0]]
-        outcomes = [dict(bid=b, impressions=int(observations["impressions"][k]),
-                         buyside_clicks=int(observations["buyside_clicks"][k]),
-                         cost=float(observations["cost"][k]),
-                         sellside_conversions=int(observations["sellside_conversions"][k]),
-                         revenue=float(observations["revenue"][k]),
-                         profit=float(observations["revenue"][k] - observations["cost"][k]))
-                    for k, b in enumerate(bids)]
-        info = {"bids": bids, "bidding_outcomes": repr(outcomes),
+        outcomes = self._vec.bidding_outcomes(0)
+        info = {"bids": bids, "bidding_outcomes": repr_outcomes(outcomes),
                 "keyword_params": self._describe_params()}
         terminated, truncated = bool(term[0]), bool(trunc[0])
         if self.render_mode == "ansi":
@@ -157,6 +154,34 @@ class BiddingSimulation(_Base):
 
     def close(self) -> None:
         pass
+
+
+def _rust_display(v: float) -> str:
+    """Rust's `{}` for f64 (src/lib.rs:269): shortest round-trip digits, no trailing `.0`."""
+    v = float(v)
+    if v == int(v) and abs(v) < 1e16:
+        return str(int(v))
+    return repr(v)
+
+
+def _rust_debug_list(vs) -> str:
+    """Rust's `{:?}` for Vec<f64>: always a decimal point."""
+    return "[" + ", ".join(repr(float(v)) for v in vs) + "]"
+
+
+def repr_outcomes(outcomes: List[dict]) -> str:
+    """``rust.repr_outcomes_py`` (src/lib.rs:250-275), host-side string formatting only."""
+    parts = []
+    for o in outcomes:
+        parts.append(
+            "{" + f"'bid': {_rust_display(o['bid'])}, 'impressions': {o['impressions']}, "
+            f"'impression_share': {_rust_display(o['impression_share'])}, "
+            f"'buyside_clicks': {o['buyside_clicks']}, 'costs': {_rust_debug_list(o['costs'])}, "
+            f"'sellside_conversions': {o['sellside_conversions']}, "
+            f"'revenues': {_rust_debug_list(o['revenues'])}, "
+            f"'revenues_per_cost': {_rust_debug_list(o['revenues_per_cost'])}, "
+            f"'profit': {_rust_display(o['profit'])}" + "}")
+    return "[" + ", ".join(parts) + "]"
 
 
 def bidding_sim_creator(env_config: Dict) -> BiddingSimulation:

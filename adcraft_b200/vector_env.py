@@ -58,6 +58,7 @@ class VectorBiddingSimulation:
         n_lanes: int = 0,
         budget_alias: bool = False,
         autoreset: bool = True,
+        detail_cap: int = 0,
         **kwargs,
     ) -> None:
         assert render_mode is None or render_mode in self.metadata["render_modes"], (
@@ -81,6 +82,7 @@ class VectorBiddingSimulation:
         self.n_lanes = int(n_lanes)
         self.budget_alias = bool(budget_alias)
         self.autoreset = bool(autoreset)
+        self.detail_cap = int(detail_cap)  # > 0: record per-click lists on the exact serial path
         self.shared_keywords = bool(shared_keywords)
         self.obs_dtype = obs_dtype
         assert obs_dtype in (torch.float32, torch.float64)
@@ -126,6 +128,11 @@ class VectorBiddingSimulation:
         self._scratch = dict(
             serial_list=z(E, dtype=i32), serial_count=z(2, dtype=i32), env_profit=z(E, dtype=i64),
             env_cost=z(E, dtype=i64), env_done=z(E, dtype=i32), unit_cost_f64=z(E, K, dtype=f64))
+        self._detail = None
+        if self.detail_cap > 0:
+            c = self.detail_cap
+            self._detail = dict(costs=z(E, K, c, dtype=f64), rev_per_cost=z(E, K, c, dtype=f64),
+                                n_recorded=z(E, K, dtype=i32), volume_seen=z(E, K, dtype=f64))
         self._bids_dev = {torch.float32: z(E, K, dtype=torch.float32), torch.float64: z(E, K, dtype=f64)}
         self._budget_dev = {torch.float32: z(E, dtype=torch.float32), torch.float64: z(E, dtype=f64)}
         self._mask_dev: Optional[torch.Tensor] = None
@@ -168,6 +175,32 @@ class VectorBiddingSimulation:
         self.keywords = table
         self.kind = table.kind
         self._have_keywords = True
+
+    def bidding_outcomes(self, e: int = 0) -> List[dict]:
+        """Per-keyword ``BiddingOutcomes`` dicts (bidding_simulation.py:10-38) of env e for the last
+        step, incl. the per-click lists; needs ``detail_cap > 0`` and a step run with
+        ``force_serial=True`` and ``n_lanes=1`` (only the exact serial walk records them)."""
+        assert self._detail is not None, "construct the env with detail_cap > 0"
+        o, d = self._out, self._detail
+        K = self.num_keywords
+        n = d["n_recorded"][e].cpu().numpy()
+        costs, rpc = d["costs"][e].cpu().numpy(), d["rev_per_cost"][e].cpu().numpy()
+        vol = d["volume_seen"][e].cpu().numpy()
+        imp = o["impressions"][e].cpu().numpy()
+        bids = self._last_bids[e].double().cpu().numpy()
+        out = []
+        for k in range(K):
+            c, r = costs[k, :n[k]], rpc[k, :n[k]]
+            revs = r[r > 0]
+            out.append(dict(
+                bid=float(np.round(np.maximum(bids[k], 0.01), 2)), impressions=int(imp[k]),
+                impression_share=float(imp[k] / vol[k]) if vol[k] > 0 else 0.0,
+                buyside_clicks=int(o["buyside_clicks"][e, k]), costs=c.tolist(),
+                sellside_conversions=int(o["sellside_conversions"][e, k]), revenues=revs.tolist(),
+                revenues_per_cost=r.tolist(),
+                profit=float(o["revenue_cents"][e, k] - o["cost_cents"][e, k]) / 100.0
+                if self.kind == 0 else float(revs.sum() - c.sum())))
+        return out
 
     def keyword_params(self) -> Dict[str, np.ndarray]:
         """Current (possibly drifted) keyword parameters, host copies."""
@@ -281,6 +314,10 @@ class VectorBiddingSimulation:
         sc = a.scratch
         for n in ("serial_list", "serial_count", "env_profit", "env_cost", "env_done", "unit_cost_f64"):
             setattr(sc, n, s[n].data_ptr())
+        if self._detail is not None:
+            a.detail.cap = self.detail_cap
+            for n in ("costs", "rev_per_cost", "n_recorded", "volume_seen"):
+                setattr(a.detail, n, self._detail[n].data_ptr())
 
     def _prepare(self, action: Dict[str, ArrayLike]):
         assert self._have_keywords, "reset required, need to generate keywords to bid on"
@@ -296,6 +333,7 @@ class VectorBiddingSimulation:
     def step(self, action: Dict[str, ArrayLike], *, force_serial: bool = False):
         """One env step for all E envs (env:160-269).  Returns device tensors."""
         bids, budget = self._prepare(action)
+        self._last_bids = bids
         a = self._fill_args(bids, budget, force_serial)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _capi.check(self._lib.adc_step_philox(C.byref(a), C.c_void_p(stream)))

@@ -121,6 +121,18 @@ typedef struct adc_scratch {
     double *unit_cost_f64;  /* [E,K] explicit keywords only: un-rounded cost sums (else NULL) */
 } adc_scratch;
 
+/* Optional per-click detail (the ragged lists of BiddingOutcomes, bidding_simulation.py:10-38, that
+ * the reference prints in info["bidding_outcomes"]).  Only the exact serial path fills it: call
+ * with force_serial = 1 and n_lanes = 1.  All pointers NULL: not recorded. */
+typedef struct adc_detail {
+    int32_t cap;            /* clicks recorded per (env, keyword) and step, at most          */
+    double *costs;          /* [E,K,cap] cost of each accepted click, in order (bsim:101)    */
+    double *rev_per_cost;   /* [E,K,cap] revenue of that click, 0 if it did not convert (:114-115) */
+    int32_t *n_recorded;    /* [E,K] min(clicks, cap)                                        */
+    double *volume_seen;    /* [E,K] combine_outcomes' share denominator (bsim:130-146): the
+                               auctions of the lanes that had at least one impression        */
+} adc_detail;
+
 typedef struct adc_step_args {
     int32_t E;              /* envs owned by this call / rank                      */
     uint32_t env_base;      /* global id of env 0 (Philox counter; rank sharding)  */
@@ -139,6 +151,7 @@ typedef struct adc_step_args {
     const void *budget_in;  /* optional [E] dollars, same dtype as bids: rounded to cents and stored */
     adc_step_out out;
     adc_scratch scratch;
+    adc_detail detail;
 } adc_step_args;
 
 /* Replay tape for E envs, consumption order, CSR over the E*K units (u = e*K + k):

@@ -116,3 +116,25 @@ def test_rollout_example_runs():
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["n_envs"] == 256 and d["episodes"] == 256 and d["units_per_s"] > 0
+
+
+def test_bidding_outcomes_detail_is_consistent():
+    """info["bidding_outcomes"] (rust.repr_outcomes_py format): per-click costs, per-click revenues,
+    impression share -- consistent with the observation of the same step."""
+    import ast
+    from adcraft_b200.gymnasium_kw_env import BiddingSimulation
+    for env in (BiddingSimulation(num_keywords=6),
+                BiddingSimulation(keyword_config={"mean_volume": 64, "conversion_rate": 0.5}, num_keywords=6)):
+        env.reset(seed=4)
+        obs, reward, _, _, info = env.step({"keyword_bids": np.full(6, 0.9), "budget": 500.0})
+        outcomes = ast.literal_eval(info["bidding_outcomes"])
+        assert len(outcomes) == 6
+        for k, o in enumerate(outcomes):
+            assert o["impressions"] == obs["impressions"][k] and o["buyside_clicks"] == obs["buyside_clicks"][k]
+            assert len(o["costs"]) == o["buyside_clicks"] == len(o["revenues_per_cost"])
+            assert len(o["revenues"]) == o["sellside_conversions"] == obs["sellside_conversions"][k]
+            assert abs(sum(o["costs"]) - obs["cost"][k]) < 1e-9 and abs(sum(o["revenues"]) - obs["revenue"][k]) < 1e-9
+            assert [r for r in o["revenues_per_cost"] if r > 0] == o["revenues"]
+            assert 0.0 <= o["impression_share"] <= 1.0 + 1e-12
+            assert abs(o["profit"] - (obs["revenue"][k] - obs["cost"][k])) < 1e-9
+        assert abs(sum(o["profit"] for o in outcomes) - reward) < 1e-9
