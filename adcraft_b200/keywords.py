@@ -228,3 +228,42 @@ def sample_implicit_keywords_from_quantiles(num_keywords: int, rng: np.random.Ge
         out = KeywordTable(out.kind, *[getattr(out, n_)[None] for n_ in PARAM_NAMES],
                            impression_thresh=out.impression_thresh)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# device-side sampling: the same distributions drawn with torch's generator on the
+# GPU, for per-env keyword sets at sizes where host sampling + upload would dominate reset time.
+# Not stream-compatible with numpy (use the host factories above for the reference's exact draws).
+# ----------------------------------------------------------------------------------------------
+def sample_implicit_keywords_device(num_envs: int, num_keywords: int, keyword_config: Dict, device,
+                                    generator=None) -> Dict[str, "object"]:
+    """Per-env implicit keyword parameters as float64 CUDA tensors [E, K] (utils:260-349 semantics:
+    uniform bucket, piecewise-linear quantile interpolation, std_* as multipliers floored at 0.01,
+    vol_std = int(1 + U * 0.5 * vol), zero-volume keywords with probability ``no_vol_prob``)."""
+    import torch
+    data = quantile_rows_from_config(keyword_config)
+    E, K = int(num_envs), int(num_keywords)
+    f64 = torch.float64
+
+    def draw(param):
+        keep = data[f"count_{param}"] > 0 if f"count_{param}" in data else np.ones(len(data[f"min_{param}"]), bool)
+        lo, mid, hi = (torch.tensor(data[f"{q}_{param}"][keep], dtype=f64, device=device)
+                       for q in ("min", "median", "max"))
+        b = torch.randint(0, len(lo), (E, K), device=device, generator=generator)
+        q = torch.rand(E, K, dtype=f64, device=device, generator=generator)
+        lo, mid, hi = lo[b], mid[b], hi[b]
+        return torch.where(q <= 0.5, lo + (mid - lo) * (q / 0.5), mid + (hi - mid) * ((q - 0.5) / 0.5))
+
+    v = draw("vol")
+    has_vol = torch.rand(E, K, dtype=f64, device=device, generator=generator) > keyword_config.get("no_vol_prob", 0.0)
+    u = torch.rand(E, K, dtype=f64, device=device, generator=generator)
+    vol_mean = torch.where(has_vol, torch.floor(v), torch.zeros_like(v))
+    vol_std = torch.where(has_vol, torch.floor(1 + u * 0.5 * v), u * 0.5)
+    loc = draw("ave_cpc")
+    scale = torch.clamp(draw("std_cpc") * loc, min=0.01)
+    bctr = draw("bctr").clamp(0.0, 1.0)
+    sctr = draw("sctr").clamp(0.0, 1.0)
+    rev = draw("rpsc")
+    rev_std = torch.clamp(draw("std_rpsc") * rev, min=0.01)
+    return dict(vol_mean=vol_mean, vol_std=vol_std, p1=loc, p2=scale, ctr=bctr, cvr=sctr,
+                rev_mean=rev, rev_std=rev_std)

@@ -67,6 +67,8 @@ class VectorBiddingSimulation:
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available() or self._lib.adc_device_count() < 1:
             raise _capi.AdcError("adcraft_b200 needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_envs = int(num_envs)
         self.keyword_config = keyword_config
         self.num_keywords = int(num_keywords)
@@ -174,6 +176,19 @@ class VectorBiddingSimulation:
         self._kw_stride = K if per_env else 0
         self.keywords = table
         self.kind = table.kind
+        self._have_keywords = True
+
+    def install_device_keywords(self, cols: Dict[str, torch.Tensor], kind: int = kwmod.IMPLICIT) -> None:
+        """Use per-env keyword parameters that already live on the device ([E, K] float64 tensors,
+        e.g. from keywords.sample_implicit_keywords_device) without a host round trip."""
+        E, K = self.num_envs, self.num_keywords
+        for n in kwmod.PARAM_NAMES:
+            t = cols[n]
+            assert t.shape == (E, K) and t.dtype == torch.float64 and t.device == self.device, n
+        self._kw_dev = {n: cols[n].contiguous() for n in kwmod.PARAM_NAMES}
+        self._kw_stride = K
+        self.kind = kind
+        self.keywords = kwmod.KeywordTable(kind, *[self._kw_dev[n][:1].cpu().numpy() for n in kwmod.PARAM_NAMES])
         self._have_keywords = True
 
     def bidding_outcomes(self, e: int = 0) -> List[dict]:

@@ -138,3 +138,26 @@ def test_bidding_outcomes_detail_is_consistent():
             assert 0.0 <= o["impression_share"] <= 1.0 + 1e-12
             assert abs(o["profit"] - (obs["revenue"][k] - obs["cost"][k])) < 1e-9
         assert abs(sum(o["profit"] for o in outcomes) - reward) < 1e-9
+
+
+def test_device_side_keyword_sampling_matches_host_distributions():
+    """per-env keyword sets drawn on the GPU follow the same distributions as the host
+    factory that reproduces the reference's draws (two-sample KS per parameter)."""
+    from scipy.stats import ks_2samp
+    from adcraft_b200 import keywords as kwm
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    cfg = {"mean_volume": 64, "conversion_rate": 0.3}
+    E, K = 64, 200
+    g = torch.Generator(device="cuda").manual_seed(11)
+    cols = kwm.sample_implicit_keywords_device(E, K, cfg, torch.device("cuda", 0), generator=g)
+    host = kwm.sample_implicit_keywords_from_quantiles(E * K // 4, np.random.default_rng(3), cfg)
+    for n in kwm.PARAM_NAMES:
+        a, b = cols[n].cpu().numpy().ravel(), getattr(host, n).ravel()
+        if np.unique(b).size == 1:
+            assert np.all(a == b[0]), n
+        else:
+            assert ks_2samp(a, b).pvalue > 1e-4, n
+    env = VectorBiddingSimulation(E, num_keywords=K, device="cuda", seed=1, budget=1e6)
+    env.install_device_keywords(cols)
+    obs = env.step({"keyword_bids": torch.full((E, K), 0.8, device="cuda")})[0]
+    assert int(obs["impressions"].sum()) > 0
