@@ -833,32 +833,63 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
         __syncwarp();
 
         // ---------------- the 32 units, one after the other, 32 lanes per unit ----------------
+        // Software-pipelined: the first 128 competitor bids and the speculative heads of the
+        // conversion / revenue streams of the NEXT non-empty unit are requested before the current
+        // unit is consumed, so two units' worth of loads are in flight per warp.
         int I = 0, B = 0, S = 0;
         long long cost = 0, rev = 0;
         bool my_overrun = false;
-        for (int b = 0; b < 32; ++b) {
-            const int Vb = __shfl_sync(FULL, myV, b);
-            if (Vb <= 0) continue;  // warp-uniform
-            const ReplayUnit h = units[b];
-            bool overrun = false;
+        struct Pre {
+            int c[4];
             double cv[2];
             int rv[2];
+            bool overrun;
+        };
+        auto issue = [&](int b, Pre &p) {
+            const ReplayUnit &h = units[b];
+            p.overrun = false;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {  // speculative head of the conversion / revenue streams
-                const int i = lane + 32 * q;
-                cv[q] = i < h.n_conv ? __ldg(h.conv + i) : 2.0;
-                rv[q] = i < h.n_rev ? __ldg(h.rev + i) : 0;
+            for (int q = 0; q < 4; ++q) {
+                const int j = 32 * q + lane;
+                p.c[q] = 0x7FFFFFFF;
+                if (j < h.V) {
+                    if (j < h.n_comp) p.c[q] = __ldg(h.comp + j); else p.overrun = true;
+                }
             }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int i = lane + 32 * q;
+                p.cv[q] = i < h.n_conv ? __ldg(h.conv + i) : 2.0;
+                p.rv[q] = i < h.n_rev ? __ldg(h.rev + i) : 0;
+            }
+        };
+        unsigned todo = __ballot_sync(FULL, myV > 0);
+        Pre nxt;
+        int b_next = todo ? __ffs(todo) - 1 : -1;
+        if (b_next >= 0) issue(b_next, nxt);
+        while (b_next >= 0) {
+            const int b = b_next;
+            const Pre cur = nxt;
+            todo &= todo - 1;
+            b_next = todo ? __ffs(todo) - 1 : -1;
+            if (b_next >= 0) issue(b_next, nxt);
+            const ReplayUnit h = units[b];
+            const int Vb = h.V;
+            bool overrun = cur.overrun;
             int nI = 0, Bl = 0;
             long long costw = 0;
             for (int base = 0; base < Vb; base += 128) {
                 int c[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int j = base + 32 * q + lane;
-                    c[q] = 0x7FFFFFFF;
-                    if (j < Vb) {
-                        if (j < h.n_comp) c[q] = __ldg(h.comp + j); else overrun = true;
+                    if (base == 0) {
+                        c[q] = cur.c[q];
+                    } else {
+                        const int j = base + 32 * q + lane;
+                        c[q] = 0x7FFFFFFF;
+                        if (j < Vb) {
+                            if (j < h.n_comp) c[q] = __ldg(h.comp + j); else overrun = true;
+                        }
                     }
                 }
                 int rank[4];
@@ -891,7 +922,7 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
             for (int q = 0; q < 2; ++q) {
                 const int i = lane + 32 * q;
                 if (i < nB) {
-                    if (i < h.n_conv) Sl += cv[q] <= h.cvr; else overrun = true;
+                    if (i < h.n_conv) Sl += cur.cv[q] <= h.cvr; else overrun = true;
                 }
             }
             for (int i = 64 + lane; i < nB; i += 32) {
@@ -903,7 +934,7 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
             for (int q = 0; q < 2; ++q) {
                 const int i = lane + 32 * q;
                 if (i < nS) {
-                    if (i < h.n_rev) revl += rv[q]; else overrun = true;
+                    if (i < h.n_rev) revl += cur.rv[q]; else overrun = true;
                 }
             }
             for (int i = 64 + lane; i < nS; i += 32) {
