@@ -62,9 +62,12 @@ int validate(const adc_step_args *a, const adc_tape *tape)
                 "drift needs per-env keyword parameters (kw.env_stride == K)");
     ADC_REQUIRE(a->drift.mask == nullptr || (a->drift.num_updates >= 0 && a->drift.num_updates <= a->kw.K),
                 "drift.num_updates");
-    if (a->n_lanes != 0) {
+    if (a->n_lanes > 0) {
         const int L = a->n_lanes;
-        ADC_REQUIRE(L >= 1 && L <= 32 && (L & (L - 1)) == 0, "n_lanes must be 0 or a power of two <= 32");
+        ADC_REQUIRE(L >= 1 && L <= 32 && (L & (L - 1)) == 0, "n_lanes must be a power of two <= 32");
+    } else {
+        ADC_REQUIRE(a->n_lanes == 0 || a->n_lanes == -8 || a->n_lanes == -16 || a->n_lanes == -32,
+                    "n_lanes <= 0 selects the batched kernel: 0, -8, -16 or -32");
     }
     if (tape) {
         ADC_REQUIRE(tape->volume && tape->click_off && tape->u_click && tape->conv_off && tape->u_conv &&

@@ -565,11 +565,15 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 // kBU = units per batch (lanes >= kBU idle during the lane<->unit phases, which are a few percent
 // of the work): small batches mean many more work items than warps, so the last round of the
 // grid-stride loop is nearly full (a 4096 x 100 step is only 2.7 batches of 32 per resident warp).
-template <int kBU>
+// G = lanes that share one unit's auctions (32, 16 or 8): with G < 32 the warp walks 32/G units at
+// a time, which keeps the lanes busy for sparse keywords (a 16-auction day fills a 32-lane trip
+// only half, and the trip's Philox calls a quarter).
+template <int kBU, int G>
 __global__ void __launch_bounds__(kFlatWarps * 32)
 adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
 {
     __shared__ FlatUnit s_unit[kFlatWarps][32];
+    __shared__ unsigned s_res[kFlatWarps][32][4];     // G < 32: per-unit sums handed to the owner lane
     __shared__ FlatRev s_rev[kFlatWarps][32];
     __shared__ int s_start[kFlatWarps][33];
     __shared__ unsigned s_revsum[kFlatWarps][32][2];  // 24-bit split: native 32-bit smem atomics
@@ -619,7 +623,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             const int64_t pi = (int64_t)e * a.kw.env_stride + k;
             const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)k), genv, k0, k1);
             const long long v = volume_draw(w.x, a.kw.vol_mean[pi], a.kw.vol_std[pi]);
-            over_cap = v > kMaxFlatVolume || p.bid_cents > kMaxFlatBidCents;
+            over_cap = v > (G == 32 ? kMaxFlatVolume : 65535) || p.bid_cents > kMaxFlatBidCents;
             V = over_cap ? 0 : (int)v;
         }
         {
@@ -635,16 +639,20 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         s_revsum[warp][lane][0] = 0u; s_revsum[warp][lane][1] = 0u;
         __syncwarp();
 
-        // ---------------- the batch's auctions: one unit after the other, 32 lanes per unit ------
-        // The unit is warp-uniform inside a trip: its parameters sit in registers, the lane
-        // accumulators are private, and one REDUX set per unit lands the sums in the owner lane's
-        // registers.  Only the last trip of a unit has idle lanes (volume rounded up to 32).
+        // ---------------- the batch's auctions: 32/G units at a time, G lanes per unit -----------
+        // Inside a trip the unit is uniform over its G lanes: parameters in registers, private lane
+        // accumulators, one REDUX set per unit.  Only the last trip of a unit has idle lanes.
+        constexpr int NG = 32 / G;
+        const int gl = lane & (G - 1), gi = lane / G;
+        const unsigned gmask = G == 32 ? FULL : (((1u << G) - 1u) << (gi * G));
         int I = 0, B = 0, S = 0;
         long long cost = 0;
-        for (int b = 0; b < cnt; ++b) {
-            const int Vb = __shfl_sync(FULL, V, b);
-            if (Vb == 0) continue;  // warp-uniform
-            FlatUnit fu = units[b];
+        for (int b0 = 0; b0 < cnt; b0 += NG) {
+            const int b = b0 + gi;  // this group's unit
+            int Vb = __shfl_sync(FULL, V, b & 31);
+            if (b >= cnt) Vb = 0;
+            if (G == 32 && Vb == 0) continue;  // warp-uniform
+            FlatUnit fu = units[b & 31];
             const bool conv_all = fu.bid_cents < 0;
             fu.bid_cents &= 0x7FFFFFFF;
             unsigned cntIB = 0, cntS = 0, cst = 0;  // I | B << 16 ; S ; cost cents (< 2^32, see caps)
@@ -658,34 +666,47 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
                 cntS += cnv ? 1u : 0u;
                 cst += clk ? (unsigned)c : 0u;
             };
-            // full trips: each lane takes one Philox call = two consecutive auctions (64 per trip)
+            // full trips: each lane takes one Philox call = two consecutive auctions (2G per trip)
             int base = 0;
-            for (; base + 64 <= Vb; base += 64) {
-                const uint4 w = philox_from_pre((uint32_t)((base >> 1) + lane), fu.n0, fu.n1, fu.x3, k0, k1);
+            for (; base + 2 * G <= Vb; base += 2 * G) {
+                const uint4 w = philox_from_pre((uint32_t)((base >> 1) + gl), fu.n0, fu.n1, fu.x3, k0, k1);
                 tally(true, w.x, w.y);
                 tally(true, w.z, w.w);
             }
-            const int rem = Vb - base;  // 0..63 auctions left
-            if (rem > 32) {             // still worth pairing: lanes past the end idle
-                const int j = base + 2 * lane;
+            const int rem = Vb - base;  // 0 .. 2G-1 auctions left
+            if (rem > G) {              // still worth pairing: lanes past the end idle
+                const int j = base + 2 * gl;
                 const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
                 tally(j < Vb, w.x, w.y);
                 tally(j + 1 < Vb, w.z, w.w);
-            } else if (rem > 0) {       // at most 32 left: one auction per lane, half a call each
-                const int j = base + lane;
+            } else if (rem > 0) {       // at most G left: one auction per lane, half a call each
+                const int j = base + gl;
                 const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
                 tally(j < Vb, (j & 1) ? w.z : w.x, (j & 1) ? w.w : w.y);
             }
-            const unsigned tI = __reduce_add_sync(FULL, cntIB & 0xFFFFu);
-            const unsigned tB = __reduce_add_sync(FULL, cntIB >> 16);
-            const unsigned tS = __reduce_add_sync(FULL, cntS);
-            const unsigned lo = __reduce_add_sync(FULL, cst & 0xFFFFu);
-            const unsigned hi = __reduce_add_sync(FULL, cst >> 16);
-            if (lane == b) {
-                I = (int)tI;
-                B = (int)tB;
-                S = (int)tS;
-                cost = (long long)lo + ((long long)hi << 16);
+            const unsigned tI = __reduce_add_sync(gmask, cntIB & 0xFFFFu);
+            const unsigned tB = __reduce_add_sync(gmask, cntIB >> 16);
+            const unsigned tS = __reduce_add_sync(gmask, cntS);
+            const unsigned lo = __reduce_add_sync(gmask, cst & 0xFFFFu);
+            const unsigned hi = __reduce_add_sync(gmask, cst >> 16);
+            if (G == 32) {
+                if (lane == b) {
+                    I = (int)tI; B = (int)tB; S = (int)tS;
+                    cost = (long long)lo + ((long long)hi << 16);
+                }
+            } else if (gl == 0 && b < cnt) {
+                s_res[warp][b][0] = tI | (tB << 16);
+                s_res[warp][b][1] = tS;
+                s_res[warp][b][2] = lo;
+                s_res[warp][b][3] = hi;
+            }
+        }
+        if (G != 32) {
+            __syncwarp();
+            if (lane < cnt) {
+                const unsigned ib = s_res[warp][lane][0];
+                I = (int)(ib & 0xFFFFu); B = (int)(ib >> 16); S = (int)s_res[warp][lane][1];
+                cost = (long long)s_res[warp][lane][2] + ((long long)s_res[warp][lane][3] << 16);
             }
         }
 
@@ -1397,17 +1418,21 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     cudaError_t err = cudaSuccess;
     adc_tape t0 = {};
     const adc_tape &tp = tape ? *tape : t0;
-    if (tape == nullptr && !explicit_kw && a.n_lanes == 0) {
+    if (tape == nullptr && !explicit_kw && a.n_lanes <= 0) {
         const int block = kFlatWarps * 32;
         int per_sm = 0;
         constexpr int kBU = 32;  // 8 and 16 were measured slower: the lane<->unit phases lose more than the tail gains
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adc_flat_philox_implicit_kernel<kBU>, block, 0);
+        // n_lanes: 0 / -32 -> 32 lanes per unit (dense keywords), -16, -8 -> sub-warp groups (sparse)
+        void (*kern)(adc_step_args) = a.n_lanes == -8    ? adc_flat_philox_implicit_kernel<kBU, 8>
+                                      : a.n_lanes == -16 ? adc_flat_philox_implicit_kernel<kBU, 16>
+                                                         : adc_flat_philox_implicit_kernel<kBU, 32>;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
         if (per_sm < 1) per_sm = 1;
         int64_t grid = (int64_t)num_sms() * per_sm;
         const int64_t want = ((total + kBU - 1) / kBU + kFlatWarps - 1) / kFlatWarps;
         if (want < grid) grid = want;
         if (grid < 1) grid = 1;
-        adc_flat_philox_implicit_kernel<kBU><<<(unsigned)grid, block, 0, s>>>(a);
+        kern<<<(unsigned)grid, block, 0, s>>>(a);
         ++*launches;
         err = cudaGetLastError();
     } else if (tape == nullptr && !explicit_kw) {

@@ -82,6 +82,7 @@ class VectorBiddingSimulation:
         self.seed = int(seed)
         self.env_base = int(env_base)
         self.n_lanes = int(n_lanes)
+        self._auto_lanes = n_lanes == 0
         self.budget_alias = bool(budget_alias)
         self.autoreset = bool(autoreset)
         self.detail_cap = int(detail_cap)  # > 0: record per-click lists on the exact serial path
@@ -177,6 +178,9 @@ class VectorBiddingSimulation:
         self.keywords = table
         self.kind = table.kind
         self._have_keywords = True
+        if self._auto_lanes:  # lanes per unit of the hot kernel from the mean daily volume
+            v = float(np.mean(table.vol_mean))
+            self.n_lanes = 0 if v >= 96 else (-16 if v >= 36 else -8)
 
     def install_device_keywords(self, cols: Dict[str, torch.Tensor], kind: int = kwmod.IMPLICIT) -> None:
         """Use per-env keyword parameters that already live on the device ([E, K] float64 tensors,

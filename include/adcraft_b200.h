@@ -139,7 +139,10 @@ typedef struct adc_step_args {
     uint32_t step;          /* global step counter (Philox counter); must advance by 1 per call
                                on a given scratch (its parity double-buffers serial_count)    */
     uint64_t seed;          /* Philox key                                          */
-    int32_t n_lanes;        /* threads cooperating on one (env,keyword): 0 = auto, else 1..32 pow2 */
+    int32_t n_lanes;        /* lanes per (env,keyword) unit.  0 / -32: warp-batched hot kernel with 32
+                               lanes per unit (dense keywords); -16 / -8: the same kernel with
+                               sub-warp groups (sparse keywords); 1..32 (pow2): the simpler
+                               L-threads-per-unit kernel (A/B and detail recording, n_lanes = 1) */
     int32_t budget_alias;   /* 1: ndarray-budget double charge (bsim:102 + :225), 0: scalar budget */
     int32_t autoreset;      /* 1: zero cum_profit/day of finished envs after reporting them */
     int32_t force_serial;   /* 1: run every env through the exact serial kernel (testing)   */

@@ -44,7 +44,7 @@ def _compare(obs, reward, term, trunc, ref, env, rtol):
     assert np.all(np.abs(reward.cpu().numpy() - ref["reward"]) <= rtol * scale)
 
 
-@pytest.mark.parametrize("n_lanes", [0, 1, 4, 8, 32])
+@pytest.mark.parametrize("n_lanes", [0, -8, -16, 1, 4, 8, 32])
 @pytest.mark.parametrize("vol,K,E,budget", [(128, 100, 64, 1e5), (16, 37, 50, 1e5), (300, 5, 33, 1e5),
                                             (64, 20, 40, 25.0), (0, 3, 4, 10.0)])
 def test_philox_implicit_matches_oracle(orc, n_lanes, vol, K, E, budget):
