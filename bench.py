@@ -42,7 +42,8 @@ PY_REFERENCE_UNITS_PER_S_1CORE = 290.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one hot-kernel launch on this workload, from the
 # committed `ncu --set full` capture (profiles/r01_flat_kernel_ncu_metrics.csv): the outputs stay in
 # the 126 MB L2 between steps, so DRAM traffic is below the 9.8 MB of algorithmic bytes.
-NCU_DRAM_BYTES_PER_LAUNCH = 1848064 + 7936
+NCU_DRAM_BYTES_PER_LAUNCH = 1854976 + 7168
+NCU_WARP_INSTR_PER_LAUNCH = 198579293  # smsp__inst_executed.sum of the same capture
 
 
 MEAN_VOLUME, CVR, DRIFT = 128, 0.8, False
@@ -350,8 +351,13 @@ def run_gpu(args):
         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if E_ENVS == 4096 else None,
         "kernel": "adc_flat_philox_implicit_kernel", "peak_source": peak_src,
         "algorithmic_bytes_per_unit": B_UNIT,
-        "note": "free-running mode draws ~128 auctions per unit from Philox: the kernel is issue-bound, "
-                "not HBM-bound (see profiles/ and DESIGN.md); the step = this kernel + an empty serial-queue kernel",
+        "issue": {"warp_instructions_per_launch": NCU_WARP_INSTR_PER_LAUNCH if E_ENVS == 4096 and K_KW == 100 else None,
+                  "frac_of_issue_peak": (NCU_WARP_INSTR_PER_LAUNCH / (ms_per_step * 1e-3) / (148 * 4 * 1.965e9)
+                                         if E_ENVS == 4096 and K_KW == 100 else None),
+                  "note": "instruction count from the committed ncu capture; peak = 148 SMs x 4 schedulers x 1965 MHz"},
+        "note": "free-running mode draws ~128 auctions per unit from Philox (half a Philox4x32-10 call + a "
+                "Laplace sampler each): the kernel is instruction-issue-bound, not HBM-bound (profiles/r01_summary.md, "
+                "DESIGN.md); the step = this kernel + a serial-queue kernel that exits when no budget binds",
     }
 
     # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------
