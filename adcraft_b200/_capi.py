@@ -13,6 +13,7 @@ from . import build as _build
 SUBSTEPS = 24
 IMPLICIT, EXPLICIT = 0, 1
 F32, F64 = 0, 1
+ABI_VERSION = 2
 
 
 class AdcError(RuntimeError):
@@ -75,7 +76,7 @@ class StepArgs(C.Structure):
 class Tape(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "volume", "comp_off", "comp_cents", "click_off", "u_click", "conv_off", "u_conv",
-        "rev_off", "rev_cents", "impr", "cost_off", "cost", "drift")]
+        "rev_off", "rev_cents", "impr", "cost_off", "cost", "drift", "packed", "packed_off")]
 
 
 _lib = None
@@ -109,8 +110,8 @@ def load() -> C.CDLL:
     lib.adc_reset_envs.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.adc_launch_count.restype = C.c_int64
     lib.adc_launch_count.argtypes = [C.c_int]
-    if lib.adc_abi_version() != 1:
-        raise AdcError(f"adcraft_b200: ABI version {lib.adc_abi_version()} != 1")
+    if lib.adc_abi_version() != ABI_VERSION:
+        raise AdcError(f"adcraft_b200: ABI version {lib.adc_abi_version()} != {ABI_VERSION}")
     if lib.adc_sizeof_step_args() != C.sizeof(StepArgs) or lib.adc_sizeof_tape() != C.sizeof(Tape):
         raise AdcError(
             "adcraft_b200: struct layout mismatch between _capi.py and the compiled library "

@@ -77,6 +77,11 @@ int validate(const adc_step_args *a, const adc_tape *tape)
         else
             ADC_REQUIRE(tape->impr && tape->cost_off && tape->cost, "tape.impr/cost_* required for explicit keywords");
         ADC_REQUIRE(a->drift.mask == nullptr || tape->drift != nullptr, "tape.drift required when drift is on");
+        if (tape->packed != nullptr) {
+            ADC_REQUIRE(tape->packed_off != nullptr, "tape.packed_off is NULL");
+            ADC_REQUIRE((reinterpret_cast<uintptr_t>(tape->packed) & 15u) == 0, "tape.packed must be 16-byte aligned");
+            ADC_REQUIRE(a->kw.kind == ADC_IMPLICIT, "tape.packed is for implicit keywords");
+        }
     }
     return ADC_OK;
 }

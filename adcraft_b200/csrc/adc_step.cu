@@ -26,6 +26,7 @@
 #include "adc_step.h"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace adc {
 
@@ -1001,6 +1002,324 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
 }
 
 // ------------------------------------------------------------------------------------------
+// packed replay kernel (implicit keywords, adc_tape.packed): the HBM-bound path.
+//
+// A unit's whole day is one 16-byte aligned record (header, competitor bids, click uniforms,
+// conversion uniforms, revenues; see include/adcraft_b200.h), so the kernel moves it with ONE bulk
+// copy (TMA, cp.async.bulk -> mbarrier complete_tx) into a per-warp ring of kPkStages shared-memory
+// buffers, kPkStages-1 units ahead of the walk.  No per-lane address arithmetic, bounds checks or
+// dependent DRAM round trips are left in the walk: the warp reads the record from shared memory
+// (128-bit loads of four consecutive competitor bids per lane, click uniforms gathered by
+// impression rank, conversion uniforms and revenues as dense prefixes) and reduces with REDUX.
+// Records that do not fit a stage (very large volumes), bids above kMaxFlatBidCents or values
+// outside the 16-bit fast-path range are walked by pk_walk_generic (64-bit sums, any address
+// space); malformed records flag an overrun, which routes the env to the serial kernel (CSR tape).
+// ------------------------------------------------------------------------------------------
+constexpr int kPkMaxCap = 4096;  // largest stage size instantiated (bounds the 32-bit fast-path sums)
+
+struct __align__(16) PkUnit {  // 32 B per unit in shared memory
+    long long off;             // byte offset of the record
+    int bytes;                 // record size, 0 = empty, < 0 = malformed offsets
+    int bid_cents;
+    double ctr, cvr;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    for (unsigned spin = 0;; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (spin > (1u << 18)) __trap();  // ~1 s: a lost copy must not hang the device
+    }
+}
+
+struct PkResult {
+    int I, B, S;
+    long long cost, rev;
+    bool overrun;
+};
+
+// Record header -> stream positions; false (and empty streams) when the header does not fit the
+// record.  All values are warp-uniform.
+struct PkView {
+    int V, n_comp, n_click, n_conv, n_rev;
+    const unsigned char *comp, *click, *conv, *rev;
+};
+
+__device__ __forceinline__ bool pk_view(const unsigned char *rec, int bytes, PkView &v)
+{
+    const int4 h0 = *reinterpret_cast<const int4 *>(rec);
+    v.V = h0.x; v.n_comp = h0.y; v.n_click = h0.z; v.n_conv = h0.w;
+    v.n_rev = *reinterpret_cast<const int *>(rec + 16);
+    const unsigned lim = (unsigned)bytes;
+    bool ok = (unsigned)v.n_comp <= lim && (unsigned)v.n_click <= lim && (unsigned)v.n_conv <= lim &&
+              (unsigned)v.n_rev <= lim && v.V >= 0 && v.n_comp <= v.V;
+    const long long comp_b = 4LL * ((v.n_comp + 3) & ~3);
+    const long long need = 32LL + comp_b + 8LL * v.n_click + 8LL * v.n_conv + 4LL * v.n_rev;
+    ok = ok && need <= (long long)bytes;
+    if (!ok) { v.n_comp = v.n_click = v.n_conv = v.n_rev = 0; }
+    v.comp = rec + 32;
+    v.click = v.comp + (ok ? comp_b : 0);
+    v.conv = v.click + 8LL * v.n_click;
+    v.rev = v.conv + 8LL * v.n_conv;
+    return ok;
+}
+
+// Any record, any address space, 64-bit sums.
+__device__ __noinline__ PkResult pk_walk_generic(const unsigned char *rec, int bytes, int bid_cents, double ctr,
+                                                 double cvr, int lane)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lt = (1u << lane) - 1u;
+    PkView v;
+    PkResult r;
+    r.overrun = !pk_view(rec, bytes, v);
+    r.overrun = r.overrun || v.V > v.n_comp;
+    const int *comp = reinterpret_cast<const int *>(v.comp);
+    const double *click = reinterpret_cast<const double *>(v.click);
+    const double *conv = reinterpret_cast<const double *>(v.conv);
+    const int *rev = reinterpret_cast<const int *>(v.rev);
+    int nI = 0, Bl = 0;
+    long long costl = 0;
+    for (int base = 0; base < v.n_comp; base += 32) {
+        const int j = base + lane;
+        const int c = j < v.n_comp ? comp[j] : 0x7FFFFFFF;
+        const bool win = bid_cents > c;
+        const unsigned m = __ballot_sync(FULL, win);
+        const int rank = nI + __popc(m & lt);
+        nI += __popc(m);
+        const bool clk = win && rank < v.n_click && click[rank] <= ctr;
+        Bl += clk;
+        costl += clk ? c : 0;
+    }
+    r.overrun = r.overrun || nI > v.n_click;
+    r.I = nI;
+    r.B = (int)__reduce_add_sync(FULL, (unsigned)Bl);
+    r.overrun = r.overrun || r.B > v.n_conv;
+    int Sl = 0;
+    for (int i = lane; i < min(r.B, v.n_conv); i += 32) Sl += conv[i] <= cvr;
+    r.S = (int)__reduce_add_sync(FULL, (unsigned)Sl);
+    r.overrun = r.overrun || r.S > v.n_rev;
+    long long revl = 0;
+    for (int i = lane; i < min(r.S, v.n_rev); i += 32) revl += rev[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        costl += __shfl_xor_sync(FULL, costl, off);
+        revl += __shfl_xor_sync(FULL, revl, off);
+    }
+    r.cost = costl;
+    r.rev = revl;
+    return r;
+}
+
+// Record resident in shared memory, bid <= kMaxFlatBidCents: 32-bit sums, REDUX reductions.  Returns
+// false when a value leaves the 16-bit range the 32-bit sums are safe for (negative competitor
+// bid, revenue >= 65536 cents): the caller redoes the unit with pk_walk_generic.
+__device__ __forceinline__ bool pk_walk_fast(const unsigned char *rec, int bytes, int bid_cents, double ctr, double cvr,
+                                             int lane, PkResult &r)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lt = (1u << lane) - 1u;
+    PkView v;
+    r.overrun = !pk_view(rec, bytes, v);
+    r.overrun = r.overrun || v.V > v.n_comp;
+    const int4 *comp = reinterpret_cast<const int4 *>(v.comp);
+    const double *click = reinterpret_cast<const double *>(v.click);
+    const double *conv = reinterpret_cast<const double *>(v.conv);
+    const int *rev = reinterpret_cast<const int *>(v.rev);
+    int nI = 0;
+    unsigned Bl = 0, costl = 0, wild = 0;
+    const int n4 = (v.n_comp + 3) >> 2;  // int4 groups; padding entries are INT32_MAX and never win
+    int4 c = make_int4(0, 0, 0, 0);
+    for (int g0 = 0; g0 < n4; g0 += 32) {
+        const int g = g0 + lane;
+        const bool ok = g < n4;
+        if (ok) c = comp[g];
+        const bool w0 = ok && bid_cents > c.x, w1 = ok && bid_cents > c.y;
+        const bool w2 = ok && bid_cents > c.z, w3 = ok && bid_cents > c.w;
+        const unsigned m0 = __ballot_sync(FULL, w0), m1 = __ballot_sync(FULL, w1);
+        const unsigned m2 = __ballot_sync(FULL, w2), m3 = __ballot_sync(FULL, w3);
+        // auction order inside the trip is lane-major (j = 4 g + q): rank = wins of lower lanes + own earlier wins
+        const int r0 = nI + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+        const int r1 = r0 + w0, r2 = r1 + w1, r3 = r2 + w2;
+        nI += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+        const bool k0 = w0 && r0 < v.n_click && click[r0] <= ctr;
+        const bool k1 = w1 && r1 < v.n_click && click[r1] <= ctr;
+        const bool k2 = w2 && r2 < v.n_click && click[r2] <= ctr;
+        const bool k3 = w3 && r3 < v.n_click && click[r3] <= ctr;
+        const int c0 = k0 ? c.x : 0, c1 = k1 ? c.y : 0, c2 = k2 ? c.z : 0, c3 = k3 ? c.w : 0;
+        Bl += (unsigned)k0 + (unsigned)k1 + (unsigned)k2 + (unsigned)k3;
+        costl += (unsigned)c0 + (unsigned)c1 + (unsigned)c2 + (unsigned)c3;
+        wild |= (unsigned)(c0 | c1 | c2 | c3);
+    }
+    r.overrun = r.overrun || nI > v.n_click;
+    r.I = nI;
+    r.B = (int)__reduce_add_sync(FULL, Bl);
+    r.overrun = r.overrun || r.B > v.n_conv;
+    const int nB = min(r.B, v.n_conv);
+    unsigned Sl = 0;
+    for (int i = lane; i < nB; i += 32) Sl += conv[i] <= cvr;
+    r.S = (int)__reduce_add_sync(FULL, Sl);
+    r.overrun = r.overrun || r.S > v.n_rev;
+    const int nS = min(r.S, v.n_rev);
+    unsigned revl = 0;
+    for (int i = lane; i < nS; i += 32) {
+        const unsigned x = (unsigned)rev[i];
+        revl += x;
+        wild |= x;
+    }
+    // a lane adds at most kPkMaxCap/4/32 = 32 values below 2^16 (c < bid <= 65535 when clicked), so the
+    // 32-bit lane and warp sums are exact unless some value had a bit above 15 set
+    if (__any_sync(FULL, (wild & 0xFFFF0000u) != 0)) return false;
+    r.cost = (long long)__reduce_add_sync(FULL, costl);
+    r.rev = (long long)__reduce_add_sync(FULL, revl);
+    return true;
+}
+
+template <int kPkWarps, int kPkStages, int kPkCap>
+__global__ void __launch_bounds__(kPkWarps * 32)
+adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_constant__ adc_tape t)
+{
+    static_assert(kPkCap <= kPkMaxCap && kPkCap % 16 == 0, "stage size");
+    extern __shared__ __align__(128) unsigned char pk_buf[];  // [kPkWarps][kPkStages][kPkCap]
+    __shared__ PkUnit s_unit[kPkWarps][32];
+    __shared__ __align__(8) unsigned long long s_bar[kPkWarps][kPkStages];
+    const int K = a.kw.K;
+    const int64_t total = (int64_t)a.E * K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gwarp = (int64_t)blockIdx.x * kPkWarps + warp;
+    const int64_t n_warps = (int64_t)gridDim.x * kPkWarps;
+    // full rounds of 32-unit batches, then 8-unit tail batches (same split as the hot kernel)
+    constexpr int kTail = 8;
+    const int64_t big_rounds = total / (32 * n_warps);
+    const int64_t n_big = big_rounds * n_warps;
+    const int64_t n_batches = n_big + (total - n_big * 32 + kTail - 1) / kTail;
+    const unsigned FULL = 0xFFFFFFFFu;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
+
+    PkUnit *units = s_unit[warp];
+    unsigned char *stage_buf = pk_buf + (size_t)warp * kPkStages * kPkCap;
+    const uint32_t stage_s = smem_addr(stage_buf);
+    const uint32_t bar_s = smem_addr(&s_bar[warp][0]);
+    if (lane < kPkStages) mbar_init(bar_s + 8u * lane, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    unsigned n_iss = 0, n_cons = 0;  // copies issued / consumed by this warp (stage = n % kPkStages)
+
+    for (int64_t batch = gwarp; batch < n_batches; batch += n_warps) {
+        // ---------------- header, lane <-> unit ----------------
+        const bool big = batch < n_big;
+        const int cnt = big ? 32 : kTail;
+        const int64_t u = (big ? batch * 32 : n_big * 32 + (batch - n_big) * kTail) + lane;
+        const bool valid = lane < cnt && u < total;
+        int e = 0;
+        PkUnit pu;
+        pu.off = 0; pu.bytes = 0; pu.bid_cents = 0; pu.ctr = 0.0; pu.cvr = 0.0;
+        if (valid) {
+            e = (int)(u / K);
+            const int64_t pi = (int64_t)e * a.kw.env_stride + (u - (int64_t)e * K);
+            const long long o0 = t.packed_off[u], o1 = t.packed_off[u + 1];
+            const long long len = o1 - o0;
+            pu.off = o0;
+            pu.bytes = (o0 < 0 || len < 0 || len > 0x7FFFFFF0LL || ((o0 | len) & 15)) ? -1 : (int)len;
+            pu.ctr = a.kw.ctr[pi];
+            pu.cvr = a.kw.cvr[pi];
+            pu.bid_cents = bid_to_cents(load_f(a.bids, a.bids_dtype, u));
+        }
+        units[lane] = pu;
+        __syncwarp();
+        const unsigned work_m = __ballot_sync(FULL, pu.bytes >= 32);
+        const unsigned fast_m = __ballot_sync(FULL, pu.bytes >= 32 && pu.bytes <= kPkCap && pu.bid_cents <= kMaxFlatBidCents);
+        bool my_overrun = pu.bytes < 0 || (pu.bytes > 0 && pu.bytes < 32);
+
+        // ---------------- the units, one after the other; copies run kPkStages-1 units ahead ----------------
+        int I = 0, B = 0, S = 0;
+        long long cost = 0, rev = 0;
+        unsigned iss_m = fast_m;
+        auto issue_next = [&]() {
+            const int bi = __ffs(iss_m) - 1;
+            iss_m &= iss_m - 1;
+            const unsigned st = n_iss % kPkStages;
+            if (lane == 0) {
+                const PkUnit h = units[bi];
+                bulk_load(stage_s + st * kPkCap, t.packed + h.off, (uint32_t)h.bytes, bar_s + 8u * st);
+            }
+            ++n_iss;
+        };
+#pragma unroll 1
+        for (int sidx = 0; sidx < kPkStages - 1 && iss_m; ++sidx) issue_next();
+        unsigned todo = work_m;
+#pragma unroll 1
+        while (todo) {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            __syncwarp();  // everyone is done reading the stage the next copy overwrites
+            if (iss_m && n_iss - n_cons < (unsigned)kPkStages) issue_next();
+            const PkUnit h = units[b];
+            PkResult r;
+            if ((fast_m >> b) & 1u) {
+                const unsigned st = n_cons % kPkStages;
+                mbar_wait(bar_s + 8u * st, (n_cons / kPkStages) & 1u);
+                ++n_cons;
+                const unsigned char *rec = stage_buf + st * kPkCap;
+                if (!pk_walk_fast(rec, h.bytes, h.bid_cents, h.ctr, h.cvr, lane, r))
+                    r = pk_walk_generic(rec, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
+            } else {
+                r = pk_walk_generic(t.packed + h.off, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
+            }
+            if (lane == b) {
+                I = r.I; B = r.B; S = r.S; cost = r.cost; rev = r.rev; my_overrun = r.overrun;
+            }
+        }
+
+        // ---------------- outputs (coalesced), env completion ----------------
+        int safe = 0;
+        if (valid) {
+            a.out.impressions[u] = I;
+            a.out.clicks[u] = B;
+            a.out.conversions[u] = S;
+            a.out.cost_cents[u] = cost;
+            a.out.revenue_cents[u] = rev;
+            store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
+            store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
+            safe = unit_done(a, e, rev - cost, my_overrun ? (1LL << 40) : cost);
+        }
+        if (a.drift.mask != nullptr) {
+            unsigned dm = __ballot_sync(FULL, safe != 0);
+            while (dm) {
+                const int src = __ffs(dm) - 1;
+                dm &= dm - 1;
+                const int ee = __shfl_sync(FULL, e, src);
+                for (int kk = lane; kk < K; kk += 32) {
+                    if (!drift_wanted(a, kk)) continue;
+                    drift_apply(a, ee, kk, unit_drift<TapeSrc>(a, &t, ee, kk, make_uint4(0, 0, 0, 0)));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // generic kernel: one thread per unit, lanes in order, no budget
 // ------------------------------------------------------------------------------------------
 template <typename Src, bool kExplicit>
@@ -1399,6 +1718,31 @@ static cudaError_t launch_lanes(const adc_step_args &a, cudaStream_t s, int64_t 
     return cudaGetLastError();
 }
 
+template <int W, int NS, int CAP>
+static cudaError_t launch_packed(const adc_step_args &a, const adc_tape &tp, cudaStream_t s, int64_t *launches)
+{
+    auto kern = adc_replay_packed_kernel<W, NS, CAP>;
+    constexpr int block = W * 32;
+    constexpr size_t dyn = (size_t)W * NS * CAP;
+    static bool configured = false;
+    if (!configured) {
+        const cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (err != cudaSuccess) return err;
+        configured = true;
+    }
+    const int64_t total = (int64_t)a.E * a.kw.K;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, dyn);
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    const int64_t want = ((total + 31) / 32 + W - 1) / W;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, block, dyn, s>>>(a, tp);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 template <typename K>
 static int64_t grid_for(K kernel, int block, int64_t work_items)
 {
@@ -1461,6 +1805,17 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         kern<<<(unsigned)grid_for(kern, 128, total), 128, 0, s>>>(a, tp);
         ++*launches;
         err = cudaGetLastError();
+    } else if (tp.packed != nullptr) {
+        // stage geometry: 8 warps x 3 stages x 4 KB = 96 KB per CTA, two CTAs per SM.  ADC_PK_VARIANT
+        // selects the other instantiations (measurement knob, read once).
+        static const int variant = [] { const char *v = getenv("ADC_PK_VARIANT"); return v ? atoi(v) : 0; }();
+        switch (variant) {
+            case 1: err = launch_packed<8, 4, 3072>(a, tp, s, launches); break;
+            case 2: err = launch_packed<4, 4, 4096>(a, tp, s, launches); break;
+            case 3: err = launch_packed<8, 2, 4096>(a, tp, s, launches); break;
+            case 4: err = launch_packed<6, 3, 4096>(a, tp, s, launches); break;
+            default: err = launch_packed<8, 3, 4096>(a, tp, s, launches); break;
+        }
     } else {
         auto kern = adc_replay_implicit_kernel;
         kern<<<(unsigned)grid_for(kern, kReplayWarps * 32, total), kReplayWarps * 32, 0, s>>>(a, tp);

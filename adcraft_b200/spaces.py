@@ -11,6 +11,9 @@ from typing import Dict as _Dict
 import numpy as np
 
 try:  # pragma: no cover - depends on the image
+    import gymnasium as _gym  # type: ignore
+    if getattr(_gym, "__file__", None) is None:  # an in-memory stand-in (the test harness installs one)
+        raise ImportError("gymnasium is a stub module")
     from gymnasium.spaces import Box, Dict  # type: ignore
     HAVE_GYMNASIUM = True
 except Exception:  # noqa: BLE001

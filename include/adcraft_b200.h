@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define ADC_ABI_VERSION 1
+#define ADC_ABI_VERSION 2
 #define ADC_SUBSTEPS 24 /* adcraft/bidding_simulation.py:213 */
 
 typedef enum adc_status {
@@ -158,7 +158,18 @@ typedef struct adc_step_args {
 } adc_step_args;
 
 /* Replay tape for E envs, consumption order, CSR over the E*K units (u = e*K + k):
- * stream[off[u] .. off[u+1]).  Streams may be longer than what gets consumed. */
+ * stream[off[u] .. off[u+1]).  Streams may be longer than what gets consumed.
+ *
+ * Optional packed copy (implicit keywords): the same values laid out as ONE record per unit, so a
+ * unit's whole day is one contiguous, 16-byte aligned block that the replay kernel fetches with a
+ * single bulk copy (TMA) into shared memory.  Record of unit u = packed[packed_off[u] ..
+ * packed_off[u+1]) (byte offsets, multiples of 16; an empty record means volume 0):
+ *     int32  hdr[8]    = { V, n_comp, n_click, n_conv, n_rev, 0, 0, 0 }   with n_comp <= V
+ *     int32  comp[n_comp rounded up to a multiple of 4]   padding entries = INT32_MAX
+ *     double click[n_click];  double conv[n_conv]
+ *     int32  rev[n_rev]       zero padded to the next multiple of 16 bytes
+ * `packed` must be 16-byte aligned.  The CSR streams stay mandatory: envs whose budget may bind and
+ * records that fail validation are re-walked by the exact serial kernel from the CSR form. */
 typedef struct adc_tape {
     const int32_t *volume;                              /* [E,K]                          */
     const int64_t *comp_off;  const int32_t *comp_cents;   /* implicit: one per auction      */
@@ -168,6 +179,8 @@ typedef struct adc_tape {
     const int32_t *impr;                                /* explicit: [E,K,24] impressions */
     const int64_t *cost_off;  const double *cost;          /* explicit: one per impression   */
     const double *drift;                                /* optional [E,3,K] coefficients  */
+    const unsigned char *packed;                        /* optional packed records, or NULL */
+    const int64_t *packed_off;                          /* [E*K+1] byte offsets into packed */
 } adc_tape;
 
 const char *adc_last_error(void);

@@ -60,15 +60,20 @@ def _check(case, s, obs, reward, term, trunc, env, E, cum):
 
 
 @pytest.mark.parametrize("E", [1, 3])
-@pytest.mark.parametrize("force_serial", [False, True])
+@pytest.mark.parametrize("force_serial", [False, True, "packed"])
 @pytest.mark.parametrize("path", CASES, ids=IDS)
 def test_replay_reproduces_reference(path, E, force_serial):
     from adcraft_b200.tape import DeviceTape
     case = golden_io.load_case(path)
+    packed = force_serial == "packed"
+    if packed:
+        force_serial = False
+        if case.meta["kind"] != "implicit":
+            pytest.skip("packed records exist for implicit keywords only")
     env = _make_env(case, E)
     cum = 0.0
     for s in case.steps:
-        tape = DeviceTape.from_host([s.tape] * E, "cuda")
+        tape = DeviceTape.from_host([s.tape] * E, "cuda", pack=packed)
         bids = torch.from_numpy(np.tile(s.bid_cents / 100.0, (E, 1))).cuda()
         budget = torch.full((E,), s.budget, dtype=torch.float64, device="cuda")  # passed every step
         obs, reward, term, trunc, _ = env.step_replay({"keyword_bids": bids, "budget": budget}, tape,

@@ -31,7 +31,7 @@ def _random_tape(orc, rng, kind, K, vols, explicit_p=0.5):
                                cost=cost if kind == orc.EXPLICIT else None)
 
 
-@pytest.mark.parametrize("n_lanes", [0, 1])
+@pytest.mark.parametrize("n_lanes", [0, 1, "packed"])
 @pytest.mark.parametrize("kind_name", ["implicit", "explicit"])
 @pytest.mark.parametrize("alias", [False, True])
 def test_replay_matches_oracle(orc, kind_name, alias, n_lanes):
@@ -39,6 +39,11 @@ def test_replay_matches_oracle(orc, kind_name, alias, n_lanes):
     from adcraft_b200.vector_env import VectorBiddingSimulation
     rng = np.random.default_rng(17 + alias)
     kind = orc.IMPLICIT if kind_name == "implicit" else orc.EXPLICIT
+    packed = n_lanes == "packed"
+    if packed:
+        n_lanes = 0
+        if kind == orc.EXPLICIT:
+            pytest.skip("packed records exist for implicit keywords only")
     K, E = 11, 37
     table = make_implicit_table(rng, K, 60) if kind == orc.IMPLICIT else make_explicit_table(rng, K)
     env = VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=1000.0, device="cuda",
@@ -54,7 +59,7 @@ def test_replay_matches_oracle(orc, kind_name, alias, n_lanes):
         bids = np.round(rng.uniform(0.01, 1.6, (E, K)), 2)
         obs, reward, term, trunc, _ = env.step_replay(
             {"keyword_bids": torch.from_numpy(bids).cuda(), "budget": torch.from_numpy(budgets).cuda()},
-            DeviceTape.from_host(tapes, "cuda"))
+            DeviceTape.from_host(tapes, "cuda", pack=packed))
         for e in range(E):
             kw = oracle_keywordset(orc, table)
             out = orc.step_replay(kw, np.rint(bids[e] * 100).astype(np.int32), float(budgets[e]), tapes[e],
@@ -69,3 +74,82 @@ def test_replay_matches_oracle(orc, kind_name, alias, n_lanes):
             assert abs(rb - out["remaining_budget"]) < 1e-9 * (1 + abs(budgets[e]))
             cum[e] += out["reward"]
         np.testing.assert_allclose(obs["cumulative_profit"][:, 0].cpu().numpy(), cum, rtol=1e-9, atol=1e-9)
+
+
+def _oracle_check(orc, table, obs, reward, bids, budgets, tapes, alias=False):
+    for e in range(len(tapes)):
+        kw = oracle_keywordset(orc, table)
+        out = orc.step_replay(kw, np.rint(bids[e] * 100).astype(np.int32), float(budgets[e]), tapes[e],
+                              budget_alias=alias)
+        for a, b in (("impressions", "impressions"), ("buyside_clicks", "clicks"),
+                     ("sellside_conversions", "conversions")):
+            assert np.array_equal(obs[a][e].cpu().numpy(), out[b]), (a, e)
+        np.testing.assert_allclose(obs["cost"][e].cpu().numpy(), out["cost"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(obs["revenue"][e].cpu().numpy(), out["revenue"], rtol=1e-9, atol=1e-12)
+        assert abs(float(reward[e]) - out["reward"]) < 1e-9 * (1 + out["cost"].sum() + out["revenue"].sum())
+
+
+def test_packed_replay_edge_records(orc):
+    """Packed kernel routes: records larger than a shared-memory stage (generic walk from global
+    memory), bids above the 16-bit fast range, negative competitor bids and revenues >= 65536
+    cents (generic re-walk of the staged record), and the unit mix of a batch boundary (E*K not a
+    multiple of 32 or 8).  Tapes shorter than the walk (overrun -> serial kernel) are covered by the
+    budget-bound goldens in test_gpu_golden.py."""
+    from adcraft_b200.tape import DeviceTape
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    rng = np.random.default_rng(5)
+    K, E = 13, 21
+    table = make_implicit_table(rng, K, 60)
+    env = VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=1e9, device="cuda",
+                                  obs_dtype=torch.float64, autoreset=False)
+    env.reset()
+    budgets = np.full(E, 1e9)
+    for step in range(2):
+        vols = rng.integers(0, 130, (E, K))
+        vols[rng.random((E, K)) < 0.1] = 0
+        vols[rng.random((E, K)) < 0.1] += 2000          # far beyond one stage
+        tapes = []
+        for e in range(E):
+            comp, ucl, ucv, rev = [], [], [], []
+            for k in range(K):
+                V = int(vols[e, k])
+                c = rng.integers(0, 160, V)
+                r = rng.integers(1, 300, V)
+                if (e + k) % 5 == 0 and V:
+                    c[rng.integers(0, V)] = -rng.integers(1, 100000)   # negative competitor bid
+                if (e + k) % 7 == 0 and V:
+                    r[: max(1, V // 3)] = rng.integers(65536, 2_000_000_000, max(1, V // 3))
+                comp.append(c); ucl.append(rng.random(V)); ucv.append(rng.random(V)); rev.append(r)
+            tapes.append(orc.Tape.from_lists(vols[e], comp, ucl, ucv, rev))
+        bids = np.round(rng.uniform(0.01, 1.6, (E, K)), 2)
+        bids[rng.random((E, K)) < 0.1] = 700.0           # above kMaxFlatBidCents
+        tape = DeviceTape.from_host(tapes, "cuda", pack=True)
+        obs, reward, *_ = env.step_replay(
+            {"keyword_bids": torch.from_numpy(bids).cuda(), "budget": torch.from_numpy(budgets).cuda()}, tape)
+        _oracle_check(orc, table, obs, reward, bids, budgets, tapes)
+
+
+def test_packed_replay_rejects_corrupt_headers(orc):
+    """A record whose header claims more entries than the record holds must neither fault nor be
+    trusted: the unit flags an overrun and its env is re-walked by the serial kernel from the CSR
+    streams, so the step still equals the oracle."""
+    from adcraft_b200.tape import DeviceTape
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    rng = np.random.default_rng(6)
+    K, E = 5, 9
+    table = make_implicit_table(rng, K, 60)
+    env = VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=1e9, device="cuda",
+                                  obs_dtype=torch.float64, autoreset=False)
+    env.reset()
+    vols = rng.integers(1, 100, (E, K))
+    tapes = [_random_tape(orc, rng, orc.IMPLICIT, K, vols[e]) for e in range(E)]
+    tape = DeviceTape.from_host(tapes, "cuda", pack=True)
+    b32 = tape.packed.view(torch.int32)
+    off = tape.packed_off.cpu().numpy()
+    for u, (field, val) in {3: (2, 1 << 28), 11: (1, 1 << 20), 17: (4, -7), 23: (3, 100000)}.items():
+        b32[off[u] // 4 + field] = val
+    bids = np.round(rng.uniform(0.01, 1.6, (E, K)), 2)
+    budgets = np.full(E, 1e9)
+    obs, reward, *_ = env.step_replay(
+        {"keyword_bids": torch.from_numpy(bids).cuda(), "budget": torch.from_numpy(budgets).cuda()}, tape)
+    _oracle_check(orc, table, obs, reward, bids, budgets, tapes)
