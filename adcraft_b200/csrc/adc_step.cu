@@ -1006,8 +1006,9 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
 //
 // A unit's whole day is one 16-byte aligned record (header, competitor bids, click uniforms,
 // conversion uniforms, revenues; see include/adcraft_b200.h), so the kernel moves it with ONE bulk
-// copy (TMA, cp.async.bulk -> mbarrier complete_tx) into a per-warp ring of kPkStages shared-memory
-// buffers, kPkStages-1 units ahead of the walk.  No per-lane address arithmetic, bounds checks or
+// copy (TMA, cp.async.bulk -> mbarrier complete_tx) into a per-warp byte ring in shared memory, as
+// many units ahead of the walk as fit (records are variable-sized: a dense day is ~1.8 KB, so a
+// 7 KB ring keeps 3 in flight).  No per-lane address arithmetic, bounds checks or
 // dependent DRAM round trips are left in the walk: the warp reads the record from shared memory
 // (128-bit loads of four consecutive competitor bids per lane, click uniforms gathered by
 // impression rank, conversion uniforms and revenues as dense prefixes) and reduces with REDUX.
@@ -1015,10 +1016,10 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
 // outside the 16-bit fast-path range are walked by pk_walk_generic (64-bit sums, any address
 // space); malformed records flag an overrun, which routes the env to the serial kernel (CSR tape).
 // ------------------------------------------------------------------------------------------
-constexpr int kPkMaxCap = 4096;  // largest stage size instantiated (bounds the 32-bit fast-path sums)
+constexpr int kPkMaxCap = 8192;  // largest ring instantiated (bounds the 32-bit fast-path sums)
 
 struct __align__(16) PkUnit {  // 32 B per unit in shared memory
-    long long off;             // byte offset of the record
+    const unsigned char *src;  // the record in global memory
     int bytes;                 // record size, 0 = empty, < 0 = malformed offsets
     int bid_cents;
     double ctr, cvr;
@@ -1130,78 +1131,88 @@ __device__ __noinline__ PkResult pk_walk_generic(const unsigned char *rec, int b
     return r;
 }
 
-// Record resident in shared memory, bid <= kMaxFlatBidCents: 32-bit sums, REDUX reductions.  Returns
-// false when a value leaves the 16-bit range the 32-bit sums are safe for (negative competitor
-// bid, revenue >= 65536 cents): the caller redoes the unit with pk_walk_generic.
+// Record resident in shared memory, bid <= kMaxFlatBidCents: 32-bit address and sum arithmetic,
+// REDUX reductions.  Returns false when the record needs pk_walk_generic instead: a negative
+// competitor bid or a revenue >= 65536 cents (the 32-bit sums are exact only for 16-bit values:
+// a lane adds at most kPkMaxCap/4/32 = 64 of them), or click uniforms running out mid-walk.
 __device__ __forceinline__ bool pk_walk_fast(const unsigned char *rec, int bytes, int bid_cents, double ctr, double cvr,
-                                             int lane, PkResult &r)
+                                             int lane, unsigned lt, PkResult &r)
 {
     const unsigned FULL = 0xFFFFFFFFu;
-    const unsigned lt = (1u << lane) - 1u;
-    PkView v;
-    r.overrun = !pk_view(rec, bytes, v);
-    r.overrun = r.overrun || v.V > v.n_comp;
-    const int4 *comp = reinterpret_cast<const int4 *>(v.comp);
-    const double *click = reinterpret_cast<const double *>(v.click);
-    const double *conv = reinterpret_cast<const double *>(v.conv);
-    const int *rev = reinterpret_cast<const int *>(v.rev);
+    const int4 h0 = *reinterpret_cast<const int4 *>(rec);
+    const int V = h0.x;
+    int n_comp = h0.y, n_click = h0.z, n_conv = h0.w;
+    int n_rev = *reinterpret_cast<const int *>(rec + 16);
+    // every count below 2048 keeps the 32-bit size arithmetic exact; then the streams must fit the record
+    const int comp_b = ((n_comp + 3) & ~3) * 4;
+    const bool ok = (unsigned)(n_comp | n_click | n_conv | n_rev) < 2048u &&
+                    32 + comp_b + 8 * (n_click + n_conv) + 4 * n_rev <= bytes && (unsigned)n_comp <= (unsigned)V;
+    if (!ok) { n_comp = 0; n_click = 0; n_conv = 0; n_rev = 0; }
+    r.overrun = !ok || V != n_comp;
+    const int4 *comp = reinterpret_cast<const int4 *>(rec + 32);
+    const double *click = reinterpret_cast<const double *>(rec + 32 + (ok ? comp_b : 0));
+    const double *conv = click + n_click;
+    const int *rev = reinterpret_cast<const int *>(conv + n_conv);
+    constexpr unsigned kOne = 1u << 22;  // click counter above the lane's cost sum (< 64 * 65536)
     int nI = 0;
-    unsigned Bl = 0, costl = 0, wild = 0;
-    const int n4 = (v.n_comp + 3) >> 2;  // int4 groups; padding entries are INT32_MAX and never win
+    unsigned acc = 0, wild = 0;
+    const int n4 = (n_comp + 3) >> 2;  // int4 groups; padding entries are INT32_MAX and never win
     int4 c = make_int4(0, 0, 0, 0);
     for (int g0 = 0; g0 < n4; g0 += 32) {
         const int g = g0 + lane;
-        const bool ok = g < n4;
-        if (ok) c = comp[g];
-        const bool w0 = ok && bid_cents > c.x, w1 = ok && bid_cents > c.y;
-        const bool w2 = ok && bid_cents > c.z, w3 = ok && bid_cents > c.w;
+        const bool in = g < n4;
+        if (in) c = comp[g];
+        const bool w0 = in && bid_cents > c.x, w1 = in && bid_cents > c.y;
+        const bool w2 = in && bid_cents > c.z, w3 = in && bid_cents > c.w;
         const unsigned m0 = __ballot_sync(FULL, w0), m1 = __ballot_sync(FULL, w1);
         const unsigned m2 = __ballot_sync(FULL, w2), m3 = __ballot_sync(FULL, w3);
         // auction order inside the trip is lane-major (j = 4 g + q): rank = wins of lower lanes + own earlier wins
         const int r0 = nI + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
         const int r1 = r0 + w0, r2 = r1 + w1, r3 = r2 + w2;
         nI += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-        const bool k0 = w0 && r0 < v.n_click && click[r0] <= ctr;
-        const bool k1 = w1 && r1 < v.n_click && click[r1] <= ctr;
-        const bool k2 = w2 && r2 < v.n_click && click[r2] <= ctr;
-        const bool k3 = w3 && r3 < v.n_click && click[r3] <= ctr;
-        const int c0 = k0 ? c.x : 0, c1 = k1 ? c.y : 0, c2 = k2 ? c.z : 0, c3 = k3 ? c.w : 0;
-        Bl += (unsigned)k0 + (unsigned)k1 + (unsigned)k2 + (unsigned)k3;
-        costl += (unsigned)c0 + (unsigned)c1 + (unsigned)c2 + (unsigned)c3;
-        wild |= (unsigned)(c0 | c1 | c2 | c3);
+        if (nI > n_click) return false;  // tape shorter than the walk: never on a consistent recording
+        if (in) wild |= (unsigned)(c.x | c.y | c.z | c.w);  // sign bit = a negative competitor bid
+        const bool k0 = w0 && click[r0] <= ctr;
+        const bool k1 = w1 && click[r1] <= ctr;
+        const bool k2 = w2 && click[r2] <= ctr;
+        const bool k3 = w3 && click[r3] <= ctr;
+        acc += (k0 ? (unsigned)c.x + kOne : 0u) + (k1 ? (unsigned)c.y + kOne : 0u);
+        acc += (k2 ? (unsigned)c.z + kOne : 0u) + (k3 ? (unsigned)c.w + kOne : 0u);
     }
-    r.overrun = r.overrun || nI > v.n_click;
+    wild &= 0x80000000u;  // INT32_MAX padding has the other bits set
     r.I = nI;
-    r.B = (int)__reduce_add_sync(FULL, Bl);
-    r.overrun = r.overrun || r.B > v.n_conv;
-    const int nB = min(r.B, v.n_conv);
+    r.B = (int)__reduce_add_sync(FULL, acc >> 22);
+    r.overrun = r.overrun || r.B > n_conv;
+    const int nB = min(r.B, n_conv);
     unsigned Sl = 0;
-    for (int i = lane; i < nB; i += 32) Sl += conv[i] <= cvr;
-    r.S = (int)__reduce_add_sync(FULL, Sl);
-    r.overrun = r.overrun || r.S > v.n_rev;
-    const int nS = min(r.S, v.n_rev);
-    unsigned revl = 0;
-    for (int i = lane; i < nS; i += 32) {
-        const unsigned x = (unsigned)rev[i];
-        revl += x;
-        wild |= x;
+    if (lane < nB) Sl += conv[lane] <= cvr;
+    if (lane + 32 < nB) Sl += conv[lane + 32] <= cvr;
+    if (nB > 64) {
+        for (int i = lane + 64; i < nB; i += 32) Sl += conv[i] <= cvr;
     }
-    // a lane adds at most kPkMaxCap/4/32 = 32 values below 2^16 (c < bid <= 65535 when clicked), so the
-    // 32-bit lane and warp sums are exact unless some value had a bit above 15 set
+    r.S = (int)__reduce_add_sync(FULL, Sl);
+    r.overrun = r.overrun || r.S > n_rev;
+    const int nS = min(r.S, n_rev);
+    unsigned revl = 0;
+    if (lane < nS) { const unsigned x = (unsigned)rev[lane]; revl += x; wild |= x; }
+    if (lane + 32 < nS) { const unsigned x = (unsigned)rev[lane + 32]; revl += x; wild |= x; }
+    if (nS > 64) {
+        for (int i = lane + 64; i < nS; i += 32) { const unsigned x = (unsigned)rev[i]; revl += x; wild |= x; }
+    }
     if (__any_sync(FULL, (wild & 0xFFFF0000u) != 0)) return false;
-    r.cost = (long long)__reduce_add_sync(FULL, costl);
+    r.cost = (long long)__reduce_add_sync(FULL, acc & (kOne - 1u));
     r.rev = (long long)__reduce_add_sync(FULL, revl);
     return true;
 }
 
-template <int kPkWarps, int kPkStages, int kPkCap>
-__global__ void __launch_bounds__(kPkWarps * 32)
+template <int kPkWarps, int kRing, int kDepth, int kMinBlocks>
+__global__ void __launch_bounds__(kPkWarps * 32, kMinBlocks)
 adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_constant__ adc_tape t)
 {
-    static_assert(kPkCap <= kPkMaxCap && kPkCap % 16 == 0, "stage size");
-    extern __shared__ __align__(128) unsigned char pk_buf[];  // [kPkWarps][kPkStages][kPkCap]
+    static_assert(kRing <= kPkMaxCap && kRing % 16 == 0, "ring size");
+    extern __shared__ __align__(128) unsigned char pk_buf[];  // [kPkWarps][kRing]
     __shared__ PkUnit s_unit[kPkWarps][32];
-    __shared__ __align__(8) unsigned long long s_bar[kPkWarps][kPkStages];
+    __shared__ __align__(8) unsigned long long s_bar[kPkWarps][kDepth];
     const int K = a.kw.K;
     const int64_t total = (int64_t)a.E * K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1216,14 +1227,19 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
     if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
 
     PkUnit *units = s_unit[warp];
-    unsigned char *stage_buf = pk_buf + (size_t)warp * kPkStages * kPkCap;
-    const uint32_t stage_s = smem_addr(stage_buf);
+    unsigned char *ring = pk_buf + (size_t)warp * kRing;
+    const uint32_t ring_s = smem_addr(ring);
     const uint32_t bar_s = smem_addr(&s_bar[warp][0]);
-    if (lane < kPkStages) mbar_init(bar_s + 8u * lane, 1u);
+    if (lane < kDepth) mbar_init(bar_s + 8u * lane, 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    unsigned n_iss = 0, n_cons = 0;  // copies issued / consumed by this warp (stage = n % kPkStages)
+    // Ring state, warp-uniform.  Records are placed in issue order at `head`, wrapping to 0 when the
+    // next one does not fit before the end; the consumer replays the same placement rule from
+    // `chead`, so no per-record bookkeeping is stored.  [chead, head) in ring order is in flight.
+    unsigned head = 0, chead = 0, slot_i = 0, slot_c = 0, ph_c = 0;
+    int in_flight = 0;
+    const unsigned lt = (1u << lane) - 1u;
 
     for (int64_t batch = gwarp; batch < n_batches; batch += n_warps) {
         // ---------------- header, lane <-> unit ----------------
@@ -1233,13 +1249,13 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
         const bool valid = lane < cnt && u < total;
         int e = 0;
         PkUnit pu;
-        pu.off = 0; pu.bytes = 0; pu.bid_cents = 0; pu.ctr = 0.0; pu.cvr = 0.0;
+        pu.src = t.packed; pu.bytes = 0; pu.bid_cents = 0; pu.ctr = 0.0; pu.cvr = 0.0;
         if (valid) {
             e = (int)(u / K);
             const int64_t pi = (int64_t)e * a.kw.env_stride + (u - (int64_t)e * K);
             const long long o0 = t.packed_off[u], o1 = t.packed_off[u + 1];
             const long long len = o1 - o0;
-            pu.off = o0;
+            pu.src = t.packed + o0;
             pu.bytes = (o0 < 0 || len < 0 || len > 0x7FFFFFF0LL || ((o0 | len) & 15)) ? -1 : (int)len;
             pu.ctr = a.kw.ctr[pi];
             pu.cvr = a.kw.cvr[pi];
@@ -1248,43 +1264,60 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
         units[lane] = pu;
         __syncwarp();
         const unsigned work_m = __ballot_sync(FULL, pu.bytes >= 32);
-        const unsigned fast_m = __ballot_sync(FULL, pu.bytes >= 32 && pu.bytes <= kPkCap && pu.bid_cents <= kMaxFlatBidCents);
+        const unsigned fast_m = __ballot_sync(FULL, pu.bytes >= 32 && pu.bytes <= kRing && pu.bid_cents <= kMaxFlatBidCents);
         bool my_overrun = pu.bytes < 0 || (pu.bytes > 0 && pu.bytes < 32);
 
-        // ---------------- the units, one after the other; copies run kPkStages-1 units ahead ----------------
+        // ---------------- the units, one after the other; copies run ahead as far as the ring allows ----------------
         int I = 0, B = 0, S = 0;
         long long cost = 0, rev = 0;
         unsigned iss_m = fast_m;
-        auto issue_next = [&]() {
+        auto try_issue = [&]() -> bool {
             const int bi = __ffs(iss_m) - 1;
-            iss_m &= iss_m - 1;
-            const unsigned st = n_iss % kPkStages;
-            if (lane == 0) {
-                const PkUnit h = units[bi];
-                bulk_load(stage_s + st * kPkCap, t.packed + h.off, (uint32_t)h.bytes, bar_s + 8u * st);
+            const uint4 hw = *reinterpret_cast<const uint4 *>(&units[bi]);  // src (64 bit), bytes, bid
+            const unsigned bytes = hw.z;
+            if (in_flight == 0) { head = 0; chead = 0; }  // both pointers coincide: restart at the ring base
+            const bool straight = head + bytes <= (unsigned)kRing;
+            const unsigned off = straight ? head : 0u;
+            bool fit = true;
+            if (in_flight != 0) {
+                fit = in_flight < kDepth &&
+                      (straight ? (head > chead || (head < chead && head + bytes <= chead))
+                                : (head > chead && bytes <= chead));
             }
-            ++n_iss;
+            if (!fit) return false;
+            iss_m &= iss_m - 1;
+            if (lane == 0) {
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(
+                    ((unsigned long long)hw.y << 32) | hw.x);
+                bulk_load(ring_s + off, src, bytes, bar_s + 8u * slot_i);
+            }
+            head = off + bytes;
+            slot_i = slot_i + 1 == kDepth ? 0 : slot_i + 1;
+            ++in_flight;
+            return true;
         };
 #pragma unroll 1
-        for (int sidx = 0; sidx < kPkStages - 1 && iss_m; ++sidx) issue_next();
+        while (iss_m && try_issue()) {}
         unsigned todo = work_m;
 #pragma unroll 1
         while (todo) {
             const int b = __ffs(todo) - 1;
             todo &= todo - 1;
-            __syncwarp();  // everyone is done reading the stage the next copy overwrites
-            if (iss_m && n_iss - n_cons < (unsigned)kPkStages) issue_next();
+            __syncwarp();  // everyone is done reading the records consumed so far
+            if (iss_m && try_issue() && iss_m) try_issue();
             const PkUnit h = units[b];
             PkResult r;
             if ((fast_m >> b) & 1u) {
-                const unsigned st = n_cons % kPkStages;
-                mbar_wait(bar_s + 8u * st, (n_cons / kPkStages) & 1u);
-                ++n_cons;
-                const unsigned char *rec = stage_buf + st * kPkCap;
-                if (!pk_walk_fast(rec, h.bytes, h.bid_cents, h.ctr, h.cvr, lane, r))
+                mbar_wait(bar_s + 8u * slot_c, ph_c);
+                if (slot_c + 1 == kDepth) { slot_c = 0; ph_c ^= 1u; } else { ++slot_c; }
+                const unsigned off = chead + (unsigned)h.bytes <= (unsigned)kRing ? chead : 0u;
+                chead = off + (unsigned)h.bytes;
+                --in_flight;
+                const unsigned char *rec = ring + off;
+                if (!pk_walk_fast(rec, h.bytes, h.bid_cents, h.ctr, h.cvr, lane, lt, r))
                     r = pk_walk_generic(rec, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
             } else {
-                r = pk_walk_generic(t.packed + h.off, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
+                r = pk_walk_generic(h.src, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
             }
             if (lane == b) {
                 I = r.I; B = r.B; S = r.S; cost = r.cost; rev = r.rev; my_overrun = r.overrun;
@@ -1718,12 +1751,12 @@ static cudaError_t launch_lanes(const adc_step_args &a, cudaStream_t s, int64_t 
     return cudaGetLastError();
 }
 
-template <int W, int NS, int CAP>
+template <int W, int RING, int DEPTH, int MINB>
 static cudaError_t launch_packed(const adc_step_args &a, const adc_tape &tp, cudaStream_t s, int64_t *launches)
 {
-    auto kern = adc_replay_packed_kernel<W, NS, CAP>;
+    auto kern = adc_replay_packed_kernel<W, RING, DEPTH, MINB>;
     constexpr int block = W * 32;
-    constexpr size_t dyn = (size_t)W * NS * CAP;
+    constexpr size_t dyn = (size_t)W * RING;
     static bool configured = false;
     if (!configured) {
         const cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -1806,15 +1839,15 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         ++*launches;
         err = cudaGetLastError();
     } else if (tp.packed != nullptr) {
-        // stage geometry: 8 warps x 3 stages x 4 KB = 96 KB per CTA, two CTAs per SM.  ADC_PK_VARIANT
-        // selects the other instantiations (measurement knob, read once).
+        // ring geometry: 8 warps x 7 KB per CTA, three CTAs per SM.  ADC_PK_VARIANT selects the other
+        // instantiations (measurement knob, read once).
         static const int variant = [] { const char *v = getenv("ADC_PK_VARIANT"); return v ? atoi(v) : 0; }();
         switch (variant) {
-            case 1: err = launch_packed<8, 4, 3072>(a, tp, s, launches); break;
-            case 2: err = launch_packed<4, 4, 4096>(a, tp, s, launches); break;
-            case 3: err = launch_packed<8, 2, 4096>(a, tp, s, launches); break;
-            case 4: err = launch_packed<6, 3, 4096>(a, tp, s, launches); break;
-            default: err = launch_packed<8, 3, 4096>(a, tp, s, launches); break;
+            case 1: err = launch_packed<8, 8192, 4, 3>(a, tp, s, launches); break;
+            case 2: err = launch_packed<8, 5632, 3, 4>(a, tp, s, launches); break;
+            case 3: err = launch_packed<8, 6144, 4, 3>(a, tp, s, launches); break;
+            case 4: err = launch_packed<4, 7168, 4, 6>(a, tp, s, launches); break;
+            default: err = launch_packed<8, 7168, 4, 3>(a, tp, s, launches); break;
         }
     } else {
         auto kern = adc_replay_implicit_kernel;
