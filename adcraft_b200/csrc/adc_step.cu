@@ -1008,21 +1008,27 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
 // conversion uniforms, revenues; see include/adcraft_b200.h), so the kernel moves it with ONE bulk
 // copy (TMA, cp.async.bulk -> mbarrier complete_tx) into a per-warp byte ring in shared memory, as
 // many units ahead of the walk as fit (records are variable-sized: a dense day is ~1.8 KB, so a
-// 7 KB ring keeps 3 in flight).  No per-lane address arithmetic, bounds checks or
+// 6 KB ring keeps 3 in flight).  No per-lane address arithmetic, bounds checks or
 // dependent DRAM round trips are left in the walk: the warp reads the record from shared memory
 // (128-bit loads of four consecutive competitor bids per lane, click uniforms gathered by
 // impression rank, conversion uniforms and revenues as dense prefixes) and reduces with REDUX.
-// Records that do not fit a stage (very large volumes), bids above kMaxFlatBidCents or values
+// Records that do not fit the ring (very large volumes), bids above kMaxFlatBidCents or values
 // outside the 16-bit fast-path range are walked by pk_walk_generic (64-bit sums, any address
 // space); malformed records flag an overrun, which routes the env to the serial kernel (CSR tape).
 // ------------------------------------------------------------------------------------------
 constexpr int kPkMaxCap = 8192;  // largest ring instantiated (bounds the 32-bit fast-path sums)
 
-struct __align__(16) PkUnit {  // 32 B per unit in shared memory
+struct __align__(16) PkUnit {  // 48 B per unit in shared memory
     const unsigned char *src;  // the record in global memory
-    int bytes;                 // record size, 0 = empty, < 0 = malformed offsets
+    int bytes;                 // record size, 0 = nothing to walk
     int bid_cents;
     double ctr, cvr;
+    int n_comp, n_click, n_conv, n_rev;  // validated header of a record that takes the fast walk
+};
+
+struct __align__(16) PkOut {  // a walked unit's sums, written over the first 32 B of its PkUnit
+    int I, B, S, overrun;
+    long long cost, rev;
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1084,6 +1090,16 @@ __device__ __forceinline__ bool pk_view(const unsigned char *rec, int bytes, PkV
     return ok;
 }
 
+// Fast-walk precondition, checked once per unit by its owner lane on the header in global memory:
+// every count below 2048 (keeps the 32-bit size arithmetic exact and the 32-bit sums safe), the
+// streams fit the record, and the competitor stream covers the whole volume.
+__device__ __forceinline__ bool pk_header_ok(const int4 h0, int n_rev, int bytes)
+{
+    const int V = h0.x, n_comp = h0.y, n_click = h0.z, n_conv = h0.w;
+    return (unsigned)(n_comp | n_click | n_conv | n_rev) < 2048u &&
+           32 + ((n_comp + 3) & ~3) * 4 + 8 * (n_click + n_conv) + 4 * n_rev <= bytes && V == n_comp;
+}
+
 // Any record, any address space, 64-bit sums.
 __device__ __noinline__ PkResult pk_walk_generic(const unsigned char *rec, int bytes, int bid_cents, double ctr,
                                                  double cvr, int lane)
@@ -1135,22 +1151,15 @@ __device__ __noinline__ PkResult pk_walk_generic(const unsigned char *rec, int b
 // REDUX reductions.  Returns false when the record needs pk_walk_generic instead: a negative
 // competitor bid or a revenue >= 65536 cents (the 32-bit sums are exact only for 16-bit values:
 // a lane adds at most kPkMaxCap/4/32 = 64 of them), or click uniforms running out mid-walk.
-__device__ __forceinline__ bool pk_walk_fast(const unsigned char *rec, int bytes, int bid_cents, double ctr, double cvr,
-                                             int lane, unsigned lt, PkResult &r)
+__device__ __forceinline__ bool pk_walk_fast(const unsigned char *rec, int n_comp, int n_click, int n_conv, int n_rev,
+                                             int bid_cents, double ctr, double cvr, int lane, unsigned lt, PkResult &r)
 {
     const unsigned FULL = 0xFFFFFFFFu;
-    const int4 h0 = *reinterpret_cast<const int4 *>(rec);
-    const int V = h0.x;
-    int n_comp = h0.y, n_click = h0.z, n_conv = h0.w;
-    int n_rev = *reinterpret_cast<const int *>(rec + 16);
-    // every count below 2048 keeps the 32-bit size arithmetic exact; then the streams must fit the record
-    const int comp_b = ((n_comp + 3) & ~3) * 4;
-    const bool ok = (unsigned)(n_comp | n_click | n_conv | n_rev) < 2048u &&
-                    32 + comp_b + 8 * (n_click + n_conv) + 4 * n_rev <= bytes && (unsigned)n_comp <= (unsigned)V;
-    if (!ok) { n_comp = 0; n_click = 0; n_conv = 0; n_rev = 0; }
-    r.overrun = !ok || V != n_comp;
+    // the header was validated by the unit's owner lane (pk_header_ok): all counts < 2048 and
+    // consistent with the record size, n_comp == V
+    r.overrun = false;
     const int4 *comp = reinterpret_cast<const int4 *>(rec + 32);
-    const double *click = reinterpret_cast<const double *>(rec + 32 + (ok ? comp_b : 0));
+    const double *click = reinterpret_cast<const double *>(rec + 32 + ((n_comp + 3) & ~3) * 4);
     const double *conv = click + n_click;
     const int *rev = reinterpret_cast<const int *>(conv + n_conv);
     constexpr unsigned kOne = 1u << 22;  // click counter above the lane's cost sum (< 64 * 65536)
@@ -1158,7 +1167,9 @@ __device__ __forceinline__ bool pk_walk_fast(const unsigned char *rec, int bytes
     unsigned acc = 0, wild = 0;
     const int n4 = (n_comp + 3) >> 2;  // int4 groups; padding entries are INT32_MAX and never win
     int4 c = make_int4(0, 0, 0, 0);
-    for (int g0 = 0; g0 < n4; g0 += 32) {
+    int g0 = 0;
+    // full trips: 128 auctions, four consecutive ones per lane (one 128-bit load)
+    for (; n4 - g0 > 16; g0 += 32) {
         const int g = g0 + lane;
         const bool in = g < n4;
         if (in) c = comp[g];
@@ -1178,6 +1189,23 @@ __device__ __forceinline__ bool pk_walk_fast(const unsigned char *rec, int bytes
         const bool k3 = w3 && click[r3] <= ctr;
         acc += (k0 ? (unsigned)c.x + kOne : 0u) + (k1 ? (unsigned)c.y + kOne : 0u);
         acc += (k2 ? (unsigned)c.z + kOne : 0u) + (k3 ? (unsigned)c.w + kOne : 0u);
+    }
+    // the last <= 64 auctions: one per lane and trip (a volume just above 128 would otherwise pay a
+    // whole 128-wide trip for a handful of auctions)
+    const int *comp1 = reinterpret_cast<const int *>(comp);
+    for (int j0 = 4 * g0; j0 < n_comp; j0 += 32) {
+        const int j = j0 + lane;
+        const bool in = j < n_comp;
+        int c1 = 0;
+        if (in) c1 = comp1[j];
+        const bool w = in && bid_cents > c1;
+        const unsigned m = __ballot_sync(FULL, w);
+        const int rk = nI + __popc(m & lt);
+        nI += __popc(m);
+        if (nI > n_click) return false;
+        wild |= (unsigned)c1;
+        const bool k = w && click[rk] <= ctr;
+        acc += k ? (unsigned)c1 + kOne : 0u;
     }
     wild &= 0x80000000u;  // INT32_MAX padding has the other bits set
     r.I = nI;
@@ -1218,11 +1246,9 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gwarp = (int64_t)blockIdx.x * kPkWarps + warp;
     const int64_t n_warps = (int64_t)gridDim.x * kPkWarps;
-    // full rounds of 32-unit batches, then 8-unit tail batches (same split as the hot kernel)
-    constexpr int kTail = 8;
-    const int64_t big_rounds = total / (32 * n_warps);
-    const int64_t n_big = big_rounds * n_warps;
-    const int64_t n_batches = n_big + (total - n_big * 32 + kTail - 1) / kTail;
+    // every warp walks one contiguous range of units (equal shares, +-1 unit) in batches of 32
+    const int64_t u_begin = (total / n_warps) * gwarp + min(gwarp, total % n_warps);
+    const int64_t u_end = u_begin + total / n_warps + (gwarp < total % n_warps ? 1 : 0);
     const unsigned FULL = 0xFFFFFFFFu;
     if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
 
@@ -1237,54 +1263,62 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
     // Ring state, warp-uniform.  Records are placed in issue order at `head`, wrapping to 0 when the
     // next one does not fit before the end; the consumer replays the same placement rule from
     // `chead`, so no per-record bookkeeping is stored.  [chead, head) in ring order is in flight.
-    unsigned head = 0, chead = 0, slot_i = 0, slot_c = 0, ph_c = 0;
+    unsigned head = 0, chead = 0, used = 0, slot_i = 0, slot_c = 0, ph_c = 0;
     int in_flight = 0;
     const unsigned lt = (1u << lane) - 1u;
 
-    for (int64_t batch = gwarp; batch < n_batches; batch += n_warps) {
+    for (int64_t u0 = u_begin; u0 < u_end; u0 += 32) {
         // ---------------- header, lane <-> unit ----------------
-        const bool big = batch < n_big;
-        const int cnt = big ? 32 : kTail;
-        const int64_t u = (big ? batch * 32 : n_big * 32 + (batch - n_big) * kTail) + lane;
-        const bool valid = lane < cnt && u < total;
+        const int64_t u = u0 + lane;
+        const bool valid = u < u_end;
         int e = 0;
         PkUnit pu;
         pu.src = t.packed; pu.bytes = 0; pu.bid_cents = 0; pu.ctr = 0.0; pu.cvr = 0.0;
+        pu.n_comp = pu.n_click = pu.n_conv = pu.n_rev = 0;
+        bool my_overrun = false, fast = false;
         if (valid) {
             e = (int)(u / K);
             const int64_t pi = (int64_t)e * a.kw.env_stride + (u - (int64_t)e * K);
             const long long o0 = t.packed_off[u], o1 = t.packed_off[u + 1];
             const long long len = o1 - o0;
+            const bool sane = o0 >= 0 && len >= 0 && len <= 0x7FFFFFF0LL && ((o0 | len) & 15) == 0 && (len == 0 || len >= 32);
+            my_overrun = !sane;
             pu.src = t.packed + o0;
-            pu.bytes = (o0 < 0 || len < 0 || len > 0x7FFFFFF0LL || ((o0 | len) & 15)) ? -1 : (int)len;
+            pu.bytes = sane ? (int)len : 0;
             pu.ctr = a.kw.ctr[pi];
             pu.cvr = a.kw.cvr[pi];
             pu.bid_cents = bid_to_cents(load_f(a.bids, a.bids_dtype, u));
+            if (pu.bytes > 0 && pu.bytes <= kRing && pu.bid_cents <= kMaxFlatBidCents) {
+                // owner lane reads the record header (the bulk copy re-reads the line from L2)
+                const int4 h0 = __ldg(reinterpret_cast<const int4 *>(pu.src));
+                const int n_rev = __ldg(reinterpret_cast<const int *>(pu.src + 16));
+                if (pk_header_ok(h0, n_rev, pu.bytes)) {
+                    fast = true;
+                    pu.n_comp = h0.y; pu.n_click = h0.z; pu.n_conv = h0.w; pu.n_rev = n_rev;
+                } else {
+                    my_overrun = true;  // the serial kernel re-walks the env from the CSR streams
+                    pu.bytes = 0;
+                }
+            }
         }
         units[lane] = pu;
         __syncwarp();
-        const unsigned work_m = __ballot_sync(FULL, pu.bytes >= 32);
-        const unsigned fast_m = __ballot_sync(FULL, pu.bytes >= 32 && pu.bytes <= kRing && pu.bid_cents <= kMaxFlatBidCents);
-        bool my_overrun = pu.bytes < 0 || (pu.bytes > 0 && pu.bytes < 32);
+        const unsigned work_m = __ballot_sync(FULL, pu.bytes > 0);
+        const unsigned fast_m = __ballot_sync(FULL, fast);
 
         // ---------------- the units, one after the other; copies run ahead as far as the ring allows ----------------
-        int I = 0, B = 0, S = 0;
-        long long cost = 0, rev = 0;
         unsigned iss_m = fast_m;
         auto try_issue = [&]() -> bool {
             const int bi = __ffs(iss_m) - 1;
             const uint4 hw = *reinterpret_cast<const uint4 *>(&units[bi]);  // src (64 bit), bytes, bid
             const unsigned bytes = hw.z;
-            if (in_flight == 0) { head = 0; chead = 0; }  // both pointers coincide: restart at the ring base
+            if (in_flight == 0) { head = 0; chead = 0; used = 0; }  // pointers coincide: restart at the ring base
+            // `used` = bytes between chead and head in ring order, skipped ring ends included
             const bool straight = head + bytes <= (unsigned)kRing;
             const unsigned off = straight ? head : 0u;
-            bool fit = true;
-            if (in_flight != 0) {
-                fit = in_flight < kDepth &&
-                      (straight ? (head > chead || (head < chead && head + bytes <= chead))
-                                : (head > chead && bytes <= chead));
-            }
-            if (!fit) return false;
+            const unsigned need = straight ? bytes : bytes + ((unsigned)kRing - head);
+            if (in_flight >= kDepth || used + need > (unsigned)kRing) return false;
+            used += need;
             iss_m &= iss_m - 1;
             if (lane == 0) {
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(
@@ -1304,24 +1338,35 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
             const int b = __ffs(todo) - 1;
             todo &= todo - 1;
             __syncwarp();  // everyone is done reading the records consumed so far
-            if (iss_m && try_issue() && iss_m) try_issue();
+            if (iss_m) try_issue();
             const PkUnit h = units[b];
             PkResult r;
             if ((fast_m >> b) & 1u) {
                 mbar_wait(bar_s + 8u * slot_c, ph_c);
                 if (slot_c + 1 == kDepth) { slot_c = 0; ph_c ^= 1u; } else { ++slot_c; }
-                const unsigned off = chead + (unsigned)h.bytes <= (unsigned)kRing ? chead : 0u;
+                const bool straight = chead + (unsigned)h.bytes <= (unsigned)kRing;
+                const unsigned off = straight ? chead : 0u;
+                used -= straight ? (unsigned)h.bytes : (unsigned)h.bytes + ((unsigned)kRing - chead);
                 chead = off + (unsigned)h.bytes;
                 --in_flight;
                 const unsigned char *rec = ring + off;
-                if (!pk_walk_fast(rec, h.bytes, h.bid_cents, h.ctr, h.cvr, lane, lt, r))
+                if (!pk_walk_fast(rec, h.n_comp, h.n_click, h.n_conv, h.n_rev, h.bid_cents, h.ctr, h.cvr, lane, lt, r))
                     r = pk_walk_generic(rec, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
             } else {
                 r = pk_walk_generic(h.src, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
             }
-            if (lane == b) {
-                I = r.I; B = r.B; S = r.S; cost = r.cost; rev = r.rev; my_overrun = r.overrun;
+            if (lane == 0) {  // hand the sums to the owner lane through the unit's slot
+                PkOut o;
+                o.I = r.I; o.B = r.B; o.S = r.S; o.overrun = r.overrun; o.cost = r.cost; o.rev = r.rev;
+                *reinterpret_cast<PkOut *>(&units[b]) = o;
             }
+        }
+        __syncwarp();
+        int I = 0, B = 0, S = 0;
+        long long cost = 0, rev = 0;
+        if (pu.bytes > 0) {
+            const PkOut o = *reinterpret_cast<const PkOut *>(&units[lane]);
+            I = o.I; B = o.B; S = o.S; cost = o.cost; rev = o.rev; my_overrun = o.overrun != 0;
         }
 
         // ---------------- outputs (coalesced), env completion ----------------
@@ -1839,15 +1884,15 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         ++*launches;
         err = cudaGetLastError();
     } else if (tp.packed != nullptr) {
-        // ring geometry: 8 warps x 7 KB per CTA, three CTAs per SM.  ADC_PK_VARIANT selects the other
-        // instantiations (measurement knob, read once).
+        // ring geometry: 8 warps x 6 KB per CTA, three CTAs (24 warps) per SM; measured on C2: 6 KB
+        // 0.2125 ms, 7 KB 0.2167 ms, 8 KB (two CTAs per SM) 0.264 ms, 5.5 KB with 64 registers and
+        // four CTAs 0.241 ms.  ADC_PK_VARIANT re-selects them (measurement knob, read once).
         static const int variant = [] { const char *v = getenv("ADC_PK_VARIANT"); return v ? atoi(v) : 0; }();
         switch (variant) {
             case 1: err = launch_packed<8, 8192, 4, 3>(a, tp, s, launches); break;
             case 2: err = launch_packed<8, 5632, 3, 4>(a, tp, s, launches); break;
-            case 3: err = launch_packed<8, 6144, 4, 3>(a, tp, s, launches); break;
-            case 4: err = launch_packed<4, 7168, 4, 6>(a, tp, s, launches); break;
-            default: err = launch_packed<8, 7168, 4, 3>(a, tp, s, launches); break;
+            case 3: err = launch_packed<8, 7168, 4, 3>(a, tp, s, launches); break;
+            default: err = launch_packed<8, 6144, 4, 3>(a, tp, s, launches); break;
         }
     } else {
         auto kern = adc_replay_implicit_kernel;
