@@ -69,6 +69,7 @@ class StepArgs(C.Structure):
         ("force_serial", C.c_int32),
         ("kw", Keywords), ("env", EnvState), ("drift", Drift),
         ("bids", C.c_void_p), ("bids_dtype", C.c_int32), ("budget_in", C.c_void_p),
+        ("env_group", C.c_int32), ("floor_cents", C.c_void_p),
         ("out", StepOut), ("scratch", Scratch), ("detail", Detail),
     ]
 

@@ -69,6 +69,11 @@ int validate(const adc_step_args *a, const adc_tape *tape)
         ADC_REQUIRE(a->n_lanes == 0 || a->n_lanes == -8 || a->n_lanes == -16 || a->n_lanes == -32,
                     "n_lanes <= 0 selects the batched kernel: 0, -8, -16 or -32");
     }
+    ADC_REQUIRE(a->env_group >= 0, "env_group must be >= 0");
+    ADC_REQUIRE(a->env_group <= 1 || a->E % a->env_group == 0, "E must be a multiple of env_group");
+    if (a->env_group > 1 || a->floor_cents != nullptr)
+        ADC_REQUIRE(tape == nullptr && a->kw.kind == ADC_IMPLICIT,
+                    "shared auctions (env_group / floor_cents) need free-running implicit keywords");
     if (tape) {
         ADC_REQUIRE(tape->volume && tape->click_off && tape->u_click && tape->conv_off && tape->u_conv &&
                         tape->rev_off && tape->rev_cents, "tape stream pointer is NULL");

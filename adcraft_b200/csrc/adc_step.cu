@@ -157,7 +157,14 @@ struct UnitPar {
     uint32_t thr_click, thr_conv, thr_impr;
     uint32_t thr_cc;  // implicit: conversion <=> conv_all || cc < thr_cc  (cc = the click word)
     bool conv_all;
+    int floor_cents;  // shared auctions: highest rival bid (INT_MIN when there are no rivals)
 };
+
+// Philox env id: the A bidders of a shared-auction world draw from the same counters.
+__device__ __forceinline__ uint32_t philox_env(const adc_step_args &a, int e)
+{
+    return a.env_base + (uint32_t)(a.env_group > 1 ? e / a.env_group : e);
+}
 
 struct LaneOut {
     int I, B, S;
@@ -258,7 +265,7 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
             } else {
                 // two auctions per Philox call: even j -> words x,y; odd j -> words z,w
                 const uint4 w = src.draw(ST_AUCTION, (uint32_t)kw, (uint32_t)(j >> 1));
-                c = laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale);
+                c = max(laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale), p.floor_cents);
                 w1 = (j & 1) ? w.w : w.y;
                 w2 = w1;
             }
@@ -331,6 +338,7 @@ __device__ __forceinline__ UnitPar load_unit_par(const adc_step_args &a, int e, 
     p.thr_impr = 0u;
     p.thr_cc = 0u;
     p.conv_all = false;
+    p.floor_cents = a.floor_cents != nullptr ? a.floor_cents[u] : (int)0x80000000;
     if (a.kw.kind == ADC_EXPLICIT) {
         p.thr_impr = prob_threshold(threshold_sigmoid(p.bid, a.kw.impression_thresh, a.kw.p1[pi], a.kw.p2[pi]));
     } else {
@@ -450,7 +458,7 @@ adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         if (valid) {
             e = (int)(u / K);
             k = (int)(u - (int64_t)e * K);
-            genv = a.env_base + (uint32_t)e;
+            genv = philox_env(a, e);
             p = load_unit_par(a, e, k);
             PhiloxSrc src{k0, k1, a.step, genv};
             V = unit_volume(a, src, nullptr, e, k, &uw);
@@ -462,7 +470,7 @@ adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         for (long long j = lane; j < V; j += L) {
             const uint4 w = philox4x32_10((uint32_t)(j >> 1), a.step, c2, genv, k0, k1);
             const uint32_t cc = (j & 1) ? w.w : w.y;
-            const int c = laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale);
+            const int c = max(laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale), p.floor_cents);
             const bool win = p.bid_cents > c;
             const bool clk = win && (cc <= p.thr_click);
             const bool cnv = clk && (p.conv_all || cc < p.thr_cc);
@@ -569,10 +577,13 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 // G = lanes that share one unit's auctions (32, 16 or 8): with G < 32 the warp walks 32/G units at
 // a time, which keeps the lanes busy for sparse keywords (a 16-auction day fills a 32-lane trip
 // only half, and the trip's Philox calls a quarter).
-template <int kBU, int G>
+template <int kBU, int G, bool kFloor>
 __global__ void __launch_bounds__(kFlatWarps * 32)
 adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
 {
+    // kFloor: shared auctions (adc_step_args.floor_cents): one extra max per auction, kept out of
+    // the single-bidder instantiation
+    __shared__ int s_floor[kFloor ? kFlatWarps : 1][32];
     __shared__ FlatUnit s_unit[kFlatWarps][32];
     __shared__ unsigned s_res[kFlatWarps][32][4];     // G < 32: per-unit sums handed to the owner lane
     __shared__ FlatRev s_rev[kFlatWarps][32];
@@ -619,14 +630,16 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         if (valid) {
             e = (int)(u / K);
             k = (int)(u - (int64_t)e * K);
-            genv = a.env_base + (uint32_t)e;
+            genv = philox_env(a, e);
             p = load_unit_par(a, e, k);
             const int64_t pi = (int64_t)e * a.kw.env_stride + k;
             const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)k), genv, k0, k1);
             const long long v = volume_draw(w.x, a.kw.vol_mean[pi], a.kw.vol_std[pi]);
             over_cap = v > (G == 32 ? kMaxFlatVolume : 65535) || p.bid_cents > kMaxFlatBidCents;
             V = over_cap ? 0 : (int)v;
+            if (kFloor && p.bid_cents <= p.floor_cents) V = 0;  // a rival bids at least as much: no auction can be won
         }
+        if (kFloor) s_floor[warp][lane] = max(p.floor_cents, 0);
         {
             const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), genv, k0, k1);
             FlatUnit fu;
@@ -656,10 +669,12 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             FlatUnit fu = units[b & 31];
             const bool conv_all = fu.bid_cents < 0;
             fu.bid_cents &= 0x7FFFFFFF;
+            const int floor_c = kFloor ? s_floor[warp][b & 31] : 0;
             unsigned cntIB = 0, cntS = 0, cst = 0;  // I | B << 16 ; S ; cost cents (< 2^32, see caps)
             // one auction: competitor bid from `wc`, click + conversion from the single word `cc`
             auto tally = [&](bool act, uint32_t wc, uint32_t cc) {
-                const int c = laplace_cents(wc, fu.loc, fu.scale, s_tab);
+                int c = laplace_cents(wc, fu.loc, fu.scale, s_tab);
+                if (kFloor) c = max(c, floor_c);
                 const bool win = act && fu.bid_cents > c;
                 const bool clk = win && (cc <= fu.thr_click);
                 const bool cnv = clk && (conv_all || cc < fu.thr_conv);
@@ -766,7 +781,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int ee = __shfl_sync(FULL, e, src);
-                const uint32_t ge = a.env_base + (uint32_t)ee;
+                const uint32_t ge = philox_env(a, ee);
                 for (int kk = lane; kk < K; kk += 32) {
                     if (!drift_wanted(a, kk)) continue;
                     const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)kk), ge, k0, k1);
@@ -1418,7 +1433,7 @@ adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant_
             src.k0 = (uint32_t)a.seed;
             src.k1 = (uint32_t)(a.seed >> 32);
             src.step = a.step;
-            src.env = a.env_base + (uint32_t)e;
+            src.env = philox_env(a, e);
         }
         const UnitPar p = load_unit_par(a, e, k);
         uint4 uw;
@@ -1491,7 +1506,7 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
             src.k0 = (uint32_t)a.seed;
             src.k1 = (uint32_t)(a.seed >> 32);
             src.step = a.step;
-            src.env = a.env_base + (uint32_t)e;
+            src.env = philox_env(a, e);
         }
         for (int k = 0; k < K; ++k) {
             const int64_t u = (int64_t)e * K + k;
@@ -1621,7 +1636,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
 
     for (int idx = gwarp; idx < count; idx += n_warps) {
         const int e = a.scratch.serial_list[idx];
-        PhiloxSrc src{k0, k1, a.step, a.env_base + (uint32_t)e};
+        PhiloxSrc src{k0, k1, a.step, philox_env(a, e)};
         for (int k = lane; k < K; k += 32) {
             const int64_t u = (int64_t)e * K + k;
             a.out.impressions[u] = 0;
@@ -1655,7 +1670,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                         const long long j = j0 + i;
                         const uint4 w = src.draw(ST_AUCTION, (uint32_t)k, (uint32_t)(j >> 1));
                         const uint32_t cc = (j & 1) ? w.w : w.y;
-                        const int c = laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale);
+                        const int c = max(laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale), p.floor_cents);
                         if (p.bid_cents > c) {
                             ++I;
                             if (cc <= p.thr_click) {
@@ -1845,9 +1860,11 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         int per_sm = 0;
         constexpr int kBU = 32;  // 8 and 16 were measured slower: the lane<->unit phases lose more than the tail gains
         // n_lanes: 0 / -32 -> 32 lanes per unit (dense keywords), -16, -8 -> sub-warp groups (sparse)
-        void (*kern)(adc_step_args) = a.n_lanes == -8    ? adc_flat_philox_implicit_kernel<kBU, 8>
-                                      : a.n_lanes == -16 ? adc_flat_philox_implicit_kernel<kBU, 16>
-                                                         : adc_flat_philox_implicit_kernel<kBU, 32>;
+        const bool fl = a.floor_cents != nullptr;
+        void (*kern)(adc_step_args) =
+            a.n_lanes == -8    ? (fl ? adc_flat_philox_implicit_kernel<kBU, 8, true> : adc_flat_philox_implicit_kernel<kBU, 8, false>)
+            : a.n_lanes == -16 ? (fl ? adc_flat_philox_implicit_kernel<kBU, 16, true> : adc_flat_philox_implicit_kernel<kBU, 16, false>)
+                               : (fl ? adc_flat_philox_implicit_kernel<kBU, 32, true> : adc_flat_philox_implicit_kernel<kBU, 32, false>);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
         if (per_sm < 1) per_sm = 1;
         int64_t grid = (int64_t)num_sms() * per_sm;

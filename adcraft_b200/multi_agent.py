@@ -48,6 +48,60 @@ class MultiAgentBiddingSimulation:
         return o, r, te, tr, {a: info for a in self._agent_ids}
 
 
+class SharedAuctionSimulation:
+    """A bidders competing inside ONE auction per (world, keyword, auction) -- BASELINE config 4
+    ("8 competing bidders per auction sharing keyword volume").  The reference
+    has no such mode (its multi-agent env is independent copies, above); the semantics are the
+    reference's own auction applied to the obvious ``other_bids`` matrix: bidder a faces the A-1
+    rival bids plus the keyword's sampled competitor under
+    ``nth_price_auction(n=2, num_winners=1)`` (synthetic_kw_helpers.py:116-180), i.e. it wins iff
+    its bid strictly exceeds every rival and the competitor, and pays the largest of them.  Ties
+    at the top win nothing.  All bidders of a world see the same keyword volumes and competitor
+    draws (``env_group`` in the C ABI); clicks, conversions, revenues, budgets, rewards and
+    episode state are per bidder.
+
+    Rows of the wrapped VectorBiddingSimulation are ``world * A + agent``.  ``step`` takes bids
+    ``[worlds, A, K]`` (device) and optional budgets ``[worlds, A]`` and returns observations with
+    a leading ``[worlds, A]``."""
+
+    def __init__(self, num_agents: int, num_worlds: int, **env_kwargs):
+        self.num_agents, self.num_worlds = int(num_agents), int(num_worlds)
+        env_kwargs["env_group"] = self.num_agents
+        env_kwargs.setdefault("shared_keywords", True)
+        self.vec = VectorBiddingSimulation(self.num_agents * self.num_worlds, **env_kwargs)
+
+    @staticmethod
+    def rival_floor_cents(bids: torch.Tensor) -> torch.Tensor:
+        """[worlds, A, K] dollars -> int32 cents of the highest RIVAL bid per bidder (bids are
+        canonicalised like the env does, ``round(max(bid, 0.01), 2)``, gymnasium_kw_env.py:215)."""
+        cents = torch.round(torch.clamp(bids.to(torch.float64), min=0.01) * 100.0).to(torch.int32)
+        top2 = torch.topk(cents, k=min(2, cents.shape[1]), dim=1).values
+        first = top2[:, 0:1]
+        second = top2[:, 1:2] if cents.shape[1] > 1 else torch.full_like(first, -2**31)
+        is_top = cents == first
+        # the unique top bidder faces the runner-up; everybody else (and tied leaders) faces the top bid
+        unique_top = is_top & (is_top.sum(dim=1, keepdim=True) == 1)
+        return torch.where(unique_top, second.expand_as(cents), first.expand_as(cents)).contiguous()
+
+    def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
+        obs, info = self.vec.reset(seed=seed, options=options)
+        return self._split(obs), info
+
+    def _split(self, obs):
+        W, A = self.num_worlds, self.num_agents
+        return {k: v.view(W, A, *v.shape[1:]) for k, v in obs.items()}
+
+    def step(self, bids: torch.Tensor, budget: Optional[torch.Tensor] = None, *, force_serial: bool = False):
+        W, A, K = self.num_worlds, self.num_agents, self.vec.num_keywords
+        assert tuple(bids.shape) == (W, A, K)
+        floor = self.rival_floor_cents(bids).view(W * A, K)
+        action = {"keyword_bids": bids.reshape(W * A, K).contiguous()}
+        if budget is not None:
+            action["budget"] = budget.reshape(W * A).contiguous()
+        obs, reward, term, trunc, info = self.vec.step(action, force_serial=force_serial, floor_cents=floor)
+        return self._split(obs), reward.view(W, A), term.view(W, A), trunc.view(W, A), info
+
+
 def make_multi_flat(num_agents: int, **env_kwargs) -> MultiAgentBiddingSimulation:
     """``adcraft/multi_agent/env.py:8`` -- one world of ``num_agents`` independent bidders."""
     return MultiAgentBiddingSimulation(num_agents, 1, **env_kwargs)

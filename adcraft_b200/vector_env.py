@@ -59,6 +59,7 @@ class VectorBiddingSimulation:
         budget_alias: bool = False,
         autoreset: bool = True,
         detail_cap: int = 0,
+        env_group: int = 0,
         **kwargs,
     ) -> None:
         assert render_mode is None or render_mode in self.metadata["render_modes"], (
@@ -86,6 +87,10 @@ class VectorBiddingSimulation:
         self.budget_alias = bool(budget_alias)
         self.autoreset = bool(autoreset)
         self.detail_cap = int(detail_cap)  # > 0: record per-click lists on the exact serial path
+        # > 1: consecutive groups of env_group envs are the bidders of ONE auction world and share
+        # every draw (see adc_step_args.env_group and multi_agent.SharedAuctionSimulation)
+        self.env_group = int(env_group)
+        assert self.env_group <= 1 or self.num_envs % self.env_group == 0
         self.shared_keywords = bool(shared_keywords)
         self.obs_dtype = obs_dtype
         assert obs_dtype in (torch.float32, torch.float64)
@@ -259,6 +264,22 @@ class VectorBiddingSimulation:
             self._out[k].zero_()
         return self._obs(), {"keyword_params": self.keywords.describe()}
 
+    def reset_envs(self, mask: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Reset the episode state of the envs with ``mask[e] != 0`` only (what a vector front end
+        without auto-reset does per finished sub-env); keywords persist like ``reset()`` without a
+        seed.  Returns the observation dict, zeroed on the reset rows."""
+        m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        assert m.shape == (self.num_envs,)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _capi.check(self._lib.adc_reset_envs(
+            self.num_envs, m.data_ptr(), self._state["cum_profit"].data_ptr(), self._state["day"].data_ptr(),
+            C.c_void_p(stream)))
+        rows = m.bool()
+        for k in ("impressions", "buyside_clicks", "sellside_conversions", "cost", "revenue",
+                  "cumulative_profit", "days_passed", "reward"):
+            self._out[k][rows] = 0
+        return self._obs()
+
     # ------------------------------------------------------------------ step
     def _obs(self) -> Dict[str, torch.Tensor]:
         if self._obs_cache is not None:
@@ -296,6 +317,8 @@ class VectorBiddingSimulation:
         a.step = self._step_count
         a.budget_alias = int(self.budget_alias)
         a.force_serial = int(force_serial)
+        a.env_group = self.env_group
+        a.floor_cents = None
         a.bids = bids.data_ptr()
         a.bids_dtype = _capi.F64 if bids.dtype == torch.float64 else _capi.F32
         a.budget_in = _ptr(budget)
@@ -349,11 +372,17 @@ class VectorBiddingSimulation:
                 budget = self._stage(budget.to(bids.dtype), self._budget_dev, (E,))
         return bids, budget
 
-    def step(self, action: Dict[str, ArrayLike], *, force_serial: bool = False):
-        """One env step for all E envs (env:160-269).  Returns device tensors."""
+    def step(self, action: Dict[str, ArrayLike], *, force_serial: bool = False,
+             floor_cents: Optional[torch.Tensor] = None):
+        """One env step for all E envs (env:160-269).  Returns device tensors.  ``floor_cents``
+        ([E, K] int32 on the device): highest rival bid per unit for shared auctions."""
         bids, budget = self._prepare(action)
         self._last_bids = bids
         a = self._fill_args(bids, budget, force_serial)
+        if floor_cents is not None:
+            assert floor_cents.dtype == torch.int32 and floor_cents.is_contiguous() and floor_cents.device == self.device
+            assert tuple(floor_cents.shape) == (self.num_envs, self.num_keywords)
+            a.floor_cents = floor_cents.data_ptr()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _capi.check(self._lib.adc_step_philox(C.byref(a), C.c_void_p(stream)))
         self._step_count += 1

@@ -152,6 +152,15 @@ typedef struct adc_step_args {
     const void *bids;       /* [E,K] dollars, canonicalised to cents inside (env:215) */
     int32_t bids_dtype;     /* ADC_F32 / ADC_F64 */
     const void *budget_in;  /* optional [E] dollars, same dtype as bids: rounded to cents and stored */
+    /* Shared auctions (several bidders in ONE auction; free-running implicit keywords only).
+     * env_group = A > 1: envs [g*A, (g+1)*A) are the A bidders of world g and share every draw
+     * (Philox env id = env_base + e / A: same volumes, same competitor bids, one click/conversion
+     * word per auction, consumed by the single winner).  floor_cents[e,k] = the highest rival bid in
+     * cents: the clearing price of an auction is max(sampled competitor, floor), i.e.
+     * nth_price_auction(n=2, num_winners=1) on rivals + competitor (synthetic_kw_helpers.py:116-180).
+     * 0 / NULL: independent envs. */
+    int32_t env_group;
+    const int32_t *floor_cents;
     adc_step_out out;
     adc_scratch scratch;
     adc_detail detail;

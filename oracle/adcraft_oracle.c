@@ -293,6 +293,7 @@ typedef struct {
     const orc_tape *tape;
     uint64_t seed; uint32_t env, step, agent;
     orc_record *rec;
+    const int32_t *floor_cents; /* shared auctions: highest rival bid per keyword, or NULL */
 } draw_src;
 
 typedef struct { /* per-keyword running cursors for one env step */
@@ -338,8 +339,11 @@ static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, dou
                 w1 = w[(j & 1) ? 3 : 1]; w2 = w1; /* click and conversion share the word cc */
                 if (rec && j < rec->cap_per_kw) { rec->comp_cents[(int64_t)k * rec->cap_per_kw + j] = c; rec->n_comp[k] = (int32_t)(j + 1); }
             }
-            /* nth_price_auction(n=2, num_winners=1) with one competitor: win iff bid > c
-             * (strict; searchsorted-left index must exceed n), cost = c. */
+            /* shared auction: the rivals' bids join the sampled competitor in other_bids; with
+             * n=2, num_winners=1 only their maximum matters (helpers:156-177) */
+            if (src->floor_cents && src->floor_cents[k] > c) c = src->floor_cents[k];
+            /* nth_price_auction(n=2, num_winners=1): win iff bid > max(other bids)
+             * (strict; searchsorted-left index must exceed n), cost = that maximum. */
             if (bid_cents > c) {
                 slot_cost[slots] = (double)c / 100.0;
                 clicked[slots] = 0;
@@ -575,6 +579,16 @@ int orc_step_philox(const orc_keywords *kw, const int32_t *bid_cents, double bud
 {
     draw_src s; memset(&s, 0, sizeof s);
     s.mode = 1; s.seed = seed; s.env = env_id; s.step = step; s.agent = agent; s.rec = rec;
+    return step_common(kw, bid_cents, budget, budget_alias, &s, out);
+}
+
+int orc_step_philox_shared(const orc_keywords *kw, const int32_t *bid_cents, const int32_t *floor_cents,
+                           double budget, int budget_alias, uint64_t seed, uint32_t world_id, uint32_t step,
+                           orc_result *out)
+{   /* one bidder of a shared-auction world: every draw is keyed by the world, the clearing price
+     * is max(sampled competitor, highest rival bid) */
+    draw_src s; memset(&s, 0, sizeof s);
+    s.mode = 1; s.seed = seed; s.env = world_id; s.step = step; s.agent = 0u; s.floor_cents = floor_cents;
     return step_common(kw, bid_cents, budget, budget_alias, &s, out);
 }
 

@@ -96,6 +96,14 @@ int orc_step_philox(const orc_keywords *kw, const int32_t *bid_cents, double bud
                     int budget_alias, uint64_t seed, uint32_t env_id, uint32_t step,
                     uint32_t agent, orc_result *out, orc_record *rec);
 
+/* One bidder of a shared-auction world: draws keyed by world_id, clearing price
+ * = max(sampled competitor, floor_cents[k]) where floor_cents[k] is the highest rival bid, i.e.
+ * nth_price_auction(n=2, num_winners=1) on [rival bids..., competitor]
+ * (synthetic_kw_helpers.py:116-180). */
+int orc_step_philox_shared(const orc_keywords *kw, const int32_t *bid_cents, const int32_t *floor_cents,
+                           double budget, int budget_alias, uint64_t seed, uint32_t world_id, uint32_t step,
+                           orc_result *out);
+
 /* Drift (gymnasium_kw_env.py:114-158).  coeff = [3][K] (vol, ctr, cvr); only the first
  * num_updates keywords are considered (zip truncation), masked ones updated. */
 void orc_drift_apply(int32_t K, const uint8_t *mask, int32_t num_updates, const double *coeff,

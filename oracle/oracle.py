@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
     L.orc_bid_to_cents.argtypes = [C.c_double]
     L.orc_step_replay.restype = C.c_int
     L.orc_step_philox.restype = C.c_int
+    L.orc_step_philox_shared.restype = C.c_int
     L.orc_batch_step.restype = C.c_int
     _lib = L
     return L
@@ -306,6 +307,21 @@ def step_philox(kw: KeywordSet, bid_cents, budget: float, seed: int, env_id: int
             cost=[bufs["cost"][k, :bufs["n_cost"][k]] for k in range(K)] if kw.kind == EXPLICIT else None)
         out["tape"] = tape
     return out
+
+
+def step_philox_shared(kw: KeywordSet, bid_cents, floor_cents, budget: float, seed: int, world_id: int,
+                       step: int, budget_alias: bool = False):
+    """One bidder of a shared-auction world: clearing price = max(competitor, highest rival bid)."""
+    bc = np.ascontiguousarray(bid_cents, np.int32)
+    fc = np.ascontiguousarray(floor_cents, np.int32)
+    ks = kw.c_struct()
+    r, arrs = _alloc_result(kw.K, True)
+    rc = lib().orc_step_philox_shared(C.byref(ks), C.c_void_p(bc.ctypes.data), C.c_void_p(fc.ctypes.data),
+                                      C.c_double(budget), C.c_int(int(budget_alias)), C.c_uint64(seed),
+                                      C.c_uint32(world_id), C.c_uint32(step), C.byref(r))
+    if rc:
+        raise RuntimeError(f"orc_step_philox_shared failed rc={rc}")
+    return _finish(r, arrs)
 
 
 def drift_philox(K: int, seed: int, env_id: int, step: int, mag=(0.03, 0.03, 0.03)) -> np.ndarray:

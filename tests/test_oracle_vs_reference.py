@@ -106,3 +106,38 @@ def test_keyword_factories_match_reference_rng_order(orc):
         for n in kwm.PARAM_NAMES:
             assert np.array_equal(getattr(a, n), getattr(t, n)), n
         assert env.np_random.random() == g.random()
+
+
+def test_shared_auction_is_nth_price_auction_on_rivals_plus_competitor(orc):
+    """with A bidders in one auction, bidder a's ``other_bids`` are the A-1 rival
+    bids plus the keyword's sampled competitor, cleared by the reference's own
+    ``nth_price_auction(n=2, num_winners=1)`` (synthetic_kw_helpers.py:116-180).  The oracle's
+    shared step (clearing price = max(competitor, highest rival)) must give the same impressions
+    and costs for every bidder, ties included."""
+    ref = rh.load_reference()
+    npa = ref["helpers"].nth_price_auction
+    rng = np.random.default_rng(8)
+    K, A = 6, 8
+    loc = rng.uniform(0.3, 1.0, K)
+    kw = orc.KeywordSet(orc.IMPLICIT, np.full(K, 60.0), np.full(K, 9.0), loc, 0.2 * loc, np.ones(K),  # ctr 1:
+                        rng.uniform(0.1, 0.9, K), rng.uniform(0.3, 1.5, K), rng.uniform(0.01, 0.3, K))  # all clicks
+    for step in range(3):
+        bids = rng.integers(20, 140, (A, K)).astype(np.int32)
+        bids[1, 0] = bids[0, 0] = bids[:, 0].max() + 1          # a tie at the top: nobody wins keyword 0
+        bids[3, 1] = 1                                           # a bidder far below the field
+        solo = orc.step_philox(kw, bids[0], 1e9, seed=5, env_id=2, step=step, record_cap=512)
+        comp = [np.asarray(solo["tape"].comp_cents[solo["tape"].comp_off[k]:solo["tape"].comp_off[k + 1]])
+                for k in range(K)]
+        winners = np.zeros(K, int)
+        for a in range(A):
+            rivals = np.delete(bids, a, axis=0)
+            floor = rivals.max(axis=0).astype(np.int32)
+            out = orc.step_philox_shared(kw, bids[a], floor, 1e9, seed=5, world_id=2, step=step)
+            for k in range(K):
+                V = len(comp[k])
+                other = np.hstack([np.tile(rivals[:, k] / 100.0, (V, 1)), comp[k][:, None] / 100.0])
+                I, _, costs = npa(bids[a, k] / 100.0, other, n=2, num_winners=1)
+                assert out["impressions"][k] == I, (step, a, k)
+                assert abs(out["cost"][k] - float(np.sum(costs))) < 1e-9, (step, a, k)
+                winners[k] += I > 0
+        assert winners[0] == 0 and (winners <= 1).all()
