@@ -292,6 +292,34 @@ def run_gpu(args):
     if args.replay_only:
         print(json.dumps({"replay": run_replay_leg(env, table, dev, torch, steps=max(args.steps, 3))}))
         return 0
+    if args.agents > 1:  # experiment: BASELINE config 4, A bidders inside every auction
+        from adcraft_b200.multi_agent import SharedAuctionSimulation
+        del env
+        A, W = args.agents, E_ENVS
+        sim = SharedAuctionSimulation(A, W, num_keywords=K_KW, keywords=table, budget=BUDGET, max_days=MAX_DAYS,
+                                      device=dev, seed=SEED, env_base=rank * W, obs_dtype=torch.float32)
+        sim.reset()
+        sbids = (0.50 + 0.05 * torch.arange(A, device=dev, dtype=torch.float32)).view(1, A, 1).expand(W, A, K_KW).contiguous()
+        for _ in range(3):
+            sobs = sim.step(sbids)[0]
+        torch.cuda.synchronize(dev)
+        n = max(args.steps, 3)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        for i in range(n):
+            starts[i].record()
+            sobs = sim.step(sbids)[0]
+            stops[i].record()
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops)) / n
+        winners = (sobs["impressions"] > 0).sum(dim=1)
+        print(json.dumps({"shared_auction": {
+            "worlds": W, "agents": A, "keywords": K_KW, "ms_per_step": ms,
+            "bidder_units_per_s": W * A * K_KW / (ms * 1e-3), "auction_units_per_s": W * K_KW / (ms * 1e-3),
+            "max_winners_per_auction_unit": int(winners.max()),
+            "note": "timed step includes the rival-floor computation (torch topk over the A bids) and one launch "
+                    "over worlds*A bidder rows; bids = 0.50 + 0.05*agent"}}))
+        return 0
 
     # ---- device-timed steps, inputs resident in HBM --------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -398,7 +426,8 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "i32+f32", "data": "synthetic",
-        "config": config_dict(n_gpus, {"n_lanes": args.n_lanes or 8}),
+        "config": config_dict(n_gpus, {"n_lanes": env.n_lanes,
+                                       "n_lanes_meaning": "0/-32: warp-batched kernel, 32 lanes per unit; -16/-8: sub-warp groups"}),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "how": "step_host: kernels read pinned host bids and write pinned host observations directly "
@@ -433,6 +462,8 @@ def main():
     ap.add_argument("--cvr", type=float, default=0.8, help="experiment only: conversion rate (C3: 0.1)")
     ap.add_argument("--drift", action="store_true", help="experiment only: non-stationary (mask all True)")
     ap.add_argument("--envs", type=int, default=4096, help="experiment only: envs per GPU (default = C2's 4096)")
+    ap.add_argument("--agents", type=int, default=1,
+                    help="experiment only: bidders per shared auction (BASELINE config 4: --agents 8 --envs 65536)")
     args = ap.parse_args()
     E_ENVS = args.envs
     BUDGET = args.budget
