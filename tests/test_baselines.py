@@ -65,3 +65,53 @@ def test_matches_reference_class():
             assert abs(float(mine.ave_sctr[0, i]) - float(c["ave_sctr"])) < 1e-5
             assert abs(float(mine.ave_rpc[0, i]) - float(c["ave_rpc"])) < 1e-5
         bids = act_ref["keyword_bids"]
+
+
+def test_interpolation_strategy_shapes_and_prior():
+    from adcraft_b200.baselines import VectorNaiveInterpolationStrategy
+    E, K = 2, 4
+    pol = VectorNaiveInterpolationStrategy(E, K, seed=3)
+    a = pol.sample_action()
+    assert a["keyword_bids"].shape == (E, K) and a["budget"].shape == (E,)
+    # nothing observed: mass only below max_observed(0.03) + bid_step -> bids in {0.01 .. 0.05}
+    assert float(a["keyword_bids"].min()) >= 0.01 - 1e-12 and float(a["keyword_bids"].max()) <= 0.05 + 1e-12
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
+def test_interpolation_strategy_matches_reference_class():
+    """Step-by-step against adcraft.baselines.interpolated_expectations.NaiveInterpolationStrategy:
+    same observations, same previous bids, the uniforms its Generator.choice would consume."""
+    import importlib
+    rh.load_reference()
+    ie = importlib.import_module("adcraft.baselines.interpolated_expectations")
+    from adcraft_b200.baselines import VectorNaiveInterpolationStrategy
+    rng = np.random.default_rng(1)
+    K = 9
+    ref = ie.NaiveInterpolationStrategy(K, seed=77)
+    mine = VectorNaiveInterpolationStrategy(1, K)
+    bids = np.full(K, 0.01)
+    for step in range(60):
+        obs = _fake_obs(rng, K)
+        if step % 7 == 3:
+            obs["buyside_clicks"][:] = 0; obs["sellside_conversions"][:] = 0; obs["revenue"][:] = 0; obs["cost"][:] = 0
+        ref.update_all_caches({"keyword_bids": bids}, {k: v.copy() for k, v in obs.items()})
+        mine.update_all_caches({"keyword_bids": torch.tensor(bids)[None]},
+                               {k: torch.tensor(v)[None] for k, v in obs.items()})
+        margins, costs = mine.expected_margins_and_costs()
+        has = []
+        for i in range(K):
+            m_ref, c_ref = ref.get_expected_margin_from_cache(i)
+            np.testing.assert_allclose(margins[0, i].numpy(), m_ref, rtol=1e-9, atol=1e-12, err_msg=f"margin {step} {i}")
+            np.testing.assert_allclose(costs[0, i].numpy(), c_ref, rtol=1e-9, atol=1e-12, err_msg=f"cost {step} {i}")
+            has.append(ref.get_profit_acquisition_function(np.array(m_ref), index=i) is not None)
+        state = ref.rng.bit_generator.state
+        act_ref = ref.sample_action()
+        ref.rng.bit_generator.state = state
+        u = np.zeros(K)
+        u[np.array(has)] = ref.rng.random(int(np.sum(has)))
+        act = mine.sample_action(uniforms=torch.tensor(u)[None])
+        np.testing.assert_allclose(act["keyword_bids"][0].numpy(), act_ref["keyword_bids"], rtol=0, atol=1e-12)
+        assert abs(float(act["budget"][0]) - act_ref["budget"]) < 1e-6 * max(1.0, abs(act_ref["budget"]))
+        bids = np.asarray(act_ref["keyword_bids"], float)
+    assert len({round(float(b), 2) for b in bids}) > 1   # the agent moved off the prior
