@@ -1248,7 +1248,7 @@ __device__ __forceinline__ bool pk_walk_fast(const unsigned char *rec, int n_com
     return true;
 }
 
-template <int kPkWarps, int kRing, int kDepth, int kMinBlocks, bool kCopyOnly = false>
+template <int kPkWarps, int kRing, int kDepth, int kMinBlocks>
 __global__ void __launch_bounds__(kPkWarps * 32, kMinBlocks)
 adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_constant__ adc_tape t)
 {
@@ -1365,9 +1365,7 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
                 chead = off + (unsigned)h.bytes;
                 --in_flight;
                 const unsigned char *rec = ring + off;
-                if (kCopyOnly) {  // measurement only: how fast do the bulk copies alone stream the tape?
-                    r.I = *reinterpret_cast<const int *>(rec); r.B = r.S = 0; r.cost = r.rev = 0; r.overrun = false;
-                } else if (!pk_walk_fast(rec, h.n_comp, h.n_click, h.n_conv, h.n_rev, h.bid_cents, h.ctr, h.cvr, lane, lt, r))
+                if (!pk_walk_fast(rec, h.n_comp, h.n_click, h.n_conv, h.n_rev, h.bid_cents, h.ctr, h.cvr, lane, lt, r))
                     r = pk_walk_generic(rec, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
             } else {
                 r = pk_walk_generic(h.src, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
@@ -1813,10 +1811,10 @@ static cudaError_t launch_lanes(const adc_step_args &a, cudaStream_t s, int64_t 
     return cudaGetLastError();
 }
 
-template <int W, int RING, int DEPTH, int MINB, bool COPYONLY = false>
+template <int W, int RING, int DEPTH, int MINB>
 static cudaError_t launch_packed(const adc_step_args &a, const adc_tape &tp, cudaStream_t s, int64_t *launches)
 {
-    auto kern = adc_replay_packed_kernel<W, RING, DEPTH, MINB, COPYONLY>;
+    auto kern = adc_replay_packed_kernel<W, RING, DEPTH, MINB>;
     constexpr int block = W * 32;
     constexpr size_t dyn = (size_t)W * RING;
     static bool configured = false;
@@ -1911,8 +1909,6 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
             case 1: err = launch_packed<8, 8192, 4, 3>(a, tp, s, launches); break;
             case 2: err = launch_packed<8, 5632, 3, 4>(a, tp, s, launches); break;
             case 3: err = launch_packed<8, 7168, 4, 3>(a, tp, s, launches); break;
-            case 9: err = launch_packed<8, 6144, 4, 3, true>(a, tp, s, launches); break;   // copies only (wrong sums)
-            case 10: err = launch_packed<8, 8192, 4, 3, true>(a, tp, s, launches); break;  // copies only, 16 warps
             default: err = launch_packed<8, 6144, 4, 3>(a, tp, s, launches); break;
         }
     } else {
