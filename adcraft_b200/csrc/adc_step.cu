@@ -626,8 +626,11 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         uint32_t genv = 0;
         UnitPar p;
         p.bid_cents = 0; p.loc = 0.f; p.scale = 0.f; p.thr_click = 0; p.thr_conv = 0;
-        p.rev_mean = 0.f; p.rev_sd = 0.f;
-        if (valid) {
+        p.rev_mean = 0.f; p.rev_sd = 0.f; p.thr_cc = 0; p.conv_all = false; p.floor_cents = (int)0x80000000;
+        bool outbid = false;  // shared auctions: a rival bids at least as much, no auction can be won
+        if (kFloor && valid)
+            outbid = bid_to_cents(load_f(a.bids, a.bids_dtype, u)) <= a.floor_cents[u];
+        if (valid && !outbid) {  // (7 of 8 bidder rows of an 8-bidder world stop here)
             e = (int)(u / K);
             k = (int)(u - (int64_t)e * K);
             genv = philox_env(a, e);
@@ -637,7 +640,9 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             const long long v = volume_draw(w.x, a.kw.vol_mean[pi], a.kw.vol_std[pi]);
             over_cap = v > (G == 32 ? kMaxFlatVolume : 65535) || p.bid_cents > kMaxFlatBidCents;
             V = over_cap ? 0 : (int)v;
-            if (kFloor && p.bid_cents <= p.floor_cents) V = 0;  // a rival bids at least as much: no auction can be won
+        } else if (valid) {
+            e = (int)(u / K);
+            k = (int)(u - (int64_t)e * K);
         }
         if (kFloor) s_floor[warp][lane] = max(p.floor_cents, 0);
         {

@@ -75,13 +75,13 @@ class SharedAuctionSimulation:
         """[worlds, A, K] dollars -> int32 cents of the highest RIVAL bid per bidder (bids are
         canonicalised like the env does, ``round(max(bid, 0.01), 2)``, gymnasium_kw_env.py:215)."""
         cents = torch.round(torch.clamp(bids.to(torch.float64), min=0.01) * 100.0).to(torch.int32)
-        top2 = torch.topk(cents, k=min(2, cents.shape[1]), dim=1).values
-        first = top2[:, 0:1]
-        second = top2[:, 1:2] if cents.shape[1] > 1 else torch.full_like(first, -2**31)
+        first = cents.amax(dim=1, keepdim=True)
         is_top = cents == first
+        lowest = torch.iinfo(torch.int32).min
+        second = torch.where(is_top, torch.full_like(cents, lowest), cents).amax(dim=1, keepdim=True)
         # the unique top bidder faces the runner-up; everybody else (and tied leaders) faces the top bid
         unique_top = is_top & (is_top.sum(dim=1, keepdim=True) == 1)
-        return torch.where(unique_top, second.expand_as(cents), first.expand_as(cents)).contiguous()
+        return torch.where(unique_top, second, first).contiguous()
 
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
         obs, info = self.vec.reset(seed=seed, options=options)
