@@ -292,6 +292,34 @@ def run_gpu(args):
     if args.replay_only:
         print(json.dumps({"replay": run_replay_leg(env, table, dev, torch, steps=max(args.steps, 3))}))
         return 0
+    if args.explicit:  # experiment: the reference's DEFAULT env (ExplicitKeyword, config 1) vectorised
+        from adcraft_b200 import keywords as kwm
+        del env
+        Kx = args.keywords if args.keywords != 100 else 10
+        xtable = kwm.sample_random_keywords(Kx, np.random.default_rng(0))
+        xenv = VectorBiddingSimulation(E_ENVS, num_keywords=Kx, keywords=xtable, budget=1000.0, max_days=MAX_DAYS,
+                                       device=dev, seed=SEED, env_base=rank * E_ENVS, obs_dtype=torch.float32)
+        xenv.reset()
+        xb = torch.from_numpy(np.round(np.random.default_rng(1).uniform(0.01, 3.0, (E_ENVS, Kx)), 2).astype(np.float32)).to(dev)
+        xact = {"keyword_bids": xb}
+        for _ in range(3):
+            xo = xenv.step(xact)[0]
+        torch.cuda.synchronize(dev)
+        n = max(args.steps, 3)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        for i in range(n):
+            starts[i].record()
+            xo = xenv.step(xact)[0]
+            stops[i].record()
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops)) / n
+        print(json.dumps({"explicit_default_env": {
+            "envs": E_ENVS, "keywords": Kx, "ms_per_step": ms, "units_per_s": E_ENVS * Kx / (ms * 1e-3),
+            "mean_volume": float(np.mean(xtable.vol_mean)), "mean_impressions": float(xo["impressions"].float().mean()),
+            "note": "ExplicitKeyword set from sample_random_keywords(default_rng(0)), bids U[0.01,3.00], budget 1000 "
+                    "(binds for many envs: those take the exact serial kernel)"}}))
+        return 0
     if args.agents > 1:  # experiment: BASELINE config 4, A bidders inside every auction
         from adcraft_b200.multi_agent import SharedAuctionSimulation
         del env
@@ -470,6 +498,8 @@ def main():
     ap.add_argument("--cvr", type=float, default=0.8, help="experiment only: conversion rate (C3: 0.1)")
     ap.add_argument("--drift", action="store_true", help="experiment only: non-stationary (mask all True)")
     ap.add_argument("--envs", type=int, default=4096, help="experiment only: envs per GPU (default = C2's 4096)")
+    ap.add_argument("--explicit", action="store_true",
+                    help="experiment only: the reference's default ExplicitKeyword env (config 1) vectorised, K=10")
     ap.add_argument("--agents", type=int, default=1,
                     help="experiment only: bidders per shared auction (BASELINE config 4: --agents 8 --envs 65536)")
     args = ap.parse_args()
