@@ -1909,15 +1909,14 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         err = cudaGetLastError();
     } else if (tp.packed != nullptr) {
         // ring geometry: 8 warps x 6 KB per CTA, three CTAs (24 warps) per SM; measured on C2: 6 KB
-        // 0.191 ms, 7 KB 0.203 ms, 5 KB with 64 registers and four CTAs 0.205 ms, 8 KB (two CTAs per
-        // SM) 0.26 ms.  ADC_PK_VARIANT re-selects them (measurement knob, read once).
+        // 0.191 ms (5.75 / 6.25 / 6.5 KB: 0.194 / 0.192 / 0.190), 7 KB 0.203 ms, 5 KB with 64 registers
+        // and four CTAs 0.205 ms, 8 KB (two CTAs per SM) 0.26 ms.  ADC_PK_VARIANT re-selects three of
+        // them (measurement knob, read once).
         static const int variant = [] { const char *v = getenv("ADC_PK_VARIANT"); return v ? atoi(v) : 0; }();
         switch (variant) {
             case 1: err = launch_packed<8, 8192, 4, 3>(a, tp, s, launches); break;
             case 2: err = launch_packed<8, 5632, 3, 4>(a, tp, s, launches); break;
             case 3: err = launch_packed<8, 7168, 4, 3>(a, tp, s, launches); break;
-            case 4: err = launch_packed<8, 5120, 4, 4>(a, tp, s, launches); break;
-            case 5: err = launch_packed<4, 6144, 4, 6>(a, tp, s, launches); break;
             default: err = launch_packed<8, 6144, 4, 3>(a, tp, s, launches); break;
         }
     } else {
