@@ -1327,27 +1327,29 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
         const unsigned fast_m = __ballot_sync(FULL, fast);
 
         // ---------------- the units, one after the other; copies run ahead as far as the ring allows ----------------
+        // issue cursor (warp-uniform): the next fast unit to copy and its {src, bytes, bid} words
         unsigned iss_m = fast_m;
+        uint4 nx = make_uint4(0, 0, 0, 0);
+        if (iss_m) nx = *reinterpret_cast<const uint4 *>(&units[__ffs(iss_m) - 1]);
         auto try_issue = [&]() -> bool {
-            const int bi = __ffs(iss_m) - 1;
-            const uint4 hw = *reinterpret_cast<const uint4 *>(&units[bi]);  // src (64 bit), bytes, bid
-            const unsigned bytes = hw.z;
+            const unsigned bytes = nx.z;
             if (in_flight == 0) { head = 0; chead = 0; used = 0; }  // pointers coincide: restart at the ring base
             // `used` = bytes between chead and head in ring order, skipped ring ends included
             const bool straight = head + bytes <= (unsigned)kRing;
-            const unsigned off = straight ? head : 0u;
             const unsigned need = straight ? bytes : bytes + ((unsigned)kRing - head);
             if (in_flight >= kDepth || used + need > (unsigned)kRing) return false;
-            used += need;
-            iss_m &= iss_m - 1;
+            const unsigned off = straight ? head : 0u;
             if (lane == 0) {
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(
-                    ((unsigned long long)hw.y << 32) | hw.x);
+                    ((unsigned long long)nx.y << 32) | nx.x);
                 bulk_load(ring_s + off, src, bytes, bar_s + 8u * slot_i);
             }
+            used += need;
             head = off + bytes;
             slot_i = slot_i + 1 == kDepth ? 0 : slot_i + 1;
             ++in_flight;
+            iss_m &= iss_m - 1;
+            if (iss_m) nx = *reinterpret_cast<const uint4 *>(&units[__ffs(iss_m) - 1]);
             return true;
         };
 #pragma unroll 1
