@@ -114,6 +114,22 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_cpus(gpu_index: int):
+    """One process per GPU: run on (and first-touch pinned host memory from) the CPUs NVML reports
+    as local to that GPU, so the e2e leg's host buffers do not sit behind the inter-socket link.
+    Best effort: a cpuset that excludes those CPUs leaves the affinity unchanged."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        before = sorted(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        return {"cpus_before": len(before), "cpus_after": len(after), "first_cpu": after[0] if after else None}
+    except Exception as exc:  # noqa: BLE001
+        return {"error": type(exc).__name__}
+
+
 # --------------------------------------------------------------------------------------------
 # clocks
 # --------------------------------------------------------------------------------------------
@@ -259,6 +275,7 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_cpus(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -472,6 +489,7 @@ def run_gpu(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "replay": replay,
+        "cpu_binding": numa,
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "auctions_per_sec": value * MEAN_VOLUME,
     }
