@@ -8,7 +8,6 @@ coefficients.  Streams are CSR over the E*K units.
 """
 from __future__ import annotations
 
-import ctypes as C
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
