@@ -1631,13 +1631,30 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
 // lanes commit in parallel.  Lanes after the one that exhausts the budget contribute nothing.
 // ------------------------------------------------------------------------------------------
 constexpr int kSerWarps = 4;
-constexpr int kSerCap = 16;  // buffered clicked slots per lane and sub-step; more -> direct re-walk
+constexpr int kSerCap = 16;     // buffered clicked slots per lane and sub-step; more -> direct re-walk
+constexpr int kSerCacheK = 128; // keywords per env whose per-unit constants are cached in shared memory
 
+struct SerUnit {  // what a (sub-step, keyword) lane needs again in each of the 24 sub-steps
+    int bid_cents, floor_cents;
+    float loc, scale, rev_mean, rev_sd;
+    uint32_t thr_click, thr_cc;  // thr_cc = 0xFFFFFFFF with conv_all in the sign of `volume`... see flags
+    int volume;                  // clamped to INT_MAX (larger volumes take the uncached path)
+    int flags;                   // bit 0: conv_all
+};
+
+// One warp per queued env.  The reference's walk is sequential in (sub-step, keyword, click) because
+// every click draws on one shared budget (bsim:214-233), but only the affordability test is: per
+// sub-step and chunk of 32 keywords the lanes evaluate their auctions in parallel and buffer the
+// clicked slots (cost already as the f64 dollar value the reference compares), then the whole warp
+// runs ONE uniform scan over the buffered clicks in keyword order -- the reference's f64 sequence
+// `if budget >= cost: budget -= cost` (bsim:97-104), alias rule and `remaining <= 0` exit included
+// -- and finally the lanes commit their accepted prefix in parallel (conversions, revenues).
 __global__ void __launch_bounds__(kSerWarps * 32)
 adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
 {
-    __shared__ int s_cost[kSerWarps][kSerCap][32];
+    __shared__ double s_costd[kSerWarps][kSerCap][32];  // cents / 100 in f64: what the reference compares
     __shared__ uint32_t s_w2[kSerWarps][kSerCap][32];
+    __shared__ SerUnit s_unit[kSerWarps][kSerCacheK];
     const int K = a.kw.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * kSerWarps + warp;
@@ -1646,6 +1663,19 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
     const unsigned FULL = 0xFFFFFFFFu;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const adc_tape *no_tape = nullptr;
+
+    auto make_unit = [&](const PhiloxSrc &src, int e, int k) {
+        const UnitPar p = load_unit_par(a, e, k);
+        uint4 uw;
+        const long long V = unit_volume(a, src, no_tape, e, k, &uw);
+        SerUnit su;
+        su.bid_cents = p.bid_cents; su.floor_cents = p.floor_cents;
+        su.loc = p.loc; su.scale = p.scale; su.rev_mean = p.rev_mean; su.rev_sd = p.rev_sd;
+        su.thr_click = p.thr_click; su.thr_cc = p.thr_cc;
+        su.volume = V > 0x7FFFFFFFLL ? 0x7FFFFFFF : (int)V;
+        su.flags = p.conv_all ? 1 : 0;
+        return su;
+    };
 
     for (int idx = gwarp; idx < count; idx += n_warps) {
         const int e = a.scratch.serial_list[idx];
@@ -1657,6 +1687,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
             a.out.conversions[u] = 0;
             a.out.cost_cents[u] = 0;
             a.out.revenue_cents[u] = 0;
+            if (k < kSerCacheK) s_unit[warp][k] = make_unit(src, e, k);
         }
         __syncwarp();
         const double budget = step_budget(a, e);
@@ -1668,35 +1699,43 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                 const bool act = k < K;
                 const int64_t u = (int64_t)e * K + (act ? k : 0);
                 // ---- phase 1 (parallel): the lane's auctions, budget-free; buffer the clicked slots
-                UnitPar p;
+                SerUnit su;
+                su.bid_cents = 0; su.floor_cents = 0; su.loc = 0.f; su.scale = 0.f; su.rev_mean = 0.f; su.rev_sd = 0.f;
+                su.thr_click = 0; su.thr_cc = 0; su.volume = 0; su.flags = 0;
                 long long n = 0, j0 = 0;
                 int I = 0, nclk = 0;
                 if (act) {
-                    p = load_unit_par(a, e, k);
-                    uint4 uw;
-                    const long long V = unit_volume(a, src, no_tape, e, k, &uw);
+                    su = k < kSerCacheK ? s_unit[warp][k] : make_unit(src, e, k);
+                    const long long V = su.volume;
                     const long long q = V / ADC_SUBSTEPS;
                     const long long n0 = V - (ADC_SUBSTEPS - 1) * q;
                     n = t == 0 ? n0 : q;
                     j0 = t == 0 ? 0 : n0 + (long long)(t - 1) * q;
-                    for (long long i = 0; i < n; ++i) {
-                        const long long j = j0 + i;
-                        const uint4 w = src.draw(ST_AUCTION, (uint32_t)k, (uint32_t)(j >> 1));
-                        const uint32_t cc = (j & 1) ? w.w : w.y;
-                        const int c = max(laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale), p.floor_cents);
-                        if (p.bid_cents > c) {
-                            ++I;
-                            if (cc <= p.thr_click) {
-                                if (nclk < kSerCap) {
-                                    s_cost[warp][nclk][lane] = c;
-                                    s_w2[warp][nclk][lane] = cc;
+                    // one Philox call serves auctions 2c and 2c+1: walk the calls that overlap [j0, j0+n)
+                    const long long j_end = j0 + n;
+                    for (long long cidx = j0 >> 1; 2 * cidx < j_end; ++cidx) {
+                        const uint4 w = src.draw(ST_AUCTION, (uint32_t)k, (uint32_t)cidx);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const long long j = 2 * cidx + h;
+                            if (j < j0 || j >= j_end) continue;
+                            const uint32_t cc = h ? w.w : w.y;
+                            const int c = max(laplace_cents(h ? w.z : w.x, su.loc, su.scale), su.floor_cents);
+                            if (su.bid_cents > c) {
+                                ++I;
+                                if (cc <= su.thr_click) {
+                                    if (nclk < kSerCap) {
+                                        s_costd[warp][nclk][lane] = cents_to_dollars(c);
+                                        s_w2[warp][nclk][lane] = cc;
+                                    }
+                                    ++nclk;
                                 }
-                                ++nclk;
                             }
                         }
                     }
                 }
-                // ---- phase 2 (serial over the lanes that have clicks): the reference's budget walk
+                __syncwarp();
+                // ---- phase 2 (one uniform scan over the lanes that have clicks): the reference's budget walk
                 int B = 0, S = 0;
                 long long cost_c = 0, rev_c = 0;
                 bool rev_done = false;
@@ -1706,47 +1745,60 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                 while (todo) {
                     const int l = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    double next = remaining;
-                    if (lane == l) {
+                    const int n_l = __shfl_sync(FULL, nclk, l);
+                    double next;
+                    if (n_l <= kSerCap) {  // every lane runs lane l's walk on the buffered f64 costs
                         double b = remaining, lane_sum = 0.0;
-                        if (nclk <= kSerCap) {
-                            for (int i = 0; i < nclk; ++i) {
-                                const int c = s_cost[warp][i][lane];
-                                const double cost = cents_to_dollars(c);
-                                if (!(b >= cost)) break;  // bsim:99-104
-                                ++B;
-                                cost_c += c;
-                                lane_sum = __dadd_rn(lane_sum, cost);
-                                b = __dsub_rn(b, cost);
-                                S += p.conv_all || s_w2[warp][i][lane] < p.thr_cc;
-                            }
-                        } else {  // more clicks than the buffer holds: walk the lane again, with the budget
+                        int acc = 0;
+                        for (int i = 0; i < n_l; ++i) {
+                            const double cost = s_costd[warp][i][l];
+                            if (!(b >= cost)) break;  // bsim:99-104
+                            ++acc;
+                            lane_sum = __dadd_rn(lane_sum, cost);
+                            b = __dsub_rn(b, cost);
+                        }
+                        if (lane == l) B = acc;
+                        next = __dsub_rn(a.budget_alias ? b : remaining, lane_sum);  // bsim:102 alias, :225
+                    } else {  // more clicks than the buffer holds: lane l walks its sub-step again, with the budget
+                        next = remaining;
+                        if (lane == l) {
+                            UnitPar p;
+                            p.bid_cents = su.bid_cents; p.floor_cents = su.floor_cents; p.loc = su.loc; p.scale = su.scale;
+                            p.rev_mean = su.rev_mean; p.rev_sd = su.rev_sd; p.thr_click = su.thr_click; p.thr_cc = su.thr_cc;
+                            p.conv_all = (su.flags & 1) != 0; p.bid = 0.0; p.ctr = 0.0; p.cvr = 0.0; p.thr_conv = 0; p.thr_impr = 0;
+                            double b = remaining, unused = 0.0;
                             UnitCur cur = {j0, 0, 0, a.out.conversions[u], 0};
-                            double unused = 0.0;
                             const LaneOut o = lane_walk<PhiloxSrc, false, true>(src, no_tape, u, k, t, n, p, cur, b, unused);
                             B = o.B; S = o.S; cost_c = o.cost_cents; rev_c = o.rev_cents;
-                            lane_sum = o.lane_cost_sum;
                             rev_done = true;
+                            next = __dsub_rn(a.budget_alias ? b : remaining, o.lane_cost_sum);
                         }
-                        next = __dsub_rn(a.budget_alias ? b : remaining, lane_sum);  // bsim:102 alias, :225
+                        next = __shfl_sync(FULL, next, l);
                     }
-                    remaining = __shfl_sync(FULL, next, l);
+                    remaining = next;
                     if (remaining <= 0) {  // bsim:230-233
                         stop = true;
                         cutoff = l;
                         break;
                     }
                 }
-                // ---- phase 3 (parallel): revenues of the lane's conversions, commit
+                // ---- phase 3 (parallel): the accepted prefix of the lane's clicks, revenues, commit
                 if (act && lane <= cutoff) {
-                    if (!rev_done && S > 0) {
-                        const int r0 = a.out.conversions[u];
-                        uint4 rw = make_uint4(0, 0, 0, 0);
-                        for (int i = 0; i < S; ++i) {
-                            const int r = r0 + i;
-                            if (i == 0 || (r & 3) == 0) rw = src.draw(ST_REVENUE, (uint32_t)k, (uint32_t)(r >> 2));
-                            const uint32_t w = (r & 3) == 0 ? rw.x : (r & 3) == 1 ? rw.y : (r & 3) == 2 ? rw.z : rw.w;
-                            rev_c += revenue_cents(w, p.rev_mean, p.rev_sd);
+                    if (!rev_done) {
+                        const bool conv_all = (su.flags & 1) != 0;
+                        for (int i = 0; i < B; ++i) {
+                            cost_c += __double2ll_rn(__dmul_rn(s_costd[warp][i][lane], 100.0));  // exact: cents < 2^31
+                            S += conv_all || s_w2[warp][i][lane] < su.thr_cc;
+                        }
+                        if (S > 0) {
+                            const int r0 = a.out.conversions[u];
+                            uint4 rw = make_uint4(0, 0, 0, 0);
+                            for (int i = 0; i < S; ++i) {
+                                const int r = r0 + i;
+                                if (i == 0 || (r & 3) == 0) rw = src.draw(ST_REVENUE, (uint32_t)k, (uint32_t)(r >> 2));
+                                const uint32_t w = (r & 3) == 0 ? rw.x : (r & 3) == 1 ? rw.y : (r & 3) == 2 ? rw.z : rw.w;
+                                rev_c += revenue_cents(w, su.rev_mean, su.rev_sd);
+                            }
                         }
                     }
                     a.out.impressions[u] += I;
