@@ -145,6 +145,7 @@ class VectorBiddingSimulation:
         self._budget_dev = {torch.float32: z(E, dtype=torch.float32), torch.float64: z(E, dtype=f64)}
         self._mask_dev: Optional[torch.Tensor] = None
         self._host: Dict[str, torch.Tensor] = {}
+        self._host_ptrs = None
         self._args = _capi.StepArgs()
         self._args_sig = None
         self._obs_cache = None
@@ -420,6 +421,7 @@ class VectorBiddingSimulation:
         if not self._host:
             self._host_block = torch.zeros(self._block_bytes, dtype=torch.uint8).pin_memory()
             self._host = self._views(self._host_block)
+            self._host_ptrs = None
         if not zero_copy or not (isinstance(bids_host, torch.Tensor) and bids_host.is_pinned()
                                  and bids_host.dtype in (torch.float32, torch.float64)
                                  and bids_host.is_contiguous()
@@ -439,12 +441,12 @@ class VectorBiddingSimulation:
         out, h = a.out, self._host
         saved = (out.impressions, out.clicks, out.conversions, out.cost, out.revenue, out.reward,
                  out.obs_cum_profit, out.obs_days, out.terminated, out.truncated)
-        out.impressions, out.clicks = h["impressions"].data_ptr(), h["buyside_clicks"].data_ptr()
-        out.conversions = h["sellside_conversions"].data_ptr()
-        out.cost, out.revenue = h["cost"].data_ptr(), h["revenue"].data_ptr()
-        out.reward, out.obs_cum_profit = h["reward"].data_ptr(), h["cumulative_profit"].data_ptr()
-        out.obs_days = h["days_passed"].data_ptr()
-        out.terminated, out.truncated = h["terminated"].data_ptr(), h["truncated"].data_ptr()
+        if self._host_ptrs is None:  # pointer values are fixed once the pinned block exists
+            self._host_ptrs = tuple(h[k].data_ptr() for k in (
+                "impressions", "buyside_clicks", "sellside_conversions", "cost", "revenue", "reward",
+                "cumulative_profit", "days_passed", "terminated", "truncated"))
+        (out.impressions, out.clicks, out.conversions, out.cost, out.revenue, out.reward,
+         out.obs_cum_profit, out.obs_days, out.terminated, out.truncated) = self._host_ptrs
         stream = torch.cuda.current_stream(self.device)
         try:
             _capi.check(self._lib.adc_step_philox(C.byref(a), C.c_void_p(stream.cuda_stream)))
