@@ -14,6 +14,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs the reference tree at /root/reference")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _cuda_library_present():
+    """The in-tree CUDA library normally travels with the tree (built by __graft_entry__.build());
+    if it is missing where nvcc exists, build it once so the product can load.  Never a fallback:
+    without the library the GPU tests fail loudly in _capi.load()."""
+    from adcraft_b200 import build as b
+    if not os.path.exists(b.LIB_PATH):
+        try:
+            b.build()
+        except Exception as exc:  # noqa: BLE001
+            print(f"conftest: could not build {b.LIB_PATH}: {exc}", file=sys.stderr)
+    yield
+
+
 @pytest.fixture(scope="session")
 def orc():
     """The C oracle (test infrastructure)."""
