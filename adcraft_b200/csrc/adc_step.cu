@@ -1742,6 +1742,39 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                 unsigned todo = __ballot_sync(FULL, act && nclk > 0);
                 if (!(remaining > 0)) todo |= 1u;  // a lane must run for `remaining <= 0` to be seen
                 int cutoff = 32;
+                // Two shortcuts that leave the reference's f64 sequence intact:
+                // (a) nothing affordable -- every lane's first click costs more than `remaining`, so each
+                //     lane breaks at once (bsim:99-104) and `remaining` does not move: the usual state of
+                //     the sub-steps after the budget ran dry;
+                // (b) everything affordable -- `remaining` exceeds this round's total spend (exact cents,
+                //     doubled under the alias rule) by more than a cent, so no `budget >= cost` test can
+                //     fail; without the alias rule the walk is then per lane `remaining -= lane_sum` with
+                //     lane_sum the lane's own sequential f64 sum (bsim:225 + rust sum_list), which the
+                //     lanes form in parallel.
+                if (remaining > 0) {
+                    const bool lane_has = act && nclk > 0;
+                    const bool none = !lane_has || !(remaining >= s_costd[warp][0][lane]);
+                    if (__all_sync(FULL, none)) {
+                        todo = 0;
+                    } else if (!a.budget_alias && !__any_sync(FULL, nclk > kSerCap || su.bid_cents > kMaxFlatBidCents)) {
+                        unsigned cents = 0;
+                        double lane_sum = 0.0;
+                        for (int i = 0; i < nclk; ++i) {
+                            const double cd = s_costd[warp][i][lane];
+                            lane_sum = __dadd_rn(lane_sum, cd);
+                            cents += (unsigned)__double2int_rn(__dmul_rn(cd, 100.0));
+                        }
+                        const unsigned total = __reduce_add_sync(FULL, cents);  // <= 32 * 16 * 65535 (bids capped above)
+                        if (remaining > __ddiv_rn((double)total, 100.0) + 0.01) {
+                            B = nclk;
+                            while (todo) {
+                                const int l = __ffs(todo) - 1;
+                                todo &= todo - 1;
+                                remaining = __dsub_rn(remaining, __shfl_sync(FULL, lane_sum, l));
+                            }
+                        }
+                    }
+                }
                 while (todo) {
                     const int l = __ffs(todo) - 1;
                     todo &= todo - 1;
