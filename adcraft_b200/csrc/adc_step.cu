@@ -1756,7 +1756,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                     const bool none = !lane_has || !(remaining >= s_costd[warp][0][lane]);
                     if (__all_sync(FULL, none)) {
                         todo = 0;
-                    } else if (!a.budget_alias && !__any_sync(FULL, nclk > kSerCap || su.bid_cents > kMaxFlatBidCents)) {
+                    } else if (!__any_sync(FULL, nclk > kSerCap || su.bid_cents > kMaxFlatBidCents)) {
                         unsigned cents = 0;
                         double lane_sum = 0.0;
                         for (int i = 0; i < nclk; ++i) {
@@ -1765,12 +1765,18 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                             cents += (unsigned)__double2int_rn(__dmul_rn(cd, 100.0));
                         }
                         const unsigned total = __reduce_add_sync(FULL, cents);  // <= 32 * 16 * 65535 (bids capped above)
-                        if (remaining > __ddiv_rn((double)total, 100.0) + 0.01) {
+                        const double spend = __ddiv_rn((double)total, 100.0);
+                        if (remaining > (a.budget_alias ? spend + spend : spend) + 0.01) {
                             B = nclk;
                             while (todo) {
                                 const int l = __ffs(todo) - 1;
                                 todo &= todo - 1;
-                                remaining = __dsub_rn(remaining, __shfl_sync(FULL, lane_sum, l));
+                                double b = remaining;
+                                if (a.budget_alias) {  // the lane's own walk already drew on the shared budget (bsim:102)
+                                    const int n_l = __shfl_sync(FULL, nclk, l);
+                                    for (int i = 0; i < n_l; ++i) b = __dsub_rn(b, s_costd[warp][i][l]);
+                                }
+                                remaining = __dsub_rn(b, __shfl_sync(FULL, lane_sum, l));
                             }
                         }
                     }

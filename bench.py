@@ -287,6 +287,7 @@ def run_gpu(args):
         seed=SEED, env_base=rank * E_ENVS, n_lanes=args.n_lanes, obs_dtype=torch.float32,
         updater_mask=[True] * K_KW if DRIFT else None)
     env.reset()
+    env.budget_alias = bool(args.alias)
     bids = torch.full((E_ENVS, K_KW), BID, dtype=torch.float32, device=dev)
     action = {"keyword_bids": bids}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -516,6 +517,8 @@ def main():
     ap.add_argument("--cvr", type=float, default=0.8, help="experiment only: conversion rate (C3: 0.1)")
     ap.add_argument("--drift", action="store_true", help="experiment only: non-stationary (mask all True)")
     ap.add_argument("--envs", type=int, default=4096, help="experiment only: envs per GPU (default = C2's 4096)")
+    ap.add_argument("--alias", action="store_true",
+                    help="experiment only: ndarray-budget double charge (bsim:102 + :225), as a Box action space yields")
     ap.add_argument("--explicit", action="store_true",
                     help="experiment only: the reference's default ExplicitKeyword env (config 1) vectorised, K=10")
     ap.add_argument("--agents", type=int, default=1,
