@@ -1660,7 +1660,7 @@ struct SerUnit {  // what a (sub-step, keyword) lane needs again in each of the 
 __global__ void __launch_bounds__(kSerWarps * 32)
 adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
 {
-    __shared__ double s_costd[kSerWarps][kSerCap][32];  // cents / 100 in f64: what the reference compares
+    __shared__ int s_cost[kSerWarps][kSerCap][32];  // clicked slots' costs in cents (dollars are 3 FMAs away)
     __shared__ uint32_t s_w2[kSerWarps][kSerCap][32];
     __shared__ SerUnit s_unit[kSerWarps][kSerCacheK];
     const int K = a.kw.K;
@@ -1733,7 +1733,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                                 ++I;
                                 if (cc <= su.thr_click) {
                                     if (nclk < kSerCap) {
-                                        s_costd[warp][nclk][lane] = cents_to_dollars(c);
+                                        s_cost[warp][nclk][lane] = c;
                                         s_w2[warp][nclk][lane] = cc;
                                     }
                                     ++nclk;
@@ -1761,16 +1761,16 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                 //     lanes form in parallel.
                 if (remaining > 0) {
                     const bool lane_has = act && nclk > 0;
-                    const bool none = !lane_has || !(remaining >= s_costd[warp][0][lane]);
+                    const bool none = !lane_has || !(remaining >= cents_to_dollars(s_cost[warp][0][lane]));
                     if (__all_sync(FULL, none)) {
                         todo = 0;
                     } else if (!__any_sync(FULL, nclk > kSerCap || su.bid_cents > kMaxFlatBidCents)) {
                         unsigned cents = 0;
                         double lane_sum = 0.0;
                         for (int i = 0; i < nclk; ++i) {
-                            const double cd = s_costd[warp][i][lane];
-                            lane_sum = __dadd_rn(lane_sum, cd);
-                            cents += (unsigned)__double2int_rn(__dmul_rn(cd, 100.0));
+                            const int c = s_cost[warp][i][lane];
+                            lane_sum = __dadd_rn(lane_sum, cents_to_dollars(c));
+                            cents += (unsigned)c;
                         }
                         const unsigned total = __reduce_add_sync(FULL, cents);  // <= 32 * 16 * 65535 (bids capped above)
                         const double spend = __ddiv_rn((double)total, 100.0);
@@ -1782,7 +1782,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                                 double b = remaining;
                                 if (a.budget_alias) {  // the lane's own walk already drew on the shared budget (bsim:102)
                                     const int n_l = __shfl_sync(FULL, nclk, l);
-                                    for (int i = 0; i < n_l; ++i) b = __dsub_rn(b, s_costd[warp][i][l]);
+                                    for (int i = 0; i < n_l; ++i) b = __dsub_rn(b, cents_to_dollars(s_cost[warp][i][l]));
                                 }
                                 remaining = __dsub_rn(b, __shfl_sync(FULL, lane_sum, l));
                             }
@@ -1798,7 +1798,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                         double b = remaining, lane_sum = 0.0;
                         int acc = 0;
                         for (int i = 0; i < n_l; ++i) {
-                            const double cost = s_costd[warp][i][l];
+                            const double cost = cents_to_dollars(s_cost[warp][i][l]);
                             if (!(b >= cost)) break;  // bsim:99-104
                             ++acc;
                             lane_sum = __dadd_rn(lane_sum, cost);
@@ -1834,7 +1834,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                     if (!rev_done) {
                         const bool conv_all = (su.flags & 1) != 0;
                         for (int i = 0; i < B; ++i) {
-                            cost_c += __double2ll_rn(__dmul_rn(s_costd[warp][i][lane], 100.0));  // exact: cents < 2^31
+                            cost_c += s_cost[warp][i][lane];
                             S += conv_all || s_w2[warp][i][lane] < su.thr_cc;
                         }
                         if (S > 0) {
