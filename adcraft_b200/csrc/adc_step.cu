@@ -1640,7 +1640,7 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
 // ------------------------------------------------------------------------------------------
 constexpr int kSerWarps = 4;
 constexpr int kSerCap = 16;     // buffered clicked slots per lane and sub-step; more -> direct re-walk
-constexpr int kSerCacheK = 128; // keywords per env whose per-unit constants are cached in shared memory
+constexpr int kSerCacheK = 104; // keywords per env whose per-unit constants and running sums live in shared memory
 
 struct SerUnit {  // what a (sub-step, keyword) lane needs again in each of the 24 sub-steps
     int bid_cents, floor_cents;
@@ -1648,6 +1648,11 @@ struct SerUnit {  // what a (sub-step, keyword) lane needs again in each of the 
     uint32_t thr_click, thr_cc;  // thr_cc = 0xFFFFFFFF with conv_all in the sign of `volume`... see flags
     int volume;                  // clamped to INT_MAX (larger volumes take the uncached path)
     int flags;                   // bit 0: conv_all
+};
+
+struct __align__(16) SerAcc {  // a keyword's running day totals (flushed to the outputs once per env)
+    int I, B, S, pad;
+    long long cost, rev;
 };
 
 // One warp per queued env.  The reference's walk is sequential in (sub-step, keyword, click) because
@@ -1663,6 +1668,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
     __shared__ int s_cost[kSerWarps][kSerCap][32];  // clicked slots' costs in cents (dollars are 3 FMAs away)
     __shared__ uint32_t s_w2[kSerWarps][kSerCap][32];
     __shared__ SerUnit s_unit[kSerWarps][kSerCacheK];
+    __shared__ SerAcc s_acc[kSerWarps][kSerCacheK];
     const int K = a.kw.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * kSerWarps + warp;
@@ -1695,7 +1701,12 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
             a.out.conversions[u] = 0;
             a.out.cost_cents[u] = 0;
             a.out.revenue_cents[u] = 0;
-            if (k < kSerCacheK) s_unit[warp][k] = make_unit(src, e, k);
+            if (k < kSerCacheK) {
+                s_unit[warp][k] = make_unit(src, e, k);
+                SerAcc z;
+                z.I = z.B = z.S = z.pad = 0; z.cost = z.rev = 0;
+                s_acc[warp][k] = z;
+            }
         }
         __syncwarp();
         const double budget = step_budget(a, e);
@@ -1814,7 +1825,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                             p.rev_mean = su.rev_mean; p.rev_sd = su.rev_sd; p.thr_click = su.thr_click; p.thr_cc = su.thr_cc;
                             p.conv_all = (su.flags & 1) != 0; p.bid = 0.0; p.ctr = 0.0; p.cvr = 0.0; p.thr_conv = 0; p.thr_impr = 0;
                             double b = remaining, unused = 0.0;
-                            UnitCur cur = {j0, 0, 0, a.out.conversions[u], 0};
+                            UnitCur cur = {j0, 0, 0, k < kSerCacheK ? s_acc[warp][k].S : a.out.conversions[u], 0};
                             const LaneOut o = lane_walk<PhiloxSrc, false, true>(src, no_tape, u, k, t, n, p, cur, b, unused);
                             B = o.B; S = o.S; cost_c = o.cost_cents; rev_c = o.rev_cents;
                             rev_done = true;
@@ -1838,7 +1849,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                             S += conv_all || s_w2[warp][i][lane] < su.thr_cc;
                         }
                         if (S > 0) {
-                            const int r0 = a.out.conversions[u];
+                            const int r0 = k < kSerCacheK ? s_acc[warp][k].S : a.out.conversions[u];
                             uint4 rw = make_uint4(0, 0, 0, 0);
                             for (int i = 0; i < S; ++i) {
                                 const int r = r0 + i;
@@ -1848,15 +1859,31 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                             }
                         }
                     }
-                    a.out.impressions[u] += I;
-                    a.out.clicks[u] += B;
-                    a.out.conversions[u] += S;
-                    a.out.cost_cents[u] += cost_c;
-                    a.out.revenue_cents[u] += rev_c;
+                    if (k < kSerCacheK) {
+                        SerAcc ac = s_acc[warp][k];
+                        ac.I += I; ac.B += B; ac.S += S; ac.cost += cost_c; ac.rev += rev_c;
+                        s_acc[warp][k] = ac;
+                    } else {
+                        a.out.impressions[u] += I;
+                        a.out.clicks[u] += B;
+                        a.out.conversions[u] += S;
+                        a.out.cost_cents[u] += cost_c;
+                        a.out.revenue_cents[u] += rev_c;
+                    }
                 }
                 __syncwarp();
             }
         }
+        for (int k = lane; k < K && k < kSerCacheK; k += 32) {
+            const int64_t u = (int64_t)e * K + k;
+            const SerAcc ac = s_acc[warp][k];
+            a.out.impressions[u] = ac.I;
+            a.out.clicks[u] = ac.B;
+            a.out.conversions[u] = ac.S;
+            a.out.cost_cents[u] = ac.cost;
+            a.out.revenue_cents[u] = ac.rev;
+        }
+        __syncwarp();
         // ---- float outputs, reward, env tail, drift
         long long profit_c = 0;
         for (int k = lane; k < K; k += 32) {
