@@ -1725,19 +1725,22 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                 int I = 0, nclk = 0;
                 if (act) {
                     su = k < kSerCacheK ? s_unit[warp][k] : make_unit(src, e, k);
-                    const long long V = su.volume;
-                    const long long q = V / ADC_SUBSTEPS;
-                    const long long n0 = V - (ADC_SUBSTEPS - 1) * q;
-                    n = t == 0 ? n0 : q;
-                    j0 = t == 0 ? 0 : n0 + (long long)(t - 1) * q;
+                    // volumes are clamped to INT_MAX, so the day's auction indices fit 32 bits
+                    const int V = su.volume;
+                    const int q = V / ADC_SUBSTEPS;
+                    const int n0 = V - (ADC_SUBSTEPS - 1) * q;
+                    const int ni = t == 0 ? n0 : q;
+                    const int ji = t == 0 ? 0 : n0 + (t - 1) * q;
+                    n = ni;
+                    j0 = ji;
                     // one Philox call serves auctions 2c and 2c+1: walk the calls that overlap [j0, j0+n)
-                    const long long j_end = j0 + n;
-                    for (long long cidx = j0 >> 1; 2 * cidx < j_end; ++cidx) {
+                    const int j_end = ji + ni;
+                    for (int cidx = ji >> 1; 2 * cidx < j_end; ++cidx) {
                         const uint4 w = src.draw(ST_AUCTION, (uint32_t)k, (uint32_t)cidx);
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const long long j = 2 * cidx + h;
-                            if (j < j0 || j >= j_end) continue;
+                            const int j = 2 * cidx + h;
+                            if (j < ji || j >= j_end) continue;
                             const uint32_t cc = h ? w.w : w.y;
                             const int c = max(laplace_cents(h ? w.z : w.x, su.loc, su.scale), su.floor_cents);
                             if (su.bid_cents > c) {
