@@ -1640,7 +1640,9 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
 // ------------------------------------------------------------------------------------------
 constexpr int kSerWarps = 4;
 constexpr int kSerCap = 16;     // buffered clicked slots per lane and sub-step; more -> direct re-walk
-constexpr int kSerCacheK = 104; // keywords per env whose per-unit constants and running sums live in shared memory
+constexpr int kSerCacheK = 104; // keywords per env whose per-unit constants (and running sums) live in shared memory
+constexpr bool kSerUseAcc = false;  // running day totals in shared memory (13 KB per CTA) or read-modify-write of the outputs
+constexpr int kSerMinBlocks = 7;    // 28 warps per SM: a 4096-env queue is resident in one wave
 
 struct SerUnit {  // what a (sub-step, keyword) lane needs again in each of the 24 sub-steps
     int bid_cents, floor_cents;
@@ -1662,15 +1664,16 @@ struct __align__(16) SerAcc {  // a keyword's running day totals (flushed to the
 // runs ONE uniform scan over the buffered clicks in keyword order -- the reference's f64 sequence
 // `if budget >= cost: budget -= cost` (bsim:97-104), alias rule and `remaining <= 0` exit included
 // -- and finally the lanes commit their accepted prefix in parallel (conversions, revenues).
-__global__ void __launch_bounds__(kSerWarps * 32)
+__global__ void __launch_bounds__(kSerWarps * 32, kSerMinBlocks)
 adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
 {
-    __shared__ int s_cost[kSerWarps][kSerCap][32];  // clicked slots' costs in cents (dollars are 3 FMAs away)
-    __shared__ uint32_t s_w2[kSerWarps][kSerCap][32];
+    // clicked slots: cost in cents (bits 0..30; dollars are 3 FMAs away) | converts (bit 31)
+    __shared__ uint32_t s_slot[kSerWarps][kSerCap][32];
     __shared__ SerUnit s_unit[kSerWarps][kSerCacheK];
-    __shared__ SerAcc s_acc[kSerWarps][kSerCacheK];
+    __shared__ SerAcc s_acc[kSerWarps][kSerUseAcc ? kSerCacheK : 1];
     const int K = a.kw.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto slot_cost = [&](int i, int l) { return (int)(s_slot[warp][i][l] & 0x7FFFFFFFu); };
     const int gwarp = blockIdx.x * kSerWarps + warp;
     const int n_warps = gridDim.x * kSerWarps;
     const int count = a.scratch.serial_count[a.step & 1u];
@@ -1703,9 +1706,11 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
             a.out.revenue_cents[u] = 0;
             if (k < kSerCacheK) {
                 s_unit[warp][k] = make_unit(src, e, k);
-                SerAcc z;
-                z.I = z.B = z.S = z.pad = 0; z.cost = z.rev = 0;
-                s_acc[warp][k] = z;
+                if (kSerUseAcc) {
+                    SerAcc z;
+                    z.I = z.B = z.S = z.pad = 0; z.cost = z.rev = 0;
+                    s_acc[warp][k] = z;
+                }
             }
         }
         __syncwarp();
@@ -1747,8 +1752,8 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                                 ++I;
                                 if (cc <= su.thr_click) {
                                     if (nclk < kSerCap) {
-                                        s_cost[warp][nclk][lane] = c;
-                                        s_w2[warp][nclk][lane] = cc;
+                                        const bool cv = (su.flags & 1) != 0 || cc < su.thr_cc;
+                                        s_slot[warp][nclk][lane] = (uint32_t)c | (cv ? 0x80000000u : 0u);
                                     }
                                     ++nclk;
                                 }
@@ -1775,14 +1780,14 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                 //     lanes form in parallel.
                 if (remaining > 0) {
                     const bool lane_has = act && nclk > 0;
-                    const bool none = !lane_has || !(remaining >= cents_to_dollars(s_cost[warp][0][lane]));
+                    const bool none = !lane_has || !(remaining >= cents_to_dollars(slot_cost(0, lane)));
                     if (__all_sync(FULL, none)) {
                         todo = 0;
                     } else if (!__any_sync(FULL, nclk > kSerCap || su.bid_cents > kMaxFlatBidCents)) {
                         unsigned cents = 0;
                         double lane_sum = 0.0;
                         for (int i = 0; i < nclk; ++i) {
-                            const int c = s_cost[warp][i][lane];
+                            const int c = slot_cost(i, lane);
                             lane_sum = __dadd_rn(lane_sum, cents_to_dollars(c));
                             cents += (unsigned)c;
                         }
@@ -1796,7 +1801,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                                 double b = remaining;
                                 if (a.budget_alias) {  // the lane's own walk already drew on the shared budget (bsim:102)
                                     const int n_l = __shfl_sync(FULL, nclk, l);
-                                    for (int i = 0; i < n_l; ++i) b = __dsub_rn(b, cents_to_dollars(s_cost[warp][i][l]));
+                                    for (int i = 0; i < n_l; ++i) b = __dsub_rn(b, cents_to_dollars(slot_cost(i, l)));
                                 }
                                 remaining = __dsub_rn(b, __shfl_sync(FULL, lane_sum, l));
                             }
@@ -1812,7 +1817,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                         double b = remaining, lane_sum = 0.0;
                         int acc = 0;
                         for (int i = 0; i < n_l; ++i) {
-                            const double cost = cents_to_dollars(s_cost[warp][i][l]);
+                            const double cost = cents_to_dollars(slot_cost(i, l));
                             if (!(b >= cost)) break;  // bsim:99-104
                             ++acc;
                             lane_sum = __dadd_rn(lane_sum, cost);
@@ -1828,7 +1833,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                             p.rev_mean = su.rev_mean; p.rev_sd = su.rev_sd; p.thr_click = su.thr_click; p.thr_cc = su.thr_cc;
                             p.conv_all = (su.flags & 1) != 0; p.bid = 0.0; p.ctr = 0.0; p.cvr = 0.0; p.thr_conv = 0; p.thr_impr = 0;
                             double b = remaining, unused = 0.0;
-                            UnitCur cur = {j0, 0, 0, k < kSerCacheK ? s_acc[warp][k].S : a.out.conversions[u], 0};
+                            UnitCur cur = {j0, 0, 0, kSerUseAcc && k < kSerCacheK ? s_acc[warp][k].S : a.out.conversions[u], 0};
                             const LaneOut o = lane_walk<PhiloxSrc, false, true>(src, no_tape, u, k, t, n, p, cur, b, unused);
                             B = o.B; S = o.S; cost_c = o.cost_cents; rev_c = o.rev_cents;
                             rev_done = true;
@@ -1846,13 +1851,13 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                 // ---- phase 3 (parallel): the accepted prefix of the lane's clicks, revenues, commit
                 if (act && lane <= cutoff) {
                     if (!rev_done) {
-                        const bool conv_all = (su.flags & 1) != 0;
                         for (int i = 0; i < B; ++i) {
-                            cost_c += s_cost[warp][i][lane];
-                            S += conv_all || s_w2[warp][i][lane] < su.thr_cc;
+                            const uint32_t sl = s_slot[warp][i][lane];
+                            cost_c += (int)(sl & 0x7FFFFFFFu);
+                            S += (int)(sl >> 31);
                         }
                         if (S > 0) {
-                            const int r0 = k < kSerCacheK ? s_acc[warp][k].S : a.out.conversions[u];
+                            const int r0 = kSerUseAcc && k < kSerCacheK ? s_acc[warp][k].S : a.out.conversions[u];
                             uint4 rw = make_uint4(0, 0, 0, 0);
                             for (int i = 0; i < S; ++i) {
                                 const int r = r0 + i;
@@ -1862,7 +1867,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                             }
                         }
                     }
-                    if (k < kSerCacheK) {
+                    if (kSerUseAcc && k < kSerCacheK) {
                         SerAcc ac = s_acc[warp][k];
                         ac.I += I; ac.B += B; ac.S += S; ac.cost += cost_c; ac.rev += rev_c;
                         s_acc[warp][k] = ac;
@@ -1877,7 +1882,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                 __syncwarp();
             }
         }
-        for (int k = lane; k < K && k < kSerCacheK; k += 32) {
+        for (int k = lane; kSerUseAcc && k < K && k < kSerCacheK; k += 32) {
             const int64_t u = (int64_t)e * K + k;
             const SerAcc ac = s_acc[warp][k];
             a.out.impressions[u] = ac.I;
