@@ -143,10 +143,18 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+
+    def mark(self):
+        """Start of the timed region: samples printed before this point (nvidia-smi needs ~0.1 s to
+        come up, so it is started ahead of the warm-up steps) are not counted."""
+        try:
+            self.skip = os.path.getsize(self.f.name)
+        except OSError:
+            self.skip = 0
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -158,7 +166,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        self.f.seek(0)
+        self.f.seek(getattr(self, "skip", 0))
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
@@ -376,14 +384,22 @@ def run_gpu(args):
         return 0
 
     # ---- device-timed steps, inputs resident in HBM --------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # nvidia-smi needs ~0.1 s to come up
     for _ in range(max(args.warmup, 3)):
         obs, reward, term, trunc, _ = env.step(action)
+    if sampler is not None:  # keep the GPU under the same load until the sampler prints (at most 0.5 s)
+        t_up = time.perf_counter()
+        while os.path.getsize(sampler.f.name) == 0 and time.perf_counter() - t_up < 0.5:
+            for _ in range(20):
+                obs, reward, term, trunc, _ = env.step(action)
+            torch.cuda.synchronize(dev)
     if world > 1:  # NCCL connects lazily: establish the all-reduce path before the timed region
         for _ in range(2):
             episode_reduce(obs, reward, term)
         metric_acc.zero_()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.mark()
     lib = _capi.load()
     lib.adc_launch_count(1)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
