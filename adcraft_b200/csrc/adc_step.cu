@@ -548,6 +548,44 @@ adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
 // kernel loses ~30 % of its lanes to it); only the last 32-auction trip of a unit has idle lanes.
 // Revenues are flattened across the batch (4 draws per Philox call).
 // ------------------------------------------------------------------------------------------
+// The hot loop's competitor bid: same value as laplace_cents (adc_rng.cuh) with the Exp(1) table
+// in shared memory, written so that it compiles to 15 instructions: 2w+1 as one multiply-add,
+// the normalising shift from bfind.shiftamt (= clz), the sign of the Laplace branch XORed into
+// the scale's sign bit.
+__device__ __forceinline__ int laplace_cents_smem(uint32_t w0, float loc, float scale, const float2 (&tab)[128])
+{
+    uint32_t a, lz;  // a = 2 * (w0 & 0x7FFFFFFF) + 1 (mod 2^32) as one multiply-add
+    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(a) : "r"(w0));
+    asm("bfind.shiftamt.u32 %0, %1;" : "=r"(lz) : "r"(a));
+    const uint32_t an = a << lz;
+    const float2 ts = tab[(an >> 24) & 0x7Fu];
+    const float lo = __uint2float_rn(an & 0x00FFFFFFu);
+    const float inner = __fmaf_rn(-lo, ts.y, ts.x);
+    const float e = __fmaf_rn(__uint2float_rn(lz), kLn2f, inner);
+    const float s = __uint_as_float(__float_as_uint(scale) ^ (w0 & 0x80000000u));
+    const float x = __fmaf_rn(s, e, loc);
+    return __float2int_rn(__fmul_rn(fabsf(x), 100.0f));
+}
+
+// win <=> bid > c; click <=> win && cc <= thr_click; conversion <=> click && cc <= thr_conv.
+// Three compares chained through their predicates and four predicated adds.
+__device__ __forceinline__ void tally_counts(int bid, int c, uint32_t cc, uint32_t thr_click, uint32_t thr_conv,
+                                             unsigned &cntIB, unsigned &cntS, unsigned &cst)
+{
+    asm("{\n\t"
+        ".reg .pred pw, pc, pv;\n\t"
+        "setp.gt.s32 pw, %3, %4;\n\t"
+        "setp.le.and.u32 pc, %5, %6, pw;\n\t"
+        "setp.le.and.u32 pv, %5, %7, pc;\n\t"
+        "@pw add.u32 %0, %0, 1;\n\t"
+        "@pc add.u32 %0, %0, 65536;\n\t"
+        "@pv add.u32 %1, %1, 1;\n\t"
+        "@pc add.u32 %2, %2, %4;\n\t"
+        "}"
+        : "+r"(cntIB), "+r"(cntS), "+r"(cst)
+        : "r"(bid), "r"(c), "r"(cc), "r"(thr_click), "r"(thr_conv));
+}
+
 struct __align__(16) FlatUnit {
     int bid_cents;
     float loc, scale;
@@ -566,8 +604,9 @@ struct __align__(16) FlatRev {
 constexpr int kFlatWarps = 8;
 // Caps of the fast kernel's 16/32-bit lane accumulators; a unit beyond them sends its env to the
 // exact serial kernel instead (volumes and bids this large do not occur in the reference's configs).
-constexpr int kMaxFlatVolume = 1 << 20;
+constexpr int kMaxFlatVolume = 65535;  // impressions and clicks share one 32-bit REDUX (I | B << 16)
 constexpr int kMaxFlatBidCents = 65535;
+constexpr long long kMaxFlatSpendCents = 0xFFFFFFFFLL;  // volume x bid: the unit's cost is one 32-bit REDUX
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 {
@@ -646,7 +685,8 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             const int64_t pi = (int64_t)e * a.kw.env_stride + k;
             const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)k), genv, k0, k1);
             const long long v = volume_draw(w.x, a.kw.vol_mean[pi], a.kw.vol_std[pi]);
-            over_cap = v > (G == 32 ? kMaxFlatVolume : 65535) || p.bid_cents > kMaxFlatBidCents;
+            over_cap = v > kMaxFlatVolume || p.bid_cents > kMaxFlatBidCents ||
+                       v * p.bid_cents > kMaxFlatSpendCents;
             V = over_cap ? 0 : (int)v;
         } else if (valid) {
             e = (int)(u / K);
@@ -657,8 +697,11 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), genv, k0, k1);
             FlatUnit fu;
             fu.bid_cents = p.bid_cents; fu.loc = p.loc; fu.scale = p.scale;
-            fu.thr_click = p.thr_click; fu.thr_conv = p.thr_cc;
-            if (p.conv_all) fu.bid_cents |= (int)0x80000000u;  // flag rides in the sign bit (bids <= 65535)
+            // conversion <=> cc < T2 (T2 = 2^32 when conv_all) is stored as cc <= T2 - 1; T2 = 0
+            // ("never") rides in the sign bit of the bid (bids <= 65535) and zeroes the unit's count
+            fu.thr_click = p.thr_click;
+            fu.thr_conv = p.conv_all ? 0xFFFFFFFFu : (p.thr_cc ? p.thr_cc - 1u : 0u);
+            if (!p.conv_all && p.thr_cc == 0u) fu.bid_cents |= (int)0x80000000u;
             fu.n0 = pa.n0; fu.n1 = pa.n1; fu.x3 = pa.x3;
             units[lane] = fu;
         }
@@ -680,54 +723,48 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             if (b >= cnt) Vb = 0;
             if (G == 32 && Vb == 0) continue;  // warp-uniform
             FlatUnit fu = units[b & 31];
-            const bool conv_all = fu.bid_cents < 0;
+            const bool conv_none = fu.bid_cents < 0;
             fu.bid_cents &= 0x7FFFFFFF;
             const int floor_c = kFloor ? s_floor[warp][b & 31] : 0;
             unsigned cntIB = 0, cntS = 0, cst = 0;  // I | B << 16 ; S ; cost cents (< 2^32, see caps)
             // one auction: competitor bid from `wc`, click + conversion from the single word `cc`
-            auto tally = [&](bool act, uint32_t wc, uint32_t cc) {
-                int c = laplace_cents(wc, fu.loc, fu.scale, s_tab);
+            // (`bid` is 0 for a lane past the unit's end: no competitor bid is below it)
+            auto tally = [&](int bid, uint32_t wc, uint32_t cc) {
+                int c = laplace_cents_smem(wc, fu.loc, fu.scale, s_tab);
                 if (kFloor) c = max(c, floor_c);
-                const bool win = act && fu.bid_cents > c;
-                const bool clk = win && (cc <= fu.thr_click);
-                const bool cnv = clk && (conv_all || cc < fu.thr_conv);
-                cntIB += (win ? 1u : 0u) + (clk ? 0x10000u : 0u);
-                cntS += cnv ? 1u : 0u;
-                cst += clk ? (unsigned)c : 0u;
+                tally_counts(bid, c, cc, fu.thr_click, fu.thr_conv, cntIB, cntS, cst);
             };
             // full trips: each lane takes one Philox call = two consecutive auctions (2G per trip)
             int base = 0;
             for (; base + 2 * G <= Vb; base += 2 * G) {
                 const uint4 w = philox_from_pre((uint32_t)((base >> 1) + gl), fu.n0, fu.n1, fu.x3, k0, k1);
-                tally(true, w.x, w.y);
-                tally(true, w.z, w.w);
+                tally(fu.bid_cents, w.x, w.y);
+                tally(fu.bid_cents, w.z, w.w);
             }
             const int rem = Vb - base;  // 0 .. 2G-1 auctions left
             if (rem > G) {              // still worth pairing: lanes past the end idle
                 const int j = base + 2 * gl;
                 const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
-                tally(j < Vb, w.x, w.y);
-                tally(j + 1 < Vb, w.z, w.w);
+                tally(j < Vb ? fu.bid_cents : 0, w.x, w.y);
+                tally(j + 1 < Vb ? fu.bid_cents : 0, w.z, w.w);
             } else if (rem > 0) {       // at most G left: one auction per lane, half a call each
                 const int j = base + gl;
                 const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
-                tally(j < Vb, (j & 1) ? w.z : w.x, (j & 1) ? w.w : w.y);
+                tally(j < Vb ? fu.bid_cents : 0, (j & 1) ? w.z : w.x, (j & 1) ? w.w : w.y);
             }
-            const unsigned tI = __reduce_add_sync(gmask, cntIB & 0xFFFFu);
-            const unsigned tB = __reduce_add_sync(gmask, cntIB >> 16);
-            const unsigned tS = __reduce_add_sync(gmask, cntS);
-            const unsigned lo = __reduce_add_sync(gmask, cst & 0xFFFFu);
-            const unsigned hi = __reduce_add_sync(gmask, cst >> 16);
+            // the caps above keep every sum below 2^32 (I, B <= V < 2^16; cost <= V x bid)
+            const unsigned tIB = __reduce_add_sync(gmask, cntIB);
+            const unsigned tS = __reduce_add_sync(gmask, conv_none ? 0u : cntS);
+            const unsigned tC = __reduce_add_sync(gmask, cst);
             if (G == 32) {
                 if (lane == b) {
-                    I = (int)tI; B = (int)tB; S = (int)tS;
-                    cost = (long long)lo + ((long long)hi << 16);
+                    I = (int)(tIB & 0xFFFFu); B = (int)(tIB >> 16); S = (int)tS;
+                    cost = (long long)tC;
                 }
             } else if (gl == 0 && b < cnt) {
-                s_res[warp][b][0] = tI | (tB << 16);
+                s_res[warp][b][0] = tIB;
                 s_res[warp][b][1] = tS;
-                s_res[warp][b][2] = lo;
-                s_res[warp][b][3] = hi;
+                s_res[warp][b][2] = tC;
             }
         }
         if (G != 32) {
@@ -735,7 +772,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             if (lane < cnt) {
                 const unsigned ib = s_res[warp][lane][0];
                 I = (int)(ib & 0xFFFFu); B = (int)(ib >> 16); S = (int)s_res[warp][lane][1];
-                cost = (long long)s_res[warp][lane][2] + ((long long)s_res[warp][lane][3] << 16);
+                cost = (long long)s_res[warp][lane][2];
             }
         }
 
