@@ -52,45 +52,7 @@ static void draw4(uint64_t seed, uint32_t env, uint32_t step, uint32_t agent, ui
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
-/* ln(m) for m in [sqrt(1/2), sqrt(2)] via f = m-1; Cephes logf coefficients, every
- * multiply-add is an explicit fmaf so CPU and GPU round identically. */
-static inline float ln_mant(float f)
-{
-    float z = f * f;
-    float y = 7.0376836292E-2f;
-    y = fmaf(y, f, -1.1514610310E-1f);
-    y = fmaf(y, f, 1.1676998740E-1f);
-    y = fmaf(y, f, -1.2420140846E-1f);
-    y = fmaf(y, f, 1.4249322787E-1f);
-    y = fmaf(y, f, -1.6668057665E-1f);
-    y = fmaf(y, f, 2.0000714765E-1f);
-    y = fmaf(y, f, -2.4999993993E-1f);
-    y = fmaf(y, f, 3.3333331174E-1f);
-    y = (y * f) * z;
-    y = fmaf(-0.5f, z, y);
-    return f + y;
-}
-
-/* split a positive normal float into exponent k and mantissa m in [sqrt(1/2), sqrt(2)) */
-static inline float split_mant(float a, int32_t *k)
-{
-    uint32_t b = f2u(a);
-    int32_t e = (int32_t)(b >> 23) - 127;
-    float m = u2f((b & 0x007FFFFFu) | 0x3F800000u);
-    if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
-    *k = e;
-    return m;
-}
-
 #define ORC_LN2F 0.693147182f
-
-float orc_lnf(float a)
-{
-    int32_t k;
-    float m = split_mant(a, &k);
-    float r = ln_mant(m - 1.0f);
-    return fmaf((float)k, ORC_LN2F, r);
-}
 
 /* -ln((w31 + 0.5) / 2^31) for a 31-bit uniform integer: an Exp(1) variate.
  * a = 2*w31+1 is normalised (a << clz) to x = an/2^32 in [0.5,1); -ln(x) is read off a 128-entry
@@ -111,39 +73,22 @@ float orc_neglog_u31(uint32_t w31)
     return fmaf((float)lz, ORC_LN2F, inner);
 }
 
-/* Standard normal from one 32-bit word: sign bit + 31-bit tail probability, inverse
- * CDF by M. Giles' single-precision erfinv polynomial evaluated on the tail variable. */
+/* Standard normal from one 32-bit word: sign bit + 31-bit two-sided tail probability
+ * t = (2*w31+1)/2^32 = P(|Z| > z).  a = 2*w31+1 is normalised (a << clz) and z = sqrt(2)*erfcinv(t)
+ * is read off a chord table on (clz, the 7 bits below the leading one), minimax-shifted
+ * (error <= 1.6e-6, tools/gen_znorm_table.py):   z = T[clz][idx] - S[clz][idx] * lo,  lo = low 24 bits. */
+static const float ORC_ZNORM_TAB[32 * 128][2] = {
+#include "znorm_table.inc"
+};
+
 float orc_znorm(uint32_t w)
 {
-    uint32_t w31 = w & 0x7FFFFFFFu;
-    float t = (float)(2u * w31 + 1u) * 2.3283064365386963e-10f; /* (w31+.5)/2^31 in (0,1] */
-    float a = t * (2.0f - t);                                   /* (1-x)(1+x), x = 1-t     */
-    float wl = -orc_lnf(a);
-    float p;
-    if (wl < 5.0f) {
-        float v = wl - 2.5f;
-        p = 2.81022636e-08f;
-        p = fmaf(p, v, 3.43273939e-07f);
-        p = fmaf(p, v, -3.5233877e-06f);
-        p = fmaf(p, v, -4.39150654e-06f);
-        p = fmaf(p, v, 0.00021858087f);
-        p = fmaf(p, v, -0.00125372503f);
-        p = fmaf(p, v, -0.00417768164f);
-        p = fmaf(p, v, 0.246640727f);
-        p = fmaf(p, v, 1.50140941f);
-    } else {
-        float v = sqrtf(wl) - 3.0f;
-        p = -0.000200214257f;
-        p = fmaf(p, v, 0.000100950558f);
-        p = fmaf(p, v, 0.00134934322f);
-        p = fmaf(p, v, -0.00367342844f);
-        p = fmaf(p, v, 0.00573950773f);
-        p = fmaf(p, v, -0.0076224613f);
-        p = fmaf(p, v, 0.00943887047f);
-        p = fmaf(p, v, 1.00167406f);
-        p = fmaf(p, v, 2.83297682f);
-    }
-    float z = (p * (1.0f - t)) * 1.41421354f;
+    const uint32_t a = 2u * w + 1u; /* = 2 * (w & 0x7FFFFFFF) + 1 (mod 2^32) */
+    const int lz = __builtin_clz(a);
+    const uint32_t an = a << lz;
+    const uint32_t idx = (uint32_t)lz * 128u + ((an >> 24) & 0x7Fu);
+    const uint32_t lo = an & 0x00FFFFFFu;
+    const float z = fmaf(-(float)lo, ORC_ZNORM_TAB[idx][1], ORC_ZNORM_TAB[idx][0]);
     return (w >> 31) ? -z : z;
 }
 

@@ -71,7 +71,6 @@ typedef struct {
 
 /* ---- Philox4x32-10 and samplers (spec: DESIGN.md "Tape function") ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-float orc_lnf(float a);
 float orc_neglog_u31(uint32_t w31);
 float orc_znorm(uint32_t w);
 double orc_exp(double x);

@@ -56,8 +56,6 @@ def lib() -> C.CDLL:
         build()
     L = C.CDLL(path)
     L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
-    L.orc_lnf.restype = C.c_float
-    L.orc_lnf.argtypes = [C.c_float]
     L.orc_neglog_u31.restype = C.c_float
     L.orc_neglog_u31.argtypes = [C.c_uint32]
     L.orc_znorm.restype = C.c_float
