@@ -95,14 +95,35 @@ __device__ __forceinline__ Drift3 drift_from_words(const adc_step_args &a, uint4
     return d;
 }
 
-// update_keywords for one keyword (env:145-158): nonnegify / probify
-__device__ __forceinline__ void drift_apply(const adc_step_args &a, int e, int k, const Drift3 &d)
+// update_keywords for one keyword (env:145-158): nonnegify / probify.  The four loads are issued
+// before the first store (one DRAM round trip per keyword instead of three dependent ones).
+struct DriftState {
+    double vol_mean, vol_std, ctr, cvr;
+};
+
+__device__ __forceinline__ DriftState drift_load(const adc_step_args &a, int e, int k)
 {
     const int64_t i = (int64_t)e * a.kw.env_stride + k;
-    const double vm = __dadd_rn(a.kw.vol_mean[i], __dmul_rn(d.c[0], a.kw.vol_std[i]));
+    DriftState s;
+    s.vol_mean = a.kw.vol_mean[i];
+    s.vol_std = a.kw.vol_std[i];
+    s.ctr = a.kw.ctr[i];
+    s.cvr = a.kw.cvr[i];
+    return s;
+}
+
+__device__ __forceinline__ void drift_store(const adc_step_args &a, int e, int k, const DriftState &s, const Drift3 &d)
+{
+    const int64_t i = (int64_t)e * a.kw.env_stride + k;
+    const double vm = __dadd_rn(s.vol_mean, __dmul_rn(d.c[0], s.vol_std));
     a.kw.vol_mean[i] = vm > 0.0 ? vm : 0.0;
-    a.kw.ctr[i] = clampd(__dmul_rn(a.kw.ctr[i], __dadd_rn(1.0, d.c[1])), 0.0, 1.0);
-    a.kw.cvr[i] = clampd(__dmul_rn(a.kw.cvr[i], __dadd_rn(1.0, d.c[2])), 0.0, 1.0);
+    a.kw.ctr[i] = clampd(__dmul_rn(s.ctr, __dadd_rn(1.0, d.c[1])), 0.0, 1.0);
+    a.kw.cvr[i] = clampd(__dmul_rn(s.cvr, __dadd_rn(1.0, d.c[2])), 0.0, 1.0);
+}
+
+__device__ __forceinline__ void drift_apply(const adc_step_args &a, int e, int k, const Drift3 &d)
+{
+    drift_store(a, e, k, drift_load(a, e, k), d);
 }
 
 __device__ __forceinline__ bool drift_wanted(const adc_step_args &a, int k)
@@ -601,6 +622,17 @@ struct __align__(16) FlatRev {
     uint32_t n1, x3, pad0, pad1;
 };
 
+// One auction of the hot kernel: competitor bid from `wc`, click + conversion from the single
+// word `cc`; `bid` is 0 for a slot past the unit's end (no competitor bid is below it).
+template <bool kFloor>
+__device__ __forceinline__ void flat_auction(int bid, uint32_t wc, uint32_t cc, const FlatUnit &fu, int floor_c,
+                                             const float2 (&tab)[128], unsigned &cntIB, unsigned &cntS, unsigned &cst)
+{
+    int c = laplace_cents_smem(wc, fu.loc, fu.scale, tab);
+    if (kFloor) c = max(c, floor_c);
+    tally_counts(bid, c, cc, fu.thr_click, fu.thr_conv, cntIB, cntS, cst);
+}
+
 constexpr int kFlatWarps = 8;
 // Caps of the fast kernel's 16/32-bit lane accumulators; a unit beyond them sends its env to the
 // exact serial kernel instead (volumes and bids this large do not occur in the reference's configs).
@@ -632,7 +664,8 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     // the single-bidder instantiation
     __shared__ int s_floor[kFloor ? kFlatWarps : 1][32];
     __shared__ FlatUnit s_unit[kFlatWarps][32];
-    __shared__ unsigned s_res[kFlatWarps][32][4];     // G < 32: per-unit sums handed to the owner lane
+    __shared__ __align__(16) unsigned s_res[kFlatWarps][32][4];  // per-unit sums handed to the owner lane
+    __shared__ int s_vol[kFlatWarps][32];
     __shared__ FlatRev s_rev[kFlatWarps][32];
     __shared__ int s_start[kFlatWarps][33];
     __shared__ unsigned s_revsum[kFlatWarps][32][2];  // 24-bit split: native 32-bit smem atomics
@@ -707,73 +740,139 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         }
         if (lane == 0) start[0] = 0;
         s_revsum[warp][lane][0] = 0u; s_revsum[warp][lane][1] = 0u;
+        if (G == 32) *reinterpret_cast<uint4 *>(s_res[warp][lane]) = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
 
         // ---------------- the batch's auctions: 32/G units at a time, G lanes per unit -----------
         // Inside a trip the unit is uniform over its G lanes: parameters in registers, private lane
         // accumulators, one REDUX set per unit.  Only the last trip of a unit has idle lanes.
-        constexpr int NG = 32 / G;
-        const int gl = lane & (G - 1), gi = lane / G;
-        const unsigned gmask = G == 32 ? FULL : (((1u << G) - 1u) << (gi * G));
         int I = 0, B = 0, S = 0;
         long long cost = 0;
-        for (int b0 = 0; b0 < cnt; b0 += NG) {
-            const int b = b0 + gi;  // this group's unit
-            int Vb = __shfl_sync(FULL, V, b & 31);
-            if (b >= cnt) Vb = 0;
-            if (G == 32 && Vb == 0) continue;  // warp-uniform
-            FlatUnit fu = units[b & 31];
-            const bool conv_none = fu.bid_cents < 0;
-            fu.bid_cents &= 0x7FFFFFFF;
-            const int floor_c = kFloor ? s_floor[warp][b & 31] : 0;
-            unsigned cntIB = 0, cntS = 0, cst = 0;  // I | B << 16 ; S ; cost cents (< 2^32, see caps)
-            // one auction: competitor bid from `wc`, click + conversion from the single word `cc`
-            // (`bid` is 0 for a lane past the unit's end: no competitor bid is below it)
-            auto tally = [&](int bid, uint32_t wc, uint32_t cc) {
-                int c = laplace_cents_smem(wc, fu.loc, fu.scale, s_tab);
-                if (kFloor) c = max(c, floor_c);
-                tally_counts(bid, c, cc, fu.thr_click, fu.thr_conv, cntIB, cntS, cst);
-            };
-            // full trips: each lane takes one Philox call = two consecutive auctions (2G per trip)
-            int base = 0;
-            for (; base + 2 * G <= Vb; base += 2 * G) {
-                const uint4 w = philox_from_pre((uint32_t)((base >> 1) + gl), fu.n0, fu.n1, fu.x3, k0, k1);
-                tally(fu.bid_cents, w.x, w.y);
-                tally(fu.bid_cents, w.z, w.w);
-            }
-            const int rem = Vb - base;  // 0 .. 2G-1 auctions left
-            if (rem > G) {              // still worth pairing: lanes past the end idle
-                const int j = base + 2 * gl;
-                const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
-                tally(j < Vb ? fu.bid_cents : 0, w.x, w.y);
-                tally(j + 1 < Vb ? fu.bid_cents : 0, w.z, w.w);
-            } else if (rem > 0) {       // at most G left: one auction per lane, half a call each
-                const int j = base + gl;
-                const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
-                tally(j < Vb ? fu.bid_cents : 0, (j & 1) ? w.z : w.x, (j & 1) ? w.w : w.y);
-            }
-            // the caps above keep every sum below 2^32 (I, B <= V < 2^16; cost <= V x bid)
-            const unsigned tIB = __reduce_add_sync(gmask, cntIB);
-            const unsigned tS = __reduce_add_sync(gmask, conv_none ? 0u : cntS);
-            const unsigned tC = __reduce_add_sync(gmask, cst);
-            if (G == 32) {
+        if constexpr (G == 32) {
+            // (1) full trips, one unit after the other: each lane takes one Philox call = two
+            // consecutive auctions, 64 per trip, the unit's parameters warp-uniform in registers
+            for (int b = 0; b < cnt; ++b) {
+                const int Vb = __shfl_sync(FULL, V, b);
+                if (Vb < 64) continue;  // warp-uniform
+                FlatUnit fu = units[b];
+                const bool conv_none = fu.bid_cents < 0;
+                fu.bid_cents &= 0x7FFFFFFF;
+                const int floor_c = kFloor ? s_floor[warp][b] : 0;
+                unsigned cntIB = 0, cntS = 0, cst = 0;  // I | B << 16 ; S ; cost cents (< 2^32, see caps)
+                for (int base = 0; base + 64 <= Vb; base += 64) {
+                    const uint4 w = philox_from_pre((uint32_t)((base >> 1) + lane), fu.n0, fu.n1, fu.x3, k0, k1);
+                    flat_auction<kFloor>(fu.bid_cents, w.x, w.y, fu, floor_c, s_tab, cntIB, cntS, cst);
+                    flat_auction<kFloor>(fu.bid_cents, w.z, w.w, fu, floor_c, s_tab, cntIB, cntS, cst);
+                }
+                // the caps above keep every sum below 2^32 (I, B <= V < 2^16; cost <= V x bid)
+                const unsigned tIB = __reduce_add_sync(FULL, cntIB);
+                const unsigned tS = __reduce_add_sync(FULL, conv_none ? 0u : cntS);
+                const unsigned tC = __reduce_add_sync(FULL, cst);
                 if (lane == b) {
                     I = (int)(tIB & 0xFFFFu); B = (int)(tIB >> 16); S = (int)tS;
                     cost = (long long)tC;
                 }
-            } else if (gl == 0 && b < cnt) {
-                s_res[warp][b][0] = tIB;
-                s_res[warp][b][1] = tS;
-                s_res[warp][b][2] = tC;
             }
-        }
-        if (G != 32) {
-            __syncwarp();
-            if (lane < cnt) {
-                const unsigned ib = s_res[warp][lane][0];
-                I = (int)(ib & 0xFFFFu); B = (int)(ib >> 16); S = (int)s_res[warp][lane][1];
-                cost = (long long)s_res[warp][lane][2];
+            // (2) the remainders (V mod 64 auctions per unit) of the whole batch, flattened: Philox
+            // call i of the batch belongs to the unit whose prefix range holds i, so every trip is
+            // full whatever the volumes are; sums land in the unit's shared-memory slot
+            {
+                const int npair = ((V & 63) + 1) >> 1;
+                const int incl_p = warp_incl_scan(npair, lane);
+                s_vol[warp][lane] = V;
+                start[lane + 1] = incl_p;
+                __syncwarp();
+                const int TP = __shfl_sync(FULL, incl_p, 31);
+                int pb0 = 0;
+                for (int base = 0; base < TP; base += 32) {
+                    while (start[pb0 + 1] <= base) ++pb0;
+                    const int i = base + lane;
+                    if (i < TP) {
+                        int b = pb0;
+                        while (i >= start[b + 1]) ++b;
+                        FlatUnit fu = units[b];
+                        const bool conv_none = fu.bid_cents < 0;
+                        fu.bid_cents &= 0x7FFFFFFF;
+                        const int floor_c = kFloor ? s_floor[warp][b] : 0;
+                        const int Vb = s_vol[warp][b];
+                        const int j = (Vb & ~63) + 2 * (i - start[b]);  // first auction of this call
+                        const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
+                        unsigned cntIB = 0, cntS = 0, cst = 0;
+                        flat_auction<kFloor>(fu.bid_cents, w.x, w.y, fu, floor_c, s_tab, cntIB, cntS, cst);
+                        flat_auction<kFloor>(j + 1 < Vb ? fu.bid_cents : 0, w.z, w.w, fu, floor_c, s_tab, cntIB, cntS, cst);
+                        atomicAdd(&s_res[warp][b][0], cntIB);
+                        atomicAdd(&s_res[warp][b][1], conv_none ? 0u : cntS);
+                        atomicAdd(&s_res[warp][b][2], cst);
+                    }
+                }
+                __syncwarp();
+                const uint4 r = *reinterpret_cast<const uint4 *>(s_res[warp][lane]);
+                I += (int)(r.x & 0xFFFFu); B += (int)(r.x >> 16); S += (int)r.y;
+                cost += (long long)r.z;
             }
+        } else {
+            constexpr int NG = 32 / G;
+            const int gl = lane & (G - 1), gi = lane / G;
+            const unsigned gmask = G == 32 ? FULL : (((1u << G) - 1u) << (gi * G));
+            for (int b0 = 0; b0 < cnt; b0 += NG) {
+                const int b = b0 + gi;  // this group's unit
+                int Vb = __shfl_sync(FULL, V, b & 31);
+                if (b >= cnt) Vb = 0;
+                if (G == 32 && Vb == 0) continue;  // warp-uniform
+                FlatUnit fu = units[b & 31];
+                const bool conv_none = fu.bid_cents < 0;
+                fu.bid_cents &= 0x7FFFFFFF;
+                const int floor_c = kFloor ? s_floor[warp][b & 31] : 0;
+                unsigned cntIB = 0, cntS = 0, cst = 0;  // I | B << 16 ; S ; cost cents (< 2^32, see caps)
+                // one auction: competitor bid from `wc`, click + conversion from the single word `cc`
+                // (`bid` is 0 for a lane past the unit's end: no competitor bid is below it)
+                auto tally = [&](int bid, uint32_t wc, uint32_t cc) {
+                    int c = laplace_cents_smem(wc, fu.loc, fu.scale, s_tab);
+                    if (kFloor) c = max(c, floor_c);
+                    tally_counts(bid, c, cc, fu.thr_click, fu.thr_conv, cntIB, cntS, cst);
+                };
+                // full trips: each lane takes one Philox call = two consecutive auctions (2G per trip)
+                int base = 0;
+                for (; base + 2 * G <= Vb; base += 2 * G) {
+                    const uint4 w = philox_from_pre((uint32_t)((base >> 1) + gl), fu.n0, fu.n1, fu.x3, k0, k1);
+                    tally(fu.bid_cents, w.x, w.y);
+                    tally(fu.bid_cents, w.z, w.w);
+                }
+                const int rem = Vb - base;  // 0 .. 2G-1 auctions left
+                if (rem > G) {              // still worth pairing: lanes past the end idle
+                    const int j = base + 2 * gl;
+                    const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
+                    tally(j < Vb ? fu.bid_cents : 0, w.x, w.y);
+                    tally(j + 1 < Vb ? fu.bid_cents : 0, w.z, w.w);
+                } else if (rem > 0) {       // at most G left: one auction per lane, half a call each
+                    const int j = base + gl;
+                    const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
+                    tally(j < Vb ? fu.bid_cents : 0, (j & 1) ? w.z : w.x, (j & 1) ? w.w : w.y);
+                }
+                // the caps above keep every sum below 2^32 (I, B <= V < 2^16; cost <= V x bid)
+                const unsigned tIB = __reduce_add_sync(gmask, cntIB);
+                const unsigned tS = __reduce_add_sync(gmask, conv_none ? 0u : cntS);
+                const unsigned tC = __reduce_add_sync(gmask, cst);
+                if (G == 32) {
+                    if (lane == b) {
+                        I = (int)(tIB & 0xFFFFu); B = (int)(tIB >> 16); S = (int)tS;
+                        cost = (long long)tC;
+                    }
+                } else if (gl == 0 && b < cnt) {
+                    s_res[warp][b][0] = tIB;
+                    s_res[warp][b][1] = tS;
+                    s_res[warp][b][2] = tC;
+                }
+            }
+            if (G != 32) {
+                __syncwarp();
+                if (lane < cnt) {
+                    const unsigned ib = s_res[warp][lane][0];
+                    I = (int)(ib & 0xFFFFu); B = (int)(ib >> 16); S = (int)s_res[warp][lane][1];
+                    cost = (long long)s_res[warp][lane][2];
+                }
+            }
+
         }
 
         // ---------------- revenues: one draw per conversion, 4 per Philox call ----------------
@@ -800,11 +899,13 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
                 const FlatRev fr = revs[b];
                 const int blk = i - start[b];
                 const uint4 w = philox_from_pre((uint32_t)blk, fr.n0, fr.n1, fr.x3, k0, k1);
-                const int r0 = 4 * blk;
-                long long sum = revenue_cents(w.x, fr.mean, fr.sd);
-                if (r0 + 1 < fr.S) sum += revenue_cents(w.y, fr.mean, fr.sd);
-                if (r0 + 2 < fr.S) sum += revenue_cents(w.z, fr.mean, fr.sd);
-                if (r0 + 3 < fr.S) sum += revenue_cents(w.w, fr.mean, fr.sd);
+                // all four draws of the call are evaluated (their table loads overlap); the ones
+                // past the unit's last conversion are dropped
+                const int left = fr.S - 4 * blk;  // >= 1
+                const int c0 = revenue_cents(w.x, fr.mean, fr.sd), c1 = revenue_cents(w.y, fr.mean, fr.sd);
+                const int c2 = revenue_cents(w.z, fr.mean, fr.sd), c3 = revenue_cents(w.w, fr.mean, fr.sd);
+                const long long sum = (long long)c0 + (left > 1 ? c1 : 0) + (long long)(left > 2 ? c2 : 0) +
+                                      (left > 3 ? c3 : 0);
                 atomicAdd(&s_revsum[warp][b][0], (unsigned)(sum & 0xFFFFFF));
                 atomicAdd(&s_revsum[warp][b][1], (unsigned)(sum >> 24));
             }
@@ -832,10 +933,22 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
                 todo &= todo - 1;
                 const int ee = __shfl_sync(FULL, e, src);
                 const uint32_t ge = philox_env(a, ee);
-                for (int kk = lane; kk < K; kk += 32) {
-                    if (!drift_wanted(a, kk)) continue;
-                    const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)kk), ge, k0, k1);
-                    drift_apply(a, ee, kk, drift_from_words(a, w));
+                // two keywords per lane and trip, all of their loads in flight before the first
+                // store: the env's K keywords cost K / 64 DRAM round trips
+                for (int kk = lane; kk < K; kk += 64) {
+                    const int kb = kk + 32;
+                    const bool wa = drift_wanted(a, kk), wb = kb < K && drift_wanted(a, kb);
+                    DriftState sa = {0.0, 0.0, 0.0, 0.0}, sb = {0.0, 0.0, 0.0, 0.0};
+                    if (wa) sa = drift_load(a, ee, kk);
+                    if (wb) sb = drift_load(a, ee, kb);
+                    if (wa) {
+                        const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)kk), ge, k0, k1);
+                        drift_store(a, ee, kk, sa, drift_from_words(a, w));
+                    }
+                    if (wb) {
+                        const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)kb), ge, k0, k1);
+                        drift_store(a, ee, kb, sb, drift_from_words(a, w));
+                    }
                 }
             }
         }

@@ -184,9 +184,11 @@ class VectorBiddingSimulation:
         self.keywords = table
         self.kind = table.kind
         self._have_keywords = True
-        if self._auto_lanes:  # lanes per unit of the hot kernel from the mean daily volume
-            v = float(np.mean(table.vol_mean))
-            self.n_lanes = 0 if v >= 96 else (-16 if v >= 36 else -8)
+        if self._auto_lanes:
+            # 32 lanes per unit for every volume: since the hot kernel flattens the volume
+            # remainders across its 32-unit batch, sparse keyword sets no longer gain from the
+            # sub-warp variants (-16 / -8, kept for A/B runs)
+            self.n_lanes = 0
 
     def install_device_keywords(self, cols: Dict[str, torch.Tensor], kind: int = kwmod.IMPLICIT) -> None:
         """Use per-env keyword parameters that already live on the device ([E, K] float64 tensors,
