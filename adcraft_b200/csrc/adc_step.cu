@@ -664,7 +664,10 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     // the single-bidder instantiation
     __shared__ int s_floor[kFloor ? kFlatWarps : 1][32];
     __shared__ FlatUnit s_unit[kFlatWarps][32];
-    __shared__ __align__(16) unsigned s_res[kFlatWarps][32][4];  // per-unit sums handed to the owner lane
+    // per-unit sums handed to the owner lane.  G == 32 (flattened remainders): four copies per unit
+    // of {I | S << 8 | B << 16, cost} (a remainder has < 64 auctions), the lanes of a trip spread
+    // over the copies so that same-address atomics stay rare; G < 32: {I | B << 16, S, cost, -}
+    __shared__ __align__(16) unsigned s_res[kFlatWarps][32][G == 32 ? 8 : 4];
     __shared__ int s_vol[kFlatWarps][32];
     __shared__ FlatRev s_rev[kFlatWarps][32];
     __shared__ int s_start[kFlatWarps][33];
@@ -740,7 +743,10 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         }
         if (lane == 0) start[0] = 0;
         s_revsum[warp][lane][0] = 0u; s_revsum[warp][lane][1] = 0u;
-        if (G == 32) *reinterpret_cast<uint4 *>(s_res[warp][lane]) = make_uint4(0u, 0u, 0u, 0u);
+        if (G == 32) {
+            *reinterpret_cast<uint4 *>(&s_res[warp][lane][0]) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(&s_res[warp][lane][G == 32 ? 4 : 0]) = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncwarp();
 
         // ---------------- the batch's auctions: 32/G units at a time, G lanes per unit -----------
@@ -800,15 +806,17 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
                         unsigned cntIB = 0, cntS = 0, cst = 0;
                         flat_auction<kFloor>(fu.bid_cents, w.x, w.y, fu, floor_c, s_tab, cntIB, cntS, cst);
                         flat_auction<kFloor>(j + 1 < Vb ? fu.bid_cents : 0, w.z, w.w, fu, floor_c, s_tab, cntIB, cntS, cst);
-                        atomicAdd(&s_res[warp][b][0], cntIB);
-                        atomicAdd(&s_res[warp][b][1], conv_none ? 0u : cntS);
-                        atomicAdd(&s_res[warp][b][2], cst);
+                        unsigned *slot = &s_res[warp][b][2 * (lane & 3)];
+                        atomicAdd(slot, cntIB + (conv_none ? 0u : cntS << 8));
+                        atomicAdd(slot + 1, cst);
                     }
                 }
                 __syncwarp();
-                const uint4 r = *reinterpret_cast<const uint4 *>(s_res[warp][lane]);
-                I += (int)(r.x & 0xFFFFu); B += (int)(r.x >> 16); S += (int)r.y;
-                cost += (long long)r.z;
+                const uint4 r0 = *reinterpret_cast<const uint4 *>(&s_res[warp][lane][0]);
+                const uint4 r1 = *reinterpret_cast<const uint4 *>(&s_res[warp][lane][G == 32 ? 4 : 0]);
+                const unsigned cnts = r0.x + r0.z + r1.x + r1.z;  // fields < 64 each: no carries
+                I += (int)(cnts & 0xFFu); S += (int)((cnts >> 8) & 0xFFu); B += (int)(cnts >> 16);
+                cost += (long long)r0.y + r0.w + r1.y + r1.w;
             }
         } else {
             constexpr int NG = 32 / G;
