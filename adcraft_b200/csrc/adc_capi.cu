@@ -58,6 +58,9 @@ int validate(const adc_step_args *a, const adc_tape *tape)
                     a->scratch.env_cost && a->scratch.env_done, "scratch pointer is NULL");
     ADC_REQUIRE(a->kw.kind != ADC_EXPLICIT || a->scratch.unit_cost_f64 != nullptr,
                 "scratch.unit_cost_f64 is required for explicit keywords");
+    ADC_REQUIRE((a->scratch.acc_impressions != nullptr) == (a->scratch.acc_clicks != nullptr) &&
+                    (a->scratch.acc_clicks != nullptr) == (a->scratch.acc_conversions != nullptr),
+                "scratch.acc_impressions / acc_clicks / acc_conversions: give all three or none");
     ADC_REQUIRE(a->drift.mask == nullptr || a->kw.env_stride == a->kw.K,
                 "drift needs per-env keyword parameters (kw.env_stride == K)");
     ADC_REQUIRE(a->drift.mask == nullptr || (a->drift.num_updates >= 0 && a->drift.num_updates <= a->kw.K),

@@ -108,15 +108,20 @@ __device__ const float2 kNeglogTab[128] = {
 #include "adc_neglog_table.inc"
 };
 
-__device__ __forceinline__ float neglog_u31(uint32_t w31, const float2 *tab)
+__device__ __forceinline__ float neglog_norm(uint32_t a, const float2 *tab)
 {
-    const uint32_t a = 2u * w31 + 1u;
-    const int lz = __clz((int)a);
+    uint32_t lz;  // a is odd, so bfind.shiftamt (= clz for a != 0) is the normalising shift
+    asm("bfind.shiftamt.u32 %0, %1;" : "=r"(lz) : "r"(a));
     const uint32_t an = a << lz;
     const float2 ts = tab[(an >> 24) & 0x7Fu];
     const float lo = __uint2float_rn(an & 0x00FFFFFFu);
     const float inner = __fmaf_rn(-lo, ts.y, ts.x);
-    return __fmaf_rn(__int2float_rn(lz), kLn2f, inner);
+    return __fmaf_rn(__uint2float_rn(lz), kLn2f, inner);
+}
+
+__device__ __forceinline__ float neglog_u31(uint32_t w31, const float2 *tab)
+{
+    return neglog_norm(2u * w31 + 1u, tab);
 }
 
 // Standard normal from one word: sign bit + 31-bit two-sided tail probability t = (2*w31+1)/2^32
@@ -170,11 +175,15 @@ __device__ __forceinline__ double exp_det(double x)
     return __dmul_rn(p, s);
 }
 
+// 15 instructions: 2 * (w0 & 0x7FFFFFFF) + 1 (mod 2^32) as one multiply-add, the sign of the
+// Laplace branch XORed into the scale's sign bit.
 __device__ __forceinline__ int laplace_cents(uint32_t w0, float loc, float scale,
                                              const float2 *tab = kNeglogTab)
 {
-    const float e = neglog_u31(w0 & 0x7FFFFFFFu, tab);
-    const float s = (w0 >> 31) ? -scale : scale;
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(a) : "r"(w0));
+    const float e = neglog_norm(a, tab);
+    const float s = __uint_as_float(__float_as_uint(scale) ^ (w0 & 0x80000000u));
     const float x = __fmaf_rn(s, e, loc);
     return __float2int_rn(__fmul_rn(fabsf(x), 100.0f));
 }

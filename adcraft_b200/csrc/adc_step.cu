@@ -569,25 +569,6 @@ adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
 // kernel loses ~30 % of its lanes to it); only the last 32-auction trip of a unit has idle lanes.
 // Revenues are flattened across the batch (4 draws per Philox call).
 // ------------------------------------------------------------------------------------------
-// The hot loop's competitor bid: same value as laplace_cents (adc_rng.cuh) with the Exp(1) table
-// in shared memory, written so that it compiles to 15 instructions: 2w+1 as one multiply-add,
-// the normalising shift from bfind.shiftamt (= clz), the sign of the Laplace branch XORed into
-// the scale's sign bit.
-__device__ __forceinline__ int laplace_cents_smem(uint32_t w0, float loc, float scale, const float2 (&tab)[128])
-{
-    uint32_t a, lz;  // a = 2 * (w0 & 0x7FFFFFFF) + 1 (mod 2^32) as one multiply-add
-    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(a) : "r"(w0));
-    asm("bfind.shiftamt.u32 %0, %1;" : "=r"(lz) : "r"(a));
-    const uint32_t an = a << lz;
-    const float2 ts = tab[(an >> 24) & 0x7Fu];
-    const float lo = __uint2float_rn(an & 0x00FFFFFFu);
-    const float inner = __fmaf_rn(-lo, ts.y, ts.x);
-    const float e = __fmaf_rn(__uint2float_rn(lz), kLn2f, inner);
-    const float s = __uint_as_float(__float_as_uint(scale) ^ (w0 & 0x80000000u));
-    const float x = __fmaf_rn(s, e, loc);
-    return __float2int_rn(__fmul_rn(fabsf(x), 100.0f));
-}
-
 // win <=> bid > c; click <=> win && cc <= thr_click; conversion <=> click && cc <= thr_conv.
 // Three compares chained through their predicates and four predicated adds.
 __device__ __forceinline__ void tally_counts(int bid, int c, uint32_t cc, uint32_t thr_click, uint32_t thr_conv,
@@ -628,7 +609,7 @@ template <bool kFloor>
 __device__ __forceinline__ void flat_auction(int bid, uint32_t wc, uint32_t cc, const FlatUnit &fu, int floor_c,
                                              const float2 (&tab)[128], unsigned &cntIB, unsigned &cntS, unsigned &cst)
 {
-    int c = laplace_cents_smem(wc, fu.loc, fu.scale, tab);
+    int c = laplace_cents(wc, fu.loc, fu.scale, tab);
     if (kFloor) c = max(c, floor_c);
     tally_counts(bid, c, cc, fu.thr_click, fu.thr_conv, cntIB, cntS, cst);
 }
@@ -669,6 +650,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     // over the copies so that same-address atomics stay rare; G < 32: {I | B << 16, S, cost, -}
     __shared__ __align__(16) unsigned s_res[kFlatWarps][32][G == 32 ? 8 : 4];
     __shared__ int s_vol[kFlatWarps][32];
+    __shared__ unsigned char s_nzl[kFlatWarps][32];   // units of the batch that have a volume remainder
     __shared__ FlatRev s_rev[kFlatWarps][32];
     __shared__ int s_start[kFlatWarps][33];
     __shared__ unsigned s_revsum[kFlatWarps][32][2];  // 24-bit split: native 32-bit smem atomics
@@ -785,17 +767,23 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             {
                 const int npair = ((V & 63) + 1) >> 1;
                 const int incl_p = warp_incl_scan(npair, lane);
+                const bool nz = npair > 0;
+                const unsigned nzmask = __ballot_sync(FULL, nz);
+                if (nz) s_nzl[warp][__popc(nzmask & ((1u << lane) - 1u))] = (unsigned char)lane;
                 s_vol[warp][lane] = V;
-                start[lane + 1] = incl_p;
+                start[lane] = incl_p - npair;  // first call of unit `lane` (start[0] stays 0)
                 __syncwarp();
                 const int TP = __shfl_sync(FULL, incl_p, 31);
-                int pb0 = 0;
                 for (int base = 0; base < TP; base += 32) {
-                    while (start[pb0 + 1] <= base) ++pb0;
+                    // which unit does call base + lane belong to?  Every owner lane marks where its
+                    // unit's calls end inside this trip; a lane's unit is the r-th one with a
+                    // remainder, r = units that ended before the trip + marks at or below the lane
+                    const int rel = incl_p - base;
+                    const unsigned marks = __reduce_or_sync(FULL, (nz && rel > 0 && rel < 32) ? (1u << rel) : 0u);
+                    const int before = __popc(__ballot_sync(FULL, nz && rel <= 0));
                     const int i = base + lane;
                     if (i < TP) {
-                        int b = pb0;
-                        while (i >= start[b + 1]) ++b;
+                        const int b = s_nzl[warp][before + __popc(marks & (0xFFFFFFFFu >> (31 - lane)))];
                         FlatUnit fu = units[b];
                         const bool conv_none = fu.bid_cents < 0;
                         fu.bid_cents &= 0x7FFFFFFF;
@@ -835,7 +823,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
                 // one auction: competitor bid from `wc`, click + conversion from the single word `cc`
                 // (`bid` is 0 for a lane past the unit's end: no competitor bid is below it)
                 auto tally = [&](int bid, uint32_t wc, uint32_t cc) {
-                    int c = laplace_cents_smem(wc, fu.loc, fu.scale, s_tab);
+                    int c = laplace_cents(wc, fu.loc, fu.scale, s_tab);
                     if (kFloor) c = max(c, floor_c);
                     tally_counts(bid, c, cc, fu.thr_click, fu.thr_conv, cntIB, cntS, cst);
                 };
@@ -1668,12 +1656,39 @@ adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant_
 // ------------------------------------------------------------------------------------------
 // exact serial kernel: one thread per queued env, (sub-step, keyword, click) order, shared budget
 // ------------------------------------------------------------------------------------------
+// Running day counts of the exact serial kernels: in the outputs themselves, or -- when the
+// caller provides adc_scratch.acc_* (outputs in mapped host memory, where a read-modify-write
+// would cross PCIe every sub-step) -- in device scratch, stored to the outputs once per env.
+struct SerCounts {
+    int32_t *I, *B, *S;
+};
+
+__device__ __forceinline__ SerCounts ser_counts(const adc_step_args &a)
+{
+    SerCounts c;
+    const bool own = a.scratch.acc_impressions != nullptr;
+    c.I = own ? a.scratch.acc_impressions : a.out.impressions;
+    c.B = own ? a.scratch.acc_clicks : a.out.clicks;
+    c.S = own ? a.scratch.acc_conversions : a.out.conversions;
+    return c;
+}
+
+__device__ __forceinline__ void ser_publish(const adc_step_args &a, const SerCounts &c, int64_t u)
+{
+    if (c.I != a.out.impressions) {
+        a.out.impressions[u] = c.I[u];
+        a.out.clicks[u] = c.B[u];
+        a.out.conversions[u] = c.S[u];
+    }
+}
+
 template <typename Src>
 __global__ void __launch_bounds__(64)
 adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant__ adc_tape tape)
 {
     const int K = a.kw.K;
     const int count = a.scratch.serial_count[a.step & 1u];
+    const SerCounts acc = ser_counts(a);
     const bool explicit_kw = a.kw.kind == ADC_EXPLICIT;
     const int stride = gridDim.x * blockDim.x;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += stride) {
@@ -1689,9 +1704,9 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
         }
         for (int k = 0; k < K; ++k) {
             const int64_t u = (int64_t)e * K + k;
-            a.out.impressions[u] = 0;
-            a.out.clicks[u] = 0;
-            a.out.conversions[u] = 0;
+            acc.I[u] = 0;
+            acc.B[u] = 0;
+            acc.S[u] = 0;
             a.out.cost_cents[u] = 0;
             a.out.revenue_cents[u] = 0;
             if (explicit_kw) a.scratch.unit_cost_f64[u] = 0.0;
@@ -1715,10 +1730,10 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
                 const long long n = t == 0 ? n0 : q;
                 UnitCur cur;
                 cur.auction = t == 0 ? 0 : n0 + (long long)(t - 1) * q;
-                cur.n_conv = a.out.clicks[u];
-                cur.n_rev = a.out.conversions[u];
-                cur.n_cost = a.out.impressions[u];
-                cur.n_click = a.out.impressions[u];
+                cur.n_conv = acc.B[u];
+                cur.n_rev = acc.S[u];
+                cur.n_cost = acc.I[u];
+                cur.n_click = acc.I[u];
                 if (explicit_kw) {
                     if constexpr (Src::kTape) {  // one slot per impression, or one phantom slot
                         int s = 0;
@@ -1740,13 +1755,13 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
                     o = lane_walk<Src, false, true>(src, &tape, u, k, t, n, p, cur, b, unused, det);
                 }
                 if (det != nullptr) {
-                    const int nb = a.out.clicks[u] + o.B;
+                    const int nb = acc.B[u] + o.B;
                     det->n_recorded[u] = nb < det->cap ? nb : det->cap;
                     if (o.I >= 1) det->volume_seen[u] += (double)n;  // bsim:130-137
                 }
-                a.out.impressions[u] += o.I;
-                a.out.clicks[u] += o.B;
-                a.out.conversions[u] += o.S;
+                acc.I[u] += o.I;
+                acc.B[u] += o.B;
+                acc.S[u] += o.S;
                 a.out.cost_cents[u] += o.cost_cents;
                 a.out.revenue_cents[u] += o.rev_cents;
                 if (a.budget_alias) remaining = b;                    // bsim:102 on an aliased ndarray
@@ -1763,6 +1778,7 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
             const int64_t u = (int64_t)e * K + k;
             const double rv = cents_to_dollars(a.out.revenue_cents[u]);
             store_f(a.out.revenue, a.out.float_dtype, u, rv);
+            ser_publish(a, acc, u);
             if (explicit_kw) {
                 const double c = a.scratch.unit_cost_f64[u];
                 store_f(a.out.cost, a.out.float_dtype, u, c);
@@ -1829,7 +1845,11 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
     __shared__ uint32_t s_slot[kSerWarps][kSerCap][32];
     __shared__ SerUnit s_unit[kSerWarps][kSerCacheK];
     __shared__ SerAcc s_acc[kSerWarps][kSerUseAcc ? kSerCacheK : 1];
+    __shared__ float2 s_tab[128];  // Exp(1) sampler table, staged from global
+    if (threadIdx.x < 128) s_tab[threadIdx.x] = kNeglogTab[threadIdx.x];
+    __syncthreads();
     const int K = a.kw.K;
+    const SerCounts acc = ser_counts(a);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto slot_cost = [&](int i, int l) { return (int)(s_slot[warp][i][l] & 0x7FFFFFFFu); };
     const int gwarp = blockIdx.x * kSerWarps + warp;
@@ -1857,9 +1877,9 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
         PhiloxSrc src{k0, k1, a.step, philox_env(a, e)};
         for (int k = lane; k < K; k += 32) {
             const int64_t u = (int64_t)e * K + k;
-            a.out.impressions[u] = 0;
-            a.out.clicks[u] = 0;
-            a.out.conversions[u] = 0;
+            acc.I[u] = 0;
+            acc.B[u] = 0;
+            acc.S[u] = 0;
             a.out.cost_cents[u] = 0;
             a.out.revenue_cents[u] = 0;
             if (k < kSerCacheK) {
@@ -1905,7 +1925,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                             const int j = 2 * cidx + h;
                             if (j < ji || j >= j_end) continue;
                             const uint32_t cc = h ? w.w : w.y;
-                            const int c = max(laplace_cents(h ? w.z : w.x, su.loc, su.scale), su.floor_cents);
+                            const int c = max(laplace_cents(h ? w.z : w.x, su.loc, su.scale, s_tab), su.floor_cents);
                             if (su.bid_cents > c) {
                                 ++I;
                                 if (cc <= su.thr_click) {
@@ -1991,7 +2011,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                             p.rev_mean = su.rev_mean; p.rev_sd = su.rev_sd; p.thr_click = su.thr_click; p.thr_cc = su.thr_cc;
                             p.conv_all = (su.flags & 1) != 0; p.bid = 0.0; p.ctr = 0.0; p.cvr = 0.0; p.thr_conv = 0; p.thr_impr = 0;
                             double b = remaining, unused = 0.0;
-                            UnitCur cur = {j0, 0, 0, kSerUseAcc && k < kSerCacheK ? s_acc[warp][k].S : a.out.conversions[u], 0};
+                            UnitCur cur = {j0, 0, 0, kSerUseAcc && k < kSerCacheK ? s_acc[warp][k].S : acc.S[u], 0};
                             const LaneOut o = lane_walk<PhiloxSrc, false, true>(src, no_tape, u, k, t, n, p, cur, b, unused);
                             B = o.B; S = o.S; cost_c = o.cost_cents; rev_c = o.rev_cents;
                             rev_done = true;
@@ -2015,7 +2035,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                             S += (int)(sl >> 31);
                         }
                         if (S > 0) {
-                            const int r0 = kSerUseAcc && k < kSerCacheK ? s_acc[warp][k].S : a.out.conversions[u];
+                            const int r0 = kSerUseAcc && k < kSerCacheK ? s_acc[warp][k].S : acc.S[u];
                             uint4 rw = make_uint4(0, 0, 0, 0);
                             for (int i = 0; i < S; ++i) {
                                 const int r = r0 + i;
@@ -2030,9 +2050,9 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                         ac.I += I; ac.B += B; ac.S += S; ac.cost += cost_c; ac.rev += rev_c;
                         s_acc[warp][k] = ac;
                     } else {
-                        a.out.impressions[u] += I;
-                        a.out.clicks[u] += B;
-                        a.out.conversions[u] += S;
+                        acc.I[u] += I;
+                        acc.B[u] += B;
+                        acc.S[u] += S;
                         a.out.cost_cents[u] += cost_c;
                         a.out.revenue_cents[u] += rev_c;
                     }
@@ -2057,6 +2077,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
             const long long cc = a.out.cost_cents[u], rc = a.out.revenue_cents[u];
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cc));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rc));
+            if (!kSerUseAcc || k >= kSerCacheK) ser_publish(a, acc, u);
             profit_c += rc - cc;
         }
 #pragma unroll

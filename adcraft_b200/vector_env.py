@@ -449,12 +449,17 @@ class VectorBiddingSimulation:
                 "cumulative_profit", "days_passed", "terminated", "truncated"))
         (out.impressions, out.clicks, out.conversions, out.cost, out.revenue, out.reward,
          out.obs_cum_profit, out.obs_days, out.terminated, out.truncated) = self._host_ptrs
+        # the exact serial walk keeps its running counts in the (otherwise idle) device observation
+        # arrays instead of read-modify-writing host memory across PCIe
+        sc = a.scratch
+        sc.acc_impressions, sc.acc_clicks, sc.acc_conversions = saved[0], saved[1], saved[2]
         stream = torch.cuda.current_stream(self.device)
         try:
             _capi.check(self._lib.adc_step_philox(C.byref(a), C.c_void_p(stream.cuda_stream)))
         finally:
             (out.impressions, out.clicks, out.conversions, out.cost, out.revenue, out.reward,
              out.obs_cum_profit, out.obs_days, out.terminated, out.truncated) = saved
+            sc.acc_impressions = sc.acc_clicks = sc.acc_conversions = None
         self._step_count += 1
         stream.synchronize()
         return self._host_views()

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define ADC_ABI_VERSION 2
+#define ADC_ABI_VERSION 3
 #define ADC_SUBSTEPS 24 /* adcraft/bidding_simulation.py:213 */
 
 typedef enum adc_status {
@@ -119,6 +119,14 @@ typedef struct adc_scratch {
     int64_t *env_cost;      /* [E] per-env cost cents accumulator,   0 on entry and on exit */
     int32_t *env_done;      /* [E] finished-unit counter,            0 on entry and on exit */
     double *unit_cost_f64;  /* [E,K] explicit keywords only: un-rounded cost sums (else NULL) */
+    /* Optional (all three or none), [E,K] DEVICE memory: running impressions / clicks / conversions
+     * of the exact serial walk.  NULL: the walk read-modify-writes out.impressions / clicks /
+     * conversions themselves, which is fine for device outputs; with outputs in mapped host memory
+     * every sub-step would cross PCIe twice, so give the walk device scratch here and it stores the
+     * day's totals to the outputs once per env. */
+    int32_t *acc_impressions;
+    int32_t *acc_clicks;
+    int32_t *acc_conversions;
 } adc_scratch;
 
 /* Optional per-click detail (the ragged lists of BiddingOutcomes, bidding_simulation.py:10-38, that

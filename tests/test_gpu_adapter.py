@@ -87,14 +87,17 @@ def test_device_metrics_against_host_definitions():
     assert s["n_envs"] == E
 
 
-def test_step_host_zero_copy_equals_staged_copy():
-    """The fused (UVA zero-copy) host round trip returns exactly what the staged one returns."""
+@pytest.mark.parametrize("K,E,budget", [(33, 70, 60.0), (120, 9, 150.0), (20, 40, 1e6)])
+def test_step_host_zero_copy_equals_staged_copy(K, E, budget):
+    """The fused (UVA zero-copy) host round trip returns exactly what the staged one returns --
+    with binding budgets too, where the exact serial walk keeps its running counts in device
+    scratch (adc_scratch.acc_*) instead of the host-mapped outputs; K = 120 is beyond the serial
+    kernel's shared-memory keyword cache."""
     from adcraft_b200 import keywords as kwm
     from adcraft_b200.vector_env import VectorBiddingSimulation
     rng = np.random.default_rng(8)
-    K, E = 33, 70
     table = kwm.sample_implicit_keywords_from_quantiles(K, rng, {"mean_volume": 64, "conversion_rate": 0.8})
-    mk = lambda: VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=60.0, device="cuda", seed=4,
+    mk = lambda: VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=budget, device="cuda", seed=4,
                                          max_days=2)
     a, b = mk(), mk()
     a.reset(); b.reset()
