@@ -54,7 +54,7 @@ class Scratch(C.Structure):
     _fields_ = [
         ("serial_list", C.c_void_p), ("serial_count", C.c_void_p), ("env_profit", C.c_void_p),
         ("env_cost", C.c_void_p), ("env_done", C.c_void_p), ("unit_cost_f64", C.c_void_p),
-        ("acc_impressions", C.c_void_p), ("acc_clicks", C.c_void_p), ("acc_conversions", C.c_void_p),
+        ("work_counter", C.c_void_p), ("acc_impressions", C.c_void_p), ("acc_clicks", C.c_void_p), ("acc_conversions", C.c_void_p),
     ]
 
 

@@ -79,6 +79,15 @@ __device__ __forceinline__ bool budget_is_safe(double budget, double spend, int 
     return s + 0.005 + 1e-7 * fabs(budget) + 1e-9 * s < budget;
 }
 
+// The serial queue length and the hot kernel's work counter are double-buffered on the step
+// parity: every first-stage kernel of a step zeroes the copies the NEXT step will use, so no
+// reset launch is needed (the previous step, the last user of those copies, has completed).
+__device__ __forceinline__ void reset_next_counters(const adc_step_args &a)
+{
+    a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
+    if (a.scratch.work_counter != nullptr) a.scratch.work_counter[(a.step & 1u) ^ 1u] = 0u;
+}
+
 struct Drift3 {
     double c[3];
 };
@@ -474,7 +483,7 @@ adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     // the serial-queue counter is double-buffered on the step parity: this step appends to
     // [step&1]; the other one (read by the previous step's serial kernel) is cleared here.
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) reset_next_counters(a);
 
     for (int64_t it = 0; it < iters; ++it) {
         const int64_t u = it * n_groups + group;
@@ -614,6 +623,38 @@ __device__ __forceinline__ void flat_auction(int bid, uint32_t wc, uint32_t cc, 
     tally_counts(bid, c, cc, fu.thr_click, fu.thr_conv, cntIB, cntS, cst);
 }
 
+// The hot kernel's work list: pull index -> a chunk of consecutive batches (see the kernel).
+// Big batches of 32 units first: all but two small batches per warp when the warps pull
+// dynamically, whole static rounds otherwise; then the rest in small batches of kFlatTail units.
+// A dynamic pull hands out up to 16 big batches (large steps: one pull per batch would be several
+// 10^5 atomics on one address per millisecond) while every warp still makes >= 8 pulls.
+// Kept out of line: its loop-invariant terms would otherwise occupy registers of the hot loops.
+constexpr int kFlatTail = 8;
+
+struct FlatChunk {
+    int64_t u0;  // first unit of the next batch
+    int cnt;     // units per batch (32 or kFlatTail)
+    int left;    // batches left in the chunk (0: no more work)
+};
+
+__device__ __noinline__ FlatChunk flat_chunk(int64_t total, int64_t n_warps, bool dynamic, int64_t pi)
+{
+    const int64_t n_big = dynamic ? max((int64_t)0, total - 2 * kFlatTail * n_warps) / 32
+                                  : total / (32 * n_warps) * n_warps;
+    const int64_t n_small = (total - n_big * 32 + kFlatTail - 1) / kFlatTail;
+    const int64_t chunk = dynamic ? min((int64_t)16, max((int64_t)1, n_big / (8 * n_warps))) : 1;
+    const int64_t n_chunks = (n_big + chunk - 1) / chunk;
+    FlatChunk c;
+    c.u0 = 0; c.cnt = 0; c.left = 0;
+    if (pi < n_chunks) {
+        const int64_t b = pi * chunk;
+        c.u0 = b * 32; c.cnt = 32; c.left = (int)min(chunk, n_big - b);
+    } else if (pi - n_chunks < n_small) {
+        c.u0 = n_big * 32 + (pi - n_chunks) * kFlatTail; c.cnt = kFlatTail; c.left = 1;
+    }
+    return c;
+}
+
 constexpr int kFlatWarps = 8;
 // Caps of the fast kernel's 16/32-bit lane accumulators; a unit beyond them sends its env to the
 // exact serial kernel instead (volumes and bids this large do not occur in the reference's configs).
@@ -631,13 +672,10 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
     return v;
 }
 
-// kBU = units per batch (lanes >= kBU idle during the lane<->unit phases, which are a few percent
-// of the work): small batches mean many more work items than warps, so the last round of the
-// grid-stride loop is nearly full (a 4096 x 100 step is only 2.7 batches of 32 per resident warp).
-// G = lanes that share one unit's auctions (32, 16 or 8): with G < 32 the warp walks 32/G units at
-// a time, which keeps the lanes busy for sparse keywords (a 16-auction day fills a 32-lane trip
-// only half, and the trip's Philox calls a quarter).
-template <int kBU, int G, bool kFloor>
+// G = lanes that share one unit's auctions.  32: full 64-auction trips one unit at a time, the
+// volume remainders of the whole batch flattened (best for every volume since the flattening);
+// 16 / 8: the warp walks 32/G units side by side (kept for A/B runs).
+template <int G, bool kFloor>
 __global__ void __launch_bounds__(kFlatWarps * 32)
 adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
 {
@@ -663,28 +701,45 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gwarp = (int64_t)blockIdx.x * kFlatWarps + warp;
     const int64_t n_warps = (int64_t)gridDim.x * kFlatWarps;
-    // Work items: R full rounds of kBU-unit batches (every warp gets exactly R of them), then the
-    // remaining units in small batches of kTail units, dealt round-robin.  The small batches cost a
-    // little more per unit (the lane<->unit phases run at kTail/32 lane efficiency) but they even
-    // out the end of the kernel: a 4096 x 100 step is only 2.7 big batches per resident warp.
-    constexpr int kTail = 8;
-    const int64_t big_rounds = total / ((int64_t)kBU * n_warps);
-    const int64_t n_big = big_rounds * n_warps;
-    const int64_t tail_units = total - n_big * kBU;
-    const int64_t n_batches = n_big + (tail_units + kTail - 1) / kTail;
+    // Work items: 32-unit batches first, then small batches of kFlatTail units (they cost ~20 %
+    // more per unit -- the lane<->unit phases run at 8/32 lane efficiency -- but even out the end
+    // of the kernel: a 4096 x 100 step is only 2.7 big batches per resident warp).
+    // With scratch.work_counter the warps pull their work from an atomic counter (the next pull is
+    // requested while the current chunk runs): a warp that was held up -- the last finisher of an
+    // env runs the env tail and the drift of its K keywords -- simply takes fewer items, where a
+    // static deal makes it the last finisher of every later env it touches.  Two small batches
+    // per warp are then enough to level the end.  Without the counter: static rounds.
+    const bool dynamic = a.scratch.work_counter != nullptr && total < (1LL << 34);  // 32-bit pull indices
+    uint32_t *const work = a.scratch.work_counter + (a.step & 1u);
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const unsigned FULL = 0xFFFFFFFFu;
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) reset_next_counters(a);
 
     FlatUnit *units = s_unit[warp];
     FlatRev *revs = s_rev[warp];
     int *start = s_start[warp];
 
-    for (int64_t batch = gwarp; batch < n_batches; batch += n_warps) {
+    auto pull = [&]() -> uint32_t { return lane == 0 ? atomicAdd(work, 1u) : 0u; };
+    uint32_t pulled = dynamic ? pull() : 0u;
+    int64_t static_pull = gwarp;
+    FlatChunk ck;
+    ck.u0 = 0; ck.cnt = 0; ck.left = 0;
+    for (;;) {
+        if (ck.left == 0) {
+            int64_t pi = static_pull;
+            static_pull += n_warps;
+            if (dynamic) {
+                pi = (int64_t)__shfl_sync(FULL, pulled, 0);
+                pulled = pull();
+            }
+            ck = flat_chunk(total, n_warps, dynamic, pi);
+            if (ck.left == 0) break;
+        }
+        --ck.left;
         // ---------------- per-unit setup, lane <-> unit ----------------
-        const bool big = batch < n_big;
-        const int cnt = big ? kBU : kTail;
-        const int64_t u = (big ? batch * kBU : n_big * kBU + (batch - n_big) * kTail) + lane;
+        const int cnt = ck.cnt;
+        const int64_t u = ck.u0 + lane;
+        ck.u0 += cnt;
         const bool valid = lane < cnt && u < total;
         int e = 0, k = 0, V = 0;
         bool over_cap = false;
@@ -996,7 +1051,7 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
     const int64_t n_batches = (total + 31) / 32;
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lt = (1u << lane) - 1u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) reset_next_counters(a);
     ReplayUnit *units = s_unit[warp];
 
     for (int64_t batch = gwarp; batch < n_batches; batch += n_warps) {
@@ -1428,7 +1483,7 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
     const int64_t u_begin = (total / n_warps) * gwarp + min(gwarp, total % n_warps);
     const int64_t u_end = u_begin + total / n_warps + (gwarp < total % n_warps ? 1 : 0);
     const unsigned FULL = 0xFFFFFFFFu;
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) reset_next_counters(a);
 
     PkUnit *units = s_unit[warp];
     unsigned char *ring = pk_buf + (size_t)warp * kRing;
@@ -1589,7 +1644,7 @@ adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant_
     const int K = a.kw.K;
     const int64_t total = (int64_t)a.E * K;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) reset_next_counters(a);
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += stride) {
         const int e = (int)(u / K);
         const int k = (int)(u - (int64_t)e * K);
@@ -2184,13 +2239,13 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     if (tape == nullptr && !explicit_kw && a.n_lanes <= 0) {
         const int block = kFlatWarps * 32;
         int per_sm = 0;
-        constexpr int kBU = 32;  // 8 and 16 were measured slower: the lane<->unit phases lose more than the tail gains
-        // n_lanes: 0 / -32 -> 32 lanes per unit (dense keywords), -16, -8 -> sub-warp groups (sparse)
+        constexpr int kBU = 32;  // units per big batch
+        // n_lanes: 0 / -32 -> 32 lanes per unit, -16, -8 -> sub-warp groups (A/B)
         const bool fl = a.floor_cents != nullptr;
         void (*kern)(adc_step_args) =
-            a.n_lanes == -8    ? (fl ? adc_flat_philox_implicit_kernel<kBU, 8, true> : adc_flat_philox_implicit_kernel<kBU, 8, false>)
-            : a.n_lanes == -16 ? (fl ? adc_flat_philox_implicit_kernel<kBU, 16, true> : adc_flat_philox_implicit_kernel<kBU, 16, false>)
-                               : (fl ? adc_flat_philox_implicit_kernel<kBU, 32, true> : adc_flat_philox_implicit_kernel<kBU, 32, false>);
+            a.n_lanes == -8    ? (fl ? adc_flat_philox_implicit_kernel<8, true> : adc_flat_philox_implicit_kernel<8, false>)
+            : a.n_lanes == -16 ? (fl ? adc_flat_philox_implicit_kernel<16, true> : adc_flat_philox_implicit_kernel<16, false>)
+                               : (fl ? adc_flat_philox_implicit_kernel<32, true> : adc_flat_philox_implicit_kernel<32, false>);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
         if (per_sm < 1) per_sm = 1;
         int64_t grid = (int64_t)num_sms() * per_sm;

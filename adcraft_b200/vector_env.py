@@ -135,7 +135,8 @@ class VectorBiddingSimulation:
             cum_profit=z(E, dtype=f64), day=z(E, dtype=i32))
         self._scratch = dict(
             serial_list=z(E, dtype=i32), serial_count=z(2, dtype=i32), env_profit=z(E, dtype=i64),
-            env_cost=z(E, dtype=i64), env_done=z(E, dtype=i32), unit_cost_f64=z(E, K, dtype=f64))
+            env_cost=z(E, dtype=i64), env_done=z(E, dtype=i32), unit_cost_f64=z(E, K, dtype=f64),
+            work_counter=z(2, dtype=i32))
         self._detail = None
         if self.detail_cap > 0:
             c = self.detail_cap
@@ -357,7 +358,8 @@ class VectorBiddingSimulation:
         out.terminated, out.truncated = o["terminated"].data_ptr(), o["truncated"].data_ptr()
         out.remaining_budget = o["remaining_budget"].data_ptr()
         sc = a.scratch
-        for n in ("serial_list", "serial_count", "env_profit", "env_cost", "env_done", "unit_cost_f64"):
+        for n in ("serial_list", "serial_count", "env_profit", "env_cost", "env_done", "unit_cost_f64",
+                  "work_counter"):
             setattr(sc, n, s[n].data_ptr())
         if self._detail is not None:
             a.detail.cap = self.detail_cap

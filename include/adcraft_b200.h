@@ -124,6 +124,10 @@ typedef struct adc_scratch {
      * conversions themselves, which is fine for device outputs; with outputs in mapped host memory
      * every sub-step would cross PCIe twice, so give the walk device scratch here and it stores the
      * day's totals to the outputs once per env. */
+    /* Optional [2] DEVICE words, both 0 before the first step (double-buffered on the step parity
+     * like serial_count): with it the hot kernel's warps pull their batches from an atomic
+     * counter instead of a static round-robin deal (results are identical either way). */
+    uint32_t *work_counter;
     int32_t *acc_impressions;
     int32_t *acc_clicks;
     int32_t *acc_conversions;
