@@ -624,8 +624,8 @@ __device__ __forceinline__ void flat_auction(int bid, uint32_t wc, uint32_t cc, 
 }
 
 // The hot kernel's work list: pull index -> a chunk of consecutive batches (see the kernel).
-// Big batches of 32 units first: all but two small batches per warp when the warps pull
-// dynamically, whole static rounds otherwise; then the rest in small batches of kFlatTail units.
+// Big batches of 32 units first: as many as there are when the warps pull dynamically, whole
+// static rounds otherwise; then the rest in small batches of kFlatTail units.
 // A dynamic pull hands out up to 16 big batches (large steps: one pull per batch would be several
 // 10^5 atomics on one address per millisecond) while every warp still makes >= 8 pulls.
 // Kept out of line: its loop-invariant terms would otherwise occupy registers of the hot loops.
@@ -639,7 +639,7 @@ struct FlatChunk {
 
 __device__ __noinline__ FlatChunk flat_chunk(int64_t total, int64_t n_warps, bool dynamic, int64_t pi)
 {
-    const int64_t n_big = dynamic ? max((int64_t)0, total - 2 * kFlatTail * n_warps) / 32
+    const int64_t n_big = dynamic ? total / 32
                                   : total / (32 * n_warps) * n_warps;
     const int64_t n_small = (total - n_big * 32 + kFlatTail - 1) / kFlatTail;
     const int64_t chunk = dynamic ? min((int64_t)16, max((int64_t)1, n_big / (8 * n_warps))) : 1;
@@ -701,14 +701,14 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gwarp = (int64_t)blockIdx.x * kFlatWarps + warp;
     const int64_t n_warps = (int64_t)gridDim.x * kFlatWarps;
-    // Work items: 32-unit batches first, then small batches of kFlatTail units (they cost ~20 %
-    // more per unit -- the lane<->unit phases run at 8/32 lane efficiency -- but even out the end
-    // of the kernel: a 4096 x 100 step is only 2.7 big batches per resident warp).
-    // With scratch.work_counter the warps pull their work from an atomic counter (the next pull is
-    // requested while the current chunk runs): a warp that was held up -- the last finisher of an
-    // env runs the env tail and the drift of its K keywords -- simply takes fewer items, where a
-    // static deal makes it the last finisher of every later env it touches.  Two small batches
-    // per warp are then enough to level the end.  Without the counter: static rounds.
+    // Work items: batches of 32 units.  With scratch.work_counter the warps pull them from an
+    // atomic counter (the next pull is requested while the current chunk runs): a warp that was
+    // held up -- the last finisher of an env runs the env tail and the drift of its K keywords --
+    // simply takes fewer items, where a static deal makes it the last finisher of every later env
+    // it touches; and the end of the kernel levels itself (a 4096 x 100 step is only 2.7 batches
+    // per resident warp; small batches at the end were measured slower than none: their
+    // lane<->unit phases run at 8/32 lane efficiency).  Without the counter: static rounds of
+    // 32-unit batches, then the remainder in 8-unit batches dealt round-robin.
     const bool dynamic = a.scratch.work_counter != nullptr && total < (1LL << 34);  // 32-bit pull indices
     uint32_t *const work = a.scratch.work_counter + (a.step & 1u);
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);

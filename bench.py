@@ -42,8 +42,8 @@ PY_REFERENCE_UNITS_PER_S_1CORE = 290.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one hot-kernel launch on this workload, from the
 # committed `ncu --set full` capture (profiles/r01_flat_kernel_ncu_metrics.csv): the outputs stay in
 # the 126 MB L2 between steps, so DRAM traffic is below the 9.8 MB of algorithmic bytes.
-NCU_DRAM_BYTES_PER_LAUNCH = 1854976 + 7168
-NCU_WARP_INSTR_PER_LAUNCH = 198579293  # smsp__inst_executed.sum of the same capture
+NCU_DRAM_BYTES_PER_LAUNCH = 1881600 + 5888
+NCU_WARP_INSTR_PER_LAUNCH = 138705777  # smsp__inst_executed.sum of the same capture
 
 
 MEAN_VOLUME, CVR, DRIFT = 128, 0.8, False
