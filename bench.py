@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's banner / debug lines (printed to stdout by default
+# when the box sets NCCL_DEBUG) go to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "keyword_auction_steps_per_sec"
 UNIT = "keyword-auction-steps/s"
@@ -527,7 +530,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-replay", action="store_true", help="skip the tape-driven (replay) leg")
     ap.add_argument("--replay-only", action="store_true", help="profiling aid: run only the replay leg")
-    ap.add_argument("--budget", type=float, default=100000.0, help="experiment only: per-day budget (default C2's 100000)")
+    ap.add_argument("--budget", type=float, default=None,
+                    help="experiment only: per-day budget (default C2's 100000, scaled by keywords / 100 so that "
+                         "larger keyword sets stay on the budget-free path like C2 does)")
     ap.add_argument("--keywords", type=int, default=100, help="experiment only (C3: 1000)")
     ap.add_argument("--volume", type=int, default=128, help="experiment only: mean volume (C3: 16 / 64)")
     ap.add_argument("--cvr", type=float, default=0.8, help="experiment only: conversion rate (C3: 0.1)")
@@ -541,7 +546,7 @@ def main():
                     help="experiment only: bidders per shared auction (BASELINE config 4: --agents 8 --envs 65536)")
     args = ap.parse_args()
     E_ENVS = args.envs
-    BUDGET = args.budget
+    BUDGET = args.budget if args.budget is not None else 100000.0 * max(1.0, args.keywords / 100.0)
     K_KW, MEAN_VOLUME, CVR, DRIFT = args.keywords, args.volume, args.cvr, args.drift
     if args.impl == "reference":
         return run_reference(args)
