@@ -60,6 +60,7 @@ class VectorBiddingSimulation:
         autoreset: bool = True,
         detail_cap: int = 0,
         env_group: int = 0,
+        dynamic_work: bool = True,
         **kwargs,
     ) -> None:
         assert render_mode is None or render_mode in self.metadata["render_modes"], (
@@ -90,6 +91,9 @@ class VectorBiddingSimulation:
         # > 1: consecutive groups of env_group envs are the bidders of ONE auction world and share
         # every draw (see adc_step_args.env_group and multi_agent.SharedAuctionSimulation)
         self.env_group = int(env_group)
+        # False: no adc_scratch.work_counter, the hot kernel deals its batches statically (A/B and
+        # tests; results are identical either way)
+        self.dynamic_work = bool(dynamic_work)
         assert self.env_group <= 1 or self.num_envs % self.env_group == 0
         self.shared_keywords = bool(shared_keywords)
         self.obs_dtype = obs_dtype
@@ -358,9 +362,9 @@ class VectorBiddingSimulation:
         out.terminated, out.truncated = o["terminated"].data_ptr(), o["truncated"].data_ptr()
         out.remaining_budget = o["remaining_budget"].data_ptr()
         sc = a.scratch
-        for n in ("serial_list", "serial_count", "env_profit", "env_cost", "env_done", "unit_cost_f64",
-                  "work_counter"):
+        for n in ("serial_list", "serial_count", "env_profit", "env_cost", "env_done", "unit_cost_f64"):
             setattr(sc, n, s[n].data_ptr())
+        sc.work_counter = s["work_counter"].data_ptr() if self.dynamic_work else None
         if self._detail is not None:
             a.detail.cap = self.detail_cap
             for n in ("costs", "rev_per_cost", "n_recorded", "volume_seen"):

@@ -154,6 +154,29 @@ def test_sharding_invariance(orc):
         assert torch.equal(of[k], torch.cat([ol[k], oh[k]])), k
 
 
+def test_work_list_static_equals_dynamic(orc):
+    """The hot kernel's work list: batches pulled from the atomic counter (adc_scratch.work_counter,
+    one batch per pull on small steps, chunks of several batches on large ones) or dealt statically
+    (no counter: full rounds + small tail batches) -- identical results, step after step, and the
+    small case equals the oracle.  Shapes are not multiples of the batch size."""
+    rng = np.random.default_rng(21)
+    for K, E, steps in ((7, 45, 3), (301, 8200, 2)):   # 315 units; 2.47 M units (chunked pulls)
+        table = make_implicit_table(rng, K, 40)
+        bids = torch.from_numpy(np.round(rng.uniform(0.2, 1.5, (E, K)), 2)).cuda()
+        dyn = _env(table, E, seed=5, budget=1e9)
+        sta = _env(table, E, seed=5, budget=1e9, dynamic_work=False)
+        ob = _oracle_batch(orc, table, E, seed=5, budget=1e9) if E < 100 else None
+        for _ in range(steps):
+            od, rd, td, ud, _i = dyn.step({"keyword_bids": bids})
+            os_, rs, ts, us, _i = sta.step({"keyword_bids": bids})
+            for k in od:
+                assert torch.equal(od[k], os_[k]), (k, K, E)
+            assert torch.equal(rd, rs) and torch.equal(td, ts) and torch.equal(ud, us)
+            if ob is not None:
+                _compare(od, rd, td, ud, ob.step(bids.cpu().numpy(), n_threads=2), dyn, RTOL32)
+        assert int(od["impressions"].sum()) > 0
+
+
 def test_bids_beyond_fast_kernel_caps_take_the_exact_route(orc):
     """Bids above 65535 cents overflow the fast kernel's 32-bit lane accumulators by design: such
     envs are routed to the exact serial kernel and still match the oracle."""
