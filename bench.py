@@ -30,9 +30,25 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's banner / debug lines (printed to stdout by default
-# when the box sets NCCL_DEBUG) go to stderr instead
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+def _claim_stdout():
+    """stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version
+    banner to stdout when the box sets NCCL_DEBUG), so file descriptor 1 is pointed at stderr for
+    the whole process and the JSON line goes to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return out
+
+
+_OUT = None
+
+
+def emit(obj) -> None:
+    (_OUT or sys.stdout).write(json.dumps(obj) + "\n")
+    (_OUT or sys.stdout).flush()
+
 
 METRIC = "keyword_auction_steps_per_sec"
 UNIT = "keyword-auction-steps/s"
@@ -113,7 +129,7 @@ def run_reference(args):
                     f"{PY_REFERENCE_UNITS_PER_S_1CORE:.0f} units/s/core (BASELINE.md)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -319,7 +335,7 @@ def run_gpu(args):
             dist.all_reduce(metric_acc)
 
     if args.replay_only:
-        print(json.dumps({"replay": run_replay_leg(env, table, dev, torch, steps=max(args.steps, 3))}))
+        emit({"replay": run_replay_leg(env, table, dev, torch, steps=max(args.steps, 3))})
         return 0
     if args.explicit:  # experiment: the reference's DEFAULT env (ExplicitKeyword, config 1) vectorised
         from adcraft_b200 import keywords as kwm
@@ -343,11 +359,11 @@ def run_gpu(args):
             stops[i].record()
         torch.cuda.synchronize(dev)
         ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops)) / n
-        print(json.dumps({"explicit_default_env": {
+        emit({"explicit_default_env": {
             "envs": E_ENVS, "keywords": Kx, "ms_per_step": ms, "units_per_s": E_ENVS * Kx / (ms * 1e-3),
             "mean_volume": float(np.mean(xtable.vol_mean)), "mean_impressions": float(xo["impressions"].float().mean()),
             "note": "ExplicitKeyword set from sample_random_keywords(default_rng(0)), bids U[0.01,3.00], budget 1000 "
-                    "(binds for many envs: those take the exact serial kernel)"}}))
+                    "(binds for many envs: those take the exact serial kernel)"}})
         return 0
     if args.agents > 1:  # experiment: BASELINE config 4, A bidders inside every auction
         from adcraft_b200.multi_agent import SharedAuctionSimulation
@@ -378,12 +394,12 @@ def run_gpu(args):
         torch.cuda.synchronize(dev)
         ms_kernel = sum(a.elapsed_time(b) for a, b in zip(starts, stops)) / n
         winners = (sobs["impressions"] > 0).sum(dim=1)
-        print(json.dumps({"shared_auction": {
+        emit({"shared_auction": {
             "worlds": W, "agents": A, "keywords": K_KW, "ms_per_step": ms, "ms_per_step_kernels_only": ms_kernel,
             "bidder_units_per_s": W * A * K_KW / (ms * 1e-3), "auction_units_per_s": W * K_KW / (ms * 1e-3),
             "max_winners_per_auction_unit": int(winners.max()),
             "note": "timed step includes the rival-floor computation (torch amax passes over the A bids) and one launch "
-                    "over worlds*A bidder rows; bids = 0.50 + 0.05*agent"}}))
+                    "over worlds*A bidder rows; bids = 0.50 + 0.05*agent"}})
         return 0
 
     # ---- device-timed steps, inputs resident in HBM --------------------------------------
@@ -513,7 +529,7 @@ def run_gpu(args):
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "auctions_per_sec": value * MEAN_VOLUME,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -545,6 +561,8 @@ def main():
     ap.add_argument("--agents", type=int, default=1,
                     help="experiment only: bidders per shared auction (BASELINE config 4: --agents 8 --envs 65536)")
     args = ap.parse_args()
+    global _OUT
+    _OUT = _claim_stdout()
     E_ENVS = args.envs
     BUDGET = args.budget if args.budget is not None else 100000.0 * max(1.0, args.keywords / 100.0)
     K_KW, MEAN_VOLUME, CVR, DRIFT = args.keywords, args.volume, args.cvr, args.drift
