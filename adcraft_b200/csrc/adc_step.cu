@@ -570,13 +570,19 @@ adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
 
 
 // ------------------------------------------------------------------------------------------
-// hot kernel, warp-batched: a warp takes a batch of 32 units.  Setup is lane <-> unit (parameters,
-// volume draw, thresholds, Philox pre-round -> 32 B per unit in shared memory), so it runs at
-// full lane efficiency; then the warp walks the 32 units one after the other with all 32 lanes
-// on one unit's auctions (warp-uniform parameters in registers, private lane accumulators, one
-// REDUX set per unit).  Volume imbalance between units costs nothing (the L-threads-per-unit
-// kernel loses ~30 % of its lanes to it); only the last 32-auction trip of a unit has idle lanes.
-// Revenues are flattened across the batch (4 draws per Philox call).
+// hot kernel, warp-batched: a warp takes a batch of 32 units.
+//   setup       lane <-> unit (parameters, volume draw, thresholds, Philox pre-round -> 32 B per
+//               unit in shared memory): full lane efficiency;
+//   full trips  the warp walks the units one after the other with all 32 lanes on one unit's
+//               auctions, 64 per trip (one Philox call = two auctions per lane), warp-uniform
+//               parameters in registers, private lane accumulators, three REDUX per unit;
+//   remainders  the V mod 64 auctions of every unit, flattened across the batch: call i belongs to
+//               the unit whose prefix range holds i, so these trips are full as well;
+//   revenues    flattened the same way, 4 draws per Philox call;
+//   outputs     lane <-> unit again: coalesced stores, env completion by L2 atomics, the last
+//               finisher of an env runs its tail and drift.
+// Volume imbalance between units costs nothing (the L-threads-per-unit kernel loses ~30 % of its
+// lanes to it).  Batches come from an atomic work counter when the caller provides one.
 // ------------------------------------------------------------------------------------------
 // win <=> bid > c; click <=> win && cc <= thr_click; conversion <=> click && cc <= thr_conv.
 // Three compares chained through their predicates and four predicated adds.
