@@ -152,9 +152,10 @@ typedef struct adc_step_args {
                                on a given scratch (its parity double-buffers serial_count)    */
     uint64_t seed;          /* Philox key                                          */
     int32_t n_lanes;        /* lanes per (env,keyword) unit.  0 / -32: warp-batched hot kernel with 32
-                               lanes per unit (dense keywords); -16 / -8: the same kernel with
-                               sub-warp groups (sparse keywords); 1..32 (pow2): the simpler
-                               L-threads-per-unit kernel (A/B and detail recording, n_lanes = 1) */
+                               lanes per unit (fastest for every volume: the volume remainders of a
+                               batch are flattened); -16 / -8: its older variant with sub-warp groups
+                               (A/B); 1..32 (pow2): the simpler L-threads-per-unit kernel (A/B and
+                               detail recording, n_lanes = 1) */
     int32_t budget_alias;   /* 1: ndarray-budget double charge (bsim:102 + :225), 0: scalar budget */
     int32_t autoreset;      /* 1: zero cum_profit/day of finished envs after reporting them */
     int32_t force_serial;   /* 1: run every env through the exact serial kernel (testing)   */
