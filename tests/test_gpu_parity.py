@@ -80,6 +80,27 @@ def test_budget_binding_serial_path(orc, alias):
         _compare(obs, reward, term, trunc, ref, env, RTOL64)
 
 
+@pytest.mark.parametrize("K,E,vol", [(150, 12, 40), (2300, 5, 12)])
+def test_budget_binding_serial_path_large_keyword_sets(orc, K, E, vol):
+    """The exact serial kernel keeps the per-unit constants of the first 104 keywords in shared
+    memory and recomputes the rest every sub-step: both tiers, with budgets that bind at different
+    sub-steps (and not at all for some envs), must equal the oracle."""
+    rng = np.random.default_rng(17)
+    table = make_implicit_table(rng, K, vol)
+    day_spend = K * vol * 0.15  # rough scale of a day's spend in dollars
+    budgets = np.resize([0.02, 0.2, 0.6, 5.0], E) * day_spend
+    env = _env(table, E, seed=31, budget=1000.0, obs_dtype=torch.float64)
+    ob = _oracle_batch(orc, table, E, seed=31, budget=1000.0)
+    for s in range(2):
+        bids = np.round(rng.uniform(0.2, 1.5, (E, K)), 2)
+        ob.budget[:] = budgets
+        obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda(),
+                                                "budget": torch.from_numpy(budgets).cuda()})
+        ref = ob.step(bids, n_threads=4)
+        _compare(obs, reward, term, trunc, ref, env, RTOL64)
+    assert float(obs["cost"].sum()) > 0
+
+
 def test_force_serial_equals_fast_path(orc):
     rng = np.random.default_rng(11)
     K, E = 30, 40
