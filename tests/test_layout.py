@@ -34,3 +34,17 @@ def test_required_top_level_layout():
     for p in ("bench.py", "__graft_entry__.py", "DESIGN.md", "INTEGRATION.md", "include/adcraft_b200.h",
               "oracle/adcraft_oracle.c", "oracle/Makefile", "tests/golden/make_golden.py", "profiles"):
         assert os.path.exists(os.path.join(ROOT, p)), p
+
+
+def test_sampler_tables_of_library_and_oracle_are_the_same_literals():
+    """The Exp(1) and normal sampler tables are spec constants: the CUDA library and the C oracle
+    each keep a copy (tools/gen_neglog_table.py, tools/gen_znorm_table.py write both), and bit-exact
+    free-running parity rests on the copies being identical."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for lib, orc, rows in (("adc_neglog_table.inc", "neglog_table.inc", 128),
+                           ("adc_znorm_table.inc", "znorm_table.inc", 32 * 128)):
+        a = open(os.path.join(root, "adcraft_b200", "csrc", lib)).read()
+        b = open(os.path.join(root, "oracle", orc)).read()
+        assert a == b, (lib, orc)
+        assert sum(1 for line in a.splitlines() if line.strip().startswith("{")) == rows, lib
