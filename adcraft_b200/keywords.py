@@ -6,8 +6,10 @@ Generator in exactly the reference's order so that ``reset(seed=s)`` yields the 
 * :func:`sample_random_keywords`  <- ``adcraft/gymnasium_kw_utils.py:113-156`` (ExplicitKeyword)
 * :func:`sample_implicit_keywords_from_quantiles` <- ``gymnasium_kw_utils.py:260-349`` +
   ``pull_quantiles_data/quantiles_to_keywords.py:13-28`` + the in-memory equivalent of
-  ``experiment_utils/experiment_quantiles.py:7-84`` (the CSV round trip is skipped; the same
-  singleton quantile rows are built directly, or a user ``load_quant_func`` is called).
+  ``experiment_utils/experiment_quantiles.py:7-84`` (the singleton quantile rows are built in
+  memory by default; the reference's CSV wire format -- ``count_/min_/median_/max_<param>``
+  columns -- is read and written by ``read_quantile_csv`` / ``write_quantile_csv``, with the
+  reference's ``quantiles_folder`` default loader and ``make/load_quant_func`` conventions).
 
 The table is SoA float64: ``((vol_mean, vol_std), loc|intercept, scale|slope, bctr, sctr,
 mean_rev, std_rev)`` of ``gymnasium_kw_utils.py:20-28``; for implicit keywords ``p2`` holds the
@@ -15,6 +17,7 @@ Laplace *scale* (the reference's params tuple stores ``1/scale``, utils:195).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -150,13 +153,91 @@ def sample_from_quantiles(n, num_buckets, mins, meds, maxs, rng) -> np.ndarray:
     return exact
 
 
+QUANTILE_PARAMS = ("vol", "ave_cpc", "std_cpc", "bctr", "sctr", "rpsc", "std_rpsc")
+_QUANTILE_STATS = ("count", "min", "median", "max")
+
+
+def write_quantile_csv(cols: Dict[str, np.ndarray], path: str) -> None:
+    """Write a quantile table in the reference's wire format: what ``DataFrame.to_csv(path)`` produces
+    for columns ``count_/min_/median_/max_<param>`` (experiment_quantiles.py:28-33,68-73) -- an
+    unnamed index column first, one row per quantile bucket, empty cell for NaN."""
+    names = [f"{st}_{p}" for p in QUANTILE_PARAMS for st in _QUANTILE_STATS if f"{st}_{p}" in cols]
+    names += [c for c in cols if c not in names]
+    arrs = [np.atleast_1d(np.asarray(cols[c], dtype=np.float64)) for c in names]
+    n = len(arrs[0])
+    assert all(len(a) == n for a in arrs), "quantile columns must have one value per bucket"
+
+    def cell(v: float) -> str:
+        if v != v:
+            return ""
+        return str(int(v)) if float(v).is_integer() and abs(v) < 2 ** 53 else repr(float(v))
+
+    with open(path, "w", newline="") as f:
+        f.write("," + ",".join(names) + "\n")
+        for i in range(n):
+            f.write(str(i) + "," + ",".join(cell(a[i]) for a in arrs) + "\n")
+
+
+def read_quantile_csv(path: str) -> Dict[str, np.ndarray]:
+    """Read a quantile table written by pandas (``to_csv``) or by ``write_quantile_csv``: float64
+    columns ``count_/min_/median_/max_<param>``; the index column and anything else is dropped.
+    Parsed by ``pandas.read_csv`` like the reference does (utils:254) when pandas is importable --
+    its default float parser is not correctly rounded, so only the same parser gives the same
+    last bits -- else by Python's ``float``."""
+    try:
+        import pandas as pd
+    except ImportError:
+        pd = None
+    if pd is not None:
+        data = pd.read_csv(path)
+        return {c: np.asarray(data[c], dtype=np.float64) for c in data.columns
+                if "_" in c and c.split("_")[0] in _QUANTILE_STATS}
+    import csv
+    with open(path, newline="") as f:
+        rows = list(csv.reader(f))
+    header, body = rows[0], [r for r in rows[1:] if r]
+    out = {}
+    for j, name in enumerate(header):
+        if "_" in name and name.split("_")[0] in _QUANTILE_STATS:
+            out[name] = np.array([float(r[j]) if j < len(r) and r[j] != "" else np.nan for r in body],
+                                 dtype=np.float64)
+    return out
+
+
+def make_experiment_quantiles(keyword_config: Dict) -> None:
+    """experiment_quantiles.py:37-47,68-73: the singleton quantile bucket of the experiment configs,
+    written to ``<outer_directory>/<mean_volume>_<conversion_rate>.csv`` (usable as ``make_quant_func``)."""
+    v, cvr = keyword_config["mean_volume"], keyword_config["conversion_rate"]
+    cols = quantile_rows_from_config({"mean_volume": v, "conversion_rate": cvr})
+    write_quantile_csv(cols, f"{keyword_config['outer_directory']}/{v}_{cvr}.csv")
+
+
+def load_experiment_quantiles(keyword_config: Dict) -> Dict[str, np.ndarray]:
+    """experiment_quantiles.py:76-84 (usable as ``load_quant_func``)."""
+    v, cvr = keyword_config["mean_volume"], keyword_config["conversion_rate"]
+    return read_quantile_csv(f"{keyword_config['outer_directory']}/{v}_{cvr}.csv")
+
+
+def load_quantile_rows_from_csv(keyword_config: Dict) -> Optional[Dict[str, np.ndarray]]:
+    """gymnasium_kw_utils.py:238-257, the reference's default ``load_quant_func``:
+    ``<outer_directory><quantiles_folder>auction_data.csv`` (plain string concatenation, as there),
+    None when the file does not exist."""
+    outer = keyword_config.get("outer_directory", os.getcwd().replace(os.sep, "/") + "/quantile_dfs/")
+    path = outer + keyword_config.get("quantiles_folder") + "auction_data.csv"
+    return read_quantile_csv(path) if os.path.isfile(path) else None
+
+
 def quantile_rows_from_config(keyword_config: Dict) -> Dict[str, np.ndarray]:
     """Quantile table as a dict of columns ``count_/min_/median_/max_<param>``.
 
     Accepts (a) a user ``load_quant_func`` (+ optional ``make_quant_func``) exactly like the
-    reference (utils:281-289), (b) an explicit ``quantile_table`` mapping, or (c) the experiment
-    configs' ``mean_volume`` / ``conversion_rate`` pair (experiment_quantiles.py:37-47)."""
+    reference (utils:281-289), returning a DataFrame or a dict of columns; (b) an explicit
+    ``quantile_table`` mapping; (c) ``quantiles_folder`` alone: the reference's default CSV loader
+    (utils:238-257); or (d) the experiment configs' ``mean_volume`` / ``conversion_rate`` pair
+    (experiment_quantiles.py:37-47) built in memory."""
     load = keyword_config.get("load_quant_func")
+    if load is None and "quantile_table" not in keyword_config and keyword_config.get("quantiles_folder", False):
+        load = load_quantile_rows_from_csv
     if load is not None:
         if not keyword_config.get("quantiles_folder", False):
             make = keyword_config.get("make_quant_func")
@@ -164,8 +245,8 @@ def quantile_rows_from_config(keyword_config: Dict) -> Dict[str, np.ndarray]:
                 make(keyword_config)
         data = load(keyword_config)
         assert data is not None, "Invalid quantile parameters specified in keyword_config for data"
-        return {c: np.asarray(data[c], dtype=np.float64) for c in data.columns if c.split("_")[0] in
-                ("count", "min", "median", "max")}
+        names = data.keys() if isinstance(data, dict) else data.columns
+        return {c: np.asarray(data[c], dtype=np.float64) for c in names if c.split("_")[0] in _QUANTILE_STATS}
     if "quantile_table" in keyword_config:
         return {k: np.atleast_1d(np.asarray(v, dtype=np.float64))
                 for k, v in keyword_config["quantile_table"].items()}

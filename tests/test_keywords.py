@@ -1,5 +1,6 @@
 """Reset-time keyword factories against the reference's notebook-printed goldens."""
 import numpy as np
+import pytest
 
 from adcraft_b200 import keywords as kwm
 
@@ -64,3 +65,45 @@ def test_quantile_table_sources():
     b = kwm.sample_implicit_keywords_from_quantiles(4, _rng(2), {"quantile_table": custom})
     for n in kwm.PARAM_NAMES:
         assert np.array_equal(getattr(a, n), getattr(b, n))
+
+
+def test_quantile_csv_wire_format_round_trip(tmp_path):
+    """count_/min_/median_/max_<param> columns behind an unnamed index column (what pandas' to_csv
+    writes, experiment_quantiles.py:68-73): written, read back, and used through the reference's
+    three loading conventions (make/load_quant_func pair, quantiles_folder default loader)."""
+    rng = np.random.default_rng(0)
+    rows = 4
+    cols = {}
+    for p in kwm.QUANTILE_PARAMS:
+        lo = np.round(rng.uniform(0.05, 0.4, rows), 3)  # short decimals: every float parser agrees on them
+        cols[f"count_{p}"] = np.array([3.0, 0.0, 5.0, 2.0]) if p == "bctr" else np.full(rows, 3.0)
+        cols[f"min_{p}"], cols[f"median_{p}"], cols[f"max_{p}"] = lo, lo + 0.125, lo + 0.5
+    cols["min_vol"], cols["median_vol"], cols["max_vol"] = (np.array([8.0, 20, np.nan, 90]),
+                                                            np.array([12.0, 40, np.nan, 120]),
+                                                            np.array([16.0, 64, np.nan, 256]))
+    folder = tmp_path / "q" / "setA"
+    folder.mkdir(parents=True)
+    kwm.write_quantile_csv(cols, str(folder / "auction_data.csv"))
+    first = open(folder / "auction_data.csv").readline().strip().split(",")
+    assert first[0] == "" and first[1:5] == ["count_vol", "min_vol", "median_vol", "max_vol"]
+    back = kwm.read_quantile_csv(str(folder / "auction_data.csv"))
+    assert set(back) == set(cols)
+    for c in cols:
+        np.testing.assert_array_equal(back[c], cols[c])
+    cfg = {"outer_directory": str(tmp_path / "q") + "/", "quantiles_folder": "setA/"}
+    a = kwm.sample_implicit_keywords_from_quantiles(12, _rng(3), cfg)                       # default CSV loader
+    b = kwm.sample_implicit_keywords_from_quantiles(12, _rng(3), {"quantile_table": cols})  # in memory
+    for n in kwm.PARAM_NAMES:
+        np.testing.assert_array_equal(getattr(a, n), getattr(b, n))
+    assert np.any(a.vol_mean == 0)  # the NaN-volume bucket gives zero-volume keywords (utils:296-300)
+    with pytest.raises(AssertionError, match="Invalid quantile parameters"):
+        kwm.sample_implicit_keywords_from_quantiles(2, _rng(3), {"outer_directory": str(tmp_path) + "/",
+                                                                 "quantiles_folder": "missing/"})
+    # experiment configs: make_quant_func writes <outer>/<vol>_<cvr>.csv, load_quant_func reads it
+    ecfg = {"outer_directory": str(tmp_path), "mean_volume": 64, "conversion_rate": 0.1,
+            "make_quant_func": kwm.make_experiment_quantiles, "load_quant_func": kwm.load_experiment_quantiles}
+    c = kwm.sample_implicit_keywords_from_quantiles(7, _rng(4), ecfg)
+    d = kwm.sample_implicit_keywords_from_quantiles(7, _rng(4), {"mean_volume": 64, "conversion_rate": 0.1})
+    assert (tmp_path / "64_0.1.csv").exists()
+    for n in kwm.PARAM_NAMES:
+        np.testing.assert_array_equal(getattr(c, n), getattr(d, n))

@@ -141,3 +141,48 @@ def test_shared_auction_is_nth_price_auction_on_rivals_plus_competitor(orc):
                 assert abs(out["cost"][k] - float(np.sum(costs))) < 1e-9, (step, a, k)
                 winners[k] += I > 0
         assert winners[0] == 0 and (winners <= 1).all()
+
+
+def test_quantile_csv_wire_format_against_reference(orc):
+    """The quantile CSVs: a file written by the reference (pandas to_csv) reads back
+    to the same table here, and a multi-bucket file written here (a bucket without data for one
+    parameter, a NaN-volume bucket) gives the reference's sampler -- through its own default loader,
+    gymnasium_kw_utils.py:238-257 -- exactly the keywords it gives ours, generator state included."""
+    import os
+    from adcraft_b200 import keywords as kwm
+    from oracle import ref_driver as rd
+    ref = rh.load_reference()
+    pytest.importorskip("pandas")
+    tmp = tempfile.mkdtemp()
+    # (1) reference-written experiment file -> our reader
+    cfg = rh.experiment_keyword_config(64, 0.1, tmp)
+    cfg["make_quant_func"](cfg)
+    theirs = cfg["load_quant_func"](cfg)
+    ours = kwm.load_experiment_quantiles(cfg)
+    assert set(ours) == {c for c in theirs.columns if not c.startswith("Unnamed")}
+    for c in ours:
+        np.testing.assert_array_equal(ours[c], np.asarray(theirs[c], dtype=np.float64))
+    # (2) our multi-bucket file -> the reference's default loader and sampler
+    rng = np.random.default_rng(1)
+    rows, cols = 5, {}
+    for p in kwm.QUANTILE_PARAMS:
+        lo = np.round(rng.uniform(0.05, 0.4, rows), 3)
+        # (the bucket without sctr data is the LAST one: the reference indexes the filtered pandas
+        # Series by label, quantiles_to_keywords.py:24-26, so a gap in the middle raises KeyError there)
+        cols[f"count_{p}"] = np.array([3.0, 1.0, 5.0, 2.0, 0.0]) if p == "sctr" else np.full(rows, 4.0)
+        cols[f"min_{p}"], cols[f"median_{p}"], cols[f"max_{p}"] = lo, lo + 0.125, lo + 0.5
+    cols["min_vol"] = np.array([8.0, 20, np.nan, 90, 300])
+    cols["median_vol"] = np.array([12.0, 40, np.nan, 120, 400])
+    cols["max_vol"] = np.array([16.0, 64, np.nan, 256, 500])
+    os.makedirs(os.path.join(tmp, "prod"))
+    kwm.write_quantile_csv(cols, os.path.join(tmp, "prod", "auction_data.csv"))
+    kcfg = {"outer_directory": tmp + "/", "quantiles_folder": "prod/", "no_vol_prob": 0.2}
+    for K, seed in [(3, 0), (40, 7)]:
+        env = ref["env"].bidding_sim_creator(dict(keyword_config=dict(kcfg), num_keywords=K))
+        env.reset(seed=seed)
+        a = rd.keywordset_from_env(env)
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        t = kwm.sample_implicit_keywords_from_quantiles(K, g, dict(kcfg))
+        for n in kwm.PARAM_NAMES:
+            np.testing.assert_allclose(getattr(a, n), getattr(t, n), rtol=1e-15 if n == "p2" else 0, err_msg=n)
+        assert env.np_random.random() == g.random()
