@@ -11,9 +11,9 @@ import os
 from . import build as _build
 
 SUBSTEPS = 24
-IMPLICIT, EXPLICIT = 0, 1
+IMPLICIT, EXPLICIT, IMPLICIT_MULTI = 0, 1, 2
 F32, F64 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class AdcError(RuntimeError):
@@ -25,6 +25,7 @@ class Keywords(C.Structure):
         ("kind", C.c_int32), ("K", C.c_int32), ("env_stride", C.c_int64),
         ("vol_mean", C.c_void_p), ("vol_std", C.c_void_p), ("p1", C.c_void_p), ("p2", C.c_void_p),
         ("ctr", C.c_void_p), ("cvr", C.c_void_p), ("rev_mean", C.c_void_p), ("rev_std", C.c_void_p),
+        ("max_bidders", C.c_void_p), ("participation", C.c_void_p),
         ("impression_thresh", C.c_double),
     ]
 
@@ -60,16 +61,19 @@ class Scratch(C.Structure):
 
 class Detail(C.Structure):
     _fields_ = [("cap", C.c_int32), ("costs", C.c_void_p), ("rev_per_cost", C.c_void_p),
-                ("n_recorded", C.c_void_p), ("volume_seen", C.c_void_p)]
+                ("n_recorded", C.c_void_p), ("volume_seen", C.c_void_p),
+                ("lane_clicks", C.c_void_p), ("lane_convs", C.c_void_p)]
 
 
 class StepArgs(C.Structure):
     _fields_ = [
-        ("E", C.c_int32), ("env_base", C.c_uint32), ("step", C.c_uint32), ("seed", C.c_uint64),
+        ("E", C.c_int32), ("env_base", C.c_uint32), ("step", C.c_uint32), ("parity", C.c_uint32),
+        ("device", C.c_int32), ("seed", C.c_uint64),
         ("n_lanes", C.c_int32), ("budget_alias", C.c_int32), ("autoreset", C.c_int32),
         ("force_serial", C.c_int32),
         ("kw", Keywords), ("env", EnvState), ("drift", Drift),
-        ("bids", C.c_void_p), ("bids_dtype", C.c_int32), ("budget_in", C.c_void_p),
+        ("bids", C.c_void_p), ("bids_dtype", C.c_int32), ("f32_ties", C.c_int32),
+        ("budget_in", C.c_void_p),
         ("env_group", C.c_int32), ("floor_cents", C.c_void_p),
         ("out", StepOut), ("scratch", Scratch), ("detail", Detail),
     ]
@@ -77,7 +81,7 @@ class StepArgs(C.Structure):
 
 class Tape(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "volume", "comp_off", "comp_cents", "click_off", "u_click", "conv_off", "u_conv",
+        "volume", "comp_off", "comp_cents", "comp_f64", "click_off", "u_click", "conv_off", "u_conv",
         "rev_off", "rev_cents", "impr", "cost_off", "cost", "drift", "packed", "packed_off")]
 
 

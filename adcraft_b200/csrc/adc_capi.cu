@@ -42,7 +42,11 @@ int validate(const adc_step_args *a, const adc_tape *tape)
     ADC_REQUIRE(a != nullptr, "args is NULL");
     ADC_REQUIRE(a->E > 0, "E must be > 0");
     ADC_REQUIRE(a->kw.K > 0 && a->kw.K < (1 << 20), "K must be in [1, 2^20)");
-    ADC_REQUIRE(a->kw.kind == ADC_IMPLICIT || a->kw.kind == ADC_EXPLICIT, "kw.kind");
+    ADC_REQUIRE(a->kw.kind == ADC_IMPLICIT || a->kw.kind == ADC_EXPLICIT || a->kw.kind == ADC_IMPLICIT_MULTI,
+                "kw.kind");
+    ADC_REQUIRE(a->kw.kind != ADC_IMPLICIT_MULTI || (a->kw.max_bidders && a->kw.participation),
+                "kw.max_bidders / kw.participation are required for ADC_IMPLICIT_MULTI");
+    ADC_REQUIRE(a->f32_ties == 0 || a->floor_cents == nullptr, "f32_ties is not defined for shared auctions");
     ADC_REQUIRE(a->kw.env_stride == 0 || a->kw.env_stride == a->kw.K, "kw.env_stride must be 0 or K");
     ADC_REQUIRE(a->kw.vol_mean && a->kw.vol_std && a->kw.p1 && a->kw.p2 && a->kw.ctr && a->kw.cvr &&
                     a->kw.rev_mean && a->kw.rev_std, "kw parameter pointer is NULL");
@@ -56,8 +60,8 @@ int validate(const adc_step_args *a, const adc_tape *tape)
                 "output pointer is NULL");
     ADC_REQUIRE(a->scratch.serial_list && a->scratch.serial_count && a->scratch.env_profit &&
                     a->scratch.env_cost && a->scratch.env_done, "scratch pointer is NULL");
-    ADC_REQUIRE(a->kw.kind != ADC_EXPLICIT || a->scratch.unit_cost_f64 != nullptr,
-                "scratch.unit_cost_f64 is required for explicit keywords");
+    ADC_REQUIRE(a->kw.kind == ADC_IMPLICIT || a->scratch.unit_cost_f64 != nullptr,
+                "scratch.unit_cost_f64 is required for explicit and multi-bidder keywords (un-rounded costs)");
     ADC_REQUIRE((a->scratch.acc_impressions != nullptr) == (a->scratch.acc_clicks != nullptr) &&
                     (a->scratch.acc_clicks != nullptr) == (a->scratch.acc_conversions != nullptr),
                 "scratch.acc_impressions / acc_clicks / acc_conversions: give all three or none");
@@ -72,6 +76,9 @@ int validate(const adc_step_args *a, const adc_tape *tape)
         ADC_REQUIRE(a->n_lanes == 0 || a->n_lanes == -8 || a->n_lanes == -16 || a->n_lanes == -32,
                     "n_lanes <= 0 selects the batched kernel: 0, -8, -16 or -32");
     }
+    if (a->detail.costs != nullptr)
+        ADC_REQUIRE(a->detail.cap > 0 && a->detail.rev_per_cost && a->detail.n_recorded && a->detail.volume_seen &&
+                        a->detail.lane_clicks && a->detail.lane_convs, "detail: give every array or none");
     ADC_REQUIRE(a->env_group >= 0, "env_group must be >= 0");
     ADC_REQUIRE(a->env_group <= 1 || a->E % a->env_group == 0, "E must be a multiple of env_group");
     if (a->env_group > 1 || a->floor_cents != nullptr)
@@ -82,6 +89,8 @@ int validate(const adc_step_args *a, const adc_tape *tape)
                         tape->rev_off && tape->rev_cents, "tape stream pointer is NULL");
         if (a->kw.kind == ADC_IMPLICIT)
             ADC_REQUIRE(tape->comp_off && tape->comp_cents, "tape.comp_* required for implicit keywords");
+        else if (a->kw.kind == ADC_IMPLICIT_MULTI)
+            ADC_REQUIRE(tape->comp_off && tape->comp_f64, "tape.comp_off / comp_f64 required for multi-bidder keywords");
         else
             ADC_REQUIRE(tape->impr && tape->cost_off && tape->cost, "tape.impr/cost_* required for explicit keywords");
         ADC_REQUIRE(a->drift.mask == nullptr || tape->drift != nullptr, "tape.drift required when drift is on");
@@ -100,6 +109,13 @@ int run(const adc_step_args *args, const adc_tape *tape, void *stream)
     if (rc) return rc;
     rc = check_device();
     if (rc) return rc;
+    if (args->device >= 0) {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != args->device)
+            return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: the buffers live on device %d but the "
+                        "calling thread's current device is %d", args->device, cur);
+    }
     const cudaError_t e = adc::launch_step(*args, tape, static_cast<cudaStream_t>(stream), &g_launches);
     if (e != cudaSuccess) return fail(ADC_ERR_CUDA, "adcraft_b200: launch failed: %s", cudaGetErrorString(e));
     return ADC_OK;

@@ -262,4 +262,14 @@ __device__ __forceinline__ int bid_to_cents(double bid)
     return (int)c;
 }
 
+// numpy >= 2 keeps a float32 bid float32 through round(np.maximum(bid, 0.01), 2) (env:215), and
+// searchsorted then compares float32(cents / 100) upcast to float64 with the float64 competitor bids
+// (helpers:166-170): when the float32 value lies above the cent value the bid wins ties.  Returns 1
+// for such a bid: the win test is `cents + bonus > competitor`.
+__device__ __forceinline__ int bid_tie_bonus(int cents)
+{
+    const float f = __fdiv_rn((float)cents, 100.0f);
+    return (double)f > __ddiv_rn((double)cents, 100.0) ? 1 : 0;
+}
+
 }  // namespace adc

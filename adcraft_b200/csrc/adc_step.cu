@@ -26,7 +26,6 @@
 #include "adc_step.h"
 
 #include <cstdio>
-#include <cstdlib>
 
 namespace adc {
 
@@ -84,8 +83,8 @@ __device__ __forceinline__ bool budget_is_safe(double budget, double spend, int 
 // reset launch is needed (the previous step, the last user of those copies, has completed).
 __device__ __forceinline__ void reset_next_counters(const adc_step_args &a)
 {
-    a.scratch.serial_count[(a.step & 1u) ^ 1u] = 0;
-    if (a.scratch.work_counter != nullptr) a.scratch.work_counter[(a.step & 1u) ^ 1u] = 0u;
+    a.scratch.serial_count[(a.parity & 1u) ^ 1u] = 0;
+    if (a.scratch.work_counter != nullptr) a.scratch.work_counter[(a.parity & 1u) ^ 1u] = 0u;
 }
 
 struct Drift3 {
@@ -189,6 +188,7 @@ struct UnitCur {
 
 struct UnitPar {
     int bid_cents;
+    int win_cents;  // what the competitor bid is compared with: bid_cents (+1 under the f32 tie rule)
     double bid;  // dollars (explicit)
     float loc, scale, rev_mean, rev_sd;
     double ctr, cvr;
@@ -197,6 +197,12 @@ struct UnitPar {
     bool conv_all;
     int floor_cents;  // shared auctions: highest rival bid (INT_MIN when there are no rivals)
 };
+
+// cents the win test uses (adc_step_args.f32_ties)
+__device__ __forceinline__ int win_cents_of(const adc_step_args &a, int bid_cents)
+{
+    return bid_cents + ((a.f32_ties && a.bids_dtype == ADC_F32) ? bid_tie_bonus(bid_cents) : 0);
+}
 
 // Philox env id: the A bidders of a shared-auction world draw from the same counters.
 __device__ __forceinline__ uint32_t philox_env(const adc_step_args &a, int e)
@@ -307,7 +313,7 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
                 w1 = (j & 1) ? w.w : w.y;
                 w2 = w1;
             }
-            if (p.bid_cents > c) {
+            if (p.win_cents > c) {
                 bool clicked;
                 if constexpr (Src::kTape)
                     clicked = tape_at(tp->u_click, tp->click_off, u, cur.n_click + slots, 2.0, o.overrun) <= p.ctr;
@@ -364,6 +370,7 @@ __device__ __forceinline__ UnitPar load_unit_par(const adc_step_args &a, int e, 
     const int64_t pi = (int64_t)e * a.kw.env_stride + k;
     const int64_t u = (int64_t)e * a.kw.K + k;
     p.bid_cents = bid_to_cents(load_f(a.bids, a.bids_dtype, u));
+    p.win_cents = win_cents_of(a, p.bid_cents);
     p.bid = cents_to_dollars(p.bid_cents);
     p.ctr = a.kw.ctr[pi];
     p.cvr = a.kw.cvr[pi];
@@ -456,7 +463,7 @@ __device__ __forceinline__ int unit_done(const adc_step_args &a, int e, long lon
         spend = cents_to_dollars(cost);
     }
     if (a.force_serial || !budget_is_safe(budget, spend, a.budget_alias)) {
-        const int slot = atomicAdd(a.scratch.serial_count + (a.step & 1u), 1);
+        const int slot = atomicAdd(a.scratch.serial_count + (a.parity & 1u), 1);
         a.scratch.serial_list[slot] = e;
         return 0;
     }
@@ -509,7 +516,7 @@ adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             const uint4 w = philox4x32_10((uint32_t)(j >> 1), a.step, c2, genv, k0, k1);
             const uint32_t cc = (j & 1) ? w.w : w.y;
             const int c = max(laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale), p.floor_cents);
-            const bool win = p.bid_cents > c;
+            const bool win = p.win_cents > c;
             const bool clk = win && (cc <= p.thr_click);
             const bool cnv = clk && (p.conv_all || cc < p.thr_cc);
             I += win;
@@ -716,7 +723,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     // lane<->unit phases run at 8/32 lane efficiency).  Without the counter: static rounds of
     // 32-unit batches, then the remainder in 8-unit batches dealt round-robin.
     const bool dynamic = a.scratch.work_counter != nullptr && total < (1LL << 34);  // 32-bit pull indices
-    uint32_t *const work = a.scratch.work_counter + (a.step & 1u);
+    uint32_t *const work = a.scratch.work_counter + (a.parity & 1u);
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const unsigned FULL = 0xFFFFFFFFu;
     if (blockIdx.x == 0 && threadIdx.x == 0) reset_next_counters(a);
@@ -751,7 +758,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         bool over_cap = false;
         uint32_t genv = 0;
         UnitPar p;
-        p.bid_cents = 0; p.loc = 0.f; p.scale = 0.f; p.thr_click = 0; p.thr_conv = 0;
+        p.bid_cents = 0; p.win_cents = 0; p.loc = 0.f; p.scale = 0.f; p.thr_click = 0; p.thr_conv = 0;
         p.rev_mean = 0.f; p.rev_sd = 0.f; p.thr_cc = 0; p.conv_all = false; p.floor_cents = (int)0x80000000;
         bool outbid = false;  // shared auctions: a rival bids at least as much, no auction can be won
         if (kFloor && valid)
@@ -764,7 +771,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             const int64_t pi = (int64_t)e * a.kw.env_stride + k;
             const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)k), genv, k0, k1);
             const long long v = volume_draw(w.x, a.kw.vol_mean[pi], a.kw.vol_std[pi]);
-            over_cap = v > kMaxFlatVolume || p.bid_cents > kMaxFlatBidCents ||
+            over_cap = v > kMaxFlatVolume || p.win_cents > kMaxFlatBidCents ||
                        v * p.bid_cents > kMaxFlatSpendCents;
             V = over_cap ? 0 : (int)v;
         } else if (valid) {
@@ -775,7 +782,7 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         {
             const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), genv, k0, k1);
             FlatUnit fu;
-            fu.bid_cents = p.bid_cents; fu.loc = p.loc; fu.scale = p.scale;
+            fu.bid_cents = p.win_cents; fu.loc = p.loc; fu.scale = p.scale;
             // conversion <=> cc < T2 (T2 = 2^32 when conv_all) is stored as cc <= T2 - 1; T2 = 0
             // ("never") rides in the sign bit of the bid (bids <= 65535) and zeroes the unit's count
             fu.thr_click = p.thr_click;
@@ -1082,7 +1089,7 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
                 ru.ctr = a.kw.ctr[pi];
                 ru.cvr = a.kw.cvr[pi];
                 ru.V = t.volume[u];
-                ru.bid_cents = bid_to_cents(load_f(a.bids, a.bids_dtype, u));
+                ru.bid_cents = win_cents_of(a, bid_to_cents(load_f(a.bids, a.bids_dtype, u)));
                 myV = ru.V;
             }
             units[lane] = ru;
@@ -1286,15 +1293,16 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
+    // try_wait suspends the thread for a hardware time slice before it reports failure, so this
+    // loop does not burn issue slots; there is no spin bound (a bound that traps kills the context
+    // when a profiler replay stretches a copy's latency)
     uint32_t ok = 0;
-    for (unsigned spin = 0;; ++spin) {
+    do {
         asm volatile("{\n\t.reg .pred p;\n\t"
                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) break;
-        if (spin > (1u << 18)) __trap();  // ~1 s: a lost copy must not hang the device
-    }
+    } while (!ok);
 }
 
 struct PkResult {
@@ -1526,7 +1534,7 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
             pu.bytes = sane ? (int)len : 0;
             pu.ctr = a.kw.ctr[pi];
             pu.cvr = a.kw.cvr[pi];
-            pu.bid_cents = bid_to_cents(load_f(a.bids, a.bids_dtype, u));
+            pu.bid_cents = win_cents_of(a, bid_to_cents(load_f(a.bids, a.bids_dtype, u)));
             if (pu.bytes > 0 && pu.bytes <= kRing && pu.bid_cents <= kMaxFlatBidCents) {
                 // owner lane reads the record header (the bulk copy re-reads the line from L2)
                 const int4 h0 = __ldg(reinterpret_cast<const int4 *>(pu.src));
@@ -1748,7 +1756,7 @@ __global__ void __launch_bounds__(64)
 adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant__ adc_tape tape)
 {
     const int K = a.kw.K;
-    const int count = a.scratch.serial_count[a.step & 1u];
+    const int count = a.scratch.serial_count[a.parity & 1u];
     const SerCounts acc = ser_counts(a);
     const bool explicit_kw = a.kw.kind == ADC_EXPLICIT;
     const int stride = gridDim.x * blockDim.x;
@@ -1774,6 +1782,10 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
             if (a.detail.costs != nullptr) {
                 a.detail.n_recorded[u] = 0;
                 a.detail.volume_seen[u] = 0.0;
+                for (int t = 0; t < ADC_SUBSTEPS; ++t) {
+                    a.detail.lane_clicks[u * ADC_SUBSTEPS + t] = 0;
+                    a.detail.lane_convs[u * ADC_SUBSTEPS + t] = 0;
+                }
             }
         }
         const adc_detail *det = a.detail.costs != nullptr ? &a.detail : nullptr;
@@ -1819,6 +1831,8 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
                     const int nb = acc.B[u] + o.B;
                     det->n_recorded[u] = nb < det->cap ? nb : det->cap;
                     if (o.I >= 1) det->volume_seen[u] += (double)n;  // bsim:130-137
+                    det->lane_clicks[u * ADC_SUBSTEPS + t] = o.B;
+                    det->lane_convs[u * ADC_SUBSTEPS + t] = o.S;
                 }
                 acc.I[u] += o.I;
                 acc.B[u] += o.B;
@@ -1915,7 +1929,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
     auto slot_cost = [&](int i, int l) { return (int)(s_slot[warp][i][l] & 0x7FFFFFFFu); };
     const int gwarp = blockIdx.x * kSerWarps + warp;
     const int n_warps = gridDim.x * kSerWarps;
-    const int count = a.scratch.serial_count[a.step & 1u];
+    const int count = a.scratch.serial_count[a.parity & 1u];
     const unsigned FULL = 0xFFFFFFFFu;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const adc_tape *no_tape = nullptr;
@@ -1925,7 +1939,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
         uint4 uw;
         const long long V = unit_volume(a, src, no_tape, e, k, &uw);
         SerUnit su;
-        su.bid_cents = p.bid_cents; su.floor_cents = p.floor_cents;
+        su.bid_cents = p.win_cents; su.floor_cents = p.floor_cents;
         su.loc = p.loc; su.scale = p.scale; su.rev_mean = p.rev_mean; su.rev_sd = p.rev_sd;
         su.thr_click = p.thr_click; su.thr_cc = p.thr_cc;
         su.volume = V > 0x7FFFFFFFLL ? 0x7FFFFFFF : (int)V;
@@ -2068,7 +2082,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                         next = remaining;
                         if (lane == l) {
                             UnitPar p;
-                            p.bid_cents = su.bid_cents; p.floor_cents = su.floor_cents; p.loc = su.loc; p.scale = su.scale;
+                            p.bid_cents = su.bid_cents; p.win_cents = su.bid_cents; p.floor_cents = su.floor_cents; p.loc = su.loc; p.scale = su.scale;
                             p.rev_mean = su.rev_mean; p.rev_sd = su.rev_sd; p.thr_click = su.thr_click; p.thr_cc = su.thr_cc;
                             p.conv_all = (su.flags & 1) != 0; p.bid = 0.0; p.ctr = 0.0; p.cvr = 0.0; p.thr_conv = 0; p.thr_impr = 0;
                             double b = remaining, unused = 0.0;
@@ -2290,15 +2304,8 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     } else if (tp.packed != nullptr) {
         // ring geometry: 8 warps x 6 KB per CTA, three CTAs (24 warps) per SM; measured on C2: 6 KB
         // 0.191 ms (5.75 / 6.25 / 6.5 KB: 0.194 / 0.192 / 0.190), 7 KB 0.203 ms, 5 KB with 64 registers
-        // and four CTAs 0.205 ms, 8 KB (two CTAs per SM) 0.26 ms.  ADC_PK_VARIANT re-selects three of
-        // them (measurement knob, read once).
-        static const int variant = [] { const char *v = getenv("ADC_PK_VARIANT"); return v ? atoi(v) : 0; }();
-        switch (variant) {
-            case 1: err = launch_packed<8, 8192, 4, 3>(a, tp, s, launches); break;
-            case 2: err = launch_packed<8, 5632, 3, 4>(a, tp, s, launches); break;
-            case 3: err = launch_packed<8, 7168, 4, 3>(a, tp, s, launches); break;
-            default: err = launch_packed<8, 6144, 4, 3>(a, tp, s, launches); break;
-        }
+        // and four CTAs 0.205 ms, 8 KB (two CTAs per SM) 0.26 ms.
+        err = launch_packed<8, 6144, 4, 3>(a, tp, s, launches);
     } else {
         auto kern = adc_replay_implicit_kernel;
         kern<<<(unsigned)grid_for(kern, kReplayWarps * 32, total), kReplayWarps * 32, 0, s>>>(a, tp);

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .spaces import HAVE_GYMNASIUM, get_action_space, get_observation_space
-from .vector_env import DEFAULT_UPDATER_PARAMS, VectorBiddingSimulation
+from .vector_env import DEFAULT_UPDATER_PARAMS, VectorBiddingSimulation, _sum_list
 
 if HAVE_GYMNASIUM:  # pragma: no cover - gymnasium is not in this image
     import gymnasium as _gym
@@ -60,9 +60,17 @@ class BiddingSimulation(_Base):
     def max_days(self):
         return self._vec.max_days
 
+    @max_days.setter
+    def max_days(self, value):  # a plain attribute in the reference (env:80-82): callers assign it
+        self._vec.max_days = int(value)
+
     @property
     def loss_threshold(self):
         return self._vec.loss_threshold
+
+    @loss_threshold.setter
+    def loss_threshold(self, value):
+        self._vec.loss_threshold = float(value)
 
     @property
     def np_random(self):
@@ -87,7 +95,9 @@ class BiddingSimulation(_Base):
         self.updater_mask = new_updater_mask
 
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
-        _, info = self._vec.reset(seed=seed, options=options)
+        self._vec.reset(seed=seed, options=options)
+        # the reference reprs the CURRENT (possibly drifted) parameters (env:343-345)
+        info = {"keyword_params": self._describe_params()}
         self._have_keywords = True
         self.current_day, self.cumulative_profit = 0, 0.0
         self._current_text = "Reset environment\n\nNew start\n"
@@ -99,17 +109,27 @@ class BiddingSimulation(_Base):
                    days_passed=np.zeros(1, np.float32))
         return obs, info
 
-    def step(self, action: Dict):
+    def step(self, action: Dict, *, tape=None):
+        """``tape`` (a DeviceTape for this one env; parity mode): the step consumes pre-drawn
+        volumes / competitor bids / uniforms / revenues instead of Philox draws."""
         assert self._have_keywords, "reset required, need to generate keywords to bid on"
         budget_in = action.get("budget", self.budget)
         # an ndarray budget is decremented in place by every lane AND by the campaign loop
         # (bidding_simulation.py:102 + :225): reproduce that double charge
         self._vec.budget_alias = isinstance(budget_in, np.ndarray) and budget_in.ndim >= 1
-        bids_in = np.asarray(action["keyword_bids"], dtype=np.float64).reshape(1, -1)
+        raw = np.asarray(action["keyword_bids"])
+        # numpy >= 2 keeps a float32 bid float32 through env:215 (the Box action space's dtype): such
+        # a bid wins ties when its float32 value lies above the cent value (SURVEY A.4-5)
+        f32 = raw.dtype == np.float32
+        self._vec.f32_ties = bool(f32)
+        bids_in = raw.astype(np.float32 if f32 else np.float64).reshape(1, -1)
         act = {"keyword_bids": bids_in,
                "budget": np.asarray(budget_in, dtype=np.float64).reshape(-1)[:1]}
         # the exact serial walk also records the per-click lists of info["bidding_outcomes"]
-        obs, reward, term, trunc, _ = self._vec.step(act, force_serial=True)
+        if tape is not None:
+            obs, reward, term, trunc, _ = self._vec.step_replay(act, tape, force_serial=True)
+        else:
+            obs, reward, term, trunc, _ = self._vec.step(act, force_serial=True)
         torch.cuda.current_stream(self._vec.device).synchronize()
         o = {k: v[0].cpu().numpy() for k, v in obs.items()}
         observations = dict(
@@ -118,17 +138,30 @@ class BiddingSimulation(_Base):
             revenue=o["revenue"].astype(np.float64),
             cumulative_profit=o["cumulative_profit"].astype(np.float64).reshape(1),
             days_passed=o["days_passed"].astype(np.int64).reshape(1))
-        profits = float(reward[0])
-        self.cumulative_profit = float(observations["cumulative_profit"][0])
         self.current_day = int(observations["days_passed"][0])
         left = float(self._vec._out["remaining_budget"][0])
         self.budget = (np.array([left]) if self._vec.budget_alias
                        else np.round(np.asarray(budget_in, dtype=float), 2))
-        bids = [float(np.round(np.maximum(b, 0.01), 2)) for b in bids_in[0]]
+        bids = [float(np.round(np.maximum(b, 0.01), 2)) for b in bids_in[0]]  # in the bids' own dtype
         outcomes = self._vec.bidding_outcomes(0)
+        for o_k, b in zip(outcomes, bids):
+            o_k["bid"] = b
+        # The device sums money as exact integer cents; the reference adds float64 dollars one click
+        # at a time.  With every click's cost and revenue at hand the single-env adapter restates the
+        # reference's own sums in its order (env:222-241: rust.sum_list over the concatenated lists,
+        # profits lane by lane), so these floats are bit-identical to the reference's, not just
+        # within the 1e-6 tolerance.
+        observations["cost"] = np.array([_sum_list(k["costs"]) for k in outcomes])
+        observations["revenue"] = np.array([_sum_list(k["revenues"]) for k in outcomes])
+        profits = _sum_list(k["profit"] for k in outcomes)
+        self.cumulative_profit += profits
+        observations["cumulative_profit"] = np.array([self.cumulative_profit])
         info = {"bids": bids, "bidding_outcomes": repr_outcomes(outcomes),
                 "keyword_params": self._describe_params()}
-        terminated, truncated = bool(term[0]), bool(trunc[0])
+        terminated = bool(term[0])
+        truncated = bool(self.cumulative_profit < -self.loss_threshold)
+        # keep the device's episode state on the same float as the host's
+        self._vec._state["cum_profit"][0] = self.cumulative_profit
         if self.render_mode == "ansi":
             self._current_text = (
                 f"Time step: {self.current_day}/{self.max_days},   "
@@ -157,16 +190,41 @@ class BiddingSimulation(_Base):
 
 
 def _rust_display(v: float) -> str:
-    """Rust's `{}` for f64 (src/lib.rs:269): shortest round-trip digits, no trailing `.0`."""
+    """Rust's ``{}`` for f64 (src/lib.rs:269): shortest round-trip digits, ALWAYS positional (no
+    exponent at any magnitude), no trailing ``.0``."""
     v = float(v)
-    if v == int(v) and abs(v) < 1e16:
-        return str(int(v))
-    return repr(v)
+    if v != v:
+        return "NaN"
+    if v in (float("inf"), float("-inf")):
+        return "inf" if v > 0 else "-inf"
+    from decimal import Decimal
+    s = format(Decimal(repr(v)), "f")
+    if "." in s:
+        s = s.rstrip("0").rstrip(".")
+    return "-0" if s in ("-", "-0") else s
+
+
+def _rust_debug(v: float) -> str:
+    """Rust's ``{:?}`` for f64 (the elements of ``{:?}`` on Vec<f64>, src/lib.rs:269): positional with
+    at least one fractional digit for 0 and 1e-4 <= |v| < 1e16, otherwise shortest-digit scientific
+    notation written like ``1.5e-7`` -- the same switch-over points as Python's repr, whose
+    exponent is zero-padded and signed (``1.5e-07``, ``1e+16``)."""
+    v = float(v)
+    if v != v:
+        return "NaN"
+    if v in (float("inf"), float("-inf")):
+        return "inf" if v > 0 else "-inf"
+    s = repr(v)
+    if "e" in s:
+        mant, exp = s.split("e")
+        if mant.endswith(".0"):
+            mant = mant[:-2]
+        return f"{mant}e{int(exp)}"
+    return s
 
 
 def _rust_debug_list(vs) -> str:
-    """Rust's `{:?}` for Vec<f64>: always a decimal point."""
-    return "[" + ", ".join(repr(float(v)) for v in vs) + "]"
+    return "[" + ", ".join(_rust_debug(v) for v in vs) + "]"
 
 
 def repr_outcomes(outcomes: List[dict]) -> str:

@@ -32,6 +32,32 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _sum_list(xs) -> float:
+    """rust.sum_list (src/lib.rs:113-116): sequential f64 sum."""
+    acc = 0.0
+    for v in xs:
+        acc += float(v)
+    return acc
+
+
+def _sum_array(xs) -> float:
+    """rust.sum_array (src/lib.rs:107-111): ndarray's 8-way unrolled f64 sum."""
+    a = [float(v) for v in xs]
+    p = [0.0] * 8
+    n8 = len(a) // 8 * 8
+    for i in range(0, n8, 8):
+        for j in range(8):
+            p[j] += a[i + j]
+    acc = 0.0
+    acc += p[0] + p[4]
+    acc += p[1] + p[5]
+    acc += p[2] + p[6]
+    acc += p[3] + p[7]
+    for v in a[n8:]:
+        acc += v
+    return acc
+
+
 class VectorBiddingSimulation:
     """E independent bidding environments on one GPU (or one rank's shard of them)."""
 
@@ -50,7 +76,7 @@ class VectorBiddingSimulation:
         updater_mask: Optional[List[bool]] = None,
         *,
         device: Union[str, torch.device] = "cuda",
-        seed: int = 0,
+        seed: Optional[int] = None,
         keywords: Optional[kwmod.KeywordTable] = None,
         shared_keywords: bool = True,
         obs_dtype: torch.dtype = torch.float32,
@@ -61,6 +87,7 @@ class VectorBiddingSimulation:
         detail_cap: int = 0,
         env_group: int = 0,
         dynamic_work: bool = True,
+        f32_ties: bool = False,
         **kwargs,
     ) -> None:
         assert render_mode is None or render_mode in self.metadata["render_modes"], (
@@ -81,7 +108,13 @@ class VectorBiddingSimulation:
         self.updater_params = updater_params
         self.updater_mask = None
         self.num_updates = 0
-        self.seed = int(seed)
+        # Philox key.  Given here or by reset(seed=...); otherwise drawn from np_random (OS entropy) at
+        # the first reset, so that unseeded envs do not share one trajectory.
+        self.seed = 0 if seed is None else int(seed)
+        self._seed_given = seed is not None
+        # numpy >= 2 tie rule for float32 bids (adc_step_args.f32_ties): off = the
+        # float64 semantics of the build contract (ties always lose)
+        self.f32_ties = bool(f32_ties)
         self.env_base = int(env_base)
         self.n_lanes = int(n_lanes)
         self._auto_lanes = n_lanes == 0
@@ -106,7 +139,8 @@ class VectorBiddingSimulation:
         self._keywords_given = keywords
         self.keywords: Optional[kwmod.KeywordTable] = None
         self._have_keywords = False
-        self._step_count = 0
+        self._step_count = 0   # Philox counter word: steps since the last seeded reset
+        self._calls = 0        # library calls on this scratch: its parity double-buffers the queues
         self._alloc()
         if updater_mask is not None:
             self.set_updater_mask(updater_mask)
@@ -145,7 +179,9 @@ class VectorBiddingSimulation:
         if self.detail_cap > 0:
             c = self.detail_cap
             self._detail = dict(costs=z(E, K, c, dtype=f64), rev_per_cost=z(E, K, c, dtype=f64),
-                                n_recorded=z(E, K, dtype=i32), volume_seen=z(E, K, dtype=f64))
+                                n_recorded=z(E, K, dtype=i32), volume_seen=z(E, K, dtype=f64),
+                                lane_clicks=z(E, K, _capi.SUBSTEPS, dtype=i32),
+                                lane_convs=z(E, K, _capi.SUBSTEPS, dtype=i32))
         self._bids_dev = {torch.float32: z(E, K, dtype=torch.float32), torch.float64: z(E, K, dtype=f64)}
         self._budget_dev = {torch.float32: z(E, dtype=torch.float32), torch.float64: z(E, dtype=f64)}
         self._mask_dev: Optional[torch.Tensor] = None
@@ -157,20 +193,38 @@ class VectorBiddingSimulation:
         self._result_cache = None
         self._host_view_cache = None
 
+    def _call(self, fn, *args) -> None:
+        """Run a library entry point with the env's device current: the ABI takes only a stream
+        handle and launches on the calling thread's current device (adc_step_args.device makes a
+        mismatch an error instead of an illegal address)."""
+        if torch.cuda.current_device() == self.device.index:
+            _capi.check(fn(*args))
+        else:
+            with torch.cuda.device(self.device):
+                _capi.check(fn(*args))
+
     def _views(self, block: torch.Tensor) -> Dict[str, torch.Tensor]:
         return {name: block[o:o + n].view(dt).view(shape) for name, dt, shape, o, n in self._block_layout}
 
     # ------------------------------------------------------------------ keywords / reset
     def set_updater_mask(self, new_updater_mask: List[bool]) -> None:
-        """Replace updater mask (env:105-112)."""
+        """Replace updater mask (env:105-112).  Only the mask changes: parameters drifted so far are
+        kept, like the reference, which swaps ``self.updater_mask`` and nothing else."""
         assert len(new_updater_mask) == self.num_keywords, (
             f"Updater mask length ({len(new_updater_mask)})\n"
             + f"must match number of keywords ({self.num_keywords}) to be applied.")
         self.updater_mask = [bool(m) for m in new_updater_mask]
         self.num_updates = int(np.sum(self.updater_mask))
-        self._mask_dev = torch.tensor(self.updater_mask, dtype=torch.uint8, device=self.device)
-        if self.keywords is not None and self.keywords.env_stride == 0:
-            self._install_keywords(self.keywords)  # drift needs per-env parameter copies
+        new = torch.tensor(self.updater_mask, dtype=torch.uint8, device=self.device)
+        if self._mask_dev is None:
+            self._mask_dev = new
+        else:
+            self._mask_dev.copy_(new)  # in place: the pointer in the argument block stays valid
+        if self._have_keywords and self._kw_stride == 0:
+            # drift needs per-env parameter copies: broadcast the CURRENT device values
+            E, K = self.num_envs, self.num_keywords
+            self._kw_dev = {n: t.reshape(1, K).expand(E, K).contiguous() for n, t in self._kw_dev.items()}
+            self._kw_stride = K
 
     def _install_keywords(self, table: kwmod.KeywordTable) -> None:
         E, K = self.num_envs, self.num_keywords
@@ -216,22 +270,34 @@ class VectorBiddingSimulation:
         o, d = self._out, self._detail
         K = self.num_keywords
         n = d["n_recorded"][e].cpu().numpy()
+        clicks = o["buyside_clicks"][e].cpu().numpy()
+        if (clicks > n).any():
+            raise _capi.AdcError(
+                f"bidding_outcomes: a keyword had {int(clicks.max())} clicks but detail_cap is "
+                f"{self.detail_cap}; construct the env with a larger detail_cap")
         costs, rpc = d["costs"][e].cpu().numpy(), d["rev_per_cost"][e].cpu().numpy()
         vol = d["volume_seen"][e].cpu().numpy()
+        lane_b, lane_s = d["lane_clicks"][e].cpu().numpy(), d["lane_convs"][e].cpu().numpy()
         imp = o["impressions"][e].cpu().numpy()
+        conv = o["sellside_conversions"][e].cpu().numpy()
         bids = self._last_bids[e].double().cpu().numpy()
         out = []
         for k in range(K):
             c, r = costs[k, :n[k]], rpc[k, :n[k]]
             revs = r[r > 0]
+            # profit accumulates lane by lane (combine_outcomes, bsim:138-139), each lane's being
+            # rust.sum_array(revenues) - rust.sum_list(costs) (bsim:117)
+            profit, ib, is_ = 0.0, 0, 0
+            for t in range(_capi.SUBSTEPS):
+                nb, ns = int(lane_b[k, t]), int(lane_s[k, t])
+                profit += _sum_array(revs[is_:is_ + ns]) - _sum_list(c[ib:ib + nb])
+                ib, is_ = ib + nb, is_ + ns
             out.append(dict(
                 bid=float(np.round(np.maximum(bids[k], 0.01), 2)), impressions=int(imp[k]),
                 impression_share=float(imp[k] / vol[k]) if vol[k] > 0 else 0.0,
-                buyside_clicks=int(o["buyside_clicks"][e, k]), costs=c.tolist(),
-                sellside_conversions=int(o["sellside_conversions"][e, k]), revenues=revs.tolist(),
-                revenues_per_cost=r.tolist(),
-                profit=float(o["revenue_cents"][e, k] - o["cost_cents"][e, k]) / 100.0
-                if self.kind == 0 else float(revs.sum() - c.sum())))
+                buyside_clicks=int(clicks[k]), costs=c.tolist(),
+                sellside_conversions=int(conv[k]), revenues=revs.tolist(),
+                revenues_per_cost=r.tolist(), profit=float(profit)))
         return out
 
     def keyword_params(self) -> Dict[str, np.ndarray]:
@@ -255,8 +321,15 @@ class VectorBiddingSimulation:
                     self.num_keywords, self.np_random,
                     num_envs=None if self.shared_keywords else self.num_envs)
             self._install_keywords(table)
-            if seed is not None:
-                self.seed = int(seed)
+        if seed is not None:
+            # a seeded reset replays: same key, Philox step counter rewound (the scratch parity,
+            # self._calls, keeps running)
+            self.seed = int(seed)
+            self._seed_given = True
+            self._step_count = 0
+        elif not self._seed_given:
+            self.seed = int(self.np_random.integers(0, 2 ** 63 - 1))
+            self._seed_given = True
         if options:
             self.max_days = options.get("max_days", self.max_days)
             rm = options.get("render_mode", self.render_mode)
@@ -264,9 +337,9 @@ class VectorBiddingSimulation:
                 self.render_mode = rm
             self.loss_threshold = options.get("loss_threshold", self.loss_threshold)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _capi.check(self._lib.adc_reset_envs(
-            self.num_envs, None, self._state["cum_profit"].data_ptr(), self._state["day"].data_ptr(),
-            C.c_void_p(stream)))
+        self._call(self._lib.adc_reset_envs,
+                   self.num_envs, None, self._state["cum_profit"].data_ptr(), self._state["day"].data_ptr(),
+                   C.c_void_p(stream))
         for k in ("impressions", "buyside_clicks", "sellside_conversions", "cost", "revenue",
                   "cumulative_profit", "days_passed", "reward"):
             self._out[k].zero_()
@@ -279,9 +352,9 @@ class VectorBiddingSimulation:
         m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
         assert m.shape == (self.num_envs,)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _capi.check(self._lib.adc_reset_envs(
-            self.num_envs, m.data_ptr(), self._state["cum_profit"].data_ptr(), self._state["day"].data_ptr(),
-            C.c_void_p(stream)))
+        self._call(self._lib.adc_reset_envs,
+                   self.num_envs, m.data_ptr(), self._state["cum_profit"].data_ptr(), self._state["day"].data_ptr(),
+                   C.c_void_p(stream))
         rows = m.bool()
         for k in ("impressions", "buyside_clicks", "sellside_conversions", "cost", "revenue",
                   "cumulative_profit", "days_passed", "reward"):
@@ -317,12 +390,14 @@ class VectorBiddingSimulation:
         """Per-step fields only; the pointer block is rebuilt when something structural changed."""
         a = self._args
         sig = (self.kind, self._kw_stride, id(self._kw_dev), self.max_days, self.loss_threshold,
-               self.updater_mask is not None, self.num_updates, self.autoreset, self.n_lanes,
-               self.seed, self.env_base)
+               None if self._mask_dev is None else self._mask_dev.data_ptr(), self.num_updates,
+               tuple(float(p[1]) for p in self.updater_params), self.autoreset, self.n_lanes,
+               self.seed, self.env_base, self.f32_ties)
         if sig != self._args_sig:
             self._fill_static_args()
             self._args_sig = sig
-        a.step = self._step_count
+        a.step = self._step_count & 0xFFFFFFFF
+        a.parity = self._calls & 0xFFFFFFFF
         a.budget_alias = int(self.budget_alias)
         a.force_serial = int(force_serial)
         a.env_group = self.env_group
@@ -335,13 +410,17 @@ class VectorBiddingSimulation:
     def _fill_static_args(self) -> None:
         a, o, s, st = self._args, self._out, self._scratch, self._state
         E, K = self.num_envs, self.num_keywords
-        a.E, a.env_base, a.seed = E, self.env_base, self.seed
+        a.E, a.env_base, a.seed = E, self.env_base, self.seed & 0xFFFFFFFFFFFFFFFF
+        a.device = self.device.index
+        a.f32_ties = int(self.f32_ties)
         a.n_lanes = self.n_lanes
         a.autoreset = int(self.autoreset)
         kw = a.kw
         kw.kind, kw.K, kw.env_stride = self.kind, K, self._kw_stride
         for n in kwmod.PARAM_NAMES:
             setattr(kw, n, self._kw_dev[n].data_ptr())
+        kw.max_bidders = _ptr(self._kw_dev.get("max_bidders"))
+        kw.participation = _ptr(self._kw_dev.get("participation"))
         kw.impression_thresh = self.keywords.impression_thresh
         a.env.budget, a.env.cum_profit, a.env.day = (st["budget"].data_ptr(), st["cum_profit"].data_ptr(),
                                                      st["day"].data_ptr())
@@ -367,7 +446,7 @@ class VectorBiddingSimulation:
         sc.work_counter = s["work_counter"].data_ptr() if self.dynamic_work else None
         if self._detail is not None:
             a.detail.cap = self.detail_cap
-            for n in ("costs", "rev_per_cost", "n_recorded", "volume_seen"):
+            for n in ("costs", "rev_per_cost", "n_recorded", "volume_seen", "lane_clicks", "lane_convs"):
                 setattr(a.detail, n, self._detail[n].data_ptr())
 
     def _prepare(self, action: Dict[str, ArrayLike]):
@@ -384,7 +463,12 @@ class VectorBiddingSimulation:
     def step(self, action: Dict[str, ArrayLike], *, force_serial: bool = False,
              floor_cents: Optional[torch.Tensor] = None):
         """One env step for all E envs (env:160-269).  Returns device tensors.  ``floor_cents``
-        ([E, K] int32 on the device): highest rival bid per unit for shared auctions."""
+        ([E, K] int32 on the device): highest rival bid per unit for shared auctions.
+
+        The returned observation / reward / flag tensors are the env's own output buffers: every
+        call overwrites them in place (no per-step allocation).  A caller that keeps a step's
+        results past the next ``step`` (a rollout buffer) must ``clone()`` them or copy them into its
+        own storage; the vector adapters' ``copy=True`` does that."""
         bids, budget = self._prepare(action)
         self._last_bids = bids
         a = self._fill_args(bids, budget, force_serial)
@@ -393,18 +477,21 @@ class VectorBiddingSimulation:
             assert tuple(floor_cents.shape) == (self.num_envs, self.num_keywords)
             a.floor_cents = floor_cents.data_ptr()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _capi.check(self._lib.adc_step_philox(C.byref(a), C.c_void_p(stream)))
+        self._call(self._lib.adc_step_philox, C.byref(a), C.c_void_p(stream))
         self._step_count += 1
+        self._calls += 1
         return self._result()
 
     def step_replay(self, action: Dict[str, ArrayLike], tape: DeviceTape, *, force_serial: bool = False):
         """Parity mode: the same step fed by pre-drawn volumes / bids / uniforms / revenues."""
         bids, budget = self._prepare(action)
+        self._last_bids = bids
         a = self._fill_args(bids, budget, force_serial)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         t = tape.c_struct()
-        _capi.check(self._lib.adc_step_replay(C.byref(a), C.byref(t), C.c_void_p(stream)))
+        self._call(self._lib.adc_step_replay, C.byref(a), C.byref(t), C.c_void_p(stream))
         self._step_count += 1
+        self._calls += 1
         return self._result()
 
     def _result(self):
@@ -461,12 +548,13 @@ class VectorBiddingSimulation:
         sc.acc_impressions, sc.acc_clicks, sc.acc_conversions = saved[0], saved[1], saved[2]
         stream = torch.cuda.current_stream(self.device)
         try:
-            _capi.check(self._lib.adc_step_philox(C.byref(a), C.c_void_p(stream.cuda_stream)))
+            self._call(self._lib.adc_step_philox, C.byref(a), C.c_void_p(stream.cuda_stream))
         finally:
             (out.impressions, out.clicks, out.conversions, out.cost, out.revenue, out.reward,
              out.obs_cum_profit, out.obs_days, out.terminated, out.truncated) = saved
             sc.acc_impressions = sc.acc_clicks = sc.acc_conversions = None
         self._step_count += 1
+        self._calls += 1
         stream.synchronize()
         return self._host_views()
 

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define ADC_ABI_VERSION 3
+#define ADC_ABI_VERSION 4
 #define ADC_SUBSTEPS 24 /* adcraft/bidding_simulation.py:213 */
 
 typedef enum adc_status {
@@ -56,7 +56,13 @@ typedef enum adc_status {
     ADC_ERR_UNSUPPORTED = -4
 } adc_status;
 
-enum { ADC_IMPLICIT = 0, ADC_EXPLICIT = 1 };  /* keyword kind (synthetic_kw_classes.py:457,578) */
+/* keyword kind (synthetic_kw_classes.py:457,578).  ADC_IMPLICIT is the experiments' ImplicitKeyword
+ * (one competitor, |Laplace| rounded to cents: gymnasium_kw_utils.py:159-166, helpers:104-113);
+ * ADC_IMPLICIT_MULTI is the class default (classes:649-688): m ~ Binomial(max_bidders,
+ * participation) bidders drawn once per (sub-step, keyword) lane, signed un-rounded
+ * Laplace(loc, scale) bids, cleared by nth_price_auction(n=2, num_winners=1) incl. its zero
+ * padding for m < 3 (helpers:156-161). */
+enum { ADC_IMPLICIT = 0, ADC_EXPLICIT = 1, ADC_IMPLICIT_MULTI = 2 };
 enum { ADC_F32 = 0, ADC_F64 = 1 };            /* dtype tags for bids / float outputs             */
 
 /* Keyword parameters, SoA float64 (gymnasium_kw_utils.py:20-28).  env_stride = 0: one keyword set
@@ -74,6 +80,8 @@ typedef struct adc_keywords {
     double *cvr;
     const double *rev_mean;
     const double *rev_std;
+    const double *max_bidders;   /* ADC_IMPLICIT_MULTI only, else NULL (classes:659-662, default 30)  */
+    const double *participation; /* ADC_IMPLICIT_MULTI only, else NULL (classes:663, default 3/5)     */
     double impression_thresh; /* explicit only (0.05, gymnasium_kw_utils.py:81) */
 } adc_keywords;
 
@@ -143,13 +151,22 @@ typedef struct adc_detail {
     int32_t *n_recorded;    /* [E,K] min(clicks, cap)                                        */
     double *volume_seen;    /* [E,K] combine_outcomes' share denominator (bsim:130-146): the
                                auctions of the lanes that had at least one impression        */
+    int32_t *lane_clicks;   /* [E,K,24] accepted clicks of each (sub-step) lane, 0 for lanes after
+                               the early break: with lane_convs it splits the two lists per lane,
+                               which is what the reference's per-lane profit sums need (bsim:117,138) */
+    int32_t *lane_convs;    /* [E,K,24] conversions of each lane                                */
 } adc_detail;
 
 typedef struct adc_step_args {
     int32_t E;              /* envs owned by this call / rank                      */
     uint32_t env_base;      /* global id of env 0 (Philox counter; rank sharding)  */
-    uint32_t step;          /* global step counter (Philox counter); must advance by 1 per call
-                               on a given scratch (its parity double-buffers serial_count)    */
+    uint32_t step;          /* Philox counter word: steps since the last seeded reset, so that
+                               reset(seed=s) replays the same trajectory                       */
+    uint32_t parity;        /* must flip (advance by 1) on every call that uses a given scratch:
+                               its low bit double-buffers serial_count / work_counter          */
+    int32_t device;         /* CUDA device ordinal every pointer lives on; the call fails with
+                               ADC_ERR_INVALID when it is not the calling thread's current
+                               device.  -1: not checked                                        */
     uint64_t seed;          /* Philox key                                          */
     int32_t n_lanes;        /* lanes per (env,keyword) unit.  0 / -32: warp-batched hot kernel with 32
                                lanes per unit (fastest for every volume: the volume remainders of a
@@ -164,6 +181,11 @@ typedef struct adc_step_args {
     adc_drift drift;
     const void *bids;       /* [E,K] dollars, canonicalised to cents inside (env:215) */
     int32_t bids_dtype;     /* ADC_F32 / ADC_F64 */
+    int32_t f32_ties;       /* 1 (with ADC_F32 bids): numpy >= 2 keeps a float32 bid float32 through
+                               np.maximum / round (env:215), so searchsorted compares float32(cents/100)
+                               upcast to float64 with the float64 competitor bids: a bid whose float32
+                               value lies above its cent value WINS ties (0.30f > 0.30), one below
+                               loses them.  0: float64 semantics, ties always lose */
     const void *budget_in;  /* optional [E] dollars, same dtype as bids: rounded to cents and stored */
     /* Shared auctions (several bidders in ONE auction; free-running implicit keywords only).
      * env_group = A > 1: envs [g*A, (g+1)*A) are the A bidders of world g and share every draw
@@ -195,6 +217,8 @@ typedef struct adc_step_args {
 typedef struct adc_tape {
     const int32_t *volume;                              /* [E,K]                          */
     const int64_t *comp_off;  const int32_t *comp_cents;   /* implicit: one per auction      */
+    const double *comp_f64;   /* ADC_IMPLICIT_MULTI (shares comp_off): the auction's clearing price,
+                                 max(other bids, and 0 when fewer than 3 bidders) -- helpers:156-177 */
     const int64_t *click_off; const double *u_click;       /* one per click slot             */
     const int64_t *conv_off;  const double *u_conv;        /* one per accepted click         */
     const int64_t *rev_off;   const int32_t *rev_cents;    /* one per conversion             */

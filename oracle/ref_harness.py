@@ -239,12 +239,23 @@ class RustShim(types.ModuleType):
 
     @staticmethod
     def repr_outcomes_py(outcomes):  # src/lib.rs:250-275 (info string only)
-        def f(v):  # Rust `{}` on f64 prints 1 for 1.0
+        def f(v):  # Rust `{}` on f64: shortest round-trip digits, always positional, 1.0 -> "1"
+            from decimal import Decimal
             v = float(v)
-            return repr(int(v)) if v == int(v) and abs(v) < 1e16 else repr(v)
+            if v != v or v in (float("inf"), float("-inf")):
+                return "NaN" if v != v else ("inf" if v > 0 else "-inf")
+            s = format(Decimal(repr(v)), "f")
+            return s.rstrip("0").rstrip(".") if "." in s else s
+
+        def g(v):  # Rust `{:?}` on f64: like Python's repr, exponent written 1.5e-7 / 1e16
+            s = repr(float(v))
+            if "e" in s:
+                mant, exp = s.split("e")
+                return f"{mant[:-2] if mant.endswith('.0') else mant}e{int(exp)}"
+            return s
 
         def fl(vs):  # Rust `{:?}` on Vec<f64>
-            return "[" + ", ".join(repr(float(v)) for v in vs) + "]"
+            return "[" + ", ".join(g(v) for v in vs) + "]"
 
         parts = []
         for o in outcomes:

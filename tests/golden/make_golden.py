@@ -89,6 +89,26 @@ def main():
     record_case("rec_explicit_budget_k4", e, bids_for(4, 3, 3.0), 6.0,
                 dict(kind="explicit", note="binding scalar budget 6.0"))
 
+    # float32 bids (what the Box(dtype=float32) action space yields): numpy >= 2 keeps them float32
+    # through np.maximum / round (env:215), so a bid whose float32 value lies above its cent value
+    # WINS ties against the float64 competitor bids.  Own rng: the cases below keep
+    # their bids.
+    rng32 = np.random.default_rng(32)
+    env32 = implicit_env(128, 0.5, 5, 7)
+    bids32 = [np.round(rng32.uniform(0.3, 0.9, 5), 2).astype(np.float32) for _ in range(4)]
+    record_case("rec_implicit_f32_bids_k5", env32, bids32, 1000.0,
+                dict(kind="implicit", f32_bids=True, note="float32 bids: numpy >= 2 tie rule"))
+    case32 = golden_io.load_case(os.path.join(HERE, "rec_implicit_f32_bids_k5.npz"))
+    differs = 0
+    for s in case32.steps:  # the fixture must exercise the rule: float64 semantics give other counts
+        kw = orc.KeywordSet(orc.IMPLICIT, *[s.kw_before[n] for n in golden_io.PARAMS])
+        t = s.tape
+        o = orc.step_replay(kw, s.bid_cents, s.budget, orc.Tape(
+            t.volume, t.comp_off, t.comp_cents, t.click_off, np.r_[t.u_click, np.ones(256)], t.conv_off,
+            np.r_[t.u_conv, np.ones(256)], t.rev_off, np.r_[t.rev_cents, np.ones(256, np.int32)]))
+        differs += int(not np.array_equal(o["impressions"], s.impressions))
+    assert differs > 0, "no tie was won in the float32 fixture; change its seed"
+
     # --- Philox tapes through the reference --------------------------------------------------
     def philox_case(name, kw, budget, alias, mask, n_steps, seed, env_id, hi):
         env = rd.build_replay_env(kw, budget=budget, drift_mask=mask, max_days=3)

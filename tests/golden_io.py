@@ -32,6 +32,8 @@ def save_case(path: str, steps: List[Dict], meta: Dict) -> None:
         for n in OUT_FIELDS:
             arrs[p + n] = np.asarray(s[n])
         arrs[p + "scalars"] = np.array([float(s[n]) for n in SCALARS], np.float64)
+        if "info_outcomes" in s:  # info["bidding_outcomes"], the reference's string (lib.rs:250-275)
+            arrs[p + "info_outcomes"] = np.array(str(s["info_outcomes"]))
     meta = dict(meta, n_steps=len(steps), kind_id=0 if meta["kind"] == "implicit" else 1)
     arrs["meta"] = np.array(json.dumps(meta))
     np.savez_compressed(path, **arrs)
@@ -53,5 +55,6 @@ def load_case(path: str) -> SimpleNamespace:
             setattr(s, n, z[p + n])
         for n, v in zip(SCALARS, z[p + "scalars"]):
             setattr(s, n, float(v))
+        s.info_outcomes = str(z[p + "info_outcomes"]) if p + "info_outcomes" in z else None
         steps.append(s)
     return SimpleNamespace(meta=meta, kind=meta["kind_id"], steps=steps, K=len(steps[0].bid_cents))

@@ -27,7 +27,9 @@ def test_header_symbols_are_exported():
 def test_struct_layout_matches_compiled_library():
     from adcraft_b200 import _capi
     lib = _capi.load()
-    assert lib.adc_abi_version() == 3
+    header = open(os.path.join(ROOT, "include", "adcraft_b200.h")).read()
+    declared = int(re.search(r"#define\s+ADC_ABI_VERSION\s+(\d+)", header).group(1))
+    assert lib.adc_abi_version() == declared == _capi.ABI_VERSION
     assert lib.adc_sizeof_step_args() == C.sizeof(_capi.StepArgs)
     assert lib.adc_sizeof_tape() == C.sizeof(_capi.Tape)
 

@@ -35,7 +35,8 @@ def _make_env(case, E, **kw):
     env = VectorBiddingSimulation(
         E, num_keywords=case.K, keywords=_table(case, s0, E), budget=s0.budget,
         max_days=case.meta.get("max_days", 60), updater_mask=None if mask is None else [bool(m) for m in mask],
-        budget_alias=bool(s0.budget_alias), obs_dtype=torch.float64, autoreset=False, device="cuda", **kw)
+        budget_alias=bool(s0.budget_alias), obs_dtype=torch.float64, autoreset=False, device="cuda",
+        f32_ties=bool(case.meta.get("f32_bids")), **kw)
     env.reset()
     return env
 
@@ -75,7 +76,9 @@ def test_replay_reproduces_reference(path, E, force_serial):
     for s in case.steps:
         tape = DeviceTape.from_host([s.tape] * E, "cuda", pack=packed)
         bids = torch.from_numpy(np.tile(s.bid_cents / 100.0, (E, 1))).cuda()
-        budget = torch.full((E,), s.budget, dtype=torch.float64, device="cuda")  # passed every step
+        if case.meta.get("f32_bids"):  # the tie rule needs the bids in float32 (adc_step_args.f32_ties)
+            bids = torch.from_numpy(np.tile(s.bid_cents.astype(np.float32) / np.float32(100), (E, 1))).cuda()
+        budget = torch.full((E,), s.budget, dtype=bids.dtype, device="cuda")  # passed every step
         obs, reward, term, trunc, _ = env.step_replay({"keyword_bids": bids, "budget": budget}, tape,
                                                       force_serial=force_serial)
         _check(case, s, obs, reward, term, trunc, env, E, cum)

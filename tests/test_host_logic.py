@@ -80,3 +80,20 @@ def test_spaces_match_reference_definitions():
                 cumulative_profit=np.zeros(1, np.float32), days_passed=np.zeros(1, np.float32))
     assert o.contains(zero)  # tests/test_env.py:52-57
     assert a.contains(a.sample())
+
+
+def test_rust_float_formatting():
+    """info["bidding_outcomes"] is built by Rust's format! (src/lib.rs:269): `{}` on f64 is always
+    positional and drops a trailing .0; `{:?}` (inside Vec<f64>) keeps one fractional digit and
+    switches to `1.5e-7`-style exponents below 1e-4 and from 1e16 on."""
+    from adcraft_b200.gymnasium_kw_env import _rust_debug, _rust_display, repr_outcomes
+    assert [_rust_display(v) for v in (0.75, 1.0, 0.0, 100.0, 1e-7, -2.5e-16, 1e21, 0.30000001192092896)] == [
+        "0.75", "1", "0", "100", "0.0000001", "-0.00000000000000025", "1000000000000000000000",
+        "0.30000001192092896"]
+    assert [_rust_debug(v) for v in (0.57, 1.0, 0.0, 1e-4, 9.9e-5, 1.5e-7, 1e16, 123456.789)] == [
+        "0.57", "1.0", "0.0", "0.0001", "9.9e-5", "1.5e-7", "1e16", "123456.789"]
+    s = repr_outcomes([dict(bid=0.5, impressions=3, impression_share=0.6, buyside_clicks=2, costs=[0.41, 0.0],
+                            sellside_conversions=1, revenues=[1.0], revenues_per_cost=[0.0, 1.0], profit=0.59)])
+    assert s == ("[{'bid': 0.5, 'impressions': 3, 'impression_share': 0.6, 'buyside_clicks': 2, "
+                 "'costs': [0.41, 0.0], 'sellside_conversions': 1, 'revenues': [1.0], "
+                 "'revenues_per_cost': [0.0, 1.0], 'profit': 0.59}]")
