@@ -34,6 +34,7 @@ class DeviceTape:
     drift: Optional[torch.Tensor] = None
     packed: Optional[torch.Tensor] = None       # uint8, one 16-byte aligned record per unit
     packed_off: Optional[torch.Tensor] = None   # int64 [E*K+1] byte offsets
+    comp_f64: Optional[torch.Tensor] = None     # multi-bidder keywords: clearing price per auction
 
     def c_struct(self) -> _capi.Tape:
         t = _capi.Tape()
