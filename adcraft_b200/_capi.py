@@ -79,6 +79,16 @@ class StepArgs(C.Structure):
     ]
 
 
+class IdealArgs(C.Structure):
+    _fields_ = [
+        ("E", C.c_int32), ("env_base", C.c_uint32), ("step", C.c_uint32), ("device", C.c_int32),
+        ("seed", C.c_uint64), ("kw", Keywords), ("n_samples", C.c_int32), ("n_grid", C.c_int32),
+        ("bid_grid_host", C.c_void_p), ("samples_cents", C.c_void_p), ("ideal_profit", C.c_void_p),
+        ("positive_frac", C.c_void_p), ("best_bid_index", C.c_void_p), ("impression_rate", C.c_void_p),
+        ("expected_cpc", C.c_void_p),
+    ]
+
+
 class Tape(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "volume", "comp_off", "comp_cents", "comp_f64", "click_off", "u_click", "conv_off", "u_conv",
@@ -114,6 +124,9 @@ def load() -> C.CDLL:
     lib.adc_step_replay.argtypes = [C.POINTER(StepArgs), C.POINTER(Tape), C.c_void_p]
     lib.adc_reset_envs.restype = C.c_int
     lib.adc_reset_envs.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.adc_ideal_profit.restype = C.c_int
+    lib.adc_ideal_profit.argtypes = [C.POINTER(IdealArgs), C.c_void_p]
+    lib.adc_sizeof_ideal_args.restype = C.c_int
     lib.adc_launch_count.restype = C.c_int64
     lib.adc_launch_count.argtypes = [C.c_int]
     if lib.adc_abi_version() != ABI_VERSION:
@@ -123,6 +136,8 @@ def load() -> C.CDLL:
             "adcraft_b200: struct layout mismatch between _capi.py and the compiled library "
             f"({lib.adc_sizeof_step_args()} vs {C.sizeof(StepArgs)}, "
             f"{lib.adc_sizeof_tape()} vs {C.sizeof(Tape)}); rebuild")
+    if lib.adc_sizeof_ideal_args() != C.sizeof(IdealArgs):
+        raise AdcError("adcraft_b200: adc_ideal_args layout mismatch; rebuild")
     _lib = lib
     return lib
 
@@ -136,4 +151,5 @@ def check(rc: int) -> None:
 EXPORTED_SYMBOLS = (
     "adc_last_error", "adc_abi_version", "adc_device_count", "adc_sizeof_step_args",
     "adc_sizeof_tape", "adc_step_philox", "adc_step_replay", "adc_reset_envs", "adc_launch_count",
+    "adc_ideal_profit", "adc_sizeof_ideal_args",
 )

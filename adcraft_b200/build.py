@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 BUILD_DIR = os.path.join(_HERE, "_build")
 LIB_PATH = os.path.join(BUILD_DIR, "libadcraft_b200.so")
-SOURCES = ["adc_step.cu", "adc_capi.cu"]
+SOURCES = ["adc_step.cu", "adc_metrics.cu", "adc_capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
     "-std=c++17", "-Xcompiler", "-fPIC", "-shared",

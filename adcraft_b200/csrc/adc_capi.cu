@@ -133,6 +133,8 @@ int adc_sizeof_step_args(void) { return (int)sizeof(adc_step_args); }
 
 int adc_sizeof_tape(void) { return (int)sizeof(adc_tape); }
 
+int adc_sizeof_ideal_args(void) { return (int)sizeof(adc_ideal_args); }
+
 int adc_device_count(void)
 {
     int n = 0;
@@ -158,6 +160,33 @@ int adc_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *
     if (rc) return rc;
     const cudaError_t e =
         adc::launch_reset_envs(E, mask, cum_profit, day, static_cast<cudaStream_t>(stream), &g_launches);
+    if (e != cudaSuccess) return fail(ADC_ERR_CUDA, "adcraft_b200: launch failed: %s", cudaGetErrorString(e));
+    return ADC_OK;
+}
+
+int adc_ideal_profit(const adc_ideal_args *a, void *stream)
+{
+    ADC_REQUIRE(a != nullptr, "args is NULL");
+    ADC_REQUIRE(a->E > 0 && a->kw.K > 0, "E and K must be > 0");
+    ADC_REQUIRE(a->kw.kind == ADC_IMPLICIT, "the ideal-profit estimator is defined for ADC_IMPLICIT keywords");
+    ADC_REQUIRE(a->kw.env_stride == 0 || a->kw.env_stride == a->kw.K, "kw.env_stride must be 0 or K");
+    ADC_REQUIRE(a->kw.vol_mean && a->kw.p1 && a->kw.p2 && a->kw.ctr && a->kw.cvr && a->kw.rev_mean,
+                "kw parameter pointer is NULL");
+    ADC_REQUIRE(a->n_samples > 0 && a->n_samples <= 65536, "n_samples must be in [1, 65536]");
+    ADC_REQUIRE(a->n_grid > 0 && a->n_grid <= ADC_IDEAL_MAX_GRID && a->bid_grid_host != nullptr, "bid grid");
+    ADC_REQUIRE(a->ideal_profit != nullptr, "ideal_profit is NULL");
+    int rc = check_device();
+    if (rc) return rc;
+    if (a->device >= 0) {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != a->device)
+            return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: the buffers live on device %d but the "
+                        "calling thread's current device is %d", a->device, cur);
+    }
+    const cudaError_t e = adc::launch_ideal_profit(*a, static_cast<cudaStream_t>(stream), &g_launches);
+    if (e == cudaErrorInvalidValue)
+        return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: a grid bid is NaN or not below 5.10");
     if (e != cudaSuccess) return fail(ADC_ERR_CUDA, "adcraft_b200: launch failed: %s", cudaGetErrorString(e));
     return ADC_OK;
 }

@@ -20,7 +20,7 @@
 
 namespace adc {
 
-enum : uint32_t { ST_AUCTION = 0u, ST_UNIT = 1u, ST_REVENUE = 2u, ST_PHANTOM = 3u };
+enum : uint32_t { ST_AUCTION = 0u, ST_UNIT = 1u, ST_REVENUE = 2u, ST_PHANTOM = 3u, ST_IDEAL = 4u };
 
 struct PhiloxKey {
     uint32_t k0, k1;

@@ -2,9 +2,10 @@
 
 ``compute_AKNCP`` / ``compute_NCP`` follow ``adcraft/experiment_utils/experiment_metrics.py:64-83``
 (inputs ``[T, K]``); the batched forms take ``[T, E, K]`` or running sums.  The ideal-profit
-estimator follows ``experiment_metrics.py:20-61`` (2048 sampled competitor bids -> sort ->
-searchsorted -> running mean; expected profit = vol_mean * impression_rate * bctr *
-(sctr * mean_rev - cpc), clipped at 0, maximised over the bid grid).
+estimator (``experiment_metrics.py:20-61``: 2048 sampled competitor bids -> sort -> searchsorted ->
+running mean; expected profit = vol_mean * impression_rate * bctr * (sctr * mean_rev - cpc),
+clipped at 0, maximised over the bid grid) is a CUDA kernel behind ``adc_ideal_profit``
+(csrc/adc_metrics.cu); ``ideal_profit`` below is its host-side call.
 
 The only collective on the path: ``reduce_metrics`` all-reduces a small float64 vector
 (NCCL for CUDA tensors, gloo for CPU tensors).
@@ -33,31 +34,52 @@ def compute_NCP(kw_profits, ideal_profits) -> float:
     return float(np.asarray(kw_profits).sum() / den)
 
 
-def implicit_bid_profile(loc: torch.Tensor, scale: torch.Tensor, bid_grid: torch.Tensor,
-                         n_samples: int = 2048, generator: Optional[torch.Generator] = None
-                         ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Batched ``get_implicit_kw_bid_cpc_impressions`` for [..., K] keywords on any device.
-
-    Returns (impression_rate, expected_cpc), each ``[..., K, len(bid_grid)]``."""
-    shape = loc.shape + (n_samples,)
-    u = torch.rand(shape, dtype=torch.float64, device=loc.device, generator=generator)
-    lap = torch.where(u >= 0.5, -torch.log(2.0 - 2.0 * u), torch.log(2.0 * u))  # numpy's laplace form
-    bids = torch.round(torch.clamp((loc[..., None] + scale[..., None] * lap).abs(), min=0.0) * 100.0) / 100.0
-    second, _ = torch.sort(bids, dim=-1)
-    grid = bid_grid.to(torch.float64).expand(loc.shape + (bid_grid.numel(),)).contiguous()
-    idx = torch.searchsorted(second, grid, right=True)
-    rate = idx.to(torch.float64) / n_samples
-    idx = torch.clamp(idx, max=n_samples - 1)
-    mean_prices = torch.cumsum(second, dim=-1) / torch.arange(1, n_samples + 1, device=loc.device, dtype=torch.float64)
-    return rate, torch.gather(mean_prices, -1, idx)
+DEFAULT_BID_GRID = np.arange(0.01, 3.00, 0.01)  # the notebooks' allowed_bids (run_heatmap_experiments cell 3)
 
 
-def max_expected_bid_profits(vol_mean, bctr, sctr, mean_rev, cpc, rate):
-    """``get_max_expected_bid_profits`` (experiment_metrics.py:40-61), batched over [..., K]."""
-    exp = torch.clamp(vol_mean[..., None] * rate * bctr[..., None] * (sctr[..., None] * mean_rev[..., None] - cpc),
-                      min=0.0)
-    best, arg = exp.max(dim=-1)
-    return torch.clamp(best, min=0.0), (exp > 0).sum(-1).to(torch.float64) / exp.shape[-1], arg
+def ideal_profit(env, bid_grid: Optional[np.ndarray] = None, n_samples: int = 2048, *,
+                 samples_cents: Optional[torch.Tensor] = None, step: Optional[int] = None,
+                 profile: bool = False) -> Dict[str, torch.Tensor]:
+    """``get_implicit_kw_bid_cpc_impressions`` + ``get_max_expected_bid_profits``
+    (experiment_metrics.py:20-61) for every (env, keyword) of a VectorBiddingSimulation, on its
+    device, through the C ABI (``adc_ideal_profit``: counting sort of the sampled competitor bids
+    in shared memory, one warp per unit).  Reads the env's CURRENT (drifted) parameters.
+
+    A keyword set shared by all envs gives ``[1, K]`` results (broadcast them), per-env sets
+    ``[E, K]``.  ``samples_cents`` ([rows, K, n_samples] int32 on the device) replaces the Philox
+    draws with given competitor bids (parity with the reference on its own samples).
+    Returns ``ideal`` (max expected profit), ``positive_frac``, ``best_bid_index`` and, with
+    ``profile``, ``impression_rate`` / ``expected_cpc`` of shape ``[rows, K, len(bid_grid)]``."""
+    import ctypes as C
+    from . import _capi
+    grid = np.ascontiguousarray(DEFAULT_BID_GRID if bid_grid is None else bid_grid, dtype=np.float64)
+    dev, K = env.device, env.num_keywords
+    rows = env.num_envs if env._kw_stride else 1
+    a = _capi.IdealArgs()
+    a.E, a.env_base, a.seed = rows, env.env_base, env.seed & 0xFFFFFFFFFFFFFFFF
+    a.step = (env._step_count if step is None else step) & 0xFFFFFFFF
+    a.device = dev.index
+    kw = a.kw
+    kw.kind, kw.K, kw.env_stride = env.kind, K, env._kw_stride
+    for n in ("vol_mean", "vol_std", "p1", "p2", "ctr", "cvr", "rev_mean", "rev_std"):
+        setattr(kw, n, env._kw_dev[n].data_ptr())
+    a.n_samples, a.n_grid, a.bid_grid_host = int(n_samples), len(grid), grid.ctypes.data
+    if samples_cents is not None:
+        assert samples_cents.dtype == torch.int32 and samples_cents.is_contiguous() and samples_cents.device == dev
+        assert tuple(samples_cents.shape) == (rows, K, n_samples)
+        a.samples_cents = samples_cents.data_ptr()
+    f64 = torch.float64
+    out = dict(ideal=torch.empty(rows, K, dtype=f64, device=dev), positive_frac=torch.empty(rows, K, dtype=f64, device=dev),
+               best_bid_index=torch.empty(rows, K, dtype=torch.int32, device=dev))
+    a.ideal_profit, a.positive_frac = out["ideal"].data_ptr(), out["positive_frac"].data_ptr()
+    a.best_bid_index = out["best_bid_index"].data_ptr()
+    if profile:
+        out["impression_rate"] = torch.empty(rows, K, len(grid), dtype=f64, device=dev)
+        out["expected_cpc"] = torch.empty(rows, K, len(grid), dtype=f64, device=dev)
+        a.impression_rate, a.expected_cpc = out["impression_rate"].data_ptr(), out["expected_cpc"].data_ptr()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    env._call(env._lib.adc_ideal_profit, C.byref(a), C.c_void_p(stream))
+    return out
 
 
 class MetricAccumulator:

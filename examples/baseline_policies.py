@@ -42,11 +42,7 @@ def main() -> int:
     env.reset(seed=args.seed)
     pol = (VectorNaiveInterpolationStrategy(E, K, device=dev, seed=args.seed) if args.policy == "interpolation"
            else VectorNaiveZeroMarginStrategy(E, K, device=dev, seed=args.seed))
-    tab = env.keywords
-    t = lambda a: torch.as_tensor(a, device=dev)
-    grid = torch.arange(0.01, 3.00, 0.01, dtype=torch.float64, device=dev)
-    rate, cpc = M.implicit_bid_profile(t(tab.p1), t(tab.p2), grid)
-    ideal, _, _ = M.max_expected_bid_profits(t(tab.vol_mean), t(tab.ctr), t(tab.cvr), t(tab.rev_mean), cpc, rate)
+    ideal = M.ideal_profit(env)["ideal"]  # [1, K]: the keyword set is shared by all envs
     acc = M.MetricAccumulator(E, K, dev)
     if args.policy == "interpolation":
         action = pol.sample_action()
@@ -58,7 +54,7 @@ def main() -> int:
     for _ in range(args.days):
         obs, reward, term, trunc, _ = env.step({"keyword_bids": action["keyword_bids"], "budget": action["budget"]})
         total_reward += reward
-        acc.update(obs, reward, ideal=ideal[None], done=term)
+        acc.update(obs, reward, ideal=ideal, done=term)
         pol.update_all_caches(action, obs)
         action = pol.sample_action()
     torch.cuda.synchronize(dev)

@@ -63,11 +63,7 @@ def main():
     obs, _ = env.reset(seed=5)
     torch.manual_seed(1234)  # same policy replica on every rank
     policy = Policy(K).to(dev)
-    tab = env.keywords
-    t = lambda a: torch.as_tensor(a, device=dev)
-    grid = torch.arange(0.01, 3.00, 0.01, dtype=torch.float64, device=dev)
-    rate, cpc = M.implicit_bid_profile(t(tab.p1), t(tab.p2), grid)
-    ideal, _, _ = M.max_expected_bid_profits(t(tab.vol_mean), t(tab.ctr), t(tab.cvr), t(tab.rev_mean), cpc, rate)
+    ideal = M.ideal_profit(env)["ideal"]  # [1, K]: the keyword set is shared by all envs
     acc = M.MetricAccumulator(E, K, dev)
     buf_obs = torch.empty(T, E, 5 * K + 2, device=dev) if E * K * T < 2e9 else None
     buf_act = torch.empty(T, E, K, device=dev) if buf_obs is not None else None
@@ -81,7 +77,7 @@ def main():
             mu, std, _v = policy(flat)
             bids = (mu + std * torch.randn_like(mu)).clamp(min=0.01)
             obs, reward, term, trunc, _ = env.step({"keyword_bids": bids, "budget": budget})
-            acc.update(obs, reward, ideal=ideal[None], done=term)
+            acc.update(obs, reward, ideal=ideal, done=term)
             if buf_obs is not None:
                 buf_obs[i], buf_act[i] = flat, bids
             buf_rew[i] = reward

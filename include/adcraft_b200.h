@@ -229,12 +229,39 @@ typedef struct adc_tape {
     const int64_t *packed_off;                          /* [E*K+1] byte offsets into packed */
 } adc_tape;
 
+/* Ideal-profit estimator behind the AKNCP / NCP metrics (experiment_metrics.py:20-61): per (env,
+ * implicit keyword) n_samples competitor bids -> sort -> searchsorted(side="right") of every grid bid
+ * -> impression rate and mean price of the idx + 1 lowest samples -> expected profit
+ * vol_mean * rate * bctr * (sctr * mean_rev - cpc) clipped at 0 -> max over the grid.  Recomputed
+ * per step when the keywords drift (the reference's notebooks call it once per reset). */
+#define ADC_IDEAL_MAX_GRID 512
+typedef struct adc_ideal_args {
+    int32_t E;
+    uint32_t env_base;
+    uint32_t step;               /* Philox counter word of the sampling stream                  */
+    int32_t device;              /* like adc_step_args.device                                   */
+    uint64_t seed;
+    adc_keywords kw;             /* ADC_IMPLICIT; reads p1, p2, vol_mean, ctr, cvr, rev_mean      */
+    int32_t n_samples;           /* 2048 in the reference (metrics.py:21), <= 65536             */
+    int32_t n_grid;              /* <= ADC_IDEAL_MAX_GRID                                       */
+    const double *bid_grid_host; /* [n_grid] HOST array, e.g. np.arange(0.01, 3.00, 0.01); every bid
+                                    below 5.10 (the exact range of the counting sort)           */
+    const int32_t *samples_cents; /* optional [E,K,n_samples] pre-drawn competitor bids in cents
+                                     (parity mode); NULL: drawn from the Philox stream         */
+    double *ideal_profit;        /* [E,K] max over the grid, >= 0 (metrics.py:58)               */
+    double *positive_frac;       /* optional [E,K] share of grid bids with positive profit (:59) */
+    int32_t *best_bid_index;     /* optional [E,K] argmax (:59)                                  */
+    double *impression_rate;     /* optional [E,K,n_grid] (metrics.py:31)                        */
+    double *expected_cpc;        /* optional [E,K,n_grid] (metrics.py:34-35)                     */
+} adc_ideal_args;
+
 const char *adc_last_error(void);
 int adc_abi_version(void);
 int adc_device_count(void);
 /* sizeof(adc_step_args) / sizeof(adc_tape) as compiled: lets an FFI binding check its layout. */
 int adc_sizeof_step_args(void);
 int adc_sizeof_tape(void);
+int adc_sizeof_ideal_args(void);
 
 /* One free-running env step for E envs (counter-based Philox draws keyed by
  * (seed, env_base+e, keyword, step)).  Launches: fused lane kernel, then the exact serial kernel
@@ -246,6 +273,9 @@ int adc_step_replay(const adc_step_args *args, const adc_tape *tape, void *strea
 
 /* Reset per-env episode state of the envs with mask[e] != 0 (mask NULL: all). */
 int adc_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day, void *stream);
+
+/* The ideal-profit estimator above for E x K units. */
+int adc_ideal_profit(const adc_ideal_args *args, void *stream);
 
 /* Number of kernel launches issued by this library on the calling thread since the last call
  * with reset != 0 (bench.py's gpu_launches). */

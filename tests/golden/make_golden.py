@@ -156,6 +156,29 @@ def main():
     philox_case("phx_explicit_k6", kw_e, 1000.0, False, [True] * K, 3, 99, 3, 3.0)
     philox_case("phx_explicit_budget_k6", kw_e, 9.0, True, None, 3, 99, 5, 3.0)
 
+    # --- ideal-profit estimator of the AKNCP / NCP metrics (experiment_metrics.py:20-61) -------
+    met = ref["metrics"]
+    env = implicit_env(128, 0.8, 7, 1, mask=[True] * 7)
+    for _ in range(3):  # drifted parameters: the estimator reads the current ones
+        env.step({"keyword_bids": np.full(7, 0.75), "budget": 100000.0})
+    allowed_bids = np.arange(0.01, 3.00, 0.01)  # run_heatmap_experiments.ipynb cell 3
+    kwset = rd.keywordset_from_env(env)
+    samples, irs, cpcs, best, frac, arg = [], [], [], [], [], []
+    for k, (kwd, params) in enumerate(zip(env.keywords, env.keyword_params)):
+        env.np_random.log = log = []
+        ir, cpc = met.get_implicit_kw_bid_cpc_impressions(kwd, allowed_bids)
+        env.np_random.log = None
+        assert len(log) == 1 and log[0][0] == "laplace"
+        c = np.around(np.maximum(np.abs(log[0][2]), 0.0).astype(float), 2).ravel()  # helpers:108-113
+        samples.append(np.rint(c * 100).astype(np.int32))
+        b, f, a = met.get_max_expected_bid_profits(params, cpc, ir)
+        irs.append(ir); cpcs.append(cpc); best.append(b); frac.append(f); arg.append(a)
+    np.savez_compressed(os.path.join(HERE, "ideal_profit.npz"), allowed_bids=allowed_bids,
+                        samples_cents=np.stack(samples), impression_rate=np.stack(irs), expected_cpc=np.stack(cpcs),
+                        ideal_profit=np.array(best), positive_frac=np.array(frac), best_bid_index=np.array(arg),
+                        **{"kw_" + n: getattr(kwset, n) for n in golden_io.PARAMS})
+    print("wrote ideal_profit", np.round(best, 3))
+
     # --- notebook known-answer lane ---------------------------------------------------------
     env = implicit_env(16, 0.5, 2, 0, max_days=10)
     kw0 = env.keywords[0]

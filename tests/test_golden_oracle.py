@@ -9,7 +9,7 @@ import pytest
 import golden_io
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = sorted(glob.glob(os.path.join(HERE, "golden", "*_*.npz")))
+CASES = sorted(glob.glob(os.path.join(HERE, "golden", "[rp][eh][cx]_*.npz")))
 CASES = [c for c in CASES if not c.endswith("notebook_lane.npz")]
 
 

@@ -68,10 +68,7 @@ def test_device_metrics_against_host_definitions():
     env = VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=1e5, device="cuda", seed=1,
                                   obs_dtype=torch.float64)
     env.reset()
-    grid = torch.arange(0.01, 3.00, 0.01, dtype=torch.float64, device="cuda")
-    dev = lambda n: torch.tensor(getattr(table, n), device="cuda")
-    rate, cpc = m.implicit_bid_profile(dev("p1"), dev("p2"), grid)
-    ideal, _, _ = m.max_expected_bid_profits(dev("vol_mean"), dev("ctr"), dev("cvr"), dev("rev_mean"), cpc, rate)
+    ideal = m.ideal_profit(env)["ideal"][0]
     acc = m.MetricAccumulator(E, K, "cuda")
     profits, bids = [], torch.full((E, K), 0.75, dtype=torch.float64, device="cuda")
     for t in range(10):

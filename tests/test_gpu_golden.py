@@ -17,7 +17,7 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = [c for c in sorted(glob.glob(os.path.join(HERE, "golden", "*_*.npz")))
+CASES = [c for c in sorted(glob.glob(os.path.join(HERE, "golden", "[rp][eh][cx]_*.npz")))
          if not c.endswith("notebook_lane.npz")]
 IDS = [os.path.basename(c)[:-4] for c in CASES]
 

@@ -44,22 +44,6 @@ def test_metrics_definitions():
     assert s["n_envs"] == 1.0 and abs(s["reward_sum"] - kw.sum()) < 1e-9
 
 
-def test_ideal_profit_estimator_shapes_and_monotonicity():
-    from adcraft_b200 import metrics as m
-    g = torch.Generator().manual_seed(0)
-    loc, scale = torch.tensor([0.6, 0.9], dtype=torch.float64), torch.tensor([0.1, 0.05], dtype=torch.float64)
-    grid = torch.arange(0.01, 3.00, 0.01, dtype=torch.float64)
-    rate, cpc = m.implicit_bid_profile(loc, scale, grid, generator=g)
-    assert rate.shape == (2, len(grid)) and cpc.shape == rate.shape
-    assert torch.all(rate[:, 1:] >= rate[:, :-1]) and float(rate[0, -1]) == 1.0
-    assert abs(float(rate[0, 59]) - 0.5) < 0.06  # P(|Laplace(0.6,0.1)| <= 0.60) ~ 0.5
-    best, frac, arg = m.max_expected_bid_profits(torch.tensor([128.0, 128.0], dtype=torch.float64),
-                                                 torch.tensor([0.5, 0.5], dtype=torch.float64),
-                                                 torch.tensor([0.8, 0.8], dtype=torch.float64),
-                                                 torch.tensor([1.0, 0.5], dtype=torch.float64), cpc, rate)
-    assert best[0] > 0 and best[1] == 0.0 and frac[1] == 0.0
-
-
 def test_env_range_partitions_everything():
     from adcraft_b200.sharding import env_range
     for total, world in [(4096, 8), (10, 3), (7, 8), (1 << 20, 8)]:
