@@ -13,8 +13,9 @@ results do not depend on N.
 One JSON line is printed by rank 0 (see the round contract): `value` is device-timed with the
 inputs resident in HBM, `e2e` is the same metric through VectorBiddingSimulation.step_host with
 pinned HOST buffers (H2D + D2H inside the timed region), `roofline` compares the dominant kernel
-with the measured HBM peak, `cpu_baseline` is the C oracle port timed on this box's host cores.
-`--impl reference` times only that CPU port (all host threads) on the same config.
+with the measured HBM peak, `cpu_baseline` is the reference's own Python (staged copy under
+baseline/_ref, one env per host core) timed on this box, with the C oracle port beside it.
+`--impl reference` times only that CPU reference on the same config.
 """
 from __future__ import annotations
 
@@ -55,9 +56,6 @@ UNIT = "keyword-auction-steps/s"
 K_KW, E_ENVS, BID, BUDGET, MAX_DAYS = 100, 4096, 0.75, 100000.0, 60
 SEED = 0x5EED
 B_UNIT = 24  # read bid 4 B + write 3 x int32 + 2 x f32 per (env, keyword, step)
-# Python reference (unmodified, numpy shim for the Rust helpers) measured in the build
-# container on 1 core, dense config: BASELINE.md section 2.
-PY_REFERENCE_UNITS_PER_S_1CORE = 290.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one hot-kernel launch on this workload, from the
 # committed `ncu --set full` capture (profiles/r01_flat_kernel_ncu_metrics.csv): the outputs stay in
 # the 126 MB L2 between steps, so DRAM traffic is below the 9.8 MB of algorithmic bytes.
@@ -109,25 +107,60 @@ def time_cpu_port(steps: int, warmup: int, envs: int, threads: int):
     return envs * K_KW * steps / dt, dt / steps
 
 
+def time_reference_python(steps: int, warmup: int, procs: int):
+    """The reference's own Python BiddingSimulation.step (staged copy, see oracle/ref_bench.py), one
+    env per host core.  Returns (units/s, s/step, info) or None when no reference tree travelled."""
+    from oracle import ref_bench
+    r = ref_bench.time_reference(K_KW, MEAN_VOLUME, CVR, BID, BUDGET, MAX_DAYS, steps, warmup, procs, drift=DRIFT)
+    if r is None:
+        return None
+    return r["units_per_s"], r["s_per_step"], r
+
+
+REF_NOTE = ("the reference's unmodified Python (gymnasium_kw_env / bidding_simulation / synthetic_kw_*), one "
+            "single-threaded env per host core; the nine helpers of its PyO3 module come from a numpy "
+            "restatement (oracle/ref_harness.RustShim): no Rust toolchain exists in the image")
+
+
+def cpu_baseline_block(steps: int, warmup: int):
+    """cpu_baseline of the JSON line: the reference itself when its staged copy is present
+    (kind "reference"), else the C oracle port (kind "port")."""
+    procs = os.cpu_count() or 1
+    ref = time_reference_python(steps, warmup, procs)
+    port_envs, port_steps = 256, 6
+    port_v, _ = time_cpu_port(port_steps, 1, port_envs, procs)
+    port = {"value": port_v, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": f"{port_envs} of {E_ENVS} envs x {K_KW} keywords per step, {port_steps} steps, OpenMP over envs",
+            "note": "C restatement of the reference algorithm (oracle/adcraft_oracle.c), for context"}
+    if ref is None:
+        return port, None
+    v, s_per_step, info = ref
+    return ({"value": v, "unit": UNIT, "cores": procs, "kind": "reference",
+             "sample": f"{procs} independent envs (one per core) x {K_KW} keywords, {steps} timed steps each "
+                       f"after {warmup} warm-up ({info['wall_s']:.1f} s wall incl. process start)",
+             "units_per_s_per_core": info["units_per_s_per_core"], "note": REF_NOTE, "c_port": port}, s_per_step)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
-    envs = 256  # bounded sample of the 4096-env step
-    val, s_per_step = time_cpu_port(args.steps, args.warmup, envs, threads)
+    # each reference step takes ~0.35 s per env: bound the sample so the arm ends within minutes
+    steps = min(args.steps, 40)
+    warmup = min(args.warmup, 3)
+    cpu, s_per_step = cpu_baseline_block(steps, warmup)
+    if s_per_step is None:  # no staged reference: the C port is what ran
+        threads = os.cpu_count() or 1
+        cpu["value"], s_per_step = time_cpu_port(args.steps, args.warmup, 256, threads)
+    val = cpu["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32+f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (numpy)",
         "data": "synthetic", "config": config_dict(args.gpus),
-        "cpu_baseline": {
-            "value": val, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{envs} of {E_ENVS} envs x {K_KW} keywords per step, {args.steps} steps, OpenMP over envs",
-            "note": "C restatement of the reference algorithm (oracle/adcraft_oracle.c); the reference's own "
-                    "Python+Rust cannot be built here (no cargo) and its Python path runs at about "
-                    f"{PY_REFERENCE_UNITS_PER_S_1CORE:.0f} units/s/core (BASELINE.md)"},
+        "cpu_baseline": cpu,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "timed_steps_per_env": steps,
     }
     emit(line)
     return 0
@@ -153,58 +186,70 @@ def bind_to_gpu_cpus(gpu_index: int):
 # clocks
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU, polled through NVML from a thread (a sample costs
+    ~0.1 ms, so even the 4 ms timed region of a 20-step run holds several; nvidia-smi's loop mode
+    cannot sample faster than every ~20 ms and needs ~0.1 s to come up)."""
 
-    def __init__(self, gpu_index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
+
+    def __init__(self, torch, dev):
+        import threading
+        self.samples = []  # (perf_counter, sm_mhz, reason bits)
+        self.t_mark = None
+        self.h = None
+        self.max_mhz = None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
-                 "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(dev).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:  # noqa: BLE001
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(dev.index or 0)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.h = None
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.samples.append((time.perf_counter(), sm, bits))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.0003)
 
     def mark(self):
-        """Start of the timed region: samples printed before this point (nvidia-smi needs ~0.1 s to
-        come up, so it is started ahead of the warm-up steps) are not counted."""
-        try:
-            self.skip = os.path.getsize(self.f.name)
-        except OSError:
-            self.skip = 0
+        self.t_mark = time.perf_counter()
+
+    def count_since_mark(self):
+        return sum(1 for t, _, _ in self.samples if self.t_mark is not None and t >= self.t_mark)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        if self.h is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(getattr(self, "skip", 0))
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        self.f.close()
-        os.unlink(self.f.name)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        rows = [(sm, bits) for t, sm, bits in self.samples if self.t_mark is None or t >= self.t_mark]
+        if rows:
+            reasons = set()
+            for name, attr in self.REASONS:
+                flag = getattr(self.nv, attr, 0)
+                if any(bits & flag for _, bits in rows):
+                    reasons.add(name)
+            out = {"sm_mhz": float(np.median([sm for sm, _ in rows])), "sm_max_mhz": self.max_mhz,
+                   "reasons": sorted(reasons), "samples": len(rows), "source": "NVML polled from a thread"}
         return out
 
 
@@ -403,15 +448,9 @@ def run_gpu(args):
         return 0
 
     # ---- device-timed steps, inputs resident in HBM --------------------------------------
-    sampler = ClockSampler(local_rank) if rank == 0 else None  # nvidia-smi needs ~0.1 s to come up
+    sampler = ClockSampler(torch, dev) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         obs, reward, term, trunc, _ = env.step(action)
-    if sampler is not None:  # keep the GPU under the same load until the sampler prints (at most 0.5 s)
-        t_up = time.perf_counter()
-        while os.path.getsize(sampler.f.name) == 0 and time.perf_counter() - t_up < 0.5:
-            for _ in range(20):
-                obs, reward, term, trunc, _ = env.step(action)
-            torch.cuda.synchronize(dev)
     if world > 1:  # NCCL connects lazily: establish the all-reduce path before the timed region
         for _ in range(2):
             episode_reduce(obs, reward, term)
@@ -434,6 +473,14 @@ def run_gpu(args):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = int(lib.adc_launch_count(0))
+    if sampler is not None and sampler.count_since_mark() < 5:
+        # the timed region was shorter than a few NVML polls: keep the GPU under the identical load
+        # (same steps, untimed) until the sampler has seen it
+        t_up = time.perf_counter()
+        while sampler.count_since_mark() < 5 and time.perf_counter() - t_up < 0.25:
+            for _ in range(20):
+                env.step(action)
+            torch.cuda.synchronize(dev)
     clocks = sampler.stop() if sampler else None
     dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -502,21 +549,13 @@ def run_gpu(args):
     # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        envs = 256
-        cpu_steps = 6
-        v, _ = time_cpu_port(cpu_steps, 1, envs, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{envs} of {E_ENVS} envs x {K_KW} keywords per step, {cpu_steps} steps, OpenMP over envs",
-               "note": f"C oracle port; the reference's Python path runs at about "
-                       f"{PY_REFERENCE_UNITS_PER_S_1CORE:.0f} units/s/core (BASELINE.md)"}
+        cpu, _ = cpu_baseline_block(6, 1)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "i32+f32", "data": "synthetic",
-        "config": config_dict(n_gpus, {"n_lanes": env.n_lanes,
-                                       "n_lanes_meaning": "0/-32: warp-batched kernel, 32 lanes per unit; -16/-8: sub-warp groups"}),
+        "config": config_dict(n_gpus),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "how": "step_host: kernels read pinned host bids and write pinned host observations directly "

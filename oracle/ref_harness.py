@@ -41,10 +41,36 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 
 REFERENCE_ROOT = os.environ.get("ADCRAFT_REFERENCE_ROOT", "/root/reference")
+# git-ignored copy of the reference's hot-path .py files made by __graft_entry__.build() in the build
+# container: it travels to the GPU box with the tree, /root/reference does not
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+HOT_PATH_FILES = (
+    "adcraft/__init__.py", "adcraft/bidding_simulation.py", "adcraft/gymnasium_kw_env.py",
+    "adcraft/gymnasium_kw_utils.py", "adcraft/synthetic_kw_classes.py", "adcraft/synthetic_kw_helpers.py",
+    "adcraft/experiment_utils/__init__.py", "adcraft/experiment_utils/experiment_quantiles.py",
+    "adcraft/experiment_utils/experiment_metrics.py", "adcraft/experiment_utils/experiment_configs.py",
+    "adcraft/pull_quantiles_data/__init__.py", "adcraft/pull_quantiles_data/quantiles_to_keywords.py",
+)
 
 
-def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "adcraft", "bidding_simulation.py"))
+def reference_available(root: Optional[str] = None) -> bool:
+    return os.path.isfile(os.path.join(root or REFERENCE_ROOT, "adcraft", "bidding_simulation.py"))
+
+
+def stage_reference(dst: str = STAGED_ROOT, src: Optional[str] = None) -> Optional[str]:
+    """Copy the reference's unmodified hot-path Python files to the git-ignored ``baseline/_ref`` so
+    that bench.py's reference arm can time them on the GPU box's host cores.  Returns the staged
+    root, or None when the reference tree is not present (on the GPU box: use what travelled)."""
+    import shutil
+    src = src or REFERENCE_ROOT
+    if not reference_available(src):
+        return dst if reference_available(dst) else None
+    for rel in HOT_PATH_FILES:
+        a, b = os.path.join(src, rel), os.path.join(dst, rel)
+        os.makedirs(os.path.dirname(b), exist_ok=True)
+        if not os.path.exists(b) or open(a, "rb").read() != open(b, "rb").read():
+            shutil.copyfile(a, b)
+    return dst
 
 
 # --------------------------------------------------------------------------- #
@@ -383,10 +409,14 @@ def _make_gymnasium_stub() -> types.ModuleType:
 _LOADED: Dict[str, Any] = {}
 
 
-def load_reference() -> Dict[str, Any]:
-    """Import the reference modules (once) and return them with the shim."""
+def load_reference(root: Optional[str] = None) -> Dict[str, Any]:
+    """Import the reference modules (once) and return them with the shim.  ``root``: the tree to
+    import from (default /root/reference; bench.py passes the staged copy)."""
+    global REFERENCE_ROOT
     if _LOADED:
         return _LOADED
+    if root is not None:
+        REFERENCE_ROOT = root
     if not reference_available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
     if "gymnasium" not in sys.modules:
