@@ -48,6 +48,7 @@ class StepOut(C.Structure):
         ("cost_cents", C.c_void_p), ("revenue_cents", C.c_void_p), ("reward", C.c_void_p),
         ("obs_cum_profit", C.c_void_p), ("obs_days", C.c_void_p), ("terminated", C.c_void_p),
         ("truncated", C.c_void_p), ("remaining_budget", C.c_void_p),
+        ("episode_profit_cents", C.c_void_p),
     ]
 
 
@@ -56,6 +57,7 @@ class Scratch(C.Structure):
         ("serial_list", C.c_void_p), ("serial_count", C.c_void_p), ("env_profit", C.c_void_p),
         ("env_cost", C.c_void_p), ("env_done", C.c_void_p), ("unit_cost_f64", C.c_void_p),
         ("work_counter", C.c_void_p), ("acc_impressions", C.c_void_p), ("acc_clicks", C.c_void_p), ("acc_conversions", C.c_void_p),
+        ("serial_ws", C.c_void_p), ("serial_ws_bytes", C.c_int64),
     ]
 
 
@@ -127,6 +129,8 @@ def load() -> C.CDLL:
     lib.adc_ideal_profit.restype = C.c_int
     lib.adc_ideal_profit.argtypes = [C.POINTER(IdealArgs), C.c_void_p]
     lib.adc_sizeof_ideal_args.restype = C.c_int
+    lib.adc_serial_slab_bytes.restype = C.c_int64
+    lib.adc_serial_slab_bytes.argtypes = [C.c_int32]
     lib.adc_launch_count.restype = C.c_int64
     lib.adc_launch_count.argtypes = [C.c_int]
     if lib.adc_abi_version() != ABI_VERSION:
@@ -151,5 +155,5 @@ def check(rc: int) -> None:
 EXPORTED_SYMBOLS = (
     "adc_last_error", "adc_abi_version", "adc_device_count", "adc_sizeof_step_args",
     "adc_sizeof_tape", "adc_step_philox", "adc_step_replay", "adc_reset_envs", "adc_launch_count",
-    "adc_ideal_profit", "adc_sizeof_ideal_args",
+    "adc_ideal_profit", "adc_sizeof_ideal_args", "adc_serial_slab_bytes",
 )

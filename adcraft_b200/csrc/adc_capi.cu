@@ -65,6 +65,9 @@ int validate(const adc_step_args *a, const adc_tape *tape)
     ADC_REQUIRE((a->scratch.acc_impressions != nullptr) == (a->scratch.acc_clicks != nullptr) &&
                     (a->scratch.acc_clicks != nullptr) == (a->scratch.acc_conversions != nullptr),
                 "scratch.acc_impressions / acc_clicks / acc_conversions: give all three or none");
+    ADC_REQUIRE(a->scratch.serial_ws == nullptr ||
+                    ((reinterpret_cast<uintptr_t>(a->scratch.serial_ws) & 15u) == 0 && a->scratch.serial_ws_bytes >= 0),
+                "scratch.serial_ws must be 16-byte aligned");
     ADC_REQUIRE(a->drift.mask == nullptr || a->kw.env_stride == a->kw.K,
                 "drift needs per-env keyword parameters (kw.env_stride == K)");
     ADC_REQUIRE(a->drift.mask == nullptr || (a->drift.num_updates >= 0 && a->drift.num_updates <= a->kw.K),
@@ -81,6 +84,7 @@ int validate(const adc_step_args *a, const adc_tape *tape)
                         a->detail.lane_clicks && a->detail.lane_convs, "detail: give every array or none");
     ADC_REQUIRE(a->env_group >= 0, "env_group must be >= 0");
     ADC_REQUIRE(a->env_group <= 1 || a->E % a->env_group == 0, "E must be a multiple of env_group");
+    ADC_REQUIRE(a->f32_ties == 0 || a->env_group <= 1, "f32_ties is not defined for shared auctions");
     if (a->env_group > 1 || a->floor_cents != nullptr)
         ADC_REQUIRE(tape == nullptr && a->kw.kind == ADC_IMPLICIT,
                     "shared auctions (env_group / floor_cents) need free-running implicit keywords");
@@ -134,6 +138,8 @@ int adc_sizeof_step_args(void) { return (int)sizeof(adc_step_args); }
 int adc_sizeof_tape(void) { return (int)sizeof(adc_tape); }
 
 int adc_sizeof_ideal_args(void) { return (int)sizeof(adc_ideal_args); }
+
+int64_t adc_serial_slab_bytes(int32_t K) { return K > 0 ? adc::serial_slab_bytes(K) : 0; }
 
 int adc_device_count(void)
 {

@@ -20,7 +20,7 @@
 
 namespace adc {
 
-enum : uint32_t { ST_AUCTION = 0u, ST_UNIT = 1u, ST_REVENUE = 2u, ST_PHANTOM = 3u, ST_IDEAL = 4u };
+enum : uint32_t { ST_AUCTION = 0u, ST_UNIT = 1u, ST_REVENUE = 2u, ST_PHANTOM = 3u, ST_IDEAL = 4u, ST_COST = 5u };
 
 struct PhiloxKey {
     uint32_t k0, k1;
@@ -260,6 +260,121 @@ __device__ __forceinline__ int bid_to_cents(double bid)
     double c = rint(__dmul_rn(b, 100.0));
     if (c > 2.0e9) c = 2.0e9;
     return (int)c;
+}
+
+// ------------------------------------------------------------------------------------------
+// Free-running implicit keywords: the O(clicks) tape function.
+//
+// The reference draws a competitor bid for every auction (helpers:104-113) although only the
+// clicked auctions' prices are ever used.  Here ONE 32-bit uniform R_j per auction decides the
+// nested events  win <=> R_j < T1,  click <=> R_j < T2 = T1 ctr,  conversion <=> R_j < T3 = T2 cvr,
+// with T1 = 2^32 P(round(|Laplace|, 2) < win_cents), and each clicked auction draws its price from
+// the competitor-bid law conditioned on that event (cost_cents2).  R_j is bit-sliced: auctions
+// come in groups of 32 (bit p of a word = auction 32 g + p); level l (0 = MSB of R) of group g is
+// word (l & 3) of Philox call 8 g + (l >> 2) of the AUCTION stream, so a thread compares 32
+// auctions with the three thresholds by a few word operations per level and stops at the first
+// level where every auction is decided (about log2(3 * 32) + 1.3 levels).
+// ------------------------------------------------------------------------------------------
+struct Unit2 {
+    uint32_t t1, t2, t3;  // thresholds mod 2^32 ...
+    uint32_t full;        // ... bit i set: threshold i+1 is 2^32 ("always")
+    uint32_t h1;          // half-width (2^-31 units) of window 1, <= 2^31
+    uint32_t a1, a2;      // e^-hi of the two windows, 2^-32 units
+    float L, b;           // |loc|, scale
+    int W;                // cents the competitor must stay below
+};
+
+__device__ __forceinline__ unsigned long long rint_u64(double x)
+{
+    return x <= 0.0 ? 0ull : (unsigned long long)rint(x);
+}
+
+__device__ __forceinline__ Unit2 unit2_make(double loc, double scale, double ctr, double cvr, int win_cents)
+{
+    const double ymax = __ddiv_rn(__dsub_rn((double)win_cents, 0.5), 100.0);
+    const double L = fabs(loc);
+    const double b = scale > 1e-9 ? scale : 1e-9;
+    const double d = __dsub_rn(L, ymax);
+    const double lo1 = __ddiv_rn(d > 0.0 ? d : 0.0, b), hi1 = __ddiv_rn(__dadd_rn(L, ymax), b);
+    const double e_lo1 = exp_det(-lo1), e_hi1 = exp_det(-hi1);
+    double l1 = __dsub_rn(e_lo1, e_hi1), l2 = 0.0, e_hi2 = 1.0;
+    if (!(l1 > 0.0)) l1 = 0.0;
+    if (ymax > L) {
+        e_hi2 = exp_det(-__ddiv_rn(__dsub_rn(ymax, L), b));
+        l2 = __dsub_rn(1.0, e_hi2);
+    }
+    unsigned long long h1 = rint_u64(__dmul_rn(l1, 2147483648.0));
+    const unsigned long long h2 = rint_u64(__dmul_rn(l2, 2147483648.0));
+    unsigned long long T1 = h1 + h2;
+    if (T1 > 4294967296ull) T1 = 4294967296ull;
+    if (h1 > T1) h1 = T1;
+    unsigned long long T2 = rint_u64(__dmul_rn((double)T1, clampd(ctr, 0.0, 1.0)));
+    if (T2 > T1) T2 = T1;
+    unsigned long long T3 = rint_u64(__dmul_rn((double)T2, clampd(cvr, 0.0, 1.0)));
+    if (T3 > T2) T3 = T2;
+    const unsigned long long a1 = rint_u64(__dmul_rn(e_hi1, 4294967296.0));
+    const unsigned long long a2 = rint_u64(__dmul_rn(e_hi2, 4294967296.0));
+    Unit2 u;
+    u.t1 = (uint32_t)T1; u.t2 = (uint32_t)T2; u.t3 = (uint32_t)T3;
+    u.full = (T1 >> 32 ? 1u : 0u) | (T2 >> 32 ? 2u : 0u) | (T3 >> 32 ? 4u : 0u);
+    u.h1 = (uint32_t)h1;  // <= 2^31
+    u.a1 = a1 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)a1;
+    u.a2 = a2 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)a2;
+    u.L = (float)L; u.b = (float)b; u.W = win_cents;
+    return u;
+}
+
+// Price of a clicked auction in cents.  t = e^-E is uniform on (e^-hi1, e^-lo1) [x = L - b E] united
+// with (e^-hi2, 1) [x = L + b E]; the word picks a point of that union (all integer up to -ln).
+__device__ __forceinline__ int cost_cents2(uint32_t w, uint32_t t1, bool t1_full, uint32_t h1, uint32_t a1, uint32_t a2,
+                                           float L, float b, int W, const float2 *tab)
+{
+    const uint32_t s = t1_full ? w : __umulhi(w, t1);
+    const bool left = s < h1;
+    const uint32_t off = left ? s : s - h1;
+    unsigned long long t = (unsigned long long)(left ? a1 : a2) + 2ull * off + 1ull;
+    if (t > 0xFFFFFFFFull) t = 0xFFFFFFFFull;
+    const float e = neglog_norm((uint32_t)t | 1u, tab);
+    const float x = __fmaf_rn(left ? -b : b, e, L);
+    int c = __float2int_rn(__fmul_rn(fabsf(x), 100.0f));
+    c = min(c, W - 1);
+    return max(c, 0);
+}
+
+// One group of up to 32 auctions against the three thresholds: `active` = bits that are auctions.
+// Returns the win / click / conversion masks.  Lazy: reads levels only while some auction is still
+// tied with some threshold's prefix.
+struct Masks3 {
+    uint32_t win, click, conv;
+};
+
+__device__ __forceinline__ Masks3 group_masks(uint32_t active, uint32_t g, uint32_t t1, uint32_t t2, uint32_t t3,
+                                              uint32_t full, uint32_t n0, uint32_t n1, uint32_t x3, uint32_t k0,
+                                              uint32_t k1)
+{
+    // E_i: auctions whose R matches T_i on the levels read so far; L_i: auctions known to be below T_i
+    uint32_t e1 = (full & 1u) ? 0u : active, e2 = (full & 2u) ? 0u : active, e3 = (full & 4u) ? 0u : active;
+    uint32_t l1 = (full & 1u) ? active : 0u, l2 = (full & 2u) ? active : 0u, l3 = (full & 4u) ? active : 0u;
+#pragma unroll 1
+    for (uint32_t q = 0; q < 8u && (e1 | e2 | e3) != 0u; ++q) {
+        const uint4 w = philox_from_pre(8u * g + q, n0, n1, x3, k0, k1);
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t r = ws[i];
+            // m_i = all ones when the threshold's bit at this level is 1:
+            //   bit 1: auctions with r = 0 drop below (L |= E & ~r), those with r = 1 stay tied (E &= r)
+            //   bit 0: auctions with r = 1 rise above (E &= ~r)
+            const uint32_t m1 = (uint32_t)((int)t1 >> 31), m2 = (uint32_t)((int)t2 >> 31), m3 = (uint32_t)((int)t3 >> 31);
+            l1 |= e1 & ~r & m1; e1 &= ~(r ^ m1);
+            l2 |= e2 & ~r & m2; e2 &= ~(r ^ m2);
+            l3 |= e3 & ~r & m3; e3 &= ~(r ^ m3);
+            t1 <<= 1; t2 <<= 1; t3 <<= 1;
+        }
+    }
+    Masks3 m;
+    m.win = l1; m.click = l2; m.conv = l3;
+    return m;
 }
 
 // numpy >= 2 keeps a float32 bid float32 through round(np.maximum(bid, 0.01), 2) (env:215), and

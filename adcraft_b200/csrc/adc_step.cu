@@ -184,6 +184,7 @@ struct UnitCur {
     int n_conv;         // accepted clicks so far
     int n_rev;          // conversions so far
     int n_cost;         // explicit: impressions so far
+    int n_clk;          // free-running implicit: clicked auctions so far, accepted or not (price draw rank)
 };
 
 struct UnitPar {
@@ -193,15 +194,34 @@ struct UnitPar {
     float loc, scale, rev_mean, rev_sd;
     double ctr, cvr;
     uint32_t thr_click, thr_conv, thr_impr;
-    uint32_t thr_cc;  // implicit: conversion <=> conv_all || cc < thr_cc  (cc = the click word)
-    bool conv_all;
     int floor_cents;  // shared auctions: highest rival bid (INT_MIN when there are no rivals)
+    Unit2 u2;         // free-running implicit keywords: thresholds + price sampler (adc_rng.cuh)
+    long long volume; // free-running implicit keywords: the day's volume (group masks need it)
 };
 
 // cents the win test uses (adc_step_args.f32_ties)
 __device__ __forceinline__ int win_cents_of(const adc_step_args &a, int bid_cents)
 {
     return bid_cents + ((a.f32_ties && a.bids_dtype == ADC_F32) ? bid_tie_bonus(bid_cents) : 0);
+}
+
+// Shared auctions: the highest RIVAL bid of unit (e, k) in cents (INT_MIN without rivals).  Either the
+// caller's floor_cents table or, when env_group = A > 1 comes without one, computed here from the A
+// bid rows of the world: the unique top bidder faces the runner-up, everybody else (tied leaders
+// too) faces the top bid -- nth_price_auction(n=2, num_winners=1) on the rivals (helpers:116-180).
+__device__ __forceinline__ int unit_floor(const adc_step_args &a, int e, int k, int own_cents)
+{
+    if (a.floor_cents != nullptr) return a.floor_cents[(int64_t)e * a.kw.K + k];
+    if (a.env_group <= 1) return (int)0x80000000;
+    const int A = a.env_group, w0 = (e / A) * A;
+    int top = (int)0x80000000, second = (int)0x80000000, n_top = 0;
+    for (int r = 0; r < A; ++r) {
+        const int c = bid_to_cents(load_f(a.bids, a.bids_dtype, (int64_t)(w0 + r) * a.kw.K + k));
+        if (c > top) { second = top; top = c; n_top = 1; }
+        else if (c == top) ++n_top;
+        else if (c > second) second = c;
+    }
+    return (own_cents == top && n_top == 1) ? second : top;
 }
 
 // Philox env id: the A bidders of a shared-auction world draw from the same counters.
@@ -231,6 +251,24 @@ __device__ __forceinline__ T tape_at(const T *vals, const int64_t *off, int64_t 
         return dflt;
     }
     return vals[idx];
+}
+
+// Free-running implicit keywords: clicked auctions among the day's first j0 (the price-draw rank of
+// the next click).  The generic thread-serial walk recounts it per lane; the warp kernel keeps it in
+// its slab.
+__device__ __noinline__ int clicks_before(const PhiloxSrc &src, int kw, const Unit2 &u2, long long volume, long long j0)
+{
+    const PhiloxPre pa = philox_pre(src.step, stream_word(ST_AUCTION, 0u, (uint32_t)kw), src.env, src.k0, src.k1);
+    int n = 0;
+    for (long long gbase = 0; gbase < j0; gbase += 32) {
+        const long long vrem = volume - gbase;
+        const uint32_t active = vrem >= 32 ? 0xFFFFFFFFu : ((1u << (int)vrem) - 1u);
+        const Masks3 m = group_masks(active, (uint32_t)(gbase >> 5), u2.t1, u2.t2, u2.t3, u2.full, pa.n0, pa.n1, pa.x3,
+                                     src.k0, src.k1);
+        const long long lim = j0 - gbase;
+        n += __popc(m.click & (lim >= 32 ? 0xFFFFFFFFu : ((1u << (int)lim) - 1u)));
+    }
+    return n;
 }
 
 // One call of simulate_epoch_of_bidding (bsim:44-120) for unit u, sub-step t, n auctions.
@@ -266,7 +304,7 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
         else if constexpr (kExplicit)
             conv = w2 <= p.thr_conv;
         else
-            conv = p.conv_all || w2 < p.thr_cc;  // w2 is the click word cc
+            conv = w2 != 0u;  // the auction's own conversion bit (R_j < T3)
         o.B += 1;
         o.cost_cents += cost_c;
         if constexpr (kExplicit) day_cost = __dadd_rn(day_cost, cost);
@@ -300,29 +338,64 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
     if constexpr (!kExplicit) {
         // second-price auction against one competitor (classes:644-646, helpers:116-180):
         // win iff bid > competitor (strict), cost = competitor's bid.
-        for (long long a = 0; a < n; ++a) {
-            const long long j = cur.auction + a;
-            int c;
-            uint32_t w1 = 0, w2 = 0;
-            if constexpr (Src::kTape) {
-                c = tape_at(tp->comp_cents, tp->comp_off, u, j, 0x7FFFFFFF, o.overrun);
-            } else {
-                // two auctions per Philox call: even j -> words x,y; odd j -> words z,w
-                const uint4 w = src.draw(ST_AUCTION, (uint32_t)kw, (uint32_t)(j >> 1));
-                c = max(laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale), p.floor_cents);
-                w1 = (j & 1) ? w.w : w.y;
-                w2 = w1;
+        if constexpr (Src::kTape) {
+            for (long long a = 0; a < n; ++a) {
+                const long long j = cur.auction + a;
+                const int c = tape_at(tp->comp_cents, tp->comp_off, u, j, 0x7FFFFFFF, o.overrun);
+                if (p.win_cents > c) {
+                    const bool clicked =
+                        tape_at(tp->u_click, tp->click_off, u, cur.n_click + slots, 2.0, o.overrun) <= p.ctr;
+                    on_slot(cents_to_dollars(c), c, clicked, 0u);
+                    ++slots;
+                    ++o.I;
+                }
             }
-            if (p.win_cents > c) {
-                bool clicked;
-                if constexpr (Src::kTape)
-                    clicked = tape_at(tp->u_click, tp->click_off, u, cur.n_click + slots, 2.0, o.overrun) <= p.ctr;
-                else
-                    clicked = w1 <= p.thr_click;
-                on_slot(cents_to_dollars(c), c, clicked, w2);
-                ++slots;
-                ++o.I;
+        } else {
+            // O(clicks) tape function (adc_rng.cuh): one bit-sliced uniform per auction decides win /
+            // click / conversion; a clicked auction draws its price by its click rank in the day
+            const PhiloxPre pa = philox_pre(src.step, stream_word(ST_AUCTION, 0u, (uint32_t)kw), src.env, src.k0, src.k1);
+            const bool beats_rivals = p.u2.W > p.floor_cents;
+            const long long j_end = cur.auction + n;
+            long long j = cur.auction;
+            int nclk = 0;
+            uint4 cw = make_uint4(0, 0, 0, 0);
+            int cw_idx = -1;
+            while (j < j_end) {
+                const uint32_t g = (uint32_t)(j >> 5);
+                const long long gbase = (long long)g << 5;
+                const long long vrem = p.volume - gbase;
+                const uint32_t active = vrem >= 32 ? 0xFFFFFFFFu : ((1u << (int)vrem) - 1u);
+                const Masks3 m = group_masks(active, g, p.u2.t1, p.u2.t2, p.u2.t3, p.u2.full, pa.n0, pa.n1, pa.x3,
+                                             src.k0, src.k1);
+                const int p0 = (int)(j - gbase);
+                const int p1 = (int)((j_end - gbase) < 32 ? (j_end - gbase) : 32);
+                const uint32_t range = (p1 >= 32 ? 0xFFFFFFFFu : ((1u << p1) - 1u)) & ~((1u << p0) - 1u);
+                uint32_t wins = m.win & range;
+                while (wins) {
+                    const int b = __ffs(wins) - 1;
+                    wins &= wins - 1;
+                    const bool clk = (m.click >> b) & 1u;
+                    int c = 0;
+                    if (clk) {
+                        const int r = cur.n_clk + nclk;
+                        ++nclk;
+                        if ((r >> 2) != cw_idx) {
+                            cw_idx = r >> 2;
+                            cw = src.draw(ST_COST, (uint32_t)kw, (uint32_t)cw_idx);
+                        }
+                        const uint32_t w = (r & 3) == 0 ? cw.x : (r & 3) == 1 ? cw.y : (r & 3) == 2 ? cw.z : cw.w;
+                        c = cost_cents2(w, p.u2.t1, (p.u2.full & 1u) != 0u, p.u2.h1, p.u2.a1, p.u2.a2, p.u2.L,
+                                        p.u2.b, p.u2.W, kNeglogTab);
+                    }
+                    if (!beats_rivals) continue;  // shared auction: a rival bids at least as much
+                    c = max(c, p.floor_cents);
+                    on_slot(cents_to_dollars(c), c, clk, (m.conv >> b) & 1u);
+                    ++slots;
+                    ++o.I;
+                }
+                j = gbase + p1;
             }
+            cur.n_clk += nclk;
         }
     } else {
         if constexpr (Src::kTape) {
@@ -364,7 +437,8 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
     return o;
 }
 
-__device__ __forceinline__ UnitPar load_unit_par(const adc_step_args &a, int e, int k)
+// free_running: also build the O(clicks) thresholds / price sampler of an implicit keyword
+__device__ __forceinline__ UnitPar load_unit_par(const adc_step_args &a, int e, int k, bool free_running = false)
 {
     UnitPar p;
     const int64_t pi = (int64_t)e * a.kw.env_stride + k;
@@ -381,16 +455,12 @@ __device__ __forceinline__ UnitPar load_unit_par(const adc_step_args &a, int e, 
     p.loc = (float)a.kw.p1[pi];
     p.scale = (float)a.kw.p2[pi];
     p.thr_impr = 0u;
-    p.thr_cc = 0u;
-    p.conv_all = false;
-    p.floor_cents = a.floor_cents != nullptr ? a.floor_cents[u] : (int)0x80000000;
-    if (a.kw.kind == ADC_EXPLICIT) {
+    p.floor_cents = unit_floor(a, e, k, p.bid_cents);
+    p.volume = 0;
+    if (a.kw.kind == ADC_EXPLICIT)
         p.thr_impr = prob_threshold(threshold_sigmoid(p.bid, a.kw.impression_thresh, a.kw.p1[pi], a.kw.p2[pi]));
-    } else {
-        const unsigned long long t2 = conv_threshold(p.thr_click, p.cvr);
-        p.conv_all = t2 > 0xFFFFFFFFull;
-        p.thr_cc = p.conv_all ? 0xFFFFFFFFu : (uint32_t)t2;
-    }
+    else if (free_running)
+        p.u2 = unit2_make(a.kw.p1[pi], a.kw.p2[pi], p.ctr, p.cvr, p.win_cents);
     return p;
 }
 
@@ -473,149 +543,27 @@ __device__ __forceinline__ int unit_done(const adc_step_args &a, int e, long lon
 }
 
 // ------------------------------------------------------------------------------------------
-// hot kernel: implicit keywords, Philox draws, L threads per unit
+// hot kernel (free-running implicit keywords, budget cannot bind): the O(clicks) step.
+// A warp takes a batch of 32 units.
+//   setup     lane <-> unit: parameters, volume draw, the unit's thresholds T1 >= T2 >= T3 and its
+//             price sampler (three deterministic exps in f64, adc_rng.cuh unit2_make);
+//   outcomes  lane <-> unit: the day's auctions in groups of 32, one bit-sliced uniform each
+//             (group_masks): impressions / clicks / conversions are three popcounts per group;
+//             a group costs ~4 Philox calls whatever happens inside it;
+//   prices    one price per CLICK, 4 per Philox call, flattened over the batch (call i belongs to
+//             the unit whose prefix range holds i) so every trip is full;
+//   revenues  one per conversion, flattened the same way;
+//   outputs   lane <-> unit: coalesced stores, env completion by L2 atomics, the last finisher of
+//             an env runs its tail, its episode accumulation and its drift.
+// Batches come from an atomic work counter when the caller provides one.
 // ------------------------------------------------------------------------------------------
-template <int L>
-__global__ void __launch_bounds__(256)
-adc_lanes_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
-{
-    const int K = a.kw.K;
-    const int64_t total = (int64_t)a.E * K;
-    const int lane = threadIdx.x & (L - 1);
-    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
-    const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / L;
-    const int64_t iters = (total + n_groups - 1) / n_groups;
-    const unsigned wl = threadIdx.x & 31u;
-    const unsigned gmask = L == 32 ? 0xFFFFFFFFu : (((1u << L) - 1u) << (wl & ~(unsigned)(L - 1)));
-    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-    // the serial-queue counter is double-buffered on the step parity: this step appends to
-    // [step&1]; the other one (read by the previous step's serial kernel) is cleared here.
-    if (blockIdx.x == 0 && threadIdx.x == 0) reset_next_counters(a);
-
-    for (int64_t it = 0; it < iters; ++it) {
-        const int64_t u = it * n_groups + group;
-        const bool valid = u < total;  // uniform inside a group
-        int e = 0, k = 0;
-        long long V = 0;
-        UnitPar p;
-        uint4 uw = make_uint4(0, 0, 0, 0);
-        uint32_t genv = 0;
-        if (valid) {
-            e = (int)(u / K);
-            k = (int)(u - (int64_t)e * K);
-            genv = philox_env(a, e);
-            p = load_unit_par(a, e, k);
-            PhiloxSrc src{k0, k1, a.step, genv};
-            V = unit_volume(a, src, nullptr, e, k, &uw);
-        }
-        // ---- the day's auctions, strided over the group's lanes ----
-        int I = 0, B = 0, S = 0;
-        long long cost = 0;
-        const uint32_t c2 = stream_word(ST_AUCTION, 0u, (uint32_t)k);
-        for (long long j = lane; j < V; j += L) {
-            const uint4 w = philox4x32_10((uint32_t)(j >> 1), a.step, c2, genv, k0, k1);
-            const uint32_t cc = (j & 1) ? w.w : w.y;
-            const int c = max(laplace_cents((j & 1) ? w.z : w.x, p.loc, p.scale), p.floor_cents);
-            const bool win = p.win_cents > c;
-            const bool clk = win && (cc <= p.thr_click);
-            const bool cnv = clk && (p.conv_all || cc < p.thr_cc);
-            I += win;
-            B += clk;
-            S += cnv;
-            cost += clk ? c : 0;
-        }
-        // ---- group reduction (counts packed 21 bits each) ----
-        unsigned long long packed = (unsigned long long)I | ((unsigned long long)B << 21) |
-                                    ((unsigned long long)S << 42);
-#pragma unroll
-        for (int off = L / 2; off > 0; off >>= 1) {
-            packed += __shfl_xor_sync(gmask, packed, off);
-            cost += __shfl_xor_sync(gmask, cost, off);
-        }
-        I = (int)(packed & 0x1FFFFFull);
-        B = (int)((packed >> 21) & 0x1FFFFFull);
-        S = (int)(packed >> 42);
-        // ---- revenues: one draw per conversion, indexed by conversion rank ----
-        long long rev = 0;
-        const uint32_t c2r = stream_word(ST_REVENUE, 0u, (uint32_t)k);
-        for (int blk = lane; 4 * blk < S; blk += L) {
-            const uint4 w = philox4x32_10((uint32_t)blk, a.step, c2r, genv, k0, k1);
-            const int r0 = 4 * blk;
-            rev += revenue_cents(w.x, p.rev_mean, p.rev_sd);
-            if (r0 + 1 < S) rev += revenue_cents(w.y, p.rev_mean, p.rev_sd);
-            if (r0 + 2 < S) rev += revenue_cents(w.z, p.rev_mean, p.rev_sd);
-            if (r0 + 3 < S) rev += revenue_cents(w.w, p.rev_mean, p.rev_sd);
-        }
-#pragma unroll
-        for (int off = L / 2; off > 0; off >>= 1) rev += __shfl_xor_sync(gmask, rev, off);
-
-        int safe = 0;
-        if (valid && lane == 0) {
-            a.out.impressions[u] = I;
-            a.out.clicks[u] = B;
-            a.out.conversions[u] = S;
-            a.out.cost_cents[u] = cost;
-            a.out.revenue_cents[u] = rev;
-            store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
-            store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
-            safe = unit_done(a, e, rev - cost, cost);
-        }
-        // ---- drift of a finished, budget-safe env (env:246); queued envs drift in the serial kernel
-        if (a.drift.mask != nullptr) {
-            safe = __shfl_sync(gmask, safe, 0, L);
-            if (safe) {
-                PhiloxSrc src{k0, k1, a.step, genv};
-                for (int kk = lane; kk < K; kk += L) {
-                    if (!drift_wanted(a, kk)) continue;
-                    const uint4 w = src.draw(ST_UNIT, (uint32_t)kk, 0u);
-                    drift_apply(a, e, kk, drift_from_words(a, w));
-                }
-            }
-        }
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------
-// hot kernel, warp-batched: a warp takes a batch of 32 units.
-//   setup       lane <-> unit (parameters, volume draw, thresholds, Philox pre-round -> 32 B per
-//               unit in shared memory): full lane efficiency;
-//   full trips  the warp walks the units one after the other with all 32 lanes on one unit's
-//               auctions, 64 per trip (one Philox call = two auctions per lane), warp-uniform
-//               parameters in registers, private lane accumulators, three REDUX per unit;
-//   remainders  the V mod 64 auctions of every unit, flattened across the batch: call i belongs to
-//               the unit whose prefix range holds i, so these trips are full as well;
-//   revenues    flattened the same way, 4 draws per Philox call;
-//   outputs     lane <-> unit again: coalesced stores, env completion by L2 atomics, the last
-//               finisher of an env runs its tail and drift.
-// Volume imbalance between units costs nothing (the L-threads-per-unit kernel loses ~30 % of its
-// lanes to it).  Batches come from an atomic work counter when the caller provides one.
-// ------------------------------------------------------------------------------------------
-// win <=> bid > c; click <=> win && cc <= thr_click; conversion <=> click && cc <= thr_conv.
-// Three compares chained through their predicates and four predicated adds.
-__device__ __forceinline__ void tally_counts(int bid, int c, uint32_t cc, uint32_t thr_click, uint32_t thr_conv,
-                                             unsigned &cntIB, unsigned &cntS, unsigned &cst)
-{
-    asm("{\n\t"
-        ".reg .pred pw, pc, pv;\n\t"
-        "setp.gt.s32 pw, %3, %4;\n\t"
-        "setp.le.and.u32 pc, %5, %6, pw;\n\t"
-        "setp.le.and.u32 pv, %5, %7, pc;\n\t"
-        "@pw add.u32 %0, %0, 1;\n\t"
-        "@pc add.u32 %0, %0, 65536;\n\t"
-        "@pv add.u32 %1, %1, 1;\n\t"
-        "@pc add.u32 %2, %2, %4;\n\t"
-        "}"
-        : "+r"(cntIB), "+r"(cntS), "+r"(cst)
-        : "r"(bid), "r"(c), "r"(cc), "r"(thr_click), "r"(thr_conv));
-}
-
-struct __align__(16) FlatUnit {
-    int bid_cents;
-    float loc, scale;
-    uint32_t thr_click;
-    uint32_t thr_conv;
-    uint32_t n0, n1, x3;  // PhiloxPre of the unit's auction stream
+struct __align__(16) FlatCost {  // 48 B per unit in shared memory: the price sampler + its Philox pre-round
+    uint32_t t1, h1, a1, a2;
+    float L, b;
+    int W;          // bit 31: T1 is 2^32
+    int floor_c;
+    uint32_t n0, n1, x3;
+    int B;
 };
 
 struct __align__(16) FlatRev {
@@ -625,18 +573,7 @@ struct __align__(16) FlatRev {
     uint32_t n1, x3, pad0, pad1;
 };
 
-// One auction of the hot kernel: competitor bid from `wc`, click + conversion from the single
-// word `cc`; `bid` is 0 for a slot past the unit's end (no competitor bid is below it).
-template <bool kFloor>
-__device__ __forceinline__ void flat_auction(int bid, uint32_t wc, uint32_t cc, const FlatUnit &fu, int floor_c,
-                                             const float2 (&tab)[128], unsigned &cntIB, unsigned &cntS, unsigned &cst)
-{
-    int c = laplace_cents(wc, fu.loc, fu.scale, tab);
-    if (kFloor) c = max(c, floor_c);
-    tally_counts(bid, c, cc, fu.thr_click, fu.thr_conv, cntIB, cntS, cst);
-}
-
-// The hot kernel's work list: pull index -> a chunk of consecutive batches (see the kernel).
+// The hot kernel's work list: pull index -> a chunk of consecutive batches.
 // Big batches of 32 units first: as many as there are when the warps pull dynamically, whole
 // static rounds otherwise; then the rest in small batches of kFlatTail units.
 // A dynamic pull hands out up to 16 big batches (large steps: one pull per batch would be several
@@ -669,11 +606,11 @@ __device__ __noinline__ FlatChunk flat_chunk(int64_t total, int64_t n_warps, boo
 }
 
 constexpr int kFlatWarps = 8;
-// Caps of the fast kernel's 16/32-bit lane accumulators; a unit beyond them sends its env to the
-// exact serial kernel instead (volumes and bids this large do not occur in the reference's configs).
-constexpr int kMaxFlatVolume = 65535;  // impressions and clicks share one 32-bit REDUX (I | B << 16)
+// Caps of the fast kernel's 32-bit sums; a unit beyond them sends its env to the exact serial kernel
+// instead (volumes and bids this large do not occur in the reference's configs).
+constexpr int kMaxFlatVolume = 65535;
 constexpr int kMaxFlatBidCents = 65535;
-constexpr long long kMaxFlatSpendCents = 0xFFFFFFFFLL;  // volume x bid: the unit's cost is one 32-bit REDUX
+constexpr long long kMaxFlatSpendCents = 0xFFFFFFFFLL;  // volume x bid: the unit's cost sum fits two 24-bit halves
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 {
@@ -685,27 +622,40 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
     return v;
 }
 
-// G = lanes that share one unit's auctions.  32: full 64-auction trips one unit at a time, the
-// volume remainders of the whole batch flattened (best for every volume since the flattening);
-// 16 / 8: the warp walks 32/G units side by side (kept for A/B runs).
-template <int G, bool kFloor>
-__global__ void __launch_bounds__(kFlatWarps * 32)
-adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
+// Episode accumulation of a finished env (optional adc_step_out.episode_profit_cents): the step's
+// exact profit per keyword, added once the env's step is final.  `lane` of `n_lanes` cooperating lanes.
+__device__ __forceinline__ void episode_accumulate(const adc_step_args &a, int e, int lane, int n_lanes)
 {
-    // kFloor: shared auctions (adc_step_args.floor_cents): one extra max per auction, kept out of
-    // the single-bidder instantiation
-    __shared__ int s_floor[kFloor ? kFlatWarps : 1][32];
-    __shared__ FlatUnit s_unit[kFlatWarps][32];
-    // per-unit sums handed to the owner lane.  G == 32 (flattened remainders): four copies per unit
-    // of {I | S << 8 | B << 16, cost} (a remainder has < 64 auctions), the lanes of a trip spread
-    // over the copies so that same-address atomics stay rare; G < 32: {I | B << 16, S, cost, -}
-    __shared__ __align__(16) unsigned s_res[kFlatWarps][32][G == 32 ? 8 : 4];
-    __shared__ int s_vol[kFlatWarps][32];
-    __shared__ unsigned char s_nzl[kFlatWarps][32];   // units of the batch that have a volume remainder
+    if (a.out.episode_profit_cents == nullptr) return;
+    const int K = a.kw.K;
+    for (int k = lane; k < K; k += n_lanes) {
+        const int64_t u = (int64_t)e * K + k;
+        const long long r = __ldcg(a.out.revenue_cents + u), c = __ldcg(a.out.cost_cents + u);
+        a.out.episode_profit_cents[u] += r - c;
+    }
+}
+
+// Flattened work of a batch: unit `lane` has `n` items (Philox calls); returns through `start`
+// (shared, [33]) the exclusive prefix, and the batch total.
+__device__ __forceinline__ int flat_prefix(int n, int lane, int *start)
+{
+    const int incl = warp_incl_scan(n, lane);
+    __syncwarp();
+    start[lane + 1] = incl;
+    if (lane == 0) start[0] = 0;
+    __syncwarp();
+    return __shfl_sync(0xFFFFFFFFu, incl, 31);
+}
+
+template <bool kFloor>
+__global__ void __launch_bounds__(kFlatWarps * 32)
+adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
+{
+    __shared__ FlatCost s_cost[kFlatWarps][32];
     __shared__ FlatRev s_rev[kFlatWarps][32];
     __shared__ int s_start[kFlatWarps][33];
-    __shared__ unsigned s_revsum[kFlatWarps][32][2];  // 24-bit split: native 32-bit smem atomics
-    __shared__ float2 s_tab[128];                     // Exp(1) sampler table, staged from global
+    __shared__ unsigned s_sum[kFlatWarps][32][2];  // 24-bit split: native 32-bit shared-memory atomics
+    __shared__ float2 s_tab[128];                  // Exp(1) sampler table, staged from global
     if (threadIdx.x < 128) s_tab[threadIdx.x] = kNeglogTab[threadIdx.x];
     __syncthreads();
 
@@ -717,18 +667,15 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
     // Work items: batches of 32 units.  With scratch.work_counter the warps pull them from an
     // atomic counter (the next pull is requested while the current chunk runs): a warp that was
     // held up -- the last finisher of an env runs the env tail and the drift of its K keywords --
-    // simply takes fewer items, where a static deal makes it the last finisher of every later env
-    // it touches; and the end of the kernel levels itself (a 4096 x 100 step is only 2.7 batches
-    // per resident warp; small batches at the end were measured slower than none: their
-    // lane<->unit phases run at 8/32 lane efficiency).  Without the counter: static rounds of
-    // 32-unit batches, then the remainder in 8-unit batches dealt round-robin.
+    // simply takes fewer items.  Without the counter: static rounds of 32-unit batches, then the
+    // remainder in 8-unit batches dealt round-robin.
     const bool dynamic = a.scratch.work_counter != nullptr && total < (1LL << 34);  // 32-bit pull indices
     uint32_t *const work = a.scratch.work_counter + (a.parity & 1u);
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const unsigned FULL = 0xFFFFFFFFu;
     if (blockIdx.x == 0 && threadIdx.x == 0) reset_next_counters(a);
 
-    FlatUnit *units = s_unit[warp];
+    FlatCost *costs = s_cost[warp];
     FlatRev *revs = s_rev[warp];
     int *start = s_start[warp];
 
@@ -757,208 +704,108 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
         int e = 0, k = 0, V = 0;
         bool over_cap = false;
         uint32_t genv = 0;
-        UnitPar p;
-        p.bid_cents = 0; p.win_cents = 0; p.loc = 0.f; p.scale = 0.f; p.thr_click = 0; p.thr_conv = 0;
-        p.rev_mean = 0.f; p.rev_sd = 0.f; p.thr_cc = 0; p.conv_all = false; p.floor_cents = (int)0x80000000;
-        bool outbid = false;  // shared auctions: a rival bids at least as much, no auction can be won
-        if (kFloor && valid)
-            outbid = bid_to_cents(load_f(a.bids, a.bids_dtype, u)) <= a.floor_cents[u];
-        if (valid && !outbid) {  // (7 of 8 bidder rows of an 8-bidder world stop here)
+        Unit2 u2;
+        u2.t1 = u2.t2 = u2.t3 = u2.full = u2.h1 = u2.a1 = u2.a2 = 0u; u2.L = 0.f; u2.b = 0.f; u2.W = 1;
+        float rev_mean = 0.f, rev_sd = 0.f;
+        int floor_c = 0;
+        if (valid) {
             e = (int)(u / K);
             k = (int)(u - (int64_t)e * K);
             genv = philox_env(a, e);
-            p = load_unit_par(a, e, k);
-            const int64_t pi = (int64_t)e * a.kw.env_stride + k;
-            const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)k), genv, k0, k1);
-            const long long v = volume_draw(w.x, a.kw.vol_mean[pi], a.kw.vol_std[pi]);
-            over_cap = v > kMaxFlatVolume || p.win_cents > kMaxFlatBidCents ||
-                       v * p.bid_cents > kMaxFlatSpendCents;
-            V = over_cap ? 0 : (int)v;
-        } else if (valid) {
-            e = (int)(u / K);
-            k = (int)(u - (int64_t)e * K);
+            const int bid_c = bid_to_cents(load_f(a.bids, a.bids_dtype, u));
+            const int win_c = win_cents_of(a, bid_c);
+            bool outbid = false;  // shared auctions: a rival bids at least as much, no auction can be won
+            if (kFloor) {
+                floor_c = unit_floor(a, e, k, bid_c);
+                outbid = bid_c <= floor_c;  // (7 of 8 bidder rows of an 8-bidder world stop here)
+                floor_c = max(floor_c, 0);
+            }
+            if (!outbid) {
+                const int64_t pi = (int64_t)e * a.kw.env_stride + k;
+                const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)k), genv, k0, k1);
+                const long long v = volume_draw(w.x, a.kw.vol_mean[pi], a.kw.vol_std[pi]);
+                over_cap = v > kMaxFlatVolume || win_c > kMaxFlatBidCents || v * win_c > kMaxFlatSpendCents;
+                V = over_cap ? 0 : (int)v;
+                u2 = unit2_make(a.kw.p1[pi], a.kw.p2[pi], a.kw.ctr[pi], a.kw.cvr[pi], win_c);
+                rev_mean = (float)a.kw.rev_mean[pi];
+                rev_sd = (float)a.kw.rev_std[pi];
+            }
         }
-        if (kFloor) s_floor[warp][lane] = max(p.floor_cents, 0);
+        // ---------------- outcomes: groups of 32 auctions, lane <-> unit ----------------
+        int I = 0, B = 0, S = 0;
         {
             const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), genv, k0, k1);
-            FlatUnit fu;
-            fu.bid_cents = p.win_cents; fu.loc = p.loc; fu.scale = p.scale;
-            // conversion <=> cc < T2 (T2 = 2^32 when conv_all) is stored as cc <= T2 - 1; T2 = 0
-            // ("never") rides in the sign bit of the bid (bids <= 65535) and zeroes the unit's count
-            fu.thr_click = p.thr_click;
-            fu.thr_conv = p.conv_all ? 0xFFFFFFFFu : (p.thr_cc ? p.thr_cc - 1u : 0u);
-            if (!p.conv_all && p.thr_cc == 0u) fu.bid_cents |= (int)0x80000000u;
-            fu.n0 = pa.n0; fu.n1 = pa.n1; fu.x3 = pa.x3;
-            units[lane] = fu;
+            const int G = (V + 31) >> 5;
+            const int Gmax = __reduce_max_sync(FULL, G);
+            for (int g = 0; g < Gmax; ++g) {
+                const int rem = V - 32 * g;  // auctions of this group that exist
+                const uint32_t active = rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? (1u << rem) - 1u : 0u);
+                const Masks3 m = group_masks(active, (uint32_t)g, u2.t1, u2.t2, u2.t3, u2.full, pa.n0, pa.n1, pa.x3, k0, k1);
+                I += __popc(m.win);
+                B += __popc(m.click);
+                S += __popc(m.conv);
+            }
         }
-        if (lane == 0) start[0] = 0;
-        s_revsum[warp][lane][0] = 0u; s_revsum[warp][lane][1] = 0u;
-        if (G == 32) {
-            *reinterpret_cast<uint4 *>(&s_res[warp][lane][0]) = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4 *>(&s_res[warp][lane][G == 32 ? 4 : 0]) = make_uint4(0u, 0u, 0u, 0u);
+        // ---------------- prices: one per click, 4 per Philox call, flattened over the batch ----------------
+        {
+            const PhiloxPre pc = philox_pre(a.step, stream_word(ST_COST, 0u, (uint32_t)k), genv, k0, k1);
+            FlatCost fc;
+            fc.t1 = u2.t1; fc.h1 = u2.h1; fc.a1 = u2.a1; fc.a2 = u2.a2; fc.L = u2.L; fc.b = u2.b;
+            fc.W = u2.W | ((u2.full & 1u) ? (int)0x80000000u : 0);
+            fc.floor_c = floor_c; fc.n0 = pc.n0; fc.n1 = pc.n1; fc.x3 = pc.x3; fc.B = B;
+            costs[lane] = fc;
+            s_sum[warp][lane][0] = 0u; s_sum[warp][lane][1] = 0u;
         }
-        __syncwarp();
-
-        // ---------------- the batch's auctions: 32/G units at a time, G lanes per unit -----------
-        // Inside a trip the unit is uniform over its G lanes: parameters in registers, private lane
-        // accumulators, one REDUX set per unit.  Only the last trip of a unit has idle lanes.
-        int I = 0, B = 0, S = 0;
         long long cost = 0;
-        if constexpr (G == 32) {
-            // (1) full trips, one unit after the other: each lane takes one Philox call = two
-            // consecutive auctions, 64 per trip, the unit's parameters warp-uniform in registers
-            for (int b = 0; b < cnt; ++b) {
-                const int Vb = __shfl_sync(FULL, V, b);
-                if (Vb < 64) continue;  // warp-uniform
-                FlatUnit fu = units[b];
-                const bool conv_none = fu.bid_cents < 0;
-                fu.bid_cents &= 0x7FFFFFFF;
-                const int floor_c = kFloor ? s_floor[warp][b] : 0;
-                unsigned cntIB = 0, cntS = 0, cst = 0;  // I | B << 16 ; S ; cost cents (< 2^32, see caps)
-                for (int base = 0; base + 64 <= Vb; base += 64) {
-                    const uint4 w = philox_from_pre((uint32_t)((base >> 1) + lane), fu.n0, fu.n1, fu.x3, k0, k1);
-                    flat_auction<kFloor>(fu.bid_cents, w.x, w.y, fu, floor_c, s_tab, cntIB, cntS, cst);
-                    flat_auction<kFloor>(fu.bid_cents, w.z, w.w, fu, floor_c, s_tab, cntIB, cntS, cst);
-                }
-                // the caps above keep every sum below 2^32 (I, B <= V < 2^16; cost <= V x bid)
-                const unsigned tIB = __reduce_add_sync(FULL, cntIB);
-                const unsigned tS = __reduce_add_sync(FULL, conv_none ? 0u : cntS);
-                const unsigned tC = __reduce_add_sync(FULL, cst);
-                if (lane == b) {
-                    I = (int)(tIB & 0xFFFFu); B = (int)(tIB >> 16); S = (int)tS;
-                    cost = (long long)tC;
-                }
-            }
-            // (2) the remainders (V mod 64 auctions per unit) of the whole batch, flattened: Philox
-            // call i of the batch belongs to the unit whose prefix range holds i, so every trip is
-            // full whatever the volumes are; sums land in the unit's shared-memory slot
-            {
-                const int npair = ((V & 63) + 1) >> 1;
-                const int incl_p = warp_incl_scan(npair, lane);
-                const bool nz = npair > 0;
-                const unsigned nzmask = __ballot_sync(FULL, nz);
-                if (nz) s_nzl[warp][__popc(nzmask & ((1u << lane) - 1u))] = (unsigned char)lane;
-                s_vol[warp][lane] = V;
-                start[lane] = incl_p - npair;  // first call of unit `lane` (start[0] stays 0)
-                __syncwarp();
-                const int TP = __shfl_sync(FULL, incl_p, 31);
-                for (int base = 0; base < TP; base += 32) {
-                    // which unit does call base + lane belong to?  Every owner lane marks where its
-                    // unit's calls end inside this trip; a lane's unit is the r-th one with a
-                    // remainder, r = units that ended before the trip + marks at or below the lane
-                    const int rel = incl_p - base;
-                    const unsigned marks = __reduce_or_sync(FULL, (nz && rel > 0 && rel < 32) ? (1u << rel) : 0u);
-                    const int before = __popc(__ballot_sync(FULL, nz && rel <= 0));
-                    const int i = base + lane;
-                    if (i < TP) {
-                        const int b = s_nzl[warp][before + __popc(marks & (0xFFFFFFFFu >> (31 - lane)))];
-                        FlatUnit fu = units[b];
-                        const bool conv_none = fu.bid_cents < 0;
-                        fu.bid_cents &= 0x7FFFFFFF;
-                        const int floor_c = kFloor ? s_floor[warp][b] : 0;
-                        const int Vb = s_vol[warp][b];
-                        const int j = (Vb & ~63) + 2 * (i - start[b]);  // first auction of this call
-                        const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
-                        unsigned cntIB = 0, cntS = 0, cst = 0;
-                        flat_auction<kFloor>(fu.bid_cents, w.x, w.y, fu, floor_c, s_tab, cntIB, cntS, cst);
-                        flat_auction<kFloor>(j + 1 < Vb ? fu.bid_cents : 0, w.z, w.w, fu, floor_c, s_tab, cntIB, cntS, cst);
-                        unsigned *slot = &s_res[warp][b][2 * (lane & 3)];
-                        atomicAdd(slot, cntIB + (conv_none ? 0u : cntS << 8));
-                        atomicAdd(slot + 1, cst);
+        {
+            const int TB = flat_prefix((B + 3) >> 2, lane, start);
+            int b0 = 0;
+            for (int base = 0; base < TB; base += 32) {
+                while (start[b0 + 1] <= base) ++b0;  // warp-uniform: the unit that holds call `base`
+                const int i = base + lane;
+                if (i < TB) {
+                    int b = b0;
+                    while (i >= start[b + 1]) ++b;
+                    const FlatCost fc = costs[b];
+                    const int q = i - start[b];
+                    const uint4 w = philox_from_pre((uint32_t)q, fc.n0, fc.n1, fc.x3, k0, k1);
+                    const bool t1_full = fc.W < 0;
+                    const int W = fc.W & 0x7FFFFFFF;
+                    const int left = fc.B - 4 * q;  // >= 1 clicks priced by this call
+                    int c0 = cost_cents2(w.x, fc.t1, t1_full, fc.h1, fc.a1, fc.a2, fc.L, fc.b, W, s_tab);
+                    int c1 = cost_cents2(w.y, fc.t1, t1_full, fc.h1, fc.a1, fc.a2, fc.L, fc.b, W, s_tab);
+                    int c2 = cost_cents2(w.z, fc.t1, t1_full, fc.h1, fc.a1, fc.a2, fc.L, fc.b, W, s_tab);
+                    int c3 = cost_cents2(w.w, fc.t1, t1_full, fc.h1, fc.a1, fc.a2, fc.L, fc.b, W, s_tab);
+                    if (kFloor) {
+                        c0 = max(c0, fc.floor_c); c1 = max(c1, fc.floor_c);
+                        c2 = max(c2, fc.floor_c); c3 = max(c3, fc.floor_c);
                     }
-                }
-                __syncwarp();
-                const uint4 r0 = *reinterpret_cast<const uint4 *>(&s_res[warp][lane][0]);
-                const uint4 r1 = *reinterpret_cast<const uint4 *>(&s_res[warp][lane][G == 32 ? 4 : 0]);
-                const unsigned cnts = r0.x + r0.z + r1.x + r1.z;  // fields < 64 each: no carries
-                I += (int)(cnts & 0xFFu); S += (int)((cnts >> 8) & 0xFFu); B += (int)(cnts >> 16);
-                cost += (long long)r0.y + r0.w + r1.y + r1.w;
-            }
-        } else {
-            constexpr int NG = 32 / G;
-            const int gl = lane & (G - 1), gi = lane / G;
-            const unsigned gmask = G == 32 ? FULL : (((1u << G) - 1u) << (gi * G));
-            for (int b0 = 0; b0 < cnt; b0 += NG) {
-                const int b = b0 + gi;  // this group's unit
-                int Vb = __shfl_sync(FULL, V, b & 31);
-                if (b >= cnt) Vb = 0;
-                if (G == 32 && Vb == 0) continue;  // warp-uniform
-                FlatUnit fu = units[b & 31];
-                const bool conv_none = fu.bid_cents < 0;
-                fu.bid_cents &= 0x7FFFFFFF;
-                const int floor_c = kFloor ? s_floor[warp][b & 31] : 0;
-                unsigned cntIB = 0, cntS = 0, cst = 0;  // I | B << 16 ; S ; cost cents (< 2^32, see caps)
-                // one auction: competitor bid from `wc`, click + conversion from the single word `cc`
-                // (`bid` is 0 for a lane past the unit's end: no competitor bid is below it)
-                auto tally = [&](int bid, uint32_t wc, uint32_t cc) {
-                    int c = laplace_cents(wc, fu.loc, fu.scale, s_tab);
-                    if (kFloor) c = max(c, floor_c);
-                    tally_counts(bid, c, cc, fu.thr_click, fu.thr_conv, cntIB, cntS, cst);
-                };
-                // full trips: each lane takes one Philox call = two consecutive auctions (2G per trip)
-                int base = 0;
-                for (; base + 2 * G <= Vb; base += 2 * G) {
-                    const uint4 w = philox_from_pre((uint32_t)((base >> 1) + gl), fu.n0, fu.n1, fu.x3, k0, k1);
-                    tally(fu.bid_cents, w.x, w.y);
-                    tally(fu.bid_cents, w.z, w.w);
-                }
-                const int rem = Vb - base;  // 0 .. 2G-1 auctions left
-                if (rem > G) {              // still worth pairing: lanes past the end idle
-                    const int j = base + 2 * gl;
-                    const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
-                    tally(j < Vb ? fu.bid_cents : 0, w.x, w.y);
-                    tally(j + 1 < Vb ? fu.bid_cents : 0, w.z, w.w);
-                } else if (rem > 0) {       // at most G left: one auction per lane, half a call each
-                    const int j = base + gl;
-                    const uint4 w = philox_from_pre((uint32_t)(j >> 1), fu.n0, fu.n1, fu.x3, k0, k1);
-                    tally(j < Vb ? fu.bid_cents : 0, (j & 1) ? w.z : w.x, (j & 1) ? w.w : w.y);
-                }
-                // the caps above keep every sum below 2^32 (I, B <= V < 2^16; cost <= V x bid)
-                const unsigned tIB = __reduce_add_sync(gmask, cntIB);
-                const unsigned tS = __reduce_add_sync(gmask, conv_none ? 0u : cntS);
-                const unsigned tC = __reduce_add_sync(gmask, cst);
-                if (G == 32) {
-                    if (lane == b) {
-                        I = (int)(tIB & 0xFFFFu); B = (int)(tIB >> 16); S = (int)tS;
-                        cost = (long long)tC;
-                    }
-                } else if (gl == 0 && b < cnt) {
-                    s_res[warp][b][0] = tIB;
-                    s_res[warp][b][1] = tS;
-                    s_res[warp][b][2] = tC;
+                    const long long sum = (long long)c0 + (left > 1 ? c1 : 0) + (long long)(left > 2 ? c2 : 0) +
+                                          (left > 3 ? c3 : 0);
+                    atomicAdd(&s_sum[warp][b][0], (unsigned)(sum & 0xFFFFFF));
+                    atomicAdd(&s_sum[warp][b][1], (unsigned)(sum >> 24));
                 }
             }
-            if (G != 32) {
-                __syncwarp();
-                if (lane < cnt) {
-                    const unsigned ib = s_res[warp][lane][0];
-                    I = (int)(ib & 0xFFFFu); B = (int)(ib >> 16); S = (int)s_res[warp][lane][1];
-                    cost = (long long)s_res[warp][lane][2];
-                }
-            }
-
+            __syncwarp();
+            cost = (long long)s_sum[warp][lane][0] + ((long long)s_sum[warp][lane][1] << 24);
         }
-
         // ---------------- revenues: one draw per conversion, 4 per Philox call ----------------
         {
             const PhiloxPre pr = philox_pre(a.step, stream_word(ST_REVENUE, 0u, (uint32_t)k), genv, k0, k1);
             FlatRev fr;
-            fr.mean = p.rev_mean; fr.sd = p.rev_sd; fr.S = S;
+            fr.mean = rev_mean; fr.sd = rev_sd; fr.S = S;
             fr.n0 = pr.n0; fr.n1 = pr.n1; fr.x3 = pr.x3; fr.pad0 = 0; fr.pad1 = 0;
             revs[lane] = fr;
+            __syncwarp();
+            s_sum[warp][lane][0] = 0u; s_sum[warp][lane][1] = 0u;
         }
-        const int nblk = (S + 3) >> 2;
-        const int incl_b = warp_incl_scan(nblk, lane);
-        __syncwarp();  // everyone has read the auction-phase tables
-        start[lane + 1] = incl_b;
-        __syncwarp();
-        const int TB = __shfl_sync(FULL, incl_b, 31);
-        int b0 = 0;
-        for (int base = 0; base < TB; base += 32) {
-            while (start[b0 + 1] <= base) ++b0;
+        const int TR = flat_prefix((S + 3) >> 2, lane, start);
+        int r0 = 0;
+        for (int base = 0; base < TR; base += 32) {
+            while (start[r0 + 1] <= base) ++r0;
             const int i = base + lane;
-            if (i < TB) {
-                int b = b0;
+            if (i < TR) {
+                int b = r0;
                 while (i >= start[b + 1]) ++b;
                 const FlatRev fr = revs[b];
                 const int blk = i - start[b];
@@ -970,12 +817,12 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
                 const int c2 = revenue_cents(w.z, fr.mean, fr.sd), c3 = revenue_cents(w.w, fr.mean, fr.sd);
                 const long long sum = (long long)c0 + (left > 1 ? c1 : 0) + (long long)(left > 2 ? c2 : 0) +
                                       (left > 3 ? c3 : 0);
-                atomicAdd(&s_revsum[warp][b][0], (unsigned)(sum & 0xFFFFFF));
-                atomicAdd(&s_revsum[warp][b][1], (unsigned)(sum >> 24));
+                atomicAdd(&s_sum[warp][b][0], (unsigned)(sum & 0xFFFFFF));
+                atomicAdd(&s_sum[warp][b][1], (unsigned)(sum >> 24));
             }
         }
         __syncwarp();
-        const long long rev = (long long)s_revsum[warp][lane][0] + ((long long)s_revsum[warp][lane][1] << 24);
+        const long long rev = (long long)s_sum[warp][lane][0] + ((long long)s_sum[warp][lane][1] << 24);
 
         // ---------------- outputs (coalesced: 32 consecutive units), env completion ----------------
         int safe = 0;
@@ -989,13 +836,16 @@ adc_flat_philox_implicit_kernel(const __grid_constant__ adc_step_args a)
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
             safe = unit_done(a, e, rev - cost, over_cap ? (1LL << 40) : cost);
         }
-        if (a.drift.mask != nullptr) {
-            // drift of finished budget-safe envs (env:246), the warp shares each env's keywords
+        if (a.drift.mask != nullptr || a.out.episode_profit_cents != nullptr) {
+            // finished budget-safe envs: episode accumulation and drift (env:246), the warp shares
+            // each env's keywords
             unsigned todo = __ballot_sync(FULL, safe != 0);
             while (todo) {
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int ee = __shfl_sync(FULL, e, src);
+                episode_accumulate(a, ee, lane, 32);
+                if (a.drift.mask == nullptr) continue;
                 const uint32_t ge = philox_env(a, ee);
                 // two keywords per lane and trip, all of their loads in flight before the first
                 // store: the env's K keywords cost K / 64 DRAM round trips
@@ -1795,14 +1645,19 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
         for (int t = 0; t < ADC_SUBSTEPS && !stop; ++t) {
             for (int k = 0; k < K; ++k) {
                 const int64_t u = (int64_t)e * K + k;
-                const UnitPar p = load_unit_par(a, e, k);
+                UnitPar p = load_unit_par(a, e, k, !Src::kTape);
                 uint4 uw;
                 const long long V = unit_volume(a, src, &tape, e, k, &uw);
+                p.volume = V;
                 const long long q = V / ADC_SUBSTEPS;
                 const long long n0 = V - (ADC_SUBSTEPS - 1) * q;
                 const long long n = t == 0 ? n0 : q;
                 UnitCur cur;
                 cur.auction = t == 0 ? 0 : n0 + (long long)(t - 1) * q;
+                cur.n_clk = 0;
+                if constexpr (!Src::kTape) {
+                    if (!explicit_kw && n > 0) cur.n_clk = clicks_before(src, k, p.u2, V, cur.auction);
+                }
                 cur.n_conv = acc.B[u];
                 cur.n_rev = acc.S[u];
                 cur.n_cost = acc.I[u];
@@ -1877,49 +1732,38 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
-// exact serial kernel, warp-cooperative (implicit keywords, Philox draws): one warp per queued env.
-// The reference's order is sub-step-major, keyword-minor with one shared float budget, so the
-// budget arithmetic is a sequential chain -- but the auctions of a lane do not depend on the
-// budget.  Per sub-step the warp takes 32 keywords at a time: every lane evaluates its keyword's
-// auctions in parallel and buffers its clicked slots (cost, conversion word); then the lanes take
-// turns, in keyword order, to run the reference's budget walk on their buffered clicks and hand
-// the remaining budget to the next lane by shuffle (same f64 operations in the same order as
-// bidding_simulation.py:97-104,225-233, incl. the ndarray-aliasing double charge); finally the
-// lanes commit in parallel.  Lanes after the one that exhausts the budget contribute nothing.
+// exact serial kernel, warp-cooperative (free-running implicit keywords): one warp per queued env.
+//
+// The reference walks (sub-step, keyword, click) with ONE shared float budget (bsim:214-233,
+// :97-104), but only the affordability tests are sequential: what is clicked, at what price and
+// whether it converts does not depend on the budget.  So a warp first EXPANDS the env's day in the
+// hot kernel's form -- lane <-> keyword, the bit-sliced outcome masks of every 32-auction group, one
+// price per click -- into a slab of global memory it owns (L2-resident; adc_scratch.serial_ws):
+// per unit the impressions and first click of each of the 24 sub-steps and the day's clicked slots
+// in order (price in cents | converts << 31).  The walk then only reads: per sub-step and chunk of
+// 32 keywords the lanes fetch their clicked slots, the whole warp runs ONE uniform scan over them in
+// keyword order -- the reference's f64 sequence `if budget >= cost: budget -= cost`, alias rule and
+// `remaining <= 0` exit included -- and the lanes commit their accepted prefix in parallel
+// (conversions, revenues).  Nothing is re-drawn per sub-step and no keyword count is special.
 // ------------------------------------------------------------------------------------------
 constexpr int kSerWarps = 4;
-constexpr int kSerCap = 16;     // buffered clicked slots per lane and sub-step; more -> direct re-walk
-constexpr int kSerCacheK = 104; // keywords per env whose per-unit constants (and running sums) live in shared memory
-constexpr bool kSerUseAcc = false;  // running day totals in shared memory (13 KB per CTA) or read-modify-write of the outputs
-constexpr int kSerMinBlocks = 7;    // 28 warps per SM: a 4096-env queue is resident in one wave
+constexpr int kSerCap = 16;        // clicked slots per lane and sub-step in shared memory; more -> direct re-walk
+constexpr int kSlabClicks = 128;   // clicked slots per unit and day in the slab; more -> direct re-walk
+constexpr int kSerMinBlocks = 6;
 
-struct SerUnit {  // what a (sub-step, keyword) lane needs again in each of the 24 sub-steps
-    int bid_cents, floor_cents;
-    float loc, scale, rev_mean, rev_sd;
-    uint32_t thr_click, thr_cc;  // thr_cc = 0xFFFFFFFF with conv_all in the sign of `volume`... see flags
-    int volume;                  // clamped to INT_MAX (larger volumes take the uncached path)
-    int flags;                   // bit 0: conv_all
+struct __align__(16) SlabUnit {
+    uint16_t cstart[ADC_SUBSTEPS + 1];  // clicked slots before sub-step t; [24] = the day's total
+    uint16_t imp[ADC_SUBSTEPS];         // impressions of sub-step t
+    uint16_t flags;                     // bit 0: walk this unit with lane_walk instead (volume / clicks beyond the slab)
+    int win_cents;
+    float rev_mean, rev_sd;
+    uint32_t click[kSlabClicks];        // price in cents (floor applied) | converts << 31
 };
 
-struct __align__(16) SerAcc {  // a keyword's running day totals (flushed to the outputs once per env)
-    int I, B, S, pad;
-    long long cost, rev;
-};
-
-// One warp per queued env.  The reference's walk is sequential in (sub-step, keyword, click) because
-// every click draws on one shared budget (bsim:214-233), but only the affordability test is: per
-// sub-step and chunk of 32 keywords the lanes evaluate their auctions in parallel and buffer the
-// clicked slots (cost already as the f64 dollar value the reference compares), then the whole warp
-// runs ONE uniform scan over the buffered clicks in keyword order -- the reference's f64 sequence
-// `if budget >= cost: budget -= cost` (bsim:97-104), alias rule and `remaining <= 0` exit included
-// -- and finally the lanes commit their accepted prefix in parallel (conversions, revenues).
 __global__ void __launch_bounds__(kSerWarps * 32, kSerMinBlocks)
-adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
+adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_slabs)
 {
-    // clicked slots: cost in cents (bits 0..30; dollars are 3 FMAs away) | converts (bit 31)
     __shared__ uint32_t s_slot[kSerWarps][kSerCap][32];
-    __shared__ SerUnit s_unit[kSerWarps][kSerCacheK];
-    __shared__ SerAcc s_acc[kSerWarps][kSerUseAcc ? kSerCacheK : 1];
     __shared__ float2 s_tab[128];  // Exp(1) sampler table, staged from global
     if (threadIdx.x < 128) s_tab[threadIdx.x] = kNeglogTab[threadIdx.x];
     __syncthreads();
@@ -1928,28 +1772,18 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto slot_cost = [&](int i, int l) { return (int)(s_slot[warp][i][l] & 0x7FFFFFFFu); };
     const int gwarp = blockIdx.x * kSerWarps + warp;
-    const int n_warps = gridDim.x * kSerWarps;
+    const int n_warps = min(gridDim.x * kSerWarps, n_slabs);
     const int count = a.scratch.serial_count[a.parity & 1u];
     const unsigned FULL = 0xFFFFFFFFu;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const adc_tape *no_tape = nullptr;
-
-    auto make_unit = [&](const PhiloxSrc &src, int e, int k) {
-        const UnitPar p = load_unit_par(a, e, k);
-        uint4 uw;
-        const long long V = unit_volume(a, src, no_tape, e, k, &uw);
-        SerUnit su;
-        su.bid_cents = p.win_cents; su.floor_cents = p.floor_cents;
-        su.loc = p.loc; su.scale = p.scale; su.rev_mean = p.rev_mean; su.rev_sd = p.rev_sd;
-        su.thr_click = p.thr_click; su.thr_cc = p.thr_cc;
-        su.volume = V > 0x7FFFFFFFLL ? 0x7FFFFFFF : (int)V;
-        su.flags = p.conv_all ? 1 : 0;
-        return su;
-    };
+    if (gwarp >= n_warps) return;
+    SlabUnit *slab = reinterpret_cast<SlabUnit *>(a.scratch.serial_ws) + (size_t)gwarp * K;
 
     for (int idx = gwarp; idx < count; idx += n_warps) {
         const int e = a.scratch.serial_list[idx];
         PhiloxSrc src{k0, k1, a.step, philox_env(a, e)};
+        // ---- phase 0 (lane <-> keyword): expand the day into the slab
         for (int k = lane; k < K; k += 32) {
             const int64_t u = (int64_t)e * K + k;
             acc.I[u] = 0;
@@ -1957,14 +1791,66 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
             acc.S[u] = 0;
             a.out.cost_cents[u] = 0;
             a.out.revenue_cents[u] = 0;
-            if (k < kSerCacheK) {
-                s_unit[warp][k] = make_unit(src, e, k);
-                if (kSerUseAcc) {
-                    SerAcc z;
-                    z.I = z.B = z.S = z.pad = 0; z.cost = z.rev = 0;
-                    s_acc[warp][k] = z;
+            UnitPar p = load_unit_par(a, e, k, true);
+            uint4 uw;
+            const long long Vl = unit_volume(a, src, no_tape, e, k, &uw);
+            SlabUnit *su = slab + k;
+            su->win_cents = p.win_cents;
+            su->rev_mean = p.rev_mean;
+            su->rev_sd = p.rev_sd;
+            const bool beats_rivals = p.u2.W > p.floor_cents;
+            uint16_t flags = Vl > kMaxFlatVolume ? 1 : 0;
+            for (int t = 0; t < ADC_SUBSTEPS; ++t) { su->imp[t] = 0; su->cstart[t] = 0; }
+            su->cstart[ADC_SUBSTEPS] = 0;
+            if (!flags && beats_rivals && Vl > 0) {
+                const int V = (int)Vl;
+                const int q = V / ADC_SUBSTEPS, n0 = V - (ADC_SUBSTEPS - 1) * q;  // bsim:151-167
+                const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), src.env, k0, k1);
+                const int floor_c = max(p.floor_cents, 0);
+                int nclk = 0, t = 0, t_end = n0;  // current sub-step and the auction index where it ends
+                int it = 0, ct = 0;               // its impressions / clicked slots so far
+                uint4 cw = make_uint4(0, 0, 0, 0);
+                const int G = (V + 31) >> 5;
+                for (int g = 0; g < G; ++g) {
+                    const int rem = V - 32 * g;
+                    const uint32_t active = rem >= 32 ? 0xFFFFFFFFu : (1u << rem) - 1u;
+                    const Masks3 m = group_masks(active, (uint32_t)g, p.u2.t1, p.u2.t2, p.u2.t3, p.u2.full, pa.n0, pa.n1,
+                                                 pa.x3, k0, k1);
+                    int pos = 0;  // bits of this group already attributed to a sub-step
+                    const int gend = min(32, rem);
+                    while (pos < gend) {
+                        const int j = 32 * g + pos;
+                        while (j >= t_end && t < ADC_SUBSTEPS - 1) {  // close sub-step t
+                            su->imp[t] = (uint16_t)it;
+                            ++t;
+                            su->cstart[t] = (uint16_t)min(nclk, 0xFFFF);
+                            it = 0; ct = 0;
+                            t_end += q;
+                        }
+                        const int upto = min(gend, t_end - 32 * g);  // bits [pos, upto) belong to sub-step t
+                        const int hi = upto > pos ? upto : gend;     // (q == 0: everything is in sub-step 0)
+                        const uint32_t range = (hi >= 32 ? 0xFFFFFFFFu : (1u << hi) - 1u) & ~((1u << pos) - 1u);
+                        it += __popc(m.win & range);
+                        uint32_t cl = m.click & range;
+                        while (cl) {
+                            const int bpos = __ffs(cl) - 1;
+                            cl &= cl - 1;
+                            if ((nclk & 3) == 0) cw = src.draw(ST_COST, (uint32_t)k, (uint32_t)(nclk >> 2));
+                            const uint32_t w = (nclk & 3) == 0 ? cw.x : (nclk & 3) == 1 ? cw.y : (nclk & 3) == 2 ? cw.z : cw.w;
+                            const int c = max(cost_cents2(w, p.u2.t1, (p.u2.full & 1u) != 0u, p.u2.h1, p.u2.a1, p.u2.a2,
+                                                          p.u2.L, p.u2.b, p.u2.W, s_tab), floor_c);
+                            if (nclk < kSlabClicks) su->click[nclk] = (uint32_t)c | (((m.conv >> bpos) & 1u) << 31);
+                            ++nclk; ++ct;
+                        }
+                        pos = hi;
+                    }
                 }
+                su->imp[t] = (uint16_t)it;
+                for (int tt = t + 1; tt <= ADC_SUBSTEPS; ++tt) su->cstart[tt] = (uint16_t)min(nclk, 0xFFFF);
+                if (nclk > kSlabClicks) flags = 1;
+                (void)ct;
             }
+            su->flags = flags;
         }
         __syncwarp();
         const double budget = step_budget(a, e);
@@ -1975,45 +1861,24 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                 const int k = c0 + lane;
                 const bool act = k < K;
                 const int64_t u = (int64_t)e * K + (act ? k : 0);
-                // ---- phase 1 (parallel): the lane's auctions, budget-free; buffer the clicked slots
-                SerUnit su;
-                su.bid_cents = 0; su.floor_cents = 0; su.loc = 0.f; su.scale = 0.f; su.rev_mean = 0.f; su.rev_sd = 0.f;
-                su.thr_click = 0; su.thr_cc = 0; su.volume = 0; su.flags = 0;
-                long long n = 0, j0 = 0;
-                int I = 0, nclk = 0;
+                // ---- phase 1 (parallel): fetch the lane's clicked slots of this sub-step
+                const SlabUnit *su = slab + (act ? k : 0);
+                int I = 0, nclk = 0, cbase = 0, win_c = 0;
+                bool direct = false;  // walk the sub-step again with lane_walk (beyond the slab / the buffer)
                 if (act) {
-                    su = k < kSerCacheK ? s_unit[warp][k] : make_unit(src, e, k);
-                    // volumes are clamped to INT_MAX, so the day's auction indices fit 32 bits
-                    const int V = su.volume;
-                    const int q = V / ADC_SUBSTEPS;
-                    const int n0 = V - (ADC_SUBSTEPS - 1) * q;
-                    const int ni = t == 0 ? n0 : q;
-                    const int ji = t == 0 ? 0 : n0 + (t - 1) * q;
-                    n = ni;
-                    j0 = ji;
-                    // one Philox call serves auctions 2c and 2c+1: walk the calls that overlap [j0, j0+n)
-                    const int j_end = ji + ni;
-                    for (int cidx = ji >> 1; 2 * cidx < j_end; ++cidx) {
-                        const uint4 w = src.draw(ST_AUCTION, (uint32_t)k, (uint32_t)cidx);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int j = 2 * cidx + h;
-                            if (j < ji || j >= j_end) continue;
-                            const uint32_t cc = h ? w.w : w.y;
-                            const int c = max(laplace_cents(h ? w.z : w.x, su.loc, su.scale, s_tab), su.floor_cents);
-                            if (su.bid_cents > c) {
-                                ++I;
-                                if (cc <= su.thr_click) {
-                                    if (nclk < kSerCap) {
-                                        const bool cv = (su.flags & 1) != 0 || cc < su.thr_cc;
-                                        s_slot[warp][nclk][lane] = (uint32_t)c | (cv ? 0x80000000u : 0u);
-                                    }
-                                    ++nclk;
-                                }
-                            }
-                        }
+                    direct = (su->flags & 1u) != 0u;
+                    win_c = su->win_cents;
+                    if (!direct) {
+                        I = su->imp[t];
+                        cbase = su->cstart[t];
+                        nclk = su->cstart[t + 1] - cbase;
+                        if (nclk <= kSerCap)
+                            for (int i = 0; i < nclk; ++i) s_slot[warp][i][lane] = su->click[cbase + i];
+                        else
+                            direct = true;
                     }
                 }
+                if (direct) nclk = kSerCap + 1;  // takes the re-walk turn below
                 __syncwarp();
                 // ---- phase 2 (one uniform scan over the lanes that have clicks): the reference's budget walk
                 int B = 0, S = 0;
@@ -2033,10 +1898,10 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                 //     lanes form in parallel.
                 if (remaining > 0) {
                     const bool lane_has = act && nclk > 0;
-                    const bool none = !lane_has || !(remaining >= cents_to_dollars(slot_cost(0, lane)));
+                    const bool none = !lane_has || (!direct && !(remaining >= cents_to_dollars(slot_cost(0, lane))));
                     if (__all_sync(FULL, none)) {
                         todo = 0;
-                    } else if (!__any_sync(FULL, nclk > kSerCap || su.bid_cents > kMaxFlatBidCents)) {
+                    } else if (!__any_sync(FULL, nclk > kSerCap || win_c > kMaxFlatBidCents)) {
                         unsigned cents = 0;
                         double lane_sum = 0.0;
                         for (int i = 0; i < nclk; ++i) {
@@ -2068,27 +1933,31 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                     double next;
                     if (n_l <= kSerCap) {  // every lane runs lane l's walk on the buffered f64 costs
                         double b = remaining, lane_sum = 0.0;
-                        int acc = 0;
+                        int nacc = 0;
                         for (int i = 0; i < n_l; ++i) {
                             const double cost = cents_to_dollars(slot_cost(i, l));
                             if (!(b >= cost)) break;  // bsim:99-104
-                            ++acc;
+                            ++nacc;
                             lane_sum = __dadd_rn(lane_sum, cost);
                             b = __dsub_rn(b, cost);
                         }
-                        if (lane == l) B = acc;
+                        if (lane == l) B = nacc;
                         next = __dsub_rn(a.budget_alias ? b : remaining, lane_sum);  // bsim:102 alias, :225
-                    } else {  // more clicks than the buffer holds: lane l walks its sub-step again, with the budget
+                    } else {  // beyond the slab or the buffer: lane l walks its sub-step again, with the budget
                         next = remaining;
                         if (lane == l) {
-                            UnitPar p;
-                            p.bid_cents = su.bid_cents; p.win_cents = su.bid_cents; p.floor_cents = su.floor_cents; p.loc = su.loc; p.scale = su.scale;
-                            p.rev_mean = su.rev_mean; p.rev_sd = su.rev_sd; p.thr_click = su.thr_click; p.thr_cc = su.thr_cc;
-                            p.conv_all = (su.flags & 1) != 0; p.bid = 0.0; p.ctr = 0.0; p.cvr = 0.0; p.thr_conv = 0; p.thr_impr = 0;
+                            UnitPar p = load_unit_par(a, e, k, true);
+                            uint4 uw;
+                            p.volume = unit_volume(a, src, no_tape, e, k, &uw);
+                            const long long q = p.volume / ADC_SUBSTEPS, n0 = p.volume - (ADC_SUBSTEPS - 1) * q;
+                            const long long n = t == 0 ? n0 : q, j0 = t == 0 ? 0 : n0 + (long long)(t - 1) * q;
+                            // clicked slots before this sub-step: from the slab, or counted again when the
+                            // slab does not describe the unit
+                            const int n_clk0 = (su->flags & 1u) != 0u ? clicks_before(src, k, p.u2, p.volume, j0) : cbase;
                             double b = remaining, unused = 0.0;
-                            UnitCur cur = {j0, 0, 0, kSerUseAcc && k < kSerCacheK ? s_acc[warp][k].S : acc.S[u], 0};
+                            UnitCur cur = {j0, 0, 0, acc.S[u], 0, n_clk0};
                             const LaneOut o = lane_walk<PhiloxSrc, false, true>(src, no_tape, u, k, t, n, p, cur, b, unused);
-                            B = o.B; S = o.S; cost_c = o.cost_cents; rev_c = o.rev_cents;
+                            I = o.I; B = o.B; S = o.S; cost_c = o.cost_cents; rev_c = o.rev_cents;
                             rev_done = true;
                             next = __dsub_rn(a.budget_alias ? b : remaining, o.lane_cost_sum);
                         }
@@ -2110,49 +1979,35 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a)
                             S += (int)(sl >> 31);
                         }
                         if (S > 0) {
-                            const int r0 = kSerUseAcc && k < kSerCacheK ? s_acc[warp][k].S : acc.S[u];
+                            const int r0 = acc.S[u];
+                            const float rm = su->rev_mean, rs = su->rev_sd;
                             uint4 rw = make_uint4(0, 0, 0, 0);
                             for (int i = 0; i < S; ++i) {
                                 const int r = r0 + i;
                                 if (i == 0 || (r & 3) == 0) rw = src.draw(ST_REVENUE, (uint32_t)k, (uint32_t)(r >> 2));
                                 const uint32_t w = (r & 3) == 0 ? rw.x : (r & 3) == 1 ? rw.y : (r & 3) == 2 ? rw.z : rw.w;
-                                rev_c += revenue_cents(w, su.rev_mean, su.rev_sd);
+                                rev_c += revenue_cents(w, rm, rs);
                             }
                         }
                     }
-                    if (kSerUseAcc && k < kSerCacheK) {
-                        SerAcc ac = s_acc[warp][k];
-                        ac.I += I; ac.B += B; ac.S += S; ac.cost += cost_c; ac.rev += rev_c;
-                        s_acc[warp][k] = ac;
-                    } else {
-                        acc.I[u] += I;
-                        acc.B[u] += B;
-                        acc.S[u] += S;
-                        a.out.cost_cents[u] += cost_c;
-                        a.out.revenue_cents[u] += rev_c;
-                    }
+                    acc.I[u] += I;
+                    acc.B[u] += B;
+                    acc.S[u] += S;
+                    a.out.cost_cents[u] += cost_c;
+                    a.out.revenue_cents[u] += rev_c;
                 }
                 __syncwarp();
             }
         }
-        for (int k = lane; kSerUseAcc && k < K && k < kSerCacheK; k += 32) {
-            const int64_t u = (int64_t)e * K + k;
-            const SerAcc ac = s_acc[warp][k];
-            a.out.impressions[u] = ac.I;
-            a.out.clicks[u] = ac.B;
-            a.out.conversions[u] = ac.S;
-            a.out.cost_cents[u] = ac.cost;
-            a.out.revenue_cents[u] = ac.rev;
-        }
-        __syncwarp();
-        // ---- float outputs, reward, env tail, drift
+        // ---- float outputs, reward, env tail, episode accumulation, drift
         long long profit_c = 0;
         for (int k = lane; k < K; k += 32) {
             const int64_t u = (int64_t)e * K + k;
             const long long cc = a.out.cost_cents[u], rc = a.out.revenue_cents[u];
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cc));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rc));
-            if (!kSerUseAcc || k >= kSerCacheK) ser_publish(a, acc, u);
+            ser_publish(a, acc, u);
+            if (a.out.episode_profit_cents != nullptr) a.out.episode_profit_cents[u] += rc - cc;
             profit_c += rc - cc;
         }
 #pragma unroll
@@ -2193,23 +2048,6 @@ static int num_sms()
         if (g_num_sms <= 0) g_num_sms = 148;
     }
     return g_num_sms;
-}
-
-template <int L>
-static cudaError_t launch_lanes(const adc_step_args &a, cudaStream_t s, int64_t *launches)
-{
-    const int block = 256;
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adc_lanes_philox_implicit_kernel<L>, block, 0);
-    if (per_sm < 1) per_sm = 1;
-    const int64_t total = (int64_t)a.E * a.kw.K;
-    const int64_t want = (total * L + block - 1) / block;
-    int64_t grid = (int64_t)num_sms() * per_sm;
-    if (want < grid) grid = want;
-    if (grid < 1) grid = 1;
-    adc_lanes_philox_implicit_kernel<L><<<(unsigned)grid, block, 0, s>>>(a);
-    ++*launches;
-    return cudaGetLastError();
 }
 
 template <int W, int RING, int DEPTH, int MINB>
@@ -2256,16 +2094,12 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     cudaError_t err = cudaSuccess;
     adc_tape t0 = {};
     const adc_tape &tp = tape ? *tape : t0;
-    if (tape == nullptr && !explicit_kw && a.n_lanes <= 0) {
+    if (tape == nullptr && !explicit_kw) {
         const int block = kFlatWarps * 32;
         int per_sm = 0;
         constexpr int kBU = 32;  // units per big batch
-        // n_lanes: 0 / -32 -> 32 lanes per unit, -16, -8 -> sub-warp groups (A/B)
-        const bool fl = a.floor_cents != nullptr;
-        void (*kern)(adc_step_args) =
-            a.n_lanes == -8    ? (fl ? adc_flat_philox_implicit_kernel<8, true> : adc_flat_philox_implicit_kernel<8, false>)
-            : a.n_lanes == -16 ? (fl ? adc_flat_philox_implicit_kernel<16, true> : adc_flat_philox_implicit_kernel<16, false>)
-                               : (fl ? adc_flat_philox_implicit_kernel<32, true> : adc_flat_philox_implicit_kernel<32, false>);
+        const bool fl = a.floor_cents != nullptr || a.env_group > 1;
+        void (*kern)(adc_step_args) = fl ? adc_flat2_implicit_kernel<true> : adc_flat2_implicit_kernel<false>;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
         if (per_sm < 1) per_sm = 1;
         int64_t grid = (int64_t)num_sms() * per_sm;
@@ -2275,17 +2109,6 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         kern<<<(unsigned)grid, block, 0, s>>>(a);
         ++*launches;
         err = cudaGetLastError();
-    } else if (tape == nullptr && !explicit_kw) {
-        int L = a.n_lanes;
-        switch (L) {
-            case 1: err = launch_lanes<1>(a, s, launches); break;
-            case 2: err = launch_lanes<2>(a, s, launches); break;
-            case 4: err = launch_lanes<4>(a, s, launches); break;
-            case 8: err = launch_lanes<8>(a, s, launches); break;
-            case 16: err = launch_lanes<16>(a, s, launches); break;
-            case 32: err = launch_lanes<32>(a, s, launches); break;
-            default: return cudaErrorInvalidValue;
-        }
     } else if (tape == nullptr) {
         auto kern = adc_units_kernel<PhiloxSrc, true>;
         kern<<<(unsigned)grid_for(kern, 128, total), 128, 0, s>>>(a, tp);
@@ -2314,9 +2137,15 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     }
     if (err != cudaSuccess) return err;
     // exact serial walk of the queued envs (reads the count on the device; exits at once if 0)
-    if (tape == nullptr && !explicit_kw && a.n_lanes != 1) {
+    const int64_t slab_bytes = (int64_t)a.kw.K * (int64_t)sizeof(SlabUnit);
+    const int64_t n_slabs = a.scratch.serial_ws != nullptr ? a.scratch.serial_ws_bytes / slab_bytes : 0;
+    if (tape == nullptr && !explicit_kw && a.n_lanes != 1 && a.detail.costs == nullptr && n_slabs > 0) {
+        // one warp per queued env, each with its own slab of the workspace
         auto kern = adc_serial_warp_implicit_kernel;
-        kern<<<(unsigned)grid_for(kern, kSerWarps * 32, (int64_t)a.E * 32), kSerWarps * 32, 0, s>>>(a);
+        int64_t grid = grid_for(kern, kSerWarps * 32, (int64_t)a.E * 32);
+        const int64_t by_ws = (n_slabs + kSerWarps - 1) / kSerWarps;
+        if (by_ws < grid) grid = by_ws;
+        kern<<<(unsigned)grid, kSerWarps * 32, 0, s>>>(a, (int)(n_slabs > 0x7FFFFFFF ? 0x7FFFFFFF : n_slabs));
     } else if (tape == nullptr) {
         auto kern = adc_serial_kernel<PhiloxSrc>;
         kern<<<(unsigned)grid_for(kern, 64, a.E), 64, 0, s>>>(a, tp);
@@ -2327,6 +2156,8 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     ++*launches;
     return cudaGetLastError();
 }
+
+int64_t serial_slab_bytes(int32_t K) { return (int64_t)K * (int64_t)sizeof(SlabUnit); }
 
 cudaError_t launch_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day,
                               cudaStream_t s, int64_t *launches)

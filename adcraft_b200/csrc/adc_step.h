@@ -11,6 +11,7 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
 cudaError_t launch_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day,
                               cudaStream_t s, int64_t *launches);
 
+int64_t serial_slab_bytes(int32_t K);
 cudaError_t launch_ideal_profit(const adc_ideal_args &a, cudaStream_t s, int64_t *launches);
 
 }  // namespace adc

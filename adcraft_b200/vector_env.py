@@ -88,6 +88,8 @@ class VectorBiddingSimulation:
         env_group: int = 0,
         dynamic_work: bool = True,
         f32_ties: bool = False,
+        episode_profit: bool = False,
+        serial_ws_bytes: int = 1 << 30,
         **kwargs,
     ) -> None:
         assert render_mode is None or render_mode in self.metadata["render_modes"], (
@@ -115,6 +117,11 @@ class VectorBiddingSimulation:
         # numpy >= 2 tie rule for float32 bids (adc_step_args.f32_ties): off = the
         # float64 semantics of the build contract (ties always lose)
         self.f32_ties = bool(f32_ties)
+        # [E, K] int64 running sum of every step's exact per-keyword profit (adc_step_out.
+        # episode_profit_cents): what AKNCP / NCP are made of, accumulated inside the step kernels
+        self.episode_profit = bool(episode_profit)
+        # cap of the exact serial walk's workspace (one 640 B x K slab per resident warp)
+        self.serial_ws_cap = int(serial_ws_bytes)
         self.env_base = int(env_base)
         self.n_lanes = int(n_lanes)
         self._auto_lanes = n_lanes == 0
@@ -175,6 +182,11 @@ class VectorBiddingSimulation:
             serial_list=z(E, dtype=i32), serial_count=z(2, dtype=i32), env_profit=z(E, dtype=i64),
             env_cost=z(E, dtype=i64), env_done=z(E, dtype=i32), unit_cost_f64=z(E, K, dtype=f64),
             work_counter=z(2, dtype=i32))
+        if self.episode_profit:
+            self._out["episode_profit_cents"] = z(E, K, dtype=i64)
+        slab = int(self._lib.adc_serial_slab_bytes(K))
+        n_slabs = max(1, min(E, 148 * 24, self.serial_ws_cap // max(slab, 1)))
+        self._scratch["serial_ws"] = torch.empty(n_slabs * slab, dtype=torch.uint8, device=dev)
         self._detail = None
         if self.detail_cap > 0:
             c = self.detail_cap
@@ -243,11 +255,6 @@ class VectorBiddingSimulation:
         self.keywords = table
         self.kind = table.kind
         self._have_keywords = True
-        if self._auto_lanes:
-            # 32 lanes per unit for every volume: since the hot kernel flattens the volume
-            # remainders across its 32-unit batch, sparse keyword sets no longer gain from the
-            # sub-warp variants (-16 / -8, kept for A/B runs)
-            self.n_lanes = 0
 
     def install_device_keywords(self, cols: Dict[str, torch.Tensor], kind: int = kwmod.IMPLICIT) -> None:
         """Use per-env keyword parameters that already live on the device ([E, K] float64 tensors,
@@ -444,6 +451,8 @@ class VectorBiddingSimulation:
         for n in ("serial_list", "serial_count", "env_profit", "env_cost", "env_done", "unit_cost_f64"):
             setattr(sc, n, s[n].data_ptr())
         sc.work_counter = s["work_counter"].data_ptr() if self.dynamic_work else None
+        sc.serial_ws, sc.serial_ws_bytes = s["serial_ws"].data_ptr(), s["serial_ws"].numel()
+        out.episode_profit_cents = _ptr(o.get("episode_profit_cents"))
         if self._detail is not None:
             a.detail.cap = self.detail_cap
             for n in ("costs", "rev_per_cost", "n_recorded", "volume_seen", "lane_clicks", "lane_convs"):

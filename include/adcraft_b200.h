@@ -117,6 +117,10 @@ typedef struct adc_step_out {
     uint8_t *terminated;    /* [E] */
     uint8_t *truncated;     /* [E] */
     double *remaining_budget; /* [E] optional: budget left after the day */
+    int64_t *episode_profit_cents; /* [E,K] optional running sum: += revenue_cents - cost_cents of every
+                                 step, added when the env's step is final (the per-keyword profits
+                                 AKNCP / NCP are made of, experiment_metrics.py:64-83); the caller
+                                 zeroes it at the episode boundaries it cares about */
 } adc_step_out;
 
 /* Scratch the step needs (caller-owned so that nothing is allocated per call). */
@@ -139,6 +143,13 @@ typedef struct adc_scratch {
     int32_t *acc_impressions;
     int32_t *acc_clicks;
     int32_t *acc_conversions;
+    /* Optional DEVICE workspace of the warp-cooperative exact serial walk (free-running implicit
+     * keywords): every resident warp expands one queued env's day into a slab of K x 640 bytes
+     * (adc_serial_slab_bytes(K)); 16-byte aligned.  The launcher runs as many warps as slabs fit
+     * (about 3500 resident warps at most); NULL / too small for one slab: the walk falls back to one
+     * thread per env (correct, much slower). */
+    void *serial_ws;
+    int64_t serial_ws_bytes;
 } adc_scratch;
 
 /* Optional per-click detail (the ragged lists of BiddingOutcomes, bidding_simulation.py:10-38, that
@@ -168,11 +179,9 @@ typedef struct adc_step_args {
                                ADC_ERR_INVALID when it is not the calling thread's current
                                device.  -1: not checked                                        */
     uint64_t seed;          /* Philox key                                          */
-    int32_t n_lanes;        /* lanes per (env,keyword) unit.  0 / -32: warp-batched hot kernel with 32
-                               lanes per unit (fastest for every volume: the volume remainders of a
-                               batch are flattened); -16 / -8: its older variant with sub-warp groups
-                               (A/B); 1..32 (pow2): the simpler L-threads-per-unit kernel (A/B and
-                               detail recording, n_lanes = 1) */
+    int32_t n_lanes;        /* 0: default.  1: queued envs take the one-thread-per-env exact walk (the only
+                               one that records adc_detail).  Other values of the round-1 ABI (-8, -16,
+                               -32, 2..32) are accepted and mean 0 */
     int32_t budget_alias;   /* 1: ndarray-budget double charge (bsim:102 + :225), 0: scalar budget */
     int32_t autoreset;      /* 1: zero cum_profit/day of finished envs after reporting them */
     int32_t force_serial;   /* 1: run every env through the exact serial kernel (testing)   */
@@ -262,6 +271,8 @@ int adc_device_count(void);
 int adc_sizeof_step_args(void);
 int adc_sizeof_tape(void);
 int adc_sizeof_ideal_args(void);
+/* Bytes of adc_scratch.serial_ws one slab (one resident warp of the exact serial walk) needs for K keywords. */
+int64_t adc_serial_slab_bytes(int32_t K);
 
 /* One free-running env step for E envs (counter-based Philox draws keyed by
  * (seed, env_base+e, keyword, step)).  Launches: fused lane kernel, then the exact serial kernel

@@ -39,7 +39,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 }
 
 /* counter layout: c0 = index, c1 = step, c2 = stream<<28 | agent<<20 | kw, c3 = env */
-enum { ST_AUCTION = 0, ST_UNIT = 1, ST_REVENUE = 2, ST_PHANTOM = 3 };
+enum { ST_AUCTION = 0, ST_UNIT = 1, ST_REVENUE = 2, ST_PHANTOM = 3, ST_IDEAL = 4, ST_COST = 5 };
 
 static void draw4(uint64_t seed, uint32_t env, uint32_t step, uint32_t agent, uint32_t kw,
                   uint32_t stream, uint32_t idx, uint32_t out[4])
@@ -231,6 +231,105 @@ int32_t orc_bid_to_cents(double bid)
 }
 
 /* ------------------------------------------------------------------------- */
+/* 2b. free-running implicit keywords: the O(clicks) tape function */
+/* ------------------------------------------------------------------------- */
+/* The reference draws one competitor bid per auction, c = around(|Laplace(loc,scale)|, 2)
+ * (helpers:104-113), wins iff bid > c (helpers:166-177), then flips click and conversion coins
+ * (helpers:73-77).  Only the clicked auctions' prices ever matter, so the free-running mode draws
+ * exactly that: per auction j ONE 32-bit uniform R_j decides the nested events
+ *     win  <=> R_j < T1 = P(c < win_cents) * 2^32
+ *     click<=> R_j < T2 = T1 * ctr           conversion <=> R_j < T3 = T2 * cvr
+ * and every CLICKED auction draws its price from the competitor-bid distribution conditioned on
+ * c < win_cents (inverse CDF of the folded Laplace restricted to the winning window).  The joint law
+ * of (impressions, clicks, conversions, costs) is the reference's; lost and unclicked auctions never
+ * materialise a competitor bid.
+ *
+ * R_j is stored bit-sliced so that the GPU can evaluate 32 auctions per word operation: auctions
+ * come in groups of 32 (g = j / 32, bit p = j % 32); level l (0 = most significant) of group g is
+ * word (l & 3) of Philox call 8 g + (l >> 2) of the AUCTION stream; bit p of that word is bit
+ * (31 - l) of R_j.  The GPU stops reading levels as soon as every auction of the group is decided;
+ * this oracle assembles the full 32-bit R_j and compares. */
+typedef struct {
+    uint64_t T1, T2, T3; /* thresholds in [0, 2^32] */
+    uint64_t h1;         /* half-width (2^-31 units) of window 1: x in (-ymax, min(L, ymax)) */
+    uint32_t A1, A2;     /* e^-hi of the two windows, 2^-32 units */
+    float L, b;          /* |loc|, scale */
+    int32_t W;           /* cents the competitor must stay below (bid cents, +1 under the f32 tie rule) */
+} orc_unit2;
+
+static uint64_t rint_u64(double x) { return x <= 0.0 ? 0u : (uint64_t)rint(x); }
+
+void orc_unit2_make(double loc, double scale, double ctr, double cvr, int32_t win_cents, orc_unit2 *u)
+{
+    const double ymax = ((double)win_cents - 0.5) / 100.0; /* round(|x| * 100) < W  <=>  |x| < (W - 0.5) / 100 */
+    const double L = fabs(loc);
+    const double b = scale > 1e-9 ? scale : 1e-9;
+    const double d = L - ymax;
+    const double lo1 = (d > 0.0 ? d : 0.0) / b, hi1 = (L + ymax) / b;
+    const double e_lo1 = orc_exp(-lo1), e_hi1 = orc_exp(-hi1);
+    double l1 = e_lo1 - e_hi1, l2 = 0.0, e_hi2 = 1.0;
+    if (!(l1 > 0.0)) l1 = 0.0;
+    if (ymax > L) { e_hi2 = orc_exp(-((ymax - L) / b)); l2 = 1.0 - e_hi2; }
+    u->h1 = rint_u64(l1 * 2147483648.0);
+    const uint64_t h2 = rint_u64(l2 * 2147483648.0);
+    u->T1 = u->h1 + h2;
+    if (u->T1 > 4294967296ull) u->T1 = 4294967296ull;
+    if (u->h1 > u->T1) u->h1 = u->T1;
+    const double c1 = clampd(ctr, 0.0, 1.0), c2 = clampd(cvr, 0.0, 1.0);
+    u->T2 = rint_u64((double)u->T1 * c1);
+    if (u->T2 > u->T1) u->T2 = u->T1;
+    u->T3 = rint_u64((double)u->T2 * c2);
+    if (u->T3 > u->T2) u->T3 = u->T2;
+    const uint64_t a1 = rint_u64(e_hi1 * 4294967296.0), a2 = rint_u64(e_hi2 * 4294967296.0);
+    u->A1 = a1 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)a1;
+    u->A2 = a2 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)a2;
+    u->L = (float)L; u->b = (float)b; u->W = win_cents;
+}
+
+/* -ln(a / 2^32) for an odd 32-bit a (the table sampler of orc_neglog_u31 on a given fixed-point value) */
+static float neglog_fixed(uint32_t a)
+{
+    const int lz = __builtin_clz(a);
+    const uint32_t an = a << lz;
+    const uint32_t idx = (an >> 24) & 0x7Fu;
+    const uint32_t lo = an & 0x00FFFFFFu;
+    const float inner = fmaf(-(float)lo, ORC_NEGLOG_TAB[idx][1], ORC_NEGLOG_TAB[idx][0]);
+    return fmaf((float)lz, ORC_LN2F, inner);
+}
+
+/* Price of a clicked auction in cents: the competitor bid given that it lost to `W`.
+ * t = e^-E is uniform on the union of (e^-hi1, e^-lo1) [x = L - b E, left of the mode or the
+ * mirrored tail] and (e^-hi2, 1) [x = L + b E, right of the mode]; w picks a point of that union. */
+int32_t orc_cost_cents(uint32_t w, const orc_unit2 *u)
+{
+    const uint64_t s = u->T1 >= 4294967296ull ? (uint64_t)w : (((uint64_t)w * u->T1) >> 32);
+    const int left = s < u->h1;
+    const uint64_t off = left ? s : s - u->h1;
+    uint64_t t = (uint64_t)(left ? u->A1 : u->A2) + 2u * off + 1u;
+    if (t > 0xFFFFFFFFull) t = 0xFFFFFFFFull;
+    const float e = neglog_fixed((uint32_t)t | 1u);
+    const float x = fmaf(left ? -u->b : u->b, e, u->L);
+    int32_t c = (int32_t)lrintf(fabsf(x) * 100.0f);
+    if (c > u->W - 1) c = u->W - 1;
+    return c < 0 ? 0 : c;
+}
+
+/* the 32 uniforms R_j of group g (auctions 32 g .. 32 g + 31) */
+static void group_uniforms(uint64_t seed, uint32_t env, uint32_t step, uint32_t agent, uint32_t kw,
+                           uint32_t g, uint32_t R[32])
+{
+    uint32_t w[4];
+    memset(R, 0, 32 * sizeof(uint32_t));
+    for (uint32_t q = 0; q < 8; ++q) {
+        draw4(seed, env, step, agent, kw, ST_AUCTION, 8u * g + q, w);
+        for (uint32_t i = 0; i < 4; ++i) {
+            const uint32_t l = 4u * q + i;
+            for (uint32_t p = 0; p < 32; ++p) R[p] |= ((w[i] >> p) & 1u) << (31u - l);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
 /* 3. one env step                                                             */
 /* ------------------------------------------------------------------------- */
 typedef struct {
@@ -239,6 +338,7 @@ typedef struct {
     uint64_t seed; uint32_t env, step, agent;
     orc_record *rec;
     const int32_t *floor_cents; /* shared auctions: highest rival bid per keyword, or NULL */
+    const int32_t *win_cents;   /* free-running: cents the competitor must stay below, or NULL = bid_cents */
 } draw_src;
 
 typedef struct { /* per-keyword running cursors for one env step */
@@ -250,7 +350,7 @@ typedef struct { /* per-keyword running cursors for one env step */
 
 static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, double *remaining,
                     int alias, int64_t n, draw_src *src, kw_cursor *cur, orc_result *out,
-                    uint32_t thr_click, uint32_t thr_conv, uint64_t thr_cc, uint32_t thr_impr,
+                    uint32_t thr_click, uint32_t thr_conv, const orc_unit2 *u2, uint32_t thr_impr,
                     double *cost_seq, double *rev_seq)
 {
     /* One call of simulate_epoch_of_bidding (bidding_simulation.py:44-120). */
@@ -271,17 +371,30 @@ static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, dou
 
     /* --- keyword.auction (classes:520-538 explicit / :623-646 + helpers:116-180) --- */
     if (!explicit_kw) {
+        uint32_t R[32]; int64_t have_g = -1;
         for (int64_t a = 0; a < n; ++a) {
             int64_t j = cur->auction + a;
             int32_t c;
-            uint32_t w1 = 0, w2 = 0;
+            int click_bit = 0, conv_bit = 0;
             if (src->mode == 0) {
                 c = tp->comp_cents[tp->comp_off[k] + j];
             } else {
-                /* two auctions per Philox call: even j -> words 0,1; odd j -> words 2,3 */
-                draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_AUCTION, (uint32_t)(j >> 1), w);
-                c = orc_laplace_cents(w[(j & 1) ? 2 : 0], (float)kw->p1[k], (float)kw->p2[k]);
-                w1 = w[(j & 1) ? 3 : 1]; w2 = w1; /* click and conversion share the word cc */
+                /* O(clicks) tape function (section 2b): one uniform per auction decides win / click /
+                 * conversion; only a clicked auction draws its price, from the competitor-bid law
+                 * conditioned on losing to us, indexed by its click rank inside the 32-auction group */
+                const int64_t g = j >> 5; const int p = (int)(j & 31);
+                if (g != have_g) { group_uniforms(src->seed, src->env, src->step, src->agent, (uint32_t)k, (uint32_t)g, R); have_g = g; }
+                const int won = (uint64_t)R[p] < u2->T1;
+                click_bit = (uint64_t)R[p] < u2->T2;
+                conv_bit = (uint64_t)R[p] < u2->T3;
+                if (click_bit) {
+                    uint32_t r = 0;
+                    for (int q = 0; q < p; ++q) r += (uint64_t)R[q] < u2->T2;
+                    draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_COST, 8u * (uint32_t)g + (r >> 2), w);
+                    c = orc_cost_cents(w[r & 3], u2);
+                } else {
+                    c = won ? 0 : u2->W; /* never looked at again: an unclicked win / a loss (what a recorded tape holds) */
+                }
                 if (rec && j < rec->cap_per_kw) { rec->comp_cents[(int64_t)k * rec->cap_per_kw + j] = c; rec->n_comp[k] = (int32_t)(j + 1); }
             }
             /* shared auction: the rivals' bids join the sampled competitor in other_bids; with
@@ -289,15 +402,14 @@ static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, dou
             if (src->floor_cents && src->floor_cents[k] > c) c = src->floor_cents[k];
             /* nth_price_auction(n=2, num_winners=1): win iff bid > max(other bids)
              * (strict; searchsorted-left index must exceed n), cost = that maximum. */
-            if (bid_cents > c) {
+            if ((src->mode == 1 ? u2->W : bid_cents) > c) {
                 slot_cost[slots] = (double)c / 100.0;
                 clicked[slots] = 0;
-                /* philox mode: click/conv words travel with the auction */
-                slot_w2[slots] = w2;
-                if (src->mode == 1) clicked[slots] = (uint8_t)(w1 <= thr_click) | 0x80; /* bit7: decided */
+                slot_w2[slots] = (uint32_t)conv_bit;
+                if (src->mode == 1) clicked[slots] = (uint8_t)click_bit | 0x80; /* bit7: decided */
                 if (src->mode == 1 && rec) {
                     int64_t pos = (int64_t)k * rec->cap_per_kw + cur->n_click + slots;
-                    if (cur->n_click + slots < rec->cap_per_kw) rec->u_click[pos] = (double)w1 * 2.3283064365386963e-10;
+                    if (cur->n_click + slots < rec->cap_per_kw) rec->u_click[pos] = click_bit ? 0.0 : 1.0;
                 }
                 ++slots; ++I;
             }
@@ -387,8 +499,8 @@ static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, dou
                 conv = aw2[i] <= thr_conv;
                 if (rec && cur->n_conv + i < rec->cap_per_kw) rec->u_conv[(int64_t)k * rec->cap_per_kw + cur->n_conv + i] = (double)aw2[i] * 2.3283064365386963e-10;
             } else {
-                conv = (uint64_t)aw2[i] < thr_cc;
-                if (rec && cur->n_conv + i < rec->cap_per_kw) rec->u_conv[(int64_t)k * rec->cap_per_kw + cur->n_conv + i] = orc_conv_uniform(aw2[i], thr_click);
+                conv = (int)aw2[i]; /* the auction's own conversion bit (R_j < T3) */
+                if (rec && cur->n_conv + i < rec->cap_per_kw) rec->u_conv[(int64_t)k * rec->cap_per_kw + cur->n_conv + i] = conv ? 0.0 : 1.0;
             }
         }
         S += conv;
@@ -440,11 +552,12 @@ static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, dou
 static int step_common(const orc_keywords *kw, const int32_t *bid_cents, double budget,
                        int alias, draw_src *src, orc_result *out)
 {
+    const int32_t *win_cents = src->win_cents; /* free-running f32 tie rule: bid cents + bonus, or NULL */
     const int K = kw->K;
     int64_t *vol = (int64_t *)malloc(sizeof(int64_t) * K);
     kw_cursor *cur = (kw_cursor *)calloc(K, sizeof(kw_cursor));
     uint32_t *thr = (uint32_t *)malloc(sizeof(uint32_t) * 3 * K);
-    uint64_t *thr_cc = (uint64_t *)malloc(sizeof(uint64_t) * K);
+    orc_unit2 *u2 = (orc_unit2 *)calloc(K, sizeof(orc_unit2));
     double *cost_seq = (double *)calloc(K, sizeof(double));
     double *rev_seq = (double *)calloc(K, sizeof(double));
     uint32_t w[4];
@@ -466,7 +579,8 @@ static int step_common(const orc_keywords *kw, const int32_t *bid_cents, double 
         thr[3 * k + 0] = orc_prob_threshold(kw->ctr[k]);
         thr[3 * k + 1] = orc_prob_threshold(kw->cvr[k]);
         thr[3 * k + 2] = 0;
-        thr_cc[k] = orc_conv_threshold(thr[3 * k + 0], kw->cvr[k]);
+        if (kw->kind == ORC_IMPLICIT && src->mode == 1)
+            orc_unit2_make(kw->p1[k], kw->p2[k], kw->ctr[k], kw->cvr[k], win_cents ? win_cents[k] : bid_cents[k], &u2[k]);
         if (kw->kind == ORC_EXPLICIT) {
             double bid = (double)bid_cents[k] / 100.0;
             double p = orc_threshold_sigmoid(bid, kw->impression_thresh, kw->p1[k], kw->p2[k]);
@@ -489,7 +603,7 @@ static int step_common(const orc_keywords *kw, const int32_t *bid_cents, double 
             int64_t q = vol[k] / ORC_SUBSTEPS;
             int64_t n = (t == 0) ? vol[k] - (ORC_SUBSTEPS - 1) * q : q;
             rc = lane_run(kw, k, t, bid_cents[k], &remaining, alias, n, src, &cur[k], out,
-                          thr[3 * k], thr[3 * k + 1], thr_cc[k], thr[3 * k + 2], &cost_seq[k], &rev_seq[k]);
+                          thr[3 * k], thr[3 * k + 1], &u2[k], thr[3 * k + 2], &cost_seq[k], &rev_seq[k]);
             if (rc) { stop = 1; break; }
             ++lanes;
             if (remaining <= 0) { stop = 1; break; } /* bsim:230-233 */
@@ -506,7 +620,7 @@ static int step_common(const orc_keywords *kw, const int32_t *bid_cents, double 
     out->reward = reward;
     out->remaining_budget = remaining;
     out->lanes_run = lanes;
-    free(vol); free(cur); free(thr); free(thr_cc); free(cost_seq); free(rev_seq);
+    free(vol); free(cur); free(thr); free(u2); free(cost_seq); free(rev_seq);
     return rc;
 }
 

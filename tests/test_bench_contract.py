@@ -28,7 +28,11 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["data"] == "synthetic"
     assert d["config"]["workload"].startswith("C2:") and d["config"]["envs_per_gpu"] == 4096
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    # the reference's own Python when its staged copy (baseline/_ref) or /root/reference is present,
+    # else the C port
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    if cb["kind"] == "reference":
+        assert 50 < cb["units_per_s_per_core"] < 5000 and cb["c_port"]["kind"] == "port"
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -125,11 +125,15 @@ def test_shared_auction_is_nth_price_auction_on_rivals_plus_competitor(orc):
         bids = rng.integers(20, 140, (A, K)).astype(np.int32)
         bids[1, 0] = bids[0, 0] = bids[:, 0].max() + 1          # a tie at the top: nobody wins keyword 0
         bids[3, 1] = 1                                           # a bidder far below the field
-        solo = orc.step_philox(kw, bids[0], 1e9, seed=5, env_id=2, step=step, record_cap=512)
-        comp = [np.asarray(solo["tape"].comp_cents[solo["tape"].comp_off[k]:solo["tape"].comp_off[k + 1]])
-                for k in range(K)]
         winners = np.zeros(K, int)
         for a in range(A):
+            # the world's draws as bidder a sees them without rivals: the free-running mode decides
+            # every auction by one shared uniform R_j (win <=> R_j < T1(bid)), so the recorded
+            # competitor stream of a solo run holds the price of every auction this bid would win
+            # and a losing value everywhere else; all bidders of a world share the R_j
+            solo = orc.step_philox(kw, bids[a], 1e9, seed=5, env_id=2, step=step, record_cap=512)
+            comp = [np.asarray(solo["tape"].comp_cents[solo["tape"].comp_off[k]:solo["tape"].comp_off[k + 1]])
+                    for k in range(K)]
             rivals = np.delete(bids, a, axis=0)
             floor = rivals.max(axis=0).astype(np.int32)
             out = orc.step_philox_shared(kw, bids[a], floor, 1e9, seed=5, world_id=2, step=step)
