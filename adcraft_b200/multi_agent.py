@@ -73,7 +73,9 @@ class SharedAuctionSimulation:
     @staticmethod
     def rival_floor_cents(bids: torch.Tensor) -> torch.Tensor:
         """[worlds, A, K] dollars -> int32 cents of the highest RIVAL bid per bidder (bids are
-        canonicalised like the env does, ``round(max(bid, 0.01), 2)``, gymnasium_kw_env.py:215)."""
+        canonicalised like the env does, ``round(max(bid, 0.01), 2)``, gymnasium_kw_env.py:215).
+        Tensor restatement of what the kernels compute per unit (``unit_floor`` in csrc/adc_step.cu);
+        ``step`` does not call it -- pass its result as ``floor_cents`` to ``vec.step`` to A/B the two."""
         cents = torch.round(torch.clamp(bids.to(torch.float64), min=0.01) * 100.0).to(torch.int32)
         first = cents.amax(dim=1, keepdim=True)
         is_top = cents == first
@@ -94,11 +96,12 @@ class SharedAuctionSimulation:
     def step(self, bids: torch.Tensor, budget: Optional[torch.Tensor] = None, *, force_serial: bool = False):
         W, A, K = self.num_worlds, self.num_agents, self.vec.num_keywords
         assert tuple(bids.shape) == (W, A, K)
-        floor = self.rival_floor_cents(bids).view(W * A, K)
+        # the kernels find every bidder's highest rival themselves (adc_step_args.env_group without a
+        # floor_cents table): one pass over the A bid rows of the world per unit
         action = {"keyword_bids": bids.reshape(W * A, K).contiguous()}
         if budget is not None:
             action["budget"] = budget.reshape(W * A).contiguous()
-        obs, reward, term, trunc, info = self.vec.step(action, force_serial=force_serial, floor_cents=floor)
+        obs, reward, term, trunc, info = self.vec.step(action, force_serial=force_serial)
         return self._split(obs), reward.view(W, A), term.view(W, A), trunc.view(W, A), info
 
 

@@ -344,6 +344,7 @@ typedef struct {
 typedef struct { /* per-keyword running cursors for one env step */
     int64_t auction; /* auctions evaluated so far (day-level ordinal) */
     int64_t n_click, n_conv, n_rev, n_cost;
+    int64_t n_clk; /* free-running implicit: clicked auctions so far, accepted or not (price-draw rank) */
 } kw_cursor;
 
 #define MAX_LANE_STACK 4096
@@ -381,16 +382,15 @@ static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, dou
             } else {
                 /* O(clicks) tape function (section 2b): one uniform per auction decides win / click /
                  * conversion; only a clicked auction draws its price, from the competitor-bid law
-                 * conditioned on losing to us, indexed by its click rank inside the 32-auction group */
+                 * conditioned on losing to us, indexed by its rank among the day's clicked auctions */
                 const int64_t g = j >> 5; const int p = (int)(j & 31);
                 if (g != have_g) { group_uniforms(src->seed, src->env, src->step, src->agent, (uint32_t)k, (uint32_t)g, R); have_g = g; }
                 const int won = (uint64_t)R[p] < u2->T1;
                 click_bit = (uint64_t)R[p] < u2->T2;
                 conv_bit = (uint64_t)R[p] < u2->T3;
                 if (click_bit) {
-                    uint32_t r = 0;
-                    for (int q = 0; q < p; ++q) r += (uint64_t)R[q] < u2->T2;
-                    draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_COST, 8u * (uint32_t)g + (r >> 2), w);
+                    const uint32_t r = (uint32_t)cur->n_clk++; /* rank among the day's clicked auctions */
+                    draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_COST, r >> 2, w);
                     c = orc_cost_cents(w[r & 3], u2);
                 } else {
                     c = won ? 0 : u2->W; /* never looked at again: an unclicked win / a loss (what a recorded tape holds) */

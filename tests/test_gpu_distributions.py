@@ -164,7 +164,7 @@ def test_explicit_click_cost_distribution():
     from adcraft_b200.vector_env import VectorBiddingSimulation
     K, E = 4, 16384
     bids = np.array([0.25, 1.0, 2.0, 2.95])
-    intercept, slope = np.array([0.3, 0.9, 2.1, 2.0]), np.array([9.0, 4.0, 4.0, 6.0])
+    intercept, slope = np.array([0.3, 0.9, 2.1, 2.9]), np.array([9.0, 4.0, 4.0, 6.0])
     table = kwm.KeywordTable(kwm.EXPLICIT, np.full(K, 1.0), np.full(K, 1e-9), intercept, slope,
                              np.full(K, 1.0), np.full(K, 0.5), np.full(K, 1.0), np.full(K, 0.2))
     env = VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=1e9, device="cuda", seed=99,
