@@ -25,6 +25,7 @@
 #include "adc_rng.cuh"
 #include "adc_step.h"
 
+#include <cstddef>
 #include <cstdio>
 
 namespace adc {
@@ -1747,23 +1748,63 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
 // (conversions, revenues).  Nothing is re-drawn per sub-step and no keyword count is special.
 // ------------------------------------------------------------------------------------------
 constexpr int kSerWarps = 4;
-constexpr int kSerCap = 16;        // clicked slots per lane and sub-step in shared memory; more -> direct re-walk
-constexpr int kSlabClicks = 128;   // clicked slots per unit and day in the slab; more -> direct re-walk
-constexpr int kSerMinBlocks = 6;
+constexpr int kSerCap = 32;        // clicked slots per lane and sub-step in shared memory; more -> direct re-walk
+constexpr int kPoolPerUnit = 64;   // the env's price pool holds K x 64 clicked slots; units that do not fit -> direct re-walk
+constexpr int kSerMinBlocks = 7;    // 28 warps per SM: a 4096-env queue is resident in one wave
 
-struct __align__(16) SlabUnit {
-    uint16_t cstart[ADC_SUBSTEPS + 1];  // clicked slots before sub-step t; [24] = the day's total
-    uint16_t imp[ADC_SUBSTEPS];         // impressions of sub-step t
-    uint16_t flags;                     // bit 0: walk this unit with lane_walk instead (volume / clicks beyond the slab)
+constexpr int kSlabGroups = 16;    // 32-auction groups per unit and day in the slab (volume <= 512); more -> direct re-walk
+
+struct __align__(8) SlabUnit {      // 216 B per keyword
+    uint32_t win[kSlabGroups], click[kSlabGroups], conv[kSlabGroups];  // outcome masks of the day's auctions
+    int volume;
     int win_cents;
     float rev_mean, rev_sd;
-    uint32_t click[kSlabClicks];        // price in cents (floor applied) | converts << 31
+    uint32_t cost_off;                  // first price of the unit in the env's pool (uint16 units, multiple of 4)
+    uint16_t n_clk_run;                 // clicked slots of the sub-steps walked so far
+    uint16_t flags;                     // bit 0: walk this unit with lane_walk instead (beyond the slab's caps)
 };
+// A slab = K SlabUnits followed by the env's price pool: uint16 cents (floor applied) of every clicked
+// slot of the day, per unit in click order, units padded to 4 entries.
+constexpr int64_t kSlabBytesPerKeyword = (int64_t)sizeof(SlabUnit) + 2 * kPoolPerUnit;
+
+// A (sub-step, keyword) lane the slab cannot describe (volume, clicks or bid beyond its caps, or more
+// clicked slots than the shared-memory buffer holds): walked again with the budget by lane_walk.  Out
+// of line: its registers stay out of the scan loop.
+struct DirectOut {
+    int I, B, S;
+    long long cost_c, rev_c;
+    double next;  // the campaign's remaining budget after this lane (bsim:102 alias, :225)
+};
+
+__device__ __noinline__ DirectOut serial_direct_lane(const adc_step_args &a, const PhiloxSrc &src, int e, int k, int t,
+                                                     bool recount, int cbase, int n_rev, double remaining)
+{
+    const adc_tape *no_tape = nullptr;
+    const int64_t u = (int64_t)e * a.kw.K + k;
+    UnitPar p = load_unit_par(a, e, k, true);
+    uint4 uw;
+    p.volume = unit_volume(a, src, no_tape, e, k, &uw);
+    const long long q = p.volume / ADC_SUBSTEPS, n0 = p.volume - (ADC_SUBSTEPS - 1) * q;
+    const long long n = t == 0 ? n0 : q, j0 = t == 0 ? 0 : n0 + (long long)(t - 1) * q;
+    // clicked slots before this sub-step: from the slab, or counted again when it does not describe the unit
+    const int n_clk0 = recount ? clicks_before(src, k, p.u2, p.volume, j0) : cbase;
+    double b = remaining, unused = 0.0;
+    UnitCur cur = {j0, 0, 0, n_rev, 0, n_clk0};
+    const LaneOut o = lane_walk<PhiloxSrc, false, true>(src, no_tape, u, k, t, n, p, cur, b, unused);
+    DirectOut d;
+    d.I = o.I; d.B = o.B; d.S = o.S; d.cost_c = o.cost_cents; d.rev_c = o.rev_cents;
+    d.next = __dsub_rn(a.budget_alias ? b : remaining, o.lane_cost_sum);
+    return d;
+}
+
+static_assert(sizeof(SlabUnit) % 8 == 0, "slab layout: the pool behind K units stays 8-byte aligned");
 
 __global__ void __launch_bounds__(kSerWarps * 32, kSerMinBlocks)
 adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_slabs)
 {
     __shared__ uint32_t s_slot[kSerWarps][kSerCap][32];
+    __shared__ FlatCost s_cost[kSerWarps][32];
+    __shared__ int s_start[kSerWarps][33];
     __shared__ float2 s_tab[128];  // Exp(1) sampler table, staged from global
     if (threadIdx.x < 128) s_tab[threadIdx.x] = kNeglogTab[threadIdx.x];
     __syncthreads();
@@ -1778,104 +1819,141 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const adc_tape *no_tape = nullptr;
     if (gwarp >= n_warps) return;
-    SlabUnit *slab = reinterpret_cast<SlabUnit *>(a.scratch.serial_ws) + (size_t)gwarp * K;
+    unsigned char *const slab_raw = reinterpret_cast<unsigned char *>(a.scratch.serial_ws) +
+                                    (size_t)gwarp * (size_t)K * (size_t)kSlabBytesPerKeyword;
+    SlabUnit *slab = reinterpret_cast<SlabUnit *>(slab_raw);
+    uint16_t *const pool = reinterpret_cast<uint16_t *>(slab_raw + (size_t)K * sizeof(SlabUnit));
+    const unsigned pool_cap = (unsigned)K * (unsigned)kPoolPerUnit;
 
     for (int idx = gwarp; idx < count; idx += n_warps) {
         const int e = a.scratch.serial_list[idx];
         PhiloxSrc src{k0, k1, a.step, philox_env(a, e)};
-        // ---- phase 0 (lane <-> keyword): expand the day into the slab
-        for (int k = lane; k < K; k += 32) {
-            const int64_t u = (int64_t)e * K + k;
-            acc.I[u] = 0;
-            acc.B[u] = 0;
-            acc.S[u] = 0;
-            a.out.cost_cents[u] = 0;
-            a.out.revenue_cents[u] = 0;
-            UnitPar p = load_unit_par(a, e, k, true);
-            uint4 uw;
-            const long long Vl = unit_volume(a, src, no_tape, e, k, &uw);
-            SlabUnit *su = slab + k;
-            su->win_cents = p.win_cents;
-            su->rev_mean = p.rev_mean;
-            su->rev_sd = p.rev_sd;
-            const bool beats_rivals = p.u2.W > p.floor_cents;
-            uint16_t flags = Vl > kMaxFlatVolume ? 1 : 0;
-            for (int t = 0; t < ADC_SUBSTEPS; ++t) { su->imp[t] = 0; su->cstart[t] = 0; }
-            su->cstart[ADC_SUBSTEPS] = 0;
-            if (!flags && beats_rivals && Vl > 0) {
-                const int V = (int)Vl;
-                const int q = V / ADC_SUBSTEPS, n0 = V - (ADC_SUBSTEPS - 1) * q;  // bsim:151-167
+        // ---- phase 0: expand the day into the slab, 32 keywords at a time
+        unsigned pool_used = 0;  // warp-uniform
+        int t_last = 0;          // last sub-step in which any keyword of the env holds an auction
+        for (int c0 = 0; c0 < K; c0 += 32) {
+            // (a) lane <-> keyword: thresholds, volume, the outcome masks of every 32-auction group
+            const int k = c0 + lane;
+            int B = 0;
+            FlatCost fc;
+            fc.t1 = fc.h1 = fc.a1 = fc.a2 = 0u; fc.L = 0.f; fc.b = 0.f; fc.W = 1; fc.floor_c = 0;
+            fc.n0 = fc.n1 = fc.x3 = 0u; fc.B = 0;
+            if (k < K) {
+                const int64_t u = (int64_t)e * K + k;
+                acc.I[u] = 0;
+                acc.B[u] = 0;
+                acc.S[u] = 0;
+                a.out.cost_cents[u] = 0;
+                a.out.revenue_cents[u] = 0;
+                const UnitPar p = load_unit_par(a, e, k, true);
+                uint4 uw;
+                const long long Vl = unit_volume(a, src, no_tape, e, k, &uw);
+                SlabUnit *su = slab + k;
+                const bool beats_rivals = p.u2.W > p.floor_cents;
+                const bool beyond = Vl > 32 * kSlabGroups || p.win_cents > kMaxFlatBidCents;
+                const int V = beyond || !beats_rivals ? 0 : (int)Vl;
+                su->volume = V;
+                su->win_cents = p.win_cents;
+                su->rev_mean = p.rev_mean;
+                su->rev_sd = p.rev_sd;
+                su->n_clk_run = 0;
                 const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), src.env, k0, k1);
-                const int floor_c = max(p.floor_cents, 0);
-                int nclk = 0, t = 0, t_end = n0;  // current sub-step and the auction index where it ends
-                int it = 0, ct = 0;               // its impressions / clicked slots so far
-                uint4 cw = make_uint4(0, 0, 0, 0);
-                const int G = (V + 31) >> 5;
-                for (int g = 0; g < G; ++g) {
+                for (int g = 0; 32 * g < V; ++g) {
                     const int rem = V - 32 * g;
                     const uint32_t active = rem >= 32 ? 0xFFFFFFFFu : (1u << rem) - 1u;
                     const Masks3 m = group_masks(active, (uint32_t)g, p.u2.t1, p.u2.t2, p.u2.t3, p.u2.full, pa.n0, pa.n1,
                                                  pa.x3, k0, k1);
-                    int pos = 0;  // bits of this group already attributed to a sub-step
-                    const int gend = min(32, rem);
-                    while (pos < gend) {
-                        const int j = 32 * g + pos;
-                        while (j >= t_end && t < ADC_SUBSTEPS - 1) {  // close sub-step t
-                            su->imp[t] = (uint16_t)it;
-                            ++t;
-                            su->cstart[t] = (uint16_t)min(nclk, 0xFFFF);
-                            it = 0; ct = 0;
-                            t_end += q;
-                        }
-                        const int upto = min(gend, t_end - 32 * g);  // bits [pos, upto) belong to sub-step t
-                        const int hi = upto > pos ? upto : gend;     // (q == 0: everything is in sub-step 0)
-                        const uint32_t range = (hi >= 32 ? 0xFFFFFFFFu : (1u << hi) - 1u) & ~((1u << pos) - 1u);
-                        it += __popc(m.win & range);
-                        uint32_t cl = m.click & range;
-                        while (cl) {
-                            const int bpos = __ffs(cl) - 1;
-                            cl &= cl - 1;
-                            if ((nclk & 3) == 0) cw = src.draw(ST_COST, (uint32_t)k, (uint32_t)(nclk >> 2));
-                            const uint32_t w = (nclk & 3) == 0 ? cw.x : (nclk & 3) == 1 ? cw.y : (nclk & 3) == 2 ? cw.z : cw.w;
-                            const int c = max(cost_cents2(w, p.u2.t1, (p.u2.full & 1u) != 0u, p.u2.h1, p.u2.a1, p.u2.a2,
-                                                          p.u2.L, p.u2.b, p.u2.W, s_tab), floor_c);
-                            if (nclk < kSlabClicks) su->click[nclk] = (uint32_t)c | (((m.conv >> bpos) & 1u) << 31);
-                            ++nclk; ++ct;
-                        }
-                        pos = hi;
-                    }
+                    su->win[g] = m.win; su->click[g] = m.click; su->conv[g] = m.conv;
+                    B += __popc(m.click);
                 }
-                su->imp[t] = (uint16_t)it;
-                for (int tt = t + 1; tt <= ADC_SUBSTEPS; ++tt) su->cstart[tt] = (uint16_t)min(nclk, 0xFFFF);
-                if (nclk > kSlabClicks) flags = 1;
-                (void)ct;
+                su->flags = beyond ? 1 : 0;
+                if (Vl >= ADC_SUBSTEPS) t_last = ADC_SUBSTEPS - 1;  // V // 24 > 0: every sub-step gets auctions (bsim:151-167)
+                const PhiloxPre pc = philox_pre(a.step, stream_word(ST_COST, 0u, (uint32_t)k), src.env, k0, k1);
+                fc.t1 = p.u2.t1; fc.h1 = p.u2.h1; fc.a1 = p.u2.a1; fc.a2 = p.u2.a2; fc.L = p.u2.L; fc.b = p.u2.b;
+                fc.W = p.u2.W | ((p.u2.full & 1u) ? (int)0x80000000u : 0);
+                fc.floor_c = max(p.floor_cents, 0); fc.n0 = pc.n0; fc.n1 = pc.n1; fc.x3 = pc.x3; fc.B = B;
             }
-            su->flags = flags;
+            {   // room in the env's price pool (units padded to 4 prices); a unit that does not fit is re-walked
+                const int b4 = (B + 3) & ~3;
+                const int incl = warp_incl_scan(b4, lane);
+                const unsigned off = pool_used + (unsigned)(incl - b4);
+                if (k < K) {
+                    SlabUnit *su = slab + k;
+                    su->cost_off = off;
+                    if (off + (unsigned)b4 > pool_cap) { su->flags = 1; B = 0; fc.B = 0; }
+                }
+                pool_used = min(pool_used + (unsigned)__shfl_sync(FULL, incl, 31), pool_cap);
+            }
+            __syncwarp();
+            s_cost[warp][lane] = fc;
+            // (b) one price per clicked slot, 4 per Philox call, flattened over the 32 keywords
+            const int TB = flat_prefix((B + 3) >> 2, lane, s_start[warp]);
+            int b0 = 0;
+            for (int base = 0; base < TB; base += 32) {
+                while (s_start[warp][b0 + 1] <= base) ++b0;
+                const int i = base + lane;
+                if (i < TB) {
+                    int b = b0;
+                    while (i >= s_start[warp][b + 1]) ++b;
+                    const FlatCost f = s_cost[warp][b];
+                    const int q = i - s_start[warp][b];
+                    const uint4 w = philox_from_pre((uint32_t)q, f.n0, f.n1, f.x3, k0, k1);
+                    const bool t1_full = f.W < 0;
+                    const int W = f.W & 0x7FFFFFFF;
+                    const int c0c = max(cost_cents2(w.x, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c);
+                    const int c1c = max(cost_cents2(w.y, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c);
+                    const int c2c = max(cost_cents2(w.z, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c);
+                    const int c3c = max(cost_cents2(w.w, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c);
+                    // 4 x uint16 = one 8-byte store (offsets are multiples of 4 entries)
+                    uint2 pk;
+                    pk.x = (uint32_t)c0c | ((uint32_t)c1c << 16);
+                    pk.y = (uint32_t)c2c | ((uint32_t)c3c << 16);
+                    *reinterpret_cast<uint2 *>(pool + slab[c0 + b].cost_off + 4 * q) = pk;
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
         const double budget = step_budget(a, e);
         double remaining = budget;  // warp-uniform (bsim:214)
         bool stop = false;
-        for (int t = 0; t < ADC_SUBSTEPS && !stop; ++t) {
+        // Sub-steps after t_last hold no auction of any keyword: their lanes have no impression, no
+        // click slot and leave `remaining` alone, so the walk ends there (a sparse keyword set, V < 24,
+        // has its whole day in sub-step 0).  `remaining <= 0` on entry still needs its one look.
+        t_last = __reduce_max_sync(FULL, t_last);
+        for (int t = 0; t <= t_last && !stop; ++t) {
             for (int c0 = 0; c0 < K && !stop; c0 += 32) {
                 const int k = c0 + lane;
                 const bool act = k < K;
                 const int64_t u = (int64_t)e * K + (act ? k : 0);
-                // ---- phase 1 (parallel): fetch the lane's clicked slots of this sub-step
-                const SlabUnit *su = slab + (act ? k : 0);
+                // ---- phase 1 (parallel): the lane's sub-step from the slab: impressions, clicked slots
+                SlabUnit *su = slab + (act ? k : 0);
                 int I = 0, nclk = 0, cbase = 0, win_c = 0;
                 bool direct = false;  // walk the sub-step again with lane_walk (beyond the slab / the buffer)
                 if (act) {
                     direct = (su->flags & 1u) != 0u;
                     win_c = su->win_cents;
-                    if (!direct) {
-                        I = su->imp[t];
-                        cbase = su->cstart[t];
-                        nclk = su->cstart[t + 1] - cbase;
-                        if (nclk <= kSerCap)
-                            for (int i = 0; i < nclk; ++i) s_slot[warp][i][lane] = su->click[cbase + i];
-                        else
-                            direct = true;
+                    const int V = su->volume;
+                    if (!direct && V > 0) {
+                        const int q = V / ADC_SUBSTEPS, n0 = V - (ADC_SUBSTEPS - 1) * q;  // bsim:151-167
+                        const int j0 = t == 0 ? 0 : n0 + (t - 1) * q, j1 = j0 + (t == 0 ? n0 : q);
+                        cbase = su->n_clk_run;
+                        const uint16_t *const prices = pool + su->cost_off + cbase;
+                        for (int g = j0 >> 5; 32 * g < j1; ++g) {
+                            const int lo = max(j0 - 32 * g, 0), hi = min(j1 - 32 * g, 32);
+                            const uint32_t range = (hi >= 32 ? 0xFFFFFFFFu : (1u << hi) - 1u) & ~((1u << lo) - 1u);
+                            I += __popc(su->win[g] & range);
+                            uint32_t cl = su->click[g] & range;
+                            const uint32_t cv = su->conv[g];
+                            while (cl) {
+                                const int bpos = __ffs(cl) - 1;
+                                cl &= cl - 1;
+                                if (nclk < kSerCap)
+                                    s_slot[warp][nclk][lane] = (uint32_t)prices[nclk] | (((cv >> bpos) & 1u) << 31);
+                                ++nclk;
+                            }
+                        }
+                        su->n_clk_run = (uint16_t)(cbase + nclk);
+                        if (nclk > kSerCap) direct = true;
                     }
                 }
                 if (direct) nclk = kSerCap + 1;  // takes the re-walk turn below
@@ -1909,7 +1987,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                             lane_sum = __dadd_rn(lane_sum, cents_to_dollars(c));
                             cents += (unsigned)c;
                         }
-                        const unsigned total = __reduce_add_sync(FULL, cents);  // <= 32 * 16 * 65535 (bids capped above)
+                        const unsigned total = __reduce_add_sync(FULL, cents);  // <= 32 lanes x kSerCap x 65535 < 2^32 (bids capped above)
                         const double spend = __ddiv_rn((double)total, 100.0);
                         if (remaining > (a.budget_alias ? spend + spend : spend) + 0.01) {
                             B = nclk;
@@ -1946,20 +2024,11 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                     } else {  // beyond the slab or the buffer: lane l walks its sub-step again, with the budget
                         next = remaining;
                         if (lane == l) {
-                            UnitPar p = load_unit_par(a, e, k, true);
-                            uint4 uw;
-                            p.volume = unit_volume(a, src, no_tape, e, k, &uw);
-                            const long long q = p.volume / ADC_SUBSTEPS, n0 = p.volume - (ADC_SUBSTEPS - 1) * q;
-                            const long long n = t == 0 ? n0 : q, j0 = t == 0 ? 0 : n0 + (long long)(t - 1) * q;
-                            // clicked slots before this sub-step: from the slab, or counted again when the
-                            // slab does not describe the unit
-                            const int n_clk0 = (su->flags & 1u) != 0u ? clicks_before(src, k, p.u2, p.volume, j0) : cbase;
-                            double b = remaining, unused = 0.0;
-                            UnitCur cur = {j0, 0, 0, acc.S[u], 0, n_clk0};
-                            const LaneOut o = lane_walk<PhiloxSrc, false, true>(src, no_tape, u, k, t, n, p, cur, b, unused);
-                            I = o.I; B = o.B; S = o.S; cost_c = o.cost_cents; rev_c = o.rev_cents;
+                            const DirectOut d = serial_direct_lane(a, src, e, k, t, (su->flags & 1u) != 0u, cbase,
+                                                                   acc.S[u], remaining);
+                            I = d.I; B = d.B; S = d.S; cost_c = d.cost_c; rev_c = d.rev_c;
                             rev_done = true;
-                            next = __dsub_rn(a.budget_alias ? b : remaining, o.lane_cost_sum);
+                            next = d.next;
                         }
                         next = __shfl_sync(FULL, next, l);
                     }
@@ -2137,7 +2206,7 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     }
     if (err != cudaSuccess) return err;
     // exact serial walk of the queued envs (reads the count on the device; exits at once if 0)
-    const int64_t slab_bytes = (int64_t)a.kw.K * (int64_t)sizeof(SlabUnit);
+    const int64_t slab_bytes = (int64_t)a.kw.K * kSlabBytesPerKeyword;
     const int64_t n_slabs = a.scratch.serial_ws != nullptr ? a.scratch.serial_ws_bytes / slab_bytes : 0;
     if (tape == nullptr && !explicit_kw && a.n_lanes != 1 && a.detail.costs == nullptr && n_slabs > 0) {
         // one warp per queued env, each with its own slab of the workspace
@@ -2157,7 +2226,7 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     return cudaGetLastError();
 }
 
-int64_t serial_slab_bytes(int32_t K) { return (int64_t)K * (int64_t)sizeof(SlabUnit); }
+int64_t serial_slab_bytes(int32_t K) { return (int64_t)K * kSlabBytesPerKeyword; }
 
 cudaError_t launch_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day,
                               cudaStream_t s, int64_t *launches)

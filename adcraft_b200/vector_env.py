@@ -184,8 +184,9 @@ class VectorBiddingSimulation:
             work_counter=z(2, dtype=i32))
         if self.episode_profit:
             self._out["episode_profit_cents"] = z(E, K, dtype=i64)
-        slab = int(self._lib.adc_serial_slab_bytes(K))
-        n_slabs = max(1, min(E, 148 * 24, self.serial_ws_cap // max(slab, 1)))
+        # one slab per resident warp of the exact serial walk (28 warps per SM), within the cap
+        slab = max(int(self._lib.adc_serial_slab_bytes(K)), 1)
+        n_slabs = max(1, min(E, 148 * 28, self.serial_ws_cap // slab))
         self._scratch["serial_ws"] = torch.empty(n_slabs * slab, dtype=torch.uint8, device=dev)
         self._detail = None
         if self.detail_cap > 0:

@@ -144,7 +144,7 @@ typedef struct adc_scratch {
     int32_t *acc_clicks;
     int32_t *acc_conversions;
     /* Optional DEVICE workspace of the warp-cooperative exact serial walk (free-running implicit
-     * keywords): every resident warp expands one queued env's day into a slab of K x 640 bytes
+     * keywords): every resident warp expands one queued env's day into a slab of K x 344 bytes
      * (adc_serial_slab_bytes(K)); 16-byte aligned.  The launcher runs as many warps as slabs fit
      * (about 3500 resident warps at most); NULL / too small for one slab: the walk falls back to one
      * thread per env (correct, much slower). */
