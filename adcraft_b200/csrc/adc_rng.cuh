@@ -332,9 +332,11 @@ __device__ __forceinline__ int cost_cents2(uint32_t w, uint32_t t1, bool t1_full
     const uint32_t s = t1_full ? w : __umulhi(w, t1);
     const bool left = s < h1;
     const uint32_t off = left ? s : s - h1;
-    unsigned long long t = (unsigned long long)(left ? a1 : a2) + 2ull * off + 1ull;
-    if (t > 0xFFFFFFFFull) t = 0xFFFFFFFFull;
-    const float e = neglog_norm((uint32_t)t | 1u, tab);
+    // base + 2 off + 1 saturated at 2^32 - 1 (off < 2^31): a wrapped 32-bit sum is below its base
+    const uint32_t base = left ? a1 : a2;
+    uint32_t t = base + 2u * off + 1u;
+    if (t < base) t = 0xFFFFFFFFu;
+    const float e = neglog_norm(t | 1u, tab);
     const float x = __fmaf_rn(left ? -b : b, e, L);
     int c = __float2int_rn(__fmul_rn(fabsf(x), 100.0f));
     c = min(c, W - 1);
@@ -347,6 +349,15 @@ __device__ __forceinline__ int cost_cents2(uint32_t w, uint32_t t1, bool t1_full
 struct Masks3 {
     uint32_t win, click, conv;
 };
+
+// all ones when bit `pos` (a compile-time position) of x is set: one BFE.S32 of a one-bit field
+template <int dummy = 0>
+__device__ __forceinline__ uint32_t sign_bit_mask(uint32_t x, int pos)
+{
+    int m;
+    asm("bfe.s32 %0, %1, %2, 1;" : "=r"(m) : "r"((int)x), "r"(pos));
+    return (uint32_t)m;
+}
 
 __device__ __forceinline__ Masks3 group_masks(uint32_t active, uint32_t g, uint32_t t1, uint32_t t2, uint32_t t3,
                                               uint32_t full, uint32_t n0, uint32_t n1, uint32_t x3, uint32_t k0,
@@ -362,15 +373,16 @@ __device__ __forceinline__ Masks3 group_masks(uint32_t active, uint32_t g, uint3
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t r = ws[i];
-            // m_i = all ones when the threshold's bit at this level is 1:
+            // m_i = all ones when the threshold's bit at this level is 1 (a sign-extending one-bit field
+            // extract at a fixed position: the thresholds move up four levels per call):
             //   bit 1: auctions with r = 0 drop below (L |= E & ~r), those with r = 1 stay tied (E &= r)
             //   bit 0: auctions with r = 1 rise above (E &= ~r)
-            const uint32_t m1 = (uint32_t)((int)t1 >> 31), m2 = (uint32_t)((int)t2 >> 31), m3 = (uint32_t)((int)t3 >> 31);
+            const uint32_t m1 = sign_bit_mask(t1, 31 - i), m2 = sign_bit_mask(t2, 31 - i), m3 = sign_bit_mask(t3, 31 - i);
             l1 |= e1 & ~r & m1; e1 &= ~(r ^ m1);
             l2 |= e2 & ~r & m2; e2 &= ~(r ^ m2);
             l3 |= e3 & ~r & m3; e3 &= ~(r ^ m3);
-            t1 <<= 1; t2 <<= 1; t3 <<= 1;
         }
+        t1 <<= 4; t2 <<= 4; t3 <<= 4;
     }
     Masks3 m;
     m.win = l1; m.click = l2; m.conv = l3;

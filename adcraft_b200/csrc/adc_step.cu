@@ -636,16 +636,38 @@ __device__ __forceinline__ void episode_accumulate(const adc_step_args &a, int e
     }
 }
 
-// Flattened work of a batch: unit `lane` has `n` items (Philox calls); returns through `start`
-// (shared, [33]) the exclusive prefix, and the batch total.
-__device__ __forceinline__ int flat_prefix(int n, int lane, int *start)
+// Flattened work of a batch: unit `lane` has `n` items (Philox calls); item i of the batch belongs to
+// the unit whose prefix range holds i.  flat_map_begin publishes, per warp, the exclusive prefix
+// (`start`, shared [32]) and the list of units that have items (`nzl`, shared [32]); flat_map_unit
+// then finds the unit of item base + lane without a search: every owner lane marks where its unit
+// ends inside the trip, one OR-REDUX + popc ranks the lane's unit among those with items.
+struct FlatMap {
+    int incl;   // inclusive prefix of this lane's unit
+    bool nz;    // this lane's unit has items
+    int total;  // items of the whole batch
+};
+
+__device__ __forceinline__ FlatMap flat_map_begin(int n, int lane, int *start, unsigned char *nzl)
 {
-    const int incl = warp_incl_scan(n, lane);
+    FlatMap m;
+    m.incl = warp_incl_scan(n, lane);
+    m.nz = n > 0;
+    const unsigned nzmask = __ballot_sync(0xFFFFFFFFu, m.nz);
+    __syncwarp();  // earlier readers of the two tables are done
+    if (m.nz) nzl[__popc(nzmask & ((1u << lane) - 1u))] = (unsigned char)lane;
+    start[lane] = m.incl - n;
     __syncwarp();
-    start[lane + 1] = incl;
-    if (lane == 0) start[0] = 0;
-    __syncwarp();
-    return __shfl_sync(0xFFFFFFFFu, incl, 31);
+    m.total = __shfl_sync(0xFFFFFFFFu, m.incl, 31);
+    return m;
+}
+
+// unit of item base + lane (valid when base + lane < total); all lanes must call
+__device__ __forceinline__ int flat_map_unit(const FlatMap &m, int base, int lane, const unsigned char *nzl)
+{
+    const int rel = m.incl - base;
+    const unsigned marks = __reduce_or_sync(0xFFFFFFFFu, (m.nz && rel > 0 && rel < 32) ? (1u << rel) : 0u);
+    const int before = __popc(__ballot_sync(0xFFFFFFFFu, m.nz && rel <= 0));
+    return nzl[min(before + __popc(marks & (0xFFFFFFFFu >> (31 - lane))), 31)];
 }
 
 template <bool kFloor>
@@ -654,7 +676,8 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
 {
     __shared__ FlatCost s_cost[kFlatWarps][32];
     __shared__ FlatRev s_rev[kFlatWarps][32];
-    __shared__ int s_start[kFlatWarps][33];
+    __shared__ int s_start[kFlatWarps][32];
+    __shared__ unsigned char s_nzl[kFlatWarps][32];
     __shared__ unsigned s_sum[kFlatWarps][32][2];  // 24-bit split: native 32-bit shared-memory atomics
     __shared__ float2 s_tab[128];                  // Exp(1) sampler table, staged from global
     if (threadIdx.x < 128) s_tab[threadIdx.x] = kNeglogTab[threadIdx.x];
@@ -679,6 +702,7 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
     FlatCost *costs = s_cost[warp];
     FlatRev *revs = s_rev[warp];
     int *start = s_start[warp];
+    unsigned char *nzl = s_nzl[warp];
 
     auto pull = [&]() -> uint32_t { return lane == 0 ? atomicAdd(work, 1u) : 0u; };
     uint32_t pulled = dynamic ? pull() : 0u;
@@ -759,14 +783,12 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
         }
         long long cost = 0;
         {
-            const int TB = flat_prefix((B + 3) >> 2, lane, start);
-            int b0 = 0;
+            const FlatMap fm = flat_map_begin((B + 3) >> 2, lane, start, nzl);
+            const int TB = fm.total;
             for (int base = 0; base < TB; base += 32) {
-                while (start[b0 + 1] <= base) ++b0;  // warp-uniform: the unit that holds call `base`
+                const int b = flat_map_unit(fm, base, lane, nzl);
                 const int i = base + lane;
                 if (i < TB) {
-                    int b = b0;
-                    while (i >= start[b + 1]) ++b;
                     const FlatCost fc = costs[b];
                     const int q = i - start[b];
                     const uint4 w = philox_from_pre((uint32_t)q, fc.n0, fc.n1, fc.x3, k0, k1);
@@ -800,14 +822,12 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
             __syncwarp();
             s_sum[warp][lane][0] = 0u; s_sum[warp][lane][1] = 0u;
         }
-        const int TR = flat_prefix((S + 3) >> 2, lane, start);
-        int r0 = 0;
+        const FlatMap rm = flat_map_begin((S + 3) >> 2, lane, start, nzl);
+        const int TR = rm.total;
         for (int base = 0; base < TR; base += 32) {
-            while (start[r0 + 1] <= base) ++r0;
+            const int b = flat_map_unit(rm, base, lane, nzl);
             const int i = base + lane;
             if (i < TR) {
-                int b = r0;
-                while (i >= start[b + 1]) ++b;
                 const FlatRev fr = revs[b];
                 const int blk = i - start[b];
                 const uint4 w = philox_from_pre((uint32_t)blk, fr.n0, fr.n1, fr.x3, k0, k1);
@@ -1804,7 +1824,8 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
 {
     __shared__ uint32_t s_slot[kSerWarps][kSerCap][32];
     __shared__ FlatCost s_cost[kSerWarps][32];
-    __shared__ int s_start[kSerWarps][33];
+    __shared__ int s_start[kSerWarps][32];
+    __shared__ unsigned char s_nzl[kSerWarps][32];
     __shared__ float2 s_tab[128];  // Exp(1) sampler table, staged from global
     if (threadIdx.x < 128) s_tab[threadIdx.x] = kNeglogTab[threadIdx.x];
     __syncthreads();
@@ -1887,14 +1908,12 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
             __syncwarp();
             s_cost[warp][lane] = fc;
             // (b) one price per clicked slot, 4 per Philox call, flattened over the 32 keywords
-            const int TB = flat_prefix((B + 3) >> 2, lane, s_start[warp]);
-            int b0 = 0;
+            const FlatMap fm = flat_map_begin((B + 3) >> 2, lane, s_start[warp], s_nzl[warp]);
+            const int TB = fm.total;
             for (int base = 0; base < TB; base += 32) {
-                while (s_start[warp][b0 + 1] <= base) ++b0;
+                const int b = flat_map_unit(fm, base, lane, s_nzl[warp]);
                 const int i = base + lane;
                 if (i < TB) {
-                    int b = b0;
-                    while (i >= s_start[warp][b + 1]) ++b;
                     const FlatCost f = s_cost[warp][b];
                     const int q = i - s_start[warp][b];
                     const uint4 w = philox_from_pre((uint32_t)q, f.n0, f.n1, f.x3, k0, k1);
