@@ -81,6 +81,11 @@ class StepArgs(C.Structure):
     ]
 
 
+class HostChunk(C.Structure):
+    _fields_ = [("args", StepArgs), ("bids_host", C.c_void_p), ("rows_dev", C.c_void_p),
+                ("rows_host", C.c_void_p), ("stream", C.c_void_p)]
+
+
 class IdealArgs(C.Structure):
     _fields_ = [
         ("E", C.c_int32), ("env_base", C.c_uint32), ("step", C.c_uint32), ("device", C.c_int32),
@@ -129,6 +134,11 @@ def load() -> C.CDLL:
     lib.adc_ideal_profit.restype = C.c_int
     lib.adc_ideal_profit.argtypes = [C.POINTER(IdealArgs), C.c_void_p]
     lib.adc_sizeof_ideal_args.restype = C.c_int
+    lib.adc_host_row_bytes.restype = C.c_int64
+    lib.adc_host_row_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.adc_step_host.restype = C.c_int
+    lib.adc_step_host.argtypes = [C.POINTER(HostChunk), C.c_int32]
+    lib.adc_sizeof_host_chunk.restype = C.c_int
     lib.adc_serial_slab_bytes.restype = C.c_int64
     lib.adc_serial_slab_bytes.argtypes = [C.c_int32]
     lib.adc_launch_count.restype = C.c_int64
@@ -140,6 +150,8 @@ def load() -> C.CDLL:
             "adcraft_b200: struct layout mismatch between _capi.py and the compiled library "
             f"({lib.adc_sizeof_step_args()} vs {C.sizeof(StepArgs)}, "
             f"{lib.adc_sizeof_tape()} vs {C.sizeof(Tape)}); rebuild")
+    if lib.adc_sizeof_host_chunk() != C.sizeof(HostChunk):
+        raise AdcError("adcraft_b200: adc_host_chunk layout mismatch; rebuild")
     if lib.adc_sizeof_ideal_args() != C.sizeof(IdealArgs):
         raise AdcError("adcraft_b200: adc_ideal_args layout mismatch; rebuild")
     _lib = lib
@@ -156,4 +168,5 @@ EXPORTED_SYMBOLS = (
     "adc_last_error", "adc_abi_version", "adc_device_count", "adc_sizeof_step_args",
     "adc_sizeof_tape", "adc_step_philox", "adc_step_replay", "adc_reset_envs", "adc_launch_count",
     "adc_ideal_profit", "adc_sizeof_ideal_args", "adc_serial_slab_bytes",
+    "adc_host_row_bytes", "adc_step_host", "adc_sizeof_host_chunk",
 )

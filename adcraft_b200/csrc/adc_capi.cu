@@ -66,8 +66,8 @@ int validate(const adc_step_args *a, const adc_tape *tape)
                     (a->scratch.acc_clicks != nullptr) == (a->scratch.acc_conversions != nullptr),
                 "scratch.acc_impressions / acc_clicks / acc_conversions: give all three or none");
     ADC_REQUIRE(a->scratch.serial_ws == nullptr ||
-                    ((reinterpret_cast<uintptr_t>(a->scratch.serial_ws) & 15u) == 0 && a->scratch.serial_ws_bytes >= 0),
-                "scratch.serial_ws must be 16-byte aligned");
+                    ((reinterpret_cast<uintptr_t>(a->scratch.serial_ws) & 7u) == 0 && a->scratch.serial_ws_bytes >= 0),
+                "scratch.serial_ws must be 8-byte aligned");
     ADC_REQUIRE(a->drift.mask == nullptr || a->kw.env_stride == a->kw.K,
                 "drift needs per-env keyword parameters (kw.env_stride == K)");
     ADC_REQUIRE(a->drift.mask == nullptr || (a->drift.num_updates >= 0 && a->drift.num_updates <= a->kw.K),
@@ -167,6 +167,50 @@ int adc_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *
     const cudaError_t e =
         adc::launch_reset_envs(E, mask, cum_profit, day, static_cast<cudaStream_t>(stream), &g_launches);
     if (e != cudaSuccess) return fail(ADC_ERR_CUDA, "adcraft_b200: launch failed: %s", cudaGetErrorString(e));
+    return ADC_OK;
+}
+
+int64_t adc_host_row_bytes(int32_t K, int32_t float_dtype) { return K > 0 ? adc::host_row_bytes(K, float_dtype) : 0; }
+
+int adc_sizeof_host_chunk(void) { return (int)sizeof(adc_host_chunk); }
+
+int adc_step_host(const adc_host_chunk *chunks, int32_t n_chunks)
+{
+    if (chunks == nullptr || n_chunks <= 0)
+        return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: adc_step_host needs at least one chunk");
+    for (int i = 0; i < n_chunks; ++i) {
+        const adc_host_chunk &c = chunks[i];
+        const int rc = validate(&c.args, nullptr);
+        if (rc) return rc;
+        ADC_REQUIRE(c.bids_host && c.rows_dev && c.rows_host, "adc_step_host: chunk buffer is NULL");
+        ADC_REQUIRE(c.args.kw.kind == ADC_IMPLICIT || c.args.kw.kind == ADC_EXPLICIT || c.args.kw.kind == ADC_IMPLICIT_MULTI,
+                    "kw.kind");
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    if (chunks[0].args.device >= 0) {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != chunks[0].args.device)
+            return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: the buffers live on device %d but the "
+                        "calling thread's current device is %d", chunks[0].args.device, cur);
+    }
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < n_chunks && e == cudaSuccess; ++i) {
+        const adc_host_chunk &c = chunks[i];
+        cudaStream_t st = static_cast<cudaStream_t>(c.stream);
+        const size_t bid_bytes = (size_t)c.args.E * c.args.kw.K * (c.args.bids_dtype == ADC_F64 ? 8 : 4);
+        const size_t row_bytes = (size_t)c.args.E * (size_t)adc::host_row_bytes(c.args.kw.K, c.args.out.float_dtype);
+        e = cudaMemcpyAsync(const_cast<void *>(c.args.bids), c.bids_host, bid_bytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = adc::launch_step(c.args, nullptr, st, &g_launches);
+        if (e == cudaSuccess) e = adc::launch_pack_rows(c.args, c.rows_dev, st, &g_launches);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c.rows_host, c.rows_dev, row_bytes, cudaMemcpyDeviceToHost, st);
+    }
+    for (int i = 0; i < n_chunks; ++i) {  // the call returns host data: wait for every chunk's stream
+        const cudaError_t es = cudaStreamSynchronize(static_cast<cudaStream_t>(chunks[i].stream));
+        if (e == cudaSuccess) e = es;
+    }
+    if (e != cudaSuccess) return fail(ADC_ERR_CUDA, "adcraft_b200: adc_step_host failed: %s", cudaGetErrorString(e));
     return ADC_OK;
 }
 

@@ -2113,6 +2113,67 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
 }
 
 
+// ------------------------------------------------------------------------------------------
+// compact host rows (adc_step_host): one warp per env packs the step's observation into one row
+// ------------------------------------------------------------------------------------------
+struct RowLayout {
+    int64_t counts, money, tail, bytes;  // byte offsets inside a row, row size
+};
+
+__host__ __device__ inline RowLayout row_layout(int K, int float_dtype)
+{
+    RowLayout r;
+    r.counts = 0;
+    r.money = ((int64_t)6 * K + 7) & ~(int64_t)7;
+    const int64_t fb = float_dtype == ADC_F64 ? 8 : 4;
+    r.tail = (r.money + 2 * fb * K + 7) & ~(int64_t)7;
+    r.bytes = r.tail + 24;
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+adc_pack_rows_kernel(const __grid_constant__ adc_step_args a, unsigned char *rows)
+{
+    const int K = a.kw.K;
+    const RowLayout L = row_layout(K, a.out.float_dtype);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = warp; e < a.E; e += n_warps) {
+        unsigned char *row = rows + e * L.bytes;
+        uint16_t *cnt = reinterpret_cast<uint16_t *>(row + L.counts);
+        bool over = false;
+        for (int k = lane; k < K; k += 32) {
+            const int64_t u = e * K + k;
+            const int i = a.out.impressions[u], b = a.out.clicks[u], c = a.out.conversions[u];
+            over = over || i > 65535 || b > 65535 || c > 65535;
+            cnt[k] = (uint16_t)min(i, 65535);
+            cnt[K + k] = (uint16_t)min(b, 65535);
+            cnt[2 * K + k] = (uint16_t)min(c, 65535);
+            if (a.out.float_dtype == ADC_F64) {
+                double *m = reinterpret_cast<double *>(row + L.money);
+                m[k] = reinterpret_cast<const double *>(a.out.cost)[u];
+                m[K + k] = reinterpret_cast<const double *>(a.out.revenue)[u];
+            } else {
+                float *m = reinterpret_cast<float *>(row + L.money);
+                m[k] = reinterpret_cast<const float *>(a.out.cost)[u];
+                m[K + k] = reinterpret_cast<const float *>(a.out.revenue)[u];
+            }
+        }
+        over = __any_sync(0xFFFFFFFFu, over);
+        if (lane == 0) {
+            double *t = reinterpret_cast<double *>(row + L.tail);
+            t[0] = a.out.reward[e];
+            t[1] = a.out.obs_cum_profit[e];
+            *reinterpret_cast<int32_t *>(row + L.tail + 16) = a.out.obs_days[e];
+            row[L.tail + 20] = a.out.terminated[e];
+            row[L.tail + 21] = a.out.truncated[e];
+            row[L.tail + 22] = over ? 1 : 0;
+            row[L.tail + 23] = 0;
+        }
+    }
+}
+
 __global__ void adc_reset_envs_kernel(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2246,6 +2307,19 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
 }
 
 int64_t serial_slab_bytes(int32_t K) { return (int64_t)K * kSlabBytesPerKeyword; }
+
+int64_t host_row_bytes(int32_t K, int32_t float_dtype) { return row_layout(K, float_dtype).bytes; }
+
+cudaError_t launch_pack_rows(const adc_step_args &a, void *rows_dev, cudaStream_t s, int64_t *launches)
+{
+    const int64_t want = ((int64_t)a.E * 32 + 255) / 256;
+    int64_t grid = (int64_t)num_sms() * 8;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    adc_pack_rows_kernel<<<(unsigned)grid, 256, 0, s>>>(a, reinterpret_cast<unsigned char *>(rows_dev));
+    ++*launches;
+    return cudaGetLastError();
+}
 
 cudaError_t launch_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day,
                               cudaStream_t s, int64_t *launches)

@@ -12,6 +12,8 @@ cudaError_t launch_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit
                               cudaStream_t s, int64_t *launches);
 
 int64_t serial_slab_bytes(int32_t K);
+int64_t host_row_bytes(int32_t K, int32_t float_dtype);
+cudaError_t launch_pack_rows(const adc_step_args &a, void *rows_dev, cudaStream_t s, int64_t *launches);
 cudaError_t launch_ideal_profit(const adc_ideal_args &a, cudaStream_t s, int64_t *launches);
 
 }  // namespace adc

@@ -210,6 +210,8 @@ class VectorBiddingSimulation:
         """Run a library entry point with the env's device current: the ABI takes only a stream
         handle and launches on the calling thread's current device (adc_step_args.device makes a
         mismatch an error instead of an illegal address)."""
+        if getattr(fn, "__name__", "") != "adc_step_host":
+            self._hp_dirty = True  # the pipelined host step must wait for this stream's work once
         if torch.cuda.current_device() == self.device.index:
             _capi.check(fn(*args))
         else:
@@ -490,6 +492,7 @@ class VectorBiddingSimulation:
         self._call(self._lib.adc_step_philox, C.byref(a), C.c_void_p(stream))
         self._step_count += 1
         self._calls += 1
+        self._hp_dirty = True
         return self._result()
 
     def step_replay(self, action: Dict[str, ArrayLike], tape: DeviceTape, *, force_serial: bool = False):
@@ -512,6 +515,123 @@ class VectorBiddingSimulation:
         return (*self._result_cache, {"step": self._step_count})
 
     # ------------------------------------------------------------------ host round trip (e2e)
+    # ------------------------------------------------------------------ pipelined host round trip
+    def _host_pipeline(self, n_chunks: int):
+        """Everything adc_step_host needs, built once per (argument block, chunk count): the chunk
+        argument blocks (every pointer offset to the chunk's first env, own scratch counters), one
+        stream per chunk, the device and pinned-host row blocks."""
+        E, K, dev = self.num_envs, self.num_keywords, self.device
+        A = max(self.env_group, 1)
+        n_chunks = max(1, min(int(n_chunks), E // A))
+        key = (self._args_sig, n_chunks)
+        hp = getattr(self, "_hp", None)
+        if hp is not None and hp["key"] == key:
+            return hp
+        fdt = _capi.F64 if self.obs_dtype == torch.float64 else _capi.F32
+        row_bytes = int(self._lib.adc_host_row_bytes(K, fdt))
+        if hp is None or hp["rows_host"].shape != (E, row_bytes):
+            rows_dev = torch.zeros(E, row_bytes, dtype=torch.uint8, device=dev)
+            rows_host = torch.zeros(E, row_bytes, dtype=torch.uint8).pin_memory()
+            bids_dev = torch.zeros(E, K, dtype=torch.float32, device=dev)
+        else:
+            rows_dev, rows_host, bids_dev = hp["rows_dev"], hp["rows_host"], hp["bids_dev"]
+        counters = torch.zeros(n_chunks, 2, 2, dtype=torch.int32, device=dev)  # [chunk][serial|work][parity]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(n_chunks)]
+        chunks = (_capi.HostChunk * n_chunks)()
+        # split the envs into n_chunks runs of whole bidder groups
+        groups = E // A
+        bounds = [(groups * i // n_chunks) * A for i in range(n_chunks + 1)]
+        base = self._args
+        ws, ws_bytes = base.scratch.serial_ws, base.scratch.serial_ws_bytes
+        slab = max(int(self._lib.adc_serial_slab_bytes(K)), 1)
+        per_chunk_ws = (ws_bytes // n_chunks) // slab * slab if ws else 0
+
+        def off(ptr, nbytes):
+            return None if not ptr else ptr + nbytes
+
+        for i in range(n_chunks):
+            e0, e1 = bounds[i], bounds[i + 1]
+            c = chunks[i]
+            C.memmove(C.byref(c.args), C.byref(base), C.sizeof(_capi.StepArgs))
+            a = c.args
+            a.E, a.env_base = e1 - e0, self.env_base + (e0 // A if A > 1 else e0)
+            if self._kw_stride:
+                for n in kwmod.PARAM_NAMES + ("max_bidders", "participation"):
+                    setattr(a.kw, n, off(getattr(base.kw, n), e0 * K * 8))
+            a.env.budget, a.env.cum_profit = off(base.env.budget, e0 * 8), off(base.env.cum_profit, e0 * 8)
+            a.env.day = off(base.env.day, e0 * 4)
+            a.bids, a.bids_dtype = bids_dev.data_ptr() + e0 * K * 4, _capi.F32
+            a.budget_in, a.floor_cents = None, None
+            o, bo = a.out, base.out
+            fb = 8 if self.obs_dtype == torch.float64 else 4
+            for n, sz in (("impressions", 4), ("clicks", 4), ("conversions", 4), ("cost", fb), ("revenue", fb),
+                          ("cost_cents", 8), ("revenue_cents", 8), ("episode_profit_cents", 8)):
+                setattr(o, n, off(getattr(bo, n), e0 * K * sz))
+            for n, sz in (("reward", 8), ("obs_cum_profit", 8), ("obs_days", 4), ("terminated", 1), ("truncated", 1),
+                          ("remaining_budget", 8)):
+                setattr(o, n, off(getattr(bo, n), e0 * sz))
+            sc, bs = a.scratch, base.scratch
+            for n, sz in (("serial_list", 4), ("env_profit", 8), ("env_cost", 8), ("env_done", 4)):
+                setattr(sc, n, off(getattr(bs, n), e0 * sz))
+            sc.unit_cost_f64 = off(bs.unit_cost_f64, e0 * K * 8)
+            sc.serial_count = counters[i, 0].data_ptr()
+            sc.work_counter = counters[i, 1].data_ptr() if self.dynamic_work else None
+            sc.acc_impressions = sc.acc_clicks = sc.acc_conversions = None
+            sc.serial_ws = off(ws, i * per_chunk_ws) if per_chunk_ws else None
+            sc.serial_ws_bytes = per_chunk_ws
+            a.detail.costs = a.detail.rev_per_cost = a.detail.n_recorded = a.detail.volume_seen = None
+            a.detail.lane_clicks = a.detail.lane_convs = None
+            c.rows_dev = rows_dev.data_ptr() + e0 * row_bytes
+            c.rows_host = rows_host.data_ptr() + e0 * row_bytes
+            c.stream = streams[i].cuda_stream
+        L6 = (6 * K + 7) // 8 * 8
+        fbytes = 8 if self.obs_dtype == torch.float64 else 4
+        tail = (L6 + 2 * fbytes * K + 7) // 8 * 8
+        u16, fdt_t = torch.uint16, self.obs_dtype
+        r = rows_host
+        views = dict(
+            impressions=r[:, 0:2 * K].view(u16), buyside_clicks=r[:, 2 * K:4 * K].view(u16),
+            sellside_conversions=r[:, 4 * K:6 * K].view(u16),
+            cost=r[:, L6:L6 + fbytes * K].view(fdt_t), revenue=r[:, L6 + fbytes * K:L6 + 2 * fbytes * K].view(fdt_t),
+            reward=r[:, tail:tail + 8].view(torch.float64).view(-1),
+            cumulative_profit=r[:, tail + 8:tail + 16].view(torch.float64),
+            days_passed=r[:, tail + 16:tail + 20].view(torch.int32),
+            terminated=r[:, tail + 20], truncated=r[:, tail + 21], count_overflow=r[:, tail + 22])
+        self._hp = dict(key=key, chunks=chunks, n=n_chunks, bounds=bounds, streams=streams, counters=counters,
+                        rows_dev=rows_dev, rows_host=rows_host, bids_dev=bids_dev, views=views, row_bytes=row_bytes)
+        return self._hp
+
+    def step_host_pipelined(self, bids_host: torch.Tensor, n_chunks: int = 4):
+        """``step`` for a CPU-side caller: pinned float32 HOST bids in, HOST observations out, through
+        ``adc_step_host``: the envs are cut into ``n_chunks`` runs and every run's host->device copy,
+        kernels, row packing and device->host copy go to its own stream, so the copy engines move
+        one run while the SMs work on the next (one cudaMemcpyAsync per run and direction).
+        Observations come back as compact rows (uint16 counts, float money; adc_host_chunk in the
+        header): the returned dict holds strided views into the pinned row block, valid until the
+        next call.  ``count_overflow[e]`` flags an env with a count above 65535 (read its exact
+        int32 counts from the device arrays then).  The device-side observation tensors of ``step``
+        are updated as well."""
+        assert self._have_keywords, "reset required, need to generate keywords to bid on"
+        E, K = self.num_envs, self.num_keywords
+        assert (isinstance(bids_host, torch.Tensor) and bids_host.is_pinned() and bids_host.dtype == torch.float32
+                and bids_host.is_contiguous() and tuple(bids_host.shape) == (E, K)), \
+            "step_host_pipelined takes a pinned, contiguous float32 [E, K] tensor"
+        self._fill_args(bids_host, None, False)  # per-step fields + (re)built pointer block
+        hp = self._host_pipeline(n_chunks)
+        if getattr(self, "_hp_dirty", True):
+            torch.cuda.synchronize(self.device)  # work queued on other streams touches the same state
+            self._hp_dirty = False
+        base, chunks = self._args, hp["chunks"]
+        for i in range(hp["n"]):
+            a = chunks[i].args
+            a.step, a.parity = base.step, base.parity
+            a.budget_alias, a.force_serial, a.f32_ties = base.budget_alias, 0, base.f32_ties
+            chunks[i].bids_host = bids_host.data_ptr() + hp["bounds"][i] * K * 4
+        self._call(self._lib.adc_step_host, chunks, hp["n"])
+        self._step_count += 1
+        self._calls += 1
+        return hp["views"]
+
     def step_host(self, bids_host: torch.Tensor, budget_host: Optional[torch.Tensor] = None,
                   zero_copy: bool = True):
         """``step`` with HOST buffers: pinned host bids in, pinned host observations out.

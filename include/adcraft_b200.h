@@ -145,7 +145,7 @@ typedef struct adc_scratch {
     int32_t *acc_conversions;
     /* Optional DEVICE workspace of the warp-cooperative exact serial walk (free-running implicit
      * keywords): every resident warp expands one queued env's day into a slab of K x 344 bytes
-     * (adc_serial_slab_bytes(K)); 16-byte aligned.  The launcher runs as many warps as slabs fit
+     * (adc_serial_slab_bytes(K)); 8-byte aligned.  The launcher runs as many warps as slabs fit
      * (about 3500 resident warps at most); NULL / too small for one slab: the walk falls back to one
      * thread per env (correct, much slower). */
     void *serial_ws;
@@ -284,6 +284,35 @@ int adc_step_replay(const adc_step_args *args, const adc_tape *tape, void *strea
 
 /* Reset per-env episode state of the envs with mask[e] != 0 (mask NULL: all). */
 int adc_reset_envs(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day, void *stream);
+
+/* ---- host round trip (the call a CPU-side RL loop makes) --------------------------------------
+ * adc_step_host runs one free-running step whose bids come from HOST memory and whose observations
+ * land in HOST memory, as a pipeline over chunks of envs: for every chunk, on the chunk's stream,
+ *   cudaMemcpyAsync(bids: host -> device)  ->  the step kernels  ->  adc_pack_rows  ->
+ *   cudaMemcpyAsync(rows: device -> host)
+ * so the copy engines move chunk i while the SMs work on chunk i + 1 (PCIe is full duplex: the two
+ * directions overlap too).  One cudaMemcpyAsync per chunk and direction.  Returns after every
+ * chunk's rows have landed (it synchronises the chunk streams).
+ *
+ * Compact row of one env (row_bytes = adc_host_row_bytes(K, float_dtype); little endian):
+ *     uint16 impressions[K] | uint16 clicks[K] | uint16 conversions[K] | pad to 8 bytes
+ *     float  cost[K] | float revenue[K]          (float_dtype ADC_F32; doubles with ADC_F64) | pad to 8 bytes
+ *     double reward | double cumulative_profit | int32 days_passed
+ *     uint8 terminated | uint8 truncated | uint8 count_overflow | uint8 0
+ * count_overflow = 1 when a count of the env exceeds 65535 (the uint16 then holds 65535; the device
+ * arrays of adc_step_out keep the exact int32 values). */
+typedef struct adc_host_chunk {
+    adc_step_args args;       /* the chunk's envs: every pointer already offset to its first env, its own
+                                 scratch counters (serial_count, work_counter); args.bids = DEVICE staging */
+    const void *bids_host;    /* [args.E, K] pinned host bids, args.bids_dtype */
+    void *rows_dev;           /* [args.E, row_bytes] device staging */
+    void *rows_host;          /* [args.E, row_bytes] pinned host output */
+    void *stream;             /* the chunk's stream (chunks may share streams; >= 2 distinct ones overlap) */
+} adc_host_chunk;
+
+int64_t adc_host_row_bytes(int32_t K, int32_t float_dtype);
+int adc_step_host(const adc_host_chunk *chunks, int32_t n_chunks);
+int adc_sizeof_host_chunk(void);
 
 /* The ideal-profit estimator above for E x K units. */
 int adc_ideal_profit(const adc_ideal_args *args, void *stream);

@@ -161,3 +161,38 @@ def test_device_side_keyword_sampling_matches_host_distributions():
     env.install_device_keywords(cols)
     obs = env.step({"keyword_bids": torch.full((E, K), 0.8, device="cuda")})[0]
     assert int(obs["impressions"].sum()) > 0
+
+
+@pytest.mark.parametrize("K,E,budget,chunks,drift", [(33, 70, 60.0, 4, False), (100, 256, 1e5, 4, True),
+                                                     (20, 40, 1e6, 3, False), (7, 5, 3.0, 8, True)])
+def test_step_host_pipelined_equals_device_step(K, E, budget, chunks, drift):
+    """adc_step_host (chunked H2D -> kernels -> row packing -> D2H on one stream per chunk) returns, in
+    its compact host rows, exactly what the plain device step computes -- budgets that bind (the
+    exact serial walk runs per chunk on its share of the workspace), drift, ragged chunk sizes."""
+    from adcraft_b200 import keywords as kwm
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    rng = np.random.default_rng(K)
+    table = kwm.sample_implicit_keywords_from_quantiles(K, rng, {"mean_volume": 64, "conversion_rate": 0.8})
+    mk = lambda: VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=budget, device="cuda", seed=4,
+                                         max_days=3, updater_mask=[True] * K if drift else None)
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    for step in range(5):
+        bids = torch.from_numpy(np.round(rng.uniform(0.2, 1.5, (E, K)), 2).astype(np.float32)).pin_memory()
+        h = a.step_host_pipelined(bids, n_chunks=chunks)
+        obs, reward, term, trunc, _ = b.step({"keyword_bids": bids.cuda()})
+        for k in ("impressions", "buyside_clicks", "sellside_conversions"):
+            assert torch.equal(h[k].to(torch.int32), obs[k].cpu()), (k, step)
+        for k in ("cost", "revenue"):
+            assert torch.equal(h[k], obs[k].cpu()), (k, step)
+        assert torch.equal(h["reward"], reward.cpu())
+        assert torch.equal(h["cumulative_profit"], obs["cumulative_profit"].cpu())
+        assert torch.equal(h["days_passed"], obs["days_passed"].cpu())
+        assert torch.equal(h["terminated"].bool(), term.cpu()) and torch.equal(h["truncated"].bool(), trunc.cpu())
+        assert int(h["count_overflow"].sum()) == 0
+        # the device-side observation of the pipelined env is up to date as well
+        assert torch.equal(a._out["impressions"], obs["impressions"])
+    assert int(h["impressions"].to(torch.int64).sum()) > 0
+    if drift:
+        pa, pb = a.keyword_params(), b.keyword_params()
+        assert all(np.array_equal(pa[n], pb[n]) for n in ("vol_mean", "ctr", "cvr"))
