@@ -47,6 +47,22 @@ __device__ __forceinline__ void store_f(void *p, int dtype, int64_t i, double v)
         reinterpret_cast<float *>(p)[i] = (float)v;
 }
 
+// Optional flat observation row of env e (adc_step_out.flat_obs): the reference's FlatArrayWrapper
+// layout, keys sorted (wrappers/flat_array.py:44-87, gymnasium_kw_utils.py:383-390):
+//   [buyside_clicks(K) | cost(K) | cumulative_profit | days_passed | impressions(K) | revenue(K) |
+//    sellside_conversions(K)], 5 K + 2 values of float_dtype.
+__device__ __forceinline__ void store_flat_unit(const adc_step_args &a, int e, int k, int I, int B, int S, double cost,
+                                                double rev)
+{
+    if (a.out.flat_obs == nullptr) return;
+    const int64_t K = a.kw.K, base = (int64_t)e * (5 * K + 2);
+    store_f(a.out.flat_obs, a.out.float_dtype, base + k, (double)B);
+    store_f(a.out.flat_obs, a.out.float_dtype, base + K + k, cost);
+    store_f(a.out.flat_obs, a.out.float_dtype, base + 2 * K + 2 + k, (double)I);
+    store_f(a.out.flat_obs, a.out.float_dtype, base + 3 * K + 2 + k, rev);
+    store_f(a.out.flat_obs, a.out.float_dtype, base + 4 * K + 2 + k, (double)S);
+}
+
 // cents / 100 correctly rounded (== np.around(x, 2) of the same cents value).  The f64 division is a
 // ~35-instruction routine; for |c| < 2^31 one Newton step on c * 0.01 with the exact FMA residual gives
 // the identical double (checked exhaustively against c / 100.0 for every c in [0, 2^31) on the host,
@@ -151,6 +167,11 @@ __device__ __forceinline__ void env_tail(const adc_step_args &a, int e, double r
     a.out.reward[e] = reward;
     a.out.obs_cum_profit[e] = cum;
     a.out.obs_days[e] = day;
+    if (a.out.flat_obs != nullptr) {
+        const int64_t K = a.kw.K, base = (int64_t)e * (5 * K + 2);
+        store_f(a.out.flat_obs, a.out.float_dtype, base + 2 * K, cum);
+        store_f(a.out.flat_obs, a.out.float_dtype, base + 2 * K + 1, (double)day);
+    }
     a.out.terminated[e] = term ? 1 : 0;
     a.out.truncated[e] = trunc ? 1 : 0;
     if (a.out.remaining_budget) a.out.remaining_budget[e] = remaining;
@@ -855,6 +876,7 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
             a.out.revenue_cents[u] = rev;
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
+            store_flat_unit(a, e, (int)(u - (int64_t)e * K), I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
             safe = unit_done(a, e, rev - cost, over_cap ? (1LL << 40) : cost);
         }
         if (a.drift.mask != nullptr || a.out.episode_profit_cents != nullptr) {
@@ -1096,14 +1118,17 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
             a.out.revenue_cents[u] = rev;
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
+            store_flat_unit(a, e, (int)(u - (int64_t)e * K), I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
             safe = unit_done(a, e, rev - cost, my_overrun ? (1LL << 40) : cost);
         }
-        if (a.drift.mask != nullptr) {
+        if (a.drift.mask != nullptr || a.out.episode_profit_cents != nullptr) {
             unsigned todo = __ballot_sync(FULL, safe != 0);
             while (todo) {
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int ee = __shfl_sync(FULL, e, src);
+                episode_accumulate(a, ee, lane, 32);
+                if (a.drift.mask == nullptr) continue;
                 for (int kk = lane; kk < K; kk += 32) {
                     if (!drift_wanted(a, kk)) continue;
                     drift_apply(a, ee, kk, unit_drift<TapeSrc>(a, &t, ee, kk, make_uint4(0, 0, 0, 0)));
@@ -1501,14 +1526,17 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
             a.out.revenue_cents[u] = rev;
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
+            store_flat_unit(a, e, (int)(u - (int64_t)e * K), I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
             safe = unit_done(a, e, rev - cost, my_overrun ? (1LL << 40) : cost);
         }
-        if (a.drift.mask != nullptr) {
+        if (a.drift.mask != nullptr || a.out.episode_profit_cents != nullptr) {
             unsigned dm = __ballot_sync(FULL, safe != 0);
             while (dm) {
                 const int src = __ffs(dm) - 1;
                 dm &= dm - 1;
                 const int ee = __shfl_sync(FULL, e, src);
+                episode_accumulate(a, ee, lane, 32);
+                if (a.drift.mask == nullptr) continue;
                 for (int kk = lane; kk < K; kk += 32) {
                     if (!drift_wanted(a, kk)) continue;
                     drift_apply(a, ee, kk, unit_drift<TapeSrc>(a, &t, ee, kk, make_uint4(0, 0, 0, 0)));
@@ -1576,12 +1604,15 @@ adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant_
             a.out.cost_cents[u] = 0;
             a.scratch.unit_cost_f64[u] = overrun ? __longlong_as_double(0x7FF0000000000000LL) : cost_f;
             store_f(a.out.cost, a.out.float_dtype, u, cost_f);
+            store_flat_unit(a, e, k, I, B, S, cost_f, cents_to_dollars(rev_c));
             safe = unit_done(a, e, 0, 0);
         } else {
             a.out.cost_cents[u] = cost_c;
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost_c));
+            store_flat_unit(a, e, k, I, B, S, cents_to_dollars(cost_c), cents_to_dollars(rev_c));
             safe = unit_done(a, e, rev_c - cost_c, overrun ? kForceSerialCents : cost_c);
         }
+        if (safe) episode_accumulate(a, e, 0, 1);
         if (safe && a.drift.mask != nullptr) {
             for (int kk = 0; kk < K; ++kk) {
                 if (!drift_wanted(a, kk)) continue;
@@ -1733,11 +1764,16 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
             if (explicit_kw) {
                 const double c = a.scratch.unit_cost_f64[u];
                 store_f(a.out.cost, a.out.float_dtype, u, c);
+                store_flat_unit(a, e, k, acc.I[u], acc.B[u], acc.S[u], c, rv);
                 reward = __dadd_rn(reward, __dsub_rn(rv, c));
             } else {
-                store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(a.out.cost_cents[u]));
+                const double c = cents_to_dollars(a.out.cost_cents[u]);
+                store_f(a.out.cost, a.out.float_dtype, u, c);
+                store_flat_unit(a, e, k, acc.I[u], acc.B[u], acc.S[u], c, rv);
                 profit_c += a.out.revenue_cents[u] - a.out.cost_cents[u];
             }
+            if (a.out.episode_profit_cents != nullptr)
+                a.out.episode_profit_cents[u] += a.out.revenue_cents[u] - a.out.cost_cents[u];
         }
         if (!explicit_kw) reward = cents_to_dollars(profit_c);
         env_tail(a, e, reward, budget, remaining);
@@ -2095,6 +2131,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cc));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rc));
             ser_publish(a, acc, u);
+            store_flat_unit(a, e, k, acc.I[u], acc.B[u], acc.S[u], cents_to_dollars(cc), cents_to_dollars(rc));
             if (a.out.episode_profit_cents != nullptr) a.out.episode_profit_cents[u] += rc - cc;
             profit_c += rc - cc;
         }

@@ -89,6 +89,7 @@ class VectorBiddingSimulation:
         dynamic_work: bool = True,
         f32_ties: bool = False,
         episode_profit: bool = False,
+        flat_obs: bool = False,
         serial_ws_bytes: int = 1 << 30,
         **kwargs,
     ) -> None:
@@ -120,6 +121,9 @@ class VectorBiddingSimulation:
         # [E, K] int64 running sum of every step's exact per-keyword profit (adc_step_out.
         # episode_profit_cents): what AKNCP / NCP are made of, accumulated inside the step kernels
         self.episode_profit = bool(episode_profit)
+        # [E, 5K+2] flat observation rows in the reference's FlatArrayWrapper layout, written by the
+        # kernels (adc_step_out.flat_obs); `flat_observation()` hands the tensor out, no gather pass
+        self.want_flat_obs = bool(flat_obs)
         # cap of the exact serial walk's workspace (one 640 B x K slab per resident warp)
         self.serial_ws_cap = int(serial_ws_bytes)
         self.env_base = int(env_base)
@@ -180,10 +184,11 @@ class VectorBiddingSimulation:
             cum_profit=z(E, dtype=f64), day=z(E, dtype=i32))
         self._scratch = dict(
             serial_list=z(E, dtype=i32), serial_count=z(2, dtype=i32), env_profit=z(E, dtype=i64),
-            env_cost=z(E, dtype=i64), env_done=z(E, dtype=i32), unit_cost_f64=z(E, K, dtype=f64),
-            work_counter=z(2, dtype=i32))
+            env_cost=z(E, dtype=i64), env_done=z(E, dtype=i32), work_counter=z(2, dtype=i32))
         if self.episode_profit:
             self._out["episode_profit_cents"] = z(E, K, dtype=i64)
+        if self.want_flat_obs:
+            self._out["flat_obs"] = z(E, 5 * K + 2, dtype=fdt)
         # one slab per resident warp of the exact serial walk (28 warps per SM), within the cap
         slab = max(int(self._lib.adc_serial_slab_bytes(K)), 1)
         n_slabs = max(1, min(E, 148 * 28, self.serial_ws_cap // slab))
@@ -195,8 +200,9 @@ class VectorBiddingSimulation:
                                 n_recorded=z(E, K, dtype=i32), volume_seen=z(E, K, dtype=f64),
                                 lane_clicks=z(E, K, _capi.SUBSTEPS, dtype=i32),
                                 lane_convs=z(E, K, _capi.SUBSTEPS, dtype=i32))
-        self._bids_dev = {torch.float32: z(E, K, dtype=torch.float32), torch.float64: z(E, K, dtype=f64)}
-        self._budget_dev = {torch.float32: z(E, dtype=torch.float32), torch.float64: z(E, dtype=f64)}
+        # staging for actions that arrive on the host or in another layout: allocated on first use
+        self._bids_dev = {torch.float32: None, torch.float64: None}
+        self._budget_dev = {torch.float32: None, torch.float64: None}
         self._mask_dev: Optional[torch.Tensor] = None
         self._host: Dict[str, torch.Tensor] = {}
         self._host_ptrs = None
@@ -310,6 +316,13 @@ class VectorBiddingSimulation:
                 revenues_per_cost=r.tolist(), profit=float(profit)))
         return out
 
+    def flat_observation(self) -> torch.Tensor:
+        """[E, 5K+2] observation rows in the reference's flat layout (wrappers/flat_array.py:44-87),
+        written by the step kernels themselves; needs ``flat_obs=True`` at construction.  The env's
+        own buffer: overwritten by the next step."""
+        assert self.want_flat_obs, "construct the env with flat_obs=True"
+        return self._out["flat_obs"]
+
     def keyword_params(self) -> Dict[str, np.ndarray]:
         """Current (possibly drifted) keyword parameters, host copies."""
         return {n: t.cpu().numpy() for n, t in self._kw_dev.items()}
@@ -351,8 +364,9 @@ class VectorBiddingSimulation:
                    self.num_envs, None, self._state["cum_profit"].data_ptr(), self._state["day"].data_ptr(),
                    C.c_void_p(stream))
         for k in ("impressions", "buyside_clicks", "sellside_conversions", "cost", "revenue",
-                  "cumulative_profit", "days_passed", "reward"):
-            self._out[k].zero_()
+                  "cumulative_profit", "days_passed", "reward", "flat_obs", "episode_profit_cents"):
+            if k in self._out:
+                self._out[k].zero_()
         return self._obs(), {"keyword_params": self.keywords.describe()}
 
     def reset_envs(self, mask: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -367,8 +381,9 @@ class VectorBiddingSimulation:
                    C.c_void_p(stream))
         rows = m.bool()
         for k in ("impressions", "buyside_clicks", "sellside_conversions", "cost", "revenue",
-                  "cumulative_profit", "days_passed", "reward"):
-            self._out[k][rows] = 0
+                  "cumulative_profit", "days_passed", "reward", "flat_obs"):
+            if k in self._out:
+                self._out[k][rows] = 0
         return self._obs()
 
     # ------------------------------------------------------------------ step
@@ -392,6 +407,8 @@ class VectorBiddingSimulation:
             x = torch.as_tensor(np.asarray(x))
         if x.dtype not in store:
             x = x.to(torch.float64 if x.dtype == torch.float64 else torch.float32)
+        if store[x.dtype] is None:
+            store[x.dtype] = torch.zeros(shape, dtype=x.dtype, device=self.device)
         dst = store[x.dtype]
         dst.copy_(x.reshape(shape) if x.numel() == dst.numel() else x.expand(shape), non_blocking=True)
         return dst
@@ -451,11 +468,15 @@ class VectorBiddingSimulation:
         out.terminated, out.truncated = o["terminated"].data_ptr(), o["truncated"].data_ptr()
         out.remaining_budget = o["remaining_budget"].data_ptr()
         sc = a.scratch
-        for n in ("serial_list", "serial_count", "env_profit", "env_cost", "env_done", "unit_cost_f64"):
+        if self.kind != kwmod.IMPLICIT and "unit_cost_f64" not in s:  # un-rounded cost sums: explicit / multi-bidder
+            s["unit_cost_f64"] = torch.zeros(E, K, dtype=torch.float64, device=self.device)
+        for n in ("serial_list", "serial_count", "env_profit", "env_cost", "env_done"):
             setattr(sc, n, s[n].data_ptr())
+        sc.unit_cost_f64 = _ptr(s.get("unit_cost_f64"))
         sc.work_counter = s["work_counter"].data_ptr() if self.dynamic_work else None
         sc.serial_ws, sc.serial_ws_bytes = s["serial_ws"].data_ptr(), s["serial_ws"].numel()
         out.episode_profit_cents = _ptr(o.get("episode_profit_cents"))
+        out.flat_obs = _ptr(o.get("flat_obs"))
         if self._detail is not None:
             a.detail.cap = self.detail_cap
             for n in ("costs", "rev_per_cost", "n_recorded", "volume_seen", "lane_clicks", "lane_convs"):
@@ -570,6 +591,7 @@ class VectorBiddingSimulation:
             for n, sz in (("reward", 8), ("obs_cum_profit", 8), ("obs_days", 4), ("terminated", 1), ("truncated", 1),
                           ("remaining_budget", 8)):
                 setattr(o, n, off(getattr(bo, n), e0 * sz))
+            o.flat_obs = off(bo.flat_obs, e0 * (5 * K + 2) * fb)
             sc, bs = a.scratch, base.scratch
             for n, sz in (("serial_list", 4), ("env_profit", 8), ("env_cost", 8), ("env_done", 4)):
                 setattr(sc, n, off(getattr(bs, n), e0 * sz))

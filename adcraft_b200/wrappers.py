@@ -22,9 +22,13 @@ def flatten_dict_array(obs: Dict[str, np.ndarray]) -> np.ndarray:
     return np.hstack([np.asarray(obs[k]).ravel() for k in sorted(obs.keys())])
 
 
-def flat_observations(obs):
-    """[E, 5K+2] tensor from a VectorBiddingSimulation observation dict (device, float of cost's dtype)."""
+def flat_observations(obs, env=None):
+    """[E, 5K+2] flat observation rows.  With ``env`` built with ``flat_obs=True`` this is the tensor
+    the step kernels wrote (zero-copy, ``env.flat_observation()``); otherwise the rows are gathered
+    from the observation dict (device, float of cost's dtype)."""
     import torch
+    if env is not None and getattr(env, "want_flat_obs", False):
+        return env.flat_observation()
     dt = obs["cost"].dtype
     return torch.cat([obs[k].to(dt).reshape(obs[k].shape[0], -1) for k in OBS_KEYS_SORTED], dim=1)
 

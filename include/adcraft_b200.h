@@ -121,6 +121,11 @@ typedef struct adc_step_out {
                                  step, added when the env's step is final (the per-keyword profits
                                  AKNCP / NCP are made of, experiment_metrics.py:64-83); the caller
                                  zeroes it at the episode boundaries it cares about */
+    void *flat_obs;           /* optional [E, 5K+2] float_dtype: the reference's flat observation row
+                                 (FlatArrayWrapper, wrappers/flat_array.py:44-87; keys sorted like
+                                 gymnasium_kw_utils.py:383-390): buyside_clicks[0:K] | cost[K:2K] |
+                                 cumulative_profit | days_passed | impressions | revenue |
+                                 sellside_conversions -- written by the kernels, no gather pass */
 } adc_step_out;
 
 /* Scratch the step needs (caller-owned so that nothing is allocated per call). */

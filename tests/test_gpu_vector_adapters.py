@@ -76,3 +76,29 @@ def test_rllib_vector_adapter_reset_at():
     assert not o1.any()
     o, r, te, tr, _ = vec.vector_step(act)
     assert o[1][2 * K + 1] == 1 and o[0][2 * K + 1] == 3 and not te[1] and te[0]
+
+
+@pytest.mark.parametrize("kind,budget", [("implicit", 1e5), ("implicit", 20.0), ("explicit", 1000.0), ("explicit", 5.0)])
+def test_kernel_written_flat_rows_equal_the_gathered_layout(kind, budget):
+    """adc_step_out.flat_obs: the [E, 5K+2] rows the kernels write (fast path, exact serial walk,
+    explicit keywords) are the FlatArrayWrapper layout of the same step's observation dict
+    (wrappers/flat_array.py:44-87; keys sorted, gymnasium_kw_utils.py:383-390)."""
+    from conftest import make_explicit_table, make_implicit_table
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    from adcraft_b200.wrappers import flat_observations, observation_slices
+    rng = np.random.default_rng(12)
+    E, K = 37, 11
+    table = make_implicit_table(rng, K, 64) if kind == "implicit" else make_explicit_table(rng, K)
+    env = VectorBiddingSimulation(E, num_keywords=K, keywords=table, device="cuda", seed=3, budget=budget, max_days=2,
+                                  flat_obs=True, obs_dtype=torch.float64)
+    obs, _ = env.reset()
+    assert float(env.flat_observation().abs().sum()) == 0.0
+    for step in range(4):
+        bids = torch.from_numpy(np.round(rng.uniform(0.2, 2.5, (E, K)), 2)).cuda()
+        obs, reward, term, trunc, _ = env.step({"keyword_bids": bids})
+        flat = flat_observations(obs, env)
+        assert flat.data_ptr() == env.flat_observation().data_ptr() and flat.shape == (E, 5 * K + 2)
+        assert torch.equal(flat, flat_observations(obs)), step  # the gathered form of the same dict
+    sl = observation_slices(K)
+    assert torch.equal(flat[:, sl["days_passed"]], obs["days_passed"].to(flat.dtype))
+    assert float(flat[:, sl["impressions"]].sum()) > 0
