@@ -48,7 +48,8 @@ class StepOut(C.Structure):
         ("cost_cents", C.c_void_p), ("revenue_cents", C.c_void_p), ("reward", C.c_void_p),
         ("obs_cum_profit", C.c_void_p), ("obs_days", C.c_void_p), ("terminated", C.c_void_p),
         ("truncated", C.c_void_p), ("remaining_budget", C.c_void_p),
-        ("episode_profit_cents", C.c_void_p), ("flat_obs", C.c_void_p),
+        ("episode_profit_cents", C.c_void_p), ("episode_reward", C.c_void_p), ("episode_count", C.c_void_p),
+        ("rows", C.c_void_p), ("flat_obs", C.c_void_p),
     ]
 
 

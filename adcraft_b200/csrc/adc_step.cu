@@ -63,6 +63,115 @@ __device__ __forceinline__ void store_flat_unit(const adc_step_args &a, int e, i
     store_f(a.out.flat_obs, a.out.float_dtype, base + 4 * K + 2 + k, (double)S);
 }
 
+// ------------------------------------------------------------------------------------------
+// compact observation rows (adc_step_out.rows / adc_step_host; layout in include/adcraft_b200.h)
+// ------------------------------------------------------------------------------------------
+struct RowLayout {
+    int64_t counts, money, tail, bytes;  // byte offsets inside a row, row size
+};
+
+__host__ __device__ inline RowLayout row_layout(int K, int float_dtype)
+{
+    RowLayout r;
+    r.counts = 0;
+    r.money = ((int64_t)6 * K + 7) & ~(int64_t)7;
+    const int64_t fb = float_dtype == ADC_F64 ? 8 : 4;
+    r.tail = (r.money + 2 * fb * K + 7) & ~(int64_t)7;
+    r.bytes = r.tail + 24;
+    return r;
+}
+
+// One warp packs env e's observation into its row: counts as uint16 (four keywords per 8-byte
+// store where the row allows), money in float_dtype, the env scalars.  Reads the step's outputs
+// with L2 loads: other warps wrote them before the env's completion counter let this warp in.
+__device__ __forceinline__ void pack_row_warp(const adc_step_args &a, int e, unsigned char *rows, int lane)
+{
+    const int K = a.kw.K;
+    const RowLayout L = row_layout(K, a.out.float_dtype);
+    unsigned char *row = rows + (int64_t)e * L.bytes;
+    const int64_t u0 = (int64_t)e * K;
+    bool over = false;
+    auto c16 = [&](const int32_t *p, int64_t u) {
+        const int v = __ldcg(p + u);
+        over = over || v > 65535;
+        return (uint32_t)min(v, 65535);
+    };
+    const int32_t *src[3] = {a.out.impressions, a.out.clicks, a.out.conversions};
+    if ((K & 3) == 0 && (L.bytes & 7) == 0) {
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            uint2 *dst = reinterpret_cast<uint2 *>(row + L.counts + (int64_t)f * 2 * K);
+            for (int k4 = lane; 4 * k4 < K; k4 += 32) {
+                uint2 v;
+                v.x = c16(src[f], u0 + 4 * k4) | (c16(src[f], u0 + 4 * k4 + 1) << 16);
+                v.y = c16(src[f], u0 + 4 * k4 + 2) | (c16(src[f], u0 + 4 * k4 + 3) << 16);
+                dst[k4] = v;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            uint16_t *dst = reinterpret_cast<uint16_t *>(row + L.counts) + (int64_t)f * K;
+            for (int k = lane; k < K; k += 32) dst[k] = (uint16_t)c16(src[f], u0 + k);
+        }
+    }
+    if (a.out.float_dtype == ADC_F64) {
+        double *m = reinterpret_cast<double *>(row + L.money);
+        for (int k = lane; k < K; k += 32) {
+            m[k] = __ldcg(reinterpret_cast<const double *>(a.out.cost) + u0 + k);
+            m[K + k] = __ldcg(reinterpret_cast<const double *>(a.out.revenue) + u0 + k);
+        }
+    } else {
+        float *m = reinterpret_cast<float *>(row + L.money);
+        for (int k = lane; k < K; k += 32) {
+            m[k] = __ldcg(reinterpret_cast<const float *>(a.out.cost) + u0 + k);
+            m[K + k] = __ldcg(reinterpret_cast<const float *>(a.out.revenue) + u0 + k);
+        }
+    }
+    over = __any_sync(0xFFFFFFFFu, over);
+    if (lane == 0) {
+        double *t = reinterpret_cast<double *>(row + L.tail);
+        t[0] = __ldcg(a.out.reward + e);
+        t[1] = __ldcg(a.out.obs_cum_profit + e);
+        *reinterpret_cast<int32_t *>(row + L.tail + 16) = __ldcg(a.out.obs_days + e);
+        const uint32_t flags = (uint32_t)__ldcg(a.out.terminated + e) | ((uint32_t)__ldcg(a.out.truncated + e) << 8) |
+                               (over ? 1u << 16 : 0u);
+        *reinterpret_cast<uint32_t *>(row + L.tail + 20) = flags;
+    }
+}
+
+// The fast path writes a unit's part of its env's row with the unit's other outputs (spread over all
+// warps, no gather) and the env scalars when the env completes; counts are below 2^16 there.
+__device__ __forceinline__ void pack_row_unit(const adc_step_args &a, int e, int k, int I, int B, int S, double cost,
+                                              double rev)
+{
+    const int K = a.kw.K;
+    const RowLayout L = row_layout(K, a.out.float_dtype);
+    unsigned char *row = reinterpret_cast<unsigned char *>(a.out.rows) + (int64_t)e * L.bytes;
+    uint16_t *cnt = reinterpret_cast<uint16_t *>(row + L.counts);
+    cnt[k] = (uint16_t)I;
+    cnt[K + k] = (uint16_t)B;
+    cnt[2 * K + k] = (uint16_t)S;
+    if (a.out.float_dtype == ADC_F64) {
+        double *m = reinterpret_cast<double *>(row + L.money);
+        m[k] = cost; m[K + k] = rev;
+    } else {
+        float *m = reinterpret_cast<float *>(row + L.money);
+        m[k] = (float)cost; m[K + k] = (float)rev;
+    }
+}
+
+__device__ __forceinline__ void pack_row_tail(const adc_step_args &a, int e)
+{
+    const RowLayout L = row_layout(a.kw.K, a.out.float_dtype);
+    unsigned char *row = reinterpret_cast<unsigned char *>(a.out.rows) + (int64_t)e * L.bytes;
+    double *t = reinterpret_cast<double *>(row + L.tail);
+    t[0] = a.out.reward[e];
+    t[1] = a.out.obs_cum_profit[e];
+    *reinterpret_cast<int32_t *>(row + L.tail + 16) = a.out.obs_days[e];
+    *reinterpret_cast<uint32_t *>(row + L.tail + 20) = (uint32_t)a.out.terminated[e] | ((uint32_t)a.out.truncated[e] << 8);
+}
+
 // cents / 100 correctly rounded (== np.around(x, 2) of the same cents value).  The f64 division is a
 // ~35-instruction routine; for |c| < 2^31 one Newton step on c * 0.01 with the exact FMA residual gives
 // the identical double (checked exhaustively against c / 100.0 for every c in [0, 2^31) on the host,
@@ -175,6 +284,8 @@ __device__ __forceinline__ void env_tail(const adc_step_args &a, int e, double r
     a.out.terminated[e] = term ? 1 : 0;
     a.out.truncated[e] = trunc ? 1 : 0;
     if (a.out.remaining_budget) a.out.remaining_budget[e] = remaining;
+    if (a.out.episode_reward != nullptr) a.out.episode_reward[e] = __dadd_rn(a.out.episode_reward[e], reward);
+    if (a.out.episode_count != nullptr && (term || trunc)) a.out.episode_count[e] += 1;
     const bool done = a.autoreset && (term || trunc);
     a.env.cum_profit[e] = done ? 0.0 : cum;
     a.env.day[e] = done ? 0 : day;
@@ -876,12 +987,14 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
             a.out.revenue_cents[u] = rev;
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
-            store_flat_unit(a, e, (int)(u - (int64_t)e * K), I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
+            store_flat_unit(a, e, k, I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
+            if (a.out.rows != nullptr) pack_row_unit(a, e, k, I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
             safe = unit_done(a, e, rev - cost, over_cap ? (1LL << 40) : cost);
+            if (safe && a.out.rows != nullptr) pack_row_tail(a, e);  // this lane ran the env tail
         }
         if (a.drift.mask != nullptr || a.out.episode_profit_cents != nullptr) {
-            // finished budget-safe envs: episode accumulation and drift (env:246), the warp shares
-            // each env's keywords
+            // finished budget-safe envs: episode accumulation and drift (env:246), the warp shares each
+            // env's keywords
             unsigned todo = __ballot_sync(FULL, safe != 0);
             while (todo) {
                 const int src = __ffs(todo) - 1;
@@ -2138,6 +2251,11 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) profit_c += __shfl_xor_sync(FULL, profit_c, off);
         if (lane == 0) env_tail(a, e, cents_to_dollars(profit_c), budget, remaining);
+        if (a.out.rows != nullptr) {
+            __threadfence();  // the row reads what this warp's lanes just stored
+            __syncwarp();
+            pack_row_warp(a, e, reinterpret_cast<unsigned char *>(a.out.rows), lane);
+        }
         if (a.drift.mask != nullptr) {
             for (int kk = lane; kk < K; kk += 32) {
                 if (!drift_wanted(a, kk)) continue;
@@ -2153,62 +2271,13 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
 // ------------------------------------------------------------------------------------------
 // compact host rows (adc_step_host): one warp per env packs the step's observation into one row
 // ------------------------------------------------------------------------------------------
-struct RowLayout {
-    int64_t counts, money, tail, bytes;  // byte offsets inside a row, row size
-};
-
-__host__ __device__ inline RowLayout row_layout(int K, int float_dtype)
-{
-    RowLayout r;
-    r.counts = 0;
-    r.money = ((int64_t)6 * K + 7) & ~(int64_t)7;
-    const int64_t fb = float_dtype == ADC_F64 ? 8 : 4;
-    r.tail = (r.money + 2 * fb * K + 7) & ~(int64_t)7;
-    r.bytes = r.tail + 24;
-    return r;
-}
-
 __global__ void __launch_bounds__(256)
 adc_pack_rows_kernel(const __grid_constant__ adc_step_args a, unsigned char *rows)
 {
-    const int K = a.kw.K;
-    const RowLayout L = row_layout(K, a.out.float_dtype);
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t e = warp; e < a.E; e += n_warps) {
-        unsigned char *row = rows + e * L.bytes;
-        uint16_t *cnt = reinterpret_cast<uint16_t *>(row + L.counts);
-        bool over = false;
-        for (int k = lane; k < K; k += 32) {
-            const int64_t u = e * K + k;
-            const int i = a.out.impressions[u], b = a.out.clicks[u], c = a.out.conversions[u];
-            over = over || i > 65535 || b > 65535 || c > 65535;
-            cnt[k] = (uint16_t)min(i, 65535);
-            cnt[K + k] = (uint16_t)min(b, 65535);
-            cnt[2 * K + k] = (uint16_t)min(c, 65535);
-            if (a.out.float_dtype == ADC_F64) {
-                double *m = reinterpret_cast<double *>(row + L.money);
-                m[k] = reinterpret_cast<const double *>(a.out.cost)[u];
-                m[K + k] = reinterpret_cast<const double *>(a.out.revenue)[u];
-            } else {
-                float *m = reinterpret_cast<float *>(row + L.money);
-                m[k] = reinterpret_cast<const float *>(a.out.cost)[u];
-                m[K + k] = reinterpret_cast<const float *>(a.out.revenue)[u];
-            }
-        }
-        over = __any_sync(0xFFFFFFFFu, over);
-        if (lane == 0) {
-            double *t = reinterpret_cast<double *>(row + L.tail);
-            t[0] = a.out.reward[e];
-            t[1] = a.out.obs_cum_profit[e];
-            *reinterpret_cast<int32_t *>(row + L.tail + 16) = a.out.obs_days[e];
-            row[L.tail + 20] = a.out.terminated[e];
-            row[L.tail + 21] = a.out.truncated[e];
-            row[L.tail + 22] = over ? 1 : 0;
-            row[L.tail + 23] = 0;
-        }
-    }
+    for (int64_t e = warp; e < a.E; e += n_warps) pack_row_warp(a, (int)e, rows, lane);
 }
 
 __global__ void adc_reset_envs_kernel(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day)
@@ -2223,6 +2292,8 @@ __global__ void adc_reset_envs_kernel(int32_t E, const uint8_t *mask, double *cu
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+cudaError_t launch_pack_rows(const adc_step_args &a, void *rows_dev, cudaStream_t s, int64_t *launches);
+
 static int g_num_sms = 0;
 
 static int num_sms()
@@ -2340,7 +2411,13 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         kern<<<(unsigned)grid_for(kern, 64, a.E), 64, 0, s>>>(a, tp);
     }
     ++*launches;
-    return cudaGetLastError();
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    // compact rows: the free-running implicit kernels pack them as they finalise each env; every
+    // other kernel family gets one packing pass over the finished step
+    const bool rows_in_kernel = tape == nullptr && !explicit_kw && a.n_lanes != 1 && a.detail.costs == nullptr && n_slabs > 0;
+    if (a.out.rows != nullptr && !rows_in_kernel) return launch_pack_rows(a, a.out.rows, s, launches);
+    return cudaSuccess;
 }
 
 int64_t serial_slab_bytes(int32_t K) { return (int64_t)K * kSlabBytesPerKeyword; }

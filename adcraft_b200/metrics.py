@@ -121,6 +121,48 @@ class MetricAccumulator:
                             self.reward_sum, self.episodes])
 
 
+def episode_summary_vector(env, steps: int, ideal: torch.Tensor, reward_sum: Optional[torch.Tensor] = None,
+                           episodes: Optional[torch.Tensor] = None, zero: bool = True,
+                           row_chunk: int = 8192) -> torch.Tensor:
+    """The metric vector of ``MetricAccumulator.summary_vector`` from the env's own kernel-side
+    accumulators (``episode_profit=True``: ``adc_step_out.episode_profit_cents`` holds the exact sum
+    of every step's per-keyword profit): per-env AKNCP = median over keywords of
+    (mean profit / mean ideal, ideal <= 0 -> 1) and NCP = sum profit / sum ideal
+    (experiment_metrics.py:64-83) over ``steps`` steps with a per-step ideal profit ``ideal``
+    ([1, K] or [E, K], stationary over the window).  ``zero``: start the next window."""
+    acc = env._out["episode_profit_cents"]
+    E, K = acc.shape
+    f64 = torch.float64
+    ideal = ideal.to(f64)
+    out = torch.zeros(8, dtype=f64, device=acc.device)
+    for r0 in range(0, E, row_chunk):
+        prof = acc[r0:r0 + row_chunk].to(f64) / 100.0
+        idl = ideal if ideal.shape[0] == 1 else ideal[r0:r0 + row_chunk]
+        den = torch.where(idl <= 0, torch.ones_like(idl), idl)
+        ratio = (prof / steps) / den
+        # np.median: mean of the two middle values for an even count
+        lo = torch.kthvalue(ratio, (K + 1) // 2, dim=1).values
+        hi = torch.kthvalue(ratio, K // 2 + 1, dim=1).values
+        akncp = 0.5 * (lo + hi)
+        isum = idl.sum(1) * steps
+        ncp = prof.sum(1) / torch.where(isum <= 0, torch.ones_like(isum), isum)
+        out[0] += prof.sum()
+        out[1] += (idl.expand_as(prof) * steps).sum()
+        out[2] += akncp.sum()
+        out[3] += (akncp ** 2).sum()
+        out[4] += ncp.sum()
+        out[5] += prof.shape[0]
+    er, ec = env._out.get("episode_reward"), env._out.get("episode_count")
+    out[6] = reward_sum if reward_sum is not None else (er.sum() if er is not None else 0.0)
+    out[7] = episodes if episodes is not None else (ec.sum() if ec is not None else 0.0)
+    if zero:
+        acc.zero_()
+        if er is not None:
+            er.zero_()
+            ec.zero_()
+    return out
+
+
 def reduce_metrics(vec: torch.Tensor, group=None) -> torch.Tensor:
     """Sum-all-reduce of the metric vector over ranks (no-op without an initialised group)."""
     import torch.distributed as dist

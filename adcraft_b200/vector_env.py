@@ -187,6 +187,8 @@ class VectorBiddingSimulation:
             env_cost=z(E, dtype=i64), env_done=z(E, dtype=i32), work_counter=z(2, dtype=i32))
         if self.episode_profit:
             self._out["episode_profit_cents"] = z(E, K, dtype=i64)
+            self._out["episode_reward"] = z(E, dtype=f64)
+            self._out["episode_count"] = z(E, dtype=i32)
         if self.want_flat_obs:
             self._out["flat_obs"] = z(E, 5 * K + 2, dtype=fdt)
         # one slab per resident warp of the exact serial walk (28 warps per SM), within the cap
@@ -476,6 +478,9 @@ class VectorBiddingSimulation:
         sc.work_counter = s["work_counter"].data_ptr() if self.dynamic_work else None
         sc.serial_ws, sc.serial_ws_bytes = s["serial_ws"].data_ptr(), s["serial_ws"].numel()
         out.episode_profit_cents = _ptr(o.get("episode_profit_cents"))
+        out.episode_reward = _ptr(o.get("episode_reward"))
+        out.episode_count = _ptr(o.get("episode_count"))
+        out.rows = None
         out.flat_obs = _ptr(o.get("flat_obs"))
         if self._detail is not None:
             a.detail.cap = self.detail_cap
@@ -589,8 +594,9 @@ class VectorBiddingSimulation:
                           ("cost_cents", 8), ("revenue_cents", 8), ("episode_profit_cents", 8)):
                 setattr(o, n, off(getattr(bo, n), e0 * K * sz))
             for n, sz in (("reward", 8), ("obs_cum_profit", 8), ("obs_days", 4), ("terminated", 1), ("truncated", 1),
-                          ("remaining_budget", 8)):
+                          ("remaining_budget", 8), ("episode_reward", 8), ("episode_count", 4)):
                 setattr(o, n, off(getattr(bo, n), e0 * sz))
+            o.rows = None
             o.flat_obs = off(bo.flat_obs, e0 * (5 * K + 2) * fb)
             sc, bs = a.scratch, base.scratch
             for n, sz in (("serial_list", 4), ("env_profit", 8), ("env_cost", 8), ("env_done", 4)):
@@ -606,12 +612,19 @@ class VectorBiddingSimulation:
             c.rows_dev = rows_dev.data_ptr() + e0 * row_bytes
             c.rows_host = rows_host.data_ptr() + e0 * row_bytes
             c.stream = streams[i].cuda_stream
-        L6 = (6 * K + 7) // 8 * 8
+        views = self._row_views(rows_host)
+        self._hp = dict(key=key, chunks=chunks, n=n_chunks, bounds=bounds, streams=streams, counters=counters,
+                        rows_dev=rows_dev, rows_host=rows_host, bids_dev=bids_dev, views=views, row_bytes=row_bytes)
+        return self._hp
+
+    def _row_views(self, r: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Strided views of a [E, row_bytes] uint8 row block (layout: adc_host_chunk in the header)."""
+        K = self.num_keywords
         fbytes = 8 if self.obs_dtype == torch.float64 else 4
+        L6 = (6 * K + 7) // 8 * 8
         tail = (L6 + 2 * fbytes * K + 7) // 8 * 8
         u16, fdt_t = torch.uint16, self.obs_dtype
-        r = rows_host
-        views = dict(
+        return dict(
             impressions=r[:, 0:2 * K].view(u16), buyside_clicks=r[:, 2 * K:4 * K].view(u16),
             sellside_conversions=r[:, 4 * K:6 * K].view(u16),
             cost=r[:, L6:L6 + fbytes * K].view(fdt_t), revenue=r[:, L6 + fbytes * K:L6 + 2 * fbytes * K].view(fdt_t),
@@ -619,9 +632,34 @@ class VectorBiddingSimulation:
             cumulative_profit=r[:, tail + 8:tail + 16].view(torch.float64),
             days_passed=r[:, tail + 16:tail + 20].view(torch.int32),
             terminated=r[:, tail + 20], truncated=r[:, tail + 21], count_overflow=r[:, tail + 22])
-        self._hp = dict(key=key, chunks=chunks, n=n_chunks, bounds=bounds, streams=streams, counters=counters,
-                        rows_dev=rows_dev, rows_host=rows_host, bids_dev=bids_dev, views=views, row_bytes=row_bytes)
-        return self._hp
+
+    def step_host_rows(self, bids_host: torch.Tensor):
+        """``step`` for a CPU-side caller, fused: ONE launch reads the pinned HOST bids (UVA) and the
+        warp that finalises an env packs its observation into a compact row (uint16 counts, float
+        money: 14 bytes per unit, layout of ``adc_host_chunk``) straight into pinned HOST memory
+        (``adc_step_out.rows``), so the PCIe traffic of both directions overlaps the auction work and no
+        copy is enqueued.  Returns strided views into the pinned row block, valid until the next
+        call; ``count_overflow[e]`` flags an env with a count above 65535."""
+        assert self._have_keywords, "reset required, need to generate keywords to bid on"
+        E, K = self.num_envs, self.num_keywords
+        assert (isinstance(bids_host, torch.Tensor) and bids_host.is_pinned() and bids_host.is_contiguous()
+                and bids_host.dtype in (torch.float32, torch.float64) and tuple(bids_host.shape) == (E, K)), \
+            "step_host_rows takes a pinned, contiguous float [E, K] tensor"
+        if getattr(self, "_rows_host", None) is None:
+            fdt = _capi.F64 if self.obs_dtype == torch.float64 else _capi.F32
+            self._rows_host = torch.zeros(E, int(self._lib.adc_host_row_bytes(K, fdt)), dtype=torch.uint8).pin_memory()
+            self._rows_views = self._row_views(self._rows_host)
+        a = self._fill_args(bids_host, None, False)
+        a.out.rows = self._rows_host.data_ptr()
+        stream = torch.cuda.current_stream(self.device)
+        try:
+            self._call(self._lib.adc_step_philox, C.byref(a), C.c_void_p(stream.cuda_stream))
+        finally:
+            a.out.rows = None
+        self._step_count += 1
+        self._calls += 1
+        stream.synchronize()
+        return self._rows_views
 
     def step_host_pipelined(self, bids_host: torch.Tensor, n_chunks: int = 4):
         """``step`` for a CPU-side caller: pinned float32 HOST bids in, HOST observations out, through

@@ -56,11 +56,31 @@ UNIT = "keyword-auction-steps/s"
 K_KW, E_ENVS, BID, BUDGET, MAX_DAYS = 100, 4096, 0.75, 100000.0, 60
 SEED = 0x5EED
 B_UNIT = 24  # read bid 4 B + write 3 x int32 + 2 x f32 per (env, keyword, step)
-# dram__bytes_read.sum + dram__bytes_write.sum of one hot-kernel launch on this workload, from the
-# committed `ncu --set full` capture (profiles/r01_flat_kernel_ncu_metrics.csv): the outputs stay in
-# the 126 MB L2 between steps, so DRAM traffic is below the 9.8 MB of algorithmic bytes.
-NCU_DRAM_BYTES_PER_LAUNCH = 1881600 + 5888
-NCU_WARP_INSTR_PER_LAUNCH = 138705777  # smsp__inst_executed.sum of the same capture
+HOT_KERNEL = "adc_flat2_implicit_kernel"
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_flat2_c2_ncu.json")
+
+
+def ncu_capture_of_hot_kernel():
+    """DRAM traffic and warp-instruction count of one hot-kernel launch on the C2 workload, read
+    from the committed summary of the `ncu --set full` capture (profiles/r02_flat2_c2_ncu.json,
+    written by tools/ncu_summary.py from the .ncu-rep).  Returns None -- loudly -- when the capture
+    does not describe what this run launches (other workload shape, or the kernel symbol is not in
+    the loaded library): stale numbers are not reported."""
+    try:
+        d = json.load(open(NCU_SUMMARY))
+    except (OSError, ValueError) as exc:
+        print(f"bench.py: no ncu summary ({exc}); roofline.traffic = null", file=sys.stderr)
+        return None
+    from adcraft_b200 import build as b
+    lib_has = HOT_KERNEL.encode() in open(b.LIB_PATH, "rb").read()
+    same = (d.get("kernel", "").find(HOT_KERNEL) >= 0 and d.get("envs") == E_ENVS and d.get("keywords") == K_KW
+            and d.get("mean_volume") == MEAN_VOLUME and not DRIFT)
+    if not (lib_has and same):
+        print(f"bench.py: the committed ncu capture ({d.get('kernel')}, {d.get('envs')} x {d.get('keywords')}) does "
+              f"not describe this run ({HOT_KERNEL} in library: {lib_has}; {E_ENVS} x {K_KW}); roofline.traffic = null",
+              file=sys.stderr)
+        return None
+    return d
 
 
 MEAN_VOLUME, CVR, DRIFT = 128, 0.8, False
@@ -357,27 +377,30 @@ def run_gpu(args):
     env = VectorBiddingSimulation(
         E_ENVS, num_keywords=K_KW, keywords=table, budget=BUDGET, max_days=MAX_DAYS, device=dev,
         seed=SEED, env_base=rank * E_ENVS, n_lanes=args.n_lanes, obs_dtype=torch.float32,
-        updater_mask=[True] * K_KW if DRIFT else None)
+        updater_mask=[True] * K_KW if DRIFT else None, episode_profit=True)
     env.reset()
     env.budget_alias = bool(args.alias)
     bids = torch.full((E_ENVS, K_KW), BID, dtype=torch.float32, device=dev)
     action = {"keyword_bids": bids}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    metric_acc = torch.zeros(4, dtype=torch.float64, device=dev)  # sum reward, cost, revenue, episodes
+    from adcraft_b200 import metrics as M
+    ideal = M.ideal_profit(env)["ideal"]  # [rows, K] per-step ideal profit (adc_ideal_profit kernel)
+    reduce_every = max(1, min(MAX_DAYS, args.steps))
+    metric = {"vec": None, "reduces": 0}
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def episode_reduce(obs, reward, term):
-        # per-episode metric reduction (the only collective on this path): O(10) doubles
-        metric_acc[0] += reward.sum()
-        metric_acc[1] += obs["cost"].sum(dtype=torch.float64)
-        metric_acc[2] += obs["revenue"].sum(dtype=torch.float64)
-        metric_acc[3] += term.sum()
-        if world > 1:
-            dist.all_reduce(metric_acc)
+    def episode_reduce():
+        # The only collective on this path: per-env AKNCP / NCP over the window (from the kernels'
+        # exact per-keyword profit accumulators, experiment_metrics.py:64-83), summed over ranks:
+        # 8 doubles through NCCL
+        # (rewards and finished episodes are summed per env by the env tail: episode_reward / episode_count)
+        vec = M.episode_summary_vector(env, reduce_every, ideal)
+        metric["vec"] = M.reduce_metrics(vec)
+        metric["reduces"] += 1
 
     if args.replay_only:
         emit({"replay": run_replay_leg(env, table, dev, torch, steps=max(args.steps, 3))})
@@ -430,31 +453,29 @@ def run_gpu(args):
             stops[i].record()
         torch.cuda.synchronize(dev)
         ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops)) / n
-        floor = sim.rival_floor_cents(sbids).view(W * A, K_KW)
         act = {"keyword_bids": sbids.reshape(W * A, K_KW)}
-        for i in range(n):
+        for i in range(n):  # A/B: the rival floor as a torch pass + table instead of in the kernel
             starts[i].record()
-            sim.vec.step(act, floor_cents=floor)
+            sim.vec.step(act, floor_cents=sim.rival_floor_cents(sbids).view(W * A, K_KW))
             stops[i].record()
         torch.cuda.synchronize(dev)
         ms_kernel = sum(a.elapsed_time(b) for a, b in zip(starts, stops)) / n
         winners = (sobs["impressions"] > 0).sum(dim=1)
         emit({"shared_auction": {
-            "worlds": W, "agents": A, "keywords": K_KW, "ms_per_step": ms, "ms_per_step_kernels_only": ms_kernel,
+            "worlds": W, "agents": A, "keywords": K_KW, "ms_per_step": ms, "ms_per_step_floor_in_torch": ms_kernel,
             "bidder_units_per_s": W * A * K_KW / (ms * 1e-3), "auction_units_per_s": W * K_KW / (ms * 1e-3),
             "max_winners_per_auction_unit": int(winners.max()),
-            "note": "timed step includes the rival-floor computation (torch amax passes over the A bids) and one launch "
-                    "over worlds*A bidder rows; bids = 0.50 + 0.05*agent"}})
+            "note": "one launch over worlds*A bidder rows; every unit finds its highest rival among the A bid rows of "
+                    "its world inside the kernel (unit_floor); bids = 0.50 + 0.05*agent"}})
         return 0
 
     # ---- device-timed steps, inputs resident in HBM --------------------------------------
     sampler = ClockSampler(torch, dev) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         obs, reward, term, trunc, _ = env.step(action)
-    if world > 1:  # NCCL connects lazily: establish the all-reduce path before the timed region
-        for _ in range(2):
-            episode_reduce(obs, reward, term)
-        metric_acc.zero_()
+    for _ in range(2):  # NCCL connects lazily: establish the all-reduce path before the timed region
+        episode_reduce()
+    metric["reduces"] = 0
     barrier()
     if sampler is not None:
         sampler.mark()
@@ -467,8 +488,8 @@ def run_gpu(args):
         flush.zero_()  # evict the 126 MB L2 between steps (outside the event pair)
         starts[i].record()
         obs, reward, term, trunc, _ = env.step(action)
-        if world > 1 and (i + 1) % MAX_DAYS == 0:
-            episode_reduce(obs, reward, term)
+        if (i + 1) % reduce_every == 0:
+            episode_reduce()
         stops[i].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -492,27 +513,29 @@ def run_gpu(args):
     ms_per_step = dev_ms / args.steps
 
     # ---- end to end through the public API with HOST buffers ------------------------------
+    # step_host_pipelined = adc_step_host: per chunk of envs H2D copy -> kernels -> compact rows ->
+    # D2H copy on the chunk's stream; returns when the observations are in host memory.
     bids_host = torch.full((E_ENVS, K_KW), BID, dtype=torch.float32).pin_memory()
-    for _ in range(3):
-        env.step_host(bids_host)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        env.step_host(bids_host)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = units_total / float(te.item())
-    h2d, d2h = env.host_bytes_per_step()
-    # same loop with staged copies (cudaMemcpyAsync H2D, step, one D2H) for comparison
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        env.step_host(bids_host, zero_copy=False)
-    barrier()
-    e2e_staged = units_total / (time.perf_counter() - t0)
+
+    def timed_host(fn):
+        for _ in range(3):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return units_total / float(te.item())
+
+    e2e_value = timed_host(lambda: env.step_host_rows(bids_host))
+    h2d = E_ENVS * K_KW * 4
+    d2h = E_ENVS * int(_capi.load().adc_host_row_bytes(K_KW, _capi.F32))
+    e2e_pipelined = timed_host(lambda: env.step_host_pipelined(bids_host, n_chunks=args.host_chunks))
+    e2e_zero_copy = timed_host(lambda: env.step_host(bids_host))
+    e2e_staged = timed_host(lambda: env.step_host(bids_host, zero_copy=False))
 
     if rank != 0:
         if world > 1:
@@ -532,18 +555,21 @@ def run_gpu(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = E_ENVS * K_KW * B_UNIT
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    cap = ncu_capture_of_hot_kernel()
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": NCU_DRAM_BYTES_PER_LAUNCH if E_ENVS == 4096 else None,
-        "kernel": "adc_flat_philox_implicit_kernel", "peak_source": peak_src,
-        "algorithmic_bytes_per_unit": B_UNIT,
-        "issue": {"warp_instructions_per_launch": NCU_WARP_INSTR_PER_LAUNCH if E_ENVS == 4096 and K_KW == 100 else None,
-                  "frac_of_issue_peak": (NCU_WARP_INSTR_PER_LAUNCH / (ms_per_step * 1e-3) / (148 * 4 * 1.965e9)
-                                         if E_ENVS == 4096 and K_KW == 100 else None),
-                  "note": "instruction count from the committed ncu capture; peak = 148 SMs x 4 schedulers x 1965 MHz"},
-        "note": "free-running mode draws ~128 auctions per unit from Philox (half a Philox4x32-10 call + a "
-                "Laplace sampler each): the kernel is instruction-issue-bound, not HBM-bound (profiles/r01_summary.md, "
-                "DESIGN.md); the step = this kernel + a serial-queue kernel that exits when no budget binds",
+        "traffic": cap["dram_bytes"] if cap else None,
+        "kernel": HOT_KERNEL, "peak_source": peak_src, "algorithmic_bytes_per_unit": B_UNIT,
+        "issue": {"warp_instructions_per_launch": cap["warp_instructions"] if cap else None,
+                  "warp_instructions_per_unit": cap["warp_instructions"] / (E_ENVS * K_KW) if cap else None,
+                  "frac_of_issue_peak": (cap["warp_instructions"] / (ms_per_step * 1e-3) / (148 * 4 * 1.965e9)
+                                         if cap else None),
+                  "note": "instruction count read from the committed ncu capture (profiles/r02_flat2_c2_ncu.json); "
+                          "peak = 148 SMs x 4 schedulers x 1965 MHz"},
+        "note": "free-running mode decides every auction by a bit-sliced uniform and draws one price per click and "
+                "one revenue per conversion from Philox: the kernel is instruction-issue-bound, not HBM-bound "
+                "(profiles/r02_summary.md, DESIGN.md); the step = this kernel + a serial-queue kernel that exits "
+                "when no budget binds",
     }
 
     # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------
@@ -558,8 +584,15 @@ def run_gpu(args):
         "config": config_dict(n_gpus),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "how": "step_host: kernels read pinned host bids and write pinned host observations directly "
-                       "(UVA zero-copy, transfer fused into the step); staged-copy variant: %.4g" % e2e_staged},
+                "how": "VectorBiddingSimulation.step_host_rows -> adc_step_philox with adc_step_out.rows in pinned host "
+                       "memory: one launch reads the pinned float32 bids over PCIe (UVA) and the warp that finalises an "
+                       "env writes its compact row (uint16 counts, float32 money: 14 B per unit + 24 B per env) straight "
+                       "into host memory; the call returns after a stream synchronize, rows landed",
+                "other_paths": {f"adc_step_host_{args.host_chunks}_chunks_copy_engine": e2e_pipelined,
+                                "zero_copy_uva_int32_arrays": e2e_zero_copy, "staged_single_copy_int32": e2e_staged}},
+        "collective": {"all_reduces_in_timed_region": metric["reduces"], "every_steps": reduce_every,
+                       "what": "AKNCP / NCP summary vector (8 doubles) from the kernels' per-keyword profit accumulators",
+                       "summary": M.summarize(metric["vec"]) if metric["vec"] is not None else None},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -574,6 +607,121 @@ def run_gpu(args):
     return 0
 
 
+# --------------------------------------------------------------------------------------------
+# C5: large sweep with PPO rollout collection and the NCCL AKNCP / NCP reduce
+# --------------------------------------------------------------------------------------------
+def run_c5(args):
+    """BASELINE.json configs[4]: 10 000 keywords x 131 072 envs per GPU (1M envs on 8), actions from
+    a small MLP policy replica on every rank (Gaussian head, PPO-style rollout collection: actions,
+    log-probabilities, values and rewards are stored per step; observations are consumed in place
+    from the kernel-written flat rows -- 26 GB per step cannot be buffered), and the per-iteration
+    AKNCP / NCP all-reduce over NCCL.  Every step of the timed region = policy forward + sampling +
+    env step + rollout bookkeeping; the iteration ends with the metric reduce inside the region."""
+    import torch
+    import torch.distributed as dist
+    from adcraft_b200 import _capi, metrics as M
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    E, K = args.envs, args.keywords
+    T = max(args.steps, 1)
+    table = workload_table()
+    env = VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=BUDGET, max_days=MAX_DAYS, device=dev,
+                                  seed=SEED, env_base=rank * E, obs_dtype=torch.float32, episode_profit=True,
+                                  flat_obs=True)
+    env.reset()
+    ideal = M.ideal_profit(env)["ideal"]
+    torch.manual_seed(1234)  # the same policy replica on every rank
+    H = 64
+    w1 = (torch.randn(5 * K + 2, H, device=dev) * 0.01)
+    w2 = (torch.randn(H, K, device=dev) * 0.01)
+    wv = (torch.randn(H, 1, device=dev) * 0.01)
+    log_std = torch.full((K,), -1.5, device=dev)
+    buf_logp = torch.empty(T, E, device=dev)
+    buf_val = torch.empty(T, E, device=dev)
+    buf_rew = torch.empty(T, E, device=dev)
+    reward_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    episodes = torch.zeros((), dtype=torch.float64, device=dev)
+    bids = torch.empty(E, K, device=dev)
+    noise = torch.empty(E, K, device=dev)
+    chunk = 8192  # env rows per policy pass: bounds the temporaries
+
+    def policy_and_step(i):
+        flat = env.flat_observation()  # [E, 5K+2], written by the previous step's kernels
+        noise.normal_()
+        for r0 in range(0, E, chunk):
+            x = flat[r0:r0 + chunk]
+            h = torch.tanh(torch.log1p(x.clamp_min(0.0)) @ w1)
+            mu = 0.75 + h @ w2
+            b = bids[r0:r0 + chunk]
+            torch.addcmul(mu, noise[r0:r0 + chunk], log_std.exp(), out=b)
+            buf_logp[i, r0:r0 + chunk] = (-0.5 * noise[r0:r0 + chunk] ** 2 - log_std).sum(1)
+            buf_val[i, r0:r0 + chunk] = (h @ wv).squeeze(1)
+            b.clamp_(min=0.01)
+        obs, reward, term, trunc, _ = env.step({"keyword_bids": bids})
+        buf_rew[i] = reward
+        reward_sum.add_(reward.sum())
+        episodes.add_(term.sum())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 1)):
+            policy_and_step(0)
+        vec = M.reduce_metrics(M.episode_summary_vector(env, max(args.warmup, 1), ideal, reward_sum, episodes))
+        reward_sum.zero_(); episodes.zero_()
+        barrier()
+        lib = _capi.load()
+        lib.adc_launch_count(1)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sim_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(T)]
+        ev0.record()
+        for i in range(T):
+            policy_and_step(i)
+        vec = M.reduce_metrics(M.episode_summary_vector(env, T, ideal, reward_sum, episodes))
+        ev1.record()
+        barrier()
+        # the simulator alone on the same bids (env.step between events)
+        for i in range(min(T, 3)):
+            sim_ev[i][0].record()
+            env.step({"keyword_bids": bids})
+            sim_ev[i][1].record()
+        barrier()
+    launches = int(lib.adc_launch_count(0))
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    sim_ms = float(np.mean([a.elapsed_time(b) for a, b in sim_ev[:min(T, 3)]]))
+    if rank == 0:
+        units = float(E) * K * T * world
+        emit({"metric": METRIC, "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": T,
+              "warmup": max(args.warmup, 1), "ms_per_step": ms / T, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "i32+f32", "data": "synthetic",
+              "config": {"workload": "C5: 10k dense implicit keywords x 131072 envs per GPU, MLP policy rollout collection "
+                                     "+ NCCL AKNCP/NCP reduce per iteration", "envs_per_gpu": E, "keywords": K,
+                         "mean_volume": MEAN_VOLUME, "conversion_rate": CVR, "iteration_steps": T,
+                         "parallelism": f"env-sharded x{world}, policy replica per rank"},
+              "simulator_only": {"ms_per_step": sim_ms, "units_per_s": float(E) * K * world / (sim_ms * 1e-3)},
+              "collective": {"all_reduces_in_timed_region": 1, "summary": M.summarize(vec)},
+              "gpu_launches": launches,
+              "memory_gb_allocated": torch.cuda.max_memory_allocated(dev) / 1e9,
+              "mean_step_reward_per_env": float(buf_rew.mean())})
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     global E_ENVS, BUDGET, K_KW, MEAN_VOLUME, CVR, DRIFT
     ap = argparse.ArgumentParser()
@@ -582,6 +730,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-lanes", type=int, default=0, dest="n_lanes")
+    ap.add_argument("--host-chunks", type=int, default=4, dest="host_chunks",
+                    help="env chunks (= streams) of the pipelined host round trip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-replay", action="store_true", help="skip the tape-driven (replay) leg")
     ap.add_argument("--replay-only", action="store_true", help="profiling aid: run only the replay leg")
@@ -599,7 +749,21 @@ def main():
                     help="experiment only: the reference's default ExplicitKeyword env (config 1) vectorised, K=10")
     ap.add_argument("--agents", type=int, default=1,
                     help="experiment only: bidders per shared auction (BASELINE config 4: --agents 8 --envs 65536)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c3ns", "c4", "c5"],
+                    help="BASELINE.json configs: c2 (default, the metric's config), c3 very sparse 1000 x 16384, c3ns "
+                         "non-stationary sparse, c4 8 bidders per auction x 65536 worlds, c5 10k x 131072 per GPU with "
+                         "policy rollout + metric reduce")
     args = ap.parse_args()
+    if args.config == "c3":
+        args.keywords, args.envs, args.volume, args.cvr = 1000, 16384, 16, 0.1
+    elif args.config == "c3ns":
+        args.keywords, args.envs, args.volume, args.cvr, args.drift = 1000, 16384, 64, 0.1, True
+    elif args.config == "c4":
+        args.agents, args.envs = 8, 65536
+    elif args.config == "c5":
+        args.keywords = 10000
+        if args.envs == 4096:
+            args.envs = 131072
     global _OUT
     _OUT = _claim_stdout()
     E_ENVS = args.envs
@@ -607,6 +771,8 @@ def main():
     K_KW, MEAN_VOLUME, CVR, DRIFT = args.keywords, args.volume, args.cvr, args.drift
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "c5":
+        return run_c5(args)
     return run_gpu(args)
 
 

@@ -121,6 +121,13 @@ typedef struct adc_step_out {
                                  step, added when the env's step is final (the per-keyword profits
                                  AKNCP / NCP are made of, experiment_metrics.py:64-83); the caller
                                  zeroes it at the episode boundaries it cares about */
+    double *episode_reward;   /* [E] optional running sum of the env's rewards (added in the env tail)   */
+    int32_t *episode_count;   /* [E] optional running count of finished episodes (terminated | truncated) */
+    void *rows;               /* optional [E, adc_host_row_bytes] compact observation rows (the layout of
+                                 adc_host_chunk below), packed by the warp that finalises the env.  May be
+                                 HOST memory mapped into the device address space (pinned, UVA): the step
+                                 then delivers its observations to the host while it runs, 14 bytes per
+                                 unit instead of 20, and no copy is enqueued */
     void *flat_obs;           /* optional [E, 5K+2] float_dtype: the reference's flat observation row
                                  (FlatArrayWrapper, wrappers/flat_array.py:44-87; keys sorted like
                                  gymnasium_kw_utils.py:383-390): buyside_clicks[0:K] | cost[K:2K] |

@@ -175,21 +175,24 @@ def test_step_host_pipelined_equals_device_step(K, E, budget, chunks, drift):
     table = kwm.sample_implicit_keywords_from_quantiles(K, rng, {"mean_volume": 64, "conversion_rate": 0.8})
     mk = lambda: VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=budget, device="cuda", seed=4,
                                          max_days=3, updater_mask=[True] * K if drift else None)
-    a, b = mk(), mk()
-    a.reset(); b.reset()
+    a, b, c = mk(), mk(), mk()
+    a.reset(); b.reset(); c.reset()
     for step in range(5):
         bids = torch.from_numpy(np.round(rng.uniform(0.2, 1.5, (E, K)), 2).astype(np.float32)).pin_memory()
         h = a.step_host_pipelined(bids, n_chunks=chunks)
+        # the fused form: rows packed by the kernels straight into pinned host memory (adc_step_out.rows)
+        hr = c.step_host_rows(bids)
         obs, reward, term, trunc, _ = b.step({"keyword_bids": bids.cuda()})
-        for k in ("impressions", "buyside_clicks", "sellside_conversions"):
-            assert torch.equal(h[k].to(torch.int32), obs[k].cpu()), (k, step)
-        for k in ("cost", "revenue"):
-            assert torch.equal(h[k], obs[k].cpu()), (k, step)
-        assert torch.equal(h["reward"], reward.cpu())
-        assert torch.equal(h["cumulative_profit"], obs["cumulative_profit"].cpu())
-        assert torch.equal(h["days_passed"], obs["days_passed"].cpu())
-        assert torch.equal(h["terminated"].bool(), term.cpu()) and torch.equal(h["truncated"].bool(), trunc.cpu())
-        assert int(h["count_overflow"].sum()) == 0
+        for hh in (h, hr):
+            for k in ("impressions", "buyside_clicks", "sellside_conversions"):
+                assert torch.equal(hh[k].to(torch.int32), obs[k].cpu()), (k, step)
+            for k in ("cost", "revenue"):
+                assert torch.equal(hh[k], obs[k].cpu()), (k, step)
+            assert torch.equal(hh["reward"], reward.cpu())
+            assert torch.equal(hh["cumulative_profit"], obs["cumulative_profit"].cpu())
+            assert torch.equal(hh["days_passed"], obs["days_passed"].cpu())
+            assert torch.equal(hh["terminated"].bool(), term.cpu()) and torch.equal(hh["truncated"].bool(), trunc.cpu())
+            assert int(hh["count_overflow"].sum()) == 0
         # the device-side observation of the pipelined env is up to date as well
         assert torch.equal(a._out["impressions"], obs["impressions"])
     assert int(h["impressions"].to(torch.int64).sum()) > 0
