@@ -693,16 +693,33 @@ class VectorBiddingSimulation:
         return hp["views"]
 
     def step_host(self, bids_host: torch.Tensor, budget_host: Optional[torch.Tensor] = None,
-                  zero_copy: bool = True):
+                  zero_copy: bool = True, mode: Optional[str] = None):
         """``step`` with HOST buffers: pinned host bids in, pinned host observations out.
 
-        This is the call a CPU-side RL loop makes; moving the bids to the GPU and the observations
-        back is part of it.  With ``zero_copy`` (default) the transfers are fused into the kernels:
-        the hot kernel reads the bids straight from the pinned host buffer and writes every
-        observation straight into a pinned host block (UVA-mapped), so PCIe traffic overlaps the
-        auction loop batch by batch and no separate copy is enqueued.  ``zero_copy=False`` stages
-        through device memory (one H2D copy, the step, one D2H copy of the contiguous block).
-        Returns a dict of pinned host tensors (valid until the next call)."""
+        ``mode`` picks how the two transfers are made (default ``None``: ``zero_copy`` decides between
+        the first and the last, as in round 1):
+
+        * ``"zero_copy"``  the kernels read the bids from the pinned host buffer and write every
+          observation array (int32 counts, float money) into a pinned host block (UVA): the fastest
+          form for ONE process per host (B200: 1.69e9 units/s on C2);
+        * ``"pipelined"``  ``step_host_pipelined``: chunks of envs on their own streams, copy engines,
+          compact rows (uint16 counts): a third fewer bytes and far fewer transactions through the
+          host memory system -- the fastest form when SEVERAL ranks share one host (8 x B200: 8.0e9
+          units/s, 96 % of what 8 concurrent cudaMemcpyAsync streams of the same rows reach);
+        * ``"rows"``       ``step_host_rows``: compact rows written by the kernels over UVA;
+        * ``"auto"``       "pipelined" when torch.distributed runs more than one rank, else "zero_copy";
+        * ``"staged"``     one H2D copy, the step, one D2H copy of the contiguous int32 block.
+
+        Returns a dict of pinned host tensors (views; valid until the next call).  The compact forms
+        return uint16 counts and a ``count_overflow`` flag per env."""
+        if mode == "auto":
+            import torch.distributed as dist
+            shared = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            mode = "pipelined" if shared else "zero_copy"
+        if mode in ("pipelined", "rows") and budget_host is None and self.kind == kwmod.IMPLICIT:
+            return self.step_host_pipelined(bids_host) if mode == "pipelined" else self.step_host_rows(bids_host)
+        if mode is not None:
+            zero_copy = mode not in ("staged",)
         if not self._host:
             self._host_block = torch.zeros(self._block_bytes, dtype=torch.uint8).pin_memory()
             self._host = self._views(self._host_block)

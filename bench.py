@@ -530,9 +530,11 @@ def run_gpu(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         return units_total / float(te.item())
 
-    e2e_value = timed_host(lambda: env.step_host_rows(bids_host))
+    e2e_value = timed_host(lambda: env.step_host(bids_host, mode="auto"))
+    auto_mode = "pipelined" if world > 1 else "zero_copy"
     h2d = E_ENVS * K_KW * 4
-    d2h = E_ENVS * int(_capi.load().adc_host_row_bytes(K_KW, _capi.F32))
+    d2h = (E_ENVS * int(_capi.load().adc_host_row_bytes(K_KW, _capi.F32)) if world > 1 else env.host_bytes_per_step()[1])
+    e2e_rows = timed_host(lambda: env.step_host_rows(bids_host))
     e2e_pipelined = timed_host(lambda: env.step_host_pipelined(bids_host, n_chunks=args.host_chunks))
     e2e_zero_copy = timed_host(lambda: env.step_host(bids_host))
     e2e_staged = timed_host(lambda: env.step_host(bids_host, zero_copy=False))
@@ -584,12 +586,18 @@ def run_gpu(args):
         "config": config_dict(n_gpus),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "how": "VectorBiddingSimulation.step_host_rows -> adc_step_philox with adc_step_out.rows in pinned host "
-                       "memory: one launch reads the pinned float32 bids over PCIe (UVA) and the warp that finalises an "
-                       "env writes its compact row (uint16 counts, float32 money: 14 B per unit + 24 B per env) straight "
-                       "into host memory; the call returns after a stream synchronize, rows landed",
-                "other_paths": {f"adc_step_host_{args.host_chunks}_chunks_copy_engine": e2e_pipelined,
-                                "zero_copy_uva_int32_arrays": e2e_zero_copy, "staged_single_copy_int32": e2e_staged}},
+                "how": f"VectorBiddingSimulation.step_host(pinned bids, mode='auto') = '{auto_mode}' at {n_gpus} rank(s) per "
+                       "host.  zero_copy: one launch reads the pinned float32 bids and writes the int32 / float32 "
+                       "observation arrays straight into pinned host memory (UVA), 20 B per unit; pipelined "
+                       "(adc_step_host): chunks of envs on their own streams, cudaMemcpyAsync in, kernels, compact rows "
+                       "(uint16 counts + float32 money, 14 B per unit), cudaMemcpyAsync out.  Either way the call "
+                       "returns when the observations are in host memory",
+                "other_paths": {f"pipelined_adc_step_host_{args.host_chunks}_chunks": e2e_pipelined,
+                                "rows_written_over_uva": e2e_rows, "zero_copy_uva_int32_arrays": e2e_zero_copy,
+                                "staged_single_copy_int32": e2e_staged},
+                "host_ceiling": "tools/host_ceiling.py, 8 ranks of plain cudaMemcpyAsync on one box: 101 GB/s aggregate "
+                                "for 8.2 MB int32 blocks (5.05e9 units/s), 138 GB/s for compact rows + bids (7.55e9): the "
+                                "shared host memory system, not the GPUs, bounds e2e at 8 GPUs (profiles/r02_host_ceiling_n8.json)"},
         "collective": {"all_reduces_in_timed_region": metric["reduces"], "every_steps": reduce_every,
                        "what": "AKNCP / NCP summary vector (8 doubles) from the kernels' per-keyword profit accumulators",
                        "summary": M.summarize(metric["vec"]) if metric["vec"] is not None else None},
