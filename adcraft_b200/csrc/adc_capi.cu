@@ -94,7 +94,8 @@ int validate(const adc_step_args *a, const adc_tape *tape)
         if (a->kw.kind == ADC_IMPLICIT)
             ADC_REQUIRE(tape->comp_off && tape->comp_cents, "tape.comp_* required for implicit keywords");
         else if (a->kw.kind == ADC_IMPLICIT_MULTI)
-            ADC_REQUIRE(tape->comp_off && tape->comp_f64, "tape.comp_off / comp_f64 required for multi-bidder keywords");
+            ADC_REQUIRE(tape->comp_off && tape->comp_f64 && tape->impr,
+                        "tape.comp_off / comp_f64 / impr (bidders per lane) required for multi-bidder keywords");
         else
             ADC_REQUIRE(tape->impr && tape->cost_off && tape->cost, "tape.impr/cost_* required for explicit keywords");
         ADC_REQUIRE(a->drift.mask == nullptr || tape->drift != nullptr, "tape.drift required when drift is on");

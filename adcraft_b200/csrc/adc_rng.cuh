@@ -20,7 +20,7 @@
 
 namespace adc {
 
-enum : uint32_t { ST_AUCTION = 0u, ST_UNIT = 1u, ST_REVENUE = 2u, ST_PHANTOM = 3u, ST_IDEAL = 4u, ST_COST = 5u };
+enum : uint32_t { ST_AUCTION = 0u, ST_UNIT = 1u, ST_REVENUE = 2u, ST_PHANTOM = 3u, ST_IDEAL = 4u, ST_COST = 5u, ST_BIDDERS = 6u };
 
 struct PhiloxKey {
     uint32_t k0, k1;
@@ -186,6 +186,17 @@ __device__ __forceinline__ int laplace_cents(uint32_t w0, float loc, float scale
     const float s = __uint_as_float(__float_as_uint(scale) ^ (w0 & 0x80000000u));
     const float x = __fmaf_rn(s, e, loc);
     return __float2int_rn(__fmul_rn(fabsf(x), 100.0f));
+}
+
+// One competitor's bid of the default ImplicitKeyword: signed, un-rounded Laplace(loc, scale)
+// (synthetic_kw_classes.py:670-688).
+__device__ __forceinline__ double laplace_signed(uint32_t w0, float loc, float scale, const float2 *tab = kNeglogTab)
+{
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(a) : "r"(w0));
+    const float e = neglog_norm(a, tab);
+    const float s = __uint_as_float(__float_as_uint(scale) ^ (w0 & 0x80000000u));
+    return (double)__fmaf_rn(s, e, loc);
 }
 
 __device__ __forceinline__ int revenue_cents(uint32_t w, float mean, float sd)

@@ -328,6 +328,9 @@ struct UnitPar {
     double ctr, cvr;
     uint32_t thr_click, thr_conv, thr_impr;
     int floor_cents;  // shared auctions: highest rival bid (INT_MIN when there are no rivals)
+    int multi;        // ADC_IMPLICIT_MULTI: m bidders per lane, signed un-rounded Laplace bids (classes:649-688)
+    int max_bidders;
+    uint32_t thr_part;
     Unit2 u2;         // free-running implicit keywords: thresholds + price sampler (adc_rng.cuh)
     long long volume; // free-running implicit keywords: the day's volume (group masks need it)
 };
@@ -530,6 +533,53 @@ __device__ __forceinline__ LaneOut lane_walk(const Src &src, const adc_tape *tp,
             }
             cur.n_clk += nclk;
         }
+    } else if (p.multi) {
+        // Default ImplicitKeyword (classes:623-688): m ~ Binomial(max_bidders, participation) bidders drawn
+        // ONCE for the lane, every auction's other bids are m signed Laplace draws, cleared by
+        // nth_price_auction(n=2, num_winners=1) (helpers:116-180): with fewer than 3 bidders zeros are
+        // appended, so the clearing price is max(bids..., and 0 when m < 3); win iff bid > that (strict),
+        // cost = that price, un-rounded and possibly negative.
+        int m = 0;
+        if constexpr (Src::kTape) {
+            m = tp->impr[u * ADC_SUBSTEPS + t];  // the lane's bidder count rides in the impr array
+        } else {
+            uint4 w = make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < p.max_bidders; ++i) {
+                if ((i & 3) == 0) w = src.draw(ST_BIDDERS, (uint32_t)kw, (uint32_t)(t * 16 + (i >> 2)));
+                const uint32_t wi = (i & 3) == 0 ? w.x : (i & 3) == 1 ? w.y : (i & 3) == 2 ? w.z : w.w;
+                m += wi <= p.thr_part;
+            }
+        }
+        for (long long a = 0; a < n; ++a) {
+            const long long j = cur.auction + a;
+            double c = 0.0;
+            uint32_t w_click = 0u, w_conv = 0u;
+            if constexpr (Src::kTape) {
+                c = tape_at(tp->comp_f64, tp->comp_off, u, j, __longlong_as_double(0x7FF0000000000000LL), o.overrun);
+                if (m < 1) c = 0.0;
+            } else {
+                uint4 w = src.draw(ST_AUCTION, (uint32_t)kw, (uint32_t)(j * 16));
+                w_click = w.x; w_conv = w.y;
+                for (int i = 0; i < m; ++i) {  // bidder i's word: slot i + 2 of the auction's 64 words
+                    const int sl = i + 2;
+                    if ((sl & 3) == 0) w = src.draw(ST_AUCTION, (uint32_t)kw, (uint32_t)(j * 16 + (sl >> 2)));
+                    const uint32_t wi = (sl & 3) == 0 ? w.x : (sl & 3) == 1 ? w.y : (sl & 3) == 2 ? w.z : w.w;
+                    const double x = laplace_signed(wi, p.loc, p.scale);
+                    c = i == 0 ? x : (x > c ? x : c);
+                }
+            }
+            if (m < 3 && !(c > 0.0)) c = 0.0;  // zero padding of the short auction (helpers:156-161)
+            if (p.bid > c) {
+                bool clicked;
+                if constexpr (Src::kTape)
+                    clicked = tape_at(tp->u_click, tp->click_off, u, cur.n_click + slots, 2.0, o.overrun) <= p.ctr;
+                else
+                    clicked = w_click <= p.thr_click;
+                on_slot(c, 0, clicked, w_conv);
+                ++slots;
+                ++o.I;
+            }
+        }
     } else {
         if constexpr (Src::kTape) {
             const int I = tp->impr[u * ADC_SUBSTEPS + t];
@@ -590,9 +640,15 @@ __device__ __forceinline__ UnitPar load_unit_par(const adc_step_args &a, int e, 
     p.thr_impr = 0u;
     p.floor_cents = unit_floor(a, e, k, p.bid_cents);
     p.volume = 0;
-    if (a.kw.kind == ADC_EXPLICIT)
+    p.multi = 0; p.max_bidders = 0; p.thr_part = 0u;
+    if (a.kw.kind == ADC_EXPLICIT) {
         p.thr_impr = prob_threshold(threshold_sigmoid(p.bid, a.kw.impression_thresh, a.kw.p1[pi], a.kw.p2[pi]));
-    else if (free_running)
+    } else if (a.kw.kind == ADC_IMPLICIT_MULTI) {
+        p.multi = 1;
+        const double mb = a.kw.max_bidders[pi];
+        p.max_bidders = mb > 0.0 ? (mb < 62.0 ? (int)mb : 62) : 0;  // 2 + 15 x 4 bid words per auction
+        p.thr_part = prob_threshold(clampd(a.kw.participation[pi], 0.0, 1.0));  // probify (classes:663)
+    } else if (free_running)
         p.u2 = unit2_make(a.kw.p1[pi], a.kw.p2[pi], p.ctr, p.cvr, p.win_cents);
     return p;
 }
@@ -649,8 +705,8 @@ __device__ __forceinline__ int unit_done(const adc_step_args &a, int e, long lon
         (long long)atomicExch(reinterpret_cast<unsigned long long *>(a.scratch.env_cost + e), 0ull);
     const double budget = step_budget(a, e);
     double reward, spend;
-    if (a.kw.kind == ADC_EXPLICIT) {
-        // un-rounded explicit costs: sum the per-unit f64 results in keyword order (env:222)
+    if (a.kw.kind != ADC_IMPLICIT) {
+        // un-rounded costs (explicit / multi-bidder keywords): sum the per-unit f64 results in keyword order (env:222)
         reward = 0.0;
         spend = 0.0;
         const int K = a.kw.K;
@@ -1773,7 +1829,7 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
     const int K = a.kw.K;
     const int count = a.scratch.serial_count[a.parity & 1u];
     const SerCounts acc = ser_counts(a);
-    const bool explicit_kw = a.kw.kind == ADC_EXPLICIT;
+    const bool explicit_kw = a.kw.kind != ADC_IMPLICIT;  // un-rounded f64 costs (explicit / multi-bidder keywords)
     const int stride = gridDim.x * blockDim.x;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += stride) {
         const int e = a.scratch.serial_list[idx];
@@ -1827,7 +1883,7 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
                 cur.n_rev = acc.S[u];
                 cur.n_cost = acc.I[u];
                 cur.n_click = acc.I[u];
-                if (explicit_kw) {
+                if (a.kw.kind == ADC_EXPLICIT) {
                     if constexpr (Src::kTape) {  // one slot per impression, or one phantom slot
                         int s = 0;
                         for (int tt = 0; tt < t; ++tt) {
@@ -2346,7 +2402,7 @@ static int64_t grid_for(K kernel, int block, int64_t work_items)
 
 cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream_t s, int64_t *launches)
 {
-    const bool explicit_kw = a.kw.kind == ADC_EXPLICIT;
+    const bool explicit_kw = a.kw.kind != ADC_IMPLICIT;  // thread-per-unit kernels, un-rounded f64 costs
     const int64_t total = (int64_t)a.E * a.kw.K;
     cudaError_t err = cudaSuccess;
     adc_tape t0 = {};

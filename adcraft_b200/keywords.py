@@ -23,7 +23,7 @@ from typing import Dict, Optional
 
 import numpy as np
 
-IMPLICIT, EXPLICIT = 0, 1
+IMPLICIT, EXPLICIT, IMPLICIT_MULTI = 0, 1, 2
 PARAM_NAMES = ("vol_mean", "vol_std", "p1", "p2", "ctr", "cvr", "rev_mean", "rev_std")
 
 # experiment_quantiles.py:16-25
@@ -50,12 +50,22 @@ class KeywordTable:
     rev_mean: np.ndarray
     rev_std: np.ndarray
     impression_thresh: float = 0.05  # gymnasium_kw_utils.py:81
+    # IMPLICIT_MULTI (the class-default ImplicitKeyword, synthetic_kw_classes.py:649-688): bidders per
+    # lane ~ Binomial(max_bidders, participation); p1 / p2 are the SIGNED Laplace's loc / scale
+    max_bidders: Optional[np.ndarray] = None
+    participation: Optional[np.ndarray] = None
 
     def __post_init__(self):
         for n in PARAM_NAMES:
             setattr(self, n, np.ascontiguousarray(getattr(self, n), dtype=np.float64))
         shapes = {getattr(self, n).shape for n in PARAM_NAMES}
         assert len(shapes) == 1, f"inconsistent keyword parameter shapes: {shapes}"
+        if self.kind == IMPLICIT_MULTI:
+            shape = self.vol_mean.shape
+            mb = 30.0 if self.max_bidders is None else self.max_bidders      # classes:659-662
+            pr = 3.0 / 5.0 if self.participation is None else self.participation  # classes:663
+            self.max_bidders = np.ascontiguousarray(np.broadcast_to(np.asarray(mb, np.float64), shape)).copy()
+            self.participation = np.ascontiguousarray(np.broadcast_to(np.asarray(pr, np.float64), shape)).copy()
 
     @property
     def K(self) -> int:
@@ -74,7 +84,9 @@ class KeywordTable:
         if not self.per_env:
             return self
         return KeywordTable(self.kind, *[getattr(self, n)[e] for n in PARAM_NAMES],
-                            impression_thresh=self.impression_thresh)
+                            impression_thresh=self.impression_thresh,
+                            max_bidders=None if self.max_bidders is None else self.max_bidders[e],
+                            participation=None if self.participation is None else self.participation[e])
 
     def describe(self, e: int = 0) -> str:
         """``repr_all_params`` (gymnasium_kw_utils.py:352-380) for env e."""

@@ -150,12 +150,15 @@ class DeviceTape:
         click_off, u_click = cat_csr("click_off", "u_click", np.float64)
         conv_off, u_conv = cat_csr("conv_off", "u_conv", np.float64)
         rev_off, rev = cat_csr("rev_off", "rev_cents", np.int32)
-        impr = cost_off = cost = drift = None
+        impr = cost_off = cost = drift = comp_f64 = None
         if getattr(t0, "impr", None) is not None:
             impr = torch.from_numpy(np.stack([np.asarray(t.impr, np.int32) for t in env_tapes])).to(device)
-            cost_off, cost = cat_csr("cost_off", "cost", np.float64)
+            if getattr(t0, "cost", None) is not None:
+                cost_off, cost = cat_csr("cost_off", "cost", np.float64)
+        if getattr(t0, "comp_f64", None) is not None:  # multi-bidder keywords: highest bid per auction
+            _, comp_f64 = cat_csr("comp_off", "comp_f64", np.float64)
         if getattr(t0, "drift", None) is not None:
             drift = torch.from_numpy(np.stack([np.asarray(t.drift, np.float64) for t in env_tapes])).to(device)
         tape = DeviceTape(volume, comp_off, comp, click_off, u_click, conv_off, u_conv, rev_off, rev,
-                          impr, cost_off, cost, drift)
-        return tape.pack() if pack and has_comp else tape
+                          impr, cost_off, cost, drift, comp_f64=comp_f64)
+        return tape.pack() if pack and has_comp and comp_f64 is None else tape

@@ -261,6 +261,13 @@ class VectorBiddingSimulation:
             if a.ndim == 2:
                 assert a.shape == (E, K), f"{name}: expected {(E, K)}, got {a.shape}"
             cols[name] = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        for name in ("max_bidders", "participation"):  # the class-default ImplicitKeyword's bidder model
+            a = getattr(table, name, None)
+            if a is not None:
+                a = np.asarray(a, dtype=np.float64)
+                if per_env and a.ndim == 1:
+                    a = np.broadcast_to(a, (E, K))
+                cols[name] = torch.from_numpy(np.ascontiguousarray(a).copy()).to(self.device)
         self._kw_dev = cols
         self._kw_stride = K if per_env else 0
         self.keywords = table

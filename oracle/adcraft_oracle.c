@@ -39,7 +39,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 }
 
 /* counter layout: c0 = index, c1 = step, c2 = stream<<28 | agent<<20 | kw, c3 = env */
-enum { ST_AUCTION = 0, ST_UNIT = 1, ST_REVENUE = 2, ST_PHANTOM = 3, ST_IDEAL = 4, ST_COST = 5 };
+enum { ST_AUCTION = 0, ST_UNIT = 1, ST_REVENUE = 2, ST_PHANTOM = 3, ST_IDEAL = 4, ST_COST = 5, ST_BIDDERS = 6 };
 
 static void draw4(uint64_t seed, uint32_t env, uint32_t step, uint32_t agent, uint32_t kw,
                   uint32_t stream, uint32_t idx, uint32_t out[4])
@@ -356,7 +356,8 @@ static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, dou
 {
     /* One call of simulate_epoch_of_bidding (bidding_simulation.py:44-120). */
     const double bid = (double)bid_cents / 100.0;
-    const int explicit_kw = kw->kind == ORC_EXPLICIT;
+    const int multi_kw = kw->kind == ORC_IMPLICIT_MULTI;
+    const int explicit_kw = kw->kind != ORC_IMPLICIT; /* un-rounded f64 costs: explicit and multi-bidder keywords */
     double stack_cost[256]; uint8_t stack_clicked[256]; uint32_t stack_aw[256];
     int64_t cap = n > 0 ? n : 1;
     double *slot_cost = stack_cost; uint8_t *clicked = stack_clicked; uint32_t *slot_w2 = stack_aw;
@@ -410,6 +411,52 @@ static int lane_run(const orc_keywords *kw, int k, int t, int32_t bid_cents, dou
                 if (src->mode == 1 && rec) {
                     int64_t pos = (int64_t)k * rec->cap_per_kw + cur->n_click + slots;
                     if (cur->n_click + slots < rec->cap_per_kw) rec->u_click[pos] = click_bit ? 0.0 : 1.0;
+                }
+                ++slots; ++I;
+            }
+        }
+    } else if (multi_kw) {
+        /* default ImplicitKeyword (classes:623-688): bidders once per lane, m signed Laplace bids per
+         * auction, nth_price_auction(n=2, num_winners=1) incl. zero padding for m < 3 (helpers:116-180) */
+        int m = 0;
+        if (src->mode == 0) {
+            m = tp->impr[k * ORC_SUBSTEPS + t];
+        } else {
+            int mb = kw->max_bidders[k] > 0.0 ? (kw->max_bidders[k] < 62.0 ? (int)kw->max_bidders[k] : 62) : 0;
+            uint32_t thr_part = orc_prob_threshold(clampd(kw->participation[k], 0.0, 1.0));
+            for (int i = 0; i < mb; ++i) {
+                if ((i & 3) == 0) draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_BIDDERS, (uint32_t)(t * 16 + (i >> 2)), w);
+                m += w[i & 3] <= thr_part;
+            }
+            if (rec) rec->impr[k * ORC_SUBSTEPS + t] = m;
+        }
+        for (int64_t a = 0; a < n; ++a) {
+            int64_t j = cur->auction + a;
+            double c = 0.0;
+            uint32_t w_click = 0, w_conv = 0;
+            if (src->mode == 0) {
+                c = m < 1 ? 0.0 : tp->comp_f64[tp->comp_off[k] + j];
+            } else {
+                draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_AUCTION, (uint32_t)(j * 16), w);
+                w_click = w[0]; w_conv = w[1];
+                for (int i = 0; i < m; ++i) {
+                    int sl = i + 2;
+                    if ((sl & 3) == 0) draw4(src->seed, src->env, src->step, src->agent, (uint32_t)k, ST_AUCTION, (uint32_t)(j * 16 + (sl >> 2)), w);
+                    uint32_t wi = w[sl & 3];
+                    float e = orc_neglog_u31(wi & 0x7FFFFFFFu);
+                    double x = (double)fmaf((wi >> 31) ? -(float)kw->p2[k] : (float)kw->p2[k], e, (float)kw->p1[k]);
+                    c = i == 0 ? x : (x > c ? x : c);
+                }
+                if (rec && j < rec->cap_per_kw) { rec->comp_f64[(int64_t)k * rec->cap_per_kw + j] = c; rec->n_comp[k] = (int32_t)(j + 1); }
+            }
+            if (m < 3 && !(c > 0.0)) c = 0.0; /* zero padding of the short auction */
+            if (bid > c) {
+                slot_cost[slots] = c;
+                clicked[slots] = 0; slot_w2[slots] = w_conv;
+                if (src->mode == 1) {
+                    clicked[slots] = (uint8_t)(w_click <= thr_click) | 0x80;
+                    if (rec && cur->n_click + slots < rec->cap_per_kw)
+                        rec->u_click[(int64_t)k * rec->cap_per_kw + cur->n_click + slots] = (double)w_click * 2.3283064365386963e-10;
                 }
                 ++slots; ++I;
             }
@@ -698,6 +745,8 @@ int orc_batch_step(orc_batch *b, const double *bids, int32_t *impressions, int32
         kw.vol_mean = b->vol_mean + po; kw.vol_std = b->vol_std + po;
         kw.p1 = b->p1 + po; kw.p2 = b->p2 + po; kw.ctr = b->ctr + po; kw.cvr = b->cvr + po;
         kw.rev_mean = b->rev_mean + po; kw.rev_std = b->rev_std + po;
+        kw.max_bidders = b->max_bidders ? b->max_bidders + po : 0;
+        kw.participation = b->participation ? b->participation + po : 0;
         kw.impression_thresh = b->impression_thresh;
         int32_t *bc = (int32_t *)malloc(sizeof(int32_t) * K);
         double *profit = (double *)malloc(sizeof(double) * K);

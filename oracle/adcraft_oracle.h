@@ -21,7 +21,10 @@ extern "C" {
 
 #define ORC_SUBSTEPS 24 /* bidding_simulation.py:213 */
 
-enum { ORC_IMPLICIT = 0, ORC_EXPLICIT = 1 };
+/* ORC_IMPLICIT_MULTI: the default ImplicitKeyword (synthetic_kw_classes.py:649-688): m ~ Binomial(
+ * max_bidders, participation) bidders per lane, signed un-rounded Laplace(p1, p2) bids, cleared by
+ * nth_price_auction(n=2, num_winners=1) with its zero padding for m < 3 (helpers:116-180). */
+enum { ORC_IMPLICIT = 0, ORC_EXPLICIT = 1, ORC_IMPLICIT_MULTI = 2 };
 
 /* Keyword parameters, SoA over K keywords of ONE env (gymnasium_kw_utils.py:20-28):
  * ((vol_mean, vol_std), loc|intercept, scale|slope, bctr, sctr, mean_rev, std_rev). */
@@ -33,6 +36,7 @@ typedef struct {
     const double *p2; /* implicit: Laplace scale    | explicit: impression_slope         */
     const double *ctr, *cvr;
     const double *rev_mean, *rev_std;
+    const double *max_bidders, *participation; /* ORC_IMPLICIT_MULTI only (classes:659-663) */
     double impression_thresh; /* explicit only (0.05, gymnasium_kw_utils.py:81) */
 } orc_keywords;
 
@@ -44,8 +48,9 @@ typedef struct {
     const int64_t *click_off; const double  *u_click;    /* per click slot            */
     const int64_t *conv_off;  const double  *u_conv;     /* per accepted click        */
     const int64_t *rev_off;   const int32_t *rev_cents;  /* per conversion            */
-    const int32_t *impr;                             /* explicit: [K*24] binomial I  */
+    const int32_t *impr;                             /* explicit: [K*24] binomial I; multi: [K*24] bidders m */
     const int64_t *cost_off;  const double  *cost;       /* explicit: per impression  */
+    const double *comp_f64;   /* multi (shares comp_off): per auction the highest of the m bids (0 when m = 0) */
 } orc_tape;
 
 /* Optional recorder: the oracle appends what it consumed (same layout as orc_tape,
@@ -55,6 +60,7 @@ typedef struct {
     int64_t cap_per_kw;                           /* capacity of each per-kw stream   */
     int32_t *comp_cents; double *u_click; double *u_conv; int32_t *rev_cents;
     int32_t *impr; double *cost;                  /* impr: [K*24]                      */
+    double *comp_f64;                             /* multi: per auction highest bid    */
     int32_t *n_comp, *n_click, *n_conv, *n_rev, *n_cost; /* [K] counts written         */
 } orc_record;
 
@@ -115,6 +121,7 @@ typedef struct {
     int32_t kind, E, K;
     int64_t param_env_stride;     /* 0: keyword set shared by all envs, K: per-env sets */
     double *vol_mean, *vol_std, *p1, *p2, *ctr, *cvr, *rev_mean, *rev_std;
+    double *max_bidders, *participation; /* ORC_IMPLICIT_MULTI, else NULL */
     double impression_thresh;
     const uint8_t *drift_mask;    /* [K] or NULL */
     double drift_mag[3];

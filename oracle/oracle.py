@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _BUILD = os.path.join(_HERE, "_build")
 SUBSTEPS = 24
-IMPLICIT, EXPLICIT = 0, 1
+IMPLICIT, EXPLICIT, IMPLICIT_MULTI = 0, 1, 2
 
 
 def build(force: bool = False) -> None:
@@ -91,19 +91,20 @@ def lib() -> C.CDLL:
 # ----------------------------------------------------------------------------- #
 class _Keywords(C.Structure):
     _fields_ = [("kind", C.c_int32), ("K", C.c_int32)] + [
-        (n, C.c_void_p) for n in ("vol_mean", "vol_std", "p1", "p2", "ctr", "cvr", "rev_mean", "rev_std")
+        (n, C.c_void_p) for n in ("vol_mean", "vol_std", "p1", "p2", "ctr", "cvr", "rev_mean", "rev_std",
+                                  "max_bidders", "participation")
     ] + [("impression_thresh", C.c_double)]
 
 
 class _Tape(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "volume", "comp_off", "comp_cents", "click_off", "u_click", "conv_off", "u_conv",
-        "rev_off", "rev_cents", "impr", "cost_off", "cost")]
+        "rev_off", "rev_cents", "impr", "cost_off", "cost", "comp_f64")]
 
 
 class _Record(C.Structure):
     _fields_ = [("volume", C.c_void_p), ("cap_per_kw", C.c_int64)] + [
-        (n, C.c_void_p) for n in ("comp_cents", "u_click", "u_conv", "rev_cents", "impr", "cost",
+        (n, C.c_void_p) for n in ("comp_cents", "u_click", "u_conv", "rev_cents", "impr", "cost", "comp_f64",
                                   "n_comp", "n_click", "n_conv", "n_rev", "n_cost")]
 
 
@@ -117,7 +118,8 @@ class _Result(C.Structure):
 class _Batch(C.Structure):
     _fields_ = [("kind", C.c_int32), ("E", C.c_int32), ("K", C.c_int32),
                 ("param_env_stride", C.c_int64)] + [
-        (n, C.c_void_p) for n in ("vol_mean", "vol_std", "p1", "p2", "ctr", "cvr", "rev_mean", "rev_std")
+        (n, C.c_void_p) for n in ("vol_mean", "vol_std", "p1", "p2", "ctr", "cvr", "rev_mean", "rev_std",
+                                  "max_bidders", "participation")
     ] + [("impression_thresh", C.c_double), ("drift_mask", C.c_void_p),
          ("drift_mag", C.c_double * 3), ("budget", C.c_void_p), ("cum_profit", C.c_void_p),
          ("day", C.c_void_p), ("max_days", C.c_int32), ("loss_threshold", C.c_double),
@@ -145,10 +147,15 @@ class KeywordSet:
     rev_mean: np.ndarray
     rev_std: np.ndarray
     impression_thresh: float = 0.05
+    max_bidders: Optional[np.ndarray] = None     # IMPLICIT_MULTI only (classes:659-662)
+    participation: Optional[np.ndarray] = None   # IMPLICIT_MULTI only (classes:663)
 
     def __post_init__(self):
         for n in PARAM_NAMES:
             setattr(self, n, np.ascontiguousarray(getattr(self, n), dtype=np.float64))
+        for n in ("max_bidders", "participation"):
+            if getattr(self, n) is not None:
+                setattr(self, n, np.ascontiguousarray(getattr(self, n), dtype=np.float64))
 
     @property
     def K(self) -> int:
@@ -159,12 +166,15 @@ class KeywordSet:
         s.kind, s.K = self.kind, self.K
         for n in PARAM_NAMES:
             setattr(s, n, getattr(self, n).ctypes.data)
+        s.max_bidders, s.participation = _p(self.max_bidders), _p(self.participation)
         s.impression_thresh = self.impression_thresh
         return s
 
     def copy(self) -> "KeywordSet":
         return KeywordSet(self.kind, *[getattr(self, n).copy() for n in PARAM_NAMES],
-                          impression_thresh=self.impression_thresh)
+                          impression_thresh=self.impression_thresh,
+                          max_bidders=None if self.max_bidders is None else self.max_bidders.copy(),
+                          participation=None if self.participation is None else self.participation.copy())
 
 
 @dataclass
@@ -183,6 +193,7 @@ class Tape:
     cost_off: Optional[np.ndarray] = None
     cost: Optional[np.ndarray] = None
     drift: Optional[np.ndarray] = None      # [3,K] coefficients (vol, ctr, cvr)
+    comp_f64: Optional[np.ndarray] = None   # multi-bidder keywords: highest bid per auction (shares comp_off)
 
     def normalise(self) -> "Tape":
         self.volume = np.ascontiguousarray(self.volume, np.int32)
@@ -194,7 +205,7 @@ class Tape:
             v = getattr(self, n)
             if v is not None:
                 setattr(self, n, np.ascontiguousarray(v, np.int32))
-        for n in ("u_click", "u_conv", "cost", "drift"):
+        for n in ("u_click", "u_conv", "cost", "drift", "comp_f64"):
             v = getattr(self, n)
             if v is not None:
                 setattr(self, n, np.ascontiguousarray(v, np.float64))
@@ -276,7 +287,7 @@ def step_philox(kw: KeywordSet, bid_cents, budget: float, seed: int, env_id: int
             volume=np.zeros(K, np.int32), comp_cents=np.zeros((K, cap), np.int32),
             u_click=np.zeros((K, cap)), u_conv=np.zeros((K, cap)),
             rev_cents=np.zeros((K, cap), np.int32), impr=np.zeros((K, SUBSTEPS), np.int32),
-            cost=np.zeros((K, cap)),
+            cost=np.zeros((K, cap)), comp_f64=np.zeros((K, cap)),
             n_comp=np.zeros(K, np.int32), n_click=np.zeros(K, np.int32),
             n_conv=np.zeros(K, np.int32), n_rev=np.zeros(K, np.int32), n_cost=np.zeros(K, np.int32))
         rec = _Record()
@@ -303,6 +314,9 @@ def step_philox(kw: KeywordSet, bid_cents, budget: float, seed: int, env_id: int
             [bufs["rev_cents"][k, :bufs["n_rev"][k]] for k in range(K)],
             impr=bufs["impr"] if kw.kind == EXPLICIT else None,
             cost=[bufs["cost"][k, :bufs["n_cost"][k]] for k in range(K)] if kw.kind == EXPLICIT else None)
+        if kw.kind == IMPLICIT_MULTI:  # bidders per lane ride in `impr`, the auctions' highest bids in comp_f64
+            tape.impr = bufs["impr"].copy()
+            tape.comp_f64 = np.concatenate([bufs["comp_f64"][k, :bufs["n_comp"][k]] for k in range(K)] + [np.zeros(0)])
         out["tape"] = tape
     return out
 
@@ -382,6 +396,13 @@ class BatchOracle:
         b.param_env_stride = K if per_env else 0
         for n in PARAM_NAMES:
             setattr(b, n, self.p[n].ctypes.data)
+        for n in ("max_bidders", "participation"):  # IMPLICIT_MULTI keywords
+            if params.get(n) is not None:
+                a = np.asarray(params[n], np.float64)
+                if per_env and a.ndim == 1:
+                    a = np.broadcast_to(a, (E, K))
+                self.p[n] = np.ascontiguousarray(a).copy()
+                setattr(b, n, self.p[n].ctypes.data)
         b.impression_thresh = impression_thresh
         b.drift_mask = _p(self.mask)
         b.drift_mag = (C.c_double * 3)(*drift_mag)

@@ -17,7 +17,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from . import ref_harness as rh
-from .oracle import EXPLICIT, IMPLICIT, SUBSTEPS, KeywordSet, Tape
+from .oracle import EXPLICIT, IMPLICIT, IMPLICIT_MULTI, SUBSTEPS, KeywordSet, Tape
 
 
 def _cents(x) -> np.ndarray:
@@ -77,6 +77,12 @@ def _collect(env, K, obs, reward, term, trunc, info, spy) -> Dict[str, object]:
 def keywordset_from_env(env) -> KeywordSet:
     """Current (possibly drifted) parameters of a reference env as SoA columns."""
     ref = rh.load_reference()
+    if getattr(env, "_adc_multi", None) is not None:
+        kw = env._adc_multi.copy()
+        kw.ctr = np.array([float(k.buyside_ctr) for k in env.keywords])
+        kw.cvr = np.array([float(k.sellside_paid_ctr) for k in env.keywords])
+        kw.vol_mean = np.array([float(p[0][0]) for p in env.keyword_params])
+        return kw
     explicit = isinstance(env.keywords[0], ref["classes"].ExplicitKeyword)
     kp = env.keyword_params
     cols = dict(
@@ -95,6 +101,7 @@ def record_step(env, action) -> Dict[str, object]:
     shim = ref["shim"]
     K = env.num_keywords
     explicit = isinstance(env.keywords[0], ref["classes"].ExplicitKeyword)
+    multi = getattr(env, "_adc_multi", None) is not None  # built by build_multi_env below
     kw_before = keywordset_from_env(env)
     # env:197-199 -- read BEFORE the step: an ndarray budget is mutated in place by the lanes
     budget_in = action.get("budget", env.budget)
@@ -124,6 +131,7 @@ def record_step(env, action) -> Dict[str, object]:
     ucv = [[] for _ in range(K)]
     rev = [[] for _ in range(K)]
     cost = [[] for _ in range(K)]
+    compf = [[] for _ in range(K)]
     impr = np.zeros((K, SUBSTEPS), np.int32)
     lane = 0
     while pos < len(ev) and ev[pos][0] != "uniform":
@@ -136,6 +144,16 @@ def record_step(env, action) -> Dict[str, object]:
                 name, _a, val = ev[pos]; pos += 1
                 assert name == "rust.cost_create", name
                 cost[k].extend(np.asarray(val, np.float64).ravel().tolist())
+        elif multi:
+            name, _a, val = ev[pos]; pos += 1
+            assert name == "binomial", name
+            m = int(val)
+            impr[k, t] = m  # the lane's bidder count rides in `impr`
+            name, _a, val = ev[pos]; pos += 1
+            assert name == "laplace", name
+            val = np.asarray(val, np.float64)  # [m, n]: signed, un-rounded (classes:683-686)
+            compf[k].extend((val.max(axis=0) if m > 0 else np.zeros(val.shape[1])).tolist())
+            comp[k].extend([0] * val.shape[1])
         else:
             name, _a, val = ev[pos]; pos += 1
             assert name == "laplace", name
@@ -163,6 +181,9 @@ def record_step(env, action) -> Dict[str, object]:
     assert pos == len(ev)
     tape = Tape.from_lists(volume, comp, ucl, ucv, rev,
                            impr=impr if explicit else None, cost=cost if explicit else None, drift=drift)
+    if multi:
+        tape.impr = impr
+        tape.comp_f64 = np.asarray([x for row in compf for x in row], np.float64)
     out["tape"] = tape
     out["kw_before"] = kw_before
     out["kw_after"] = keywordset_from_env(env)
@@ -199,6 +220,39 @@ class _ShimTapeSource:
         return self.tape.cost[a:a + n]
 
 
+def multi_keyword(kw: KeywordSet, k: int, rng):
+    """The reference's class-default ImplicitKeyword (synthetic_kw_classes.py:578-688): bidders ~
+    Binomial(max_bidders, participation) per lane, signed Laplace(bid_loc, bid_scale) bids -- only the
+    parameters are given, the two distributions are the class's own defaults."""
+    ref = rh.load_reference()
+    helpers = ref["helpers"]
+    vol = (kw.vol_mean[k], kw.vol_std[k])
+    key = ref["classes"].ImplicitKeyword({
+        "rng": rng, "max_bidders": int(kw.max_bidders[k]), "participation_rate": float(kw.participation[k]),
+        "bid_loc": float(kw.p1[k]), "bid_scale": float(kw.p2[k]),
+        "sellside_paid_ctr": float(kw.cvr[k]), "buyside_ctr": float(kw.ctr[k]),
+        "volume_sampler": helpers.nonneg_int_normal_sampler(rng, the_mean=vol[0], std=vol[1]),
+        "reward_distribution_sampler": helpers.rev_normal(float(kw.rev_mean[k]), std_dev=float(kw.rev_std[k]), rng=rng),
+    }, verbose=False)
+    return key, (vol, kw.p1[k], kw.p2[k], kw.ctr[k], kw.cvr[k], kw.rev_mean[k], kw.rev_std[k])
+
+
+def build_multi_env(kw: KeywordSet, seed: int, *, budget=1000.0, max_days=60):
+    """A reference BiddingSimulation of class-default ImplicitKeywords on ONE RecordingRNG (record mode)."""
+    ref = rh.load_reference()
+    env = ref["env"].BiddingSimulation(num_keywords=kw.K, budget=budget, max_days=max_days)
+    env._np_random = rh.RecordingRNG(np.random.PCG64(np.random.SeedSequence(seed)))
+    kws, params = [], []
+    for k in range(kw.K):
+        key, p = multi_keyword(kw, k, env._np_random)
+        kws.append(key); params.append(list(p))
+    env.keywords, env.keyword_params = kws, params
+    env._adc_multi = kw.copy()
+    env._have_keywords = True
+    env.current_day, env.cumulative_profit = 0, 0.0
+    return env
+
+
 def build_replay_env(kw: KeywordSet, *, budget=1000.0, max_days=60, loss_threshold=10000.0,
                      drift_mask=None, drift_mag=(0.03, 0.03, 0.03), cum_profit=0.0, day=0):
     """A reference BiddingSimulation whose keywords draw from TapeRNGs."""
@@ -217,11 +271,15 @@ def build_replay_env(kw: KeywordSet, *, budget=1000.0, max_days=60, loss_thresho
         if kw.kind == IMPLICIT:
             key, p = utils.generate_implicit_keyword_from_params(
                 vol, kw.p1[k], kw.p2[k], kw.ctr[k], kw.cvr[k], kw.rev_mean[k], kw.rev_std[k], r)
+        elif kw.kind == IMPLICIT_MULTI:
+            key, p = multi_keyword(kw, k, r)
         else:
             key, p = utils.generate_keyword_from_params(
                 vol, kw.p1[k], kw.p2[k], kw.ctr[k], kw.cvr[k], kw.rev_mean[k], kw.rev_std[k], r)
         rngs.append(r); kws.append(key); params.append(list(p))
     env.keywords, env.keyword_params = kws, params
+    if kw.kind == IMPLICIT_MULTI:
+        env._adc_multi = kw.copy()
     env._have_keywords = True
     env.current_day = day
     env.cumulative_profit = cum_profit
@@ -235,7 +293,15 @@ def replay_step(env, bids_dollars, budget, tape: Tape) -> Dict[str, object]:
     shim = ref["shim"]
     K = env.num_keywords
     tape.normalise()
+    multi = getattr(env, "_adc_multi", None) is not None
     for k, r in enumerate(env._tape_rngs):
+        if multi:
+            r.bidders = np.asarray(tape.impr[k], np.int64)  # lanes of keyword k run in sub-step order
+            r.load(tape.comp_f64[tape.comp_off[k]:tape.comp_off[k + 1]],
+                   tape.u_click[tape.click_off[k]:tape.click_off[k + 1]],
+                   tape.u_conv[tape.conv_off[k]:tape.conv_off[k + 1]],
+                   tape.rev_cents[tape.rev_off[k]:tape.rev_off[k + 1]].astype(np.float64) / 100.0)
+            continue
         r.load(tape.comp_cents[tape.comp_off[k]:tape.comp_off[k + 1]].astype(np.float64) / 100.0,
                tape.u_click[tape.click_off[k]:tape.click_off[k + 1]],
                tape.u_conv[tape.conv_off[k]:tape.conv_off[k + 1]],

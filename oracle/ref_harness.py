@@ -104,6 +104,9 @@ class RecordingRNG(np.random.Generator):
     def uniform(self, low=0.0, high=1.0, size=None):
         return self._rec("uniform", (low, high, size), super().uniform(low, high, size))
 
+    def binomial(self, n, p, size=None):
+        return self._rec("binomial", (n, p, size), super().binomial(n, p, size))
+
 
 class TapeRNG(np.random.Generator):
     """Replay front-end for one keyword (or for the env-level drift draws).
@@ -124,6 +127,7 @@ class TapeRNG(np.random.Generator):
         self.rev = np.zeros(0)
         self.drift = []  # list of arrays for env-level uniform() calls
         self.armed = False  # keyword constructors probe their samplers (classes:337-339)
+        self.bidders = None  # multi-bidder keywords: bidder count per lane, in lane order
         self.reset_cursors()
 
     def load(self, comp, u_click, u_conv, rev):
@@ -135,7 +139,7 @@ class TapeRNG(np.random.Generator):
         self.reset_cursors()
 
     def reset_cursors(self):
-        self.i_comp = self.i_click = self.i_conv = self.i_rev = 0
+        self.i_comp = self.i_click = self.i_conv = self.i_rev = self.i_lane = 0
         self._phase = 0  # 0: next random() is click, 1: next random() is conv
         self.i_drift = 0
 
@@ -144,13 +148,23 @@ class TapeRNG(np.random.Generator):
             raise AssertionError(f"tape exhausted: {what} needs {pos + n} > {len(arr)}")
         return arr[pos:pos + n].copy()
 
+    def binomial(self, n, p, size=None):
+        """Bidders of the next lane (default ImplicitKeyword, classes:664-665)."""
+        m = int(self.bidders[self.i_lane])
+        self.i_lane += 1
+        return m
+
     def laplace(self, loc=0.0, scale=1.0, size=None):
         s, n = size
-        assert s == 1, "tape replay supports the single-competitor keywords only"
         out = self._take(self.comp, self.i_comp, n, "comp")
         self.i_comp += n
         self._phase = 0
-        return out.reshape(1, n)
+        if self.bidders is None:
+            assert s == 1, "single-competitor keywords draw one bid per auction"
+            return out.reshape(1, n)
+        # multi-bidder keyword: the tape holds each auction's HIGHEST bid; any [s, n] matrix with that
+        # column maximum gives the same auction (helpers:116-180 with n=2, num_winners=1)
+        return np.vstack([out.reshape(1, n)] + [out.reshape(1, n) - 1.0] * (s - 1)) if s > 0 else np.zeros((0, n))
 
     def random(self, size=None, *a, **k):
         n = int(size[0]) if isinstance(size, tuple) else int(size)

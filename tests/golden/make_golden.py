@@ -156,6 +156,43 @@ def main():
     philox_case("phx_explicit_k6", kw_e, 1000.0, False, [True] * K, 3, 99, 3, 3.0)
     philox_case("phx_explicit_budget_k6", kw_e, 9.0, True, None, 3, 99, 5, 3.0)
 
+    # --- the class-default ImplicitKeyword: m ~ Binomial bidders per lane, signed Laplace bids ----
+    rngm = np.random.default_rng(77)
+    K = 5
+    kw_m = orc.KeywordSet(orc.IMPLICIT_MULTI, np.full(K, 40.0), np.full(K, 6.0), np.array([0.0, 0.05, -0.1, 0.2, 0.0]),
+                          np.array([0.1, 0.2, 0.05, 0.1, 0.1]), rngm.uniform(0.2, 0.9, K), rngm.uniform(0.2, 0.9, K),
+                          rngm.uniform(0.3, 1.5, K), rngm.uniform(0.05, 0.3, K),
+                          max_bidders=np.array([30.0, 2.0, 5.0, 0.0, 30.0]),      # classes:659-662 default 30; 2 and 0:
+                          participation=np.array([0.6, 0.5, 0.3, 0.6, 0.6]))      # zero-padded short auctions
+    envm = rd.build_multi_env(kw_m, seed=5, budget=1000.0)
+    record_case("rec_multi_default_k5", envm, [np.round(rngm.uniform(0.01, 0.5, K), 2) for _ in range(3)], 1000.0,
+                dict(kind="multi", note="class-default ImplicitKeyword: Binomial bidders per lane, signed Laplace, "
+                                        "zero padding for m < 3, negative costs (helpers:116-180)"))
+    envm = rd.build_multi_env(kw_m, seed=6, budget=1000.0)
+    record_case("rec_multi_budget_k5", envm, [np.round(rngm.uniform(0.05, 0.5, K), 2) for _ in range(3)], np.array([2.5]),
+                dict(kind="multi", note="binding ndarray budget: double charge + early break"))
+
+    def philox_multi(name, budget, alias, n_steps, seed, env_id):
+        env = rd.build_replay_env(kw_m, budget=budget, max_days=3)
+        steps = []
+        for step in range(n_steps):
+            bids = np.round(rngm.uniform(0.02, 0.5, K), 2)
+            bc = np.rint(bids * 100).astype(np.int32)
+            o = orc.step_philox(kw_m, bc, budget, seed=seed, env_id=env_id, step=step, record_cap=8192, budget_alias=alias)
+            r = rd.replay_step(env, bids, np.array([budget]) if alias else None, o["tape"])
+            for f in ("impressions", "clicks", "conversions"):
+                assert np.array_equal(np.asarray(r[f], np.int64), np.asarray(o[f], np.int64)), (name, f)
+            assert r["reward"] == o["reward"], name
+            r.update(tape=o["tape"], kw_before=kw_m.copy(), bid_cents=bc, budget=float(budget), budget_alias=bool(alias))
+            steps.append(r)
+        golden_io.save_case(os.path.join(HERE, name + ".npz"), steps,
+                            dict(kind="multi", note="Philox tape function replayed through the reference",
+                                 seed=seed, env_id=env_id, max_days=3, mask=None))
+        print("wrote", name, "lanes", [s["lanes_run"] for s in steps])
+
+    philox_multi("phx_multi_k5", 1000.0, False, 3, 21, 9)
+    philox_multi("phx_multi_budget_k5", 1.5, True, 3, 21, 10)
+
     # --- ideal-profit estimator of the AKNCP / NCP metrics (experiment_metrics.py:20-61) -------
     met = ref["metrics"]
     env = implicit_env(128, 0.8, 7, 1, mask=[True] * 7)

@@ -14,12 +14,12 @@ CASES = [c for c in CASES if not c.endswith("notebook_lane.npz")]
 
 
 def _kw(orc, case, step):
-    return orc.KeywordSet(case.kind, *[step.kw_before[n] for n in golden_io.PARAMS])
+    return orc.KeywordSet(case.kind, *[step.kw_before[n] for n in golden_io.PARAMS], **step.kw_extra)
 
 
 def _tape(orc, t):
     return orc.Tape(t.volume, t.comp_off, t.comp_cents, t.click_off, t.u_click, t.conv_off, t.u_conv,
-                    t.rev_off, t.rev_cents, t.impr, t.cost_off, t.cost, t.drift)
+                    t.rev_off, t.rev_cents, t.impr, t.cost_off, t.cost, t.drift, t.comp_f64)
 
 
 def test_fixtures_present():

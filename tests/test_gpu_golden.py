@@ -25,7 +25,8 @@ IDS = [os.path.basename(c)[:-4] for c in CASES]
 def _table(case, step, E):
     from adcraft_b200 import keywords as kwm
     cols = [np.tile(step.kw_before[n], (E, 1)) for n in golden_io.PARAMS]
-    return kwm.KeywordTable(case.kind, *cols)
+    extra = {n: np.tile(v, (E, 1)) for n, v in step.kw_extra.items()}
+    return kwm.KeywordTable(case.kind, *cols, **extra)
 
 
 def _make_env(case, E, **kw):

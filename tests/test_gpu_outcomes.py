@@ -30,7 +30,7 @@ def test_bidding_outcomes_string_equals_reference(path):
     case = golden_io.load_case(path)
     s0 = case.steps[0]
     assert s0.info_outcomes is not None, "regenerate the goldens (tests/golden/make_golden.py)"
-    table = kwm.KeywordTable(case.kind, *[s0.kw_before[n] for n in golden_io.PARAMS])
+    table = kwm.KeywordTable(case.kind, *[s0.kw_before[n] for n in golden_io.PARAMS], **s0.kw_extra)
     mask = case.meta.get("mask")
     env = BiddingSimulation(num_keywords=case.K, budget=s0.budget, max_days=case.meta.get("max_days", 60),
                             updater_mask=None if mask is None else [bool(m) for m in mask], keywords=table)

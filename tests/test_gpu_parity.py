@@ -234,3 +234,25 @@ def test_serial_warp_kernel_buffer_overflow_and_zero_budget(orc, alias):
         _compare(obs, reward, term, trunc, ref, env, RTOL64)
         np.testing.assert_allclose(env._out["remaining_budget"].cpu().numpy(),
                                    [0.0] * 0 + list(env._out["remaining_budget"].cpu().numpy()))
+
+
+@pytest.mark.parametrize("budget", [1e5, 3.0])
+def test_philox_multi_bidder_matches_oracle(orc, budget):
+    """ADC_IMPLICIT_MULTI (the class-default ImplicitKeyword): per-lane Binomial bidder counts, signed
+    un-rounded Laplace bids, zero padding below three bidders, negative costs -- CUDA == C oracle."""
+    from adcraft_b200 import keywords as kwm
+    rng = np.random.default_rng(21)
+    K, E = 9, 40
+    table = kwm.KeywordTable(
+        kwm.IMPLICIT_MULTI, np.full(K, 30.0), np.full(K, 5.0), rng.uniform(-0.1, 0.2, K), rng.uniform(0.05, 0.2, K),
+        rng.uniform(0.2, 0.9, K), rng.uniform(0.2, 0.9, K), rng.uniform(0.3, 1.5, K), rng.uniform(0.05, 0.3, K),
+        max_bidders=rng.choice([0.0, 1.0, 2.0, 3.0, 5.0, 30.0], K), participation=rng.uniform(0.2, 0.9, K))
+    env = _env(table, E, seed=9, budget=budget, obs_dtype=torch.float64, max_days=3)
+    params = {n: getattr(table, n) for n in kwm.PARAM_NAMES + ("max_bidders", "participation")}
+    ob = orc.BatchOracle(table.kind, E, K, params, seed=9, budget=budget, max_days=3)
+    for s in range(4):
+        bids = np.round(rng.uniform(0.01, 0.5, (E, K)), 2)
+        obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda()})
+        ref = ob.step(bids, n_threads=4)
+        _compare(obs, reward, term, trunc, ref, env, RTOL64)
+    assert float(obs["cost"].min()) < 0.0 or budget < 10  # negative clearing prices occur (m >= 3, all bids < 0)

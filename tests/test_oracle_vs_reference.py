@@ -190,3 +190,40 @@ def test_quantile_csv_wire_format_against_reference(orc):
         for n in kwm.PARAM_NAMES:
             np.testing.assert_allclose(getattr(a, n), getattr(t, n), rtol=1e-15 if n == "p2" else 0, err_msg=n)
         assert env.np_random.random() == g.random()
+
+
+def _multi_set(orc, rng, K):
+    return orc.KeywordSet(orc.IMPLICIT_MULTI, np.full(K, 40.0), np.full(K, 6.0), rng.uniform(-0.1, 0.2, K),
+                          rng.uniform(0.05, 0.2, K), rng.uniform(0.2, 0.9, K), rng.uniform(0.2, 0.9, K),
+                          rng.uniform(0.3, 1.5, K), rng.uniform(0.05, 0.3, K),
+                          max_bidders=rng.choice([0.0, 1.0, 2.0, 3.0, 5.0, 30.0], K), participation=rng.uniform(0.2, 0.9, K))
+
+
+@pytest.mark.parametrize("budget,seed", [(1000.0, 0), (np.array([4.0]), 1), (2.0, 2)])
+def test_recorded_multi_bidder_steps(orc, budget, seed):
+    """The class-default ImplicitKeyword (classes:578-688: Binomial bidders per lane, signed Laplace
+    bids, nth_price_auction with zero padding) on its own numpy Generator -> tape -> oracle replay."""
+    from oracle import ref_driver as rd
+    rng = np.random.default_rng(seed)
+    kw = _multi_set(orc, rng, 6)
+    env = rd.build_multi_env(kw, seed=seed)
+    for s in range(3):
+        bids = np.round(rng.uniform(0.01, 0.5, 6), 2)
+        r = rd.record_step(env, {"keyword_bids": bids, "budget": budget})
+        o = orc.step_replay(r["kw_before"], r["bid_cents"], r["budget"], r["tape"], budget_alias=r["budget_alias"])
+        _check(r, o, ("multi", s))
+    assert (np.asarray(r["tape"].impr) < 3).any() and (np.asarray(r["tape"].impr) >= 3).any()
+
+
+@pytest.mark.parametrize("budget,alias", [(1000.0, False), (3.0, False), (5.0, True)])
+def test_philox_multi_bidder_tapes_through_the_reference(orc, budget, alias):
+    from oracle import ref_driver as rd
+    rng = np.random.default_rng(11)
+    kw = _multi_set(orc, rng, 5)
+    env = rd.build_replay_env(kw, budget=budget)
+    for step in range(3):
+        bids = np.round(rng.uniform(0.02, 0.5, 5), 2)
+        bc = np.rint(bids * 100).astype(np.int32)
+        o = orc.step_philox(kw, bc, budget, seed=77, env_id=3, step=step, record_cap=4096, budget_alias=alias)
+        r = rd.replay_step(env, bids, np.array([budget]) if alias else None, o["tape"])
+        _check(r, o, ("multi-philox", step))
