@@ -66,8 +66,8 @@ int validate(const adc_step_args *a, const adc_tape *tape)
                     (a->scratch.acc_clicks != nullptr) == (a->scratch.acc_conversions != nullptr),
                 "scratch.acc_impressions / acc_clicks / acc_conversions: give all three or none");
     ADC_REQUIRE(a->scratch.serial_ws == nullptr ||
-                    ((reinterpret_cast<uintptr_t>(a->scratch.serial_ws) & 7u) == 0 && a->scratch.serial_ws_bytes >= 0),
-                "scratch.serial_ws must be 8-byte aligned");
+                    ((reinterpret_cast<uintptr_t>(a->scratch.serial_ws) & 15u) == 0 && a->scratch.serial_ws_bytes >= 0),
+                "scratch.serial_ws must be 16-byte aligned");
     ADC_REQUIRE(a->drift.mask == nullptr || a->kw.env_stride == a->kw.K,
                 "drift needs per-env keyword parameters (kw.env_stride == K)");
     ADC_REQUIRE(a->drift.mask == nullptr || (a->drift.num_updates >= 0 && a->drift.num_updates <= a->kw.K),

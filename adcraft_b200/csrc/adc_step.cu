@@ -1962,38 +1962,54 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
 //
 // The reference walks (sub-step, keyword, click) with ONE shared float budget (bsim:214-233,
 // :97-104), but only the affordability tests are sequential: what is clicked, at what price and
-// whether it converts does not depend on the budget.  So a warp first EXPANDS the env's day in the
-// hot kernel's form -- lane <-> keyword, the bit-sliced outcome masks of every 32-auction group, one
-// price per click -- into a slab of global memory it owns (L2-resident; adc_scratch.serial_ws):
-// per unit the impressions and first click of each of the 24 sub-steps and the day's clicked slots
-// in order (price in cents | converts << 31).  The walk then only reads: per sub-step and chunk of
-// 32 keywords the lanes fetch their clicked slots, the whole warp runs ONE uniform scan over them in
-// keyword order -- the reference's f64 sequence `if budget >= cost: budget -= cost`, alias rule and
-// `remaining <= 0` exit included -- and the lanes commit their accepted prefix in parallel
-// (conversions, revenues).  Nothing is re-drawn per sub-step and no keyword count is special.
+// whether it converts does not depend on the budget.  So a warp
+//   (0) EXPANDS the env's day in the hot kernel's form into a slab of global memory it owns
+//       (adc_scratch.serial_ws): lane <-> keyword, the bit-sliced outcome masks of every 32-auction
+//       group; from them one HEADER WORD per (sub-step, keyword) lane -- impressions, clicked slots,
+//       where the lane's slots start in the env's slot pool -- laid out sub-step-major, and the pool
+//       itself: one word per clicked slot of the day in click order (price in cents | converts << 31),
+//       prices drawn four per Philox call, flattened over the 32 keywords;
+//   (1) WALKS: per sub-step and chunk of 32 keywords one coalesced load brings the lanes' headers, a
+//       short gather their slots; the whole warp runs ONE uniform scan over them in keyword order --
+//       the reference's f64 sequence `if budget >= cost: budget -= cost`, alias rule and
+//       `remaining <= 0` exit included -- and a lane whose accepted count differs from its slot
+//       count writes it back into its header (nothing else is stored in the loop);
+//   (2) COMMITS: lane <-> keyword again, every keyword sums its lanes that ran -- impressions,
+//       accepted clicks, their prices and conversions, one revenue per conversion by conversion
+//       rank -- and stores the day's outputs once.
+// Nothing is re-drawn per sub-step and no keyword count is special.  Lanes the slab cannot
+// describe (volume > 512, more than kSerCap clicked slots in one sub-step, pool overflow) are
+// walked again by lane_walk with the budget (serial_direct_lane) and committed on the spot.
 // ------------------------------------------------------------------------------------------
 constexpr int kSerWarps = 4;
 constexpr int kSerCap = 32;        // clicked slots per lane and sub-step in shared memory; more -> direct re-walk
-constexpr int kPoolPerUnit = 64;   // the env's price pool holds K x 64 clicked slots; units that do not fit -> direct re-walk
-constexpr int kSerMinBlocks = 7;    // 28 warps per SM: a 4096-env queue is resident in one wave
+constexpr int kSlabGroups = 16;    // 32-auction groups per unit and day the slab describes (volume <= 512)
+constexpr int kPoolPerUnit = 64;   // the env's slot pool holds K x 64 clicked slots; units that do not fit -> direct
+constexpr int kSerMinBlocks = 7;   // 28 warps per SM: a 4096-env queue is resident in one wave
 
-constexpr int kSlabGroups = 16;    // 32-auction groups per unit and day in the slab (volume <= 512); more -> direct re-walk
+// lane header: bits 0..5 clicked slots (after the walk: accepted ones), 6..11 impressions, 12..31 first slot
+// in the pool.  Slot field 63: the lane is walked by lane_walk; 62: it was, and bits 12..31 hold its conversions.
+constexpr uint32_t kHdrDirect = 63u, kHdrDirectDone = 62u, kHdrMaxCount = 61u;
 
-struct __align__(8) SlabUnit {      // 216 B per keyword
-    uint32_t win[kSlabGroups], click[kSlabGroups], conv[kSlabGroups];  // outcome masks of the day's auctions
-    int volume;
+struct __align__(16) SlabUnit {     // 96 B per keyword
+    uint32_t convr[kSlabGroups];    // bit r: the r-th clicked slot of the day converts
     int win_cents;
     float rev_mean, rev_sd;
-    uint32_t cost_off;                  // first price of the unit in the env's pool (uint16 units, multiple of 4)
-    uint16_t n_clk_run;                 // clicked slots of the sub-steps walked so far
-    uint16_t flags;                     // bit 0: walk this unit with lane_walk instead (beyond the slab's caps)
+    int volume;
+    uint32_t pool_off;              // first slot of the unit in the env's pool
+    uint32_t flags;                 // bit 0: the whole unit is walked by lane_walk (beyond the slab's caps)
+    uint32_t pad[2];
 };
-// A slab = K SlabUnits followed by the env's price pool: uint16 cents (floor applied) of every clicked
-// slot of the day, per unit in click order, units padded to 4 entries.
-constexpr int64_t kSlabBytesPerKeyword = (int64_t)sizeof(SlabUnit) + 2 * kPoolPerUnit;
+static_assert(sizeof(SlabUnit) == 96, "slab layout");
 
-// A (sub-step, keyword) lane the slab cannot describe (volume, clicks or bid beyond its caps, or more
-// clicked slots than the shared-memory buffer holds): walked again with the budget by lane_walk.  Out
+// slab of one warp: SlabUnit[K] | uint32 hdr[24][Kp] (Kp = K rounded up to 32) | uint32 pool[K * kPoolPerUnit]
+__host__ __device__ inline int64_t slab_kp(int K) { return ((int64_t)K + 31) & ~(int64_t)31; }
+__host__ __device__ inline int64_t slab_bytes_of(int K)
+{
+    return (int64_t)K * (int64_t)sizeof(SlabUnit) + (int64_t)ADC_SUBSTEPS * slab_kp(K) * 4 + (int64_t)K * kPoolPerUnit * 4;
+}
+
+// A (sub-step, keyword) lane the slab cannot describe: walked again with the budget by lane_walk.  Out
 // of line: its registers stay out of the scan loop.
 struct DirectOut {
     int I, B, S;
@@ -2002,7 +2018,7 @@ struct DirectOut {
 };
 
 __device__ __noinline__ DirectOut serial_direct_lane(const adc_step_args &a, const PhiloxSrc &src, int e, int k, int t,
-                                                     bool recount, int cbase, int n_rev, double remaining)
+                                                     int n_rev, double remaining)
 {
     const adc_tape *no_tape = nullptr;
     const int64_t u = (int64_t)e * a.kw.K + k;
@@ -2011,8 +2027,7 @@ __device__ __noinline__ DirectOut serial_direct_lane(const adc_step_args &a, con
     p.volume = unit_volume(a, src, no_tape, e, k, &uw);
     const long long q = p.volume / ADC_SUBSTEPS, n0 = p.volume - (ADC_SUBSTEPS - 1) * q;
     const long long n = t == 0 ? n0 : q, j0 = t == 0 ? 0 : n0 + (long long)(t - 1) * q;
-    // clicked slots before this sub-step: from the slab, or counted again when it does not describe the unit
-    const int n_clk0 = recount ? clicks_before(src, k, p.u2, p.volume, j0) : cbase;
+    const int n_clk0 = clicks_before(src, k, p.u2, p.volume, j0);  // price-draw rank of the lane's first click
     double b = remaining, unused = 0.0;
     UnitCur cur = {j0, 0, 0, n_rev, 0, n_clk0};
     const LaneOut o = lane_walk<PhiloxSrc, false, true>(src, no_tape, u, k, t, n, p, cur, b, unused);
@@ -2022,7 +2037,19 @@ __device__ __noinline__ DirectOut serial_direct_lane(const adc_step_args &a, con
     return d;
 }
 
-static_assert(sizeof(SlabUnit) % 8 == 0, "slab layout: the pool behind K units stays 8-byte aligned");
+// conversions a keyword's lanes accepted in the sub-steps before t (the revenue-draw rank of the next one)
+__device__ __noinline__ int conversions_before(const uint32_t *hdr, const uint32_t *pool, int64_t Kp, int k, int t)
+{
+    int s = 0;
+    for (int tt = 0; tt < t; ++tt) {
+        const uint32_t h = hdr[(int64_t)tt * Kp + k];
+        const uint32_t f = h & 63u;
+        if (f == kHdrDirectDone) { s += (int)(h >> 12); continue; }
+        if (f == kHdrDirect) continue;
+        for (uint32_t i = 0; i < f; ++i) s += (int)(pool[(h >> 12) + i] >> 31);
+    }
+    return s;
+}
 
 __global__ void __launch_bounds__(kSerWarps * 32, kSerMinBlocks)
 adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_slabs)
@@ -2035,6 +2062,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
     if (threadIdx.x < 128) s_tab[threadIdx.x] = kNeglogTab[threadIdx.x];
     __syncthreads();
     const int K = a.kw.K;
+    const int64_t Kp = slab_kp(K);
     const SerCounts acc = ser_counts(a);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto slot_cost = [&](int i, int l) { return (int)(s_slot[warp][i][l] & 0x7FFFFFFFu); };
@@ -2045,28 +2073,31 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const adc_tape *no_tape = nullptr;
     if (gwarp >= n_warps) return;
-    unsigned char *const slab_raw = reinterpret_cast<unsigned char *>(a.scratch.serial_ws) +
-                                    (size_t)gwarp * (size_t)K * (size_t)kSlabBytesPerKeyword;
-    SlabUnit *slab = reinterpret_cast<SlabUnit *>(slab_raw);
-    uint16_t *const pool = reinterpret_cast<uint16_t *>(slab_raw + (size_t)K * sizeof(SlabUnit));
-    const unsigned pool_cap = (unsigned)K * (unsigned)kPoolPerUnit;
+    unsigned char *const slab_raw = reinterpret_cast<unsigned char *>(a.scratch.serial_ws) + (size_t)gwarp * (size_t)slab_bytes_of(K);
+    SlabUnit *const slab = reinterpret_cast<SlabUnit *>(slab_raw);
+    uint32_t *const hdr = reinterpret_cast<uint32_t *>(slab_raw + (size_t)K * sizeof(SlabUnit));
+    uint32_t *const pool = hdr + (size_t)ADC_SUBSTEPS * Kp;
+    const unsigned pool_cap = min((unsigned)K * (unsigned)kPoolPerUnit, 1u << 20);  // 20-bit slot index in the header
 
     for (int idx = gwarp; idx < count; idx += n_warps) {
         const int e = a.scratch.serial_list[idx];
         PhiloxSrc src{k0, k1, a.step, philox_env(a, e)};
         // ---- phase 0: expand the day into the slab, 32 keywords at a time
         unsigned pool_used = 0;  // warp-uniform
-        int t_last = 0;          // last sub-step in which any keyword of the env holds an auction
         for (int c0 = 0; c0 < K; c0 += 32) {
-            // (a) lane <-> keyword: thresholds, volume, the outcome masks of every 32-auction group
+            // (a) lane <-> keyword: thresholds, volume, outcome masks -> lane headers, conversion-by-rank bits
             const int k = c0 + lane;
             int B = 0;
+            unsigned char cnt_i[ADC_SUBSTEPS], cnt_c[ADC_SUBSTEPS];  // impressions / clicked slots per sub-step
+#pragma unroll
+            for (int t = 0; t < ADC_SUBSTEPS; ++t) { cnt_i[t] = 0; cnt_c[t] = 0; }
+            bool whole_direct = false;
             FlatCost fc;
             fc.t1 = fc.h1 = fc.a1 = fc.a2 = 0u; fc.L = 0.f; fc.b = 0.f; fc.W = 1; fc.floor_c = 0;
             fc.n0 = fc.n1 = fc.x3 = 0u; fc.B = 0;
             if (k < K) {
                 const int64_t u = (int64_t)e * K + k;
-                acc.I[u] = 0;
+                acc.I[u] = 0;  // the direct lanes accumulate here; everything else is stored once in phase 2
                 acc.B[u] = 0;
                 acc.S[u] = 0;
                 a.out.cost_cents[u] = 0;
@@ -2076,37 +2107,68 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 const long long Vl = unit_volume(a, src, no_tape, e, k, &uw);
                 SlabUnit *su = slab + k;
                 const bool beats_rivals = p.u2.W > p.floor_cents;
-                const bool beyond = Vl > 32 * kSlabGroups || p.win_cents > kMaxFlatBidCents;
-                const int V = beyond || !beats_rivals ? 0 : (int)Vl;
+                whole_direct = (Vl > 32 * kSlabGroups || p.win_cents > kMaxFlatBidCents) && beats_rivals;
+                const int V = whole_direct || !beats_rivals ? 0 : (int)Vl;
                 su->volume = V;
                 su->win_cents = p.win_cents;
                 su->rev_mean = p.rev_mean;
                 su->rev_sd = p.rev_sd;
-                su->n_clk_run = 0;
+#pragma unroll
+                for (int g = 0; g < kSlabGroups; ++g) su->convr[g] = 0u;
                 const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), src.env, k0, k1);
+                const int q = V / ADC_SUBSTEPS, n0 = V - (ADC_SUBSTEPS - 1) * q;  // bsim:151-167
                 for (int g = 0; 32 * g < V; ++g) {
                     const int rem = V - 32 * g;
                     const uint32_t active = rem >= 32 ? 0xFFFFFFFFu : (1u << rem) - 1u;
                     const Masks3 m = group_masks(active, (uint32_t)g, p.u2.t1, p.u2.t2, p.u2.t3, p.u2.full, pa.n0, pa.n1,
                                                  pa.x3, k0, k1);
-                    su->win[g] = m.win; su->click[g] = m.click; su->conv[g] = m.conv;
-                    B += __popc(m.click);
+                    // conversion flags by click rank: the click bits in order
+                    uint32_t cl = m.click;
+                    while (cl) {
+                        const int bpos = __ffs(cl) - 1;
+                        cl &= cl - 1;
+                        if ((m.conv >> bpos) & 1u) su->convr[(B >> 5) & (kSlabGroups - 1)] |= 1u << (B & 31);
+                        ++B;
+                    }
+                    // this group's share of every sub-step it overlaps
+                    const int j_lo = 32 * g, j_hi = min(32 * g + 32, V);
+                    int t = j_lo < n0 ? 0 : (q > 0 ? 1 + (j_lo - n0) / q : 0);
+                    while (t < ADC_SUBSTEPS) {
+                        const int s0 = t == 0 ? 0 : n0 + (t - 1) * q, s1 = t == 0 ? n0 : s0 + q;
+                        if (s0 >= j_hi) break;
+                        const int lo = max(s0, j_lo) - j_lo, hi = min(s1, j_hi) - j_lo;
+                        if (hi > lo) {
+                            const uint32_t range = (hi >= 32 ? 0xFFFFFFFFu : (1u << hi) - 1u) & ~((1u << lo) - 1u);
+                            cnt_i[t] = (unsigned char)min(cnt_i[t] + __popc(m.win & range), 255);
+                            cnt_c[t] = (unsigned char)min(cnt_c[t] + __popc(m.click & range), 255);
+                        }
+                        ++t;
+                    }
                 }
-                su->flags = beyond ? 1 : 0;
-                if (Vl >= ADC_SUBSTEPS) t_last = ADC_SUBSTEPS - 1;  // V // 24 > 0: every sub-step gets auctions (bsim:151-167)
+                su->flags = whole_direct ? 1u : 0u;
                 const PhiloxPre pc = philox_pre(a.step, stream_word(ST_COST, 0u, (uint32_t)k), src.env, k0, k1);
                 fc.t1 = p.u2.t1; fc.h1 = p.u2.h1; fc.a1 = p.u2.a1; fc.a2 = p.u2.a2; fc.L = p.u2.L; fc.b = p.u2.b;
                 fc.W = p.u2.W | ((p.u2.full & 1u) ? (int)0x80000000u : 0);
                 fc.floor_c = max(p.floor_cents, 0); fc.n0 = pc.n0; fc.n1 = pc.n1; fc.x3 = pc.x3; fc.B = B;
             }
-            {   // room in the env's price pool (units padded to 4 prices); a unit that does not fit is re-walked
+            {   // room in the env's slot pool (units padded to 4 slots); a unit that does not fit is re-walked
                 const int b4 = (B + 3) & ~3;
                 const int incl = warp_incl_scan(b4, lane);
                 const unsigned off = pool_used + (unsigned)(incl - b4);
                 if (k < K) {
                     SlabUnit *su = slab + k;
-                    su->cost_off = off;
-                    if (off + (unsigned)b4 > pool_cap) { su->flags = 1; B = 0; fc.B = 0; }
+                    su->pool_off = off;
+                    if (off + (unsigned)b4 > pool_cap) { su->flags = 1u; whole_direct = true; B = 0; fc.B = 0; }
+                    // lane headers, sub-step-major: one coalesced store per sub-step
+                    unsigned cb = off;
+                    for (int t = 0; t < ADC_SUBSTEPS; ++t) {
+                        uint32_t h;
+                        if (whole_direct) h = kHdrDirect;
+                        else if (cnt_c[t] > kSerCap || cnt_i[t] > kHdrMaxCount) h = kHdrDirect | (cb << 12);
+                        else h = (uint32_t)cnt_c[t] | ((uint32_t)cnt_i[t] << 6) | (cb << 12);
+                        hdr[(int64_t)t * Kp + k] = h;
+                        cb += cnt_c[t];
+                    }
                 }
                 pool_used = min(pool_used + (unsigned)__shfl_sync(FULL, incl, 31), pool_cap);
             }
@@ -2124,71 +2186,51 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                     const uint4 w = philox_from_pre((uint32_t)q, f.n0, f.n1, f.x3, k0, k1);
                     const bool t1_full = f.W < 0;
                     const int W = f.W & 0x7FFFFFFF;
-                    const int c0c = max(cost_cents2(w.x, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c);
-                    const int c1c = max(cost_cents2(w.y, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c);
-                    const int c2c = max(cost_cents2(w.z, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c);
-                    const int c3c = max(cost_cents2(w.w, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c);
-                    // 4 x uint16 = one 8-byte store (offsets are multiples of 4 entries)
-                    uint2 pk;
-                    pk.x = (uint32_t)c0c | ((uint32_t)c1c << 16);
-                    pk.y = (uint32_t)c2c | ((uint32_t)c3c << 16);
-                    *reinterpret_cast<uint2 *>(pool + slab[c0 + b].cost_off + 4 * q) = pk;
+                    const SlabUnit *sb = slab + c0 + b;
+                    const uint32_t cvw = sb->convr[((4 * q) >> 5) & (kSlabGroups - 1)] >> ((4 * q) & 31);  // 4 q .. 4 q + 3 share a word
+                    uint4 pk;
+                    pk.x = (uint32_t)max(cost_cents2(w.x, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c) | ((cvw & 1u) << 31);
+                    pk.y = (uint32_t)max(cost_cents2(w.y, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c) | (((cvw >> 1) & 1u) << 31);
+                    pk.z = (uint32_t)max(cost_cents2(w.z, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c) | (((cvw >> 2) & 1u) << 31);
+                    pk.w = (uint32_t)max(cost_cents2(w.w, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c) | (((cvw >> 3) & 1u) << 31);
+                    *reinterpret_cast<uint4 *>(pool + sb->pool_off + 4 * q) = pk;  // offsets are multiples of 4 slots
                 }
             }
             __syncwarp();
         }
+        __threadfence_block();
+        __syncwarp();
+        // ---- phase 1: the walk
         const double budget = step_budget(a, e);
         double remaining = budget;  // warp-uniform (bsim:214)
         bool stop = false;
-        // Sub-steps after t_last hold no auction of any keyword: their lanes have no impression, no
-        // click slot and leave `remaining` alone, so the walk ends there (a sparse keyword set, V < 24,
-        // has its whole day in sub-step 0).  `remaining <= 0` on entry still needs its one look.
-        t_last = __reduce_max_sync(FULL, t_last);
-        for (int t = 0; t <= t_last && !stop; ++t) {
+        int t_stop = ADC_SUBSTEPS, k_stop = K;  // the lane after which nothing ran (bsim:230-233)
+        for (int t = 0; t < ADC_SUBSTEPS && !stop; ++t) {
             for (int c0 = 0; c0 < K && !stop; c0 += 32) {
                 const int k = c0 + lane;
                 const bool act = k < K;
                 const int64_t u = (int64_t)e * K + (act ? k : 0);
-                // ---- phase 1 (parallel): the lane's sub-step from the slab: impressions, clicked slots
-                SlabUnit *su = slab + (act ? k : 0);
-                int I = 0, nclk = 0, cbase = 0, win_c = 0;
-                bool direct = false;  // walk the sub-step again with lane_walk (beyond the slab / the buffer)
-                if (act) {
-                    direct = (su->flags & 1u) != 0u;
-                    win_c = su->win_cents;
-                    const int V = su->volume;
-                    if (!direct && V > 0) {
-                        const int q = V / ADC_SUBSTEPS, n0 = V - (ADC_SUBSTEPS - 1) * q;  // bsim:151-167
-                        const int j0 = t == 0 ? 0 : n0 + (t - 1) * q, j1 = j0 + (t == 0 ? n0 : q);
-                        cbase = su->n_clk_run;
-                        const uint16_t *const prices = pool + su->cost_off + cbase;
-                        for (int g = j0 >> 5; 32 * g < j1; ++g) {
-                            const int lo = max(j0 - 32 * g, 0), hi = min(j1 - 32 * g, 32);
-                            const uint32_t range = (hi >= 32 ? 0xFFFFFFFFu : (1u << hi) - 1u) & ~((1u << lo) - 1u);
-                            I += __popc(su->win[g] & range);
-                            uint32_t cl = su->click[g] & range;
-                            const uint32_t cv = su->conv[g];
-                            while (cl) {
-                                const int bpos = __ffs(cl) - 1;
-                                cl &= cl - 1;
-                                if (nclk < kSerCap)
-                                    s_slot[warp][nclk][lane] = (uint32_t)prices[nclk] | (((cv >> bpos) & 1u) << 31);
-                                ++nclk;
-                            }
-                        }
-                        su->n_clk_run = (uint16_t)(cbase + nclk);
-                        if (nclk > kSerCap) direct = true;
-                    }
-                }
+                // the lanes' headers (one coalesced load), then their clicked slots from the pool
+                const uint32_t h = act ? hdr[(int64_t)t * Kp + k] : 0u;
+                // a chunk without an impression or a clicked slot in this sub-step leaves everything alone
+                // (a sparse keyword, V < 24, has its whole day in sub-step 0); `remaining <= 0` on entry still
+                // gets its one look
+                if (remaining > 0 && __all_sync(FULL, (h & 0xFFFu) == 0u)) continue;
+                int nclk = (int)(h & 63u);
+                const bool direct = nclk == (int)kHdrDirect;
+                const int win_c = act ? slab[k].win_cents : 0;
                 if (direct) nclk = kSerCap + 1;  // takes the re-walk turn below
+                else
+                    for (int i = 0; i < nclk; ++i) s_slot[warp][i][lane] = pool[(h >> 12) + i];
                 __syncwarp();
-                // ---- phase 2 (one uniform scan over the lanes that have clicks): the reference's budget walk
-                int B = 0, S = 0;
-                long long cost_c = 0, rev_c = 0;
-                bool rev_done = false;
+                // ---- one uniform scan over the lanes that have clicks: the reference's budget walk
+                int B = direct ? 0 : nclk;
                 unsigned todo = __ballot_sync(FULL, act && nclk > 0);
                 if (!(remaining > 0)) todo |= 1u;  // a lane must run for `remaining <= 0` to be seen
                 int cutoff = 32;
+                DirectOut dout;
+                dout.I = dout.B = dout.S = 0; dout.cost_c = dout.rev_c = 0; dout.next = 0.0;
+                bool direct_done = false;
                 // Two shortcuts that leave the reference's f64 sequence intact:
                 // (a) nothing affordable -- every lane's first click costs more than `remaining`, so each
                 //     lane breaks at once (bsim:99-104) and `remaining` does not move: the usual state of
@@ -2198,11 +2240,13 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 //     fail; without the alias rule the walk is then per lane `remaining -= lane_sum` with
                 //     lane_sum the lane's own sequential f64 sum (bsim:225 + rust sum_list), which the
                 //     lanes form in parallel.
+                bool all_accepted = false;
                 if (remaining > 0) {
                     const bool lane_has = act && nclk > 0;
                     const bool none = !lane_has || (!direct && !(remaining >= cents_to_dollars(slot_cost(0, lane))));
                     if (__all_sync(FULL, none)) {
                         todo = 0;
+                        B = 0;
                     } else if (!__any_sync(FULL, nclk > kSerCap || win_c > kMaxFlatBidCents)) {
                         unsigned cents = 0;
                         double lane_sum = 0.0;
@@ -2214,7 +2258,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                         const unsigned total = __reduce_add_sync(FULL, cents);  // <= 32 lanes x kSerCap x 65535 < 2^32 (bids capped above)
                         const double spend = __ddiv_rn((double)total, 100.0);
                         if (remaining > (a.budget_alias ? spend + spend : spend) + 0.01) {
-                            B = nclk;
+                            all_accepted = true;
                             while (todo) {
                                 const int l = __ffs(todo) - 1;
                                 todo &= todo - 1;
@@ -2228,6 +2272,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                         }
                     }
                 }
+                if (!all_accepted && todo) B = 0;  // the scan below decides lane by lane; lanes it never reaches accept nothing
                 while (todo) {
                     const int l = __ffs(todo) - 1;
                     todo &= todo - 1;
@@ -2248,11 +2293,9 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                     } else {  // beyond the slab or the buffer: lane l walks its sub-step again, with the budget
                         next = remaining;
                         if (lane == l) {
-                            const DirectOut d = serial_direct_lane(a, src, e, k, t, (su->flags & 1u) != 0u, cbase,
-                                                                   acc.S[u], remaining);
-                            I = d.I; B = d.B; S = d.S; cost_c = d.cost_c; rev_c = d.rev_c;
-                            rev_done = true;
-                            next = d.next;
+                            dout = serial_direct_lane(a, src, e, k, t, conversions_before(hdr, pool, Kp, k, t), remaining);
+                            direct_done = true;
+                            next = dout.next;
                         }
                         next = __shfl_sync(FULL, next, l);
                     }
@@ -2260,49 +2303,82 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                     if (remaining <= 0) {  // bsim:230-233
                         stop = true;
                         cutoff = l;
+                        t_stop = t;
+                        k_stop = c0 + l;
                         break;
                     }
                 }
-                // ---- phase 3 (parallel): the accepted prefix of the lane's clicks, revenues, commit
+                // the lanes that ran write back what the commit cannot infer: an accepted count below the
+                // slot count, a direct lane's totals
                 if (act && lane <= cutoff) {
-                    if (!rev_done) {
-                        for (int i = 0; i < B; ++i) {
-                            const uint32_t sl = s_slot[warp][i][lane];
-                            cost_c += (int)(sl & 0x7FFFFFFFu);
-                            S += (int)(sl >> 31);
-                        }
-                        if (S > 0) {
-                            const int r0 = acc.S[u];
-                            const float rm = su->rev_mean, rs = su->rev_sd;
-                            uint4 rw = make_uint4(0, 0, 0, 0);
-                            for (int i = 0; i < S; ++i) {
-                                const int r = r0 + i;
-                                if (i == 0 || (r & 3) == 0) rw = src.draw(ST_REVENUE, (uint32_t)k, (uint32_t)(r >> 2));
-                                const uint32_t w = (r & 3) == 0 ? rw.x : (r & 3) == 1 ? rw.y : (r & 3) == 2 ? rw.z : rw.w;
-                                rev_c += revenue_cents(w, rm, rs);
-                            }
-                        }
+                    if (direct_done) {
+                        acc.I[u] += dout.I;
+                        acc.B[u] += dout.B;
+                        acc.S[u] += dout.S;
+                        a.out.cost_cents[u] += dout.cost_c;
+                        a.out.revenue_cents[u] += dout.rev_c;
+                        hdr[(int64_t)t * Kp + k] = kHdrDirectDone | ((uint32_t)dout.S << 12);
+                    } else if (direct) {
+                        hdr[(int64_t)t * Kp + k] = kHdrDirectDone;  // never reached: nothing of it counts
+                    } else if (B != nclk) {
+                        hdr[(int64_t)t * Kp + k] = (h & ~63u) | (uint32_t)B;
                     }
-                    acc.I[u] += I;
-                    acc.B[u] += B;
-                    acc.S[u] += S;
-                    a.out.cost_cents[u] += cost_c;
-                    a.out.revenue_cents[u] += rev_c;
                 }
                 __syncwarp();
             }
         }
-        // ---- float outputs, reward, env tail, episode accumulation, drift
+        __threadfence_block();
+        __syncwarp();
+        // ---- phase 2: commit, lane <-> keyword: the lanes that ran, in sub-step order
         long long profit_c = 0;
         for (int k = lane; k < K; k += 32) {
             const int64_t u = (int64_t)e * K + k;
-            const long long cc = a.out.cost_cents[u], rc = a.out.revenue_cents[u];
-            store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cc));
-            store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rc));
+            const SlabUnit *su = slab + k;
+            const float rm = su->rev_mean, rs = su->rev_sd;
+            int I = 0, B = 0, S = 0;
+            long long cost_c = 0, rev_c = 0;
+            uint4 rw = make_uint4(0, 0, 0, 0);
+            int rw_idx = -1;
+            for (int t = 0; t < ADC_SUBSTEPS; ++t) {
+                if (t > t_stop || (t == t_stop && k > k_stop)) break;  // after the early break nothing ran
+                const uint32_t h = hdr[(int64_t)t * Kp + k];
+                const uint32_t f = h & 63u;
+                if (f == kHdrDirectDone) { S += (int)(h >> 12); continue; }  // committed on the spot
+                if (f == kHdrDirect) continue;
+                I += (int)((h >> 6) & 63u);
+                B += (int)f;
+                for (uint32_t i = 0; i < f; ++i) {
+                    const uint32_t w = pool[(h >> 12) + i];
+                    cost_c += (int)(w & 0x7FFFFFFFu);
+                    if (w >> 31) {  // one revenue per conversion, by conversion rank (direct lanes' included)
+                        const int r = S++;
+                        if ((r >> 2) != rw_idx) {
+                            rw_idx = r >> 2;
+                            rw = src.draw(ST_REVENUE, (uint32_t)k, (uint32_t)rw_idx);
+                        }
+                        const uint32_t ww = (r & 3) == 0 ? rw.x : (r & 3) == 1 ? rw.y : (r & 3) == 2 ? rw.z : rw.w;
+                        rev_c += revenue_cents(ww, rm, rs);
+                    }
+                }
+            }
+            // S counted the direct lanes' conversions for the ranks only: they are in acc.S already
+            const int S_direct = acc.S[u];
+            I += acc.I[u];
+            B += acc.B[u];
+            cost_c += a.out.cost_cents[u];
+            rev_c += a.out.revenue_cents[u];
+            acc.I[u] = I;
+            acc.B[u] = B;
+            acc.S[u] = S;
+            (void)S_direct;
+            a.out.cost_cents[u] = cost_c;
+            a.out.revenue_cents[u] = rev_c;
+            store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost_c));
+            store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev_c));
             ser_publish(a, acc, u);
-            store_flat_unit(a, e, k, acc.I[u], acc.B[u], acc.S[u], cents_to_dollars(cc), cents_to_dollars(rc));
-            if (a.out.episode_profit_cents != nullptr) a.out.episode_profit_cents[u] += rc - cc;
-            profit_c += rc - cc;
+            store_flat_unit(a, e, k, I, B, S, cents_to_dollars(cost_c), cents_to_dollars(rev_c));
+            if (a.out.episode_profit_cents != nullptr) a.out.episode_profit_cents[u] += rev_c - cost_c;
+            profit_c += rev_c - cost_c;
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) profit_c += __shfl_xor_sync(FULL, profit_c, off);
@@ -2450,7 +2526,7 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     }
     if (err != cudaSuccess) return err;
     // exact serial walk of the queued envs (reads the count on the device; exits at once if 0)
-    const int64_t slab_bytes = (int64_t)a.kw.K * kSlabBytesPerKeyword;
+    const int64_t slab_bytes = slab_bytes_of(a.kw.K);
     const int64_t n_slabs = a.scratch.serial_ws != nullptr ? a.scratch.serial_ws_bytes / slab_bytes : 0;
     if (tape == nullptr && !explicit_kw && a.n_lanes != 1 && a.detail.costs == nullptr && n_slabs > 0) {
         // one warp per queued env, each with its own slab of the workspace
@@ -2476,7 +2552,7 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     return cudaSuccess;
 }
 
-int64_t serial_slab_bytes(int32_t K) { return (int64_t)K * kSlabBytesPerKeyword; }
+int64_t serial_slab_bytes(int32_t K) { return slab_bytes_of(K); }
 
 int64_t host_row_bytes(int32_t K, int32_t float_dtype) { return row_layout(K, float_dtype).bytes; }
 
