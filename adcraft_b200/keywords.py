@@ -360,3 +360,34 @@ def sample_implicit_keywords_device(num_envs: int, num_keywords: int, keyword_co
     rev_std = torch.clamp(draw("std_rpsc") * rev, min=0.01)
     return dict(vol_mean=vol_mean, vol_std=vol_std, p1=loc, p2=scale, ctr=bctr, cvr=sctr,
                 rev_mean=rev, rev_std=rev_std)
+
+
+def sample_random_keywords_device(num_envs: int, num_keywords: int, device, generator=None) -> Dict[str, "object"]:
+    """Per-env ExplicitKeyword parameters (the default env's factory, gymnasium_kw_utils.py:113-156) as
+    float64 CUDA tensors [E, K], drawn on the device: v_mean = int(2 ** Beta(2,5) * 15 - 1),
+    v_std = U * 0.5 * (v_mean + 1), sctr ~ Beta(5,2), intercept ~ 1.5 U, mean_rev ~ 1.5 Beta(2,5),
+    std_rev ~ Beta(2,5) * mean_rev, bctr ~ Beta(2,5), slope ~ 25 Beta(5,5).  Beta(a, b) with integer
+    shapes is drawn exactly as the a-th smallest of a + b - 1 uniforms (order statistics), so the
+    torch Generator is the only source of randomness.  Same distributions as the host factory
+    (``sample_random_keywords``, which reproduces the reference's draws bit for bit); KS-tested."""
+    import torch
+    E, K = int(num_envs), int(num_keywords)
+    f64 = torch.float64
+
+    def uniform():
+        return torch.rand(E, K, dtype=f64, device=device, generator=generator)
+
+    def beta(a: int, b: int):
+        u = torch.rand(E, K, a + b - 1, dtype=f64, device=device, generator=generator)
+        return torch.kthvalue(u, a, dim=-1).values
+
+    v_mean = torch.trunc(torch.pow(2.0, beta(2, 5)) * 15.0 - 1.0)
+    v_std = uniform() * 0.5 * (v_mean + 1.0)
+    sctr = beta(5, 2)
+    intercept = uniform() * 1.5
+    mean_rev = beta(2, 5) * 1.5
+    std_rev = beta(2, 5) * mean_rev
+    bctr = beta(2, 5)
+    slope = beta(5, 5) * 25.0
+    return dict(vol_mean=v_mean, vol_std=v_std, p1=intercept, p2=slope, ctr=bctr.clamp(0.0, 1.0),
+                cvr=sctr.clamp(0.0, 1.0), rev_mean=mean_rev, rev_std=std_rev)

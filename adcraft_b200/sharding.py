@@ -31,3 +31,26 @@ def init_distributed(backend: str = "nccl"):
         else:
             dist.init_process_group(backend)
     return rank, world
+
+
+def gather_observations(flat, dst: int = 0, group=None, max_bytes: int = 64 << 30):
+    """Optional observation gather to the learner GPU (BASELINE.json north_star): every rank's flat
+    observation rows ``[E_rank, 5K+2]`` (``VectorBiddingSimulation.flat_observation()``, written by the
+    step kernels) are gathered on rank ``dst`` in rank order -- which is global env order, since rank g
+    owns envs ``[g * E, (g + 1) * E)`` -- with ONE ``torch.distributed.gather`` (NCCL over NVLink for
+    CUDA tensors, gloo for CPU tensors).  Returns ``[world * E_rank, 5K+2]`` on ``dst``, None
+    elsewhere.  Refuses what cannot fit one GPU (C5: 200 GB per step; a data-parallel learner is the
+    answer there): ``max_bytes`` bounds the gathered tensor."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return flat
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    total = world * flat.numel() * flat.element_size()
+    if total > max_bytes:
+        raise ValueError(f"gather_observations: {total / 1e9:.1f} GB of observations do not fit the learner GPU "
+                         f"(limit {max_bytes / 1e9:.1f} GB); keep the learner data-parallel")
+    flat = flat.contiguous()
+    parts = [torch.empty_like(flat) for _ in range(world)] if rank == dst else None
+    dist.gather(flat, parts, dst=dst, group=group)
+    return torch.cat(parts, dim=0) if rank == dst else None

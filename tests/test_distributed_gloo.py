@@ -31,8 +31,20 @@ def _worker(rank, world, port, total_envs, K, out):
         obs = {"revenue": torch.tensor(rev[lo:hi]), "cost": torch.tensor(cost[lo:hi])}
         acc.update(obs, torch.tensor((rev - cost)[lo:hi].sum(1)), ideal=torch.tensor(ideal[lo:hi]))
     vec = m.reduce_metrics(acc.summary_vector())
+    # optional observation gather to the learner rank: rank order = global env order
+    from adcraft_b200.sharding import gather_observations
+    flat = torch.arange(lo * 6, hi * 6, dtype=torch.float32).view(hi - lo, 6)
+    whole = gather_observations(flat, dst=0)
+    try:
+        gather_observations(flat, dst=0, max_bytes=16)
+        refused = False
+    except ValueError:
+        refused = True
     if rank == 0:
-        out.put(vec.numpy().copy())
+        ok = torch.equal(whole, torch.arange(total_envs * 6, dtype=torch.float32).view(total_envs, 6)) and refused
+        out.put((vec.numpy().copy(), bool(ok)))
+    else:
+        assert whole is None and refused
     dist.destroy_process_group()
 
 
@@ -46,7 +58,8 @@ def test_two_rank_metric_reduction_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, world, port, total_envs, K, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = q.get(timeout=120)
+    got, gathered_ok = q.get(timeout=120)
+    assert gathered_ok, "gather_observations did not return the rows in global env order"
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

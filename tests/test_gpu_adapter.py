@@ -199,3 +199,27 @@ def test_step_host_pipelined_equals_device_step(K, E, budget, chunks, drift):
     if drift:
         pa, pb = a.keyword_params(), b.keyword_params()
         assert all(np.array_equal(pa[n], pb[n]) for n in ("vol_mean", "ctr", "cvr"))
+
+
+def test_device_side_explicit_keyword_sampling_matches_host_distributions():
+    """SURVEY 8f-2, the default env's factory (gymnasium_kw_utils.py:113-156): per-env ExplicitKeyword
+    sets drawn on the GPU follow the distributions of the host factory that reproduces the
+    reference's draws bit for bit (two-sample KS per parameter), and an env steps on them."""
+    from scipy.stats import ks_2samp
+    from adcraft_b200 import keywords as kwm
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    E, K = 128, 100
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cols = kwm.sample_random_keywords_device(E, K, torch.device("cuda", 0), generator=g)
+    host = kwm.sample_random_keywords(K * 32, np.random.default_rng(9))
+    for n in kwm.PARAM_NAMES:
+        a, b = cols[n].cpu().numpy().ravel(), getattr(host, n).ravel()
+        assert ks_2samp(a, b).pvalue > 1e-4, n
+    assert float(cols["vol_mean"].min()) >= 14 and float(cols["vol_mean"].max()) <= 29  # SURVEY A.4-3
+    g2 = torch.Generator(device="cuda").manual_seed(5)
+    again = kwm.sample_random_keywords_device(E, K, torch.device("cuda", 0), generator=g2)
+    assert all(torch.equal(cols[n], again[n]) for n in kwm.PARAM_NAMES)
+    env = VectorBiddingSimulation(E, num_keywords=K, device="cuda", seed=1, budget=1e6)
+    env.install_device_keywords(cols, kind=kwm.EXPLICIT)
+    obs = env.step({"keyword_bids": torch.full((E, K), 1.5, device="cuda")})[0]
+    assert int(obs["impressions"].sum()) > 0 and float(obs["cost"].max()) <= 4.4 * 40
