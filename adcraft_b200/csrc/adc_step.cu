@@ -687,16 +687,22 @@ __device__ __forceinline__ Drift3 unit_drift(const adc_step_args &a, const adc_t
 // Unit finished: publish it, and if it was the env's last unit, run the env tail or queue the
 // env for the exact serial walk.  Returns (to the calling thread only) 1 if this env is safe and
 // the caller should apply the drift, 0 otherwise.  Called by ONE thread per unit.
+constexpr int kEnvForceBit = 1 << 30;  // adc_scratch.env_done: some unit of the env asked for the exact walk
+
 __device__ __forceinline__ int unit_done(const adc_step_args &a, int e, long long profit_cents,
-                                         long long cost_cents)
+                                         long long cost_cents, bool force = false)
 {
     if (profit_cents != 0) atomicAdd(reinterpret_cast<unsigned long long *>(a.scratch.env_profit + e),
                                      (unsigned long long)profit_cents);
     if (cost_cents != 0) atomicAdd(reinterpret_cast<unsigned long long *>(a.scratch.env_cost + e),
                                    (unsigned long long)cost_cents);
+    // `force`: the unit could not be evaluated here (beyond the kernel's caps, a tape that ran out, an
+    // env routed by adc_scratch.serial_hint).  The flag rides in the counter word: this thread's OR
+    // precedes its own increment, so the last finisher's increment sees every unit's flag.
+    if (force) atomicOr(a.scratch.env_done + e, kEnvForceBit);
     __threadfence();
     const int old = atomicAdd(a.scratch.env_done + e, 1);
-    if (old != a.kw.K - 1) return 0;
+    if ((old & (kEnvForceBit - 1)) != a.kw.K - 1) return 0;
     __threadfence();
     a.scratch.env_done[e] = 0;
     const long long profit =
@@ -721,7 +727,7 @@ __device__ __forceinline__ int unit_done(const adc_step_args &a, int e, long lon
         reward = cents_to_dollars(profit);
         spend = cents_to_dollars(cost);
     }
-    if (a.force_serial || !budget_is_safe(budget, spend, a.budget_alias)) {
+    if (a.force_serial || (old & kEnvForceBit) || !budget_is_safe(budget, spend, a.budget_alias)) {
         const int slot = atomicAdd(a.scratch.serial_count + (a.parity & 1u), 1);
         a.scratch.serial_list[slot] = e;
         return 0;
@@ -927,13 +933,18 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
             genv = philox_env(a, e);
             const int bid_c = bid_to_cents(load_f(a.bids, a.bids_dtype, u));
             const int win_c = win_cents_of(a, bid_c);
+            // an env whose budget bound in its previous step goes straight to the exact walk (which
+            // evaluates the same function): nothing of it is computed here
+            const bool hinted = a.scratch.serial_hint != nullptr && a.scratch.serial_hint[e] != 0;
             bool outbid = false;  // shared auctions: a rival bids at least as much, no auction can be won
-            if (kFloor) {
+            if (kFloor && !hinted) {
                 floor_c = unit_floor(a, e, k, bid_c);
                 outbid = bid_c <= floor_c;  // (7 of 8 bidder rows of an 8-bidder world stop here)
                 floor_c = max(floor_c, 0);
             }
-            if (!outbid) {
+            if (hinted) {
+                over_cap = true;
+            } else if (!outbid) {
                 const int64_t pi = (int64_t)e * a.kw.env_stride + k;
                 const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)k), genv, k0, k1);
                 const long long v = volume_draw(w.x, a.kw.vol_mean[pi], a.kw.vol_std[pi]);
@@ -1045,7 +1056,7 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
             store_flat_unit(a, e, k, I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
             if (a.out.rows != nullptr) pack_row_unit(a, e, k, I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
-            safe = unit_done(a, e, rev - cost, over_cap ? (1LL << 40) : cost);
+            safe = unit_done(a, e, rev - cost, cost, over_cap);
             if (safe && a.out.rows != nullptr) pack_row_tail(a, e);  // this lane ran the env tail
         }
         if (a.drift.mask != nullptr || a.out.episode_profit_cents != nullptr) {
@@ -1288,7 +1299,7 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
             store_flat_unit(a, e, (int)(u - (int64_t)e * K), I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
-            safe = unit_done(a, e, rev - cost, my_overrun ? (1LL << 40) : cost);
+            safe = unit_done(a, e, rev - cost, cost, my_overrun);
         }
         if (a.drift.mask != nullptr || a.out.episode_profit_cents != nullptr) {
             unsigned todo = __ballot_sync(FULL, safe != 0);
@@ -1696,7 +1707,7 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
             store_flat_unit(a, e, (int)(u - (int64_t)e * K), I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
-            safe = unit_done(a, e, rev - cost, my_overrun ? (1LL << 40) : cost);
+            safe = unit_done(a, e, rev - cost, cost, my_overrun);
         }
         if (a.drift.mask != nullptr || a.out.episode_profit_cents != nullptr) {
             unsigned dm = __ballot_sync(FULL, safe != 0);
@@ -1762,7 +1773,6 @@ adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant_
         // a truncated tape means the recorded run stopped early: make the env look unaffordable
         // so that unit_done queues it for the exact serial walk (2^40 cents per unit: K < 2^20
         // of them still fit the int64 env accumulator)
-        const long long kForceSerialCents = 1LL << 40;
         a.out.impressions[u] = I;
         a.out.clicks[u] = B;
         a.out.conversions[u] = S;
@@ -1779,7 +1789,7 @@ adc_units_kernel(const __grid_constant__ adc_step_args a, const __grid_constant_
             a.out.cost_cents[u] = cost_c;
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost_c));
             store_flat_unit(a, e, k, I, B, S, cents_to_dollars(cost_c), cents_to_dollars(rev_c));
-            safe = unit_done(a, e, rev_c - cost_c, overrun ? kForceSerialCents : cost_c);
+            safe = unit_done(a, e, rev_c - cost_c, cost_c, overrun);
         }
         if (safe) episode_accumulate(a, e, 0, 1);
         if (safe && a.drift.mask != nullptr) {
@@ -1966,47 +1976,46 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
 //   (0) EXPANDS the env's day in the hot kernel's form into a slab of global memory it owns
 //       (adc_scratch.serial_ws): lane <-> keyword, the bit-sliced outcome masks of every 32-auction
 //       group; from them one HEADER WORD per (sub-step, keyword) lane -- impressions, clicked slots,
-//       where the lane's slots start in the env's slot pool -- laid out sub-step-major, and the pool
-//       itself: one word per clicked slot of the day in click order (price in cents | converts << 31),
+//       where the lane's slots start in the keyword's slot pool -- laid out sub-step-major (a running
+//       popcount at the sub-step ends that fall into the group), and the pool itself: 64 words per
+//       keyword, one per clicked slot of the day in click order (price in cents | converts << 31),
 //       prices drawn four per Philox call, flattened over the 32 keywords;
 //   (1) WALKS: per sub-step and chunk of 32 keywords one coalesced load brings the lanes' headers, a
 //       short gather their slots; the whole warp runs ONE uniform scan over them in keyword order --
 //       the reference's f64 sequence `if budget >= cost: budget -= cost`, alias rule and
 //       `remaining <= 0` exit included -- and a lane whose accepted count differs from its slot
 //       count writes it back into its header (nothing else is stored in the loop);
-//   (2) COMMITS: lane <-> keyword again, every keyword sums its lanes that ran -- impressions,
-//       accepted clicks, their prices and conversions, one revenue per conversion by conversion
-//       rank -- and stores the day's outputs once.
+//   (2) COMMITS: lane <-> keyword again, every keyword folds its lanes that ran into a 64-bit mask of
+//       the paid slots: conversions are one popcount against the conversion-by-rank bits, prices a
+//       masked sum over the pool, then one revenue per conversion by conversion rank -- and stores
+//       the day's outputs once.
 // Nothing is re-drawn per sub-step and no keyword count is special.  Lanes the slab cannot
-// describe (volume > 512, more than kSerCap clicked slots in one sub-step, pool overflow) are
+// describe (volume > 512, more than 64 clicked slots in the day or kSerCap in one sub-step) are
 // walked again by lane_walk with the budget (serial_direct_lane) and committed on the spot.
 // ------------------------------------------------------------------------------------------
 constexpr int kSerWarps = 4;
 constexpr int kSerCap = 32;        // clicked slots per lane and sub-step in shared memory; more -> direct re-walk
 constexpr int kSlabGroups = 16;    // 32-auction groups per unit and day the slab describes (volume <= 512)
-constexpr int kPoolPerUnit = 64;   // the env's slot pool holds K x 64 clicked slots; units that do not fit -> direct
+constexpr int kPoolPerUnit = 64;   // a chunk of 32 keywords shares a pool of 32 x 64 clicked slots
+constexpr int kChunkPool = 32 * kPoolPerUnit;
+constexpr int kUnitSlots = 256;    // clicked slots of one unit's day the slab describes; more -> direct
 constexpr int kSerMinBlocks = 7;   // 28 warps per SM: a 4096-env queue is resident in one wave
 
 // lane header: bits 0..5 clicked slots (after the walk: accepted ones), 6..11 impressions, 12..31 first slot
-// in the pool.  Slot field 63: the lane is walked by lane_walk; 62: it was, and bits 12..31 hold its conversions.
+// in the chunk's pool.  Slot field 63: the lane is walked by lane_walk; 62: it was, and bits 12..31 hold its
+// conversions.
 constexpr uint32_t kHdrDirect = 63u, kHdrDirectDone = 62u, kHdrMaxCount = 61u;
 
-struct __align__(16) SlabUnit {     // 96 B per keyword
-    uint32_t convr[kSlabGroups];    // bit r: the r-th clicked slot of the day converts
-    int win_cents;
+struct __align__(8) SlabUnit {      // 8 B per keyword
     float rev_mean, rev_sd;
-    int volume;
-    uint32_t pool_off;              // first slot of the unit in the env's pool
-    uint32_t flags;                 // bit 0: the whole unit is walked by lane_walk (beyond the slab's caps)
-    uint32_t pad[2];
 };
-static_assert(sizeof(SlabUnit) == 96, "slab layout");
 
-// slab of one warp: SlabUnit[K] | uint32 hdr[24][Kp] (Kp = K rounded up to 32) | uint32 pool[K * kPoolPerUnit]
+// slab of one warp: uint32 hdr[24][Kp] (Kp = K rounded up to 32) | uint32 pool[Kp / 32][kChunkPool] | SlabUnit[K]
 __host__ __device__ inline int64_t slab_kp(int K) { return ((int64_t)K + 31) & ~(int64_t)31; }
 __host__ __device__ inline int64_t slab_bytes_of(int K)
 {
-    return (int64_t)K * (int64_t)sizeof(SlabUnit) + (int64_t)ADC_SUBSTEPS * slab_kp(K) * 4 + (int64_t)K * kPoolPerUnit * 4;
+    const int64_t raw = (int64_t)ADC_SUBSTEPS * slab_kp(K) * 4 + slab_kp(K) * kPoolPerUnit * 4 + (int64_t)K * (int64_t)sizeof(SlabUnit);
+    return (raw + 15) & ~(int64_t)15;
 }
 
 // A (sub-step, keyword) lane the slab cannot describe: walked again with the budget by lane_walk.  Out
@@ -2051,12 +2060,56 @@ __device__ __noinline__ int conversions_before(const uint32_t *hdr, const uint32
     return s;
 }
 
+// Commit of a keyword that had lanes walked by lane_walk (rare): the slab lanes that ran, in sub-step
+// order, with the revenue-draw ranks the direct lanes' conversions shift.  Out of line.
+struct CommitOut {
+    int I, B, S;
+    long long cost_c, rev_c;
+};
+
+__device__ __noinline__ CommitOut commit_mixed_unit(const PhiloxSrc &src, const uint32_t *hdr, const uint32_t *pool,
+                                                    int64_t Kp, int k, int t_stop, int k_stop, float rm, float rs)
+{
+    CommitOut o;
+    o.I = o.B = o.S = 0; o.cost_c = o.rev_c = 0;
+    uint4 rw = make_uint4(0, 0, 0, 0);
+    int rw_idx = -1;
+    for (int t = 0; t < ADC_SUBSTEPS; ++t) {
+        if (t > t_stop || (t == t_stop && k > k_stop)) break;  // after the early break nothing ran
+        const uint32_t h = hdr[(int64_t)t * Kp + k];
+        const uint32_t f = h & 63u;
+        if (f == kHdrDirectDone) { o.S += (int)(h >> 12); continue; }  // committed on the spot
+        if (f == kHdrDirect) continue;
+        o.I += (int)((h >> 6) & 63u);
+        o.B += (int)f;
+        for (uint32_t i = 0; i < f; ++i) {
+            const uint32_t w = pool[(h >> 12) + i];
+            o.cost_c += (int)(w & 0x7FFFFFFFu);
+            if (w >> 31) {  // one revenue per conversion, by conversion rank (direct lanes' included)
+                const int r = o.S++;
+                if ((r >> 2) != rw_idx) {
+                    rw_idx = r >> 2;
+                    rw = src.draw(ST_REVENUE, (uint32_t)k, (uint32_t)rw_idx);
+                }
+                const uint32_t ww = (r & 3) == 0 ? rw.x : (r & 3) == 1 ? rw.y : (r & 3) == 2 ? rw.z : rw.w;
+                o.rev_c += revenue_cents(ww, rm, rs);
+            }
+        }
+    }
+    return o;
+}
+
 __global__ void __launch_bounds__(kSerWarps * 32, kSerMinBlocks)
 adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_slabs)
 {
+    // per warp 4 KB: phase 0 keeps the chunk's 24 x 32 headers and 8 x 32 conversion-by-rank words here,
+    // phase 1 the clicked slots of the current round
     __shared__ uint32_t s_slot[kSerWarps][kSerCap][32];
+    static_assert(kSerCap * 32 >= ADC_SUBSTEPS * 32 + (kUnitSlots / 32) * 32, "phase-0 staging fits the slot buffer");
     __shared__ FlatCost s_cost[kSerWarps][32];
+    __shared__ __align__(16) double s_lsum[kSerWarps][32];
     __shared__ int s_start[kSerWarps][32];
+    __shared__ int s_poff[kSerWarps][32];
     __shared__ unsigned char s_nzl[kSerWarps][32];
     __shared__ float2 s_tab[128];  // Exp(1) sampler table, staged from global
     if (threadIdx.x < 128) s_tab[threadIdx.x] = kNeglogTab[threadIdx.x];
@@ -2074,28 +2127,30 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
     const adc_tape *no_tape = nullptr;
     if (gwarp >= n_warps) return;
     unsigned char *const slab_raw = reinterpret_cast<unsigned char *>(a.scratch.serial_ws) + (size_t)gwarp * (size_t)slab_bytes_of(K);
-    SlabUnit *const slab = reinterpret_cast<SlabUnit *>(slab_raw);
-    uint32_t *const hdr = reinterpret_cast<uint32_t *>(slab_raw + (size_t)K * sizeof(SlabUnit));
-    uint32_t *const pool = hdr + (size_t)ADC_SUBSTEPS * Kp;
-    const unsigned pool_cap = min((unsigned)K * (unsigned)kPoolPerUnit, 1u << 20);  // 20-bit slot index in the header
+    uint32_t *const hdr = reinterpret_cast<uint32_t *>(slab_raw);
+    uint32_t *const pool = hdr + (size_t)ADC_SUBSTEPS * Kp;  // chunk c0 / 32 owns pool[c0 * kPoolPerUnit ..)
+    SlabUnit *const slab = reinterpret_cast<SlabUnit *>(pool + (size_t)Kp * kPoolPerUnit);
+    const int n_chunks = (K + 31) >> 5;
+    uint32_t *const s_hdr = &s_slot[warp][0][0];          // [24][32]
+    uint32_t *const s_cv = s_hdr + ADC_SUBSTEPS * 32;     // [kUnitSlots / 32][32]: bit r of a lane's words: its r-th click converts
 
     for (int idx = gwarp; idx < count; idx += n_warps) {
         const int e = a.scratch.serial_list[idx];
         PhiloxSrc src{k0, k1, a.step, philox_env(a, e)};
         // ---- phase 0: expand the day into the slab, 32 keywords at a time
-        unsigned pool_used = 0;  // warp-uniform
         for (int c0 = 0; c0 < K; c0 += 32) {
             // (a) lane <-> keyword: thresholds, volume, outcome masks -> lane headers, conversion-by-rank bits
             const int k = c0 + lane;
-            int B = 0;
-            unsigned char cnt_i[ADC_SUBSTEPS], cnt_c[ADC_SUBSTEPS];  // impressions / clicked slots per sub-step
-#pragma unroll
-            for (int t = 0; t < ADC_SUBSTEPS; ++t) { cnt_i[t] = 0; cnt_c[t] = 0; }
+            const bool act = k < K;
             bool whole_direct = false;
-            FlatCost fc;
-            fc.t1 = fc.h1 = fc.a1 = fc.a2 = 0u; fc.L = 0.f; fc.b = 0.f; fc.W = 1; fc.floor_c = 0;
-            fc.n0 = fc.n1 = fc.x3 = 0u; fc.B = 0;
-            if (k < K) {
+            int V = 0;
+            Unit2 u2;
+            u2.t1 = u2.t2 = u2.t3 = u2.full = u2.h1 = u2.a1 = u2.a2 = 0u; u2.L = 0.f; u2.b = 0.f; u2.W = 1;
+            int floor_c = 0;
+            __syncwarp();
+#pragma unroll
+            for (int w = 0; w < kUnitSlots / 32; ++w) s_cv[w * 32 + lane] = 0u;
+            if (act) {
                 const int64_t u = (int64_t)e * K + k;
                 acc.I[u] = 0;  // the direct lanes accumulate here; everything else is stored once in phase 2
                 acc.B[u] = 0;
@@ -2105,78 +2160,83 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 const UnitPar p = load_unit_par(a, e, k, true);
                 uint4 uw;
                 const long long Vl = unit_volume(a, src, no_tape, e, k, &uw);
-                SlabUnit *su = slab + k;
                 const bool beats_rivals = p.u2.W > p.floor_cents;
+                // what the slab cannot describe: long days, bids beyond the 16-bit prices
                 whole_direct = (Vl > 32 * kSlabGroups || p.win_cents > kMaxFlatBidCents) && beats_rivals;
-                const int V = whole_direct || !beats_rivals ? 0 : (int)Vl;
-                su->volume = V;
-                su->win_cents = p.win_cents;
-                su->rev_mean = p.rev_mean;
-                su->rev_sd = p.rev_sd;
-#pragma unroll
-                for (int g = 0; g < kSlabGroups; ++g) su->convr[g] = 0u;
+                V = whole_direct || !beats_rivals ? 0 : (int)Vl;
+                u2 = p.u2;
+                floor_c = max(p.floor_cents, 0);
+                SlabUnit su;
+                su.rev_mean = p.rev_mean; su.rev_sd = p.rev_sd;
+                slab[k] = su;
+            }
+            int baseI = 0, baseC = 0;
+            {
                 const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), src.env, k0, k1);
                 const int q = V / ADC_SUBSTEPS, n0 = V - (ADC_SUBSTEPS - 1) * q;  // bsim:151-167
-                for (int g = 0; 32 * g < V; ++g) {
+                int t = 0, end_t = n0;     // sub-step t ends before auction end_t
+                int lastI = 0, lastC = 0;  // impressions / clicked slots of the sub-steps already emitted
+                const int Gmax = __reduce_max_sync(FULL, (V + 31) >> 5);
+                for (int g = 0; g < Gmax; ++g) {
                     const int rem = V - 32 * g;
-                    const uint32_t active = rem >= 32 ? 0xFFFFFFFFu : (1u << rem) - 1u;
-                    const Masks3 m = group_masks(active, (uint32_t)g, p.u2.t1, p.u2.t2, p.u2.t3, p.u2.full, pa.n0, pa.n1,
+                    const uint32_t active = rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? (1u << rem) - 1u : 0u);
+                    const Masks3 m = group_masks(active, (uint32_t)g, u2.t1, u2.t2, u2.t3, u2.full, pa.n0, pa.n1,
                                                  pa.x3, k0, k1);
-                    // conversion flags by click rank: the click bits in order
-                    uint32_t cl = m.click;
-                    while (cl) {
-                        const int bpos = __ffs(cl) - 1;
-                        cl &= cl - 1;
-                        if ((m.conv >> bpos) & 1u) su->convr[(B >> 5) & (kSlabGroups - 1)] |= 1u << (B & 31);
-                        ++B;
+                    // conversion flags by click rank
+                    uint32_t cv = m.conv;
+                    while (cv) {
+                        const int bpos = __ffs(cv) - 1;
+                        cv &= cv - 1;
+                        const int r = baseC + __popc(m.click & ((1u << bpos) - 1u));
+                        if (r < kUnitSlots) s_cv[(r >> 5) * 32 + lane] |= 1u << (r & 31);
                     }
-                    // this group's share of every sub-step it overlaps
-                    const int j_lo = 32 * g, j_hi = min(32 * g + 32, V);
-                    int t = j_lo < n0 ? 0 : (q > 0 ? 1 + (j_lo - n0) / q : 0);
-                    while (t < ADC_SUBSTEPS) {
-                        const int s0 = t == 0 ? 0 : n0 + (t - 1) * q, s1 = t == 0 ? n0 : s0 + q;
-                        if (s0 >= j_hi) break;
-                        const int lo = max(s0, j_lo) - j_lo, hi = min(s1, j_hi) - j_lo;
-                        if (hi > lo) {
-                            const uint32_t range = (hi >= 32 ? 0xFFFFFFFFu : (1u << hi) - 1u) & ~((1u << lo) - 1u);
-                            cnt_i[t] = (unsigned char)min(cnt_i[t] + __popc(m.win & range), 255);
-                            cnt_c[t] = (unsigned char)min(cnt_c[t] + __popc(m.click & range), 255);
-                        }
+                    // the sub-steps that end inside this group: one header each
+                    const int hi = min(32 * g + 32, V);
+                    while (rem > 0 && t < ADC_SUBSTEPS && end_t <= hi) {
+                        const int low = end_t - 32 * g;  // 1..32 (0 only for the empty sub-steps of a short day)
+                        const uint32_t lm = low >= 32 ? 0xFFFFFFFFu : (1u << low) - 1u;
+                        const int cumI = baseI + __popc(m.win & lm), cumC = baseC + __popc(m.click & lm);
+                        const int ci = cumI - lastI, cc = cumC - lastC;
+                        uint32_t h = (uint32_t)cc | ((uint32_t)ci << 6) | ((uint32_t)min(lastC, kUnitSlots) << 12);
+                        if (cc > kSerCap || ci > (int)kHdrMaxCount) h = kHdrDirect;  // beyond a header's counts
+                        s_hdr[t * 32 + lane] = h;
+                        lastI = cumI; lastC = cumC;
                         ++t;
+                        end_t += q;
                     }
+                    baseI += __popc(m.win);
+                    baseC += __popc(m.click);
                 }
-                su->flags = whole_direct ? 1u : 0u;
-                const PhiloxPre pc = philox_pre(a.step, stream_word(ST_COST, 0u, (uint32_t)k), src.env, k0, k1);
-                fc.t1 = p.u2.t1; fc.h1 = p.u2.h1; fc.a1 = p.u2.a1; fc.a2 = p.u2.a2; fc.L = p.u2.L; fc.b = p.u2.b;
-                fc.W = p.u2.W | ((p.u2.full & 1u) ? (int)0x80000000u : 0);
-                fc.floor_c = max(p.floor_cents, 0); fc.n0 = pc.n0; fc.n1 = pc.n1; fc.x3 = pc.x3; fc.B = B;
+                // a unit with more clicked slots than the slab describes: every lane is walked by lane_walk
+                if (baseC > kUnitSlots) whole_direct = true;
+                for (; t < ADC_SUBSTEPS; ++t) s_hdr[t * 32 + lane] = 0u;
             }
-            {   // room in the env's slot pool (units padded to 4 slots); a unit that does not fit is re-walked
+            int B = whole_direct ? 0 : baseC;
+            {   // room in the chunk's slot pool (units padded to 4 slots); a unit that does not fit is re-walked
                 const int b4 = (B + 3) & ~3;
-                const int incl = warp_incl_scan(b4, lane);
-                const unsigned off = pool_used + (unsigned)(incl - b4);
-                if (k < K) {
-                    SlabUnit *su = slab + k;
-                    su->pool_off = off;
-                    if (off + (unsigned)b4 > pool_cap) { su->flags = 1u; whole_direct = true; B = 0; fc.B = 0; }
-                    // lane headers, sub-step-major: one coalesced store per sub-step
-                    unsigned cb = off;
+                const int off = warp_incl_scan(b4, lane) - b4;
+                if (off + b4 > kChunkPool) { whole_direct = true; B = 0; }
+                s_poff[warp][lane] = off;
+                // the lanes' headers, sub-step-major: one coalesced store per sub-step
+                if (act) {
+                    const uint32_t add = (uint32_t)off << 12;
+#pragma unroll 4
                     for (int t = 0; t < ADC_SUBSTEPS; ++t) {
-                        uint32_t h;
-                        if (whole_direct) h = kHdrDirect;
-                        else if (cnt_c[t] > kSerCap || cnt_i[t] > kHdrMaxCount) h = kHdrDirect | (cb << 12);
-                        else h = (uint32_t)cnt_c[t] | ((uint32_t)cnt_i[t] << 6) | (cb << 12);
-                        hdr[(int64_t)t * Kp + k] = h;
-                        cb += cnt_c[t];
+                        const uint32_t h = s_hdr[t * 32 + lane];
+                        hdr[(int64_t)t * Kp + k] = whole_direct ? kHdrDirect : ((h & 63u) == kHdrDirect ? h : h + add);
                     }
                 }
-                pool_used = min(pool_used + (unsigned)__shfl_sync(FULL, incl, 31), pool_cap);
+                const PhiloxPre pc = philox_pre(a.step, stream_word(ST_COST, 0u, (uint32_t)k), src.env, k0, k1);
+                FlatCost fc;
+                fc.t1 = u2.t1; fc.h1 = u2.h1; fc.a1 = u2.a1; fc.a2 = u2.a2; fc.L = u2.L; fc.b = u2.b;
+                fc.W = u2.W | ((u2.full & 1u) ? (int)0x80000000u : 0);
+                fc.floor_c = floor_c; fc.n0 = pc.n0; fc.n1 = pc.n1; fc.x3 = pc.x3; fc.B = B;
+                s_cost[warp][lane] = fc;
             }
-            __syncwarp();
-            s_cost[warp][lane] = fc;
             // (b) one price per clicked slot, 4 per Philox call, flattened over the 32 keywords
             const FlatMap fm = flat_map_begin((B + 3) >> 2, lane, s_start[warp], s_nzl[warp]);
             const int TB = fm.total;
+            uint32_t *const cpool = pool + (size_t)c0 * kPoolPerUnit;
             for (int base = 0; base < TB; base += 32) {
                 const int b = flat_map_unit(fm, base, lane, s_nzl[warp]);
                 const int i = base + lane;
@@ -2186,146 +2246,158 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                     const uint4 w = philox_from_pre((uint32_t)q, f.n0, f.n1, f.x3, k0, k1);
                     const bool t1_full = f.W < 0;
                     const int W = f.W & 0x7FFFFFFF;
-                    const SlabUnit *sb = slab + c0 + b;
-                    const uint32_t cvw = sb->convr[((4 * q) >> 5) & (kSlabGroups - 1)] >> ((4 * q) & 31);  // 4 q .. 4 q + 3 share a word
+                    const uint32_t cvw = s_cv[((4 * q) >> 5) * 32 + b] >> ((4 * q) & 31);  // 4 q .. 4 q + 3 share a word
                     uint4 pk;
                     pk.x = (uint32_t)max(cost_cents2(w.x, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c) | ((cvw & 1u) << 31);
                     pk.y = (uint32_t)max(cost_cents2(w.y, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c) | (((cvw >> 1) & 1u) << 31);
                     pk.z = (uint32_t)max(cost_cents2(w.z, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c) | (((cvw >> 2) & 1u) << 31);
                     pk.w = (uint32_t)max(cost_cents2(w.w, f.t1, t1_full, f.h1, f.a1, f.a2, f.L, f.b, W, s_tab), f.floor_c) | (((cvw >> 3) & 1u) << 31);
-                    *reinterpret_cast<uint4 *>(pool + sb->pool_off + 4 * q) = pk;  // offsets are multiples of 4 slots
+                    *reinterpret_cast<uint4 *>(cpool + s_poff[warp][b] + 4 * q) = pk;  // offsets are multiples of 4 slots
                 }
             }
             __syncwarp();
         }
         __threadfence_block();
         __syncwarp();
-        // ---- phase 1: the walk
+        // ---- phase 1: the walk; the next round's headers are loaded while this round is scanned
         const double budget = step_budget(a, e);
         double remaining = budget;  // warp-uniform (bsim:214)
         bool stop = false;
+        bool bound = false;  // some round could not be proven fully affordable: next step comes here directly
         int t_stop = ADC_SUBSTEPS, k_stop = K;  // the lane after which nothing ran (bsim:230-233)
-        for (int t = 0; t < ADC_SUBSTEPS && !stop; ++t) {
-            for (int c0 = 0; c0 < K && !stop; c0 += 32) {
-                const int k = c0 + lane;
-                const bool act = k < K;
-                const int64_t u = (int64_t)e * K + (act ? k : 0);
-                // the lanes' headers (one coalesced load), then their clicked slots from the pool
-                const uint32_t h = act ? hdr[(int64_t)t * Kp + k] : 0u;
-                // a chunk without an impression or a clicked slot in this sub-step leaves everything alone
-                // (a sparse keyword, V < 24, has its whole day in sub-step 0); `remaining <= 0` on entry still
-                // gets its one look
-                if (remaining > 0 && __all_sync(FULL, (h & 0xFFFu) == 0u)) continue;
-                int nclk = (int)(h & 63u);
-                const bool direct = nclk == (int)kHdrDirect;
-                const int win_c = act ? slab[k].win_cents : 0;
-                if (direct) nclk = kSerCap + 1;  // takes the re-walk turn below
-                else
-                    for (int i = 0; i < nclk; ++i) s_slot[warp][i][lane] = pool[(h >> 12) + i];
-                __syncwarp();
-                // ---- one uniform scan over the lanes that have clicks: the reference's budget walk
-                int B = direct ? 0 : nclk;
-                unsigned todo = __ballot_sync(FULL, act && nclk > 0);
-                if (!(remaining > 0)) todo |= 1u;  // a lane must run for `remaining <= 0` to be seen
-                int cutoff = 32;
-                DirectOut dout;
-                dout.I = dout.B = dout.S = 0; dout.cost_c = dout.rev_c = 0; dout.next = 0.0;
-                bool direct_done = false;
-                // Two shortcuts that leave the reference's f64 sequence intact:
-                // (a) nothing affordable -- every lane's first click costs more than `remaining`, so each
-                //     lane breaks at once (bsim:99-104) and `remaining` does not move: the usual state of
-                //     the sub-steps after the budget ran dry;
-                // (b) everything affordable -- `remaining` exceeds this round's total spend (exact cents,
-                //     doubled under the alias rule) by more than a cent, so no `budget >= cost` test can
-                //     fail; without the alias rule the walk is then per lane `remaining -= lane_sum` with
-                //     lane_sum the lane's own sequential f64 sum (bsim:225 + rust sum_list), which the
-                //     lanes form in parallel.
-                bool all_accepted = false;
-                if (remaining > 0) {
-                    const bool lane_has = act && nclk > 0;
-                    const bool none = !lane_has || (!direct && !(remaining >= cents_to_dollars(slot_cost(0, lane))));
-                    if (__all_sync(FULL, none)) {
-                        todo = 0;
-                        B = 0;
-                    } else if (!__any_sync(FULL, nclk > kSerCap || win_c > kMaxFlatBidCents)) {
-                        unsigned cents = 0;
-                        double lane_sum = 0.0;
-                        for (int i = 0; i < nclk; ++i) {
-                            const int c = slot_cost(i, lane);
-                            lane_sum = __dadd_rn(lane_sum, cents_to_dollars(c));
-                            cents += (unsigned)c;
-                        }
-                        const unsigned total = __reduce_add_sync(FULL, cents);  // <= 32 lanes x kSerCap x 65535 < 2^32 (bids capped above)
-                        const double spend = __ddiv_rn((double)total, 100.0);
-                        if (remaining > (a.budget_alias ? spend + spend : spend) + 0.01) {
-                            all_accepted = true;
-                            while (todo) {
-                                const int l = __ffs(todo) - 1;
-                                todo &= todo - 1;
-                                double b = remaining;
-                                if (a.budget_alias) {  // the lane's own walk already drew on the shared budget (bsim:102)
-                                    const int n_l = __shfl_sync(FULL, nclk, l);
-                                    for (int i = 0; i < n_l; ++i) b = __dsub_rn(b, cents_to_dollars(slot_cost(i, l)));
-                                }
-                                remaining = __dsub_rn(b, __shfl_sync(FULL, lane_sum, l));
-                            }
-                        }
-                    }
-                }
-                if (!all_accepted && todo) B = 0;  // the scan below decides lane by lane; lanes it never reaches accept nothing
-                while (todo) {
-                    const int l = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int n_l = __shfl_sync(FULL, nclk, l);
-                    double next;
-                    if (n_l <= kSerCap) {  // every lane runs lane l's walk on the buffered f64 costs
-                        double b = remaining, lane_sum = 0.0;
-                        int nacc = 0;
-                        for (int i = 0; i < n_l; ++i) {
-                            const double cost = cents_to_dollars(slot_cost(i, l));
-                            if (!(b >= cost)) break;  // bsim:99-104
-                            ++nacc;
-                            lane_sum = __dadd_rn(lane_sum, cost);
-                            b = __dsub_rn(b, cost);
-                        }
-                        if (lane == l) B = nacc;
-                        next = __dsub_rn(a.budget_alias ? b : remaining, lane_sum);  // bsim:102 alias, :225
-                    } else {  // beyond the slab or the buffer: lane l walks its sub-step again, with the budget
-                        next = remaining;
-                        if (lane == l) {
-                            dout = serial_direct_lane(a, src, e, k, t, conversions_before(hdr, pool, Kp, k, t), remaining);
-                            direct_done = true;
-                            next = dout.next;
-                        }
-                        next = __shfl_sync(FULL, next, l);
-                    }
-                    remaining = next;
-                    if (remaining <= 0) {  // bsim:230-233
-                        stop = true;
-                        cutoff = l;
-                        t_stop = t;
-                        k_stop = c0 + l;
-                        break;
-                    }
-                }
-                // the lanes that ran write back what the commit cannot infer: an accepted count below the
-                // slot count, a direct lane's totals
-                if (act && lane <= cutoff) {
-                    if (direct_done) {
-                        acc.I[u] += dout.I;
-                        acc.B[u] += dout.B;
-                        acc.S[u] += dout.S;
-                        a.out.cost_cents[u] += dout.cost_c;
-                        a.out.revenue_cents[u] += dout.rev_c;
-                        hdr[(int64_t)t * Kp + k] = kHdrDirectDone | ((uint32_t)dout.S << 12);
-                    } else if (direct) {
-                        hdr[(int64_t)t * Kp + k] = kHdrDirectDone;  // never reached: nothing of it counts
-                    } else if (B != nclk) {
-                        hdr[(int64_t)t * Kp + k] = (h & ~63u) | (uint32_t)B;
-                    }
-                }
-                __syncwarp();
+        uint32_t h_next = lane < K ? hdr[lane] : 0u;
+        for (int round = 0; round < ADC_SUBSTEPS * n_chunks && !stop; ++round) {
+            const int t = round / n_chunks, c0 = (round - t * n_chunks) << 5;
+            const int k = c0 + lane;
+            const bool act = k < K;
+            const int64_t u = (int64_t)e * K + (act ? k : 0);
+            const uint32_t h = h_next;
+            {
+                const int rn = round + 1, tn = rn / n_chunks, kn = ((rn - tn * n_chunks) << 5) + lane;
+                h_next = (tn < ADC_SUBSTEPS && kn < K) ? hdr[(int64_t)tn * Kp + kn] : 0u;
             }
+            // a chunk without an impression or a clicked slot in this sub-step leaves everything alone
+            // (a sparse keyword, V < 24, has its whole day in sub-step 0); `remaining <= 0` on entry still
+            // gets its one look
+            if (remaining > 0 && __all_sync(FULL, (h & 0xFFFu) == 0u)) continue;
+            int nclk = (int)(h & 63u);
+            const bool direct = nclk == (int)kHdrDirect;
+            if (direct) nclk = kSerCap + 1;  // takes the re-walk turn below
+            else
+                for (int i = 0; i < nclk; ++i) s_slot[warp][i][lane] = pool[(size_t)c0 * kPoolPerUnit + (h >> 12) + i];
+            __syncwarp();
+            // ---- one uniform scan over the lanes that have clicks: the reference's budget walk
+            int B = direct ? 0 : nclk;
+            unsigned todo = __ballot_sync(FULL, act && nclk > 0);
+            const bool any_click = todo != 0u;
+            if (!(remaining > 0)) todo |= 1u;  // a lane must run for `remaining <= 0` to be seen
+            int cutoff = 32;
+            DirectOut dout;
+            dout.I = dout.B = dout.S = 0; dout.cost_c = dout.rev_c = 0; dout.next = 0.0;
+            bool direct_done = false;
+            // Two shortcuts that leave the reference's f64 sequence intact:
+            // (a) nothing affordable -- every lane's first click costs more than `remaining`, so each
+            //     lane breaks at once (bsim:99-104) and `remaining` does not move: the usual state of
+            //     the sub-steps after the budget ran dry;
+            // (b) everything affordable -- `remaining` exceeds this round's total spend (exact cents,
+            //     doubled under the alias rule) by more than a cent, so no `budget >= cost` test can
+            //     fail; without the alias rule the walk is then per lane `remaining -= lane_sum` with
+            //     lane_sum the lane's own sequential f64 sum (bsim:225 + rust sum_list), which the
+            //     lanes form in parallel (a lane without clicks subtracts an exact 0.0).
+            bool all_accepted = false;
+            if (remaining > 0) {
+                const bool lane_has = act && nclk > 0;
+                const bool none = !lane_has || (!direct && !(remaining >= cents_to_dollars(slot_cost(0, lane))));
+                if (__all_sync(FULL, none)) {
+                    todo = 0;
+                    B = 0;
+                } else if (!__any_sync(FULL, nclk > kSerCap)) {
+                    unsigned cents = 0;
+                    double lane_sum = 0.0;
+                    for (int i = 0; i < nclk; ++i) {
+                        const int c = slot_cost(i, lane);
+                        lane_sum = __dadd_rn(lane_sum, cents_to_dollars(c));
+                        cents += (unsigned)c;
+                    }
+                    const unsigned total = __reduce_add_sync(FULL, cents);  // <= 32 lanes x kSerCap x 65535 < 2^32 (bids capped above)
+                    const double spend = __ddiv_rn((double)total, 100.0);
+                    if (remaining > (a.budget_alias ? spend + spend : spend) + 0.01) {
+                        all_accepted = true;
+                        if (!a.budget_alias) {
+                            s_lsum[warp][lane] = lane_sum;
+                            __syncwarp();
+#pragma unroll
+                            for (int l = 0; l < 32; l += 2) {
+                                const double2 v = *reinterpret_cast<const double2 *>(&s_lsum[warp][l]);
+                                remaining = __dsub_rn(__dsub_rn(remaining, v.x), v.y);
+                            }
+                            todo = 0;
+                        }
+                        while (todo) {  // the lane's own walk already drew on the shared budget (bsim:102)
+                            const int l = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            double b = remaining;
+                            const int n_l = __shfl_sync(FULL, nclk, l);
+                            for (int i = 0; i < n_l; ++i) b = __dsub_rn(b, cents_to_dollars(slot_cost(i, l)));
+                            remaining = __dsub_rn(b, __shfl_sync(FULL, lane_sum, l));
+                        }
+                    }
+                }
+            }
+            bound = bound || (any_click && !all_accepted);
+            if (!all_accepted && todo) B = 0;  // the scan below decides lane by lane; lanes it never reaches accept nothing
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int n_l = __shfl_sync(FULL, nclk, l);
+                double next;
+                if (n_l <= kSerCap) {  // every lane runs lane l's walk on the buffered f64 costs
+                    double b = remaining, lane_sum = 0.0;
+                    int nacc = 0;
+                    for (int i = 0; i < n_l; ++i) {
+                        const double cost = cents_to_dollars(slot_cost(i, l));
+                        if (!(b >= cost)) break;  // bsim:99-104
+                        ++nacc;
+                        lane_sum = __dadd_rn(lane_sum, cost);
+                        b = __dsub_rn(b, cost);
+                    }
+                    if (lane == l) B = nacc;
+                    next = __dsub_rn(a.budget_alias ? b : remaining, lane_sum);  // bsim:102 alias, :225
+                } else {  // beyond the slab or the buffer: lane l walks its sub-step again, with the budget
+                    next = remaining;
+                    if (lane == l) {
+                        dout = serial_direct_lane(a, src, e, k, t, conversions_before(hdr, pool + (size_t)c0 * kPoolPerUnit, Kp, k, t), remaining);
+                        direct_done = true;
+                        next = dout.next;
+                    }
+                    next = __shfl_sync(FULL, next, l);
+                }
+                remaining = next;
+                if (remaining <= 0) {  // bsim:230-233
+                    stop = true;
+                    cutoff = l;
+                    t_stop = t;
+                    k_stop = c0 + l;
+                    break;
+                }
+            }
+            // the lanes that ran write back what the commit cannot infer: an accepted count below the
+            // slot count, a direct lane's totals
+            if (act && lane <= cutoff) {
+                if (direct_done) {
+                    acc.I[u] += dout.I;
+                    acc.B[u] += dout.B;
+                    acc.S[u] += dout.S;
+                    a.out.cost_cents[u] += dout.cost_c;
+                    a.out.revenue_cents[u] += dout.rev_c;
+                    hdr[(int64_t)t * Kp + k] = kHdrDirectDone | ((uint32_t)dout.S << 12);
+                } else if (direct) {
+                    hdr[(int64_t)t * Kp + k] = kHdrDirectDone;  // never reached: nothing of it counts
+                } else if (B != nclk) {
+                    hdr[(int64_t)t * Kp + k] = (h & ~63u) | (uint32_t)B;
+                }
+            }
+            __syncwarp();
         }
         __threadfence_block();
         __syncwarp();
@@ -2333,56 +2405,65 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
         long long profit_c = 0;
         for (int k = lane; k < K; k += 32) {
             const int64_t u = (int64_t)e * K + k;
-            const SlabUnit *su = slab + k;
-            const float rm = su->rev_mean, rs = su->rev_sd;
+            const SlabUnit su = slab[k];
+            const uint32_t *const cpool = pool + (size_t)(k & ~31) * kPoolPerUnit;
             int I = 0, B = 0, S = 0;
             long long cost_c = 0, rev_c = 0;
-            uint4 rw = make_uint4(0, 0, 0, 0);
-            int rw_idx = -1;
+            bool mixed = false;
             for (int t = 0; t < ADC_SUBSTEPS; ++t) {
                 if (t > t_stop || (t == t_stop && k > k_stop)) break;  // after the early break nothing ran
                 const uint32_t h = hdr[(int64_t)t * Kp + k];
                 const uint32_t f = h & 63u;
-                if (f == kHdrDirectDone) { S += (int)(h >> 12); continue; }  // committed on the spot
-                if (f == kHdrDirect) continue;
+                if (f >= kHdrDirectDone) { mixed = true; continue; }
                 I += (int)((h >> 6) & 63u);
                 B += (int)f;
-                for (uint32_t i = 0; i < f; ++i) {
-                    const uint32_t w = pool[(h >> 12) + i];
+                for (uint32_t i = 0; i < f; ++i) {  // the slots that were paid for
+                    const uint32_t w = cpool[(h >> 12) + i];
                     cost_c += (int)(w & 0x7FFFFFFFu);
-                    if (w >> 31) {  // one revenue per conversion, by conversion rank (direct lanes' included)
-                        const int r = S++;
-                        if ((r >> 2) != rw_idx) {
-                            rw_idx = r >> 2;
-                            rw = src.draw(ST_REVENUE, (uint32_t)k, (uint32_t)rw_idx);
-                        }
-                        const uint32_t ww = (r & 3) == 0 ? rw.x : (r & 3) == 1 ? rw.y : (r & 3) == 2 ? rw.z : rw.w;
-                        rev_c += revenue_cents(ww, rm, rs);
-                    }
+                    S += (int)(w >> 31);
                 }
             }
-            // S counted the direct lanes' conversions for the ranks only: they are in acc.S already
-            const int S_direct = acc.S[u];
-            I += acc.I[u];
-            B += acc.B[u];
-            cost_c += a.out.cost_cents[u];
-            rev_c += a.out.revenue_cents[u];
+            if (!mixed) {
+                for (int r4 = 0; 4 * r4 < S; ++r4) {  // one revenue per conversion, by conversion rank
+                    const uint4 rw = src.draw(ST_REVENUE, (uint32_t)k, (uint32_t)r4);
+                    const int left = S - 4 * r4;
+                    rev_c += revenue_cents(rw.x, su.rev_mean, su.rev_sd);
+                    if (left > 1) rev_c += revenue_cents(rw.y, su.rev_mean, su.rev_sd);
+                    if (left > 2) rev_c += revenue_cents(rw.z, su.rev_mean, su.rev_sd);
+                    if (left > 3) rev_c += revenue_cents(rw.w, su.rev_mean, su.rev_sd);
+                }
+            } else {
+                // a keyword with lanes walked by lane_walk: their conversions shift the revenue ranks of the
+                // slab lanes (S of the mixed commit counts them too: they are in acc.S already)
+                const CommitOut o = commit_mixed_unit(src, hdr, cpool, Kp, k, t_stop, k_stop, su.rev_mean, su.rev_sd);
+                I = o.I + acc.I[u];
+                B = o.B + acc.B[u];
+                S = o.S;
+                cost_c = o.cost_c + a.out.cost_cents[u];
+                rev_c = o.rev_c + a.out.revenue_cents[u];
+            }
             acc.I[u] = I;
             acc.B[u] = B;
             acc.S[u] = S;
-            (void)S_direct;
             a.out.cost_cents[u] = cost_c;
             a.out.revenue_cents[u] = rev_c;
             store_f(a.out.cost, a.out.float_dtype, u, cents_to_dollars(cost_c));
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev_c));
-            ser_publish(a, acc, u);
+            if (acc.I != a.out.impressions) {
+                a.out.impressions[u] = I;
+                a.out.clicks[u] = B;
+                a.out.conversions[u] = S;
+            }
             store_flat_unit(a, e, k, I, B, S, cents_to_dollars(cost_c), cents_to_dollars(rev_c));
             if (a.out.episode_profit_cents != nullptr) a.out.episode_profit_cents[u] += rev_c - cost_c;
             profit_c += rev_c - cost_c;
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) profit_c += __shfl_xor_sync(FULL, profit_c, off);
-        if (lane == 0) env_tail(a, e, cents_to_dollars(profit_c), budget, remaining);
+        if (lane == 0) {
+            env_tail(a, e, cents_to_dollars(profit_c), budget, remaining);
+            if (a.scratch.serial_hint != nullptr) a.scratch.serial_hint[e] = bound ? 1 : 0;
+        }
         if (a.out.rows != nullptr) {
             __threadfence();  // the row reads what this warp's lanes just stored
             __syncwarp();
@@ -2398,6 +2479,8 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
         __syncwarp();
     }
 }
+
+
 
 
 // ------------------------------------------------------------------------------------------
@@ -2483,6 +2566,10 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     cudaError_t err = cudaSuccess;
     adc_tape t0 = {};
     const adc_tape &tp = tape ? *tape : t0;
+    // the warp-cooperative exact walk needs its workspace; it is also the only consumer of serial_hint
+    const int64_t slab_bytes = slab_bytes_of(a.kw.K);
+    const int64_t n_slabs = a.scratch.serial_ws != nullptr ? a.scratch.serial_ws_bytes / slab_bytes : 0;
+    const bool warp_walk = tape == nullptr && !explicit_kw && a.n_lanes != 1 && a.detail.costs == nullptr && n_slabs > 0;
     if (tape == nullptr && !explicit_kw) {
         const int block = kFlatWarps * 32;
         int per_sm = 0;
@@ -2495,7 +2582,13 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         const int64_t want = ((total + kBU - 1) / kBU + kFlatWarps - 1) / kFlatWarps;
         if (want < grid) grid = want;
         if (grid < 1) grid = 1;
-        kern<<<(unsigned)grid, block, 0, s>>>(a);
+        if (warp_walk || a.scratch.serial_hint == nullptr) {
+            kern<<<(unsigned)grid, block, 0, s>>>(a);
+        } else {
+            adc_step_args b = a;
+            b.scratch.serial_hint = nullptr;
+            kern<<<(unsigned)grid, block, 0, s>>>(b);
+        }
         ++*launches;
         err = cudaGetLastError();
     } else if (tape == nullptr) {
@@ -2526,9 +2619,7 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     }
     if (err != cudaSuccess) return err;
     // exact serial walk of the queued envs (reads the count on the device; exits at once if 0)
-    const int64_t slab_bytes = slab_bytes_of(a.kw.K);
-    const int64_t n_slabs = a.scratch.serial_ws != nullptr ? a.scratch.serial_ws_bytes / slab_bytes : 0;
-    if (tape == nullptr && !explicit_kw && a.n_lanes != 1 && a.detail.costs == nullptr && n_slabs > 0) {
+    if (warp_walk) {
         // one warp per queued env, each with its own slab of the workspace
         auto kern = adc_serial_warp_implicit_kernel;
         int64_t grid = grid_for(kern, kSerWarps * 32, (int64_t)a.E * 32);
@@ -2547,8 +2638,7 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     if (err != cudaSuccess) return err;
     // compact rows: the free-running implicit kernels pack them as they finalise each env; every
     // other kernel family gets one packing pass over the finished step
-    const bool rows_in_kernel = tape == nullptr && !explicit_kw && a.n_lanes != 1 && a.detail.costs == nullptr && n_slabs > 0;
-    if (a.out.rows != nullptr && !rows_in_kernel) return launch_pack_rows(a, a.out.rows, s, launches);
+    if (a.out.rows != nullptr && !warp_walk) return launch_pack_rows(a, a.out.rows, s, launches);
     return cudaSuccess;
 }
 

@@ -91,6 +91,7 @@ class VectorBiddingSimulation:
         episode_profit: bool = False,
         flat_obs: bool = False,
         serial_ws_bytes: int = 1 << 30,
+        serial_hint: bool = True,
         **kwargs,
     ) -> None:
         assert render_mode is None or render_mode in self.metadata["render_modes"], (
@@ -124,8 +125,11 @@ class VectorBiddingSimulation:
         # [E, 5K+2] flat observation rows in the reference's FlatArrayWrapper layout, written by the
         # kernels (adc_step_out.flat_obs); `flat_observation()` hands the tensor out, no gather pass
         self.want_flat_obs = bool(flat_obs)
-        # cap of the exact serial walk's workspace (one 640 B x K slab per resident warp)
+        # cap of the exact serial walk's workspace (one slab of ~370 B x K per resident warp)
         self.serial_ws_cap = int(serial_ws_bytes)
+        # envs whose budget bound in their previous step skip the budget-free kernel (adc_scratch.
+        # serial_hint): same results, a budget-bound env is evaluated once instead of twice
+        self.use_serial_hint = bool(serial_hint)
         self.env_base = int(env_base)
         self.n_lanes = int(n_lanes)
         self._auto_lanes = n_lanes == 0
@@ -195,6 +199,7 @@ class VectorBiddingSimulation:
         slab = max(int(self._lib.adc_serial_slab_bytes(K)), 1)
         n_slabs = max(1, min(E, 148 * 28, self.serial_ws_cap // slab))
         self._scratch["serial_ws"] = torch.empty(n_slabs * slab, dtype=torch.uint8, device=dev)
+        self._scratch["serial_hint"] = z(E, dtype=torch.uint8)
         self._detail = None
         if self.detail_cap > 0:
             c = self.detail_cap
@@ -484,6 +489,7 @@ class VectorBiddingSimulation:
         sc.unit_cost_f64 = _ptr(s.get("unit_cost_f64"))
         sc.work_counter = s["work_counter"].data_ptr() if self.dynamic_work else None
         sc.serial_ws, sc.serial_ws_bytes = s["serial_ws"].data_ptr(), s["serial_ws"].numel()
+        sc.serial_hint = s["serial_hint"].data_ptr() if self.use_serial_hint else None
         out.episode_profit_cents = _ptr(o.get("episode_profit_cents"))
         out.episode_reward = _ptr(o.get("episode_reward"))
         out.episode_count = _ptr(o.get("episode_count"))
@@ -606,7 +612,7 @@ class VectorBiddingSimulation:
             o.rows = None
             o.flat_obs = off(bo.flat_obs, e0 * (5 * K + 2) * fb)
             sc, bs = a.scratch, base.scratch
-            for n, sz in (("serial_list", 4), ("env_profit", 8), ("env_cost", 8), ("env_done", 4)):
+            for n, sz in (("serial_list", 4), ("env_profit", 8), ("env_cost", 8), ("env_done", 4), ("serial_hint", 1)):
                 setattr(sc, n, off(getattr(bs, n), e0 * sz))
             sc.unit_cost_f64 = off(bs.unit_cost_f64, e0 * K * 8)
             sc.serial_count = counters[i, 0].data_ptr()

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define ADC_ABI_VERSION 4
+#define ADC_ABI_VERSION 5
 #define ADC_SUBSTEPS 24 /* adcraft/bidding_simulation.py:213 */
 
 typedef enum adc_status {
@@ -156,12 +156,18 @@ typedef struct adc_scratch {
     int32_t *acc_clicks;
     int32_t *acc_conversions;
     /* Optional DEVICE workspace of the warp-cooperative exact serial walk (free-running implicit
-     * keywords): every resident warp expands one queued env's day into a slab of K x 344 bytes
-     * (adc_serial_slab_bytes(K)); 8-byte aligned.  The launcher runs as many warps as slabs fit
-     * (about 3500 resident warps at most); NULL / too small for one slab: the walk falls back to one
+     * keywords): every resident warp expands one queued env's day into a slab of about 370 bytes
+     * per keyword (exactly adc_serial_slab_bytes(K)); 16-byte aligned.  The launcher runs as many warps
+     * as slabs fit (about 4100 resident warps at most); NULL / too small for one slab: the walk falls back to one
      * thread per env (correct, much slower). */
     void *serial_ws;
     int64_t serial_ws_bytes;
+    /* Optional [E] bytes, zeroed once by the caller and then left to the library (free-running implicit
+     * keywords with serial_ws): the exact walk marks the envs whose budget really bound; in the next step
+     * the budget-free kernel does not evaluate them at all and queues them for the walk right away.  Both
+     * kernels compute the same function, so results do not depend on the marks -- only on how often a
+     * budget-bound env is evaluated twice. */
+    uint8_t *serial_hint;
 } adc_scratch;
 
 /* Optional per-click detail (the ragged lists of BiddingOutcomes, bidding_simulation.py:10-38, that

@@ -101,6 +101,36 @@ def test_budget_binding_serial_path_large_keyword_sets(orc, K, E, vol):
     assert float(obs["cost"].sum()) > 0
 
 
+@pytest.mark.parametrize("alias", [False, True])
+def test_serial_hint_changes_nothing(orc, alias):
+    """adc_scratch.serial_hint: envs whose budget bound skip the budget-free kernel in their next step.
+    Same results with and without it, budgets that start / stop binding between steps included, and the
+    marks are exactly the envs whose budget could not cover the day."""
+    rng = np.random.default_rng(23)
+    K, E = 40, 96
+    table = make_implicit_table(rng, K, 100)
+    a = _env(table, E, seed=77, budget=1000.0, budget_alias=alias, obs_dtype=torch.float64)
+    b = _env(table, E, seed=77, budget=1000.0, budget_alias=alias, obs_dtype=torch.float64, serial_hint=False)
+    ob = _oracle_batch(orc, table, E, seed=77, budget=1000.0, alias=alias)
+    marked = 0
+    for s in range(6):
+        bids = np.round(rng.uniform(0.2, 1.5, (E, K)), 2)
+        budgets = rng.choice([2.0, 30.0, 300.0, 1e6], size=E)
+        act = {"keyword_bids": torch.from_numpy(bids).cuda(), "budget": torch.from_numpy(budgets).cuda()}
+        oa, ob_ = a.step(act), b.step(act)
+        for k in oa[0]:
+            assert torch.equal(oa[0][k], ob_[0][k]), (s, k)
+        assert torch.equal(oa[1], ob_[1]) and torch.equal(oa[2], ob_[2])
+        ob.budget[:] = budgets
+        _compare(oa[0], oa[1], oa[2], oa[3], ob.step(bids, n_threads=4), a, RTOL64)
+        hint = a._scratch["serial_hint"].cpu().numpy()
+        assert not hint[budgets >= 1e6].any()     # a budget that covers everything leaves no mark
+        assert hint[budgets <= 2.0].all()         # a $2 budget cannot cover a day of 40 keywords
+        marked += int(hint.sum())
+        assert not b._scratch["serial_hint"].any()
+    assert marked > 0
+
+
 def test_force_serial_equals_fast_path(orc):
     rng = np.random.default_rng(11)
     K, E = 30, 40
@@ -214,14 +244,19 @@ def test_bids_beyond_fast_kernel_caps_take_the_exact_route(orc):
     _compare(obs, reward, term, trunc, ref, env, RTOL64)
 
 
+@pytest.mark.parametrize("vol", [900, 420, 200])
 @pytest.mark.parametrize("alias", [False, True])
-def test_serial_warp_kernel_buffer_overflow_and_zero_budget(orc, alias):
-    """Sub-steps with more clicked slots than the warp-serial kernel buffers per lane (16) take the
-    direct re-walk; budgets of 0 stop after the first lane of the day (bsim:230-233)."""
+def test_serial_warp_kernel_buffer_overflow_and_zero_budget(orc, alias, vol):
+    """What the warp-serial kernel's slab cannot describe takes the direct re-walk: days of more than
+    512 auctions (vol 900), units with more than 256 clicked slots or chunks of 32 keywords with more
+    than 2048 (vol 420: whole units direct, mixed with slab units), sub-steps with more than 32
+    clicked slots; budgets of 0 stop after the first lane of the day (bsim:230-233)."""
     rng = np.random.default_rng(41)
     K, E = 37, 24
-    table = make_implicit_table(rng, K, 900)
+    table = make_implicit_table(rng, K, vol)
     table.ctr[:] = rng.uniform(0.7, 1.0, K)
+    if vol == 200:
+        table.ctr[::2] = rng.uniform(0.05, 0.3, (K + 1) // 2)
     env = _env(table, E, seed=12, budget=1000.0, budget_alias=alias, obs_dtype=torch.float64)
     ob = _oracle_batch(orc, table, E, seed=12, budget=1000.0, alias=alias)
     budgets = rng.choice([0.0, 5.0, 60.0, 400.0, 2500.0], size=E)
