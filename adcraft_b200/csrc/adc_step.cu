@@ -176,6 +176,14 @@ __device__ __forceinline__ void pack_row_tail(const adc_step_args &a, int e)
 // ~35-instruction routine; for |c| < 2^31 one Newton step on c * 0.01 with the exact FMA residual gives
 // the identical double (checked exhaustively against c / 100.0 for every c in [0, 2^31) on the host,
 // and the operations are sign-symmetric), in three FMA-pipe instructions.
+__device__ __forceinline__ double cents32_to_dollars(int c)  // the same for 32-bit cents (one I2F)
+{
+    const double x = (double)c;
+    const double q0 = __dmul_rn(x, 0.01);
+    const double r = __fma_rn(-q0, 100.0, x);
+    return __fma_rn(r, 0.01, q0);
+}
+
 __device__ __forceinline__ double cents_to_dollars(long long c)
 {
     const double x = (double)c;
@@ -1990,15 +1998,16 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
 //       masked sum over the pool, then one revenue per conversion by conversion rank -- and stores
 //       the day's outputs once.
 // Nothing is re-drawn per sub-step and no keyword count is special.  Lanes the slab cannot
-// describe (volume > 512, more than 64 clicked slots in the day or kSerCap in one sub-step) are
+// describe (volume > 512, more than 61 impressions or clicked slots in one sub-step, a chunk of 32
+// keywords with more than 4096 clicked slots) are
 // walked again by lane_walk with the budget (serial_direct_lane) and committed on the spot.
 // ------------------------------------------------------------------------------------------
 constexpr int kSerWarps = 4;
-constexpr int kSerCap = 32;        // clicked slots per lane and sub-step in shared memory; more -> direct re-walk
 constexpr int kSlabGroups = 16;    // 32-auction groups per unit and day the slab describes (volume <= 512)
-constexpr int kPoolPerUnit = 64;   // a chunk of 32 keywords shares a pool of 32 x 64 clicked slots
+constexpr int kPoolPerUnit = 128;  // a chunk of 32 keywords shares a pool of 32 x 128 clicked slots
 constexpr int kChunkPool = 32 * kPoolPerUnit;
-constexpr int kUnitSlots = 256;    // clicked slots of one unit's day the slab describes; more -> direct
+constexpr int kUnitSlots = 512;    // clicked slots of one unit's day the slab describes (every day of <= 512 auctions)
+constexpr int kSerRegs = 6;       // clicked slots of a lane and sub-step the walk holds in registers
 constexpr int kSerMinBlocks = 7;   // 28 warps per SM: a 4096-env queue is resident in one wave
 
 // lane header: bits 0..5 clicked slots (after the walk: accepted ones), 6..11 impressions, 12..31 first slot
@@ -2006,16 +2015,13 @@ constexpr int kSerMinBlocks = 7;   // 28 warps per SM: a 4096-env queue is resid
 // conversions.
 constexpr uint32_t kHdrDirect = 63u, kHdrDirectDone = 62u, kHdrMaxCount = 61u;
 
-struct __align__(8) SlabUnit {      // 8 B per keyword
-    float rev_mean, rev_sd;
-};
-
-// slab of one warp: uint32 hdr[24][Kp] (Kp = K rounded up to 32) | uint32 pool[Kp / 32][kChunkPool] | SlabUnit[K]
+// slab of one warp: uint32 hdr[24][Kp] (Kp = K rounded up to 32) | uint32 pool[Kp / 32][kChunkPool] |
+// uint4 acc[Kp]: the keywords' running sums of the walk (impressions | bit 31: mixed commit, clicks,
+// conversions, cents)
 __host__ __device__ inline int64_t slab_kp(int K) { return ((int64_t)K + 31) & ~(int64_t)31; }
 __host__ __device__ inline int64_t slab_bytes_of(int K)
 {
-    const int64_t raw = (int64_t)ADC_SUBSTEPS * slab_kp(K) * 4 + slab_kp(K) * kPoolPerUnit * 4 + (int64_t)K * (int64_t)sizeof(SlabUnit);
-    return (raw + 15) & ~(int64_t)15;
+    return (int64_t)ADC_SUBSTEPS * slab_kp(K) * 4 + slab_kp(K) * kPoolPerUnit * 4 + slab_kp(K) * 16;
 }
 
 // A (sub-step, keyword) lane the slab cannot describe: walked again with the budget by lane_walk.  Out
@@ -2102,10 +2108,8 @@ __device__ __noinline__ CommitOut commit_mixed_unit(const PhiloxSrc &src, const 
 __global__ void __launch_bounds__(kSerWarps * 32, kSerMinBlocks)
 adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_slabs)
 {
-    // per warp 4 KB: phase 0 keeps the chunk's 24 x 32 headers and 8 x 32 conversion-by-rank words here,
-    // phase 1 the clicked slots of the current round
-    __shared__ uint32_t s_slot[kSerWarps][kSerCap][32];
-    static_assert(kSerCap * 32 >= ADC_SUBSTEPS * 32 + (kUnitSlots / 32) * 32, "phase-0 staging fits the slot buffer");
+    // phase 0 stages a chunk's 24 x 32 headers and 8 x 32 conversion-by-rank words here
+    __shared__ uint32_t s_stage[kSerWarps][(ADC_SUBSTEPS + kUnitSlots / 32) * 32];
     __shared__ FlatCost s_cost[kSerWarps][32];
     __shared__ __align__(16) double s_lsum[kSerWarps][32];
     __shared__ int s_start[kSerWarps][32];
@@ -2118,7 +2122,6 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
     const int64_t Kp = slab_kp(K);
     const SerCounts acc = ser_counts(a);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    auto slot_cost = [&](int i, int l) { return (int)(s_slot[warp][i][l] & 0x7FFFFFFFu); };
     const int gwarp = blockIdx.x * kSerWarps + warp;
     const int n_warps = min(gridDim.x * kSerWarps, n_slabs);
     const int count = a.scratch.serial_count[a.parity & 1u];
@@ -2129,20 +2132,21 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
     unsigned char *const slab_raw = reinterpret_cast<unsigned char *>(a.scratch.serial_ws) + (size_t)gwarp * (size_t)slab_bytes_of(K);
     uint32_t *const hdr = reinterpret_cast<uint32_t *>(slab_raw);
     uint32_t *const pool = hdr + (size_t)ADC_SUBSTEPS * Kp;  // chunk c0 / 32 owns pool[c0 * kPoolPerUnit ..)
-    SlabUnit *const slab = reinterpret_cast<SlabUnit *>(pool + (size_t)Kp * kPoolPerUnit);
-    const int n_chunks = (K + 31) >> 5;
-    uint32_t *const s_hdr = &s_slot[warp][0][0];          // [24][32]
+    uint4 *const acc4 = reinterpret_cast<uint4 *>(pool + (size_t)Kp * kPoolPerUnit);
+    const uint32_t Kp32 = (uint32_t)Kp;
+    uint32_t *const s_hdr = &s_stage[warp][0];            // [24][32]
     uint32_t *const s_cv = s_hdr + ADC_SUBSTEPS * 32;     // [kUnitSlots / 32][32]: bit r of a lane's words: its r-th click converts
 
     for (int idx = gwarp; idx < count; idx += n_warps) {
         const int e = a.scratch.serial_list[idx];
         PhiloxSrc src{k0, k1, a.step, philox_env(a, e)};
         // ---- phase 0: expand the day into the slab, 32 keywords at a time
+        bool env_direct = false;  // some lane of the env is walked by lane_walk: the headers must track the walk
         for (int c0 = 0; c0 < K; c0 += 32) {
             // (a) lane <-> keyword: thresholds, volume, outcome masks -> lane headers, conversion-by-rank bits
             const int k = c0 + lane;
             const bool act = k < K;
-            bool whole_direct = false;
+            bool whole_direct = false, lane_direct = false;
             int V = 0;
             Unit2 u2;
             u2.t1 = u2.t2 = u2.t3 = u2.full = u2.h1 = u2.a1 = u2.a2 = 0u; u2.L = 0.f; u2.b = 0.f; u2.W = 1;
@@ -2166,9 +2170,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 V = whole_direct || !beats_rivals ? 0 : (int)Vl;
                 u2 = p.u2;
                 floor_c = max(p.floor_cents, 0);
-                SlabUnit su;
-                su.rev_mean = p.rev_mean; su.rev_sd = p.rev_sd;
-                slab[k] = su;
+                acc4[k] = make_uint4(0, 0, 0, 0);
             }
             int baseI = 0, baseC = 0;
             {
@@ -2198,7 +2200,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                         const int cumI = baseI + __popc(m.win & lm), cumC = baseC + __popc(m.click & lm);
                         const int ci = cumI - lastI, cc = cumC - lastC;
                         uint32_t h = (uint32_t)cc | ((uint32_t)ci << 6) | ((uint32_t)min(lastC, kUnitSlots) << 12);
-                        if (cc > kSerCap || ci > (int)kHdrMaxCount) h = kHdrDirect;  // beyond a header's counts
+                        if (cc > (int)kHdrMaxCount || ci > (int)kHdrMaxCount) { h = kHdrDirect; lane_direct = true; }  // beyond a header's counts
                         s_hdr[t * 32 + lane] = h;
                         lastI = cumI; lastC = cumC;
                         ++t;
@@ -2216,6 +2218,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 const int b4 = (B + 3) & ~3;
                 const int off = warp_incl_scan(b4, lane) - b4;
                 if (off + b4 > kChunkPool) { whole_direct = true; B = 0; }
+                env_direct = env_direct || __any_sync(FULL, whole_direct || lane_direct);
                 s_poff[warp][lane] = off;
                 // the lanes' headers, sub-step-major: one coalesced store per sub-step
                 if (act) {
@@ -2223,7 +2226,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
 #pragma unroll 4
                     for (int t = 0; t < ADC_SUBSTEPS; ++t) {
                         const uint32_t h = s_hdr[t * 32 + lane];
-                        hdr[(int64_t)t * Kp + k] = whole_direct ? kHdrDirect : ((h & 63u) == kHdrDirect ? h : h + add);
+                        hdr[(uint32_t)t * Kp32 + (uint32_t)k] = whole_direct ? kHdrDirect : ((h & 63u) == kHdrDirect ? h : h + add);
                     }
                 }
                 const PhiloxPre pc = philox_pre(a.step, stream_word(ST_COST, 0u, (uint32_t)k), src.env, k0, k1);
@@ -2259,33 +2262,76 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
         }
         __threadfence_block();
         __syncwarp();
-        // ---- phase 1: the walk; the next round's headers are loaded while this round is scanned
+        // ---- phase 1: the walk.  A lane's clicked slots of the round come into registers with one batch
+        // of independent loads (kSerRegs of them; the rare longer lane reads on), the next round's headers are
+        // already on their way; what a lane accepted goes straight into its keyword's accumulators in the slab.
         const double budget = step_budget(a, e);
         double remaining = budget;  // warp-uniform (bsim:214)
         bool stop = false;
         bool bound = false;  // some round could not be proven fully affordable: next step comes here directly
         int t_stop = ADC_SUBSTEPS, k_stop = K;  // the lane after which nothing ran (bsim:230-233)
         uint32_t h_next = lane < K ? hdr[lane] : 0u;
-        for (int round = 0; round < ADC_SUBSTEPS * n_chunks && !stop; ++round) {
-            const int t = round / n_chunks, c0 = (round - t * n_chunks) << 5;
+        int t = 0, c0 = 0;
+        while (t < ADC_SUBSTEPS && !stop) {
             const int k = c0 + lane;
             const bool act = k < K;
-            const int64_t u = (int64_t)e * K + (act ? k : 0);
+            const uint32_t hoff = (uint32_t)t * Kp32 + (uint32_t)k;
             const uint32_t h = h_next;
-            {
-                const int rn = round + 1, tn = rn / n_chunks, kn = ((rn - tn * n_chunks) << 5) + lane;
-                h_next = (tn < ADC_SUBSTEPS && kn < K) ? hdr[(int64_t)tn * Kp + kn] : 0u;
-            }
+            const int t_cur = t, c_cur = c0;
+            c0 += 32;
+            if (c0 >= K) { c0 = 0; ++t; }
+            h_next = (t < ADC_SUBSTEPS && c0 + lane < K) ? hdr[(uint32_t)t * Kp32 + (uint32_t)(c0 + lane)] : 0u;
             // a chunk without an impression or a clicked slot in this sub-step leaves everything alone
             // (a sparse keyword, V < 24, has its whole day in sub-step 0); `remaining <= 0` on entry still
             // gets its one look
             if (remaining > 0 && __all_sync(FULL, (h & 0xFFFu) == 0u)) continue;
             int nclk = (int)(h & 63u);
             const bool direct = nclk == (int)kHdrDirect;
-            if (direct) nclk = kSerCap + 1;  // takes the re-walk turn below
-            else
-                for (int i = 0; i < nclk; ++i) s_slot[warp][i][lane] = pool[(size_t)c0 * kPoolPerUnit + (h >> 12) + i];
-            __syncwarp();
+            const uint32_t my_off = (uint32_t)c_cur * kPoolPerUnit + (h >> 12);
+            const uint32_t *const sp = pool + my_off;
+            uint32_t w[kSerRegs];
+#pragma unroll
+            for (int i = 0; i < kSerRegs; ++i) w[i] = (!direct && i < nclk) ? sp[i] : 0u;
+            uint4 a4 = make_uint4(0, 0, 0, 0);
+            if (act) a4 = acc4[k];
+            // nothing affordable -- every lane's first click costs more than `remaining`, so each lane breaks
+            // at once (bsim:99-104) and `remaining` does not move: the usual state of the sub-steps after the
+            // budget ran dry.  Only the impressions count.
+            if (remaining > 0) {
+                const bool lane_has = act && nclk > 0;
+                const bool none = !lane_has || (!direct && !(remaining >= cents32_to_dollars((int)(w[0] & 0x7FFFFFFFu))));
+                if (__all_sync(FULL, none)) {
+                    bound = bound || __any_sync(FULL, lane_has);
+                    if (act) {
+                        if (env_direct && nclk > 0) hdr[hoff] = h & ~63u;
+                        a4.x += (h >> 6) & 63u;
+                        acc4[k] = a4;
+                    }
+                    continue;
+                }
+            }
+            // the lane's own sequential f64 sum (rust sum_list), exact cents and conversions of all its slots
+            unsigned cents = 0, convs = 0;
+            double lane_sum = 0.0;
+#pragma unroll
+            for (int i = 0; i < kSerRegs; ++i) {
+                if (!direct && i < nclk) {
+                    const unsigned c = w[i] & 0x7FFFFFFFu;
+                    lane_sum = __dadd_rn(lane_sum, cents32_to_dollars((int)c));
+                    cents += c;
+                    convs += w[i] >> 31;
+                }
+            }
+            if (!direct && nclk > kSerRegs) {
+                for (int i = kSerRegs; i < nclk; ++i) {
+                    const uint32_t ww = sp[i];
+                    const unsigned c = ww & 0x7FFFFFFFu;
+                    lane_sum = __dadd_rn(lane_sum, cents32_to_dollars((int)c));
+                    cents += c;
+                    convs += ww >> 31;
+                }
+            }
+            if (direct) nclk = (int)kHdrDirect;  // takes the re-walk turn below
             // ---- one uniform scan over the lanes that have clicks: the reference's budget walk
             int B = direct ? 0 : nclk;
             unsigned todo = __ballot_sync(FULL, act && nclk > 0);
@@ -2295,32 +2341,16 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
             DirectOut dout;
             dout.I = dout.B = dout.S = 0; dout.cost_c = dout.rev_c = 0; dout.next = 0.0;
             bool direct_done = false;
-            // Two shortcuts that leave the reference's f64 sequence intact:
-            // (a) nothing affordable -- every lane's first click costs more than `remaining`, so each
-            //     lane breaks at once (bsim:99-104) and `remaining` does not move: the usual state of
-            //     the sub-steps after the budget ran dry;
-            // (b) everything affordable -- `remaining` exceeds this round's total spend (exact cents,
-            //     doubled under the alias rule) by more than a cent, so no `budget >= cost` test can
-            //     fail; without the alias rule the walk is then per lane `remaining -= lane_sum` with
-            //     lane_sum the lane's own sequential f64 sum (bsim:225 + rust sum_list), which the
-            //     lanes form in parallel (a lane without clicks subtracts an exact 0.0).
+            // Everything affordable -- `remaining` exceeds this round's total spend (exact cents, doubled
+            // under the alias rule) by more than a cent, so no `budget >= cost` test can fail; without the
+            // alias rule the walk is then per lane `remaining -= lane_sum` with lane_sum the lane's own
+            // sequential f64 sum (bsim:225 + rust sum_list), which the lanes form in parallel (a lane
+            // without clicks subtracts an exact 0.0).
             bool all_accepted = false;
             if (remaining > 0) {
-                const bool lane_has = act && nclk > 0;
-                const bool none = !lane_has || (!direct && !(remaining >= cents_to_dollars(slot_cost(0, lane))));
-                if (__all_sync(FULL, none)) {
-                    todo = 0;
-                    B = 0;
-                } else if (!__any_sync(FULL, nclk > kSerCap)) {
-                    unsigned cents = 0;
-                    double lane_sum = 0.0;
-                    for (int i = 0; i < nclk; ++i) {
-                        const int c = slot_cost(i, lane);
-                        lane_sum = __dadd_rn(lane_sum, cents_to_dollars(c));
-                        cents += (unsigned)c;
-                    }
-                    const unsigned total = __reduce_add_sync(FULL, cents);  // <= 32 lanes x kSerCap x 65535 < 2^32 (bids capped above)
-                    const double spend = __ddiv_rn((double)total, 100.0);
+                if (!__any_sync(FULL, direct)) {
+                    const unsigned total = __reduce_add_sync(FULL, cents);  // <= 32 lanes x 61 x 65535 < 2^32 (bids capped above)
+                    const double spend = cents_to_dollars((long long)total);
                     if (remaining > (a.budget_alias ? spend + spend : spend) + 0.01) {
                         all_accepted = true;
                         if (!a.budget_alias) {
@@ -2333,40 +2363,59 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                             }
                             todo = 0;
                         }
-                        while (todo) {  // the lane's own walk already drew on the shared budget (bsim:102)
-                            const int l = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            double b = remaining;
-                            const int n_l = __shfl_sync(FULL, nclk, l);
-                            for (int i = 0; i < n_l; ++i) b = __dsub_rn(b, cents_to_dollars(slot_cost(i, l)));
-                            remaining = __dsub_rn(b, __shfl_sync(FULL, lane_sum, l));
-                        }
                     }
                 }
             }
             bound = bound || (any_click && !all_accepted);
-            if (!all_accepted && todo) B = 0;  // the scan below decides lane by lane; lanes it never reaches accept nothing
+            // From here every lane follows lane l's walk: its slots are read again from the pool, all lanes
+            // the same word (the owner's loads above left the lines in L1).
+            if (todo) {
+                if (all_accepted) {  // alias rule: the lane's own walk already drew on the shared budget (bsim:102)
+                    while (todo) {
+                        const int l = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        double b = remaining;
+                        const int n_l = __shfl_sync(FULL, nclk, l);
+                        const uint32_t *const sl = pool + __shfl_sync(FULL, my_off, l);
+                        for (int i = 0; i < n_l; ++i) b = __dsub_rn(b, cents32_to_dollars((int)(sl[i] & 0x7FFFFFFFu)));
+                        remaining = __dsub_rn(b, __shfl_sync(FULL, lane_sum, l));
+                    }
+                } else {
+                    B = 0;  // the scan decides lane by lane; lanes it never reaches accept nothing
+                    // A lane whose first click costs more than `remaining` does now cannot afford it later in
+                    // the round either (`remaining` only falls): it breaks at once, subtracts an exact 0.0 and
+                    // leaves `remaining` as it is -- out of the scan.  After the budget ran dry this leaves the
+                    // few lanes with a cheap first click.
+                    if (remaining > 0) {
+                        const bool cannot = !direct && nclk > 0 && !(remaining >= cents32_to_dollars((int)(w[0] & 0x7FFFFFFFu)));
+                        todo &= ~__ballot_sync(FULL, cannot);
+                    }
+                }
+            }
             while (todo) {
                 const int l = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int n_l = __shfl_sync(FULL, nclk, l);
+                const uint32_t *const sl = pool + __shfl_sync(FULL, my_off, l);
                 double next;
-                if (n_l <= kSerCap) {  // every lane runs lane l's walk on the buffered f64 costs
-                    double b = remaining, lane_sum = 0.0;
+                if (n_l != (int)kHdrDirect) {  // every lane runs lane l's walk on its f64 costs
+                    double b = remaining, lsum = 0.0;
                     int nacc = 0;
                     for (int i = 0; i < n_l; ++i) {
-                        const double cost = cents_to_dollars(slot_cost(i, l));
+                        const double cost = cents32_to_dollars((int)(sl[i] & 0x7FFFFFFFu));
                         if (!(b >= cost)) break;  // bsim:99-104
                         ++nacc;
-                        lane_sum = __dadd_rn(lane_sum, cost);
+                        lsum = __dadd_rn(lsum, cost);
                         b = __dsub_rn(b, cost);
                     }
                     if (lane == l) B = nacc;
-                    next = __dsub_rn(a.budget_alias ? b : remaining, lane_sum);  // bsim:102 alias, :225
+                    next = __dsub_rn(a.budget_alias ? b : remaining, lsum);  // bsim:102 alias, :225
                 } else {  // beyond the slab or the buffer: lane l walks its sub-step again, with the budget
                     next = remaining;
                     if (lane == l) {
-                        dout = serial_direct_lane(a, src, e, k, t, conversions_before(hdr, pool + (size_t)c0 * kPoolPerUnit, Kp, k, t), remaining);
+                        dout = serial_direct_lane(a, src, e, k, t_cur,
+                                                  conversions_before(hdr, pool + (uint32_t)c_cur * kPoolPerUnit, Kp, k, t_cur),
+                                                  remaining);
                         direct_done = true;
                         next = dout.next;
                     }
@@ -2376,66 +2425,69 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 if (remaining <= 0) {  // bsim:230-233
                     stop = true;
                     cutoff = l;
-                    t_stop = t;
-                    k_stop = c0 + l;
+                    t_stop = t_cur;
+                    k_stop = c_cur + l;
                     break;
                 }
             }
-            // the lanes that ran write back what the commit cannot infer: an accepted count below the
-            // slot count, a direct lane's totals
+            // the lanes that ran: their keyword's running sums; the header keeps an accepted count below the
+            // slot count (the mixed commit and conversions_before read it), a direct lane's totals go to the outputs
             if (act && lane <= cutoff) {
-                if (direct_done) {
-                    acc.I[u] += dout.I;
-                    acc.B[u] += dout.B;
-                    acc.S[u] += dout.S;
-                    a.out.cost_cents[u] += dout.cost_c;
-                    a.out.revenue_cents[u] += dout.rev_c;
-                    hdr[(int64_t)t * Kp + k] = kHdrDirectDone | ((uint32_t)dout.S << 12);
-                } else if (direct) {
-                    hdr[(int64_t)t * Kp + k] = kHdrDirectDone;  // never reached: nothing of it counts
-                } else if (B != nclk) {
-                    hdr[(int64_t)t * Kp + k] = (h & ~63u) | (uint32_t)B;
+                if (direct) {
+                    const int64_t u = (int64_t)e * K + k;
+                    if (direct_done) {
+                        acc.I[u] += dout.I;
+                        acc.B[u] += dout.B;
+                        acc.S[u] += dout.S;
+                        a.out.cost_cents[u] += dout.cost_c;
+                        a.out.revenue_cents[u] += dout.rev_c;
+                    }
+                    hdr[hoff] = kHdrDirectDone | ((uint32_t)dout.S << 12);  // (never reached: nothing of it counts)
+                    a4.x |= 0x80000000u;  // the keyword takes the mixed commit
+                } else {
+                    if (B != nclk) {
+                        if (env_direct) hdr[hoff] = (h & ~63u) | (uint32_t)B;
+                        cents = 0; convs = 0;
+                        for (int i = 0; i < B; ++i) {
+                            const uint32_t ww = sp[i];
+                            cents += ww & 0x7FFFFFFFu;
+                            convs += ww >> 31;
+                        }
+                    }
+                    a4.x += (h >> 6) & 63u;
+                    a4.y += (uint32_t)B;
+                    a4.z += convs;
+                    a4.w += cents;
                 }
+                acc4[k] = a4;
             }
             __syncwarp();
         }
         __threadfence_block();
         __syncwarp();
-        // ---- phase 2: commit, lane <-> keyword: the lanes that ran, in sub-step order
+        // ---- phase 2: commit, lane <-> keyword: one revenue per conversion by conversion rank, the outputs
         long long profit_c = 0;
         for (int k = lane; k < K; k += 32) {
             const int64_t u = (int64_t)e * K + k;
-            const SlabUnit su = slab[k];
-            const uint32_t *const cpool = pool + (size_t)(k & ~31) * kPoolPerUnit;
-            int I = 0, B = 0, S = 0;
-            long long cost_c = 0, rev_c = 0;
-            bool mixed = false;
-            for (int t = 0; t < ADC_SUBSTEPS; ++t) {
-                if (t > t_stop || (t == t_stop && k > k_stop)) break;  // after the early break nothing ran
-                const uint32_t h = hdr[(int64_t)t * Kp + k];
-                const uint32_t f = h & 63u;
-                if (f >= kHdrDirectDone) { mixed = true; continue; }
-                I += (int)((h >> 6) & 63u);
-                B += (int)f;
-                for (uint32_t i = 0; i < f; ++i) {  // the slots that were paid for
-                    const uint32_t w = cpool[(h >> 12) + i];
-                    cost_c += (int)(w & 0x7FFFFFFFu);
-                    S += (int)(w >> 31);
-                }
-            }
-            if (!mixed) {
-                for (int r4 = 0; 4 * r4 < S; ++r4) {  // one revenue per conversion, by conversion rank
+            const int64_t pi = (int64_t)e * a.kw.env_stride + k;
+            const float rev_mean = (float)a.kw.rev_mean[pi], rev_sd = (float)a.kw.rev_std[pi];
+            const uint4 a4 = acc4[k];
+            int I = (int)(a4.x & 0x7FFFFFFFu), B = (int)a4.y, S = (int)a4.z;
+            long long cost_c = a4.w, rev_c = 0;
+            if (!(a4.x >> 31)) {
+                for (int r4 = 0; 4 * r4 < S; ++r4) {
                     const uint4 rw = src.draw(ST_REVENUE, (uint32_t)k, (uint32_t)r4);
                     const int left = S - 4 * r4;
-                    rev_c += revenue_cents(rw.x, su.rev_mean, su.rev_sd);
-                    if (left > 1) rev_c += revenue_cents(rw.y, su.rev_mean, su.rev_sd);
-                    if (left > 2) rev_c += revenue_cents(rw.z, su.rev_mean, su.rev_sd);
-                    if (left > 3) rev_c += revenue_cents(rw.w, su.rev_mean, su.rev_sd);
+                    rev_c += revenue_cents(rw.x, rev_mean, rev_sd);
+                    if (left > 1) rev_c += revenue_cents(rw.y, rev_mean, rev_sd);
+                    if (left > 2) rev_c += revenue_cents(rw.z, rev_mean, rev_sd);
+                    if (left > 3) rev_c += revenue_cents(rw.w, rev_mean, rev_sd);
                 }
             } else {
                 // a keyword with lanes walked by lane_walk: their conversions shift the revenue ranks of the
                 // slab lanes (S of the mixed commit counts them too: they are in acc.S already)
-                const CommitOut o = commit_mixed_unit(src, hdr, cpool, Kp, k, t_stop, k_stop, su.rev_mean, su.rev_sd);
+                const CommitOut o = commit_mixed_unit(src, hdr, pool + (uint32_t)(k & ~31) * kPoolPerUnit, Kp, k, t_stop, k_stop,
+                                                      rev_mean, rev_sd);
                 I = o.I + acc.I[u];
                 B = o.B + acc.B[u];
                 S = o.S;

@@ -90,7 +90,7 @@ class VectorBiddingSimulation:
         f32_ties: bool = False,
         episode_profit: bool = False,
         flat_obs: bool = False,
-        serial_ws_bytes: int = 1 << 30,
+        serial_ws_bytes: int = 4 << 30,
         serial_hint: bool = True,
         **kwargs,
     ) -> None:

@@ -248,9 +248,9 @@ def test_bids_beyond_fast_kernel_caps_take_the_exact_route(orc):
 @pytest.mark.parametrize("alias", [False, True])
 def test_serial_warp_kernel_buffer_overflow_and_zero_budget(orc, alias, vol):
     """What the warp-serial kernel's slab cannot describe takes the direct re-walk: days of more than
-    512 auctions (vol 900), units with more than 256 clicked slots or chunks of 32 keywords with more
-    than 2048 (vol 420: whole units direct, mixed with slab units), sub-steps with more than 32
-    clicked slots; budgets of 0 stop after the first lane of the day (bsim:230-233)."""
+    512 auctions (vol 900), sub-steps with more than 61 impressions, chunks of 32 keywords with more
+    than 4096 clicked slots in the day (vol 420: whole units direct, mixed with slab units); budgets of
+    0 stop after the first lane of the day (bsim:230-233)."""
     rng = np.random.default_rng(41)
     K, E = 37, 24
     table = make_implicit_table(rng, K, vol)
