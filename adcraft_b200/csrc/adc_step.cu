@@ -2016,12 +2016,13 @@ constexpr int kSerMinBlocks = 7;   // 28 warps per SM: a 4096-env queue is resid
 constexpr uint32_t kHdrDirect = 63u, kHdrDirectDone = 62u, kHdrMaxCount = 61u;
 
 // slab of one warp: uint32 hdr[24][Kp] (Kp = K rounded up to 32) | uint32 pool[Kp / 32][kChunkPool] |
-// uint4 acc[Kp]: the keywords' running sums of the walk (impressions | bit 31: mixed commit, clicks,
-// conversions, cents)
+// uint4 acc[Kp]: per keyword the day's impressions | bit 31: mixed commit, and the running sums of the walk
+// (clicks, conversions, cents) | uint32 rmin[24 x Kp / 32]: the round index of the walk
 __host__ __device__ inline int64_t slab_kp(int K) { return ((int64_t)K + 31) & ~(int64_t)31; }
 __host__ __device__ inline int64_t slab_bytes_of(int K)
 {
-    return (int64_t)ADC_SUBSTEPS * slab_kp(K) * 4 + slab_kp(K) * kPoolPerUnit * 4 + slab_kp(K) * 16;
+    return (int64_t)ADC_SUBSTEPS * slab_kp(K) * 4 + slab_kp(K) * kPoolPerUnit * 4 + slab_kp(K) * 16 +
+           ((ADC_SUBSTEPS * (slab_kp(K) / 32) * 4 + 15) & ~(int64_t)15);
 }
 
 // A (sub-step, keyword) lane the slab cannot describe: walked again with the budget by lane_walk.  Out
@@ -2133,7 +2134,9 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
     uint32_t *const hdr = reinterpret_cast<uint32_t *>(slab_raw);
     uint32_t *const pool = hdr + (size_t)ADC_SUBSTEPS * Kp;  // chunk c0 / 32 owns pool[c0 * kPoolPerUnit ..)
     uint4 *const acc4 = reinterpret_cast<uint4 *>(pool + (size_t)Kp * kPoolPerUnit);
+    uint32_t *const rmin = reinterpret_cast<uint32_t *>(acc4 + Kp);  // [24 x Kp / 32] cheapest first click of a round
     const uint32_t Kp32 = (uint32_t)Kp;
+    const int n_chunks = (int)(Kp32 >> 5), n_rounds = ADC_SUBSTEPS * n_chunks;
     uint32_t *const s_hdr = &s_stage[warp][0];            // [24][32]
     uint32_t *const s_cv = s_hdr + ADC_SUBSTEPS * 32;     // [kUnitSlots / 32][32]: bit r of a lane's words: its r-th click converts
 
@@ -2170,7 +2173,6 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 V = whole_direct || !beats_rivals ? 0 : (int)Vl;
                 u2 = p.u2;
                 floor_c = max(p.floor_cents, 0);
-                acc4[k] = make_uint4(0, 0, 0, 0);
             }
             int baseI = 0, baseC = 0;
             {
@@ -2214,6 +2216,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 for (; t < ADC_SUBSTEPS; ++t) s_hdr[t * 32 + lane] = 0u;
             }
             int B = whole_direct ? 0 : baseC;
+            if (act) acc4[k] = make_uint4((uint32_t)baseI, 0u, 0u, 0u);  // the day's impressions | clicks, conversions, cents paid
             {   // room in the chunk's slot pool (units padded to 4 slots); a unit that does not fit is re-walked
                 const int b4 = (B + 3) & ~3;
                 const int off = warp_incl_scan(b4, lane) - b4;
@@ -2259,6 +2262,25 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 }
             }
             __syncwarp();
+            // (c) the round index: the cheapest FIRST click of every (sub-step, chunk) round -- a round whose
+            // cheapest first click costs more than what is left of the budget changes nothing (every lane
+            // breaks at once, bsim:99-104), and the walk does not visit it.  0: a lane of the round is walked
+            // by lane_walk (always visited); all ones: no clicked slot in the round.
+            {
+                const uint32_t off = (uint32_t)s_poff[warp][lane];
+#pragma unroll 4
+                for (int t = 0; t < ADC_SUBSTEPS; ++t) {
+                    const uint32_t h = s_hdr[t * 32 + lane];
+                    uint32_t v = 0xFFFFFFFFu;
+                    if (act) {
+                        if (whole_direct || (h & 63u) == kHdrDirect) v = 0u;
+                        else if ((h & 63u) != 0u) v = cpool[off + (h >> 12)] & 0x7FFFFFFFu;
+                    }
+                    v = __reduce_min_sync(FULL, v);
+                    if (lane == 0) rmin[t * n_chunks + (c0 >> 5)] = v;
+                }
+            }
+            __syncwarp();
         }
         __threadfence_block();
         __syncwarp();
@@ -2270,17 +2292,39 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
         bool stop = false;
         bool bound = false;  // some round could not be proven fully affordable: next step comes here directly
         int t_stop = ADC_SUBSTEPS, k_stop = K;  // the lane after which nothing ran (bsim:230-233)
-        uint32_t h_next = lane < K ? hdr[lane] : 0u;
-        int t = 0, c0 = 0;
-        while (t < ADC_SUBSTEPS && !stop) {
-            const int k = c0 + lane;
+        // Rounds are visited through the index: 32 rounds' cheapest first clicks per load, the next round
+        // worth a visit is the first whose value `remaining` still covers.  An env with lane_walk lanes
+        // visits every round (their headers track the walk); a budget <= 0 gets its one look at round 0.
+        int round = 0;
+        uint32_t rm = 0u;  // this lane's round of the current block of 32
+        int rm_block = -1;
+        while (round < n_rounds && !stop) {
+            if (!env_direct && remaining > 0) {
+                if ((round >> 5) != rm_block) {
+                    rm_block = round >> 5;
+                    const int r = (rm_block << 5) + lane;
+                    rm = r < n_rounds ? rmin[r] : 0xFFFFFFFFu;
+                }
+                const bool worth = rm != 0xFFFFFFFFu && remaining >= cents32_to_dollars((int)(rm & 0x7FFFFFFFu));
+                const unsigned ahead = 0xFFFFFFFFu << (round & 31);
+                const unsigned cand = __ballot_sync(FULL, worth) & ahead;
+                // rounds passed over although they have clicked slots: the budget binds
+                const unsigned dry = __ballot_sync(FULL, rm != 0xFFFFFFFFu && !worth) & ahead;
+                if (cand == 0u) {
+                    bound = bound || dry != 0u;
+                    round = (rm_block + 1) << 5;
+                    continue;
+                }
+                const int nxt = __ffs(cand) - 1;
+                bound = bound || (dry & ((1u << nxt) - 1u)) != 0u;
+                round = (rm_block << 5) + nxt;
+            }
+            const int t_cur = round / n_chunks, c_cur = (round - t_cur * n_chunks) << 5;
+            ++round;
+            const int k = c_cur + lane;
             const bool act = k < K;
-            const uint32_t hoff = (uint32_t)t * Kp32 + (uint32_t)k;
-            const uint32_t h = h_next;
-            const int t_cur = t, c_cur = c0;
-            c0 += 32;
-            if (c0 >= K) { c0 = 0; ++t; }
-            h_next = (t < ADC_SUBSTEPS && c0 + lane < K) ? hdr[(uint32_t)t * Kp32 + (uint32_t)(c0 + lane)] : 0u;
+            const uint32_t hoff = (uint32_t)t_cur * Kp32 + (uint32_t)k;
+            const uint32_t h = act ? hdr[hoff] : 0u;
             // a chunk without an impression or a clicked slot in this sub-step leaves everything alone
             // (a sparse keyword, V < 24, has its whole day in sub-step 0); `remaining <= 0` on entry still
             // gets its one look
@@ -2302,11 +2346,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 const bool none = !lane_has || (!direct && !(remaining >= cents32_to_dollars((int)(w[0] & 0x7FFFFFFFu))));
                 if (__all_sync(FULL, none)) {
                     bound = bound || __any_sync(FULL, lane_has);
-                    if (act) {
-                        if (env_direct && nclk > 0) hdr[hoff] = h & ~63u;
-                        a4.x += (h >> 6) & 63u;
-                        acc4[k] = a4;
-                    }
+                    if (act && env_direct && nclk > 0) hdr[hoff] = h & ~63u;
                     continue;
                 }
             }
@@ -2454,7 +2494,6 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                             convs += ww >> 31;
                         }
                     }
-                    a4.x += (h >> 6) & 63u;
                     a4.y += (uint32_t)B;
                     a4.z += convs;
                     a4.w += cents;
@@ -2475,6 +2514,13 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
             int I = (int)(a4.x & 0x7FFFFFFFu), B = (int)a4.y, S = (int)a4.z;
             long long cost_c = a4.w, rev_c = 0;
             if (!(a4.x >> 31)) {
+                if (stop) {  // the lanes after the early break never ran: only the others' impressions count
+                    I = 0;
+                    for (int t = 0; t < ADC_SUBSTEPS; ++t) {
+                        if (t > t_stop || (t == t_stop && k > k_stop)) break;
+                        I += (int)((hdr[(uint32_t)t * Kp32 + (uint32_t)k] >> 6) & 63u);
+                    }
+                }
                 for (int r4 = 0; 4 * r4 < S; ++r4) {
                     const uint4 rw = src.draw(ST_REVENUE, (uint32_t)k, (uint32_t)r4);
                     const int left = S - 4 * r4;

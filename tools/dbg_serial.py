@@ -3,8 +3,10 @@ sys.path.insert(0, ".")
 import bench
 from adcraft_b200.vector_env import VectorBiddingSimulation
 from adcraft_b200 import _capi
+import os
+E, K = int(os.environ.get("DBG_E", 4096)), int(os.environ.get("DBG_K", 100))
+bench.K_KW, bench.MEAN_VOLUME, bench.CVR = K, int(os.environ.get("DBG_V", 128)), float(os.environ.get("DBG_CVR", 0.8))
 table = bench.workload_table()
-E, K = 4096, 100
 env = VectorBiddingSimulation(E, num_keywords=K, keywords=table, device="cuda", seed=1234, budget=1000.0)
 env.reset()
 bids = torch.full((E, K), 0.75, device="cuda", dtype=torch.float32)
