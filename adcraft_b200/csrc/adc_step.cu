@@ -2175,12 +2175,16 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 floor_c = max(p.floor_cents, 0);
             }
             int baseI = 0, baseC = 0;
+            bool short_day = false;
             {
                 const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), src.env, k0, k1);
                 const int q = V / ADC_SUBSTEPS, n0 = V - (ADC_SUBSTEPS - 1) * q;  // bsim:151-167
                 int t = 0, end_t = n0;     // sub-step t ends before auction end_t
                 int lastI = 0, lastC = 0;  // impressions / clicked slots of the sub-steps already emitted
                 const int Gmax = __reduce_max_sync(FULL, (V + 31) >> 5);
+                // a chunk of short days (sparse keywords, V < 24): every unit has its whole day in sub-step 0,
+                // one header row instead of 24
+                short_day = Gmax <= 1 && __all_sync(FULL, V < ADC_SUBSTEPS);
                 for (int g = 0; g < Gmax; ++g) {
                     const int rem = V - 32 * g;
                     const uint32_t active = rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? (1u << rem) - 1u : 0u);
@@ -2196,7 +2200,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                     }
                     // the sub-steps that end inside this group: one header each
                     const int hi = min(32 * g + 32, V);
-                    while (rem > 0 && t < ADC_SUBSTEPS && end_t <= hi) {
+                    while (!short_day && rem > 0 && t < ADC_SUBSTEPS && end_t <= hi) {
                         const int low = end_t - 32 * g;  // 1..32 (0 only for the empty sub-steps of a short day)
                         const uint32_t lm = low >= 32 ? 0xFFFFFFFFu : (1u << low) - 1u;
                         const int cumI = baseI + __popc(m.win & lm), cumC = baseC + __popc(m.click & lm);
@@ -2213,7 +2217,9 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 }
                 // a unit with more clicked slots than the slab describes: every lane is walked by lane_walk
                 if (baseC > kUnitSlots) whole_direct = true;
-                for (; t < ADC_SUBSTEPS; ++t) s_hdr[t * 32 + lane] = 0u;
+                if (short_day) s_hdr[lane] = (uint32_t)baseC | ((uint32_t)baseI << 6);  // < 24 auctions: the counts fit
+                else
+                    for (; t < ADC_SUBSTEPS; ++t) s_hdr[t * 32 + lane] = 0u;
             }
             int B = whole_direct ? 0 : baseC;
             if (act) acc4[k] = make_uint4((uint32_t)baseI, 0u, 0u, 0u);  // the day's impressions | clicks, conversions, cents paid
@@ -2226,11 +2232,13 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 // the lanes' headers, sub-step-major: one coalesced store per sub-step
                 if (act) {
                     const uint32_t add = (uint32_t)off << 12;
+                    const int rows = short_day ? 1 : ADC_SUBSTEPS;
 #pragma unroll 4
-                    for (int t = 0; t < ADC_SUBSTEPS; ++t) {
+                    for (int t = 0; t < rows; ++t) {
                         const uint32_t h = s_hdr[t * 32 + lane];
                         hdr[(uint32_t)t * Kp32 + (uint32_t)k] = whole_direct ? kHdrDirect : ((h & 63u) == kHdrDirect ? h : h + add);
                     }
+                    for (int t = rows; t < ADC_SUBSTEPS; ++t) hdr[(uint32_t)t * Kp32 + (uint32_t)k] = whole_direct ? kHdrDirect : 0u;
                 }
                 const PhiloxPre pc = philox_pre(a.step, stream_word(ST_COST, 0u, (uint32_t)k), src.env, k0, k1);
                 FlatCost fc;
@@ -2268,8 +2276,13 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
             // by lane_walk (always visited); all ones: no clicked slot in the round.
             {
                 const uint32_t off = (uint32_t)s_poff[warp][lane];
+                const int rows = short_day ? 1 : ADC_SUBSTEPS;
+                if (short_day) {  // rows 1..23: no clicked slots (or nothing but lane_walk lanes)
+                    const bool some_direct = __any_sync(FULL, act && whole_direct);
+                    if (lane >= 1 && lane < ADC_SUBSTEPS) rmin[lane * n_chunks + (c0 >> 5)] = some_direct ? 0u : 0xFFFFFFFFu;
+                }
 #pragma unroll 4
-                for (int t = 0; t < ADC_SUBSTEPS; ++t) {
+                for (int t = 0; t < rows; ++t) {
                     const uint32_t h = s_hdr[t * 32 + lane];
                     uint32_t v = 0xFFFFFFFFu;
                     if (act) {
@@ -2319,7 +2332,10 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 bound = bound || (dry & ((1u << nxt) - 1u)) != 0u;
                 round = (rm_block << 5) + nxt;
             }
-            const int t_cur = round / n_chunks, c_cur = (round - t_cur * n_chunks) << 5;
+            // round / n_chunks without the integer-division routine: (round + 0.5) / n is never within 0.5 / n of
+            // an integer, far more than the float quotient's error for any slab that fits a header index
+            const int t_cur = __float2int_rd(__fdividef((float)round + 0.5f, (float)n_chunks));
+            const int c_cur = (round - t_cur * n_chunks) << 5;
             ++round;
             const int k = c_cur + lane;
             const bool act = k < K;
