@@ -1103,6 +1103,235 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
 
 
 // ------------------------------------------------------------------------------------------
+// explicit keywords, free-running, budget cannot bind: the flattened step.
+//
+// An ExplicitKeyword's day (classes:493-538) is one Philox call per auction (impression / click /
+// conversion coin flips and the click's price) plus one per sub-step that had no impression (the phantom
+// zero-cost slot, classes:514-515) -- with the default env's ~16 auctions a day that is 16 + 23 calls
+// per unit, all independent.  A warp takes a batch of `cnt` units (32 on large steps, fewer on small
+// ones so that every SM has warps: the default env is 4096 x 10 units) and spreads
+//   the auctions of the batch over its lanes (item i belongs to the unit whose prefix range holds i):
+//     counts by shared-memory atomics, the sub-steps that saw an impression as a 24-bit mask, and the
+//     unit's un-rounded f64 cost sum IN AUCTION ORDER (env:235 sums the day's concatenated clicks): the
+//     first lane of every unit segment of the trip adds the segment's clicked prices one after the other;
+//   the phantom slots of the batch (the i-th empty sub-step of a unit: fns on the mask);
+//   one revenue per conversion, 4 per Philox call, as in the implicit kernel.
+// Same draws, same results as one thread walking the unit (adc_units_kernel / the C oracle).
+// ------------------------------------------------------------------------------------------
+struct __align__(16) FlatExp {  // 64 B per unit in shared memory
+    uint32_t thr_impr, thr_click, thr_conv, genv;
+    int k, n0, q, pad0;
+    double mean, sd;  // price = clamp(mean + sd * z, 0, 4.4) (explicit_cost)
+    uint32_t pad1[4];
+};
+static_assert(sizeof(FlatExp) == 64, "FlatExp layout");
+
+constexpr int kMaxFlatExplicitVolume = 1 << 16;  // beyond: the env takes the exact serial kernel
+
+__global__ void __launch_bounds__(kFlatWarps * 32)
+adc_flat_explicit_kernel(const __grid_constant__ adc_step_args a, int cnt)
+{
+    __shared__ FlatExp s_exp[kFlatWarps][32];
+    __shared__ FlatRev s_rev[kFlatWarps][32];
+    __shared__ int s_start[kFlatWarps][32];
+    __shared__ unsigned char s_nzl[kFlatWarps][32];
+    __shared__ int s_cnt[kFlatWarps][3][32];       // impressions, clicks, conversions
+    __shared__ unsigned s_mask[kFlatWarps][32];    // sub-steps with an impression; then: sub-steps that get a phantom slot
+    __shared__ double s_acc[kFlatWarps][32];       // the units' running f64 cost sums
+    __shared__ double s_trip[kFlatWarps][32];      // the prices of the current trip
+    __shared__ unsigned s_sum[kFlatWarps][32][2];  // revenue sums, 24-bit split
+
+    const int K = a.kw.K;
+    const int64_t total = (int64_t)a.E * K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gwarp = (int64_t)blockIdx.x * kFlatWarps + warp;
+    const int64_t n_warps = (int64_t)gridDim.x * kFlatWarps;
+    const int64_t n_batches = (total + cnt - 1) / cnt;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const unsigned FULL = 0xFFFFFFFFu;
+    const adc_tape *no_tape = nullptr;
+    if (blockIdx.x == 0 && threadIdx.x == 0) reset_next_counters(a);
+
+    FlatExp *exps = s_exp[warp];
+    int *start = s_start[warp];
+    unsigned char *nzl = s_nzl[warp];
+
+    for (int64_t batch = gwarp; batch < n_batches; batch += n_warps) {
+        // ---------------- per-unit setup, lane <-> unit ----------------
+        const int64_t u = batch * cnt + lane;
+        const bool valid = lane < cnt && u < total;
+        int e = 0, k = 0, V = 0;
+        bool force = false;
+        float rev_mean = 0.f, rev_sd = 0.f;
+        FlatExp fx;
+        fx.thr_impr = fx.thr_click = fx.thr_conv = fx.genv = 0u; fx.k = 0; fx.n0 = 0; fx.q = 1; fx.pad0 = 0;
+        fx.mean = 0.0; fx.sd = 0.0; fx.pad1[0] = fx.pad1[1] = fx.pad1[2] = fx.pad1[3] = 0u;
+        if (valid) {
+            e = (int)(u / K);
+            k = (int)(u - (int64_t)e * K);
+            const UnitPar p = load_unit_par(a, e, k);
+            PhiloxSrc src{k0, k1, a.step, philox_env(a, e)};
+            uint4 uw;
+            const long long Vl = unit_volume(a, src, no_tape, e, k, &uw);
+            force = Vl > kMaxFlatExplicitVolume;
+            V = force ? 0 : (int)Vl;
+            fx.thr_impr = p.thr_impr; fx.thr_click = p.thr_click; fx.thr_conv = p.thr_conv; fx.genv = src.env;
+            fx.k = k;
+            fx.q = V / ADC_SUBSTEPS;
+            fx.n0 = V - (ADC_SUBSTEPS - 1) * fx.q;  // bsim:151-167
+            const double xs = __dsqrt_rn(p.bid);     // explicit_cost's constants, once per unit
+            fx.sd = __dadd_rn(1e-10, __ddiv_rn(xs, 6.0));
+            fx.mean = __dadd_rn(__ddiv_rn(xs, 4.0), 4.4 / 2.0);
+            rev_mean = p.rev_mean;
+            rev_sd = p.rev_sd;
+        }
+        __syncwarp();
+        exps[lane] = fx;
+        s_cnt[warp][0][lane] = 0; s_cnt[warp][1][lane] = 0; s_cnt[warp][2][lane] = 0;
+        s_mask[warp][lane] = 0u;
+        s_acc[warp][lane] = 0.0;
+        // ---------------- auctions, flattened over the batch ----------------
+        {
+            const FlatMap fm = flat_map_begin(V, lane, start, nzl);
+            const int TA = fm.total;
+            for (int base = 0; base < TA; base += 32) {
+                const int b = flat_map_unit(fm, base, lane, nzl);
+                const int i = base + lane;
+                const bool act = i < TA;
+                bool clk = false;
+                double cost = 0.0;
+                if (act) {
+                    const FlatExp f = exps[b];
+                    const int j = i - start[b];
+                    const uint4 w = philox4x32_10((uint32_t)j, a.step, stream_word(ST_AUCTION, 0u, (uint32_t)f.k), f.genv, k0, k1);
+                    if (w.x <= f.thr_impr) {  // Bernoulli(p); the lane's sum is Binomial(n, p)
+                        const int t = j < f.n0 ? 0 : 1 + (j - f.n0) / f.q;
+                        atomicOr(&s_mask[warp][b], 1u << t);
+                        atomicAdd(&s_cnt[warp][0][b], 1);
+                        clk = w.y <= f.thr_click;
+                        if (clk) {
+                            cost = clampd(__dadd_rn(f.mean, __dmul_rn(f.sd, (double)znorm(w.w))), 0.0, 4.4);
+                            atomicAdd(&s_cnt[warp][1][b], 1);
+                            if (w.z <= f.thr_conv) atomicAdd(&s_cnt[warp][2][b], 1);
+                        }
+                    }
+                }
+                // the units' cost sums, in auction order: lanes of one unit are neighbours
+                s_trip[warp][lane] = cost;
+                __syncwarp();
+                const unsigned clicked = __ballot_sync(FULL, clk);
+                const int b_prev = __shfl_up_sync(FULL, b, 1);
+                const bool first = act && (lane == 0 || b != b_prev);
+                const unsigned firsts = __ballot_sync(FULL, first);
+                if (first) {
+                    const unsigned above = lane == 31 ? 0u : firsts & (0xFFFFFFFFu << (lane + 1));
+                    const unsigned upto = above ? (1u << (__ffs(above) - 1)) - 1u : 0xFFFFFFFFu;
+                    unsigned seg = clicked & upto & (0xFFFFFFFFu << lane);
+                    if (seg) {
+                        double sum = s_acc[warp][b];
+                        while (seg) {
+                            const int l = __ffs(seg) - 1;
+                            seg &= seg - 1;
+                            sum = __dadd_rn(sum, s_trip[warp][l]);
+                        }
+                        s_acc[warp][b] = sum;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // ---------------- phantom slots: the sub-steps without an impression (classes:514-515) ----------------
+        {
+            __syncwarp();
+            const unsigned pm = valid && !force ? ~s_mask[warp][lane] & ((1u << ADC_SUBSTEPS) - 1u) : 0u;
+            __syncwarp();
+            s_mask[warp][lane] = pm;
+            const FlatMap fm = flat_map_begin(__popc(pm), lane, start, nzl);
+            const int TP = fm.total;
+            for (int base = 0; base < TP; base += 32) {
+                const int b = flat_map_unit(fm, base, lane, nzl);
+                const int i = base + lane;
+                if (i < TP) {
+                    const FlatExp f = exps[b];
+                    const int t = (int)__fns(s_mask[warp][b], 0u, i - start[b] + 1);
+                    const uint4 w = philox4x32_10((uint32_t)t, a.step, stream_word(ST_PHANTOM, 0u, (uint32_t)f.k), f.genv, k0, k1);
+                    if (w.y <= f.thr_click) {
+                        atomicAdd(&s_cnt[warp][1][b], 1);
+                        if (w.z <= f.thr_conv) atomicAdd(&s_cnt[warp][2][b], 1);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        const int I = s_cnt[warp][0][lane], B = s_cnt[warp][1][lane], S = s_cnt[warp][2][lane];
+        const double cost_f = s_acc[warp][lane];
+        // ---------------- revenues: one draw per conversion, 4 per Philox call ----------------
+        {
+            const PhiloxPre pr = philox_pre(a.step, stream_word(ST_REVENUE, 0u, (uint32_t)k), fx.genv, k0, k1);
+            FlatRev fr;
+            fr.mean = rev_mean; fr.sd = rev_sd; fr.S = S;
+            fr.n0 = pr.n0; fr.n1 = pr.n1; fr.x3 = pr.x3; fr.pad0 = 0; fr.pad1 = 0;
+            s_rev[warp][lane] = fr;
+            s_sum[warp][lane][0] = 0u; s_sum[warp][lane][1] = 0u;
+        }
+        const FlatMap rm = flat_map_begin((S + 3) >> 2, lane, start, nzl);
+        const int TR = rm.total;
+        for (int base = 0; base < TR; base += 32) {
+            const int b = flat_map_unit(rm, base, lane, nzl);
+            const int i = base + lane;
+            if (i < TR) {
+                const FlatRev fr = s_rev[warp][b];
+                const int blk = i - start[b];
+                const uint4 w = philox_from_pre((uint32_t)blk, fr.n0, fr.n1, fr.x3, k0, k1);
+                const int left = fr.S - 4 * blk;  // >= 1
+                const int c0 = revenue_cents(w.x, fr.mean, fr.sd), c1 = revenue_cents(w.y, fr.mean, fr.sd);
+                const int c2 = revenue_cents(w.z, fr.mean, fr.sd), c3 = revenue_cents(w.w, fr.mean, fr.sd);
+                const long long sum = (long long)c0 + (left > 1 ? c1 : 0) + (long long)(left > 2 ? c2 : 0) +
+                                      (left > 3 ? c3 : 0);
+                atomicAdd(&s_sum[warp][b][0], (unsigned)(sum & 0xFFFFFF));
+                atomicAdd(&s_sum[warp][b][1], (unsigned)(sum >> 24));
+            }
+        }
+        __syncwarp();
+        const long long rev_c = (long long)s_sum[warp][lane][0] + ((long long)s_sum[warp][lane][1] << 24);
+
+        // ---------------- outputs, env completion ----------------
+        int safe = 0;
+        if (valid) {
+            a.out.impressions[u] = I;
+            a.out.clicks[u] = B;
+            a.out.conversions[u] = S;
+            a.out.revenue_cents[u] = rev_c;
+            store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev_c));
+            a.out.cost_cents[u] = 0;
+            // a unit beyond the kernel's volume cap makes the env look unaffordable: the serial kernel walks it
+            a.scratch.unit_cost_f64[u] = force ? __longlong_as_double(0x7FF0000000000000LL) : cost_f;
+            store_f(a.out.cost, a.out.float_dtype, u, cost_f);
+            store_flat_unit(a, e, k, I, B, S, cost_f, cents_to_dollars(rev_c));
+            safe = unit_done(a, e, 0, 0);
+        }
+        if (a.drift.mask != nullptr || a.out.episode_profit_cents != nullptr) {
+            unsigned todo = __ballot_sync(FULL, safe != 0);
+            while (todo) {
+                const int src_lane = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int ee = __shfl_sync(FULL, e, src_lane);
+                episode_accumulate(a, ee, lane, 32);
+                if (a.drift.mask == nullptr) continue;
+                const uint32_t ge = philox_env(a, ee);
+                for (int kk = lane; kk < K; kk += 32) {
+                    if (!drift_wanted(a, kk)) continue;
+                    const uint4 w = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)kk), ge, k0, k1);
+                    drift_apply(a, ee, kk, drift_from_words(a, w));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
 // replay kernel (implicit keywords, tape-driven, budget cannot bind): HBM-bound by construction.
 // One warp per unit; every tape stream is read with coalesced loads:
 //   competitor bids  32 x int32 per trip, 4 trips in flight;
@@ -2705,7 +2934,16 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         }
         ++*launches;
         err = cudaGetLastError();
-    } else if (tape == nullptr) {
+    } else if (tape == nullptr && a.kw.kind == ADC_EXPLICIT && a.n_lanes != 1) {
+        // units per warp and batch: 32 on large steps, fewer on small ones so that every SM gets ~64 warps
+        int cnt = 32;
+        while (cnt > 1 && total / cnt < (int64_t)num_sms() * 64) cnt >>= 1;
+        auto kern = adc_flat_explicit_kernel;
+        const int64_t n_batches = (total + cnt - 1) / cnt;
+        kern<<<(unsigned)grid_for(kern, kFlatWarps * 32, n_batches * 32), kFlatWarps * 32, 0, s>>>(a, cnt);
+        ++*launches;
+        err = cudaGetLastError();
+    } else if (tape == nullptr) {  // multi-bidder keywords; explicit keywords with n_lanes = 1 (A/B against the flattened kernel)
         auto kern = adc_units_kernel<PhiloxSrc, true>;
         kern<<<(unsigned)grid_for(kern, 128, total), 128, 0, s>>>(a, tp);
         ++*launches;

@@ -146,17 +146,40 @@ def test_force_serial_equals_fast_path(orc):
         assert torch.equal(oa[1], ob_[1])
 
 
-def test_philox_explicit_matches_oracle(orc):
+@pytest.mark.parametrize("n_lanes", [0, 1])
+def test_philox_explicit_matches_oracle(orc, n_lanes):
+    """Explicit keywords, free-running: the flattened kernel (n_lanes 0: a warp spreads the auctions and the
+    phantom slots of a batch of units over its lanes) and one thread per unit (n_lanes 1) against the oracle;
+    shapes that give batches of 1, 2 and 32 units per warp, budgets that bind (exact serial kernel)."""
     rng = np.random.default_rng(3)
-    for (K, E, budget) in [(1, 16, 1000.0), (10, 32, 1000.0), (10, 32, 15.0)]:
+    for (K, E, budget) in [(1, 16, 1000.0), (10, 32, 1000.0), (10, 32, 15.0), (7, 3000, 1000.0)]:
         table = make_explicit_table(rng, K)
-        env = _env(table, E, seed=77, budget=budget, obs_dtype=torch.float64)
+        env = _env(table, E, seed=77, budget=budget, obs_dtype=torch.float64, n_lanes=n_lanes)
         ob = _oracle_batch(orc, table, E, seed=77, budget=budget)
         for s in range(4):
             bids = np.round(rng.uniform(0.01, 3.0, (E, K)), 2)
             obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda()})
             ref = ob.step(bids, n_threads=4)
             _compare(obs, reward, term, trunc, ref, env, RTOL64)
+
+
+def test_philox_explicit_large_volume_and_drift(orc):
+    """A unit beyond the flattened explicit kernel's volume cap sends its env to the exact serial kernel;
+    non-stationary explicit keywords drift from the same ST_UNIT draw in both."""
+    rng = np.random.default_rng(13)
+    K, E = 4, 6
+    table = make_explicit_table(rng, K, E=E)
+    table.vol_mean[::2, 1] = 70000.0
+    table.vol_std[::2, 1] = 5.0
+    mask = [True, False, True, True]
+    env = _env(table, E, seed=5, budget=1e9, obs_dtype=torch.float64, updater_mask=mask)
+    ob = _oracle_batch(orc, table, E, seed=5, budget=1e9, mask=np.array(mask))
+    for s in range(3):
+        bids = np.round(rng.uniform(0.01, 3.0, (E, K)), 2)
+        obs, reward, term, trunc, _ = env.step({"keyword_bids": torch.from_numpy(bids).cuda()})
+        ref = ob.step(bids, n_threads=4)
+        _compare(obs, reward, term, trunc, ref, env, RTOL64)
+    assert int(obs["impressions"].max()) > 1000
 
 
 def test_drift_matches_oracle(orc):
