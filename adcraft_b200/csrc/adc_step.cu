@@ -25,6 +25,7 @@
 #include "adc_rng.cuh"
 #include "adc_step.h"
 
+#include <algorithm>
 #include <cstddef>
 #include <cstdio>
 
@@ -2233,9 +2234,9 @@ adc_serial_kernel(const __grid_constant__ adc_step_args a, const __grid_constant
 // ------------------------------------------------------------------------------------------
 constexpr int kSerWarps = 4;
 constexpr int kSlabGroups = 16;    // 32-auction groups per unit and day the slab describes (volume <= 512)
-constexpr int kPoolPerUnit = 128;  // a chunk of 32 keywords shares a pool of 32 x 128 clicked slots
-constexpr int kChunkPool = 32 * kPoolPerUnit;
 constexpr int kUnitSlots = 512;    // clicked slots of one unit's day the slab describes (every day of <= 512 auctions)
+constexpr int kPoolPerUnit = 128;  // a chunk of 32 keywords shares a pool of >= 32 x 128 clicked slots: the smallest slab
+constexpr int kMaxPoolPerUnit = kUnitSlots;  // ... and of 32 x 512 when the workspace has the room (no chunk can overflow then)
 constexpr int kSerRegs = 6;       // clicked slots of a lane and sub-step the walk holds in registers
 constexpr int kSerMinBlocks = 7;   // 28 warps per SM: a 4096-env queue is resident in one wave
 
@@ -2244,7 +2245,7 @@ constexpr int kSerMinBlocks = 7;   // 28 warps per SM: a 4096-env queue is resid
 // conversions.
 constexpr uint32_t kHdrDirect = 63u, kHdrDirectDone = 62u, kHdrMaxCount = 61u;
 
-// slab of one warp: uint32 hdr[24][Kp] (Kp = K rounded up to 32) | uint32 pool[Kp / 32][kChunkPool] |
+// slab of one warp: uint32 hdr[24][Kp] (Kp = K rounded up to 32) | uint32 pool[Kp / 32][32 x slots per keyword] |
 // uint4 acc[Kp]: per keyword the day's impressions | bit 31: mixed commit, and the running sums of the walk
 // (clicks, conversions, cents) | uint32 rmin[24 x Kp / 32]: the round index of the walk
 __host__ __device__ inline int64_t slab_kp(int K) { return ((int64_t)K + 31) & ~(int64_t)31; }
@@ -2252,6 +2253,11 @@ __host__ __device__ inline int64_t slab_bytes_of(int K)
 {
     return (int64_t)ADC_SUBSTEPS * slab_kp(K) * 4 + slab_kp(K) * kPoolPerUnit * 4 + slab_kp(K) * 16 +
            ((ADC_SUBSTEPS * (slab_kp(K) / 32) * 4 + 15) & ~(int64_t)15);
+}
+// ... of which everything but the pool:
+__host__ __device__ inline int64_t slab_fixed_bytes_of(int K)
+{
+    return slab_bytes_of(K) - slab_kp(K) * kPoolPerUnit * 4;
 }
 
 // A (sub-step, keyword) lane the slab cannot describe: walked again with the budget by lane_walk.  Out
@@ -2336,7 +2342,7 @@ __device__ __noinline__ CommitOut commit_mixed_unit(const PhiloxSrc &src, const 
 }
 
 __global__ void __launch_bounds__(kSerWarps * 32, kSerMinBlocks)
-adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_slabs)
+adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_slabs, long long slab_stride, int pool_per_unit)
 {
     // phase 0 stages a chunk's 24 x 32 headers and 8 x 32 conversion-by-rank words here
     __shared__ uint32_t s_stage[kSerWarps][(ADC_SUBSTEPS + kUnitSlots / 32) * 32];
@@ -2359,10 +2365,11 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const adc_tape *no_tape = nullptr;
     if (gwarp >= n_warps) return;
-    unsigned char *const slab_raw = reinterpret_cast<unsigned char *>(a.scratch.serial_ws) + (size_t)gwarp * (size_t)slab_bytes_of(K);
+    unsigned char *const slab_raw = reinterpret_cast<unsigned char *>(a.scratch.serial_ws) + (size_t)gwarp * (size_t)slab_stride;
+    const uint32_t ppu = (uint32_t)pool_per_unit;  // clicked slots per keyword in a chunk's pool (a multiple of 4)
     uint32_t *const hdr = reinterpret_cast<uint32_t *>(slab_raw);
     uint32_t *const pool = hdr + (size_t)ADC_SUBSTEPS * Kp;  // chunk c0 / 32 owns pool[c0 * kPoolPerUnit ..)
-    uint4 *const acc4 = reinterpret_cast<uint4 *>(pool + (size_t)Kp * kPoolPerUnit);
+    uint4 *const acc4 = reinterpret_cast<uint4 *>(pool + (size_t)Kp * ppu);
     uint32_t *const rmin = reinterpret_cast<uint32_t *>(acc4 + Kp);  // [24 x Kp / 32] cheapest first click of a round
     const uint32_t Kp32 = (uint32_t)Kp;
     const int n_chunks = (int)(Kp32 >> 5), n_rounds = ADC_SUBSTEPS * n_chunks;
@@ -2455,7 +2462,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
             {   // room in the chunk's slot pool (units padded to 4 slots); a unit that does not fit is re-walked
                 const int b4 = (B + 3) & ~3;
                 const int off = warp_incl_scan(b4, lane) - b4;
-                if (off + b4 > kChunkPool) { whole_direct = true; B = 0; }
+                if ((uint32_t)(off + b4) > 32u * ppu) { whole_direct = true; B = 0; }
                 env_direct = env_direct || __any_sync(FULL, whole_direct || lane_direct);
                 s_poff[warp][lane] = off;
                 // the lanes' headers, sub-step-major: one coalesced store per sub-step
@@ -2479,7 +2486,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
             // (b) one price per clicked slot, 4 per Philox call, flattened over the 32 keywords
             const FlatMap fm = flat_map_begin((B + 3) >> 2, lane, s_start[warp], s_nzl[warp]);
             const int TB = fm.total;
-            uint32_t *const cpool = pool + (size_t)c0 * kPoolPerUnit;
+            uint32_t *const cpool = pool + (size_t)c0 * ppu;
             for (int base = 0; base < TB; base += 32) {
                 const int b = flat_map_unit(fm, base, lane, s_nzl[warp]);
                 const int i = base + lane;
@@ -2576,7 +2583,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
             if (remaining > 0 && __all_sync(FULL, (h & 0xFFFu) == 0u)) continue;
             int nclk = (int)(h & 63u);
             const bool direct = nclk == (int)kHdrDirect;
-            const uint32_t my_off = (uint32_t)c_cur * kPoolPerUnit + (h >> 12);
+            const uint32_t my_off = (uint32_t)c_cur * ppu + (h >> 12);
             const uint32_t *const sp = pool + my_off;
             uint32_t w[kSerRegs];
 #pragma unroll
@@ -2699,7 +2706,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                     next = remaining;
                     if (lane == l) {
                         dout = serial_direct_lane(a, src, e, k, t_cur,
-                                                  conversions_before(hdr, pool + (uint32_t)c_cur * kPoolPerUnit, Kp, k, t_cur),
+                                                  conversions_before(hdr, pool + (uint32_t)c_cur * ppu, Kp, k, t_cur),
                                                   remaining);
                         direct_done = true;
                         next = dout.next;
@@ -2777,7 +2784,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
             } else {
                 // a keyword with lanes walked by lane_walk: their conversions shift the revenue ranks of the
                 // slab lanes (S of the mixed commit counts them too: they are in acc.S already)
-                const CommitOut o = commit_mixed_unit(src, hdr, pool + (uint32_t)(k & ~31) * kPoolPerUnit, Kp, k, t_stop, k_stop,
+                const CommitOut o = commit_mixed_unit(src, hdr, pool + (uint32_t)(k & ~31) * ppu, Kp, k, t_stop, k_stop,
                                                       rev_mean, rev_sd);
                 I = o.I + acc.I[u];
                 B = o.B + acc.B[u];
@@ -2977,7 +2984,13 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         int64_t grid = grid_for(kern, kSerWarps * 32, (int64_t)a.E * 32);
         const int64_t by_ws = (n_slabs + kSerWarps - 1) / kSerWarps;
         if (by_ws < grid) grid = by_ws;
-        kern<<<(unsigned)grid, kSerWarps * 32, 0, s>>>(a, (int)(n_slabs > 0x7FFFFFFF ? 0x7FFFFFFF : n_slabs));
+        // The warps that run share the whole workspace: what a slab has beyond the smallest layout goes to its
+        // slot pools (up to 512 slots per keyword, where no chunk of keywords can overflow its pool any more).
+        const int64_t n_run = std::min<int64_t>(std::min<int64_t>(n_slabs, grid * kSerWarps), 0x7FFFFFFF);
+        const int64_t stride = (a.scratch.serial_ws_bytes / n_run) & ~(int64_t)15;
+        int64_t ppu = (stride - slab_fixed_bytes_of(a.kw.K)) / (slab_kp(a.kw.K) * 4) & ~(int64_t)3;
+        if (ppu > kMaxPoolPerUnit) ppu = kMaxPoolPerUnit;
+        kern<<<(unsigned)grid, kSerWarps * 32, 0, s>>>(a, (int)n_run, (long long)stride, (int)ppu);
     } else if (tape == nullptr) {
         auto kern = adc_serial_kernel<PhiloxSrc>;
         kern<<<(unsigned)grid_for(kern, 64, a.E), 64, 0, s>>>(a, tp);

@@ -198,7 +198,11 @@ class VectorBiddingSimulation:
         # one slab per resident warp of the exact serial walk (28 warps per SM), within the cap
         slab = max(int(self._lib.adc_serial_slab_bytes(K)), 1)
         n_slabs = max(1, min(E, 148 * 28, self.serial_ws_cap // slab))
-        self._scratch["serial_ws"] = torch.empty(n_slabs * slab, dtype=torch.uint8, device=dev)
+        # the smallest slab keeps 128 clicked slots per keyword; the warps share whatever the workspace has
+        # beyond it, up to 512 per keyword (every day of <= 512 auctions fits whatever its clicks are)
+        roomy = slab + (K + 31) // 32 * 32 * (512 - 128) * 4
+        self._scratch["serial_ws"] = torch.empty(min(n_slabs * roomy, max(self.serial_ws_cap, n_slabs * slab)),
+                                                 dtype=torch.uint8, device=dev)
         self._scratch["serial_hint"] = z(E, dtype=torch.uint8)
         self._detail = None
         if self.detail_cap > 0:

@@ -156,9 +156,11 @@ typedef struct adc_scratch {
     int32_t *acc_clicks;
     int32_t *acc_conversions;
     /* Optional DEVICE workspace of the warp-cooperative exact serial walk (free-running implicit
-     * keywords): every resident warp expands one queued env's day into a slab of about 370 bytes
-     * per keyword (exactly adc_serial_slab_bytes(K)); 16-byte aligned.  The launcher runs as many warps
-     * as slabs fit (about 4100 resident warps at most); NULL / too small for one slab: the walk falls back to one
+     * keywords): every resident warp expands one queued env's day into a slab; the smallest
+     * slab is adc_serial_slab_bytes(K) (about 630 bytes per keyword, 128 clicked slots per keyword), and
+     * the warps that run share the whole workspace: room beyond the minimum goes to the slabs' slot pools
+     * (up to 512 slots per keyword, where no day of <= 512 auctions can overflow them).  16-byte aligned.
+     * The launcher runs as many warps as smallest slabs fit (about 4100 resident warps at most); NULL / too small for one slab: the walk falls back to one
      * thread per env (correct, much slower). */
     void *serial_ws;
     int64_t serial_ws_bytes;

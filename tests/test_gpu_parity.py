@@ -267,20 +267,25 @@ def test_bids_beyond_fast_kernel_caps_take_the_exact_route(orc):
     _compare(obs, reward, term, trunc, ref, env, RTOL64)
 
 
-@pytest.mark.parametrize("vol", [900, 420, 200])
+@pytest.mark.parametrize("vol,tight_ws", [(900, False), (420, False), (420, True), (200, True)])
 @pytest.mark.parametrize("alias", [False, True])
-def test_serial_warp_kernel_buffer_overflow_and_zero_budget(orc, alias, vol):
+def test_serial_warp_kernel_buffer_overflow_and_zero_budget(orc, alias, vol, tight_ws):
     """What the warp-serial kernel's slab cannot describe takes the direct re-walk: days of more than
     512 auctions (vol 900), sub-steps with more than 61 impressions, chunks of 32 keywords with more
-    than 4096 clicked slots in the day (vol 420: whole units direct, mixed with slab units); budgets of
-    0 stop after the first lane of the day (bsim:230-233)."""
+    than 4096 clicked slots in the day (vol 420 with the smallest workspace, `tight_ws`: whole units
+    direct, mixed with slab units; with the default workspace the pools grow to 512 slots per keyword and
+    nothing overflows); budgets of 0 stop after the first lane of the day (bsim:230-233)."""
     rng = np.random.default_rng(41)
     K, E = 37, 24
     table = make_implicit_table(rng, K, vol)
     table.ctr[:] = rng.uniform(0.7, 1.0, K)
     if vol == 200:
         table.ctr[::2] = rng.uniform(0.05, 0.3, (K + 1) // 2)
-    env = _env(table, E, seed=12, budget=1000.0, budget_alias=alias, obs_dtype=torch.float64)
+    extra = {}
+    if tight_ws:
+        from adcraft_b200 import _capi
+        extra["serial_ws_bytes"] = E * int(_capi.load().adc_serial_slab_bytes(K))
+    env = _env(table, E, seed=12, budget=1000.0, budget_alias=alias, obs_dtype=torch.float64, **extra)
     ob = _oracle_batch(orc, table, E, seed=12, budget=1000.0, alias=alias)
     budgets = rng.choice([0.0, 5.0, 60.0, 400.0, 2500.0], size=E)
     for s in range(2):
