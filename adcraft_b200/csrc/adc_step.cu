@@ -809,7 +809,8 @@ __device__ __noinline__ FlatChunk flat_chunk(int64_t total, int64_t n_warps, boo
     return c;
 }
 
-constexpr int kFlatWarps = 8;
+// 7 warps x 4 CTAs = 28 warps per SM at 72 registers (8 x 3 = 24: C2 0.188 -> 0.179 ms, C3 very sparse 1.61 -> 1.54 ms)
+constexpr int kFlatWarps = 7;
 // Caps of the fast kernel's 32-bit sums; a unit beyond them sends its env to the exact serial kernel
 // instead (volumes and bids this large do not occur in the reference's configs).
 constexpr int kMaxFlatVolume = 65535;
