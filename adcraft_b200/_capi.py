@@ -13,7 +13,7 @@ from . import build as _build
 SUBSTEPS = 24
 IMPLICIT, EXPLICIT, IMPLICIT_MULTI = 0, 1, 2
 F32, F64 = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class AdcError(RuntimeError):
@@ -49,7 +49,7 @@ class StepOut(C.Structure):
         ("obs_cum_profit", C.c_void_p), ("obs_days", C.c_void_p), ("terminated", C.c_void_p),
         ("truncated", C.c_void_p), ("remaining_budget", C.c_void_p),
         ("episode_profit_cents", C.c_void_p), ("episode_reward", C.c_void_p), ("episode_count", C.c_void_p),
-        ("rows", C.c_void_p), ("flat_obs", C.c_void_p),
+        ("rows", C.c_void_p), ("flat_obs", C.c_void_p), ("unit_records", C.c_void_p),
     ]
 
 

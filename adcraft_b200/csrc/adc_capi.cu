@@ -58,6 +58,9 @@ int validate(const adc_step_args *a, const adc_tape *tape)
                     a->out.revenue && a->out.cost_cents && a->out.revenue_cents && a->out.reward &&
                     a->out.obs_cum_profit && a->out.obs_days && a->out.terminated && a->out.truncated,
                 "output pointer is NULL");
+    ADC_REQUIRE(a->out.unit_records == nullptr ||
+                    (a->out.float_dtype == ADC_F32 && ((uintptr_t)a->out.unit_records & 15) == 0),
+                "out.unit_records needs float_dtype ADC_F32 and 16-byte alignment");
     ADC_REQUIRE(a->scratch.serial_list && a->scratch.serial_count && a->scratch.env_profit &&
                     a->scratch.env_cost && a->scratch.env_done, "scratch pointer is NULL");
     ADC_REQUIRE(a->kw.kind == ADC_IMPLICIT || a->scratch.unit_cost_f64 != nullptr,

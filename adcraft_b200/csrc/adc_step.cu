@@ -173,6 +173,35 @@ __device__ __forceinline__ void pack_row_tail(const adc_step_args &a, int e)
     *reinterpret_cast<uint32_t *>(row + L.tail + 20) = (uint32_t)a.out.terminated[e] | ((uint32_t)a.out.truncated[e] << 8);
 }
 
+// ------------------------------------------------------------------------------------------
+// unit records (adc_step_out.unit_records): a unit's observation as one aligned 16-byte store
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_unit_record(const adc_step_args &a, int64_t u, int I, int B, int S, double cost,
+                                                  double rev)
+{
+    const unsigned over = (I > 65535 || B > 65535 || S > 65535) ? 1u : 0u;
+    uint4 r;
+    r.x = (unsigned)min(I, 65535) | ((unsigned)min(B, 65535) << 16);
+    r.y = (unsigned)min(S, 65535) | (over << 16);
+    r.z = __float_as_uint((float)cost);
+    r.w = __float_as_uint((float)rev);
+    reinterpret_cast<uint4 *>(a.out.unit_records)[u] = r;
+}
+
+// env e's records from the step's finished outputs (the exact walk and the kernel families that do
+// not write records themselves); `lane` of 32
+__device__ __forceinline__ void pack_units_warp(const adc_step_args &a, int e, int lane)
+{
+    const int K = a.kw.K;
+    const int64_t u0 = (int64_t)e * K;
+    for (int k = lane; k < K; k += 32) {
+        const int64_t u = u0 + k;
+        store_unit_record(a, u, __ldcg(a.out.impressions + u), __ldcg(a.out.clicks + u), __ldcg(a.out.conversions + u),
+                          (double)__ldcg(reinterpret_cast<const float *>(a.out.cost) + u),
+                          (double)__ldcg(reinterpret_cast<const float *>(a.out.revenue) + u));
+    }
+}
+
 // cents / 100 correctly rounded (== np.around(x, 2) of the same cents value).  The f64 division is a
 // ~35-instruction routine; for |c| < 2^31 one Newton step on c * 0.01 with the exact FMA residual gives
 // the identical double (checked exhaustively against c / 100.0 for every c in [0, 2^31) on the host,
@@ -1066,6 +1095,7 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
             store_f(a.out.revenue, a.out.float_dtype, u, cents_to_dollars(rev));
             store_flat_unit(a, e, k, I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
             if (a.out.rows != nullptr) pack_row_unit(a, e, k, I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
+            if (a.out.unit_records != nullptr) store_unit_record(a, u, I, B, S, cents_to_dollars(cost), cents_to_dollars(rev));
             safe = unit_done(a, e, rev - cost, cost, over_cap);
             if (safe && a.out.rows != nullptr) pack_row_tail(a, e);  // this lane ran the env tail
         }
@@ -2820,6 +2850,11 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
             __syncwarp();
             pack_row_warp(a, e, reinterpret_cast<unsigned char *>(a.out.rows), lane);
         }
+        if (a.out.unit_records != nullptr) {
+            __threadfence();
+            __syncwarp();
+            pack_units_warp(a, e, lane);
+        }
         if (a.drift.mask != nullptr) {
             for (int kk = lane; kk < K; kk += 32) {
                 if (!drift_wanted(a, kk)) continue;
@@ -2844,6 +2879,15 @@ adc_pack_rows_kernel(const __grid_constant__ adc_step_args a, unsigned char *row
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t e = warp; e < a.E; e += n_warps) pack_row_warp(a, (int)e, rows, lane);
+}
+
+__global__ void __launch_bounds__(256)
+adc_pack_units_kernel(const __grid_constant__ adc_step_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = warp; e < a.E; e += n_warps) pack_units_warp(a, (int)e, lane);
 }
 
 __global__ void adc_reset_envs_kernel(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day)
@@ -3004,6 +3048,14 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     if (err != cudaSuccess) return err;
     // compact rows: the free-running implicit kernels pack them as they finalise each env; every
     // other kernel family gets one packing pass over the finished step
+    if (a.out.unit_records != nullptr && !warp_walk) {
+        const int64_t want = ((int64_t)a.E * 32 + 255) / 256;
+        const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * 8));
+        adc_pack_units_kernel<<<(unsigned)grid, 256, 0, s>>>(a);
+        ++*launches;
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
     if (a.out.rows != nullptr && !warp_walk) return launch_pack_rows(a, a.out.rows, s, launches);
     return cudaSuccess;
 }

@@ -678,6 +678,57 @@ class VectorBiddingSimulation:
         stream.synchronize()
         return self._rows_views
 
+    def step_host_records(self, bids_host: torch.Tensor, budget_host: Optional[torch.Tensor] = None):
+        """``step`` for a CPU-side caller, fused, in its leanest form: ONE launch reads the pinned HOST
+        bids (UVA) and every unit's observation goes to pinned HOST memory as one aligned 16-byte record
+        (``adc_step_out.unit_records``: uint16 impressions / clicks / conversions / flags, float32
+        cost / revenue) -- 512 contiguous bytes per warp, full-size PCIe write transactions, 16 bytes per
+        unit instead of the 20 of ``mode="zero_copy"``'s five 4-byte streams; the env scalars land in
+        pinned host arrays as well.  No copy is enqueued; the int32 / float observation tensors of
+        ``step`` stay on the device and are updated too.  Returns strided views into the pinned record
+        block, valid until the next call; ``count_overflow[e, k]`` flags a count above 65535."""
+        assert self._have_keywords, "reset required, need to generate keywords to bid on"
+        E, K = self.num_envs, self.num_keywords
+        assert self.obs_dtype == torch.float32, "unit records carry float32 money: obs_dtype must be float32"
+        assert (isinstance(bids_host, torch.Tensor) and bids_host.is_pinned() and bids_host.is_contiguous()
+                and bids_host.dtype in (torch.float32, torch.float64) and tuple(bids_host.shape) == (E, K)), \
+            "step_host_records takes a pinned, contiguous float [E, K] tensor"
+        if getattr(self, "_rec_host", None) is None:
+            rec = torch.zeros(E, K, 16, dtype=torch.uint8).pin_memory()
+            env = torch.zeros(E, 24, dtype=torch.uint8).pin_memory()  # reward f64 | cum_profit f64 | days i32 | term u8 | trunc u8 | pad
+            envT = torch.zeros(24 * E, dtype=torch.uint8).pin_memory()
+            u16, f32 = rec.view(torch.uint16), rec.view(torch.float32)
+            scal = dict(reward=envT[0:8 * E].view(torch.float64), cumulative_profit=envT[8 * E:16 * E].view(torch.float64),
+                        days_passed=envT[16 * E:20 * E].view(torch.int32), terminated=envT[20 * E:21 * E],
+                        truncated=envT[21 * E:22 * E])
+            self._rec_host, self._rec_env = rec, envT
+            self._rec_ptrs = tuple(scal[k].data_ptr() for k in
+                                   ("reward", "cumulative_profit", "days_passed", "terminated", "truncated"))
+            self._rec_views = dict(
+                impressions=u16[:, :, 0], buyside_clicks=u16[:, :, 1], sellside_conversions=u16[:, :, 2],
+                count_overflow=u16[:, :, 3], cost=f32[:, :, 2], revenue=f32[:, :, 3],
+                reward=scal["reward"], cumulative_profit=scal["cumulative_profit"].view(-1, 1),
+                days_passed=scal["days_passed"].view(-1, 1), terminated=scal["terminated"], truncated=scal["truncated"])
+            del env
+        budget = None
+        if budget_host is not None:
+            budget = self._stage(budget_host.to(bids_host.dtype), self._budget_dev, (E,))
+        a = self._fill_args(bids_host, budget, False)
+        out = a.out
+        saved = (out.reward, out.obs_cum_profit, out.obs_days, out.terminated, out.truncated)
+        (out.reward, out.obs_cum_profit, out.obs_days, out.terminated, out.truncated) = self._rec_ptrs
+        out.unit_records = self._rec_host.data_ptr()
+        stream = torch.cuda.current_stream(self.device)
+        try:
+            self._call(self._lib.adc_step_philox, C.byref(a), C.c_void_p(stream.cuda_stream))
+        finally:
+            (out.reward, out.obs_cum_profit, out.obs_days, out.terminated, out.truncated) = saved
+            out.unit_records = None
+        self._step_count += 1
+        self._calls += 1
+        stream.synchronize()
+        return self._rec_views
+
     def step_host_pipelined(self, bids_host: torch.Tensor, n_chunks: int = 4):
         """``step`` for a CPU-side caller: pinned float32 HOST bids in, HOST observations out, through
         ``adc_step_host``: the envs are cut into ``n_chunks`` runs and every run's host->device copy,
@@ -717,14 +768,18 @@ class VectorBiddingSimulation:
         the first and the last, as in round 1):
 
         * ``"zero_copy"``  the kernels read the bids from the pinned host buffer and write every
-          observation array (int32 counts, float money) into a pinned host block (UVA): the fastest
-          form for ONE process per host (B200: 1.69e9 units/s on C2);
+          observation array (int32 counts, float money) into a pinned host block (UVA), 20 bytes per
+          unit in five 4-byte streams (B200: 1.65e9 units/s on C2);
         * ``"pipelined"``  ``step_host_pipelined``: chunks of envs on their own streams, copy engines,
           compact rows (uint16 counts): a third fewer bytes and far fewer transactions through the
           host memory system -- the fastest form when SEVERAL ranks share one host (8 x B200: 8.0e9
           units/s, 96 % of what 8 concurrent cudaMemcpyAsync streams of the same rows reach);
         * ``"rows"``       ``step_host_rows``: compact rows written by the kernels over UVA;
-        * ``"auto"``       "pipelined" when torch.distributed runs more than one rank, else "zero_copy";
+        * ``"records"``    ``step_host_records``: one aligned 16-byte record per unit written by the
+          kernels over UVA (float32 observations only): the fastest form for ONE process per host
+          (B200: 1.91e9 units/s on C2, 88 % of the device-timed rate);
+        * ``"auto"``       "pipelined" when torch.distributed runs more than one rank, else "records"
+          ("zero_copy" for float64 observations);
         * ``"staged"``     one H2D copy, the step, one D2H copy of the contiguous int32 block.
 
         Returns a dict of pinned host tensors (views; valid until the next call).  The compact forms
@@ -732,7 +787,9 @@ class VectorBiddingSimulation:
         if mode == "auto":
             import torch.distributed as dist
             shared = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-            mode = "pipelined" if shared else "zero_copy"
+            mode = "pipelined" if shared else ("records" if self.obs_dtype == torch.float32 else "zero_copy")
+        if mode == "records":
+            return self.step_host_records(bids_host, budget_host)
         if mode in ("pipelined", "rows") and budget_host is None and self.kind == kwmod.IMPLICIT:
             return self.step_host_pipelined(bids_host) if mode == "pipelined" else self.step_host_rows(bids_host)
         if mode is not None:
@@ -795,6 +852,11 @@ class VectorBiddingSimulation:
         E, K = self.num_envs, self.num_keywords
         fb = 8 if self.obs_dtype == torch.float64 else 4
         return E * K * 4, self._block_bytes
+
+    def host_record_bytes_per_step(self):
+        """(h2d, d2h) bytes moved by step_host(mode="records") for this shape."""
+        E, K = self.num_envs, self.num_keywords
+        return E * K * 4, E * K * 16 + E * 22
 
     # ------------------------------------------------------------------ misc reference API
     def render(self) -> Optional[str]:

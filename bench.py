@@ -531,10 +531,11 @@ def run_gpu(args):
         return units_total / float(te.item())
 
     e2e_value = timed_host(lambda: env.step_host(bids_host, mode="auto"))
-    auto_mode = "pipelined" if world > 1 else "zero_copy"
+    auto_mode = "pipelined" if world > 1 else "records"
     h2d = E_ENVS * K_KW * 4
-    d2h = (E_ENVS * int(_capi.load().adc_host_row_bytes(K_KW, _capi.F32)) if world > 1 else env.host_bytes_per_step()[1])
+    d2h = (E_ENVS * int(_capi.load().adc_host_row_bytes(K_KW, _capi.F32)) if world > 1 else env.host_record_bytes_per_step()[1])
     e2e_rows = timed_host(lambda: env.step_host_rows(bids_host))
+    e2e_records = timed_host(lambda: env.step_host_records(bids_host))
     e2e_pipelined = timed_host(lambda: env.step_host_pipelined(bids_host, n_chunks=args.host_chunks))
     e2e_zero_copy = timed_host(lambda: env.step_host(bids_host))
     e2e_staged = timed_host(lambda: env.step_host(bids_host, zero_copy=False))
@@ -587,13 +588,15 @@ def run_gpu(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "how": f"VectorBiddingSimulation.step_host(pinned bids, mode='auto') = '{auto_mode}' at {n_gpus} rank(s) per "
-                       "host.  zero_copy: one launch reads the pinned float32 bids and writes the int32 / float32 "
-                       "observation arrays straight into pinned host memory (UVA), 20 B per unit; pipelined "
+                       "host.  records: one launch reads the pinned float32 bids over UVA and writes every unit's observation "
+                       "as one aligned 16-byte record (uint16 counts + float32 money) plus the env scalars straight "
+                       "into pinned host memory; zero_copy: the same with the five int32 / float32 arrays, 20 B per unit; pipelined "
                        "(adc_step_host): chunks of envs on their own streams, cudaMemcpyAsync in, kernels, compact rows "
                        "(uint16 counts + float32 money, 14 B per unit), cudaMemcpyAsync out.  Either way the call "
                        "returns when the observations are in host memory",
                 "other_paths": {f"pipelined_adc_step_host_{args.host_chunks}_chunks": e2e_pipelined,
-                                "rows_written_over_uva": e2e_rows, "zero_copy_uva_int32_arrays": e2e_zero_copy,
+                                "rows_written_over_uva": e2e_rows, "unit_records_over_uva": e2e_records,
+                                "zero_copy_uva_int32_arrays": e2e_zero_copy,
                                 "staged_single_copy_int32": e2e_staged},
                 "host_ceiling": "tools/host_ceiling.py, 8 ranks of plain cudaMemcpyAsync on one box: 101 GB/s aggregate "
                                 "for 8.2 MB int32 blocks (5.05e9 units/s), 138 GB/s for compact rows + bids (7.55e9): the "

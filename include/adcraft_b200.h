@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define ADC_ABI_VERSION 5
+#define ADC_ABI_VERSION 6
 #define ADC_SUBSTEPS 24 /* adcraft/bidding_simulation.py:213 */
 
 typedef enum adc_status {
@@ -133,7 +133,22 @@ typedef struct adc_step_out {
                                  gymnasium_kw_utils.py:383-390): buyside_clicks[0:K] | cost[K:2K] |
                                  cumulative_profit | days_passed | impressions | revenue |
                                  sellside_conversions -- written by the kernels, no gather pass */
+    void *unit_records;       /* optional [E,K] adc_unit_record (16 bytes per unit): the unit's whole
+                                 observation in ONE aligned 16-byte store, 512 contiguous bytes per warp.
+                                 Meant to be HOST memory mapped into the device address space (pinned,
+                                 UVA): with reward / obs_cum_profit / obs_days / terminated / truncated
+                                 pointing at host memory as well, the step delivers its observations over
+                                 PCIe while it runs -- 16 bytes per unit in full-size write transactions
+                                 instead of 20 in five 4-byte streams -- and the int32 / float arrays above
+                                 stay in device memory.  Needs float_dtype ADC_F32 */
 } adc_step_out;
+
+/* One unit of adc_step_out.unit_records (little endian).  A count above 65535 is stored as 65535 with
+ * bit 0 of `flags` set (the device arrays keep the exact int32 values). */
+typedef struct adc_unit_record {
+    uint16_t impressions, clicks, conversions, flags;
+    float cost, revenue;
+} adc_unit_record;
 
 /* Scratch the step needs (caller-owned so that nothing is allocated per call). */
 typedef struct adc_scratch {

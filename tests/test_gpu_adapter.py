@@ -175,15 +175,17 @@ def test_step_host_pipelined_equals_device_step(K, E, budget, chunks, drift):
     table = kwm.sample_implicit_keywords_from_quantiles(K, rng, {"mean_volume": 64, "conversion_rate": 0.8})
     mk = lambda: VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=budget, device="cuda", seed=4,
                                          max_days=3, updater_mask=[True] * K if drift else None)
-    a, b, c = mk(), mk(), mk()
-    a.reset(); b.reset(); c.reset()
+    a, b, c, d = mk(), mk(), mk(), mk()
+    a.reset(); b.reset(); c.reset(); d.reset()
     for step in range(5):
         bids = torch.from_numpy(np.round(rng.uniform(0.2, 1.5, (E, K)), 2).astype(np.float32)).pin_memory()
         h = a.step_host_pipelined(bids, n_chunks=chunks)
         # the fused form: rows packed by the kernels straight into pinned host memory (adc_step_out.rows)
         hr = c.step_host_rows(bids)
+        # ... and one aligned 16-byte record per unit (adc_step_out.unit_records)
+        hu = d.step_host(bids, mode="records")
         obs, reward, term, trunc, _ = b.step({"keyword_bids": bids.cuda()})
-        for hh in (h, hr):
+        for hh in (h, hr, hu):
             for k in ("impressions", "buyside_clicks", "sellside_conversions"):
                 assert torch.equal(hh[k].to(torch.int32), obs[k].cpu()), (k, step)
             for k in ("cost", "revenue"):
@@ -195,10 +197,55 @@ def test_step_host_pipelined_equals_device_step(K, E, budget, chunks, drift):
             assert int(hh["count_overflow"].sum()) == 0
         # the device-side observation of the pipelined env is up to date as well
         assert torch.equal(a._out["impressions"], obs["impressions"])
+        assert torch.equal(d._out["impressions"], obs["impressions"]) and torch.equal(d._out["cost"], obs["cost"])
     assert int(h["impressions"].to(torch.int64).sum()) > 0
     if drift:
         pa, pb = a.keyword_params(), b.keyword_params()
         assert all(np.array_equal(pa[n], pb[n]) for n in ("vol_mean", "ctr", "cvr"))
+
+
+def test_unit_records_other_kernel_families_and_count_overflow():
+    """adc_step_out.unit_records beyond the free-running implicit kernels: explicit keywords get their
+    records from the packing pass over the finished step; a count above 65535 (a day of 70 000
+    auctions, walked by the exact serial kernel) is stored as 65535 with the record's flag set while the
+    device arrays keep the exact value; a per-env budget tensor goes through the same call."""
+    from adcraft_b200 import keywords as kwm
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    E, K = 37, 10
+    table = kwm.sample_random_keywords(K, np.random.default_rng(0))
+    mk = lambda: VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=1000.0, device="cuda", seed=2)
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    rng = np.random.default_rng(1)
+    for step in range(3):
+        bids = torch.from_numpy(np.round(rng.uniform(0.01, 3.0, (E, K)), 2).astype(np.float32)).pin_memory()
+        budget = torch.from_numpy(rng.uniform(5.0, 2000.0, E).astype(np.float32)).pin_memory()
+        h = a.step_host(bids, budget, mode="records")
+        obs, reward, term, trunc, _ = b.step({"keyword_bids": bids.cuda(), "budget": budget.cuda()})
+        for k in ("impressions", "buyside_clicks", "sellside_conversions"):
+            assert torch.equal(h[k].to(torch.int32), obs[k].cpu()), (k, step)
+        for k in ("cost", "revenue"):
+            assert torch.equal(h[k], obs[k].cpu()), (k, step)
+        assert torch.equal(h["reward"], reward.cpu()) and int(h["count_overflow"].sum()) == 0
+    assert int(h["buyside_clicks"].to(torch.int64).sum()) > 0
+    # counts beyond uint16
+    K2, E2 = 3, 4
+    big = kwm.sample_implicit_keywords_from_quantiles(K2, np.random.default_rng(2), {"mean_volume": 64, "conversion_rate": 0.8})
+    big.vol_mean[:] = [70000.0, 100.0, 66000.0]
+    big.vol_std[:] = 0.0
+    mk2 = lambda: VectorBiddingSimulation(E2, num_keywords=K2, keywords=big, budget=1e9, device="cuda", seed=5)
+    a, b = mk2(), mk2()
+    a.reset(); b.reset()
+    bids = torch.full((E2, K2), 50.0, dtype=torch.float32).pin_memory()
+    h = a.step_host(bids, mode="records")
+    obs = b.step({"keyword_bids": bids.cuda()})[0]
+    imp = obs["impressions"].cpu()
+    assert int(imp[:, 0].min()) > 65535 and int(imp[:, 1].max()) <= 65535
+    assert torch.equal(h["impressions"].to(torch.int32), imp.clamp(max=65535))
+    assert torch.equal(h["count_overflow"].bool(), (imp > 65535) | (obs["buyside_clicks"].cpu() > 65535)
+                       | (obs["sellside_conversions"].cpu() > 65535))
+    assert torch.equal(a._out["impressions"], obs["impressions"])
+    assert torch.equal(h["cost"], obs["cost"].cpu())
 
 
 def test_device_side_explicit_keyword_sampling_matches_host_distributions():
