@@ -2291,6 +2291,25 @@ __host__ __device__ inline int64_t slab_fixed_bytes_of(int K)
     return slab_bytes_of(K) - slab_kp(K) * kPoolPerUnit * 4;
 }
 
+// The bits of x at the set positions of m, packed towards bit 0 (parallel suffix compress, Hacker's
+// Delight 7-4): bit r of the result = x at the r-th set bit of m.
+__device__ __forceinline__ uint32_t compress32(uint32_t x, uint32_t m)
+{
+    x &= m;
+    uint32_t mk = ~m << 1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        uint32_t mp = mk ^ (mk << 1);
+        mp ^= mp << 2; mp ^= mp << 4; mp ^= mp << 8; mp ^= mp << 16;
+        const uint32_t mv = mp & m;
+        m = (m ^ mv) | (mv >> (1 << i));
+        const uint32_t t = x & mv;
+        x = (x ^ t) | (t >> (1 << i));
+        mk &= ~mp;
+    }
+    return x;
+}
+
 // A (sub-step, keyword) lane the slab cannot describe: walked again with the budget by lane_walk.  Out
 // of line: its registers stay out of the scan loop.
 struct DirectOut {
@@ -2457,13 +2476,22 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                     const uint32_t active = rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? (1u << rem) - 1u : 0u);
                     const Masks3 m = group_masks(active, (uint32_t)g, u2.t1, u2.t2, u2.t3, u2.full, pa.n0, pa.n1,
                                                  pa.x3, k0, k1);
-                    // conversion flags by click rank
-                    uint32_t cv = m.conv;
-                    while (cv) {
-                        const int bpos = __ffs(cv) - 1;
-                        cv &= cv - 1;
-                        const int r = baseC + __popc(m.click & ((1u << bpos) - 1u));
-                        if (r < kUnitSlots) s_cv[(r >> 5) * 32 + lane] |= 1u << (r & 31);
+                    // conversion flags by click rank, appended to the lane's bitmap at its running click count:
+                    // the group's conversion bits compressed onto its click bits (a fixed ~80 instructions) when
+                    // the slowest lane has many conversions, a loop over them when all have few (sparse keywords)
+                    if (__reduce_max_sync(FULL, (unsigned)__popc(m.conv)) > 7u) {
+                        const uint32_t cb = compress32(m.conv, m.click);
+                        const int w0 = baseC >> 5, sh = baseC & 31;
+                        if (w0 < kUnitSlots / 32) s_cv[w0 * 32 + lane] |= cb << sh;
+                        if (sh != 0 && w0 + 1 < kUnitSlots / 32) s_cv[(w0 + 1) * 32 + lane] |= cb >> (32 - sh);
+                    } else {
+                        uint32_t cv = m.conv;
+                        while (cv) {
+                            const int bpos = __ffs(cv) - 1;
+                            cv &= cv - 1;
+                            const int r = baseC + __popc(m.click & ((1u << bpos) - 1u));
+                            if (r < kUnitSlots) s_cv[(r >> 5) * 32 + lane] |= 1u << (r & 31);
+                        }
                     }
                     // the sub-steps that end inside this group: one header each
                     const int hi = min(32 * g + 32, V);
