@@ -994,8 +994,12 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
                 rev_sd = (float)a.kw.rev_std[pi];
             }
         }
-        // ---------------- outcomes: groups of 32 auctions, lane <-> unit ----------------
         int I = 0, B = 0, S = 0;
+        long long cost = 0, rev = 0;
+        // shared auctions: a batch in which every unit is outbid (7 of the 8 bidder rows of an 8-bidder world)
+        // has no auction to evaluate and goes straight to its outputs
+        if (!kFloor || __any_sync(FULL, V > 0)) {
+        // ---------------- outcomes: groups of 32 auctions, lane <-> unit ----------------
         {
             const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), genv, k0, k1);
             const int G = (V + 31) >> 5;
@@ -1019,7 +1023,6 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
             costs[lane] = fc;
             s_sum[warp][lane][0] = 0u; s_sum[warp][lane][1] = 0u;
         }
-        long long cost = 0;
         {
             const FlatMap fm = flat_map_begin((B + 3) >> 2, lane, start, nzl);
             const int TB = fm.total;
@@ -1081,7 +1084,8 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
             }
         }
         __syncwarp();
-        const long long rev = (long long)s_sum[warp][lane][0] + ((long long)s_sum[warp][lane][1] << 24);
+        rev = (long long)s_sum[warp][lane][0] + ((long long)s_sum[warp][lane][1] << 24);
+        }
 
         // ---------------- outputs (coalesced: 32 consecutive units), env completion ----------------
         int safe = 0;
