@@ -2517,8 +2517,8 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                 // a unit with more clicked slots than the slab describes: every lane is walked by lane_walk
                 if (baseC > kUnitSlots) whole_direct = true;
                 if (short_day) s_hdr[lane] = (uint32_t)baseC | ((uint32_t)baseI << 6);  // < 24 auctions: the counts fit
-                else
-                    for (; t < ADC_SUBSTEPS; ++t) s_hdr[t * 32 + lane] = 0u;
+                else  // (empty sub-steps after the day's last auction still carry the running first-slot field)
+                    for (; t < ADC_SUBSTEPS; ++t) s_hdr[t * 32 + lane] = (uint32_t)min(lastC, kUnitSlots) << 12;
             }
             int B = whole_direct ? 0 : baseC;
             if (act) acc4[k] = make_uint4((uint32_t)baseI, 0u, 0u, 0u);  // the day's impressions | clicks, conversions, cents paid
@@ -2537,7 +2537,8 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
                         const uint32_t h = s_hdr[t * 32 + lane];
                         hdr[(uint32_t)t * Kp32 + (uint32_t)k] = whole_direct ? kHdrDirect : ((h & 63u) == kHdrDirect ? h : h + add);
                     }
-                    for (int t = rows; t < ADC_SUBSTEPS; ++t) hdr[(uint32_t)t * Kp32 + (uint32_t)k] = whole_direct ? kHdrDirect : 0u;
+                    for (int t = rows; t < ADC_SUBSTEPS; ++t)
+                        hdr[(uint32_t)t * Kp32 + (uint32_t)k] = whole_direct ? kHdrDirect : (uint32_t)(off + B) << 12;
                 }
                 const PhiloxPre pc = philox_pre(a.step, stream_word(ST_COST, 0u, (uint32_t)k), src.env, k0, k1);
                 FlatCost fc;
@@ -2608,6 +2609,73 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
         // worth a visit is the first whose value `remaining` still covers.  An env with lane_walk lanes
         // visits every round (their headers track the walk); a budget <= 0 gets its one look at round 0.
         int round = 0;
+        // ---- phase 1a: the affordable prefix.  While `remaining` exceeds a round's total spend (exact cents)
+        // by more than a cent no `budget >= cost` test of the round can fail: every click is accepted and the
+        // walk is `remaining -= lane_sum` lane after lane (bsim:225 + rust sum_list).  Such a round needs
+        // nothing but its lanes' own sequential f64 sums: header -> slots -> sums -> the 32-step chain, the next
+        // round's headers already on their way; no accumulator, no index, no scan.  The first round that
+        // cannot be proven affordable hands over to the general walk below; what the prefix accepted is
+        // recounted at the commit from the keywords' slots.  (Alias rule, lane_walk lanes: general walk.)
+        int n_prefix = 0;  // rounds [0, n_prefix) were accepted whole
+        if (!env_direct && !a.budget_alias && remaining > 0) {
+            bool go = true;
+            // the headers of a round (this lane's keyword of its chunk) and the chunk's pool base
+            auto header_of = [&](int rd, uint32_t &cbase) -> uint32_t {
+                const int t_cur = __float2int_rd(__fdividef((float)rd + 0.5f, (float)n_chunks));
+                const uint32_t c_cur = (uint32_t)(rd - t_cur * n_chunks) << 5;
+                cbase = c_cur * ppu;
+                return c_cur + (uint32_t)lane < (uint32_t)K ? hdr[(uint32_t)t_cur * Kp32 + c_cur + (uint32_t)lane] : 0u;
+            };
+            for (int blk = 0; blk < n_rounds && go; blk += 32) {
+                const int r = blk + lane;
+                unsigned has = __ballot_sync(FULL, r < n_rounds && rmin[r] != 0xFFFFFFFFu);  // rounds with clicked slots
+                n_prefix = min(blk + 32, n_rounds);
+                uint32_t cbase = 0u, h = 0u;
+                if (has) h = header_of(blk + __ffs(has) - 1, cbase);
+                while (has) {
+                    const int rd = blk + __ffs(has) - 1;
+                    has &= has - 1;
+                    const int cc = (int)(h & 63u);
+                    const uint32_t *const sp = pool + cbase + (h >> 12);
+                    uint32_t ncbase = 0u, nh = 0u;  // the next round's headers are on their way during this round
+                    if (has) nh = header_of(blk + __ffs(has) - 1, ncbase);
+                    double ls = 0.0;
+                    unsigned cents = 0u;
+                    const int mcc = (int)__reduce_max_sync(FULL, (unsigned)cc);
+                    for (int i0 = 0; i0 < mcc; i0 += kSerRegs) {  // kSerRegs independent loads, then the ordered sum
+                        uint32_t w[kSerRegs];
+#pragma unroll
+                        for (int i = 0; i < kSerRegs; ++i) w[i] = i0 + i < cc ? sp[i0 + i] : 0u;
+#pragma unroll
+                        for (int i = 0; i < kSerRegs; ++i) {
+                            if (i0 + i < cc) {
+                                const unsigned c = w[i] & 0x7FFFFFFFu;
+                                ls = __dadd_rn(ls, cents32_to_dollars((int)c));
+                                cents += c;
+                            }
+                        }
+                    }
+                    const unsigned total = __reduce_add_sync(FULL, cents);  // <= 32 lanes x 61 x 65535 < 2^31
+                    const double spend = cents32_to_dollars((int)total);
+                    if (!(remaining > spend + 0.01)) {
+                        go = false;
+                        n_prefix = rd;
+                        break;
+                    }
+                    s_lsum[warp][lane] = ls;
+                    __syncwarp();
+#pragma unroll
+                    for (int l = 0; l < 32; l += 2) {
+                        const double2 v = *reinterpret_cast<const double2 *>(&s_lsum[warp][l]);
+                        remaining = __dsub_rn(__dsub_rn(remaining, v.x), v.y);
+                    }
+                    __syncwarp();
+                    h = nh;
+                    cbase = ncbase;
+                }
+            }
+            round = n_prefix;
+        }
         uint32_t rm = 0u;  // this lane's round of the current block of 32
         int rm_block = -1;
         while (round < n_rounds && !stop) {
@@ -2828,6 +2896,28 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
             const uint4 a4 = acc4[k];
             int I = (int)(a4.x & 0x7FFFFFFFu), B = (int)a4.y, S = (int)a4.z;
             long long cost_c = a4.w, rev_c = 0;
+            if (n_prefix > 0) {
+                // the keyword's sub-steps inside the affordable prefix: every clicked slot was accepted -- its
+                // first t_k sub-steps' slots are one contiguous run of the chunk's pool
+                const int t_full = __float2int_rd(__fdividef((float)n_prefix + 0.5f, (float)n_chunks));
+                const int t_k = t_full + ((k >> 5) < n_prefix - t_full * n_chunks ? 1 : 0);
+                if (t_k > 0) {
+                    const uint32_t first = hdr[(uint32_t)k] >> 12;  // sub-step 0: the keyword's first slot
+                    // (every header's slot field is the keyword's running slot count, empty sub-steps included)
+                    const uint32_t hl = hdr[(uint32_t)(t_k - 1) * Kp32 + (uint32_t)k];
+                    const uint32_t n = (hl >> 12) + (hl & 63u) - first;
+                    const uint32_t *const sp = pool + (uint32_t)(k & ~31) * ppu + first;
+                    unsigned cents = 0u, convs = 0u;
+                    for (uint32_t i = 0; i < n; ++i) {
+                        const uint32_t w = sp[i];
+                        cents += w & 0x7FFFFFFFu;
+                        convs += w >> 31;
+                    }
+                    B += (int)n;
+                    S += (int)convs;
+                    cost_c += cents;
+                }
+            }
             if (!(a4.x >> 31)) {
                 if (stop) {  // the lanes after the early break never ran: only the others' impressions count
                     I = 0;
