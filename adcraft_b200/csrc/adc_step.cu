@@ -1607,7 +1607,7 @@ adc_replay_implicit_kernel(const __grid_constant__ adc_step_args a, const __grid
 // outside the 16-bit fast-path range are walked by pk_walk_generic (64-bit sums, any address
 // space); malformed records flag an overrun, which routes the env to the serial kernel (CSR tape).
 // ------------------------------------------------------------------------------------------
-constexpr int kPkMaxCap = 8192;  // largest ring instantiated (bounds the 32-bit fast-path sums)
+constexpr int kPkMaxCap = 7936;  // largest ring that may be instantiated: bounds the 32-bit fast-path sums (see pk_walk_fast)
 
 struct __align__(16) PkUnit {  // 48 B per unit in shared memory
     const unsigned char *src;  // the record in global memory
@@ -1631,10 +1631,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 
 // The tape streams through once per step: evict-first keeps it from displacing the outputs and the
 // per-env accumulators in L2.
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+__device__ __forceinline__ unsigned long long evict_first_policy()
 {
     unsigned long long policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, unsigned long long policy)
+{
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
@@ -1743,87 +1748,109 @@ __device__ __noinline__ PkResult pk_walk_generic(const unsigned char *rec, int b
     return r;
 }
 
-// Record resident in shared memory, bid <= kMaxFlatBidCents: 32-bit address and sum arithmetic,
-// REDUX reductions.  Returns false when the record needs pk_walk_generic instead: a negative
-// competitor bid or a revenue >= 65536 cents (the 32-bit sums are exact only for 16-bit values:
-// a lane adds at most kPkMaxCap/4/32 = 64 of them), or click uniforms running out mid-walk.
-__device__ __forceinline__ bool pk_walk_fast(const unsigned char *rec, int n_comp, int n_click, int n_conv, int n_rev,
+// Shared-memory loads by 32-bit shared-space address.  (Through generic pointers the compiler
+// re-derives the CTA's shared window base -- SR_CgaCtaId, two adds, a LEA -- next to every predicated
+// load of the walk: a fifth of its instructions.)
+__device__ __forceinline__ int4 lds_v4(uint32_t a)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// Record resident in shared memory (`rec`: its shared-space address), bid <= kMaxFlatBidCents, header flag
+// ADC_PACKED_NARROW (no negative competitor bid, revenues below 65536 cents: checked by the caller): 32-bit
+// address and sum arithmetic, REDUX reductions.  Returns false when the record needs pk_walk_generic
+// instead: click uniforms running out mid-walk.  The 32-bit sums are exact: a record of at most kPkMaxCap
+// bytes holds at most 1976 bids = 15 full trips and 2 single ones, so a lane adds at most 62 16-bit values below
+// its click counter at bit 22.  No load is conditional: a lane without a bid or a won auction
+// reads the record's first bytes instead and ignores them.
+__device__ __forceinline__ bool pk_walk_fast(uint32_t rec, int n_comp, int n_click, int n_conv, int n_rev,
                                              int bid_cents, double ctr, double cvr, int lane, unsigned lt, PkResult &r)
 {
     const unsigned FULL = 0xFFFFFFFFu;
     // the header was validated by the unit's owner lane (pk_header_ok): all counts < 2048 and
     // consistent with the record size, n_comp == V
     r.overrun = false;
-    const int4 *comp = reinterpret_cast<const int4 *>(rec + 32);
-    const double *click = reinterpret_cast<const double *>(rec + 32 + ((n_comp + 3) & ~3) * 4);
-    const double *conv = click + n_click;
-    const int *rev = reinterpret_cast<const int *>(conv + n_conv);
+    const int n4 = (n_comp + 3) >> 2;  // int4 groups; padding entries are INT32_MAX and never win
+    const uint32_t click = rec + 32u + 16u * (uint32_t)n4;
+    const uint32_t conv = click + 8u * (uint32_t)n_click, rev = conv + 8u * (uint32_t)n_conv;
     constexpr unsigned kOne = 1u << 22;  // click counter above the lane's cost sum (< 64 * 65536)
     int nI = 0;
-    unsigned acc = 0, wild = 0;
-    const int n4 = (n_comp + 3) >> 2;  // int4 groups; padding entries are INT32_MAX and never win
-    int4 c = make_int4(0, 0, 0, 0);
-    int g0 = 0;
+    unsigned acc = 0;
     // full trips: 128 auctions, four consecutive ones per lane (one 128-bit load)
+    uint32_t cp = rec + 32u + 16u * (uint32_t)lane;
+    int left = n4 - lane;  // > 0: the lane has bids in the trip
+    int g0 = 0;
     for (; n4 - g0 > 16; g0 += 32) {
-        const int g = g0 + lane;
-        const bool in = g < n4;
-        if (in) c = comp[g];
+        const bool in = left > 0;
+        const int4 c = lds_v4(in ? cp : rec);
         const bool w0 = in && bid_cents > c.x, w1 = in && bid_cents > c.y;
         const bool w2 = in && bid_cents > c.z, w3 = in && bid_cents > c.w;
         const unsigned m0 = __ballot_sync(FULL, w0), m1 = __ballot_sync(FULL, w1);
         const unsigned m2 = __ballot_sync(FULL, w2), m3 = __ballot_sync(FULL, w3);
-        // auction order inside the trip is lane-major (j = 4 g + q): rank = wins of lower lanes + own earlier wins
-        const int r0 = nI + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
-        const int r1 = r0 + w0, r2 = r1 + w1, r3 = r2 + w2;
+        // auction order inside the trip is lane-major (j = 4 g + q): rank = wins of lower lanes + own earlier wins;
+        // the click uniforms of a lane's wins are consecutive
+        // (a tape shorter than the walk -- never on a consistent recording -- is noticed after the loops: the
+        // index is clamped so that the loads stay within 32 bytes of the record, which the launch pads for)
+        const uint32_t u0 = click + 8u * (uint32_t)min(nI + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt), n_click);
+        const uint32_t u1 = u0 + (w0 ? 8u : 0u), u2 = u1 + (w1 ? 8u : 0u), u3 = u2 + (w2 ? 8u : 0u);
         nI += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-        if (nI > n_click) return false;  // tape shorter than the walk: never on a consistent recording
-        if (in) wild |= (unsigned)(c.x | c.y | c.z | c.w);  // sign bit = a negative competitor bid
-        const bool k0 = w0 && click[r0] <= ctr;
-        const bool k1 = w1 && click[r1] <= ctr;
-        const bool k2 = w2 && click[r2] <= ctr;
-        const bool k3 = w3 && click[r3] <= ctr;
+        const bool k0 = w0 & (lds_f64(w0 ? u0 : rec) <= ctr);
+        const bool k1 = w1 & (lds_f64(w1 ? u1 : rec) <= ctr);
+        const bool k2 = w2 & (lds_f64(w2 ? u2 : rec) <= ctr);
+        const bool k3 = w3 & (lds_f64(w3 ? u3 : rec) <= ctr);
         acc += (k0 ? (unsigned)c.x + kOne : 0u) + (k1 ? (unsigned)c.y + kOne : 0u);
         acc += (k2 ? (unsigned)c.z + kOne : 0u) + (k3 ? (unsigned)c.w + kOne : 0u);
+        cp += 512u;
+        left -= 32;
     }
     // the last <= 64 auctions: one per lane and trip (a volume just above 128 would otherwise pay a
     // whole 128-wide trip for a handful of auctions)
-    const int *comp1 = reinterpret_cast<const int *>(comp);
     for (int j0 = 4 * g0; j0 < n_comp; j0 += 32) {
         const int j = j0 + lane;
         const bool in = j < n_comp;
-        int c1 = 0;
-        if (in) c1 = comp1[j];
+        const int c1 = lds_s32(in ? rec + 32u + 4u * (uint32_t)j : rec);
         const bool w = in && bid_cents > c1;
         const unsigned m = __ballot_sync(FULL, w);
-        const int rk = nI + __popc(m & lt);
+        const int rk = min(nI + __popc(m & lt), n_click);
         nI += __popc(m);
-        if (nI > n_click) return false;
-        wild |= (unsigned)c1;
-        const bool k = w && click[rk] <= ctr;
+        const bool k = w & (lds_f64(w ? click + 8u * (uint32_t)rk : rec) <= ctr);
         acc += k ? (unsigned)c1 + kOne : 0u;
     }
-    wild &= 0x80000000u;  // INT32_MAX padding has the other bits set
+    if (nI > n_click) return false;  // click uniforms ran out: pk_walk_generic decides
     r.I = nI;
     r.B = (int)__reduce_add_sync(FULL, acc >> 22);
     r.overrun = r.overrun || r.B > n_conv;
     const int nB = min(r.B, n_conv);
-    unsigned Sl = 0;
-    if (lane < nB) Sl += conv[lane] <= cvr;
-    if (lane + 32 < nB) Sl += conv[lane + 32] <= cvr;
+    // (two per lane without a loop: a day of more than 64 accepted clicks is the exception)
+    unsigned Sl = (unsigned)((lane < nB) & (lds_f64(lane < nB ? conv + 8u * (uint32_t)lane : rec) <= cvr)) +
+                  (unsigned)((lane + 32 < nB) & (lds_f64(lane + 32 < nB ? conv + 8u * (uint32_t)(lane + 32) : rec) <= cvr));
     if (nB > 64) {
-        for (int i = lane + 64; i < nB; i += 32) Sl += conv[i] <= cvr;
+#pragma unroll 1
+        for (int i = lane + 64; i < nB; i += 32) Sl += lds_f64(conv + 8u * (uint32_t)i) <= cvr;
     }
     r.S = (int)__reduce_add_sync(FULL, Sl);
     r.overrun = r.overrun || r.S > n_rev;
     const int nS = min(r.S, n_rev);
-    unsigned revl = 0;
-    if (lane < nS) { const unsigned x = (unsigned)rev[lane]; revl += x; wild |= x; }
-    if (lane + 32 < nS) { const unsigned x = (unsigned)rev[lane + 32]; revl += x; wild |= x; }
+    unsigned revl = (lane < nS ? (unsigned)lds_s32(rev + 4u * (uint32_t)lane) : 0u) +
+                    (lane + 32 < nS ? (unsigned)lds_s32(rev + 4u * (uint32_t)(lane + 32)) : 0u);
     if (nS > 64) {
-        for (int i = lane + 64; i < nS; i += 32) { const unsigned x = (unsigned)rev[i]; revl += x; wild |= x; }
+#pragma unroll 1
+        for (int i = lane + 64; i < nS; i += 32) revl += (unsigned)lds_s32(rev + 4u * (uint32_t)i);
     }
-    if (__any_sync(FULL, (wild & 0xFFFF0000u) != 0)) return false;
     r.cost = (long long)__reduce_add_sync(FULL, acc & (kOne - 1u));
     r.rev = (long long)__reduce_add_sync(FULL, revl);
     return true;
@@ -1834,6 +1861,7 @@ __global__ void __launch_bounds__(kPkWarps * 32, kMinBlocks)
 adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_constant__ adc_tape t)
 {
     static_assert(kRing <= kPkMaxCap && kRing % 16 == 0, "ring size");
+    static_assert((kDepth & (kDepth - 1)) == 0, "copies in flight: a power of two");
     extern __shared__ __align__(128) unsigned char pk_buf[];  // [kPkWarps][kRing]
     __shared__ PkUnit s_unit[kPkWarps][32];
     __shared__ __align__(8) unsigned long long s_bar[kPkWarps][kDepth];
@@ -1859,8 +1887,9 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
     // Ring state, warp-uniform.  Records are placed in issue order at `head`, wrapping to 0 when the
     // next one does not fit before the end; the consumer replays the same placement rule from
     // `chead`, so no per-record bookkeeping is stored.  [chead, head) in ring order is in flight.
-    unsigned head = 0, chead = 0, used = 0, slot_i = 0, slot_c = 0, ph_c = 0;
+    unsigned head = 0, chead = 0, used = 0, n_iss = 0, n_con = 0;  // (copies issued / consumed so far)
     int in_flight = 0;
+    const unsigned long long policy = evict_first_policy();
     const unsigned lt = (1u << lane) - 1u;
 
     for (int64_t u0 = u_begin; u0 < u_end; u0 += 32) {
@@ -1887,9 +1916,12 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
             if (pu.bytes > 0 && pu.bytes <= kRing && pu.bid_cents <= kMaxFlatBidCents) {
                 // owner lane reads the record header (the bulk copy re-reads the line from L2)
                 const int4 h0 = __ldg(reinterpret_cast<const int4 *>(pu.src));
-                const int n_rev = __ldg(reinterpret_cast<const int *>(pu.src + 16));
+                const int2 h1 = __ldg(reinterpret_cast<const int2 *>(pu.src + 16));  // n_rev, flags
+                const int n_rev = h1.x;
                 if (pk_header_ok(h0, n_rev, pu.bytes)) {
-                    fast = true;
+                    // (a record without ADC_PACKED_NARROW -- negative competitor bids, revenues beyond 16 bits --
+                    // is walked by pk_walk_generic from global memory)
+                    fast = (h1.y & ADC_PACKED_NARROW) != 0;
                     pu.n_comp = h0.y; pu.n_click = h0.z; pu.n_conv = h0.w; pu.n_rev = n_rev;
                 } else {
                     my_overrun = true;  // the serial kernel re-walks the env from the CSR streams
@@ -1909,7 +1941,9 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
         if (iss_m) nx = *reinterpret_cast<const uint4 *>(&units[__ffs(iss_m) - 1]);
         auto try_issue = [&]() -> bool {
             const unsigned bytes = nx.z;
-            if (in_flight == 0) { head = 0; chead = 0; used = 0; }  // pointers coincide: restart at the ring base
+            // pointers coincide: restart at the ring base (an empty ring whose head sits behind a record's size
+            // could otherwise never take that record)
+            if (in_flight == 0) { head = 0; chead = 0; used = 0; }
             // `used` = bytes between chead and head in ring order, skipped ring ends included
             const bool straight = head + bytes <= (unsigned)kRing;
             const unsigned need = straight ? bytes : bytes + ((unsigned)kRing - head);
@@ -1918,11 +1952,11 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
             if (lane == 0) {
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(
                     ((unsigned long long)nx.y << 32) | nx.x);
-                bulk_load(ring_s + off, src, bytes, bar_s + 8u * slot_i);
+                bulk_load(ring_s + off, src, bytes, bar_s + 8u * (n_iss & (kDepth - 1)), policy);
             }
             used += need;
             head = off + bytes;
-            slot_i = slot_i + 1 == kDepth ? 0 : slot_i + 1;
+            ++n_iss;
             ++in_flight;
             iss_m &= iss_m - 1;
             if (iss_m) nx = *reinterpret_cast<const uint4 *>(&units[__ffs(iss_m) - 1]);
@@ -1938,20 +1972,19 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
             __syncwarp();  // everyone is done reading the records consumed so far
             // up to two copies per unit: a copy that did not fit last time (ring end skipped) is caught
             // up here, otherwise the lead over the walk decays to zero within a batch
-            if (iss_m && try_issue() && iss_m) try_issue();
+            if (iss_m && try_issue() && iss_m && in_flight < 3) try_issue();
             const PkUnit h = units[b];
             PkResult r;
             if ((fast_m >> b) & 1u) {
-                mbar_wait(bar_s + 8u * slot_c, ph_c);
-                if (slot_c + 1 == kDepth) { slot_c = 0; ph_c ^= 1u; } else { ++slot_c; }
+                mbar_wait(bar_s + 8u * (n_con & (kDepth - 1)), (n_con / kDepth) & 1u);  // slot and phase of the n-th copy
+                ++n_con;
                 const bool straight = chead + (unsigned)h.bytes <= (unsigned)kRing;
                 const unsigned off = straight ? chead : 0u;
                 used -= straight ? (unsigned)h.bytes : (unsigned)h.bytes + ((unsigned)kRing - chead);
                 chead = off + (unsigned)h.bytes;
                 --in_flight;
-                const unsigned char *rec = ring + off;
-                if (!pk_walk_fast(rec, h.n_comp, h.n_click, h.n_conv, h.n_rev, h.bid_cents, h.ctr, h.cvr, lane, lt, r))
-                    r = pk_walk_generic(rec, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
+                if (!pk_walk_fast(ring_s + off, h.n_comp, h.n_click, h.n_conv, h.n_rev, h.bid_cents, h.ctr, h.cvr, lane, lt, r))
+                    r = pk_walk_generic(ring + off, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
             } else {
                 r = pk_walk_generic(h.src, h.bytes, h.bid_cents, h.ctr, h.cvr, lane);
             }
@@ -3044,7 +3077,7 @@ static cudaError_t launch_packed(const adc_step_args &a, const adc_tape &tp, cud
 {
     auto kern = adc_replay_packed_kernel<W, RING, DEPTH, MINB>;
     constexpr int block = W * 32;
-    constexpr size_t dyn = (size_t)W * RING;
+    constexpr size_t dyn = (size_t)W * RING + 64;  // (+64: pk_walk_fast's clamped loads may pass a record's end by 32 bytes)
     static bool configured = false;
     if (!configured) {
         const cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -3136,7 +3169,12 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         // ring geometry: 8 warps x 6 KB per CTA, three CTAs (24 warps) per SM; measured on C2: 6 KB
         // 0.191 ms (5.75 / 6.25 / 6.5 KB: 0.194 / 0.192 / 0.190), 7 KB 0.203 ms, 5 KB with 64 registers
         // and four CTAs 0.205 ms, 8 KB (two CTAs per SM) 0.26 ms.
-        err = launch_packed<8, 6144, 4, 3>(a, tp, s, launches);
+#ifndef ADC_PK_W
+#define ADC_PK_W 8
+#define ADC_PK_RING 6144
+#define ADC_PK_MINB 3
+#endif
+        err = launch_packed<ADC_PK_W, ADC_PK_RING, 4, ADC_PK_MINB>(a, tp, s, launches);
     } else {
         auto kern = adc_replay_implicit_kernel;
         kern<<<(unsigned)grid_for(kern, kReplayWarps * 32, total), kReplayWarps * 32, 0, s>>>(a, tp);

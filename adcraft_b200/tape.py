@@ -48,7 +48,7 @@ class DeviceTape:
 
     def pack(self) -> "DeviceTape":
         """Build the packed copy of an implicit-keyword tape (include/adcraft_b200.h, `adc_tape`):
-        per unit one record  hdr[8] | comp (padded to 4 entries with INT32_MAX) | click | conv | rev
+        per unit one record  hdr[8] (V, counts, flags) | comp (padded to 4 entries with INT32_MAX) | click | conv | rev
         at a 16-byte aligned offset, so the replay kernel fetches a unit's day with one bulk copy.
         Pure tensor ops on whatever device the tape lives on; returns self."""
         if self.comp_cents is None:
@@ -96,6 +96,21 @@ class DeviceTape:
         scatter(b64, click_base, n_click, self.u_click, self.click_off[:-1])
         scatter(b64, click_base + n_click, n_conv, self.u_conv, self.conv_off[:-1])
         scatter(b32, (click_base + n_click + n_conv) * 2, n_rev, self.rev_cents, self.rev_off[:-1])
+        # flags (hdr[5]) bit 0, ADC_PACKED_NARROW: no negative competitor bid, revenues in [0, 65535]
+        def seg_extreme(vals, base, counts, reduce, init):
+            out = torch.full((U,), init, dtype=i64, device=dev)
+            total = int(counts.sum())
+            if total:
+                unit = torch.repeat_interleave(torch.arange(U, device=dev), counts)
+                k = torch.arange(total, device=dev) - (torch.cumsum(counts, 0) - counts)[unit]
+                out.scatter_reduce_(0, unit, vals[base[unit] + k].to(i64), reduce, include_self=True)
+            return out
+
+        comp_min = seg_extreme(self.comp_cents, self.comp_off[:-1], n_comp, "amin", 0)
+        rev_min = seg_extreme(self.rev_cents, self.rev_off[:-1], n_rev, "amin", 0)
+        rev_max = seg_extreme(self.rev_cents, self.rev_off[:-1], n_rev, "amax", 0)
+        narrow = (comp_min >= 0) & (rev_min >= 0) & (rev_max <= 65535)
+        b32[h + 5] = narrow[live].to(torch.int32)
         self.packed, self.packed_off = buf, off
         return self
 

@@ -252,12 +252,17 @@ typedef struct adc_step_args {
  * unit's whole day is one contiguous, 16-byte aligned block that the replay kernel fetches with a
  * single bulk copy (TMA) into shared memory.  Record of unit u = packed[packed_off[u] ..
  * packed_off[u+1]) (byte offsets, multiples of 16; an empty record means volume 0):
- *     int32  hdr[8]    = { V, n_comp, n_click, n_conv, n_rev, 0, 0, 0 }   with n_comp <= V
+ *     int32  hdr[8]    = { V, n_comp, n_click, n_conv, n_rev, flags, 0, 0 }   with n_comp <= V;
+ *                        flags bit 0 (ADC_PACKED_NARROW): no competitor bid of the record is negative and
+ *                        every revenue lies in [0, 65535] cents -- the replay kernel then walks the record
+ *                        with 32-bit sums without looking for such values; a record without the flag takes
+ *                        the generic 64-bit walk (same results)
  *     int32  comp[n_comp rounded up to a multiple of 4]   padding entries = INT32_MAX
  *     double click[n_click];  double conv[n_conv]
  *     int32  rev[n_rev]       zero padded to the next multiple of 16 bytes
  * `packed` must be 16-byte aligned.  The CSR streams stay mandatory: envs whose budget may bind and
  * records that fail validation are re-walked by the exact serial kernel from the CSR form. */
+#define ADC_PACKED_NARROW 1
 typedef struct adc_tape {
     const int32_t *volume;                              /* [E,K]                          */
     const int64_t *comp_off;  const int32_t *comp_cents;   /* implicit: one per auction      */

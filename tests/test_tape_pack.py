@@ -19,10 +19,20 @@ def _random_csr(rng, U, max_v):
         off[1:] = np.cumsum(counts)
         return torch.from_numpy(off), torch.from_numpy(gen(int(off[-1])))
 
-    comp = csr(n_comp, lambda n: rng.integers(0, 200, n).astype(np.int32))
+    def comps(n):
+        c = rng.integers(0, 200, n).astype(np.int32)
+        c[rng.random(n) < 0.01] = -5                        # a negative competitor bid: not a narrow record
+        return c
+
+    def revs(n):
+        r = rng.integers(1, 500, n).astype(np.int32)
+        r[rng.random(n) < 0.01] = 70000                     # beyond 16 bits: not a narrow record
+        return r
+
+    comp = csr(n_comp, comps)
     click = csr(n_click, lambda n: rng.random(n))
     conv = csr(n_conv, lambda n: rng.random(n))
-    rev = csr(n_rev, lambda n: rng.integers(1, 500, n).astype(np.int32))
+    rev = csr(n_rev, revs)
     return V, comp, click, conv, rev
 
 
@@ -35,6 +45,7 @@ def test_packed_records_hold_the_csr_streams():
                    conv[0], conv[1], rev[0], rev[1]).pack()
     buf, off = t.packed.numpy(), t.packed_off.numpy()
     assert off[0] == 0 and np.all(off % 16 == 0) and np.all(np.diff(off) >= 0) and off[-1] == buf.size
+    seen_flags = set()
     for u in range(E * K):
         rec = buf[off[u]:off[u + 1]]
         if V[u] == 0:
@@ -43,7 +54,11 @@ def test_packed_records_hold_the_csr_streams():
         hdr = rec[:32].view(np.int32)
         n_comp = min(V[u], comp[0][u + 1] - comp[0][u])
         lens = [int(x[0][u + 1] - x[0][u]) for x in (click, conv, rev)]
-        assert hdr.tolist() == [V[u], n_comp, *lens, 0, 0, 0]
+        cs = comp[1][comp[0][u]:comp[0][u] + n_comp].numpy()
+        rs = rev[1][rev[0][u]:rev[0][u] + lens[2]].numpy()
+        narrow = int((cs.size == 0 or cs.min() >= 0) and (rs.size == 0 or (rs.min() >= 0 and rs.max() <= 65535)))
+        assert hdr.tolist() == [V[u], n_comp, *lens, narrow, 0, 0]   # flags bit 0 = ADC_PACKED_NARROW
+        seen_flags.add(narrow)
         pad = (n_comp + 3) & ~3
         c = rec[32:32 + 4 * pad].view(np.int32)
         assert np.array_equal(c[:n_comp], comp[1][comp[0][u]:comp[0][u] + n_comp].numpy())
@@ -54,6 +69,7 @@ def test_packed_records_hold_the_csr_streams():
             assert np.array_equal(rec[p:p + w * n].view(dt), vals[o[u]:o[u] + n].numpy())
             p += w * n
         assert rec.size == (p + 15) & ~15 and not rec[p:].any()
+    assert seen_flags == {0, 1}
 
 
 def test_trimmed_cuts_streams_to_what_was_consumed():
