@@ -13,7 +13,13 @@ python tools/ncu_summary.py $O/r2_serial_b1000.ncu-rep $O/r02_serial_warp_b1000_
 cp $O/r02_flat2_c2_ncu.json profiles/r02_flat2_c2_ncu.json
 ncu -i $O/r2_flat2_c2.ncu-rep --page source --print-source cuda,sass --csv > $O/r2_flat2_src.csv 2>/dev/null
 ncu -i $O/r2_serial_b1000.ncu-rep --page source --print-source cuda,sass --csv > $O/r2_serial_src.csv 2>/dev/null
-rm -f $O/*.ncu-rep
+
 bash tools/bench_sweep.sh > $O/sweep.log 2>&1
 python bench.py --explicit --steps 20 --no-replay --no-cpu-baseline > $O/r2_bench_explicit.json 2>> $O/sweep.log
 ls $O | tail -30
+# replay (packed tape) kernel: one full capture + summary
+python bench.py --replay-only --steps 3 --warmup 3 > $O/ncu_plain_replay.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:adc_replay_packed -s 4 -c 1 -f -o $O/r2_replay_packed python bench.py --replay-only --steps 3 --warmup 3 > $O/ncu_replay.log 2>&1
+python tools/ncu_summary.py $O/r2_replay_packed.ncu-rep $O/r02_replay_packed_ncu --envs 4096 --keywords 100 --note "tape-driven step on the packed tape (bench.py --replay-only)"
+
+rm -f $O/*.ncu-rep
