@@ -1631,6 +1631,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 
 // The tape streams through once per step: evict-first keeps it from displacing the outputs and the
 // per-env accumulators in L2.
+// One lane of the (converged) warp, chosen by the hardware: unlike `lane == 0` the compiler knows that a
+// single lane is active behind it and moves a bulk copy's operands to uniform registers without a loop.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0u;
+}
+
 __device__ __forceinline__ unsigned long long evict_first_policy()
 {
     unsigned long long policy;
@@ -1949,7 +1958,7 @@ adc_replay_packed_kernel(const __grid_constant__ adc_step_args a, const __grid_c
             const unsigned need = straight ? bytes : bytes + ((unsigned)kRing - head);
             if (in_flight >= kDepth || used + need > (unsigned)kRing) return false;
             const unsigned off = straight ? head : 0u;
-            if (lane == 0) {
+            if (elect_one()) {
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(
                     ((unsigned long long)nx.y << 32) | nx.x);
                 bulk_load(ring_s + off, src, bytes, bar_s + 8u * (n_iss & (kDepth - 1)), policy);
