@@ -1785,7 +1785,8 @@ __device__ __forceinline__ int lds_s32(uint32_t a)
 // instead: click uniforms running out mid-walk.  The 32-bit sums are exact: a record of at most kPkMaxCap
 // bytes holds at most 1976 bids = 15 full trips and 2 single ones, so a lane adds at most 62 16-bit values below
 // its click counter at bit 22.  No load is conditional: a lane without a bid or a won auction
-// reads the record's first bytes instead and ignores them.
+// reads whatever follows (at most 544 bytes past the record's end: the launch pads the rings for it) and
+// ignores it.
 __device__ __forceinline__ bool pk_walk_fast(uint32_t rec, int n_comp, int n_click, int n_conv, int n_rev,
                                              int bid_cents, double ctr, double cvr, int lane, unsigned lt, PkResult &r)
 {
@@ -1805,7 +1806,7 @@ __device__ __forceinline__ bool pk_walk_fast(uint32_t rec, int n_comp, int n_cli
     int g0 = 0;
     for (; n4 - g0 > 16; g0 += 32) {
         const bool in = left > 0;
-        const int4 c = lds_v4(in ? cp : rec);
+        const int4 c = lds_v4(cp);  // (a lane past the last bid reads at most 512 bytes past the record: padded for)
         const bool w0 = in && bid_cents > c.x, w1 = in && bid_cents > c.y;
         const bool w2 = in && bid_cents > c.z, w3 = in && bid_cents > c.w;
         const unsigned m0 = __ballot_sync(FULL, w0), m1 = __ballot_sync(FULL, w1);
@@ -1813,14 +1814,12 @@ __device__ __forceinline__ bool pk_walk_fast(uint32_t rec, int n_comp, int n_cli
         // auction order inside the trip is lane-major (j = 4 g + q): rank = wins of lower lanes + own earlier wins;
         // the click uniforms of a lane's wins are consecutive
         // (a tape shorter than the walk -- never on a consistent recording -- is noticed after the loops: the
-        // index is clamped so that the loads stay within 32 bytes of the record, which the launch pads for)
+        // index is clamped so that the loads stay within 32 bytes of the record)
         const uint32_t u0 = click + 8u * (uint32_t)min(nI + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt), n_click);
         const uint32_t u1 = u0 + (w0 ? 8u : 0u), u2 = u1 + (w1 ? 8u : 0u), u3 = u2 + (w2 ? 8u : 0u);
         nI += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-        const bool k0 = w0 & (lds_f64(w0 ? u0 : rec) <= ctr);
-        const bool k1 = w1 & (lds_f64(w1 ? u1 : rec) <= ctr);
-        const bool k2 = w2 & (lds_f64(w2 ? u2 : rec) <= ctr);
-        const bool k3 = w3 & (lds_f64(w3 ? u3 : rec) <= ctr);
+        const bool k0 = w0 & (lds_f64(u0) <= ctr), k1 = w1 & (lds_f64(u1) <= ctr);
+        const bool k2 = w2 & (lds_f64(u2) <= ctr), k3 = w3 & (lds_f64(u3) <= ctr);
         acc += (k0 ? (unsigned)c.x + kOne : 0u) + (k1 ? (unsigned)c.y + kOne : 0u);
         acc += (k2 ? (unsigned)c.z + kOne : 0u) + (k3 ? (unsigned)c.w + kOne : 0u);
         cp += 512u;
@@ -1831,12 +1830,12 @@ __device__ __forceinline__ bool pk_walk_fast(uint32_t rec, int n_comp, int n_cli
     for (int j0 = 4 * g0; j0 < n_comp; j0 += 32) {
         const int j = j0 + lane;
         const bool in = j < n_comp;
-        const int c1 = lds_s32(in ? rec + 32u + 4u * (uint32_t)j : rec);
+        const int c1 = lds_s32(rec + 32u + 4u * (uint32_t)j);
         const bool w = in && bid_cents > c1;
         const unsigned m = __ballot_sync(FULL, w);
         const int rk = min(nI + __popc(m & lt), n_click);
         nI += __popc(m);
-        const bool k = w & (lds_f64(w ? click + 8u * (uint32_t)rk : rec) <= ctr);
+        const bool k = w & (lds_f64(click + 8u * (uint32_t)rk) <= ctr);
         acc += k ? (unsigned)c1 + kOne : 0u;
     }
     if (nI > n_click) return false;  // click uniforms ran out: pk_walk_generic decides
@@ -3086,7 +3085,7 @@ static cudaError_t launch_packed(const adc_step_args &a, const adc_tape &tp, cud
 {
     auto kern = adc_replay_packed_kernel<W, RING, DEPTH, MINB>;
     constexpr int block = W * 32;
-    constexpr size_t dyn = (size_t)W * RING + 64;  // (+64: pk_walk_fast's clamped loads may pass a record's end by 32 bytes)
+    constexpr size_t dyn = (size_t)W * RING + 640;  // (pk_walk_fast's unconditional loads may pass a record's end by 512 + 32 bytes)
     static bool configured = false;
     if (!configured) {
         const cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
