@@ -531,9 +531,9 @@ def run_gpu(args):
         return units_total / float(te.item())
 
     e2e_value = timed_host(lambda: env.step_host(bids_host, mode="auto"))
-    auto_mode = "pipelined" if world > 1 else "records"
+    auto_mode = "pipelined" if world > 2 else "records"
     h2d = E_ENVS * K_KW * 4
-    d2h = (E_ENVS * int(_capi.load().adc_host_row_bytes(K_KW, _capi.F32)) if world > 1 else env.host_record_bytes_per_step()[1])
+    d2h = (E_ENVS * int(_capi.load().adc_host_row_bytes(K_KW, _capi.F32)) if world > 2 else env.host_record_bytes_per_step()[1])
     e2e_rows = timed_host(lambda: env.step_host_rows(bids_host))
     e2e_records = timed_host(lambda: env.step_host_records(bids_host))
     e2e_pipelined = timed_host(lambda: env.step_host_pipelined(bids_host, n_chunks=args.host_chunks))
