@@ -695,7 +695,7 @@ class VectorBiddingSimulation:
             "step_host_records takes a pinned, contiguous float [E, K] tensor"
         if getattr(self, "_rec_host", None) is None:
             rec = torch.zeros(E, K, 16, dtype=torch.uint8).pin_memory()
-            env = torch.zeros(E, 24, dtype=torch.uint8).pin_memory()  # reward f64 | cum_profit f64 | days i32 | term u8 | trunc u8 | pad
+            # env scalars, one pinned array each: reward f64 | cum_profit f64 | days i32 | terminated u8 | truncated u8
             envT = torch.zeros(24 * E, dtype=torch.uint8).pin_memory()
             u16, f32 = rec.view(torch.uint16), rec.view(torch.float32)
             scal = dict(reward=envT[0:8 * E].view(torch.float64), cumulative_profit=envT[8 * E:16 * E].view(torch.float64),
@@ -709,7 +709,6 @@ class VectorBiddingSimulation:
                 count_overflow=u16[:, :, 3], cost=f32[:, :, 2], revenue=f32[:, :, 3],
                 reward=scal["reward"], cumulative_profit=scal["cumulative_profit"].view(-1, 1),
                 days_passed=scal["days_passed"].view(-1, 1), terminated=scal["terminated"], truncated=scal["truncated"])
-            del env
         budget = None
         if budget_host is not None:
             budget = self._stage(budget_host.to(bids_host.dtype), self._budget_dev, (E,))
