@@ -799,6 +799,12 @@ struct __align__(16) FlatCost {  // 48 B per unit in shared memory: the price sa
     int B;
 };
 
+struct __align__(16) FlatGroups {  // 32 B per unit in shared memory: what a (unit, group) item needs of its unit
+    uint32_t t1, t2, t3, full;
+    uint32_t n0, n1, x3;
+    int V;
+};
+
 struct __align__(16) FlatRev {
     float mean, sd;
     int S;
@@ -999,18 +1005,54 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
         // shared auctions: a batch in which every unit is outbid (7 of the 8 bidder rows of an 8-bidder world)
         // has no auction to evaluate and goes straight to its outputs
         if (!kFloor || __any_sync(FULL, V > 0)) {
-        // ---------------- outcomes: groups of 32 auctions, lane <-> unit ----------------
+        // ---------------- outcomes: groups of 32 auctions ----------------
         {
             const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), genv, k0, k1);
             const int G = (V + 31) >> 5;
             const int Gmax = __reduce_max_sync(FULL, G);
-            for (int g = 0; g < Gmax; ++g) {
-                const int rem = V - 32 * g;  // auctions of this group that exist
-                const uint32_t active = rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? (1u << rem) - 1u : 0u);
-                const Masks3 m = group_masks(active, (uint32_t)g, u2.t1, u2.t2, u2.t3, u2.full, pa.n0, pa.n1, pa.x3, k0, k1);
-                I += __popc(m.win);
-                B += __popc(m.click);
-                S += __popc(m.conv);
+            const int Gsum = (int)__reduce_add_sync(FULL, (unsigned)G);
+            if (((Gsum + 31) >> 5) + 1 < Gmax) {
+                // Uneven days (dense keywords: volumes 128 +- 60 in one batch): lane <-> unit would run the
+                // longest day's group count for everybody.  When that costs at least two trips more, the
+                // batch's (unit, group) pairs are spread over the lanes instead, like the price draws below:
+                // same Philox calls, same masks.
+                FlatGroups fg;
+                fg.t1 = u2.t1; fg.t2 = u2.t2; fg.t3 = u2.t3; fg.full = u2.full;
+                fg.n0 = pa.n0; fg.n1 = pa.n1; fg.x3 = pa.x3; fg.V = V;
+                // (the units' group parameters live where their revenue parameters will: the revenue phase
+                // writes its own after the prices)
+                static_assert(sizeof(FlatGroups) == sizeof(FlatRev), "FlatGroups overlays FlatRev");
+                FlatGroups *const grps = reinterpret_cast<FlatGroups *>(revs);
+                grps[lane] = fg;
+                s_sum[warp][lane][0] = 0u; s_sum[warp][lane][1] = 0u;
+                const FlatMap gm = flat_map_begin(G, lane, start, nzl);
+                for (int base = 0; base < gm.total; base += 32) {
+                    const int b = flat_map_unit(gm, base, lane, nzl);
+                    const int i = base + lane;
+                    if (i < gm.total) {
+                        const FlatGroups f = grps[b];
+                        const int g = i - start[b];
+                        const int rem = f.V - 32 * g;
+                        const uint32_t active = rem >= 32 ? 0xFFFFFFFFu : (1u << rem) - 1u;  // rem >= 1
+                        const Masks3 m = group_masks(active, (uint32_t)g, f.t1, f.t2, f.t3, f.full, f.n0, f.n1, f.x3, k0, k1);
+                        atomicAdd(&s_sum[warp][b][0], (unsigned)__popc(m.win));
+                        atomicAdd(&s_sum[warp][b][1], (unsigned)__popc(m.click) | ((unsigned)__popc(m.conv) << 16));  // <= 65535 each
+                    }
+                }
+                __syncwarp();
+                I = (int)s_sum[warp][lane][0];
+                B = (int)(s_sum[warp][lane][1] & 0xFFFFu);
+                S = (int)(s_sum[warp][lane][1] >> 16);
+                __syncwarp();
+            } else {
+                for (int g = 0; g < Gmax; ++g) {  // lane <-> unit
+                    const int rem = V - 32 * g;  // auctions of this group that exist
+                    const uint32_t active = rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? (1u << rem) - 1u : 0u);
+                    const Masks3 m = group_masks(active, (uint32_t)g, u2.t1, u2.t2, u2.t3, u2.full, pa.n0, pa.n1, pa.x3, k0, k1);
+                    I += __popc(m.win);
+                    B += __popc(m.click);
+                    S += __popc(m.conv);
+                }
             }
         }
         // ---------------- prices: one per click, 4 per Philox call, flattened over the batch ----------------
