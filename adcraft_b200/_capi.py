@@ -98,6 +98,17 @@ class IdealArgs(C.Structure):
     ]
 
 
+class MetricsArgs(C.Structure):
+    _fields_ = [
+        ("E", C.c_int32), ("K", C.c_int32), ("steps", C.c_int32), ("device", C.c_int32),
+        ("episode_profit_cents", C.c_void_p), ("ideal", C.c_void_p), ("ideal_env_stride", C.c_int64),
+        ("sums", C.c_void_p), ("akncp", C.c_void_p), ("ncp", C.c_void_p), ("zero", C.c_int32), ("pad_", C.c_int32),
+    ]
+
+
+METRICS_MAX_K = 2048
+
+
 class Tape(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "volume", "comp_off", "comp_cents", "comp_f64", "click_off", "u_click", "conv_off", "u_conv",
@@ -136,6 +147,9 @@ def load() -> C.CDLL:
     lib.adc_ideal_profit.restype = C.c_int
     lib.adc_ideal_profit.argtypes = [C.POINTER(IdealArgs), C.c_void_p]
     lib.adc_sizeof_ideal_args.restype = C.c_int
+    lib.adc_episode_metrics.restype = C.c_int
+    lib.adc_episode_metrics.argtypes = [C.POINTER(MetricsArgs), C.c_void_p]
+    lib.adc_sizeof_metrics_args.restype = C.c_int
     lib.adc_host_row_bytes.restype = C.c_int64
     lib.adc_host_row_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.adc_step_host.restype = C.c_int
@@ -156,6 +170,8 @@ def load() -> C.CDLL:
         raise AdcError("adcraft_b200: adc_host_chunk layout mismatch; rebuild")
     if lib.adc_sizeof_ideal_args() != C.sizeof(IdealArgs):
         raise AdcError("adcraft_b200: adc_ideal_args layout mismatch; rebuild")
+    if lib.adc_sizeof_metrics_args() != C.sizeof(MetricsArgs):
+        raise AdcError("adcraft_b200: adc_metrics_args layout mismatch; rebuild")
     _lib = lib
     return lib
 
@@ -171,4 +187,5 @@ EXPORTED_SYMBOLS = (
     "adc_sizeof_tape", "adc_step_philox", "adc_step_replay", "adc_reset_envs", "adc_launch_count",
     "adc_ideal_profit", "adc_sizeof_ideal_args", "adc_serial_slab_bytes",
     "adc_host_row_bytes", "adc_step_host", "adc_sizeof_host_chunk",
+    "adc_episode_metrics", "adc_sizeof_metrics_args",
 )

@@ -245,6 +245,29 @@ int adc_ideal_profit(const adc_ideal_args *a, void *stream)
     return ADC_OK;
 }
 
+int adc_sizeof_metrics_args(void) { return (int)sizeof(adc_metrics_args); }
+
+int adc_episode_metrics(const adc_metrics_args *a, void *stream)
+{
+    if (a == nullptr) return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: args is NULL");
+    ADC_REQUIRE(a->E > 0 && a->K > 0 && a->K <= ADC_METRICS_MAX_K, "E > 0 and 0 < K <= ADC_METRICS_MAX_K");
+    ADC_REQUIRE(a->steps > 0, "steps must be positive");
+    ADC_REQUIRE(a->episode_profit_cents && a->ideal && a->sums, "episode_profit_cents, ideal and sums are required");
+    ADC_REQUIRE(a->ideal_env_stride == 0 || a->ideal_env_stride == a->K, "ideal_env_stride must be 0 or K");
+    int rc = check_device();
+    if (rc) return rc;
+    if (a->device >= 0) {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != a->device)
+            return fail(ADC_ERR_INVALID, "adcraft_b200: invalid argument: the buffers live on device %d but the "
+                        "calling thread's current device is %d", a->device, cur);
+    }
+    const cudaError_t e = adc::launch_episode_metrics(*a, static_cast<cudaStream_t>(stream), &g_launches);
+    if (e != cudaSuccess) return fail(ADC_ERR_CUDA, "adcraft_b200: launch failed: %s", cudaGetErrorString(e));
+    return ADC_OK;
+}
+
 int64_t adc_launch_count(int reset)
 {
     const int64_t n = g_launches;

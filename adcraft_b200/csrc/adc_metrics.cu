@@ -173,4 +173,105 @@ cudaError_t launch_ideal_profit(const adc_ideal_args &a, cudaStream_t s, int64_t
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// AKNCP / NCP of a window from the episode accumulators (adc_episode_metrics): one warp per env.
+// The K ratios go to shared memory; the two middle order statistics come from stable ranks
+// (rank_i = #{j : r_j < r_i or (r_j == r_i and j < i)}: K^2 / 32 comparisons per warp, nothing is
+// sorted or moved).  A CTA adds its envs' sums with six atomics.
+// ------------------------------------------------------------------------------------------
+constexpr int kMetWarps = 4;
+
+__global__ void __launch_bounds__(kMetWarps * 32)
+adc_episode_metrics_kernel(const __grid_constant__ adc_metrics_args a)
+{
+    extern __shared__ __align__(16) double m_ratio[];  // [kMetWarps][K]
+    __shared__ double s_part[kMetWarps][6];
+    const int K = a.K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *ratio = m_ratio + (size_t)warp * K;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const double steps = (double)a.steps;
+    double t_prof = 0.0, t_ideal = 0.0, t_ak = 0.0, t_ak2 = 0.0, t_ncp = 0.0, t_n = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * kMetWarps + warp; e < a.E; e += (int64_t)gridDim.x * kMetWarps) {
+        int64_t *acc = a.episode_profit_cents + e * K;
+        const double *idl = a.ideal + e * a.ideal_env_stride;
+        double prof_s = 0.0, ideal_s = 0.0;
+        for (int k = lane; k < K; k += 32) {
+            const double prof = __ddiv_rn((double)acc[k], 100.0);
+            const double id = idl[k];
+            const double den = id <= 0.0 ? 1.0 : id;
+            ratio[k] = __ddiv_rn(__ddiv_rn(prof, steps), den);
+            prof_s += prof;
+            ideal_s += id;
+            if (a.zero) acc[k] = 0;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            prof_s += __shfl_xor_sync(FULL, prof_s, off);
+            ideal_s += __shfl_xor_sync(FULL, ideal_s, off);
+        }
+        __syncwarp();
+        // the two middle order statistics by stable rank
+        const int r_lo = (K + 1) / 2 - 1, r_hi = K / 2;
+        double lo = 0.0, hi = 0.0;
+        for (int i = lane; i < K; i += 32) {
+            const double x = ratio[i];
+            int rank = 0;
+            for (int j = 0; j < K; ++j) {
+                const double y = ratio[j];
+                rank += (y < x) || (y == x && j < i);
+            }
+            if (rank == r_lo) lo = x;
+            if (rank == r_hi) hi = x;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {  // exactly one lane holds each of them: the others add 0.0
+            lo += __shfl_xor_sync(FULL, lo, off);
+            hi += __shfl_xor_sync(FULL, hi, off);
+        }
+        __syncwarp();
+        const double akncp = 0.5 * (lo + hi);
+        const double isum = ideal_s * steps;
+        const double ncp = __ddiv_rn(prof_s, isum <= 0.0 ? 1.0 : isum);
+        if (lane == 0) {
+            if (a.akncp != nullptr) a.akncp[e] = akncp;
+            if (a.ncp != nullptr) a.ncp[e] = ncp;
+        }
+        t_prof += prof_s; t_ideal += isum; t_ak += akncp; t_ak2 += akncp * akncp; t_ncp += ncp; t_n += 1.0;
+    }
+    if (lane == 0) {
+        s_part[warp][0] = t_prof; s_part[warp][1] = t_ideal; s_part[warp][2] = t_ak;
+        s_part[warp][3] = t_ak2; s_part[warp][4] = t_ncp; s_part[warp][5] = t_n;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kMetWarps; ++w) v += s_part[w][threadIdx.x];
+        if (v != 0.0) atomicAdd(a.sums + threadIdx.x, v);
+    }
+}
+
+cudaError_t launch_episode_metrics(const adc_metrics_args &a, cudaStream_t s, int64_t *launches)
+{
+    auto kern = adc_episode_metrics_kernel;
+    const size_t dyn = (size_t)kMetWarps * (size_t)a.K * sizeof(double);
+    static size_t configured = 0;
+    if (dyn > 48 * 1024 && dyn > configured) {
+        const cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (err != cudaSuccess) return err;
+        configured = dyn;
+    }
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t grid = ((int64_t)a.E + kMetWarps - 1) / kMetWarps;
+    const int64_t cap = (int64_t)(sms > 0 ? sms : 148) * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kMetWarps * 32, dyn, s>>>(a);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 }  // namespace adc

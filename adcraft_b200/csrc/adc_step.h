@@ -15,5 +15,6 @@ int64_t serial_slab_bytes(int32_t K);
 int64_t host_row_bytes(int32_t K, int32_t float_dtype);
 cudaError_t launch_pack_rows(const adc_step_args &a, void *rows_dev, cudaStream_t s, int64_t *launches);
 cudaError_t launch_ideal_profit(const adc_ideal_args &a, cudaStream_t s, int64_t *launches);
+cudaError_t launch_episode_metrics(const adc_metrics_args &a, cudaStream_t s, int64_t *launches);
 
 }  // namespace adc

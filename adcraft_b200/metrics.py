@@ -123,18 +123,37 @@ class MetricAccumulator:
 
 def episode_summary_vector(env, steps: int, ideal: torch.Tensor, reward_sum: Optional[torch.Tensor] = None,
                            episodes: Optional[torch.Tensor] = None, zero: bool = True,
-                           row_chunk: int = 8192) -> torch.Tensor:
+                           row_chunk: int = 8192, use_kernel: bool = True) -> torch.Tensor:
     """The metric vector of ``MetricAccumulator.summary_vector`` from the env's own kernel-side
     accumulators (``episode_profit=True``: ``adc_step_out.episode_profit_cents`` holds the exact sum
     of every step's per-keyword profit): per-env AKNCP = median over keywords of
     (mean profit / mean ideal, ideal <= 0 -> 1) and NCP = sum profit / sum ideal
     (experiment_metrics.py:64-83) over ``steps`` steps with a per-step ideal profit ``ideal``
     ([1, K] or [E, K], stationary over the window).  ``zero``: start the next window."""
+    from . import _capi
     acc = env._out["episode_profit_cents"]
     E, K = acc.shape
     f64 = torch.float64
     ideal = ideal.to(f64)
     out = torch.zeros(8, dtype=f64, device=acc.device)
+    er, ec = env._out.get("episode_reward"), env._out.get("episode_count")
+    if use_kernel and acc.is_cuda and K <= _capi.METRICS_MAX_K and ideal.dim() == 2 and ideal.shape[0] in (1, E):
+        # one launch: a warp per env (adc_episode_metrics); the torch form below is its reference
+        import ctypes as C
+        idl = ideal.contiguous()
+        a = _capi.MetricsArgs()
+        a.E, a.K, a.steps, a.device = E, K, int(steps), acc.device.index
+        a.episode_profit_cents, a.ideal = acc.data_ptr(), idl.data_ptr()
+        a.ideal_env_stride = 0 if idl.shape[0] == 1 else K
+        a.sums, a.akncp, a.ncp, a.zero = out.data_ptr(), None, None, int(zero)
+        with torch.cuda.device(acc.device):
+            _capi.check(_capi.load().adc_episode_metrics(C.byref(a), C.c_void_p(torch.cuda.current_stream(acc.device).cuda_stream)))
+        out[6] = reward_sum if reward_sum is not None else (er.sum() if er is not None else 0.0)
+        out[7] = episodes if episodes is not None else (ec.sum() if ec is not None else 0.0)
+        if zero and er is not None:
+            er.zero_()
+            ec.zero_()
+        return out
     for r0 in range(0, E, row_chunk):
         prof = acc[r0:r0 + row_chunk].to(f64) / 100.0
         idl = ideal if ideal.shape[0] == 1 else ideal[r0:r0 + row_chunk]
@@ -152,7 +171,6 @@ def episode_summary_vector(env, steps: int, ideal: torch.Tensor, reward_sum: Opt
         out[3] += (akncp ** 2).sum()
         out[4] += ncp.sum()
         out[5] += prof.shape[0]
-    er, ec = env._out.get("episode_reward"), env._out.get("episode_count")
     out[6] = reward_sum if reward_sum is not None else (er.sum() if er is not None else 0.0)
     out[7] = episodes if episodes is not None else (ec.sum() if ec is not None else 0.0)
     if zero:

@@ -357,6 +357,30 @@ int adc_sizeof_host_chunk(void);
 /* The ideal-profit estimator above for E x K units. */
 int adc_ideal_profit(const adc_ideal_args *args, void *stream);
 
+/* AKNCP / NCP of a window of steps (experiment_metrics.py:64-83) from the step kernels' per-keyword
+ * episode accumulators: per env  AKNCP = median over its keywords of (mean profit / mean ideal profit,
+ * an ideal <= 0 counts as 1)  and  NCP = sum profit / sum ideal (a sum <= 0 counts as 1); the median is
+ * np.median's (mean of the two middle values for an even K), taken per env, never across ranks.
+ * One warp per env; the six sums a rank contributes to the NCCL all-reduce are ADDED to `sums`:
+ *   sums[0] += sum profit, [1] += sum ideal * steps, [2] += sum AKNCP_e, [3] += sum AKNCP_e^2,
+ *   [4] += sum NCP_e, [5] += E                 (dollars; entries 6 and 7 belong to the caller). */
+#define ADC_METRICS_MAX_K 2048
+typedef struct adc_metrics_args {
+    int32_t E, K;                        /* K <= ADC_METRICS_MAX_K                                        */
+    int32_t steps;                       /* steps accumulated in episode_profit_cents (> 0)              */
+    int32_t device;                      /* like adc_step_args.device                                    */
+    int64_t *episode_profit_cents;       /* [E,K] adc_step_out.episode_profit_cents                      */
+    const double *ideal;                 /* per-step ideal profit, [K] (ideal_env_stride 0) or [E,K] (K) */
+    int64_t ideal_env_stride;
+    double *sums;                        /* [8] device doubles, see above                                */
+    double *akncp;                       /* optional [E] per-env AKNCP                                   */
+    double *ncp;                         /* optional [E] per-env NCP                                     */
+    int32_t zero;                        /* != 0: zero episode_profit_cents after reading (next window)  */
+    int32_t pad_;
+} adc_metrics_args;
+int adc_episode_metrics(const adc_metrics_args *args, void *stream);
+int adc_sizeof_metrics_args(void);
+
 /* Number of kernel launches issued by this library on the calling thread since the last call
  * with reset != 0 (bench.py's gpu_launches). */
 int64_t adc_launch_count(int reset);

@@ -114,3 +114,37 @@ def test_grid_beyond_the_exact_range_is_refused():
     env = _env(cols)
     with pytest.raises(_capi.AdcError, match="grid bid"):
         m.ideal_profit(env, np.array([0.5, 5.2]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,E,per_env", [(100, 300, False), (7, 33, True), (64, 129, False), (1, 5, False), (501, 40, True)])
+def test_episode_metrics_kernel_matches_torch_form(K, E, per_env):
+    """adc_episode_metrics (a warp per env: AKNCP = np.median over the keywords of mean profit / mean
+    ideal, NCP = sum / sum; experiment_metrics.py:64-83) against the eager torch form of the same
+    window -- odd and even K (np.median averages the two middle values), ties, ideal profits <= 0,
+    shared and per-env ideal tables; the accumulators are zeroed for the next window."""
+    from adcraft_b200 import metrics as M
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    from conftest import make_implicit_table
+    rng = np.random.default_rng(K + E)
+    table = make_implicit_table(rng, K, 40)
+    mk = lambda: VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=1e6, device="cuda", seed=9,
+                                         episode_profit=True)
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    steps = 4
+    bids = torch.from_numpy(np.round(rng.uniform(0.2, 1.5, (E, K)), 2)).cuda()
+    for _ in range(steps):
+        a.step({"keyword_bids": bids}); b.step({"keyword_bids": bids})
+    ideal = torch.from_numpy(rng.uniform(-0.5, 3.0, (E if per_env else 1, K))).cuda()
+    ideal[:, ::5] = 0.0                                    # ideal <= 0 counts as 1
+    if K >= 4:                                             # ties around the middle
+        for env in (a, b):
+            env._out["episode_profit_cents"][:, 1] = env._out["episode_profit_cents"][:, 2]
+        ideal[:, 1] = ideal[:, 2]
+    assert int(a._out["episode_profit_cents"].abs().sum()) > 0
+    va = M.episode_summary_vector(a, steps, ideal, use_kernel=True)
+    vb = M.episode_summary_vector(b, steps, ideal, use_kernel=False)
+    np.testing.assert_allclose(va.cpu().numpy(), vb.cpu().numpy(), rtol=1e-11, atol=1e-9)
+    assert float(va[5]) == E
+    assert int(a._out["episode_profit_cents"].abs().sum()) == 0 and int(b._out["episode_profit_cents"].abs().sum()) == 0
