@@ -78,7 +78,7 @@ class StepArgs(C.Structure):
         ("kw", Keywords), ("env", EnvState), ("drift", Drift),
         ("bids", C.c_void_p), ("bids_dtype", C.c_int32), ("f32_ties", C.c_int32),
         ("budget_in", C.c_void_p),
-        ("env_group", C.c_int32), ("floor_cents", C.c_void_p),
+        ("env_group", C.c_int32), ("spread_outcomes", C.c_int32), ("floor_cents", C.c_void_p),
         ("out", StepOut), ("scratch", Scratch), ("detail", Detail),
     ]
 

@@ -909,7 +909,7 @@ __device__ __forceinline__ int flat_map_unit(const FlatMap &m, int base, int lan
     return nzl[min(before + __popc(marks & (0xFFFFFFFFu >> (31 - lane))), 31)];
 }
 
-template <bool kFloor>
+template <bool kFloor, bool kSpread>
 __global__ void __launch_bounds__(kFlatWarps * 32)
 adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
 {
@@ -1010,8 +1010,8 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
             const PhiloxPre pa = philox_pre(a.step, stream_word(ST_AUCTION, 0u, (uint32_t)k), genv, k0, k1);
             const int G = (V + 31) >> 5;
             const int Gmax = __reduce_max_sync(FULL, G);
-            const int Gsum = (int)__reduce_add_sync(FULL, (unsigned)G);
-            if (((Gsum + 31) >> 5) + 1 < Gmax) {
+            const int Gsum = kSpread ? (int)__reduce_add_sync(FULL, (unsigned)G) : 0;
+            if (kSpread && ((Gsum + 31) >> 5) + 1 < Gmax) {
                 // Uneven days (dense keywords: volumes 128 +- 60 in one batch): lane <-> unit would run the
                 // longest day's group count for everybody.  When that costs at least two trips more, the
                 // batch's (unit, group) pairs are spread over the lanes instead, like the price draws below:
@@ -3175,7 +3175,11 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         int per_sm = 0;
         constexpr int kBU = 32;  // units per big batch
         const bool fl = a.floor_cents != nullptr || a.env_group > 1;
-        void (*kern)(adc_step_args) = fl ? adc_flat2_implicit_kernel<true> : adc_flat2_implicit_kernel<false>;
+        // (the variant that may spread a batch's (unit, group) pairs over the lanes is 2.4 % slower on sparse
+        // keyword sets, which never use it: the caller says which one it wants, adc_step_args.spread_outcomes)
+        const bool sp = a.spread_outcomes != 0;
+        void (*kern)(adc_step_args) = fl ? (sp ? adc_flat2_implicit_kernel<true, true> : adc_flat2_implicit_kernel<true, false>)
+                                         : (sp ? adc_flat2_implicit_kernel<false, true> : adc_flat2_implicit_kernel<false, false>);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
         if (per_sm < 1) per_sm = 1;
         int64_t grid = (int64_t)num_sms() * per_sm;

@@ -87,6 +87,7 @@ class VectorBiddingSimulation:
         detail_cap: int = 0,
         env_group: int = 0,
         dynamic_work: bool = True,
+        spread_outcomes: Optional[bool] = None,
         f32_ties: bool = False,
         episode_profit: bool = False,
         flat_obs: bool = False,
@@ -142,6 +143,8 @@ class VectorBiddingSimulation:
         # False: no adc_scratch.work_counter, the hot kernel deals its batches statically (A/B and
         # tests; results are identical either way)
         self.dynamic_work = bool(dynamic_work)
+        # adc_step_args.spread_outcomes: None = decided from the keyword table (dense, uneven days), True / False for A/B
+        self.spread_outcomes = spread_outcomes
         assert self.env_group <= 1 or self.num_envs % self.env_group == 0
         self.shared_keywords = bool(shared_keywords)
         self.obs_dtype = obs_dtype
@@ -219,6 +222,7 @@ class VectorBiddingSimulation:
         self._host_ptrs = None
         self._args = _capi.StepArgs()
         self._args_sig = None
+        self._spread_hint = None
         self._obs_cache = None
         self._result_cache = None
         self._host_view_cache = None
@@ -446,13 +450,28 @@ class VectorBiddingSimulation:
         a.budget_alias = int(self.budget_alias)
         a.force_serial = int(force_serial)
         a.env_group = self.env_group
+        a.spread_outcomes = self._spread_outcomes()
         a.floor_cents = None
         a.bids = bids.data_ptr()
         a.bids_dtype = _capi.F64 if bids.dtype == torch.float64 else _capi.F32
         a.budget_in = _ptr(budget)
         return a
 
+    def _spread_outcomes(self) -> int:
+        """adc_step_args.spread_outcomes from the keyword table: worth it for dense, uneven days (a mean volume
+        of at least three 32-auction groups and a spread of at least half a group), see the header."""
+        if self.spread_outcomes is not None:
+            return int(bool(self.spread_outcomes))
+        if self._spread_hint is None:
+            kw = getattr(self, "_kw_dev", None)
+            if self.kind != kwmod.IMPLICIT or not kw:
+                self._spread_hint = 0
+            else:
+                self._spread_hint = int(float(kw["vol_mean"].mean()) >= 96.0 and float(kw["vol_std"].max()) >= 16.0)
+        return self._spread_hint
+
     def _fill_static_args(self) -> None:
+        self._spread_hint = None  # (the keyword table may be another one)
         a, o, s, st = self._args, self._out, self._scratch, self._state
         E, K = self.num_envs, self.num_keywords
         a.E, a.env_base, a.seed = E, self.env_base, self.seed & 0xFFFFFFFFFFFFFFFF

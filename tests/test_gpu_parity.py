@@ -319,3 +319,24 @@ def test_philox_multi_bidder_matches_oracle(orc, budget):
         ref = ob.step(bids, n_threads=4)
         _compare(obs, reward, term, trunc, ref, env, RTOL64)
     assert int(obs["impressions"].sum()) > 0  # (negative clearing prices are in the rec_multi_* goldens)
+
+
+@pytest.mark.parametrize("vol", [128, 40])
+def test_spread_outcomes_changes_nothing(vol):
+    """adc_step_args.spread_outcomes picks the hot kernel's variant that may spread a batch's (unit, group)
+    pairs over the lanes: same Philox calls, same masks -- the step is bit-identical either way, on dense
+    uneven days (where batches do spread) and on short ones (where none does)."""
+    rng = np.random.default_rng(vol)
+    K, E = 100, 96
+    table = make_implicit_table(rng, K, vol)
+    a = _env(table, E, seed=5, budget=1e7, spread_outcomes=True)
+    b = _env(table, E, seed=5, budget=1e7, spread_outcomes=False)
+    c = _env(table, E, seed=5, budget=1e7)                     # decided from the table
+    for s in range(3):
+        bids = torch.from_numpy(np.round(rng.uniform(0.2, 1.5, (E, K)), 2)).cuda()
+        oa, ob_, oc = (x.step({"keyword_bids": bids}) for x in (a, b, c))
+        for k in oa[0]:
+            assert torch.equal(oa[0][k], ob_[0][k]) and torch.equal(oa[0][k], oc[0][k]), k
+        assert torch.equal(oa[1], ob_[1]) and torch.equal(oa[1], oc[1])
+    assert c._spread_outcomes() == (1 if vol >= 96 else 0)
+    assert int(oa[0]["impressions"].sum()) > 0
