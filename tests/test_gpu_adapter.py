@@ -270,3 +270,30 @@ def test_device_side_explicit_keyword_sampling_matches_host_distributions():
     env.install_device_keywords(cols, kind=kwm.EXPLICIT)
     obs = env.step({"keyword_bids": torch.full((E, K), 1.5, device="cuda")})[0]
     assert int(obs["impressions"].sum()) > 0 and float(obs["cost"].max()) <= 4.4 * 40
+
+
+@pytest.mark.parametrize("obs_dtype", [torch.float32, torch.float64])
+def test_step_host_auto_routes_by_observation_dtype(obs_dtype):
+    """step_host(mode="auto") with one rank per host: 16-byte unit records for float32 observations, the
+    int32 / float64 zero-copy arrays for float64 ones (a record carries float32 money) -- either way the
+    host observation equals the device step's."""
+    from adcraft_b200 import keywords as kwm
+    from adcraft_b200.vector_env import VectorBiddingSimulation
+    rng = np.random.default_rng(21)
+    E, K = 50, 40
+    table = kwm.sample_implicit_keywords_from_quantiles(K, rng, {"mean_volume": 128, "conversion_rate": 0.8})
+    mk = lambda: VectorBiddingSimulation(E, num_keywords=K, keywords=table, budget=500.0, device="cuda", seed=8,
+                                         obs_dtype=obs_dtype)
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    for step in range(3):
+        bids = torch.from_numpy(np.round(rng.uniform(0.2, 1.5, (E, K)), 2).astype(np.float32)).pin_memory()
+        h = a.step_host(bids, mode="auto")
+        obs, reward, term, trunc, _ = b.step({"keyword_bids": bids.cuda()})
+        assert ("count_overflow" in h) == (obs_dtype == torch.float32)
+        for k in ("impressions", "buyside_clicks", "sellside_conversions"):
+            assert torch.equal(h[k].to(torch.int64), obs[k].cpu().to(torch.int64)), (k, step)
+        for k in ("cost", "revenue"):
+            assert torch.equal(h[k].contiguous(), obs[k].cpu()), (k, step)
+        assert torch.equal(h["reward"].double().view(-1), reward.cpu().double().view(-1))
+    assert int(obs["buyside_clicks"].sum()) > 0
