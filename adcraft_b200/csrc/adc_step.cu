@@ -2478,6 +2478,7 @@ __device__ __noinline__ CommitOut commit_mixed_unit(const PhiloxSrc &src, const 
     return o;
 }
 
+template <bool kPrefix>
 __global__ void __launch_bounds__(kSerWarps * 32, kSerMinBlocks)
 adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_slabs, long long slab_stride, int pool_per_unit)
 {
@@ -2700,7 +2701,7 @@ adc_serial_warp_implicit_kernel(const __grid_constant__ adc_step_args a, int n_s
         // cannot be proven affordable hands over to the general walk below; what the prefix accepted is
         // recounted at the commit from the keywords' slots.  (Alias rule, lane_walk lanes: general walk.)
         int n_prefix = 0;  // rounds [0, n_prefix) were accepted whole
-        if (!env_direct && !a.budget_alias && remaining > 0) {
+        if (kPrefix && !env_direct && !a.budget_alias && remaining > 0) {
             bool go = true;
             // the headers of a round (this lane's keyword of its chunk) and the chunk's pool base
             auto header_of = [&](int rd, uint32_t &cbase) -> uint32_t {
@@ -3239,7 +3240,12 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
     // exact serial walk of the queued envs (reads the count on the device; exits at once if 0)
     if (warp_walk) {
         // one warp per queued env, each with its own slab of the workspace
-        auto kern = adc_serial_warp_implicit_kernel;
+        // The variant with the affordable prefix pays where a day has many rounds the budget covers whole (C2 with
+        // budget 1000: 41 of the 44 visited rounds, -20 %); compiled in where it cannot run (alias rule) or
+        // rarely does (1000 keywords: 12 of 768 rounds) it costs 2-3 %.  Same results either way.
+        const bool prefix = !a.budget_alias && a.kw.K <= 256;
+        void (*kern)(adc_step_args, int, long long, int) =
+            prefix ? adc_serial_warp_implicit_kernel<true> : adc_serial_warp_implicit_kernel<false>;
         int64_t grid = grid_for(kern, kSerWarps * 32, (int64_t)a.E * 32);
         const int64_t by_ws = (n_slabs + kSerWarps - 1) / kSerWarps;
         if (by_ws < grid) grid = by_ws;
