@@ -59,7 +59,7 @@ class Scratch(C.Structure):
         ("env_cost", C.c_void_p), ("env_done", C.c_void_p), ("unit_cost_f64", C.c_void_p),
         ("work_counter", C.c_void_p), ("acc_impressions", C.c_void_p), ("acc_clicks", C.c_void_p), ("acc_conversions", C.c_void_p),
         ("serial_ws", C.c_void_p), ("serial_ws_bytes", C.c_int64),
-        ("serial_hint", C.c_void_p),
+        ("serial_hint", C.c_void_p), ("outbid_mask", C.c_void_p),
     ]
 
 

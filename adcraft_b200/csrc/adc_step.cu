@@ -728,7 +728,7 @@ __device__ __forceinline__ Drift3 unit_drift(const adc_step_args &a, const adc_t
 constexpr int kEnvForceBit = 1 << 30;  // adc_scratch.env_done: some unit of the env asked for the exact walk
 
 __device__ __forceinline__ int unit_done(const adc_step_args &a, int e, long long profit_cents,
-                                         long long cost_cents, bool force = false)
+                                         long long cost_cents, bool force = false, bool fenced = false, int n_units = 1)
 {
     if (profit_cents != 0) atomicAdd(reinterpret_cast<unsigned long long *>(a.scratch.env_profit + e),
                                      (unsigned long long)profit_cents);
@@ -738,9 +738,9 @@ __device__ __forceinline__ int unit_done(const adc_step_args &a, int e, long lon
     // env routed by adc_scratch.serial_hint).  The flag rides in the counter word: this thread's OR
     // precedes its own increment, so the last finisher's increment sees every unit's flag.
     if (force) atomicOr(a.scratch.env_done + e, kEnvForceBit);
-    __threadfence();
-    const int old = atomicAdd(a.scratch.env_done + e, 1);
-    if ((old & (kEnvForceBit - 1)) != a.kw.K - 1) return 0;
+    if (!fenced) __threadfence();  // (`fenced`: the caller's stores are already ordered before this call)
+    const int old = atomicAdd(a.scratch.env_done + e, n_units);  // (n_units > 1: a warp's units of one env, published by one lane)
+    if ((old & (kEnvForceBit - 1)) != a.kw.K - n_units) return 0;
     __threadfence();
     a.scratch.env_done[e] = 0;
     const long long profit =
@@ -964,7 +964,12 @@ adc_flat2_implicit_kernel(const __grid_constant__ adc_step_args a)
         const int cnt = ck.cnt;
         const int64_t u = ck.u0 + lane;
         ck.u0 += cnt;
-        const bool valid = lane < cnt && u < total;
+        bool valid = lane < cnt && u < total;
+        if (kFloor && a.scratch.outbid_mask != nullptr) {
+            // shared auctions: the pre-pass (adc_outbid_rows_kernel) finished the units that cannot win
+            if (valid && a.scratch.outbid_mask[u] != 0) valid = false;
+            if (!__any_sync(FULL, valid)) continue;
+        }
         int e = 0, k = 0, V = 0;
         bool over_cap = false;
         uint32_t genv = 0;
@@ -3096,6 +3101,95 @@ adc_pack_units_kernel(const __grid_constant__ adc_step_args a)
     for (int64_t e = warp; e < a.E; e += n_warps) pack_units_warp(a, (int)e, lane);
 }
 
+// ------------------------------------------------------------------------------------------
+// shared auctions (env_group = A > 1): the rows that cannot win.  One thread per (world, keyword):
+// the unique top bidder among the world's A bids is left to the hot kernel; every other row's unit
+// (and every unit of an env routed by serial_hint) is finished here -- zero outputs, env completion,
+// episode accumulation and drift of the envs that complete -- and marked in adc_scratch.outbid_mask.
+// Compact on purpose: seven of eight rows of an 8-bidder world end here, and as straight-line
+// passages of the hot kernel they made its instruction caches thrash.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adc_outbid_rows_kernel(const __grid_constant__ adc_step_args a)
+{
+    const int K = a.kw.K, A = a.env_group;
+    const int64_t total = (int64_t)(a.E / A) * K;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const int64_t n_thr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < total; base += n_thr) {
+        const int64_t idx = base + lane;
+        const bool in = idx < total;
+        int w = 0, k = 0;
+        int top = (int)0x80000000, n_top = 0;
+        if (in) {
+            w = (int)(idx / K);
+            k = (int)(idx - (int64_t)w * K);
+#pragma unroll 4
+            for (int r = 0; r < A; ++r) {  // (independent loads: four rows' bids in flight)
+                const int c = bid_to_cents(load_f(a.bids, a.bids_dtype, ((int64_t)w * A + r) * K + k));
+                if (c > top) { top = c; n_top = 1; }
+                else if (c == top) ++n_top;
+            }
+        }
+        // the zero outputs of all the rows that end here first, ONE fence, then their completions
+        unsigned mine_m = 0u, hint_m = 0u;  // rows of this (world, keyword) finished here / routed by serial_hint
+        if (in) {
+            for (int r = 0; r < A; ++r) {
+                const int e = w * A + r;
+                const int64_t u = (int64_t)e * K + k;
+                const int c = bid_to_cents(load_f(a.bids, a.bids_dtype, u));
+                const bool hinted = a.scratch.serial_hint != nullptr && a.scratch.serial_hint[e] != 0;
+                const bool mine = hinted || !(c == top && n_top == 1);  // unit_floor: outbid <=> not the unique top bid
+                a.scratch.outbid_mask[u] = mine ? 1 : 0;
+                if (!mine) continue;
+                mine_m |= 1u << r;
+                if (hinted) hint_m |= 1u << r;
+                a.out.impressions[u] = 0;
+                a.out.clicks[u] = 0;
+                a.out.conversions[u] = 0;
+                a.out.cost_cents[u] = 0;
+                a.out.revenue_cents[u] = 0;
+                store_f(a.out.cost, a.out.float_dtype, u, 0.0);
+                store_f(a.out.revenue, a.out.float_dtype, u, 0.0);
+                store_flat_unit(a, e, k, 0, 0, 0, 0.0, 0.0);
+                if (a.out.rows != nullptr) pack_row_unit(a, e, k, 0, 0, 0, 0.0, 0.0);
+                if (a.out.unit_records != nullptr) store_unit_record(a, u, 0, 0, 0, 0.0, 0.0);
+            }
+        }
+        __threadfence();
+        for (int r = 0; r < A; ++r) {  // (warp-uniform: the env tails below are warp-cooperative)
+            int safe = 0;
+            const int e = w * A + r;
+            // the warp's units of one env (consecutive keywords of one world's row) are published by one lane
+            const bool mine = in && ((mine_m >> r) & 1u);
+            const unsigned peers = __match_any_sync(FULL, mine ? w : -1 - lane);
+            if (mine && lane == __ffs(peers) - 1) {
+                safe = unit_done(a, e, 0, 0, ((hint_m >> r) & 1u) != 0, true, __popc(peers));
+                if (safe && a.out.rows != nullptr) pack_row_tail(a, e);
+            }
+            if (a.drift.mask != nullptr || a.out.episode_profit_cents != nullptr) {
+                unsigned todo = __ballot_sync(FULL, safe != 0);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int ee = __shfl_sync(FULL, e, src);
+                    episode_accumulate(a, ee, lane, 32);
+                    if (a.drift.mask == nullptr) continue;
+                    const uint32_t ge = philox_env(a, ee);
+                    for (int kk = lane; kk < K; kk += 32) {
+                        if (!drift_wanted(a, kk)) continue;
+                        const uint4 wd = philox4x32_10(0u, a.step, stream_word(ST_UNIT, 0u, (uint32_t)kk), ge, k0, k1);
+                        drift_apply(a, ee, kk, drift_from_words(a, wd));
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void adc_reset_envs_kernel(int32_t E, const uint8_t *mask, double *cum_profit, int32_t *day)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -3176,6 +3270,19 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         int per_sm = 0;
         constexpr int kBU = 32;  // units per big batch
         const bool fl = a.floor_cents != nullptr || a.env_group > 1;
+        adc_step_args b = a;
+        if (!warp_walk) b.scratch.serial_hint = nullptr;  // (only the warp-cooperative walk keeps the marks up to date)
+        if (a.env_group > 1 && a.env_group <= 32 && a.floor_cents == nullptr && a.scratch.outbid_mask != nullptr) {
+            // shared auctions: the compact pre-pass finishes the rows that cannot win
+            const int64_t pairs = (int64_t)(a.E / a.env_group) * a.kw.K;
+            const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((pairs + 255) / 256, (int64_t)num_sms() * 16));
+            adc_outbid_rows_kernel<<<(unsigned)grid, 256, 0, s>>>(b);
+            ++*launches;
+            err = cudaGetLastError();
+            if (err != cudaSuccess) return err;
+        } else {
+            b.scratch.outbid_mask = nullptr;  // (an explicit floor table: every unit goes through the hot kernel)
+        }
         // (the variant that may spread a batch's (unit, group) pairs over the lanes is 2.4 % slower on sparse
         // keyword sets, which never use it: the caller says which one it wants, adc_step_args.spread_outcomes)
         const bool sp = a.spread_outcomes != 0;
@@ -3187,13 +3294,7 @@ cudaError_t launch_step(const adc_step_args &a, const adc_tape *tape, cudaStream
         const int64_t want = ((total + kBU - 1) / kBU + kFlatWarps - 1) / kFlatWarps;
         if (want < grid) grid = want;
         if (grid < 1) grid = 1;
-        if (warp_walk || a.scratch.serial_hint == nullptr) {
-            kern<<<(unsigned)grid, block, 0, s>>>(a);
-        } else {
-            adc_step_args b = a;
-            b.scratch.serial_hint = nullptr;
-            kern<<<(unsigned)grid, block, 0, s>>>(b);
-        }
+        kern<<<(unsigned)grid, block, 0, s>>>(b);
         ++*launches;
         err = cudaGetLastError();
     } else if (tape == nullptr && a.kw.kind == ADC_EXPLICIT && a.n_lanes != 1) {

@@ -513,6 +513,9 @@ class VectorBiddingSimulation:
         sc.work_counter = s["work_counter"].data_ptr() if self.dynamic_work else None
         sc.serial_ws, sc.serial_ws_bytes = s["serial_ws"].data_ptr(), s["serial_ws"].numel()
         sc.serial_hint = s["serial_hint"].data_ptr() if self.use_serial_hint else None
+        if self.env_group > 1 and self.kind == kwmod.IMPLICIT and "outbid_mask" not in s:
+            s["outbid_mask"] = torch.zeros(E, K, dtype=torch.uint8, device=self.device)  # shared auctions: units finished by the pre-pass
+        sc.outbid_mask = _ptr(s.get("outbid_mask"))
         out.episode_profit_cents = _ptr(o.get("episode_profit_cents"))
         out.episode_reward = _ptr(o.get("episode_reward"))
         out.episode_count = _ptr(o.get("episode_count"))
@@ -638,6 +641,7 @@ class VectorBiddingSimulation:
             for n, sz in (("serial_list", 4), ("env_profit", 8), ("env_cost", 8), ("env_done", 4), ("serial_hint", 1)):
                 setattr(sc, n, off(getattr(bs, n), e0 * sz))
             sc.unit_cost_f64 = off(bs.unit_cost_f64, e0 * K * 8)
+            sc.outbid_mask = off(bs.outbid_mask, e0 * K)
             sc.serial_count = counters[i, 0].data_ptr()
             sc.work_counter = counters[i, 1].data_ptr() if self.dynamic_work else None
             sc.acc_impressions = sc.acc_clicks = sc.acc_conversions = None

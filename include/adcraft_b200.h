@@ -185,6 +185,12 @@ typedef struct adc_scratch {
      * kernels compute the same function, so results do not depend on the marks -- only on how often a
      * budget-bound env is evaluated twice. */
     uint8_t *serial_hint;
+    /* Optional [E,K] DEVICE bytes, used with env_group > 1 (shared auctions, free-running, no floor_cents
+     * table): a compact pre-pass finds every (world, keyword)'s unique top bidder, finishes the units of
+     * all the others (zero outputs, env completion) and marks them here; the hot kernel skips marked
+     * units.  Without it every unit goes through the hot kernel, whose instruction caches thrash when
+     * seven of eight batches only run its straight-line setup and output code (C4: 4.6 ms). */
+    uint8_t *outbid_mask;
 } adc_scratch;
 
 /* Optional per-click detail (the ragged lists of BiddingOutcomes, bidding_simulation.py:10-38, that
